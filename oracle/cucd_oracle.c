@@ -1,0 +1,408 @@
+/* cucd_oracle.c - plain-C restatement of the reference's CU-decision cost arithmetic.
+ *
+ * TEST INFRASTRUCTURE (see cucd_oracle.h): the checker for the CUDA path, never the product.
+ * Parity status: PINNED against reference-encoder KAT dumps (tests/golden/) and oracle/_ref.
+ * All citations are file:line in /root/reference (Jiraiya812/Fast-CU-Decision-HEVC).
+ * Scalar, single-threaded, written for clarity rather than speed.
+ */
+#include "cucd_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+static int iabs(int v) { return v < 0 ? -v : v; }
+static int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* ------------------------------------------------------------------------------------------
+ * Neighbour availability (frame / replay mode).
+ * The reference asks TComDataCU (TComPattern.cpp:550-727 -> getPUAbove/Left/AboveRight/BelowLeft)
+ * which, for one slice, one tile and constrained_intra_pred off, is the HEVC 6.4.1 rule: a
+ * neighbouring 4x4 unit is available iff it is inside the picture and precedes the current block
+ * in decoding order (CTU raster order, z-scan inside the CTU).
+ * ------------------------------------------------------------------------------------------ */
+static unsigned zscan4(unsigned ux, unsigned uy) {
+  unsigned r = 0; int b;
+  for (b = 0; b < 4; b++) r |= ((ux >> b) & 1u) << (2 * b) | ((uy >> b) & 1u) << (2 * b + 1);
+  return r;
+}
+
+int oracle_unit_available(int xc, int yc, int xn, int yn, int W, int H) {
+  int wc, ctuC, ctuN;
+  if (xn < 0 || yn < 0 || xn >= W || yn >= H) return 0;
+  wc = (W + 63) >> 6;
+  ctuC = (yc >> 6) * wc + (xc >> 6);
+  ctuN = (yn >> 6) * wc + (xn >> 6);
+  if (ctuN != ctuC) return ctuN < ctuC;
+  return zscan4((unsigned)(xn & 63) >> 2, (unsigned)(yn & 63) >> 2) < zscan4((unsigned)(xc & 63) >> 2, (unsigned)(yc & 63) >> 2);
+}
+
+/* flag order of bNeighborFlags, TComPattern.cpp:134-139 */
+void oracle_neighbour_flags(int x0, int y0, int n, int W, int H, uint8_t* flags) {
+  const int half = n / 2; /* units per side = 2N/4 */
+  int u;
+  for (u = 0; u < half; u++) flags[u] = (uint8_t)oracle_unit_available(x0, y0, x0 - 1, y0 + (half - 1 - u) * 4, W, H);
+  flags[half] = (uint8_t)oracle_unit_available(x0, y0, x0 - 1, y0 - 1, W, H);
+  for (u = 0; u < half; u++) flags[half + 1 + u] = (uint8_t)oracle_unit_available(x0, y0, x0 + u * 4, y0 - 1, W, H);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Reference-sample gathering and substitution: fillReferenceSamples, TComPattern.cpp:314-521.
+ * Sample-wise statement of the same process: walk the border from the below-left end to the
+ * above-right end; if nothing is available use 1<<(bd-1); an unavailable first unit takes the
+ * first available sample found walking forward; every other unavailable sample repeats its
+ * predecessor.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_fill_border(int bitDepth, int n, const int16_t* rec, int stride, const uint8_t* flags, int16_t* b) {
+  const int n2 = 2 * n, total = 4 * n + 1, units = n + 1; /* n/2 + 1 + n/2 units of 4 -> but corner is 1 sample */
+  uint8_t av[4 * 64 + 1];
+  int i, any = 0;
+  (void)units;
+  for (i = 0; i < n2; i++) { av[i] = flags[i >> 2]; }
+  av[n2] = flags[n / 2];
+  for (i = 0; i < n2; i++) { av[n2 + 1 + i] = flags[n / 2 + 1 + (i >> 2)]; }
+  for (i = 0; i < total; i++) any |= av[i];
+  if (!any) { for (i = 0; i < total; i++) b[i] = (int16_t)(1 << (bitDepth - 1)); return; }
+  for (i = 0; i < n2; i++) if (av[i]) b[i] = rec[(n2 - 1 - i) * stride - 1];
+  if (av[n2]) b[n2] = rec[-stride - 1];
+  for (i = 0; i < n2; i++) if (av[n2 + 1 + i]) b[n2 + 1 + i] = rec[-stride + i];
+  if (!av[0]) {
+    int j = 1;
+    while (!av[j]) j++;
+    for (i = 0; i < j; i++) b[i] = b[j];
+    /* samples 0..j-1 are now defined; mark so the forward pass keeps them */
+    for (i = 0; i < j; i++) av[i] = 1;
+  }
+  for (i = 1; i < total; i++) if (!av[i]) b[i] = b[i - 1];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Reference-sample smoothing: TComPattern.cpp:185-283.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_filter_border(int bitDepth, int n, int strongSmoothing, const int16_t* b, int16_t* f) {
+  const int n2 = 2 * n, last = 4 * n;
+  int i, strong = 0;
+  if (strongSmoothing && n >= 32) {                                   /* :201-214 */
+    const int thr = 1 << (bitDepth - 5);
+    const int bl = b[0], tl = b[n2], tr = b[last];
+    strong = iabs(bl + tl - 2 * b[n]) < thr && iabs(tl + tr - 2 * b[n2 + n]) < thr;
+  }
+  f[0] = b[0]; f[last] = b[last];                                     /* :216, :283 */
+  if (strong) {                                                        /* :224-272 */
+    const int shift = ilog2(n2), bl = b[0], tl = b[n2], tr = b[last];
+    for (i = 1; i < n2; i++) f[i] = (int16_t)(((n2 - i) * bl + i * tl + n) >> shift);
+    f[n2] = b[n2];
+    for (i = 1; i < n2; i++) f[n2 + i] = (int16_t)(((n2 - i) * tl + i * tr + n) >> shift);
+  } else {                                                             /* :237-279; the corner uses its two neighbours across the bend */
+    for (i = 1; i < last; i++) f[i] = (int16_t)((b[i - 1] + 2 * b[i] + b[i + 1] + 2) >> 2);
+  }
+}
+
+/* TComPattern.cpp:523-548 with m_aucIntraFilter TComPrediction.cpp:50-67 (luma row) */
+int oracle_use_filtered(int n, int mode) {
+  static const int thr[5] = {10, 7, 1, 0, 10};
+  int d10, d26, diff;
+  if (mode == 1) return 0;
+  d10 = iabs(mode - 10); d26 = iabs(mode - 26);
+  diff = d10 < d26 ? d10 : d26;
+  return diff > thr[ilog2(n) - 2];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Prediction: predIntraAng TComPrediction.cpp:412-496 for luma, bAbove=bLeft=true
+ * (TComPattern.cpp:141-142), edge filters enabled (:481).
+ * ------------------------------------------------------------------------------------------ */
+static void predict_planar(int n, const int16_t* b, int16_t* pred) {   /* :755-805 */
+  const int n2 = 2 * n, sh = ilog2(n);
+  const int16_t* top = b + n2 + 1;
+  const int tr = top[n], bl = b[n2 - 1 - n];
+  int x, y;
+  for (y = 0; y < n; y++) {
+    const int l = b[n2 - 1 - y];
+    for (x = 0; x < n; x++)
+      pred[y * n + x] = (int16_t)(((n - 1 - x) * l + (x + 1) * tr + (n - 1 - y) * top[x] + (y + 1) * bl + n) >> (sh + 1));
+  }
+}
+
+static void predict_dc(int n, const int16_t* b, int16_t* pred) {        /* :183-222, 266-276, 818-841 */
+  const int n2 = 2 * n;
+  const int16_t* top = b + n2 + 1;
+  int sum = 0, i, x, y, dc;
+  for (i = 0; i < n; i++) sum += top[i] + b[n2 - 1 - i];
+  dc = (sum + n) / (2 * n);
+  for (i = 0; i < n * n; i++) pred[i] = (int16_t)dc;
+  if (n <= 16) {
+    pred[0] = (int16_t)((top[0] + b[n2 - 1] + 2 * dc + 2) >> 2);
+    for (x = 1; x < n; x++) pred[x] = (int16_t)((top[x] + 3 * dc + 2) >> 2);
+    for (y = 1; y < n; y++) pred[y * n] = (int16_t)((b[n2 - 1 - y] + 3 * dc + 2) >> 2);
+  }
+}
+
+static void predict_angular(int bitDepth, int n, int mode, const int16_t* b, int16_t* pred) { /* :278-409 */
+  static const int angTable[9] = {0, 2, 5, 9, 13, 17, 21, 26, 32};
+  static const int invAngTable[9] = {0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+  const int n2 = 2 * n, vertical = mode >= 18;
+  const int am = vertical ? mode - 26 : -(mode - 10);
+  const int angle = (am < 0 ? -1 : 1) * angTable[iabs(am)], invAngle = invAngTable[iabs(am)];
+  int16_t mainBuf[3 * 64 + 2], side[2 * 64 + 1];
+  int16_t* ref = mainBuf + 64;  /* ref[0] = corner, ref[1..] along the main edge, ref[-k] projected side samples */
+  int i, x, y;
+  /* main = above row for vertical modes, left column for horizontal ones (then the block is transposed) */
+  for (i = 0; i <= n2; i++) {
+    const int16_t t = b[n2 + i];        /* corner, top[0..] */
+    const int16_t l = b[n2 - i];        /* corner, left[0..] */
+    ref[i] = vertical ? t : l;
+    side[i] = vertical ? l : t;
+  }
+  if (angle < 0) {                      /* :300-322 */
+    const int lastIdx = (n * angle) >> 5;
+    int k, acc = 128;
+    for (k = -1; k > lastIdx; k--) { acc += invAngle; ref[k] = side[acc >> 8]; }
+  }
+  for (y = 0; y < n; y++) {
+    const int delta = (y + 1) * angle, di = delta >> 5, df = delta & 31;
+    for (x = 0; x < n; x++) {
+      int v;
+      if (angle == 0) v = ref[x + 1];
+      else if (df) v = ((32 - df) * ref[x + di + 1] + df * ref[x + di + 2] + 16) >> 5;
+      else v = ref[x + di + 1];
+      if (angle == 0 && x == 0 && n <= 16)                          /* :356-362 */
+        v = clip3(0, (1 << bitDepth) - 1, v + ((side[y + 1] - side[0]) >> 1));
+      if (vertical) pred[y * n + x] = (int16_t)v; else pred[x * n + y] = (int16_t)v;  /* :397-408 */
+    }
+  }
+}
+
+void oracle_predict(int bitDepth, int n, int mode, const int16_t* unf, const int16_t* fil, int16_t* pred) {
+  const int16_t* b = oracle_use_filtered(n, mode) ? fil : unf;
+  if (mode == 0) predict_planar(n, b, pred);
+  else if (mode == 1) predict_dc(n, b, pred);
+  else predict_angular(bitDepth, n, mode, b, pred);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SATD: xGetHADs TComRdCost.cpp:1537-1604 with xCalcHADs8x8 :1439-1534, 4x4 :1343-1437, 2x2 :1321-1341.
+ * Only sum|coeff| matters, so a generic in-place Walsh-Hadamard is used.
+ * ------------------------------------------------------------------------------------------ */
+static uint32_t had_block(const int16_t* o, int os, const int16_t* c, int cs, int s) {
+  int32_t m[64];
+  int i, j, len, x, y, cnt = s * s;
+  uint32_t sum = 0;
+  for (y = 0; y < s; y++) for (x = 0; x < s; x++) m[y * s + x] = o[y * os + x] - c[y * cs + x];
+  for (y = 0; y < s; y++)                               /* rows */
+    for (len = 1; len < s; len <<= 1)
+      for (i = 0; i < s; i += 2 * len)
+        for (j = i; j < i + len; j++) { int32_t a = m[y * s + j], b2 = m[y * s + j + len]; m[y * s + j] = a + b2; m[y * s + j + len] = a - b2; }
+  for (x = 0; x < s; x++)                               /* columns */
+    for (len = 1; len < s; len <<= 1)
+      for (i = 0; i < s; i += 2 * len)
+        for (j = i; j < i + len; j++) { int32_t a = m[j * s + x], b2 = m[(j + len) * s + x]; m[j * s + x] = a + b2; m[(j + len) * s + x] = a - b2; }
+  for (i = 0; i < cnt; i++) sum += (uint32_t)iabs(m[i]);
+  if (s == 8) return (sum + 2) >> 2;                    /* :1531 */
+  if (s == 4) return (sum + 1) >> 1;                    /* :1434 */
+  return sum;                                           /* 2x2 :1335-1340 */
+}
+
+uint32_t oracle_satd(int bitDepth, const int16_t* org, int os, const int16_t* cur, int cs, int w, int h) {
+  const int s = (w % 8 == 0 && h % 8 == 0) ? 8 : ((w % 4 == 0 && h % 4 == 0) ? 4 : 2);
+  uint32_t sum = 0; int x, y;
+  for (y = 0; y < h; y += s) for (x = 0; x < w; x += s) sum += had_block(org + y * os + x, os, cur + y * cs + x, cs, s);
+  return sum >> (bitDepth - 8);                         /* :1603, DISTORTION_PRECISION_ADJUSTMENT TypeDef.h:343-347 */
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SAD: TComRdCost.cpp:465-962.  The width-specialised variants (4,8,12,16,24,32,48,64 and
+ * multiples of 16 through xGetSAD16N) honour iSubShift; the generic xGetSAD (:465-491), reached
+ * for any other width, ignores it.
+ * ------------------------------------------------------------------------------------------ */
+uint32_t oracle_sad(int bitDepth, const int16_t* org, int os, const int16_t* ref, int rs, int w, int h, int subShift) {
+  const int special = (w == 4 || w == 8 || w == 12 || w == 16 || w == 24 || w == 32 || w == 48 || w == 64);
+  const int sh = special ? subShift : 0, step = 1 << sh;
+  uint32_t sum = 0; int x, y;
+  for (y = 0; y < h; y += step) for (x = 0; x < w; x++) sum += (uint32_t)iabs(org[y * os + x] - ref[y * rs + x]);
+  sum <<= sh;
+  return sum >> (bitDepth - 8);
+}
+
+void oracle_sad_surface(int bitDepth, const int16_t* org, int os, int w, int h, const int16_t* ref0, int rs,
+                        int left, int right, int top, int bottom, int subShift, uint32_t* out) {
+  const int cols = right - left + 1; int x, y;
+  for (y = top; y <= bottom; y++) for (x = left; x <= right; x++)
+    out[(y - top) * cols + (x - left)] = oracle_sad(bitDepth, org, os, ref0 + y * rs + x, rs, w, h, subShift);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Rough mode decision for one PU: TEncSearch.cpp:2327-2361 minus xModeBitsIntra.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_rmd_pu(int bitDepth, int n, int strong, const int16_t* org, int os, const int16_t* border, uint32_t* sad) {
+  int16_t fil[4 * 64 + 1], pred[64 * 64];
+  int mode;
+  oracle_filter_border(bitDepth, n, strong, border, fil);
+  for (mode = 0; mode < 35; mode++) {
+    oracle_predict(bitDepth, n, mode, border, fil, pred);
+    sad[mode] = oracle_satd(bitDepth, org, os, pred, n, n, n);
+  }
+}
+
+void oracle_rmd_frame(int bitDepth, int strong, const int16_t* org, int os, const int16_t* rec, int rs,
+                      int W, int H, int ctuBegin, int ctuEnd, uint32_t* out) {
+  const int wc = (W + 63) >> 6;
+  int ctu;
+  for (ctu = ctuBegin; ctu < ctuEnd; ctu++) {
+    const int cx = (ctu % wc) * 64, cy = (ctu / wc) * 64;
+    uint32_t* o = out + (size_t)(ctu - ctuBegin) * ORACLE_PUS_PER_CTU * 35;
+    int d, pu = 0;
+    for (d = 0; d < 5; d++) {
+      const int n = 64 >> d, cnt = 1 << (2 * d);
+      int z;
+      for (z = 0; z < cnt; z++, pu++) {
+        int px = 0, py = 0, bit, m;
+        uint8_t flags[33]; int16_t border[4 * 64 + 1];
+        for (bit = 0; bit < d; bit++) { px |= ((z >> (2 * bit)) & 1) << bit; py |= ((z >> (2 * bit + 1)) & 1) << bit; }
+        if (cx + (px + 1) * n > W || cy + (py + 1) * n > H) { for (m = 0; m < 35; m++) o[pu * 35 + m] = 0xFFFFFFFFu; continue; }
+        oracle_neighbour_flags(cx + px * n, cy + py * n, n, W, H, flags);
+        oracle_fill_border(bitDepth, n, rec + (size_t)(cy + py * n) * rs + cx + px * n, rs, flags, border);
+        oracle_rmd_pu(bitDepth, n, strong, org + (size_t)(cy + py * n) * os + cx + px * n, os, border, o + pu * 35);
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Outlier feature pass: TEncSlice.cpp:55-77 (4-point butterfly with g_aiT4 = {64,83,36},
+ * TComRom.cpp:464-468), :878-1173.
+ * ------------------------------------------------------------------------------------------ */
+static void dct4_stage(const int32_t* src, int32_t* dst, int shift) {   /* :55-77, line = 4 */
+  const int add = shift > 0 ? 1 << (shift - 1) : 0;
+  int j;
+  for (j = 0; j < 4; j++) {
+    const int32_t e0 = src[4 * j] + src[4 * j + 3], o0 = src[4 * j] - src[4 * j + 3];
+    const int32_t e1 = src[4 * j + 1] + src[4 * j + 2], o1 = src[4 * j + 1] - src[4 * j + 2];
+    dst[j] = (64 * e0 + 64 * e1 + add) >> shift;
+    dst[8 + j] = (64 * e0 - 64 * e1 + add) >> shift;
+    dst[4 + j] = (83 * o0 + 36 * o1 + add) >> shift;
+    dst[12 + j] = (36 * o0 - 83 * o1 + add) >> shift;
+  }
+}
+
+void oracle_dct4x4(int bitDepth, const int16_t* blk, int stride, int32_t* coeff) {
+  const int shift1 = 2 + bitDepth + 6 - 15, shift2 = 2 + 6;            /* :925-926, g_maxTrDynamicRange = 15 */
+  int32_t in[16], tmp[16]; int x, y;
+  for (y = 0; y < 4; y++) for (x = 0; x < 4; x++) in[y * 4 + x] = blk[y * stride + x];
+  dct4_stage(in, tmp, shift1);
+  dct4_stage(tmp, coeff, shift2);
+}
+
+/* TCM: TEncSlice.cpp:202-392.  Works from the histogram of |c| (the reference builds the same
+ * histogram from the coefficient list at :315-333). */
+static double tcm_lambda(double yc, double sumYi, double total) {      /* :202-230 */
+  const double c = sumYi / total;
+  double lam, old; int k;
+  if (c / yc >= 0.95) return -1.0;
+  old = c;
+  lam = c - yc * (1.0 - 1.0 / (1.0 - exp(-yc / old)));
+  for (k = 0; k < 5; k++) { old = lam; lam = c - yc * (1.0 - 1.0 / (1.0 - exp(-yc / old))); }
+  while (fabs(lam - old) > 0.1) { old = lam; lam = c - yc * (1.0 - 1.0 / (1.0 - exp(-yc / old))); }
+  return lam;
+}
+
+double oracle_tcm_yc(const uint32_t* count, int peak, int len) {
+  double *accAmp, *accNum, best, like, ycBest;
+  int k, start, N = len;
+  if (peak == 0 || peak >= 65536) return 0.0;                           /* :304-313 */
+  accAmp = (double*)calloc((size_t)peak + 1, sizeof(double));
+  accNum = (double*)calloc((size_t)peak + 1, sizeof(double));
+  accNum[0] = count[0];
+  for (k = 1; k <= peak; k++) { accAmp[k] = accAmp[k - 1] + (double)k * count[k]; accNum[k] = accNum[k - 1] + count[k]; }
+  /* FindStartPoint :233-256 */
+  for (k = peak; k > 0; k--) { if (count[k] == 0) continue; if (accNum[k] < N * (1.0 - 0.1)) break; }
+  if (peak >= 3 && (int)count[0] > N / 100 && (int)count[1] > N / 100 && (int)count[2] > N / 100 && (int)count[3] > N / 100) { if (k < 3) k = 3; }
+  else if (peak >= 2 && (int)count[0] > N / 100 && (int)count[1] > N / 100 && (int)count[2] > N / 100) { if (k < 2) k = 2; }
+  else { if (k < 1) k = 1; }
+  start = k;
+  best = 0; ycBest = 0;
+  for (k = start; k <= peak; k++) {                                     /* :356-374 */
+    double n1, n2, yc, sumYi, lam, prob;
+    if (k != start && count[k] == 0) continue;
+    n1 = accNum[k]; n2 = N - n1; yc = k; sumYi = accAmp[k];
+    lam = tcm_lambda(yc, sumYi, n1);                                    /* ComputeLikelyhood :258-289 */
+    prob = n1 / (double)N;
+    if (lam > 0)
+      like = n2 * log(1 - prob) + n1 * log(prob) - n2 * log((peak - yc) * 2.0) - n1 * log(1 - exp(-yc / lam)) - n1 * log(2 * lam) - sumYi / lam;
+    else
+      like = 1.e30;                                                     /* -MinLikelyhood :284 */
+    if (k == start || like > best) { best = like; ycBest = k; }
+  }
+  free(accAmp); free(accNum);
+  return best > -1.e30 ? ycBest : 0.0;                                  /* :376-389 */
+}
+
+void oracle_outlier_frame(int bitDepth, const int16_t* org, int os, int W, int H, int16_t* obf, int16_t* outlier, double* yc) {
+  const int bw = W / 4, bh = H / 4, nblk = bw * bh;
+  int32_t* coeff = (int32_t*)malloc((size_t)nblk * 16 * sizeof(int32_t));
+  uint32_t* hist = (uint32_t*)malloc(65536 * sizeof(uint32_t));
+  int bx, by, f, i;
+  for (by = 0; by < bh; by++) for (bx = 0; bx < bw; bx++) oracle_dct4x4(bitDepth, org + (by * 4) * os + bx * 4, os, coeff + (size_t)(by * bw + bx) * 16);
+  yc[0] = 0;
+  for (f = 1; f < 16; f++) {                                            /* :998-1004 on CoeffFrequency = coeff/8.0 truncated (:962) */
+    int peak = 0;
+    memset(hist, 0, 65536 * sizeof(uint32_t));
+    for (i = 0; i < nblk; i++) { int a = iabs(coeff[(size_t)i * 16 + f] / 8); if (a > 65535) a = 65535; if (a > peak) peak = a; hist[a]++; }
+    yc[f] = oracle_tcm_yc(hist, peak, nblk);
+  }
+  for (by = 0; by < bh; by++) for (bx = 0; bx < bw; bx++) {
+    const int32_t* c = coeff + (size_t)(by * bw + bx) * 16;
+    int cnt = 0;
+    for (f = 0; f < 16; f++) {
+      int32_t v = 0;
+      if (f > 0) {                                                      /* DC dropped :987-988 */
+        const double t = yc[f] * 8.0;
+        v = c[f];
+        if ((double)v < t && (double)v > -t) v = 0;                     /* :1010 */
+        if (v != 0) cnt++;                                              /* :1027-1035 */
+      }
+      {                                                                 /* :1106-1112, coefficient domain, Pel = short */
+        int16_t p = (int16_t)v;
+        if (p < 0) p = (int16_t)-p;
+        outlier[(by * 4 + f / 4) * W + bx * 4 + (f & 3)] = (int16_t)(p / 100);
+      }
+    }
+    obf[by * bw + bx] = (int16_t)cnt;
+  }
+  /* samples right of / below the last whole 4x4 block are not written by the reference (:930-931) */
+  for (by = 0; by < H; by++) for (bx = 0; bx < W; bx++) if (bx >= bw * 4 || by >= bh * 4) outlier[by * W + bx] = 0;
+  free(coeff); free(hist);
+}
+
+void oracle_cu_sums(const int16_t* obf, int W, int H, int depth, int32_t* numObf, int32_t* nOutlier) {
+  const int size = 64 >> depth, cells = size / 4, cw = W / size, ch = H / size, bw = W / 4;
+  int cx, cy, x, y;
+  for (cy = 0; cy < ch; cy++) for (cx = 0; cx < cw; cx++) {
+    int32_t num = 0, sum = 0;
+    for (y = 0; y < cells; y++) for (x = 0; x < cells; x++) {          /* TEncCu.cpp:589-598 */
+      const int v = obf[(cy * cells + y) * bw + cx * cells + x];
+      if (v > 0) { num++; sum += v; }
+    }
+    numObf[cy * cw + cx] = num; nOutlier[cy * cw + cx] = sum;
+  }
+}
+
+void oracle_ctu_src_had(const int16_t* org, int os, int W, int H, int32_t* perCtu) {
+  const int wc = (W + 63) >> 6, hc = (H + 63) >> 6;
+  static const int16_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int cx, cy, x, y, i, j;
+  for (cy = 0; cy < hc; cy++) for (cx = 0; cx < wc; cx++) {
+    const int w = W - cx * 64 < 64 ? W - cx * 64 : 64, h = H - cy * 64 < 64 ? H - cy * 64 : 64;
+    int32_t sum = 0;
+    for (y = 0; y + 8 <= h; y += 8) for (x = 0; x + 8 <= w; x += 8) {  /* TEncCu.cpp:1874-1893 */
+      const int16_t* p = org + (cy * 64 + y) * os + cx * 64 + x;
+      int32_t m[64], tot = 0; int len;
+      for (i = 0; i < 8; i++) for (j = 0; j < 8; j++) m[i * 8 + j] = p[i * os + j] - zero[j];
+      for (i = 0; i < 8; i++) for (len = 1; len < 8; len <<= 1) for (j = 0; j < 8; j++) if (!(j & len)) { int32_t a = m[i * 8 + j], b = m[i * 8 + j + len]; m[i * 8 + j] = a + b; m[i * 8 + j + len] = a - b; }
+      for (j = 0; j < 8; j++) for (len = 1; len < 8; len <<= 1) for (i = 0; i < 8; i++) if (!(i & len)) { int32_t a = m[i * 8 + j], b = m[(i + len) * 8 + j]; m[i * 8 + j] = a + b; m[(i + len) * 8 + j] = a - b; }
+      for (i = 1; i < 64; i++) tot += iabs(m[i]);                       /* DC removed :1868 */
+      sum += (tot + 2) >> 2;                                            /* :1869 */
+    }
+    perCtu[cy * wc + cx] = sum;
+  }
+}

@@ -1,0 +1,67 @@
+/* cucd_oracle.h - CPU restatement of the reference's CU-decision cost arithmetic.
+ *
+ * TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+ * load this.  The product (libcucudecide.so) never links or calls it.
+ *
+ * Parity status: PINNED.  Every function below is checked (tests/test_oracle_golden.py) against
+ * known-answer vectors dumped from the reference encoder's own call sites (the .npz files in tests/golden/,
+ * made by tests/golden/gen_golden.py from oracle/_ref/TAppEncoder) and, where oracle/_ref is
+ * present, against the reference's compiled functions on random inputs (tests/test_oracle_vs_ref.py).
+ *
+ * Conventions shared with include/cucudecide.h:
+ *   sample     int16_t (HM `Pel`, TypeDef.h:769), 8..12-bit content
+ *   border     linear array of 4N+1 samples: [0..2N-1] left column bottom(below-left end)->top,
+ *              [2N] top-left corner, [2N+1..4N] above row left->right (above-right end last)
+ *   flags      one byte per 4-sample unit in the same order: N/2 left units, 1 corner, N/2 above
+ *   cost table uint32_t[35], index = HEVC intra mode (0 planar, 1 DC, 2..34 angular)
+ *   PU order   inside a CTU: depth-major (64,32,16,8,4), z-order (Morton) inside a depth -> 341 PUs
+ */
+#ifndef CUCD_ORACLE_H
+#define CUCD_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORACLE_PUS_PER_CTU 341
+#define ORACLE_NUM_MODES 35
+
+/* TComPattern.cpp:550-727 in frame (replay) mode == HEVC 6.4.1 z-scan availability */
+int  oracle_unit_available(int xc, int yc, int xn, int yn, int W, int H);
+void oracle_neighbour_flags(int x0, int y0, int n, int W, int H, uint8_t* flags);
+/* TComPattern.cpp:314-521 */
+void oracle_fill_border(int bitDepth, int n, const int16_t* recOrigin, int recStride, const uint8_t* flags, int16_t* border);
+/* TComPattern.cpp:185-283 */
+void oracle_filter_border(int bitDepth, int n, int strongSmoothing, const int16_t* border, int16_t* filtered);
+/* TComPattern.cpp:523-548, TComPrediction.cpp:50-67 */
+int  oracle_use_filtered(int n, int mode);
+/* TComPrediction.cpp:183-222, 250-410, 412-496, 755-841; pred is n x n, stride n */
+void oracle_predict(int bitDepth, int n, int mode, const int16_t* unfiltered, const int16_t* filtered, int16_t* pred);
+/* TComRdCost.cpp:1321-1604 */
+uint32_t oracle_satd(int bitDepth, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h);
+/* TComRdCost.cpp:465-962 */
+uint32_t oracle_sad(int bitDepth, const int16_t* org, int orgStride, const int16_t* ref, int refStride, int w, int h, int subShift);
+/* TEncSearch.cpp:2327-2361 without the mode-bit term */
+void oracle_rmd_pu(int bitDepth, int n, int strongSmoothing, const int16_t* org, int orgStride, const int16_t* border, uint32_t* sad35);
+/* whole-frame replay enumeration; out[(ctu-ctuBegin)*341*35 + pu*35 + mode], 0xFFFFFFFF for PUs outside the picture */
+void oracle_rmd_frame(int bitDepth, int strongSmoothing, const int16_t* org, int orgStride, const int16_t* rec, int recStride,
+                      int W, int H, int ctuBegin, int ctuEnd, uint32_t* out);
+/* TEncSearch.cpp:3886-3943 raw SAD part; out[(dy-top)*(right-left+1)+(dx-left)] */
+void oracle_sad_surface(int bitDepth, const int16_t* org, int orgStride, int w, int h, const int16_t* refAtZeroMv, int refStride,
+                        int left, int right, int top, int bottom, int subShift, uint32_t* out);
+/* TEncSlice.cpp:55-77 + 944-966: forward 4x4 DCT of one block -> coeff[16] (row = vertical frequency) */
+void oracle_dct4x4(int bitDepth, const int16_t* blk, int stride, int32_t* coeff);
+/* TEncSlice.cpp:291-392 on a histogram of |coeff/8| : count[0..peak], len samples -> Yc */
+double oracle_tcm_yc(const uint32_t* count, int peak, int len);
+/* TEncSlice.cpp:878-1173. obf (W/4)x(H/4) tight, outlier WxH tight, yc[16] (yc[0] unused) */
+void oracle_outlier_frame(int bitDepth, const int16_t* org, int orgStride, int W, int H, int16_t* obf, int16_t* outlier, double* yc);
+/* TEncCu.cpp:589-600 for every CU of depth d (size 64>>d) fully inside the picture, raster order over
+ * the (W/size)x(H/size) grid of whole CUs: numObf = #cells>0, nOutlier = sum of cells */
+void oracle_cu_sums(const int16_t* obf, int W, int H, int depth, int32_t* numObf, int32_t* nOutlier);
+/* TEncCu.cpp:1780-1893: per CTU sum of DC-less 8x8 source Hadamard costs (whole 8x8 blocks inside the picture) */
+void oracle_ctu_src_had(const int16_t* org, int orgStride, int W, int H, int32_t* perCtu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,119 @@
+/* Known-answer-test dump hooks for the patched copy of the reference (test infrastructure).
+ *
+ * oracle/build_ref.sh force-includes this header into the /tmp copy of the reference and inserts
+ * one-line calls at the hot-path seams listed in SURVEY.md §8c.  Every hook is a no-op unless the
+ * matching environment variable names an output file, so the instrumented TAppEncoder produces
+ * the same bitstream as the un-instrumented one.  Records are little-endian int32 words followed
+ * by int16 sample payloads; tests/golden/gen_golden.py is the only reader.
+ *
+ *   CUCD_DUMP_RMD  : one record per rough-mode-decision PU   (TEncSearch.cpp:2252-2361)
+ *   CUCD_DUMP_ME   : every CUCD_DUMP_ME_EVERY-th integer-ME SAD probe (TEncSearch.cpp:336-437)
+ *   CUCD_DUMP_OBF  : one record per picture of the outlier feature pass (TEncSlice.cpp:878-1173)
+ *   CUCD_DUMP_CU   : one record per CU visited by xCompressCU (TEncCu.cpp:589-600)
+ */
+#ifndef CUCD_DUMP_H
+#define CUCD_DUMP_H
+#ifdef __cplusplus
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdint.h>
+
+struct CucdDump {
+  FILE* f;
+  bool  tried;
+  CucdDump() : f(0), tried(false) {}
+  FILE* get(const char* env) {
+    if (!tried) { tried = true; const char* p = getenv(env); if (p && *p) f = fopen(p, "wb"); }
+    return f;
+  }
+};
+inline void cucd_w32(FILE* f, int32_t v) { fwrite(&v, 4, 1, f); }
+
+/* ---- RMD ------------------------------------------------------------------------------- */
+struct CucdRmdState {
+  CucdDump out;
+  unsigned char flags[4 * 32 + 1];
+  int nflags, nintra;
+  uint32_t sad[35];
+  int32_t hdr[8];
+  const short *unf, *fil, *org; int orgStride;
+};
+inline CucdRmdState& cucd_rmd() { static CucdRmdState s; return s; }
+
+/* TComPattern.cpp:134-139 — neighbour availability per 4-sample unit, luma only */
+inline void cucd_hook_flags(int isLuma, const bool* flags, int n, int numIntra) {
+  CucdRmdState& s = cucd_rmd();
+  if (!isLuma) return;
+  s.nflags = n; s.nintra = numIntra;
+  for (int i = 0; i < n; i++) s.flags[i] = flags[i] ? 1 : 0;
+}
+/* TEncSearch.cpp:2311-2327 — before the 35-mode loop */
+inline void cucd_hook_rmd_begin(int poc, int x, int y, int n, int bitDepth, const short* unf, const short* fil,
+                                const short* org, int orgStride) {
+  CucdRmdState& s = cucd_rmd();
+  s.hdr[0] = 0x444d5243; s.hdr[1] = poc; s.hdr[2] = x; s.hdr[3] = y; s.hdr[4] = n; s.hdr[5] = bitDepth;
+  s.unf = unf; s.fil = fil; s.org = org; s.orgStride = orgStride;
+}
+inline void cucd_hook_rmd_mode(int mode, unsigned sad) { cucd_rmd().sad[mode] = sad; }
+/* L-shaped (2N+1)-stride array -> linear bottom-left .. top-left .. top-right, 4N+1 samples */
+inline void cucd_write_border(FILE* f, const short* ext, int n) {
+  const int sw = 2 * n + 1;
+  for (int i = 2 * n; i >= 1; i--) fwrite(&ext[i * sw], 2, 1, f);
+  fwrite(ext, 2, sw, f);
+}
+inline void cucd_hook_rmd_end() {
+  CucdRmdState& s = cucd_rmd();
+  FILE* f = s.out.get("CUCD_DUMP_RMD");
+  if (!f) return;
+  const int n = s.hdr[4];
+  s.hdr[6] = s.nflags; s.hdr[7] = s.nintra;
+  fwrite(s.hdr, 4, 8, f);
+  fwrite(s.flags, 1, s.nflags, f);
+  cucd_write_border(f, s.unf, n);
+  cucd_write_border(f, s.fil, n);
+  for (int r = 0; r < n; r++) fwrite(s.org + r * s.orgStride, 2, n, f);
+  fwrite(s.sad, 4, 35, f);
+}
+
+/* ---- integer ME probe ------------------------------------------------------------------ */
+inline void cucd_hook_me(const short* org, int orgStride, const short* ref, int refStride, int cols, int rows,
+                         int subShift, int bitDepth, int mvx, int mvy, unsigned sad) {
+  static CucdDump out; static long cnt = 0; static long every = -1;
+  FILE* f = out.get("CUCD_DUMP_ME");
+  if (!f) return;
+  if (every < 0) { const char* e = getenv("CUCD_DUMP_ME_EVERY"); every = e ? atol(e) : 97; if (every < 1) every = 1; }
+  if ((cnt++ % every) != 0) return;
+  int32_t hdr[8] = {0x454d5243, cols, rows, subShift, bitDepth, mvx, mvy, (int32_t)sad};
+  fwrite(hdr, 4, 8, f);
+  for (int r = 0; r < rows; r++) fwrite(org + r * orgStride, 2, cols, f);
+  for (int r = 0; r < rows; r++) fwrite(ref + r * refStride, 2, cols, f);
+}
+
+/* ---- OBF / outlier picture pass -------------------------------------------------------- */
+inline void cucd_hook_obf_yc(const double* yc, int n) {
+  static CucdDump out; FILE* f = out.get("CUCD_DUMP_OBF_YC");
+  if (!f) return;
+  cucd_w32(f, n); fwrite(yc, 8, n, f); fflush(f);
+}
+inline void cucd_hook_obf(int poc, int w, int h, int bitDepth, const short* org, int orgStride, const short* obf,
+                          int obfStride, const short* outl, int outlStride) {
+  static CucdDump out; FILE* f = out.get("CUCD_DUMP_OBF");
+  if (!f) return;
+  int32_t hdr[5] = {0x46424f43, poc, w, h, bitDepth};
+  fwrite(hdr, 4, 5, f);
+  for (int r = 0; r < h; r++) fwrite(org + r * orgStride, 2, w, f);
+  for (int r = 0; r < h / 4; r++) fwrite(obf + r * obfStride, 2, w / 4, f);
+  for (int r = 0; r < h; r++) fwrite(outl + r * outlStride, 2, w, f);
+  fflush(f);
+}
+
+/* ---- per-CU block sums ----------------------------------------------------------------- */
+inline void cucd_hook_cu(int poc, int depth, int x, int y, int size, int numObf, int nOutlier) {
+  static CucdDump out; FILE* f = out.get("CUCD_DUMP_CU");
+  if (!f) return;
+  int32_t rec[7] = {poc, depth, x, y, size, numObf, nOutlier};
+  fwrite(rec, 4, 7, f);
+}
+#endif /* __cplusplus */
+#endif
