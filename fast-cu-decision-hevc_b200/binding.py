@@ -1,0 +1,300 @@
+"""ctypes binding of include/cucudecide.h (one Python method per C entry point).
+
+Argument meaning follows the header, which in turn cites the reference call site each entry point
+replaces.  numpy arrays go in and out for the host-buffer API; the ``dev_*`` methods take raw device
+pointers (ints) and a CUDA stream handle so that callers holding data in HBM (bench.py through
+torch) can launch the kernels on their own stream.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+NUM_MODES = 35
+PUS_PER_CTU = 341
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcucudecide.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "cucudecide.h")
+
+_i16p = C.POINTER(C.c_int16)
+_i32p = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
+_f64p = C.POINTER(C.c_double)
+
+
+class CucdError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "bit_depth", "ctu_size", "max_depth", "strong_intra_smoothing",
+                                       "device", "max_pictures", "host_threads")]
+
+
+class _FrameOut(C.Structure):
+    _fields_ = [("obf", _i16p), ("outlier", _i16p), ("yc", _f64p), ("num_obf", _i32p * 4), ("n_outlier", _i32p * 4),
+                ("ctu_src_had", _i32p), ("rmd_cost", _u32p)]
+
+
+class _DevOut(C.Structure):
+    _fields_ = [("obf", C.c_void_p), ("outlier", C.c_void_p), ("num_obf", C.c_void_p * 4), ("n_outlier", C.c_void_p * 4),
+                ("ctu_src_had", C.c_void_p), ("rmd_cost", C.c_void_p)]
+
+
+class _PuDesc(C.Structure):
+    _fields_ = [("log2_size", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+
+
+class _MeDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("x", "y", "w", "h", "ref_idx", "left", "right", "top", "bottom", "sub_shift")]
+
+
+def declared_symbols():
+    """Every function name include/cucudecide.h declares."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cucd_[a-z_0-9]+|cuCUDecide_[a-z]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load_library():
+    """Load libcucudecide.so (built in-tree by __graft_entry__.build / make). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CucdError(f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.cucd_last_error.restype = C.c_char_p
+    lib.cucd_last_error.argtypes = [C.c_void_p]
+    lib.cucd_launch_count.restype = C.c_longlong
+    lib.cucd_launch_count.argtypes = [C.c_void_p]
+    lib.cucd_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    lib.cucd_destroy.argtypes = [C.c_void_p]
+    lib.cuCUDecide_frames.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                      C.POINTER(_FrameOut)]
+    lib.cuCUDecide_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(_FrameOut)]
+    lib.cucd_intra_rmd_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PuDesc), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cucd_set_ref_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.cucd_set_cur_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.cucd_me_sad_surface.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MeDesc), C.c_void_p]
+    lib.cucd_dev_rmd_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
+                                        C.c_longlong, C.c_int, C.c_void_p]
+    lib.cucd_dev_feature_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    lib.cucd_dev_feature_obf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+    lib.cucd_dev_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
+                                    C.c_int, C.POINTER(_DevOut), C.c_void_p]
+    lib.cucd_tcm_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def tcm_fit(hist, n_blocks):
+    """cucd_tcm_fit: 16x4096 uint32 histogram of one picture -> (yc[16] float64, thr[16] int32)."""
+    lib = load_library()
+    hist = np.ascontiguousarray(hist, np.uint32)
+    assert hist.size == 16 * 4096
+    yc = np.zeros(16, np.float64)
+    thr = np.zeros(16, np.int32)
+    rc = lib.cucd_tcm_fit(hist.ctypes.data, int(n_blocks), yc.ctypes.data, thr.ctypes.data)
+    if rc != 0:
+        raise CucdError(f"cucd_tcm_fit failed ({rc})")
+    return yc, thr
+
+
+def _plane(a):
+    a = np.asarray(a)
+    if a.dtype != np.int16 or a.ndim != 2 or a.strides[1] != 2 or a.strides[0] % 2:
+        raise ValueError("planes must be 2-D int16 arrays with contiguous rows")
+    return a, a.strides[0] // 2
+
+
+class Engine:
+    """One cucd_handle: one encoder instance on one GPU."""
+
+    def __init__(self, width, height, bit_depth=8, strong_intra_smoothing=1, device=0, max_pictures=1, host_threads=0):
+        self.lib = load_library()
+        self.width, self.height, self.bit_depth = int(width), int(height), int(bit_depth)
+        self.ctus_per_row = (self.width + 63) // 64
+        self.ctus_per_pic = self.ctus_per_row * ((self.height + 63) // 64)
+        cfg = _Config(self.width, self.height, self.bit_depth, 64, 4, int(strong_intra_smoothing), int(device), int(max_pictures),
+                      int(host_threads))
+        self.h = C.c_void_p()
+        rc = self.lib.cucd_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.cucd_last_error(None).decode()
+            self.h = None
+            raise CucdError(f"cucd_create failed ({rc}): {msg}")
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise CucdError(f"{what} failed ({rc}): {self.lib.cucd_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cucd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def launch_count(self):
+        return int(self.lib.cucd_launch_count(self.h))
+
+    def cu_grid(self, depth):
+        s = 64 >> depth
+        return self.height // s, self.width // s
+
+    # ---- S1/S4 (+ replay S2) --------------------------------------------------------------------
+    def alloc_frame_out(self, want_rmd=True, pinned_alloc=None):
+        """numpy output buffers for one picture (pinned_alloc(shape, dtype) may supply pinned memory)."""
+        mk = pinned_alloc or (lambda shape, dtype: np.zeros(shape, dtype))
+        W, H = self.width, self.height
+        out = {"obf": mk((H // 4, W // 4), np.int16), "outlier": mk((H, W), np.int16), "yc": mk((16,), np.float64),
+               "ctu_src_had": mk((self.ctus_per_pic,), np.int32)}
+        for d in range(4):
+            out[f"num_obf{d}"] = mk(self.cu_grid(d), np.int32)
+            out[f"n_outlier{d}"] = mk(self.cu_grid(d), np.int32)
+        if want_rmd:
+            out["rmd_cost"] = mk((self.ctus_per_pic, PUS_PER_CTU, NUM_MODES), np.uint32)
+        return out
+
+    def _frame_out_struct(self, o):
+        fo = _FrameOut()
+
+        def ptr(name, t):
+            a = o.get(name)
+            return a.ctypes.data_as(t) if a is not None and a.size else t()
+
+        fo.obf = ptr("obf", _i16p)
+        fo.outlier = ptr("outlier", _i16p)
+        fo.yc = ptr("yc", _f64p)
+        for d in range(4):
+            fo.num_obf[d] = ptr(f"num_obf{d}", _i32p)
+            fo.n_outlier[d] = ptr(f"n_outlier{d}", _i32p)
+        fo.ctu_src_had = ptr("ctu_src_had", _i32p)
+        fo.rmd_cost = ptr("rmd_cost", _u32p)
+        return fo
+
+    def frames(self, orgs, recs=None, outs=None, want_rmd=True):
+        """cuCUDecide_frames on host planes; returns the list of output dicts."""
+        n = len(orgs)
+        planes = [_plane(a) for a in orgs]
+        stride = planes[0][1]
+        assert all(s == stride and p.shape == (self.height, self.width) for p, s in planes)
+        org_ptrs = (C.c_void_p * n)(*[p.ctypes.data for p, _ in planes])
+        rec_ptrs, rstride = None, 0
+        if recs is not None:
+            rp = [_plane(a) for a in recs]
+            rstride = rp[0][1]
+            assert len(rp) == n and all(s == rstride and p.shape == (self.height, self.width) for p, s in rp)
+            rec_ptrs = (C.c_void_p * n)(*[p.ctypes.data for p, _ in rp])
+        if outs is None:
+            outs = [self.alloc_frame_out(want_rmd and recs is not None) for _ in range(n)]
+        fos = (_FrameOut * n)(*[self._frame_out_struct(o) for o in outs])
+        self._check(self.lib.cuCUDecide_frames(self.h, n, org_ptrs, stride, rec_ptrs, rstride, fos), "cuCUDecide_frames")
+        return outs
+
+    def frame(self, org, rec=None, poc=0, out=None, want_rmd=True):
+        """cuCUDecide_frame: one picture."""
+        p, stride = _plane(org)
+        rptr, rstride = None, 0
+        if rec is not None:
+            r, rstride = _plane(rec)
+            rptr = r.ctypes.data
+        if out is None:
+            out = self.alloc_frame_out(want_rmd and rec is not None)
+        fo = self._frame_out_struct(out)
+        self._check(self.lib.cuCUDecide_frame(self.h, p.ctypes.data, stride, rptr, rstride, int(poc), C.byref(fo)), "cuCUDecide_frame")
+        return out
+
+    # ---- S2 ---------------------------------------------------------------------------------------
+    def intra_rmd_batch(self, log2_sizes, org, border):
+        """cucd_intra_rmd_batch: PUs of mixed sizes, org/border packed back to back. Returns (nPU, 35) uint32."""
+        log2_sizes = np.asarray(log2_sizes, np.uint8)
+        n = int(log2_sizes.size)
+        org = np.ascontiguousarray(org, np.int16).ravel()
+        border = np.ascontiguousarray(border, np.int16).ravel()
+        sizes = 1 << log2_sizes.astype(np.int64)
+        assert org.size == int((sizes * sizes).sum()) and border.size == int((4 * sizes + 1).sum())
+        desc = (_PuDesc * max(n, 1))()
+        for i in range(n):
+            desc[i].log2_size = int(log2_sizes[i])
+        sad = np.zeros((n, NUM_MODES), np.uint32)
+        self._check(self.lib.cucd_intra_rmd_batch(self.h, n, desc, org.ctypes.data, border.ctypes.data, sad.ctypes.data), "cucd_intra_rmd_batch")
+        return sad
+
+    # ---- S3 ---------------------------------------------------------------------------------------
+    def set_ref_picture(self, ref_idx, padded, margin_x, margin_y):
+        """padded: (H+2my, W+2mx) int16 plane including the replicated margins."""
+        p, stride = _plane(padded)
+        assert p.shape == (self.height + 2 * margin_y, self.width + 2 * margin_x)
+        origin = p.ctypes.data + 2 * (margin_y * stride + margin_x)
+        self._check(self.lib.cucd_set_ref_picture(self.h, int(ref_idx), origin, stride, int(margin_x), int(margin_y)), "cucd_set_ref_picture")
+
+    def set_cur_picture(self, org):
+        p, stride = _plane(org)
+        self._check(self.lib.cucd_set_cur_picture(self.h, p.ctypes.data, stride), "cucd_set_cur_picture")
+
+    def me_sad_surface(self, descs):
+        """descs: list of dicts(x,y,w,h,ref_idx,left,right,top,bottom,sub_shift). Returns list of (rows, cols) uint32 surfaces."""
+        n = len(descs)
+        arr = (_MeDesc * max(n, 1))()
+        total = 0
+        shapes = []
+        for i, d in enumerate(descs):
+            for k in ("x", "y", "w", "h", "ref_idx", "left", "right", "top", "bottom", "sub_shift"):
+                setattr(arr[i], k, int(d[k]))
+            shapes.append((d["bottom"] - d["top"] + 1, d["right"] - d["left"] + 1))
+            total += shapes[-1][0] * shapes[-1][1]
+        out = np.zeros(max(total, 1), np.uint32)
+        self._check(self.lib.cucd_me_sad_surface(self.h, n, arr, out.ctypes.data), "cucd_me_sad_surface")
+        res, off = [], 0
+        for r, c in shapes:
+            res.append(out[off:off + r * c].reshape(r, c))
+            off += r * c
+        return res
+
+    # ---- device-resident entry points (raw pointers) ----------------------------------------------
+    def dev_rmd_frames(self, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride, d_cost):
+        self._check(self.lib.cucd_dev_rmd_frames(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride,
+                                                 rec_stride, d_cost), "cucd_dev_rmd_frames")
+
+    def dev_feature_hist(self, stream, n_pics, d_org, org_pic_stride, org_stride, d_hist):
+        self._check(self.lib.cucd_dev_feature_hist(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_hist), "cucd_dev_feature_hist")
+
+    def dev_feature_obf(self, stream, n_pics, d_org, org_pic_stride, org_stride, d_thr, d_obf, d_outlier, d_num, d_sum, d_ctu_had):
+        num = (C.c_void_p * 4)(*d_num)
+        summ = (C.c_void_p * 4)(*d_sum)
+        self._check(self.lib.cucd_dev_feature_obf(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_thr, d_obf, d_outlier,
+                                                  num, summ, d_ctu_had), "cucd_dev_feature_obf")
+
+    def dev_frames(self, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride, d_out, yc_host=None):
+        """cucd_dev_frames: d_out = dict of device pointers (obf, outlier, num_obf[4], n_outlier[4], ctu_src_had, rmd_cost)."""
+        o = _DevOut()
+        o.obf = d_out.get("obf")
+        o.outlier = d_out.get("outlier")
+        for d in range(4):
+            o.num_obf[d] = (d_out.get("num_obf") or [None] * 4)[d]
+            o.n_outlier[d] = (d_out.get("n_outlier") or [None] * 4)[d]
+        o.ctu_src_had = d_out.get("ctu_src_had")
+        o.rmd_cost = d_out.get("rmd_cost")
+        yc = yc_host.ctypes.data if yc_host is not None else None
+        self._check(self.lib.cucd_dev_frames(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride,
+                                             C.byref(o), yc), "cucd_dev_frames")

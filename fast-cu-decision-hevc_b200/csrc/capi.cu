@@ -1,0 +1,499 @@
+// capi.cu - the C ABI (include/cucudecide.h) and the host runtime behind it: device buffers, pinned
+// staging, streams, the two-pass feature pipeline with the host TCM fit in between, size-class
+// bucketing of batched RMD requests and tiling of ME search windows.  There is no CPU compute path:
+// every entry point either runs the CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include "../../include/cucudecide.h"
+#include "kernels.h"
+#include "tcm_host.h"
+
+using namespace cucd;
+
+namespace {
+std::string g_createError;
+
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  cudaError_t reserve(size_t count) {
+    if (count <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+template <class T> struct PinBuf {
+  T* p = nullptr; size_t n = 0;
+  cudaError_t reserve(size_t count) {
+    if (count <= n) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+struct RefPlane { DevBuf<int16_t> buf; int stride = 0, marginX = 0, marginY = 0; bool set = false; };
+}  // namespace
+
+struct cucd_handle {
+  cucd_config cfg;
+  int ctusPerRow = 0, ctusPerCol = 0, ctusPerPic = 0, pitch = 0;
+  size_t planeSamples = 0;
+  cudaStream_t sMain = nullptr, sFeat = nullptr;
+  cudaEvent_t evUp = nullptr, evHist = nullptr;
+  int launches = 0;
+  long long launchTotal = 0;
+  std::string err;
+  int hostThreads = 1;
+  // frame path
+  DevBuf<int16_t> dOrg, dRec, dObf, dOutlier;
+  DevBuf<uint32_t> dCost, dHist;
+  DevBuf<int32_t> dThr, dNum[4], dSum[4], dCtuHad;
+  PinBuf<uint32_t> hHist;
+  PinBuf<int32_t> hThr;
+  size_t cuCount[4] = {0, 0, 0, 0};
+  // batch RMD path
+  DevBuf<int16_t> bOrg, bBorder;
+  DevBuf<BatchPu> bPus;
+  DevBuf<uint32_t> bOut;
+  // ME path
+  std::vector<RefPlane> refs;
+  DevBuf<int16_t> dCur; int curStride = 0; bool curSet = false;
+  DevBuf<const int16_t*> dRefPtr; DevBuf<int32_t> dRefStride;
+  DevBuf<MeJob> dJobs; DevBuf<int32_t> dTileJob, dTileIdx; DevBuf<uint32_t> dSad;
+};
+
+namespace {
+
+int fail(cucd_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_createError = msg;
+  return code;
+}
+int cuda_fail(cucd_handle* h, cudaError_t e, const char* what) {
+  return fail(h, CUCD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                         \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return cuda_fail(h, e__, #call);             \
+  } while (0)
+
+void flush_launches(cucd_handle* h) { h->launchTotal += h->launches; h->launches = 0; }
+
+FrameSource make_frame_source(const cucd_handle* h, const int16_t* org, long long orgPic, int orgStride, const int16_t* rec, long long recPic,
+                              int recStride, uint32_t* out) {
+  FrameSource fs;
+  fs.org = org; fs.rec = rec; fs.orgPicStride = orgPic; fs.recPicStride = recPic; fs.orgStride = orgStride; fs.recStride = recStride;
+  fs.W = h->cfg.width; fs.H = h->cfg.height; fs.ctusPerRow = h->ctusPerRow; fs.ctusPerPic = h->ctusPerPic; fs.out = out;
+  return fs;
+}
+FeaturePlanes make_feature_planes(const cucd_handle* h, const int16_t* org, long long orgPic, int orgStride) {
+  FeaturePlanes fp;
+  fp.org = org; fp.orgPicStride = orgPic; fp.orgStride = orgStride; fp.W = h->cfg.width; fp.H = h->cfg.height;
+  fp.ctusPerRow = h->ctusPerRow; fp.ctusPerPic = h->ctusPerPic; fp.bitDepth = h->cfg.bit_depth;
+  return fp;
+}
+
+// parallel-for over [0, n) on up to `threads` host threads
+template <class F> void parallel_for(int n, int threads, F fn) {
+  if (threads <= 1 || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+  std::atomic<int> next(0);
+  auto body = [&]() { for (;;) { const int i = next.fetch_add(1); if (i >= n) break; fn(i); } };
+  const int nt = std::min(threads, n);
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(body);
+  body();
+  for (auto& t : pool) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int cucd_abi_version(void) { return CUCD_ABI_VERSION; }
+
+const char* cucd_last_error(const cucd_handle* h) { return h ? h->err.c_str() : g_createError.c_str(); }
+long long cucd_launch_count(const cucd_handle* h) { return h ? h->launchTotal + h->launches : 0; }
+
+int cucd_create(const cucd_config* cfg, cucd_handle** out) {
+  if (!cfg || !out) return fail(nullptr, CUCD_ERR_INVALID, "cucd_create: null argument");
+  *out = nullptr;
+  if (cfg->ctu_size != 64 || cfg->max_depth != 4) return fail(nullptr, CUCD_ERR_UNSUPPORTED, "cucd_create: only CTU 64 / depth 4 is built");
+  if (cfg->bit_depth < 8 || cfg->bit_depth > 10) return fail(nullptr, CUCD_ERR_UNSUPPORTED, "cucd_create: bit depth must be 8..10");
+  if (cfg->width < 8 || cfg->height < 8 || (cfg->width & 7) || (cfg->height & 7)) return fail(nullptr, CUCD_ERR_INVALID, "cucd_create: width/height must be multiples of 8");
+  if (cfg->max_pictures < 1) return fail(nullptr, CUCD_ERR_INVALID, "cucd_create: max_pictures < 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return fail(nullptr, CUCD_ERR_NO_DEVICE, std::string("cucd_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CUCD_ERR_INVALID, "cucd_create: bad device ordinal");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10) return fail(nullptr, CUCD_ERR_NO_DEVICE, "cucd_create: kernels are built for sm_100a only, device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+
+  cucd_handle* h = new cucd_handle;
+  h->cfg = *cfg;
+  h->ctusPerRow = (cfg->width + 63) / 64; h->ctusPerCol = (cfg->height + 63) / 64; h->ctusPerPic = h->ctusPerRow * h->ctusPerCol;
+  h->pitch = (cfg->width + 63) & ~63;
+  h->planeSamples = (size_t)h->pitch * cfg->height;
+  h->hostThreads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  for (int d = 0; d < 4; d++) h->cuCount[d] = (size_t)(cfg->width / (64 >> d)) * (cfg->height / (64 >> d));
+  const size_t P = (size_t)cfg->max_pictures;
+  bool ok = cudaStreamCreateWithFlags(&h->sMain, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->sFeat, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->evUp, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->evHist, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && h->dOrg.reserve(P * h->planeSamples) == cudaSuccess && h->dRec.reserve(P * h->planeSamples) == cudaSuccess;
+  ok = ok && h->dCost.reserve(P * h->ctusPerPic * kPusPerCtu * kNumModes) == cudaSuccess;
+  ok = ok && h->dHist.reserve(P * kHistFreqs * kHistBins) == cudaSuccess && h->dThr.reserve(P * kHistFreqs) == cudaSuccess;
+  ok = ok && h->dObf.reserve(P * (size_t)(cfg->width / 4) * (cfg->height / 4)) == cudaSuccess;
+  ok = ok && h->dOutlier.reserve(P * (size_t)cfg->width * cfg->height) == cudaSuccess;
+  for (int d = 0; d < 4; d++) ok = ok && h->dNum[d].reserve(P * std::max<size_t>(1, h->cuCount[d])) == cudaSuccess && h->dSum[d].reserve(P * std::max<size_t>(1, h->cuCount[d])) == cudaSuccess;
+  ok = ok && h->dCtuHad.reserve(P * h->ctusPerPic) == cudaSuccess;
+  ok = ok && h->hHist.reserve(P * kHistFreqs * kHistBins) == cudaSuccess && h->hThr.reserve(P * kHistFreqs) == cudaSuccess;
+  if (!ok) {
+    const std::string msg = std::string("cucd_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    cucd_destroy(h);
+    return fail(nullptr, CUCD_ERR_NOMEM, msg);
+  }
+  *out = h;
+  return CUCD_OK;
+}
+
+int cucd_destroy(cucd_handle* h) {
+  if (!h) return CUCD_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  h->dOrg.release(); h->dRec.release(); h->dObf.release(); h->dOutlier.release(); h->dCost.release(); h->dHist.release(); h->dThr.release();
+  for (int d = 0; d < 4; d++) { h->dNum[d].release(); h->dSum[d].release(); }
+  h->dCtuHad.release(); h->hHist.release(); h->hThr.release();
+  h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
+  for (auto& r : h->refs) r.buf.release();
+  h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
+  if (h->evUp) cudaEventDestroy(h->evUp);
+  if (h->evHist) cudaEventDestroy(h->evHist);
+  if (h->sMain) cudaStreamDestroy(h->sMain);
+  if (h->sFeat) cudaStreamDestroy(h->sFeat);
+  delete h;
+  return CUCD_OK;
+}
+
+int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr) {
+  if (!hist || !yc || !thr || nBlocks <= 0) return CUCD_ERR_INVALID;
+  tcm_fit_picture(hist, nBlocks, yc, thr);
+  return CUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident entry points
+// ------------------------------------------------------------------------------------------------
+int cucd_dev_rmd_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                        const int16_t* d_rec, long long recPicStride, int recStride, uint32_t* d_rmd_cost) {
+  if (!h || nPics < 1 || !d_org || !d_rec || !d_rmd_cost) return fail(h, CUCD_ERR_INVALID, "cucd_dev_rmd_frames: bad argument");
+  if ((orgStride & 7) || (orgPicStride & 7) || ((uintptr_t)d_org & 15)) return fail(h, CUCD_ERR_INVALID, "cucd_dev_rmd_frames: source plane must be 16-byte aligned with strides multiple of 8");
+  CK(cudaSetDevice(h->cfg.device));
+  const FrameSource fs = make_frame_source(h, d_org, orgPicStride, orgStride, d_rec, recPicStride, recStride, d_rmd_cost);
+  CK(launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, (cudaStream_t)stream, &h->launches));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+int cucd_dev_feature_hist(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride, uint32_t* d_hist) {
+  if (!h || nPics < 1 || !d_org || !d_hist) return fail(h, CUCD_ERR_INVALID, "cucd_dev_feature_hist: bad argument");
+  if ((orgStride & 3) || (orgPicStride & 3) || ((uintptr_t)d_org & 7)) return fail(h, CUCD_ERR_INVALID, "cucd_dev_feature_hist: source plane must be 8-byte aligned with strides multiple of 4");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(launch_feature_hist(make_feature_planes(h, d_org, orgPicStride, orgStride), nPics, d_hist, (cudaStream_t)stream, &h->launches));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+int cucd_dev_feature_obf(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                         const int32_t* d_thr, int16_t* d_obf, int16_t* d_outlier, int32_t* const d_num_obf[4],
+                         int32_t* const d_n_outlier[4], int32_t* d_ctu_src_had) {
+  if (!h || nPics < 1 || !d_org || !d_thr || !d_obf || !d_outlier || !d_num_obf || !d_n_outlier) return fail(h, CUCD_ERR_INVALID, "cucd_dev_feature_obf: bad argument");
+  if ((orgStride & 7) || (orgPicStride & 7) || ((uintptr_t)d_org & 15)) return fail(h, CUCD_ERR_INVALID, "cucd_dev_feature_obf: source plane must be 16-byte aligned with strides multiple of 8");
+  CK(cudaSetDevice(h->cfg.device));
+  const FeaturePlanes fp = make_feature_planes(h, d_org, orgPicStride, orgStride);
+  FeatureOut fo;
+  fo.obf = d_obf; fo.obfPicStride = (long long)(h->cfg.width / 4) * (h->cfg.height / 4);
+  fo.outlier = d_outlier; fo.outlierPicStride = (long long)h->cfg.width * h->cfg.height;
+  for (int d = 0; d < 4; d++) {
+    if (!d_num_obf[d] || !d_n_outlier[d]) return fail(h, CUCD_ERR_INVALID, "cucd_dev_feature_obf: null per-depth output");
+    fo.numObf[d] = d_num_obf[d]; fo.nOutlier[d] = d_n_outlier[d]; fo.cuPicStride[d] = (long long)h->cuCount[d];
+  }
+  CK(launch_feature_obf(fp, nPics, d_thr, fo, (cudaStream_t)stream, &h->launches));
+  if (d_ctu_src_had) CK(launch_ctu_src_had(fp, nPics, d_ctu_src_had, (cudaStream_t)stream, &h->launches));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                    const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host) {
+  if (!h || nPics < 1 || nPics > h->cfg.max_pictures || !d_org || !out) return fail(h, CUCD_ERR_INVALID, "cucd_dev_frames: bad argument (nPics must be <= max_pictures)");
+  if ((orgStride & 7) || (orgPicStride & 7) || ((uintptr_t)d_org & 15)) return fail(h, CUCD_ERR_INVALID, "cucd_dev_frames: source plane must be 16-byte aligned with strides multiple of 8");
+  if ((out->rmd_cost != nullptr) != (d_rec != nullptr)) return fail(h, CUCD_ERR_INVALID, "cucd_dev_frames: d_rec and rmd_cost go together");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = h->cfg.width, H = h->cfg.height;
+  const bool wantFeat = out->obf || out->outlier || out->ctu_src_had || yc_host;
+  const FeaturePlanes fp = make_feature_planes(h, d_org, orgPicStride, orgStride);
+  if (wantFeat) {
+    CK(launch_feature_hist(fp, nPics, h->dHist.p, st, &h->launches));
+    CK(cudaMemcpyAsync(h->hHist.p, h->dHist.p, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->evHist, st));
+  }
+  if (d_rec) {
+    const FrameSource fs = make_frame_source(h, d_org, orgPicStride, orgStride, d_rec, recPicStride, recStride, out->rmd_cost);
+    CK(launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches));
+  }
+  if (wantFeat) {
+    CK(cudaEventSynchronize(h->evHist));      // the RMD kernel keeps the GPU busy while the host fits
+    const int nBlocks = (W / 4) * (H / 4);
+    std::vector<double> yc((size_t)nPics * 16, 0.0);
+    parallel_for(nPics * 15, h->hostThreads, [&](int i) {
+      const int p = i / 15, f = 1 + i % 15;
+      const double y = tcm_fit_one(h->hHist.p + ((size_t)p * kHistFreqs + f) * kHistBins, nBlocks);
+      yc[(size_t)p * 16 + f] = y;
+      h->hThr.p[p * kHistFreqs + f] = (int32_t)(y * 8.0);
+    });
+    for (int p = 0; p < nPics; p++) h->hThr.p[p * kHistFreqs] = 0;
+    if (yc_host) memcpy(yc_host, yc.data(), yc.size() * sizeof(double));
+    CK(cudaMemcpyAsync(h->dThr.p, h->hThr.p, (size_t)nPics * kHistFreqs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FeatureOut fo;
+    fo.obf = out->obf ? out->obf : h->dObf.p; fo.obfPicStride = (long long)(W / 4) * (H / 4);
+    fo.outlier = out->outlier ? out->outlier : h->dOutlier.p; fo.outlierPicStride = (long long)W * H;
+    for (int d = 0; d < 4; d++) {
+      fo.numObf[d] = out->num_obf[d] ? out->num_obf[d] : h->dNum[d].p;
+      fo.nOutlier[d] = out->n_outlier[d] ? out->n_outlier[d] : h->dSum[d].p;
+      fo.cuPicStride[d] = (long long)h->cuCount[d];
+    }
+    CK(launch_feature_obf(fp, nPics, h->dThr.p, fo, st, &h->launches));
+    if (out->ctu_src_had) CK(launch_ctu_src_had(fp, nPics, out->ctu_src_had, st, &h->launches));
+  }
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S1/S4 (+ replay S2) with host buffers
+// ------------------------------------------------------------------------------------------------
+static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, int strideY, const int16_t* const* recY, int strideRec,
+                        cucd_frame_out* outs) {
+  const int W = h->cfg.width, H = h->cfg.height;
+  bool wantRmd = false;
+  if (recY) for (int p = 0; p < nPics; p++) wantRmd = wantRmd || outs[p].rmd_cost != nullptr;
+  // ---- upload ----------------------------------------------------------------------------------
+  for (int p = 0; p < nPics; p++) {
+    CK(cudaMemcpy2DAsync(h->dOrg.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, orgY[p], (size_t)strideY * 2, (size_t)W * 2, H,
+                         cudaMemcpyHostToDevice, h->sFeat));
+  }
+  CK(cudaEventRecord(h->evUp, h->sFeat));
+  // ---- feature pass 1 on sFeat -----------------------------------------------------------------
+  const FeaturePlanes fp = make_feature_planes(h, h->dOrg.p, (long long)h->planeSamples, h->pitch);
+  CK(launch_feature_hist(fp, nPics, h->dHist.p, h->sFeat, &h->launches));
+  CK(cudaMemcpyAsync(h->hHist.p, h->dHist.p, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sFeat));
+  CK(cudaEventRecord(h->evHist, h->sFeat));
+  // ---- RMD replay on sMain (overlaps the host TCM fit) -----------------------------------------
+  if (wantRmd) {
+    for (int p = 0; p < nPics; p++) {
+      CK(cudaMemcpy2DAsync(h->dRec.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, recY[p], (size_t)strideRec * 2, (size_t)W * 2, H,
+                           cudaMemcpyHostToDevice, h->sMain));
+    }
+    CK(cudaStreamWaitEvent(h->sMain, h->evUp, 0));
+    const FrameSource fs = make_frame_source(h, h->dOrg.p, (long long)h->planeSamples, h->pitch, h->dRec.p, (long long)h->planeSamples, h->pitch, h->dCost.p);
+    CK(launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
+    const size_t perPic = (size_t)h->ctusPerPic * kPusPerCtu * kNumModes;
+    for (int p = 0; p < nPics; p++)
+      if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
+  }
+  // ---- host: TCM fit per picture and frequency -------------------------------------------------
+  CK(cudaEventSynchronize(h->evHist));
+  const int nBlocks = (W / 4) * (H / 4);
+  std::vector<double> yc((size_t)nPics * 16, 0.0);
+  parallel_for(nPics * 15, h->hostThreads, [&](int i) {
+    const int p = i / 15, f = 1 + i % 15;
+    const double y = tcm_fit_one(h->hHist.p + ((size_t)p * kHistFreqs + f) * kHistBins, nBlocks);
+    yc[(size_t)p * 16 + f] = y;
+    h->hThr.p[p * kHistFreqs + f] = (int32_t)(y * 8.0);
+  });
+  for (int p = 0; p < nPics; p++) { h->hThr.p[p * kHistFreqs] = 0; if (outs[p].yc) memcpy(outs[p].yc, &yc[(size_t)p * 16], 16 * sizeof(double)); }
+  // ---- feature pass 2 on sFeat -----------------------------------------------------------------
+  CK(cudaMemcpyAsync(h->dThr.p, h->hThr.p, (size_t)nPics * kHistFreqs * sizeof(int32_t), cudaMemcpyHostToDevice, h->sFeat));
+  FeatureOut fo;
+  fo.obf = h->dObf.p; fo.obfPicStride = (long long)(W / 4) * (H / 4);
+  fo.outlier = h->dOutlier.p; fo.outlierPicStride = (long long)W * H;
+  for (int d = 0; d < 4; d++) { fo.numObf[d] = h->dNum[d].p; fo.nOutlier[d] = h->dSum[d].p; fo.cuPicStride[d] = (long long)h->cuCount[d]; }
+  CK(launch_feature_obf(fp, nPics, h->dThr.p, fo, h->sFeat, &h->launches));
+  CK(launch_ctu_src_had(fp, nPics, h->dCtuHad.p, h->sFeat, &h->launches));
+  for (int p = 0; p < nPics; p++) {
+    const cucd_frame_out& o = outs[p];
+    if (o.obf) CK(cudaMemcpyAsync(o.obf, h->dObf.p + (size_t)p * fo.obfPicStride, (size_t)fo.obfPicStride * 2, cudaMemcpyDeviceToHost, h->sFeat));
+    if (o.outlier) CK(cudaMemcpyAsync(o.outlier, h->dOutlier.p + (size_t)p * fo.outlierPicStride, (size_t)fo.outlierPicStride * 2, cudaMemcpyDeviceToHost, h->sFeat));
+    for (int d = 0; d < 4; d++) {
+      if (!h->cuCount[d]) continue;
+      if (o.num_obf[d]) CK(cudaMemcpyAsync(o.num_obf[d], h->dNum[d].p + (size_t)p * h->cuCount[d], h->cuCount[d] * 4, cudaMemcpyDeviceToHost, h->sFeat));
+      if (o.n_outlier[d]) CK(cudaMemcpyAsync(o.n_outlier[d], h->dSum[d].p + (size_t)p * h->cuCount[d], h->cuCount[d] * 4, cudaMemcpyDeviceToHost, h->sFeat));
+    }
+    if (o.ctu_src_had) CK(cudaMemcpyAsync(o.ctu_src_had, h->dCtuHad.p + (size_t)p * h->ctusPerPic, (size_t)h->ctusPerPic * 4, cudaMemcpyDeviceToHost, h->sFeat));
+  }
+  CK(cudaStreamSynchronize(h->sFeat));
+  CK(cudaStreamSynchronize(h->sMain));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+int cuCUDecide_frames(cucd_handle* h, int nPics, const int16_t* const* orgY, int strideY, const int16_t* const* recY, int strideRec,
+                      cucd_frame_out* outs) {
+  if (!h || nPics < 1 || !orgY || !outs || strideY < h->cfg.width) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: bad argument");
+  if (recY && strideRec < h->cfg.width) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: bad reconstruction stride");
+  for (int p = 0; p < nPics; p++) {
+    if (!orgY[p] || (recY && !recY[p])) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: null plane");
+    if (outs[p].rmd_cost && !recY) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: rmd_cost wanted but no reconstruction plane given");
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  for (int first = 0; first < nPics; first += h->cfg.max_pictures) {
+    const int n = std::min(h->cfg.max_pictures, nPics - first);
+    const int rc = frames_group(h, n, orgY + first, strideY, recY ? recY + first : nullptr, strideRec, outs + first);
+    if (rc != CUCD_OK) return rc;
+  }
+  return CUCD_OK;
+}
+
+int cuCUDecide_frame(cucd_handle* h, const int16_t* orgY, int strideY, const int16_t* recY, int strideRec, int poc, cucd_frame_out* out) {
+  (void)poc;   // the train/verify/test schedule keyed on POC (tools_YS.cpp:1237-1242) is host-side state
+  const int16_t* o[1] = {orgY};
+  const int16_t* r[1] = {recY};
+  return cuCUDecide_frames(h, 1, o, strideY, recY ? r : nullptr, strideRec, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// S2: batched RMD with caller-supplied borders
+// ------------------------------------------------------------------------------------------------
+int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, const int16_t* org, const int16_t* border, uint32_t* sad) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !org || !border || !sad))) return fail(h, CUCD_ERR_INVALID, "cucd_intra_rmd_batch: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  // bucket by size; offsets follow the caller's back-to-back packing
+  std::vector<BatchPu> pus[7];
+  size_t orgOff = 0, borderOff = 0;
+  for (int i = 0; i < nPU; i++) {
+    const int l = desc[i].log2_size;
+    if (l < 2 || l > 6) return fail(h, CUCD_ERR_INVALID, "cucd_intra_rmd_batch: log2_size must be 2..6");
+    const int n = 1 << l;
+    BatchPu b; b.orgOff = (int32_t)orgOff; b.borderOff = (int32_t)borderOff; b.outIndex = i; b.pad = 0;
+    pus[l].push_back(b);
+    orgOff += (size_t)n * n; borderOff += (size_t)4 * n + 1;
+    if (orgOff > 0x7fffffffull) return fail(h, CUCD_ERR_INVALID, "cucd_intra_rmd_batch: batch too large");
+  }
+  std::vector<BatchPu> all; all.reserve(nPU);
+  size_t first[7] = {0};
+  for (int l = 2; l <= 6; l++) { first[l] = all.size(); all.insert(all.end(), pus[l].begin(), pus[l].end()); }
+  CK(h->bOrg.reserve(orgOff + 64)); CK(h->bBorder.reserve(borderOff + 8)); CK(h->bPus.reserve(all.size())); CK(h->bOut.reserve((size_t)nPU * kNumModes));
+  CK(cudaMemcpyAsync(h->bOrg.p, org, orgOff * 2, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->bBorder.p, border, borderOff * 2, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->bPus.p, all.data(), all.size() * sizeof(BatchPu), cudaMemcpyHostToDevice, h->sMain));
+  for (int l = 6; l >= 2; l--) {
+    if (pus[l].empty()) continue;
+    BatchSource bs;
+    bs.org = h->bOrg.p; bs.border = h->bBorder.p; bs.pus = h->bPus.p + first[l]; bs.out = h->bOut.p; bs.count = (int)pus[l].size();
+    CK(launch_rmd_batch(l, bs, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
+  }
+  CK(cudaMemcpyAsync(sad, h->bOut.p, (size_t)nPU * kNumModes * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));   // `all` and the caller's buffers must outlive the copies
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S3: integer ME SAD surfaces
+// ------------------------------------------------------------------------------------------------
+int cucd_set_ref_picture(cucd_handle* h, int ref_idx, const int16_t* recY, int stride, int marginX, int marginY) {
+  if (!h || ref_idx < 0 || ref_idx >= 64 || !recY || marginX < 0 || marginY < 0 || stride < h->cfg.width + 2 * marginX)
+    return fail(h, CUCD_ERR_INVALID, "cucd_set_ref_picture: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if ((int)h->refs.size() <= ref_idx) h->refs.resize(ref_idx + 1);
+  RefPlane& r = h->refs[ref_idx];
+  const int pw = h->cfg.width + 2 * marginX, ph = h->cfg.height + 2 * marginY;
+  const int pitch = (pw + 7) & ~7;
+  CK(r.buf.reserve((size_t)pitch * ph));
+  CK(cudaMemcpy2DAsync(r.buf.p, (size_t)pitch * 2, recY - (ptrdiff_t)marginY * stride - marginX, (size_t)stride * 2, (size_t)pw * 2, ph,
+                       cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  r.stride = pitch; r.marginX = marginX; r.marginY = marginY; r.set = true;
+  return CUCD_OK;
+}
+
+int cucd_set_cur_picture(cucd_handle* h, const int16_t* orgY, int stride) {
+  if (!h || !orgY || stride < h->cfg.width) return fail(h, CUCD_ERR_INVALID, "cucd_set_cur_picture: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(h->dCur.reserve(h->planeSamples));
+  CK(cudaMemcpy2DAsync(h->dCur.p, (size_t)h->pitch * 2, orgY, (size_t)stride * 2, (size_t)h->cfg.width * 2, h->cfg.height, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  h->curStride = h->pitch; h->curSet = true;
+  return CUCD_OK;
+}
+
+int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !sadOut))) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  const int W = h->cfg.width, H = h->cfg.height;
+  std::vector<MeJob> jobs(nPU);
+  std::vector<int32_t> tileJob, tileIdx;
+  long long total = 0;
+  for (int i = 0; i < nPU; i++) {
+    const cucd_me_desc& d = desc[i];
+    if (d.w < 4 || d.h < 4 || d.w > 64 || d.h > 64 || (d.w & 1) || d.x < 0 || d.y < 0 || d.x + d.w > W || d.y + d.h > H || d.left > d.right || d.top > d.bottom ||
+        d.sub_shift < 0 || d.sub_shift > 4)
+      return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: bad PU / window");
+    if (d.ref_idx < 0 || d.ref_idx >= (int)h->refs.size() || !h->refs[d.ref_idx].set) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: reference picture not set");
+    const RefPlane& r = h->refs[d.ref_idx];
+    if (d.x + d.left < -r.marginX || d.y + d.top < -r.marginY || d.x + d.w - 1 + d.right > W - 1 + r.marginX || d.y + d.h - 1 + d.bottom > H - 1 + r.marginY)
+      return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: window leaves the padded reference picture");
+    MeJob& j = jobs[i];
+    j.curOff = d.y * h->curStride + d.x;
+    j.refOff = (d.y + r.marginY) * r.stride + d.x + r.marginX;
+    j.refSlot = d.ref_idx; j.w = (int16_t)d.w; j.h = (int16_t)d.h;
+    j.left = (int16_t)d.left; j.right = (int16_t)d.right; j.top = (int16_t)d.top; j.bottom = (int16_t)d.bottom;
+    // the width-specialised xGetSAD* honour iSubShift, the generic xGetSAD (TComRdCost.cpp:465-491) does not
+    const bool special = d.w == 4 || d.w == 8 || d.w == 12 || d.w == 16 || d.w == 24 || d.w == 32 || d.w == 48 || d.w == 64;
+    j.subShift = (int16_t)(special ? d.sub_shift : 0); j.pad = 0;
+    j.outOff = total;
+    const int cols = d.right - d.left + 1, rows = d.bottom - d.top + 1;
+    const int tiles = ((cols + 31) / 32) * ((rows + 7) / 8);
+    for (int t = 0; t < tiles; t++) { tileJob.push_back(i); tileIdx.push_back(t); }
+    total += (long long)cols * rows;
+  }
+  std::vector<const int16_t*> refPtr(h->refs.size(), nullptr);
+  std::vector<int32_t> refStride(h->refs.size(), 0);
+  for (size_t i = 0; i < h->refs.size(); i++) { refPtr[i] = h->refs[i].buf.p; refStride[i] = h->refs[i].stride; }
+  CK(h->dRefPtr.reserve(refPtr.size())); CK(h->dRefStride.reserve(refStride.size()));
+  CK(h->dJobs.reserve(jobs.size())); CK(h->dTileJob.reserve(tileJob.size())); CK(h->dTileIdx.reserve(tileIdx.size())); CK(h->dSad.reserve((size_t)total));
+  CK(cudaMemcpyAsync(h->dRefPtr.p, refPtr.data(), refPtr.size() * sizeof(void*), cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->dRefStride.p, refStride.data(), refStride.size() * 4, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->dJobs.p, jobs.data(), jobs.size() * sizeof(MeJob), cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->dTileJob.p, tileJob.data(), tileJob.size() * 4, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->dTileIdx.p, tileIdx.data(), tileIdx.size() * 4, cudaMemcpyHostToDevice, h->sMain));
+  MePlanes mp;
+  mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
+  CK(launch_me_sad(mp, h->dJobs.p, nPU, h->dTileJob.p, h->dTileIdx.p, (int)tileJob.size(), h->dSad.p, h->sMain, &h->launches));
+  CK(cudaMemcpyAsync(sadOut, h->dSad.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// kernels.h - launch entry points of the CUDA kernels (internal to libcucudecide.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rmd_chunk.cuh"
+
+namespace cucd {
+
+constexpr int kHistBins = 4096;     // |coeff/8| <= 4095 for bit depths <= 12 (see feature_kernels.cu)
+constexpr int kHistFreqs = 16;      // index 0 (DC) unused
+
+// ---- intra RMD (rmd_kernels.cu) ---------------------------------------------------------------
+cudaError_t launch_rmd_frames(const FrameSource& fs, int nPics, int bitDepth, int strong, cudaStream_t st, int* launches);
+cudaError_t launch_rmd_batch(int log2n, const BatchSource& bs, int bitDepth, int strong, cudaStream_t st, int* launches);
+
+// ---- per-picture texture features (feature_kernels.cu) ----------------------------------------
+struct FeaturePlanes {
+  const int16_t* org; long long orgPicStride; int orgStride;   // source luma
+  int W, H, ctusPerRow, ctusPerPic, bitDepth;
+};
+// pass 1: 4x4 DCT of every block, histogram of |coeff/8| per AC frequency: hist[pic][16][4096]
+cudaError_t launch_feature_hist(const FeaturePlanes& fp, int nPics, uint32_t* hist, cudaStream_t st, int* launches);
+// pass 2: outlier thresholds thr[pic][16] (= Yc*8 as int) -> OBF plane, Outlier plane, per-depth CU sums
+struct FeatureOut {
+  int16_t* obf; long long obfPicStride;           // [(H/4)][(W/4)] tight
+  int16_t* outlier; long long outlierPicStride;   // [H][W] tight
+  int32_t* numObf[4]; int32_t* nOutlier[4];       // per depth: [(H/size)][(W/size)] tight
+  long long cuPicStride[4];
+};
+cudaError_t launch_feature_obf(const FeaturePlanes& fp, int nPics, const int32_t* thr, const FeatureOut& out, cudaStream_t st, int* launches);
+// source-only DC-less 8x8 Hadamard cost per CTU: ctuHad[pic][ctusPerPic]
+cudaError_t launch_ctu_src_had(const FeaturePlanes& fp, int nPics, int32_t* ctuHad, cudaStream_t st, int* launches);
+
+// ---- integer-ME SAD surfaces (me_kernels.cu) ---------------------------------------------------
+struct MeJob {
+  int32_t curOff;      // sample offset of the PU's top-left inside the current picture plane
+  int32_t refOff;      // sample offset of the co-located sample inside the padded reference plane
+  int32_t refSlot;     // which resident reference plane
+  int16_t w, h;
+  int16_t left, right, top, bottom;   // integer MV window, inclusive
+  int16_t subShift, pad;
+  int64_t outOff;      // offset (in uint32) of this PU's surface inside the output buffer
+};
+struct MePlanes {
+  const int16_t* cur; int curStride;
+  const int16_t* const* ref;  // device array of plane origins (sample (0,0) of each padded plane)
+  const int32_t* refStride;   // device array
+  int bitDepth;
+};
+cudaError_t launch_me_sad(const MePlanes& mp, const MeJob* jobs, int nJobs, const int32_t* tileJob, const int32_t* tileIdx, int nTiles,
+                          uint32_t* out, cudaStream_t st, int* launches);
+
+}  // namespace cucd

@@ -1,0 +1,221 @@
+// rmd_kernels.cu - intra rough-mode-decision cost tables on sm_100a.
+//
+// One CTA of 256 threads per chunk (see rmd_chunk.cuh): borders are built cooperatively in shared
+// memory, every lane keeps its 8x8 source tile in registers, the 35 modes are spread over the 8 warps
+// (mode is warp-uniform), predictions and Hadamard butterflies stay in registers, per-PU costs are
+// accumulated in shared memory and leave the SM as one coalesced block of 35*PUS uint32.
+// Replaces, per PU, the reference loop TEncSearch.cpp:2327-2361 (initAdiPatternChType ->
+// predIntraAng x35 -> xGetHADs).
+#include <cuda_runtime.h>
+#include "rmd_chunk.cuh"
+#include "kernels.h"
+
+namespace cucd {
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+template <int LOG2N, bool FRAME>
+__device__ __forceinline__ void rmd_body(const int chunk, const FrameSource& fs, const BatchSource& bs, const int bitDepth, const int strong) {
+  typedef Geo<LOG2N> G;
+  constexpr int N = G::N;
+  SmemView<LOG2N> sm; sm.base = smem_raw;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- chunk placement --------------------------------------------------------------------
+  int pic = 0, ctu = 0, ctuX = 0, ctuY = 0;
+  const int16_t* orgPic = nullptr; const int16_t* recPic = nullptr;
+  if (FRAME) {
+    pic = chunk / fs.ctusPerPic; ctu = chunk - pic * fs.ctusPerPic;
+    ctuX = (ctu % fs.ctusPerRow) * 64; ctuY = (ctu / fs.ctusPerRow) * 64;
+    orgPic = fs.org + (size_t)pic * fs.orgPicStride;
+    recPic = fs.rec + (size_t)pic * fs.recPicStride;
+  }
+
+  // ---- phase A: validity + unfiltered linear borders --------------------------------------
+  for (int p = tid; p < G::PUS; p += kRmdThreads) {
+    bool ok;
+    if (FRAME) { int px, py; demorton(p, px, py); ok = (ctuX + (px + 1) * N <= fs.W) && (ctuY + (py + 1) * N <= fs.H); }
+    else ok = chunk * G::PUS + p < bs.count;
+    sm.valid()[p] = ok ? 1 : 0;
+  }
+  if (FRAME) {
+    border_gather_frame<LOG2N>(tid, kRmdThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, sm.lin(), sm.flags());
+  } else {
+    const int first = chunk * G::PUS;
+    const int npu = min(G::PUS, bs.count - first);
+    for (int idx = tid; idx < npu * (4 * N + 1); idx += kRmdThreads) {
+      const int p = idx / (4 * N + 1), i = idx - p * (4 * N + 1);
+      sm.lin()[p * G::LIN + i] = bs.border[(size_t)bs.pus[first + p].borderOff + i];
+    }
+  }
+  __syncthreads();
+  if (FRAME) {
+    border_substitute<LOG2N>(tid, kRmdThreads, bitDepth, sm.lin(), sm.flags());
+    __syncthreads();
+  }
+  // ---- phase C: ascending ref arrays, smoothed copies, DC ---------------------------------
+  border_derive<LOG2N>(tid, kRmdThreads, bitDepth, strong, sm.lin(), sm.arrs());
+  border_pad<LOG2N>(tid, kRmdThreads, sm.arrs());
+  __syncthreads();
+  border_dc<LOG2N>(tid, kRmdThreads, sm.arrs(), sm.dc());
+  for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) sm.acc()[i] = 0;   // aliases lin/flags: derive is done
+  __syncthreads();
+
+  // ---- phase E: modes ----------------------------------------------------------------------
+  {
+    const int cls = warp_class(warp), half = warp_half(warp), par = warp & 1;
+    LaneGeo<LOG2N> lg; lg.init(half, lane);
+    const bool ok = sm.valid()[lg.pu] != 0;     // N = 4: the four PUs of a region share validity (W, H multiples of 8)
+    Tile src;
+    if (ok) {
+      Tile raw;
+      if (FRAME) {
+        int px, py;
+        if constexpr (LOG2N == 2) { demorton(lg.pu >> 2, px, py); px *= 8; py *= 8; }
+        else { demorton(lg.pu, px, py); px = px * N + lg.tx0; py = py * N + lg.ty0; }
+        tile_load(raw, orgPic + (size_t)(ctuY + py) * fs.orgStride + ctuX + px, fs.orgStride);
+      } else {
+        if constexpr (LOG2N == 2) {
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            const bool okS = chunk * G::PUS + lg.pu + s < bs.count;
+            const int16_t* base = bs.org + (okS ? (size_t)bs.pus[chunk * G::PUS + lg.pu + s].orgOff : 0);
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+              uint2 v = make_uint2(0u, 0u);
+              if (okS) v = *reinterpret_cast<const uint2*>(base + y * 4);
+              raw.r[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 0] = v.x;
+              raw.r[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 1] = v.y;
+            }
+          }
+        } else {
+          const int16_t* base = bs.org + (size_t)bs.pus[chunk * G::PUS + lg.pu].orgOff;
+          tile_load(raw, base + lg.ty0 * N + lg.tx0, N);
+        }
+      }
+      if (cls == 0) src = raw;
+      else if constexpr (LOG2N == 2) tile_transpose4x4(raw, src);
+      else tile_transpose8(raw, src);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; k++) src.r[k] = 0;
+    }
+
+    const int nModes = class_num_modes(cls);
+    for (int i = par; i < nModes; i += 2) {
+      const int mode = class_mode(cls, i);
+      const bool neg = mode >= 2 && mode_angle(mode) < 0;
+      if (neg) {
+        if (ok) lane_build_ext<LOG2N>(sm, warp, lg, cls, mode);
+        __syncwarp();
+      }
+      if constexpr (LOG2N == 2) {
+        if (ok) {
+          uint32_t c4[4];
+          lane_eval_region4(sm, warp, lg, cls, mode, bitDepth, src, c4);
+#pragma unroll
+          for (int s = 0; s < 4; s++) sm.acc()[(lg.pu + s) * kNumModes + mode] = c4[s];
+        }
+      } else {
+        uint32_t v = 0;
+        if (ok) v = lane_eval_tile<LOG2N>(sm, warp, lg, cls, mode, bitDepth, src);
+        constexpr int LPP = G::TILES_PER_PU < 32 ? G::TILES_PER_PU : 32;
+#pragma unroll
+        for (int m = 1; m < LPP; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (ok && (lane % LPP) == 0) {
+          if (G::TILES_PER_PU > 32) atomicAdd(&sm.acc()[lg.pu * kNumModes + mode], v);
+          else sm.acc()[lg.pu * kNumModes + mode] = v;
+        }
+      }
+      if (neg) __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- phase F: coalesced cost-table store --------------------------------------------------
+  const int shift = bitDepth - 8;     // xGetHADs' final DISTORTION_PRECISION_ADJUSTMENT, TComRdCost.cpp:1603
+  if (FRAME) {
+    uint32_t* o = fs.out + ((size_t)chunk * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
+    for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) {
+      const int p = i / kNumModes;
+      o[i] = sm.valid()[p] ? (sm.acc()[i] >> shift) : 0xffffffffu;
+    }
+  } else {
+    const int first = chunk * G::PUS;
+    for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) {
+      const int p = i / kNumModes, m = i - p * kNumModes;
+      if (sm.valid()[p]) bs.out[(size_t)bs.pus[first + p].outIndex * kNumModes + m] = sm.acc()[i] >> shift;
+    }
+  }
+}
+
+// Frame (replay) mode: ONE launch covers every (picture, CTU, depth); the five depths of a CTU are
+// neighbouring CTAs so that its source tile and border rows are hit in L2.
+__global__ void __launch_bounds__(kRmdThreads, 2)
+rmd_frame_kernel(const FrameSource fs, const int bitDepth, const int strong) {
+  const BatchSource bs = {};
+  const int chunk = blockIdx.x / 5, depth = blockIdx.x - chunk * 5;
+  switch (depth) {
+    case 0: rmd_body<6, true>(chunk, fs, bs, bitDepth, strong); break;
+    case 1: rmd_body<5, true>(chunk, fs, bs, bitDepth, strong); break;
+    case 2: rmd_body<4, true>(chunk, fs, bs, bitDepth, strong); break;
+    case 3: rmd_body<3, true>(chunk, fs, bs, bitDepth, strong); break;
+    default: rmd_body<2, true>(chunk, fs, bs, bitDepth, strong); break;
+  }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(kRmdThreads, 2)
+rmd_batch_kernel(const BatchSource bs, const int bitDepth, const int strong) {
+  const FrameSource fs = {};
+  rmd_body<LOG2N, false>(blockIdx.x, fs, bs, bitDepth, strong);
+}
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int kFrameSmem = cmax(cmax(cmax(Smem<2>::TOTAL, Smem<3>::TOTAL), cmax(Smem<4>::TOTAL, Smem<5>::TOTAL)), Smem<6>::TOTAL);
+
+cudaError_t launch_rmd_frames(const FrameSource& fs, int nPics, int bitDepth, int strong, cudaStream_t st, int* launches) {
+  const int chunks = nPics * fs.ctusPerPic;
+  if (chunks <= 0) return cudaSuccess;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rmd_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrameSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  rmd_frame_kernel<<<chunks * 5, kRmdThreads, kFrameSmem, st>>>(fs, bitDepth, strong);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+template <int LOG2N>
+static cudaError_t launch_batch(int chunks, const BatchSource& bs, int bitDepth, int strong, cudaStream_t st) {
+  constexpr int bytes = Smem<LOG2N>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rmd_batch_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  rmd_batch_kernel<LOG2N><<<chunks, kRmdThreads, bytes, st>>>(bs, bitDepth, strong);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rmd_batch(int log2n, const BatchSource& bs, int bitDepth, int strong, cudaStream_t st, int* launches) {
+  if (bs.count <= 0) return cudaSuccess;
+  const int n = 1 << log2n, pus = 4096 / (n * n);
+  const int chunks = (bs.count + pus - 1) / pus;
+  cudaError_t e;
+  switch (log2n) {
+    case 2: e = launch_batch<2>(chunks, bs, bitDepth, strong, st); break;
+    case 3: e = launch_batch<3>(chunks, bs, bitDepth, strong, st); break;
+    case 4: e = launch_batch<4>(chunks, bs, bitDepth, strong, st); break;
+    case 5: e = launch_batch<5>(chunks, bs, bitDepth, strong, st); break;
+    case 6: e = launch_batch<6>(chunks, bs, bitDepth, strong, st); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e == cudaSuccess && launches) *launches += 1;
+  return e;
+}
+
+}  // namespace cucd

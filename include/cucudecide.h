@@ -1,0 +1,158 @@
+/* cucudecide.h - C ABI of libcucudecide.so, the B200 (sm_100a) CU-decision cost engine.
+ *
+ * Drop-in for the data-parallel cost arithmetic of the HM-16.3 based Fast-CU-Decision-HEVC encoder.
+ * The reference has no plugin/FFI layer (its hot path is direct C++ member calls plus the
+ * TComRdCost::m_afpDistortFunc table, TComRdCost.h:109), so every entry point names the reference
+ * call site (file:line under the reference tree) it replaces.  INTEGRATION.md shows the few lines a
+ * maintainer adds to the reference to call them.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns 0 (CUCD_OK) or a negative cucd_status;
+ *     cucd_last_error(h) gives the text.  HM's own convention is assert/exit(1)
+ *     (CommonDef.h:141-164): the shim turns a non-zero return into FATAL_ERROR_0.
+ *   - samples are HM `Pel` = int16_t (TypeDef.h:769) with a caller-given stride in samples; luma only.
+ *   - the caller owns every host buffer; the library owns device memory, pinned staging and streams.
+ *   - a handle belongs to one encoder instance and one CUDA device; it is not thread-safe.
+ *   - cost tables are uint32_t[35] per PU, index = HEVC intra mode, value = what
+ *     distParam.DistFunc returns at TEncSearch.cpp:2339 (Hadamard SATD >> (bitDepth-8)).
+ *   - "border" = the unfiltered reference samples of a PU as a linear array of 4N+1 int16:
+ *     [0..2N-1] left column from the below-left end up to the top, [2N] the top-left corner,
+ *     [2N+1..4N] the above row left to right (row 0 / column 0 of m_piYuvExt[Y][UNFILTERED],
+ *     TComPattern.cpp:155-163, re-ordered).
+ *   - PU order inside a CTU's 341-entry table: depth-major (64,32,16,8,4), z-order inside a depth
+ *     (= HM's absPartIdx order).
+ */
+#ifndef CUCUDECIDE_H
+#define CUCUDECIDE_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUCD_NUM_INTRA_MODES 35
+#define CUCD_PUS_PER_CTU 341
+#define CUCD_ABI_VERSION 1
+
+typedef enum {
+  CUCD_OK = 0,
+  CUCD_ERR_INVALID = -1,      /* bad argument                                  */
+  CUCD_ERR_UNSUPPORTED = -2,  /* e.g. bit depth > 10, CTU size != 64           */
+  CUCD_ERR_CUDA = -3,         /* a CUDA call failed; see cucd_last_error       */
+  CUCD_ERR_NOMEM = -4,
+  CUCD_ERR_NO_DEVICE = -5     /* no usable sm_100 device: there is NO CPU path */
+} cucd_status;
+
+typedef struct cucd_handle cucd_handle;
+
+/* replaces nothing 1:1; created where TEncTop::create() builds the encoder (TEncTop.cpp:106) */
+typedef struct {
+  int width, height;           /* luma picture size, multiples of 8 (min CU size)                 */
+  int bit_depth;               /* internal luma bit depth, 8..10                                  */
+  int ctu_size;                /* 64                                                              */
+  int max_depth;               /* 4: CU 64..8, PU 4x4 through NxN                                 */
+  int strong_intra_smoothing;  /* SPS flag (TComPattern.cpp:195)                                  */
+  int device;                  /* CUDA device ordinal                                             */
+  int max_pictures;            /* pictures one cuCUDecide_frames call may carry (>= 1)            */
+  int host_threads;            /* threads for the host-side TCM fit, 0 = hardware concurrency     */
+} cucd_config;
+
+int cucd_abi_version(void);
+int cucd_create(const cucd_config* cfg, cucd_handle** out);
+int cucd_destroy(cucd_handle* h);
+const char* cucd_last_error(const cucd_handle* h);   /* h may be NULL: error of the last failed create */
+/* kernels launched by this handle so far (what bench.py reports as gpu_launches) */
+long long cucd_launch_count(const cucd_handle* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * S1 + S4 (+ frame-replay S2): one picture, or a batch of pictures.
+ * Replaces TEncGOP.cpp:1095-1096 -> TEncSlice::getOutlierWithDCT (TEncSlice.cpp:878-1173), the
+ * per-CU OBF block sums of TEncCu.cpp:589-600, TEncCu::updateCtuDataISlice (TEncCu.cpp:1874-1893)
+ * and, when rec/rmd_cost are given, the full enumeration of the RMD loop TEncSearch.cpp:2327-2361
+ * over all 341 PUs of every CTU with borders taken from `rec` under z-scan availability
+ * (replay / throughput mode).  Any output pointer may be NULL = not wanted.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int16_t* obf;            /* (W/4)*(H/4), row-major: outlier AC coefficients per 4x4 block (0..15)       */
+  int16_t* outlier;        /* W*H, row-major: |kept coefficient| / 100 at its coefficient position        */
+  double*  yc;             /* 16: outlier threshold per frequency (index 0 unused)                        */
+  int32_t* num_obf[4];     /* depth d: (W/s)*(H/s) with s = 64>>d: Num_OBF of every whole CU              */
+  int32_t* n_outlier[4];   /* same shape: N_Outlier                                                       */
+  int32_t* ctu_src_had;    /* one per CTU: updateCtuDataISlice's iSumHad                                  */
+  uint32_t* rmd_cost;      /* nCtu*341*35: SATD tables; 0xFFFFFFFF for PUs not inside the picture         */
+} cucd_frame_out;
+
+int cuCUDecide_frame(cucd_handle* h, const int16_t* orgY, int strideY, const int16_t* recY, int strideRec, int poc,
+                     cucd_frame_out* out);
+int cuCUDecide_frames(cucd_handle* h, int nPics, const int16_t* const* orgY, int strideY, const int16_t* const* recY,
+                      int strideRec, cucd_frame_out* outs);
+
+/* ------------------------------------------------------------------------------------------------
+ * S2: intra rough mode decision for a batch of PUs with caller-supplied borders.
+ * Replaces the body of the loop TEncSearch.cpp:2327-2361 minus xModeBitsIntra: for PU i,
+ * sad[i*35 + m] = predIntraAng(m) + xGetHADs.  PUs may have mixed sizes; org holds the source
+ * blocks back to back (N*N each, row-major), border the 4N+1 arrays back to back, in PU order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint8_t log2_size;        /* 2..6 */
+  uint8_t reserved[3];
+} cucd_pu_desc;
+int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, const int16_t* org, const int16_t* border,
+                         uint32_t* sad);
+
+/* ------------------------------------------------------------------------------------------------
+ * S3: integer motion estimation.
+ * cucd_set_ref_picture  uploads a reconstructed reference plane with its replicated margins
+ *                       (TComPicYuv layout: TComPicYuv.cpp:77-101, extendPicBorder :191).
+ * cucd_set_cur_picture  uploads the source plane the PUs are cut from.
+ * cucd_me_sad_surface   replaces m_cDistParam.DistFunc at TEncSearch.cpp:421 / :3924 for every
+ *                       integer mv of a window: out[off_i + (mvy-top)*(right-left+1) + (mvx-left)]
+ *                       = xGetSAD*(cur PU, ref + mv) with iSubShift = sub_shift; off_i = sum of the
+ *                       previous PUs' window sizes.  The host adds getCost(mv).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int x, y, w, h;            /* PU position and size in luma samples */
+  int ref_idx;               /* slot given to cucd_set_ref_picture    */
+  int left, right, top, bottom; /* inclusive integer MV window (iSrchRngHorLeft.. of xTZSearch) */
+  int sub_shift;             /* DistParam::iSubShift (1 when FEN and rows > 8, TEncSearch.cpp:350-356) */
+} cucd_me_desc;
+int cucd_set_ref_picture(cucd_handle* h, int ref_idx, const int16_t* recY, int stride, int marginX, int marginY);
+int cucd_set_cur_picture(cucd_handle* h, const int16_t* orgY, int stride);
+int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident variants (inputs already in HBM, outputs stay in HBM): what a caller that keeps
+ * pictures on the GPU uses, and what bench.py times for the kernel-only figure.  Pointers are
+ * device pointers; `stream` is a cudaStream_t (NULL = default stream).  No host synchronisation.
+ * ---------------------------------------------------------------------------------------------- */
+/* org/rec: nPics planes, picture p at base + p*picStride samples, rows `stride` samples apart.
+ * rmd_cost: nPics*nCtu*341*35 uint32. */
+int cucd_dev_rmd_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                        const int16_t* d_rec, long long recPicStride, int recStride, uint32_t* d_rmd_cost);
+/* pass 1 of the feature path: d_hist = nPics*16*4096 uint32 histograms of |coeff/8| */
+int cucd_dev_feature_hist(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                          uint32_t* d_hist);
+/* pass 2: d_thr = nPics*16 int32 thresholds (Yc*8); outputs tight per picture as in cucd_frame_out */
+int cucd_dev_feature_obf(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                         const int32_t* d_thr, int16_t* d_obf, int16_t* d_outlier, int32_t* const d_num_obf[4],
+                         int32_t* const d_n_outlier[4], int32_t* d_ctu_src_had);
+/* the whole frame path on device-resident pictures, enqueued on `stream`: feature pass 1, RMD replay,
+ * host TCM fit (the only host synchronisation: it waits for the pass-1 histograms), feature pass 2.
+ * All outputs are device pointers, batch-contiguous (picture p at p * per-picture size), any may be
+ * NULL except that d_rec and d_rmd_cost go together.  yc_host: nPics*16 doubles on the host or NULL. */
+typedef struct {
+  int16_t* obf; int16_t* outlier;
+  int32_t* num_obf[4]; int32_t* n_outlier[4];
+  int32_t* ctu_src_had;
+  uint32_t* rmd_cost;
+} cucd_dev_out;
+int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                    const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
+/* the host-side fit that sits between the two passes (TEncSlice.cpp:291-392): hist = 16*4096 counts
+ * of ONE picture, nBlocks = (W/4)*(H/4); writes yc[16] and thr[16] */
+int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -257,7 +257,7 @@ void oracle_rmd_frame(int bitDepth, int strong, const int16_t* org, int os, cons
       int z;
       for (z = 0; z < cnt; z++, pu++) {
         int px = 0, py = 0, bit, m;
-        uint8_t flags[33]; int16_t border[4 * 64 + 1];
+        uint8_t flags[65]; int16_t border[4 * 64 + 1];
         for (bit = 0; bit < d; bit++) { px |= ((z >> (2 * bit)) & 1) << bit; py |= ((z >> (2 * bit + 1)) & 1) << bit; }
         if (cx + (px + 1) * n > W || cy + (py + 1) * n > H) { for (m = 0; m < 35; m++) o[pu * 35 + m] = 0xFFFFFFFFu; continue; }
         oracle_neighbour_flags(cx + px * n, cy + py * n, n, W, H, flags);

@@ -1,0 +1,145 @@
+"""Shared helpers of the test-suite: loaders for the checker libraries and seeded synthetic content.
+
+oracle/libcucd_oracle.so  - the plain-C restatement (the checker)
+oracle/_ref/libhmref.so   - the reference's own compiled functions (only where it was built)
+tests/emul/librmd_emul.so - CPU replay of the CUDA kernels' per-thread code
+"""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+PKG = "fast-cu-decision-hevc_b200"
+
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int32)
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+f64p = C.POINTER(C.c_double)
+
+
+def P(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def load_oracle():
+    d = os.path.join(ROOT, "oracle")
+    so = os.path.join(d, "libcucd_oracle.so")
+    if not _newer(so, [os.path.join(d, "cucd_oracle.c"), os.path.join(d, "cucd_oracle.h")]):
+        subprocess.run(["make", "-C", d, "libcucd_oracle.so"], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.oracle_satd.restype = C.c_uint32
+    lib.oracle_sad.restype = C.c_uint32
+    lib.oracle_tcm_yc.restype = C.c_double
+    return lib
+
+
+def load_hmref():
+    so = os.path.join(ROOT, "oracle", "_ref", "libhmref.so")
+    if not os.path.exists(so):
+        return None
+    lib = C.CDLL(so)
+    lib.hmref_hads.restype = C.c_uint32
+    lib.hmref_sad.restype = C.c_uint32
+    lib.hmref_init(8)
+    return lib
+
+
+def load_emul():
+    d = os.path.join(ROOT, "tests", "emul")
+    so = os.path.join(d, "librmd_emul.so")
+    csrc = os.path.join(ROOT, PKG, "csrc")
+    srcs = [os.path.join(d, "rmd_emul.cpp")] + [os.path.join(csrc, f) for f in ("rmd_core.cuh", "rmd_chunk.cuh", "feature_core.cuh")]
+    if not _newer(so, srcs):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I" + csrc, "-o", so, srcs[0]],
+                       check=True, capture_output=True)
+    return C.CDLL(so)
+
+
+def load_package():
+    return importlib.import_module(PKG)
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded synthetic content
+# ---------------------------------------------------------------------------------------------------
+def textured_plane(W, H, bit_depth=8, seed=20261018, t=0):
+    """The "textured motion" luma of SURVEY.md 8d: 8x8-blocky random texture translated (2,1) px per
+    frame + two low-frequency sinusoids + uniform noise, clipped; scaled for >8 bit."""
+    rng = np.random.default_rng(seed)
+    field = rng.integers(0, 256, (H // 8 + 2 + 16, W // 8 + 2 + 32)).astype(np.float64)
+    tex = np.kron(field, np.ones((8, 8)))[t: t + H, 2 * t: 2 * t + W]
+    x = np.arange(W)[None, :]
+    y = np.arange(H)[:, None]
+    noise = np.random.default_rng(seed + 1000 + t).uniform(-6, 6, (H, W))
+    Y = 0.6 * tex + 30 + 20 * np.sin((x + 3 * t) / 37.0) + 15 * np.cos((y - 2 * t) / 29.0) + noise
+    Y = np.clip(np.rint(Y), 0, 255).astype(np.int64)
+    if bit_depth > 8:
+        sh = bit_depth - 8
+        Y = (Y << sh) + np.random.default_rng(seed + 2000 + t).integers(0, 1 << sh, (H, W))
+    return Y.astype(np.int16)
+
+
+def pseudo_recon(org, bit_depth=8, seed=7):
+    """A stand-in reconstruction: the source low-passed a little plus small noise (what a codec's
+    reconstruction looks like statistically), so that borders differ from the source."""
+    o = org.astype(np.int32)
+    pad = np.pad(o, 1, mode="edge")
+    blur = (pad[:-2, 1:-1] + pad[2:, 1:-1] + pad[1:-1, :-2] + pad[1:-1, 2:] + 4 * o + 4) >> 3
+    noise = np.random.default_rng(seed).integers(-2, 3, o.shape)
+    return np.clip(blur + noise, 0, (1 << bit_depth) - 1).astype(np.int16)
+
+
+def oracle_rmd_frame(lib, org, rec, bit_depth, strong=1, ctu_begin=0, ctu_end=None):
+    H, W = org.shape
+    nctu = ((W + 63) // 64) * ((H + 63) // 64)
+    if ctu_end is None:
+        ctu_end = nctu
+    org = np.ascontiguousarray(org)
+    rec = np.ascontiguousarray(rec)
+    out = np.zeros((ctu_end - ctu_begin, 341, 35), np.uint32)
+    lib.oracle_rmd_frame(bit_depth, strong, P(org, i16p), W, P(rec, i16p), W, W, H, ctu_begin, ctu_end, P(out, u32p))
+    return out
+
+
+def oracle_outlier_frame(lib, org, bit_depth):
+    H, W = org.shape
+    org = np.ascontiguousarray(org)
+    obf = np.zeros((H // 4, W // 4), np.int16)
+    outl = np.zeros((H, W), np.int16)
+    yc = np.zeros(16, np.float64)
+    lib.oracle_outlier_frame(bit_depth, P(org, i16p), W, W, H, P(obf, i16p), P(outl, i16p), P(yc, f64p))
+    return obf, outl, yc
+
+
+def oracle_cu_sums(lib, obf, W, H, depth):
+    s = 64 >> depth
+    a = np.zeros((H // s, W // s), np.int32)
+    b = np.zeros((H // s, W // s), np.int32)
+    obf = np.ascontiguousarray(obf)
+    if a.size:
+        lib.oracle_cu_sums(P(obf, i16p), W, H, depth, P(a, i32p), P(b, i32p))
+    return a, b
+
+
+def oracle_ctu_src_had(lib, org):
+    H, W = org.shape
+    org = np.ascontiguousarray(org)
+    out = np.zeros(((W + 63) // 64) * ((H + 63) // 64), np.int32)
+    lib.oracle_ctu_src_had(P(org, i16p), W, W, H, P(out, i32p))
+    return out

@@ -1,0 +1,71 @@
+"""CPU replay of the CUDA kernels' per-thread code (tests/emul, built from the same __host__ __device__
+headers the sm_100a kernels compile) against the golden vectors and the oracle.  Lets the kernel
+arithmetic be checked where there is no GPU; the -m gpu tests check the real kernels."""
+import numpy as np
+import pytest
+
+from _util import P, golden, i16p, i32p, u32p, oracle_outlier_frame, oracle_rmd_frame, pseudo_recon, textured_plane
+
+
+@pytest.mark.parametrize("clip", ["ai8", "ai10"])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64])
+def test_batch_kernel_code_vs_golden(emul, clip, n):
+    g = golden(f"rmd_{clip}.npz")
+    bd = int(g["meta"][2])
+    org = np.ascontiguousarray(g[f"n{n}_org"])
+    unf = np.ascontiguousarray(g[f"n{n}_unf"])
+    out = np.zeros((len(org), 35), np.uint32)
+    assert emul.emul_rmd_batch(bd, 1, int(np.log2(n)), len(org), P(org, i16p), P(unf, i16p), P(out, u32p)) == 0
+    assert np.array_equal(out, g[f"n{n}_sad"])
+
+
+@pytest.mark.parametrize("bd,W,H", [(8, 200, 136), (10, 136, 72)])
+def test_frame_kernel_code_vs_oracle(emul, oracle, bd, W, H):
+    org = textured_plane(W, H, bd, seed=5)
+    rec = pseudo_recon(org, bd)
+    rec[:, : W // 2] = (np.arange(H)[:, None] // 3 + np.arange(W // 2)[None, :] // 5 + 40).astype(np.int16)  # flat: strong smoothing
+    want = oracle_rmd_frame(oracle, org, rec, bd)
+    S = (W + 7) // 8 * 8
+    orgp = np.zeros((H, S), np.int16)
+    orgp[:, :W] = org
+    got = np.zeros_like(want)
+    emul.emul_rmd_frame(bd, 1, P(orgp, i16p), S, P(rec, i16p), W, W, H, 0, want.shape[0], P(got, u32p))
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_extreme_values_do_not_overflow_packed_lanes(emul, oracle, bd):
+    """worst case for the 16-bit packed butterflies: full-scale checkerboards against 0 / max borders"""
+    hi = (1 << bd) - 1
+    for n in (4, 8, 16, 32, 64):
+        yy, xx = np.mgrid[0:n, 0:n]
+        pats = [np.where((xx + yy) & 1, hi, 0), np.where(xx & 1, hi, 0), np.full((n, n), hi), np.where((xx // 4 + yy // 4) & 1, hi, 0)]
+        borders = [np.zeros(4 * n + 1), np.full(4 * n + 1, hi), np.where(np.arange(4 * n + 1) & 1, hi, 0)]
+        org = np.concatenate([p.ravel() for p in pats for _ in borders]).astype(np.int16)
+        brd = np.concatenate([b for _ in pats for b in borders]).astype(np.int16)
+        cnt = len(pats) * len(borders)
+        got = np.zeros((cnt, 35), np.uint32)
+        emul.emul_rmd_batch(bd, 1, int(np.log2(n)), cnt, P(org, i16p), P(brd, i16p), P(got, u32p))
+        for k in range(cnt):
+            want = np.zeros(35, np.uint32)
+            o = np.ascontiguousarray(org[k * n * n:(k + 1) * n * n])
+            b = np.ascontiguousarray(brd[k * (4 * n + 1):(k + 1) * (4 * n + 1)])
+            oracle.oracle_rmd_pu(bd, n, 1, P(o, i16p), n, P(b, i16p), P(want, u32p))
+            assert np.array_equal(got[k], want), (n, k)
+
+
+@pytest.mark.parametrize("clip", ["ai8", "ai10"])
+def test_feature_kernel_code_vs_golden(emul, cucd, clip):
+    """DCT + histogram (pass 1) -> host TCM fit of the library -> threshold/OBF/Outlier (pass 2)"""
+    g = golden(f"obf_{clip}.npz")
+    _, W, H, bd = [int(v) for v in g["f0_meta"]]
+    org = np.ascontiguousarray(g["f0_org"])
+    hist = np.zeros(16 * 4096, np.uint32)
+    emul.emul_feature_hist(bd, P(org, i16p), W, W, H, P(hist, u32p))
+    yc, thr = cucd.tcm_fit(hist, (W // 4) * (H // 4))
+    assert np.array_equal(yc[1:], g["f0_yc"][1:])
+    obf = np.zeros((H // 4, W // 4), np.int16)
+    outl = np.zeros((H, W), np.int16)
+    emul.emul_feature_obf(bd, P(org, i16p), W, W, H, P(thr, i32p), P(obf, i16p), P(outl, i16p))
+    assert np.array_equal(obf, g["f0_obf"])
+    assert np.array_equal(outl, g["f0_outlier"])

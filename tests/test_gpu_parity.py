@@ -1,0 +1,228 @@
+"""Parity of the CUDA path, called through the C ABI (libcucudecide.so), against the golden vectors of
+the real reference encoder and against the oracle on seeded inputs.  Everything is integer work:
+the bar is bit-exact."""
+import numpy as np
+import pytest
+
+from _util import (P, golden, i16p, u32p, oracle_ctu_src_had, oracle_cu_sums, oracle_outlier_frame, oracle_rmd_frame,
+                   pseudo_recon, textured_plane)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng8(cucd):
+    e = cucd.Engine(416, 240, bit_depth=8, max_pictures=3)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng10(cucd):
+    e = cucd.Engine(416, 240, bit_depth=10, max_pictures=2)
+    yield e
+    e.close()
+
+
+# ---- S2: batched RMD with caller-supplied borders vs the encoder's own uiSad[35] --------------------
+@pytest.mark.parametrize("clip", ["ai8", "ai10"])
+def test_rmd_batch_vs_reference_encoder_dump(eng8, eng10, clip):
+    g = golden(f"rmd_{clip}.npz")
+    eng = eng8 if clip == "ai8" else eng10
+    sizes, orgs, brds, want = [], [], [], []
+    for n in (4, 8, 16, 32, 64):
+        k = len(g[f"n{n}_org"])
+        sizes += [int(np.log2(n))] * k
+        orgs.append(g[f"n{n}_org"].ravel()); brds.append(g[f"n{n}_unf"].ravel()); want.append(g[f"n{n}_sad"])
+    # interleave the sizes so that the library's size bucketing and output scatter are exercised
+    order = np.random.default_rng(3).permutation(len(sizes))
+    sizes = np.array(sizes)
+    org_list, brd_list, o_off, b_off = [], [], 0, 0
+    flat_org, flat_brd = np.concatenate(orgs), np.concatenate(brds)
+    offs_o, offs_b = [], []
+    for s in sizes:
+        n = 1 << s
+        offs_o.append(o_off); offs_b.append(b_off)
+        o_off += n * n; b_off += 4 * n + 1
+    for i in order:
+        n = 1 << sizes[i]
+        org_list.append(flat_org[offs_o[i]: offs_o[i] + n * n]); brd_list.append(flat_brd[offs_b[i]: offs_b[i] + 4 * n + 1])
+    got = eng.intra_rmd_batch(sizes[order], np.concatenate(org_list), np.concatenate(brd_list))
+    assert np.array_equal(got, np.concatenate(want)[order])
+
+
+def test_rmd_batch_edge_cases(eng8, oracle):
+    assert eng8.intra_rmd_batch([], np.zeros(0, np.int16), np.zeros(0, np.int16)).shape == (0, 35)
+    rng = np.random.default_rng(11)
+    for n, cnt in ((4, 1), (4, 5), (4, 257), (8, 65), (16, 17), (32, 5), (64, 3)):   # ragged: not a multiple of a chunk
+        org = rng.integers(0, 256, (cnt, n * n)).astype(np.int16)
+        brd = rng.integers(0, 256, (cnt, 4 * n + 1)).astype(np.int16)
+        got = eng8.intra_rmd_batch([int(np.log2(n))] * cnt, org, brd)
+        for k in range(cnt):
+            want = np.zeros(35, np.uint32)
+            oracle.oracle_rmd_pu(8, n, 1, P(org[k], i16p), n, P(brd[k], i16p), P(want, u32p))
+            assert np.array_equal(got[k], want), (n, k)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_rmd_batch_extreme_values(cucd, oracle, bd):
+    hi = (1 << bd) - 1
+    with cucd.Engine(64, 64, bit_depth=bd) as eng:
+        for n in (4, 8, 16, 32, 64):
+            yy, xx = np.mgrid[0:n, 0:n]
+            pats = [np.where((xx + yy) & 1, hi, 0), np.where(xx & 1, hi, 0), np.full((n, n), hi), np.zeros((n, n))]
+            borders = [np.zeros(4 * n + 1), np.full(4 * n + 1, hi), np.where(np.arange(4 * n + 1) & 1, hi, 0)]
+            org = np.stack([p.ravel() for p in pats for _ in borders]).astype(np.int16)
+            brd = np.stack([b for _ in pats for b in borders]).astype(np.int16)
+            got = eng.intra_rmd_batch([int(np.log2(n))] * len(org), org, brd)
+            for k in range(len(org)):
+                want = np.zeros(35, np.uint32)
+                oracle.oracle_rmd_pu(bd, n, 1, P(org[k], i16p), n, P(brd[k], i16p), P(want, u32p))
+                assert np.array_equal(got[k], want), (n, k)
+
+
+# ---- S1/S4 + replay S2 through cuCUDecide_frame(s) ----------------------------------------------------
+@pytest.mark.parametrize("clip", ["ai8", "ai10"])
+def test_frame_features_vs_reference_encoder_dump(eng8, eng10, oracle, clip):
+    g = golden(f"obf_{clip}.npz")
+    eng = eng8 if clip == "ai8" else eng10
+    nf = int(g["nframes"][0])
+    orgs = [np.ascontiguousarray(g[f"f{k}_org"]) for k in range(nf)]
+    outs = eng.frames(orgs)                    # no reconstruction plane: features only
+    for k in range(nf):
+        _, W, H, bd = [int(v) for v in g[f"f{k}_meta"]]
+        o = outs[k]
+        assert np.array_equal(o["yc"][1:], g[f"f{k}_yc"][1:])
+        assert np.array_equal(o["obf"], g[f"f{k}_obf"])
+        assert np.array_equal(o["outlier"], g[f"f{k}_outlier"])
+        cu = g[f"f{k}_cu"]
+        for depth in range(4):
+            sel = cu[cu[:, 0] == depth]
+            s = 64 >> depth
+            assert np.array_equal(o[f"num_obf{depth}"][sel[:, 2] // s, sel[:, 1] // s], sel[:, 4])
+            assert np.array_equal(o[f"n_outlier{depth}"][sel[:, 2] // s, sel[:, 1] // s], sel[:, 5])
+        assert np.array_equal(o["ctu_src_had"], oracle_ctu_src_had(oracle, orgs[k]))
+
+
+@pytest.mark.parametrize("bd,W,H", [(8, 416, 240), (10, 200, 136), (8, 64, 64), (8, 8, 8), (10, 72, 136)])
+def test_frame_replay_vs_oracle(cucd, oracle, bd, W, H):
+    """full enumeration (341 PUs x 35 modes per CTU), partial CTUs on the right and bottom edges"""
+    org = textured_plane(W, H, bd, seed=W + H)
+    rec = pseudo_recon(org, bd)
+    if W >= 128:
+        rec[:, : W // 2] = ((np.arange(H)[:, None] // 3 + np.arange(W // 2)[None, :] // 5 + 40) << (bd - 8)).astype(np.int16)
+    with cucd.Engine(W, H, bit_depth=bd) as eng:
+        out = eng.frame(org, rec)
+    want = oracle_rmd_frame(oracle, org, rec, bd)
+    assert np.array_equal(out["rmd_cost"], want)
+    obf, outl, yc = oracle_outlier_frame(oracle, org, bd)
+    assert np.array_equal(out["yc"][1:], yc[1:])
+    assert np.array_equal(out["obf"], obf)
+    assert np.array_equal(out["outlier"], outl)
+    for d in range(4):
+        a, b = oracle_cu_sums(oracle, obf, W, H, d)
+        assert np.array_equal(out[f"num_obf{d}"], a) and np.array_equal(out[f"n_outlier{d}"], b)
+    assert np.array_equal(out["ctu_src_had"], oracle_ctu_src_had(oracle, org))
+
+
+def test_frames_batch_equals_single_pictures(cucd):
+    """a batch of pictures (also larger than max_pictures -> grouped) gives what one picture at a time gives"""
+    W, H = 200, 136
+    orgs = [textured_plane(W, H, 8, seed=9, t=t) for t in range(5)]
+    recs = [pseudo_recon(o, 8, seed=t) for t, o in enumerate(orgs)]
+    with cucd.Engine(W, H, max_pictures=2) as eng:
+        batch = eng.frames(orgs, recs)
+        for t in range(5):
+            one = eng.frame(orgs[t], recs[t], poc=t)
+            for k in one:
+                assert np.array_equal(one[k], batch[t][k]), (t, k)
+
+
+def test_strong_smoothing_flag_is_honoured(cucd, oracle):
+    W, H = 128, 128
+    org = textured_plane(W, H, 8, seed=2)
+    rec = np.full((H, W), 100, np.int16) + (np.arange(W)[None, :] // 9).astype(np.int16)
+    for strong in (0, 1):
+        with cucd.Engine(W, H, strong_intra_smoothing=strong) as eng:
+            got = eng.frame(org, rec)["rmd_cost"]
+        assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8, strong=strong))
+
+
+def test_strided_host_planes(cucd, oracle):
+    """HM hands over planes with stride W+160 and an 80-sample margin (TComPicYuv.cpp:83-101)"""
+    W, H = 136, 72
+    org = textured_plane(W, H, 8, seed=4)
+    rec = pseudo_recon(org, 8)
+    big_o = np.zeros((H + 160, W + 160), np.int16); big_o[80:80 + H, 80:80 + W] = org
+    big_r = np.zeros((H + 160, W + 160), np.int16); big_r[80:80 + H, 80:80 + W] = rec
+    with cucd.Engine(W, H) as eng:
+        out = eng.frame(big_o[80:80 + H, 80:80 + W], big_r[80:80 + H, 80:80 + W])
+    assert np.array_equal(out["rmd_cost"], oracle_rmd_frame(oracle, org, rec, 8))
+
+
+def test_invalid_arguments_are_rejected(cucd):
+    with pytest.raises(cucd.CucdError):
+        cucd.Engine(100, 64)              # not a multiple of 8
+    with pytest.raises(cucd.CucdError):
+        cucd.Engine(64, 64, bit_depth=12)  # packed 16-bit butterflies are valid up to 10 bit
+    with cucd.Engine(64, 64) as eng:
+        with pytest.raises(cucd.CucdError):
+            eng.intra_rmd_batch([7], np.zeros(128 * 128, np.int16), np.zeros(513, np.int16))
+
+
+# ---- S3: integer-ME SAD ---------------------------------------------------------------------------------
+def test_me_probes_vs_reference_encoder_dump(cucd):
+    """every sampled xTZSearchHelp probe: place PU and reference block into planes, ask for the 1x1 window"""
+    g = golden("me_ldp8.npz")
+    hdr, org, ref = g["hdr"], g["org"], g["ref"]
+    W = H = 128
+    with cucd.Engine(W, H) as eng:
+        off = 0
+        for cols, rows, sub, bd, _, _, sad in hdr[:120]:
+            cols, rows = int(cols), int(rows)
+            cur = np.zeros((H, W), np.int16); refp = np.zeros((H + 16, W + 16), np.int16)
+            cur[8:8 + rows, 16:16 + cols] = org[off: off + cols * rows].reshape(rows, cols)
+            refp[8 + 8 + 3:8 + 8 + 3 + rows, 8 + 16 - 2:8 + 16 - 2 + cols] = ref[off: off + cols * rows].reshape(rows, cols)
+            off += cols * rows
+            eng.set_cur_picture(cur)
+            eng.set_ref_picture(0, refp, 8, 8)
+            s = eng.me_sad_surface([dict(x=16, y=8, w=cols, h=rows, ref_idx=0, left=-2, right=-2, top=3, bottom=3, sub_shift=int(sub))])[0]
+            assert s.shape == (1, 1) and int(s[0, 0]) == int(sad), (cols, rows, sub)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_me_surfaces_vs_oracle(cucd, oracle, bd):
+    W, H, M = 192, 128, 80
+    cur = textured_plane(W, H, bd, seed=21, t=1)
+    ref = pseudo_recon(textured_plane(W, H, bd, seed=21, t=0), bd)
+    refp = np.pad(ref, M, mode="edge")
+    descs = [dict(x=64, y=64, w=64, h=64, ref_idx=1, left=-64, right=64, top=-64, bottom=64, sub_shift=1),
+             dict(x=0, y=0, w=16, h=16, ref_idx=1, left=-72, right=8, top=-72, bottom=8, sub_shift=1),
+             dict(x=176, y=112, w=16, h=16, ref_idx=1, left=-5, right=72, top=-3, bottom=72, sub_shift=1),
+             dict(x=32, y=16, w=12, h=16, ref_idx=1, left=-7, right=9, top=-4, bottom=4, sub_shift=1),
+             dict(x=40, y=24, w=24, h=32, ref_idx=1, left=-33, right=0, top=0, bottom=9, sub_shift=1),
+             dict(x=8, y=8, w=8, h=4, ref_idx=1, left=-3, right=3, top=-3, bottom=3, sub_shift=0),
+             dict(x=8, y=8, w=4, h=8, ref_idx=1, left=0, right=0, top=0, bottom=0, sub_shift=0),
+             dict(x=64, y=32, w=48, h=64, ref_idx=1, left=-16, right=15, top=-8, bottom=7, sub_shift=1),
+             dict(x=64, y=32, w=64, h=16, ref_idx=1, left=-40, right=-9, top=-2, bottom=2, sub_shift=1),
+             dict(x=96, y=64, w=32, h=32, ref_idx=1, left=-64, right=64, top=-64, bottom=63, sub_shift=2)]
+    with cucd.Engine(W, H, bit_depth=bd) as eng:
+        eng.set_cur_picture(cur)
+        eng.set_ref_picture(1, refp, M, M)
+        got = eng.me_sad_surface(descs)
+    S = W + 2 * M
+    for d, g_ in zip(descs, got):
+        want = np.zeros_like(g_)
+        o = np.ascontiguousarray(cur[d["y"]:d["y"] + d["h"], d["x"]:d["x"] + d["w"]])
+        base = refp.ctypes.data + 2 * ((d["y"] + M) * S + d["x"] + M)
+        import ctypes as C
+        oracle.oracle_sad_surface(bd, P(o, i16p), d["w"], d["w"], d["h"], C.c_void_p(base), S, d["left"], d["right"], d["top"], d["bottom"],
+                                  d["sub_shift"], P(want, u32p))
+        assert np.array_equal(g_, want), d
+    # zero motion on identical planes is zero; window leaving the padded plane is refused
+    with cucd.Engine(W, H, bit_depth=bd) as eng:
+        eng.set_cur_picture(cur)
+        eng.set_ref_picture(0, np.pad(cur, M, mode="edge"), M, M)
+        assert int(eng.me_sad_surface([dict(x=64, y=64, w=32, h=32, ref_idx=0, left=0, right=0, top=0, bottom=0, sub_shift=1)])[0][0, 0]) == 0
+        with pytest.raises(cucd.CucdError):
+            eng.me_sad_surface([dict(x=0, y=0, w=16, h=16, ref_idx=0, left=-81, right=0, top=0, bottom=0, sub_shift=0)])

@@ -1,0 +1,114 @@
+"""The oracle against the reference's own compiled functions (oracle/_ref/libhmref.so) on seeded random
+inputs - covers what the encoder dumps cannot reach (arbitrary availability patterns, extreme sample
+values, every mode's raw prediction block).  Skipped where oracle/_ref was not built."""
+import numpy as np
+import pytest
+
+from _util import P, i16p, i32p, u8p, u32p, f64p, oracle_outlier_frame, oracle_ctu_src_had, textured_plane
+
+SIZES = [4, 8, 16, 32, 64]
+
+
+def rand_border(rng, n, bd, kind):
+    hi = (1 << bd) - 1
+    if kind == 0:
+        return rng.integers(0, hi + 1, 4 * n + 1).astype(np.int16)
+    if kind == 1:  # smooth ramp: makes strong smoothing fire
+        return np.clip(np.linspace(rng.integers(0, hi), rng.integers(0, hi), 4 * n + 1) + rng.integers(-1, 2, 4 * n + 1), 0, hi).astype(np.int16)
+    return np.full(4 * n + 1, rng.integers(0, hi + 1), np.int16)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("n", SIZES)
+def test_fill_border_random_flags(oracle, hmref, n, bd):
+    rng = np.random.default_rng(100 + n + bd)
+    S = 2 * n + 40
+    for trial in range(60):
+        rec = rng.integers(0, 1 << bd, (S, S)).astype(np.int16)
+        flags = (rng.random(n + 1) < rng.choice([0.0, 0.3, 0.7, 1.0])).astype(np.uint8)
+        if trial == 0:
+            flags[:] = 0
+        origin = rec[20:, 20:]
+        a = np.zeros(4 * n + 1, np.int16)
+        b = np.zeros(4 * n + 1, np.int16)
+        base = rec.ctypes.data + 2 * (20 * S + 20)
+        import ctypes as C
+        oracle.oracle_fill_border(bd, n, C.c_void_p(base), S, P(flags, u8p), P(a, i16p))
+        hmref.hmref_fill_border(bd, n, C.c_void_p(base), S, P(flags, u8p), P(b, i16p))
+        assert np.array_equal(a, b), (trial, flags)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("n", SIZES)
+def test_every_mode_prediction_block(oracle, hmref, n, bd):
+    rng = np.random.default_rng(200 + n + bd)
+    for trial in range(6):
+        border = rand_border(rng, n, bd, trial % 3)
+        fil = np.zeros(4 * n + 1, np.int16)
+        oracle.oracle_filter_border(bd, n, 1, P(border, i16p), P(fil, i16p))
+        for mode in range(35):
+            a = np.zeros(n * n, np.int16)
+            b = np.zeros(n * n, np.int16)
+            oracle.oracle_predict(bd, n, mode, P(border, i16p), P(fil, i16p), P(a, i16p))
+            hmref.hmref_predict(bd, n, mode, P(border, i16p), 0, 1, P(b, i16p))
+            assert np.array_equal(a, b), (trial, mode)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("n", SIZES)
+def test_rmd_pu_random(oracle, hmref, n, bd):
+    rng = np.random.default_rng(300 + n + bd)
+    for trial in range(8):
+        border = rand_border(rng, n, bd, trial % 3)
+        org = rng.integers(0, 1 << bd, n * n).astype(np.int16) if trial % 2 else np.full(n * n, (1 << bd) - 1, np.int16)
+        a = np.zeros(35, np.uint32)
+        b = np.zeros(35, np.uint32)
+        oracle.oracle_rmd_pu(bd, n, 1, P(org, i16p), n, P(border, i16p), P(a, u32p))
+        hmref.hmref_rmd_pu(bd, n, 1, P(org, i16p), n, P(border, i16p), P(b, u32p))
+        assert np.array_equal(a, b), trial
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_satd_and_sad_shapes(oracle, hmref, bd):
+    rng = np.random.default_rng(400 + bd)
+    for (w, h) in [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 8), (16, 4), (12, 16), (24, 32), (48, 64), (64, 16), (16, 64)]:
+        o = rng.integers(0, 1 << bd, (h, w)).astype(np.int16)
+        r = rng.integers(0, 1 << bd, (h, w)).astype(np.int16)
+        assert oracle.oracle_satd(bd, P(o, i16p), w, P(r, i16p), w, w, h) == hmref.hmref_hads(bd, P(o, i16p), w, P(r, i16p), w, w, h)
+        for sub in (0, 1, 2):
+            if h >> sub < 1 or (h % (1 << sub)):
+                continue
+            assert oracle.oracle_sad(bd, P(o, i16p), w, P(r, i16p), w, w, h, sub) == hmref.hmref_sad(bd, P(o, i16p), w, P(r, i16p), w, w, h, sub), (w, h, sub)
+
+
+@pytest.mark.parametrize("bd,W,H", [(8, 192, 128), (10, 136, 72)])
+def test_outlier_frame_and_src_had(oracle, hmref, bd, W, H):
+    org = textured_plane(W, H, bd, seed=31 + bd)
+    obf, outl, _ = oracle_outlier_frame(oracle, org, bd)
+    robf = np.zeros_like(obf)
+    rout = np.zeros_like(outl)
+    hmref.hmref_outlier_frame(bd, P(org, i16p), W, W, H, P(robf, i16p), P(rout, i16p))
+    assert np.array_equal(obf, robf)
+    assert np.array_equal(outl, rout)
+    had = oracle_ctu_src_had(oracle, org)
+    wc = (W + 63) // 64
+    for ctu in range(len(had)):
+        cx, cy = (ctu % wc) * 64, (ctu // wc) * 64
+        tot = 0
+        for y in range(cy, min(cy + 64, H) - 7, 8):
+            for x in range(cx, min(cx + 64, W) - 7, 8):
+                blk = np.ascontiguousarray(org[y:y + 8, x:x + 8])
+                tot += hmref.hmref_src_had8x8(P(blk, i16p), 8)
+        assert had[ctu] == tot
+
+
+def test_rmd_frame_enumeration(oracle, hmref):
+    """replay-mode enumeration (z-scan availability + fill + 35 modes) on a picture with partial CTUs"""
+    from _util import oracle_rmd_frame, pseudo_recon
+    W, H, bd = 136, 88, 8
+    org = textured_plane(W, H, bd, seed=77)
+    rec = pseudo_recon(org, bd)
+    a = oracle_rmd_frame(oracle, org, rec, bd)
+    b = np.zeros_like(a)
+    hmref.hmref_rmd_frame(bd, 1, P(org, i16p), W, P(rec, i16p), W, W, H, 0, a.shape[0], 2, P(b, u32p))
+    assert np.array_equal(a, b)
