@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py - CU-decision CTUs/s at 1080p All-Intra (BASELINE.json's metric) on N B200s of one node.
+
+A "step" is one pass of the hot path over one batch of P synthetic 1080p pictures: the per-picture
+outlier/OBF feature pass (GPU pass 1 -> host TCM fit -> GPU pass 2, per-CU block sums, per-CTU source
+Hadamard) plus the full rough-mode-decision enumeration (341 PUs x 35 modes per CTU, borders built
+from a reconstruction plane).  Workload = BASELINE.json configs[1] (1920x1080 8-bit All-Intra).
+
+  value      whole-job CTUs/s with inputs resident in HBM (cucd_dev_frames on torch's stream, CUDA events)
+  e2e        the same pass through the host-buffer C-ABI call cuCUDecide_frames: pinned host planes in,
+             every output back on the host, copies inside the timed region (wall clock around the calls)
+  roofline   the RMD kernel (the one dominant launch of a step): algorithmic bytes / its event-timed duration
+  cpu_baseline  the reference's own CPU functions (oracle/_ref/libhmref.so) or the oracle port on a bounded sample
+
+`--impl reference` times the reference's CPU implementation of the same path on the host cores.
+Multi-GPU: pictures shard across ranks (weak scaling, no collective on the data path).
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = "fast-cu-decision-hevc_b200"
+METRIC = "cu_decision_ctus_per_s_1080p_all_intra"
+ALGO_BYTES_PER_CTU = 72484          # source 8192 + borders 16552 + cost tables 47740 (int16 samples)
+
+
+def textured_plane(W, H, bit_depth, seed, t):
+    """SURVEY.md 8d 'textured motion' luma: 8x8-blocky random field translated (2,1) px/frame + two
+    sinusoids + uniform noise +-6, clipped to 8 bit (scaled with random LSBs for >8 bit)."""
+    rng = np.random.default_rng(seed)
+    field = rng.integers(0, 256, (H // 8 + 2 + 16, W // 8 + 2 + 32)).astype(np.float32)
+    tex = np.kron(field, np.ones((8, 8), np.float32))[t % 64: t % 64 + H, (2 * t) % 128: (2 * t) % 128 + W]
+    x = np.arange(W, dtype=np.float32)[None, :]
+    y = np.arange(H, dtype=np.float32)[:, None]
+    noise = np.random.default_rng(seed + 1000 + t).uniform(-6, 6, (H, W)).astype(np.float32)
+    Y = 0.6 * tex + 30 + 20 * np.sin((x + 3 * t) / 37.0) + 15 * np.cos((y - 2 * t) / 29.0) + noise
+    Y = np.clip(np.rint(Y), 0, 255).astype(np.int32)
+    if bit_depth > 8:
+        sh = bit_depth - 8
+        Y = (Y << sh) + np.random.default_rng(seed + 2000 + t).integers(0, 1 << sh, (H, W))
+    return Y.astype(np.int16)
+
+
+def pseudo_recon(org, bit_depth, seed):
+    o = org.astype(np.int32)
+    pad = np.pad(o, 1, mode="edge")
+    blur = (pad[:-2, 1:-1] + pad[2:, 1:-1] + pad[1:-1, :-2] + pad[1:-1, 2:] + 4 * o + 4) >> 3
+    noise = np.random.default_rng(seed).integers(-2, 3, o.shape)
+    return np.clip(blur + noise, 0, (1 << bit_depth) - 1).astype(np.int16)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# ---------------------------------------------------------------------------------------------------
+def load_cpu_checker():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libhmref.so")
+    if os.path.exists(ref):
+        lib = C.CDLL(ref)
+        lib.hmref_init(8)
+        return lib, "reference"
+    so = os.path.join(ROOT, "oracle", "libcucd_oracle.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "libcucd_oracle.so"], check=True, capture_output=True)
+    return C.CDLL(so), "port"
+
+
+def _feature_pass(lib, kind, org, bd):
+    """one picture through the reference's single-threaded feature pass (TEncSlice::getOutlierWithDCT)"""
+    H, W = org.shape
+    obf, outl, yc = np.zeros((H // 4, W // 4), np.int16), np.zeros((H, W), np.int16), np.zeros(16)
+    vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    if kind == "reference":
+        lib.hmref_outlier_frame(bd, vp(org), W, W, H, vp(obf), vp(outl))
+    else:
+        lib.oracle_outlier_frame(bd, vp(org), W, W, H, vp(obf), vp(outl), vp(yc))
+
+
+def cpu_path_sample(lib, kind, pics, bit_depth, threads, ctus_per_pic_limit=None):
+    """One CPU step: every picture in `pics` [(org, rec), ...] through the RMD enumeration (CTUs spread over
+    `threads` host threads inside the reference driver) and through the per-picture feature pass.  The
+    reference's feature pass is single-threaded and not re-entrant, so pictures run concurrently in
+    forked child processes (up to `threads` of them) while the parent runs the RMD enumeration.
+    Returns (ctus_per_s, seconds, ctus)."""
+    H, W = pics[0][0].shape
+    nctu_pic = ((W + 63) // 64) * ((H + 63) // 64)
+    n_ctus = nctu_pic if ctus_per_pic_limit is None else min(nctu_pic, ctus_per_pic_limit)
+
+    def vp(a):
+        return C.c_void_p(a.ctypes.data)
+    out = np.zeros((n_ctus, 341, 35), np.uint32)
+    nproc = max(1, min(threads, len(pics)))
+    sys.stdout.flush()
+    t0 = time.perf_counter()
+    kids = []
+    for k in range(nproc):
+        pid = os.fork()
+        if pid == 0:
+            try:
+                devnull = os.open(os.devnull, os.O_WRONLY)
+                os.dup2(devnull, 1)        # the reference prints diagnostics from its TCM fit
+                for i in range(k, len(pics), nproc):
+                    _feature_pass(lib, kind, pics[i][0], bit_depth)
+            finally:
+                os._exit(0)
+        kids.append(pid)
+    for org, rec in pics:
+        if kind == "reference":
+            lib.hmref_rmd_frame(bit_depth, 1, vp(org), W, vp(rec), W, W, H, 0, n_ctus, threads, vp(out))
+        else:
+            lib.oracle_rmd_frame(bit_depth, 1, vp(org), W, vp(rec), W, W, H, 0, n_ctus, vp(out))
+    for pid in kids:
+        _, status = os.waitpid(pid, 0)
+        if status != 0:
+            raise RuntimeError("a CPU feature-pass worker failed")
+    dt = time.perf_counter() - t0
+    ctus = n_ctus * len(pics)
+    return ctus / dt, dt, ctus
+
+
+def cpu_reference_run(args, steps, warmup, target_step_s=2.0):
+    """The reference's CPU implementation of the path on all host threads: returns (mean CTU/s, dict)."""
+    lib, kind = load_cpu_checker()
+    threads = (os.cpu_count() or 1) if kind == "reference" else 1
+    W, H, bd = args.width, args.height, args.bit_depth
+    base = [(textured_plane(W, H, bd, 20261018, t), None) for t in range(2)]
+    base = [(o, pseudo_recon(o, bd, t)) for t, (o, _) in enumerate(base)]
+    if kind == "reference":
+        rate, dt, _ = cpu_path_sample(lib, kind, base[:1], bd, threads)            # calibration picture
+        n_pics = int(max(1, min(64, round(target_step_s / max(dt, 1e-3)))))
+        limit = None
+    else:                                                                         # scalar port: a slice of one picture
+        n_pics, limit = 1, 48
+    pics = [base[i % len(base)] for i in range(n_pics)]
+    vals, secs, ctus = [], 0.0, 0
+    for i in range(warmup + steps):
+        v, dt, n = cpu_path_sample(lib, kind, pics, bd, threads, limit)
+        if i >= warmup:
+            vals.append(v); secs += dt; ctus += n
+    desc = (f"{steps} steps x {n_pics} picture(s) of {W}x{H}" + (f" ({limit} CTUs each)" if limit else "") +
+            f": RMD enumeration 341 PUs x 35 modes per CTU + feature pass, {ctus} CTUs in {secs:.1f} s on {threads} thread(s)")
+    return float(np.mean(vals)), {"value": float(np.mean(vals)), "unit": "CTU/s", "cores": threads, "kind": kind, "sample": desc}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    value, base = cpu_reference_run(args, args.steps, args.warmup)
+    ctus_per_step = args.pics * ((args.width + 63) // 64) * ((args.height + 63) // 64)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * ctus_per_step / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "CTU/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"{args.width}x{args.height} {args.bit_depth}-bit All-Intra (BASELINE configs[1]): full intra RMD enumeration "
+                        f"341 PUs x 35 modes per CTU + OBF/outlier feature pass, {args.pics} pictures per step per GPU",
+            "pictures_per_step_per_gpu": args.pics, "ctus_per_picture": ((args.width + 63) // 64) * ((args.height + 63) // 64),
+            "l2_policy": "inputs larger than L2: one step reads 2 planes x pictures and writes the cost tables (> 126 MB) before any reuse",
+            "parallelism": f"pictures sharded over {args.gpus} GPU(s), no collective"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out, _ = self.proc.communicate(timeout=10)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    cucd = importlib.import_module(PKG)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, bd, P = args.width, args.height, args.bit_depth, args.pics
+    eng = cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P)
+    nctu = eng.ctus_per_pic
+    pitch = (W + 63) // 64 * 64
+    # each rank works on its own pictures (different seeds): weak scaling
+    orgs = [textured_plane(W, H, bd, 20261018 + 97 * rank, t) for t in range(P)]
+    recs = [pseudo_recon(o, bd, t) for t, o in enumerate(orgs)]
+
+    def pinned(shape, dtype):
+        tdt = {np.int16: torch.int16, np.int32: torch.int32, np.uint32: torch.int32, np.float64: torch.float64}[dtype]
+        t = torch.empty(shape, dtype=tdt, pin_memory=True)
+        pinned.keep.append(t)
+        a = t.numpy()
+        return a.view(np.uint32) if dtype is np.uint32 else a
+    pinned.keep = []
+
+    h_org = [pinned((H, W), np.int16) for _ in range(P)]
+    h_rec = [pinned((H, W), np.int16) for _ in range(P)]
+    for p in range(P):
+        h_org[p][:] = orgs[p]; h_rec[p][:] = recs[p]
+    h_outs = [eng.alloc_frame_out(True, pinned_alloc=pinned) for _ in range(P)]
+
+    # ---- device-resident buffers -------------------------------------------------------------------
+    d_org = torch.zeros((P, H, pitch), dtype=torch.int16, device=dev)
+    d_rec = torch.zeros((P, H, pitch), dtype=torch.int16, device=dev)
+    for p in range(P):
+        d_org[p, :, :W] = torch.from_numpy(orgs[p]).to(dev)
+        d_rec[p, :, :W] = torch.from_numpy(recs[p]).to(dev)
+    d_cost = torch.empty((P, nctu, 341, 35), dtype=torch.int32, device=dev)
+    d_obf = torch.empty((P, H // 4, W // 4), dtype=torch.int16, device=dev)
+    d_outl = torch.empty((P, H, W), dtype=torch.int16, device=dev)
+    d_num = [torch.empty((P,) + eng.cu_grid(d), dtype=torch.int32, device=dev) for d in range(4)]
+    d_sum = [torch.empty((P,) + eng.cu_grid(d), dtype=torch.int32, device=dev) for d in range(4)]
+    d_had = torch.empty((P, nctu), dtype=torch.int32, device=dev)
+    d_out = {"obf": d_obf.data_ptr(), "outlier": d_outl.data_ptr(), "num_obf": [t.data_ptr() for t in d_num],
+             "n_outlier": [t.data_ptr() for t in d_sum], "ctu_src_had": d_had.data_ptr(), "rmd_cost": d_cost.data_ptr()}
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def dev_step():
+        eng.dev_frames(stream, P, d_org.data_ptr(), H * pitch, pitch, d_rec.data_ptr(), H * pitch, pitch, d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident timing ----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        dev_step()
+    e1.record()
+    barrier()
+    launches = eng.launch_count - l0
+    dev_ms = e0.elapsed_time(e1)
+    rmd_ms, n_timed = eng.rmd_kernel_time_ms(min(args.steps, 64))
+    clk = clocks.stop()
+
+    # ---- end to end through the host-buffer ABI -------------------------------------------------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        eng.frames(h_org, h_rec, h_outs)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.frames(h_org, h_rec, h_outs)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = 2 * P * W * H * 2
+    d2h = sum(int(a.nbytes) for o in h_outs for a in o.values())
+
+    # spot-check that both paths produced the same tables (device-resident vs host-buffer)
+    same = bool(np.array_equal(d_cost[0].cpu().numpy().view(np.uint32), h_outs[0]["rmd_cost"]))
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s, rmd_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s, rmd_ms = [float(v) for v in t.tolist()]
+    ctus_step_gpu = P * nctu
+    value = world * ctus_step_gpu * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * ctus_step_gpu * e2e_steps / e2e_s
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = ALGO_BYTES_PER_CTU * ctus_step_gpu / (rmd_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "rmd_frame_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "launch_ms": rmd_ms, "launches_timed": n_timed, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CTU * ctus_step_gpu,
+                "peak_source": peak_src,
+                "note": "RMD is integer-ALU bound by construction (~140 int-op/B, SURVEY.md 8d): the HBM fraction is small; see profiles/ for pipe utilisation"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cpu_baseline = cpu_reference_run(args, steps=3, warmup=1, target_step_s=3.0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "CTU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host)"},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "paths_agree": same}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pics", type=int, default=16, help="pictures per step per GPU")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--bit-depth", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.gpus = world if world > 1 else args.gpus
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,7 @@ def load_library():
                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     lib.cucd_dev_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
                                     C.c_int, C.POINTER(_DevOut), C.c_void_p]
+    lib.cucd_rmd_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
     lib.cucd_tcm_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
@@ -298,3 +299,11 @@ class Engine:
         yc = yc_host.ctypes.data if yc_host is not None else None
         self._check(self.lib.cucd_dev_frames(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride,
                                              C.byref(o), yc), "cucd_dev_frames")
+
+    def rmd_kernel_time_ms(self, n_calls):
+        """mean device duration of the RMD launch over the last n_calls dev_frames calls (stream must be synchronised)"""
+        ms = C.c_float(0)
+        n = self.lib.cucd_rmd_kernel_time(self.h, int(n_calls), C.byref(ms))
+        if n < 0:
+            self._check(n, "cucd_rmd_kernel_time")
+        return float(ms.value), int(n)

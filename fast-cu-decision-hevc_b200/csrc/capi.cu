@@ -53,6 +53,9 @@ struct cucd_handle {
   size_t planeSamples = 0;
   cudaStream_t sMain = nullptr, sFeat = nullptr;
   cudaEvent_t evUp = nullptr, evHist = nullptr;
+  static constexpr int kTimeRing = 64;
+  cudaEvent_t evRmd0[kTimeRing] = {}, evRmd1[kTimeRing] = {};
+  long long rmdCalls = 0;
   int launches = 0;
   long long launchTotal = 0;
   std::string err;
@@ -155,6 +158,7 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
             cudaStreamCreateWithFlags(&h->sFeat, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->evUp, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->evHist, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < cucd_handle::kTimeRing; i++) ok = ok && cudaEventCreate(&h->evRmd0[i]) == cudaSuccess && cudaEventCreate(&h->evRmd1[i]) == cudaSuccess;
   ok = ok && h->dOrg.reserve(P * h->planeSamples) == cudaSuccess && h->dRec.reserve(P * h->planeSamples) == cudaSuccess;
   ok = ok && h->dCost.reserve(P * h->ctusPerPic * kPusPerCtu * kNumModes) == cudaSuccess;
   ok = ok && h->dHist.reserve(P * kHistFreqs * kHistBins) == cudaSuccess && h->dThr.reserve(P * kHistFreqs) == cudaSuccess;
@@ -182,12 +186,28 @@ int cucd_destroy(cucd_handle* h) {
   h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
   for (auto& r : h->refs) r.buf.release();
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
+  for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
   if (h->evUp) cudaEventDestroy(h->evUp);
   if (h->evHist) cudaEventDestroy(h->evHist);
   if (h->sMain) cudaStreamDestroy(h->sMain);
   if (h->sFeat) cudaStreamDestroy(h->sFeat);
   delete h;
   return CUCD_OK;
+}
+
+int cucd_rmd_kernel_time(cucd_handle* h, int nCalls, float* avg_ms) {
+  if (!h || !avg_ms || nCalls < 1) return fail(h, CUCD_ERR_INVALID, "cucd_rmd_kernel_time: bad argument");
+  const int n = (int)std::min<long long>(std::min<long long>(nCalls, h->rmdCalls), cucd_handle::kTimeRing);
+  if (n < 1) return fail(h, CUCD_ERR_INVALID, "cucd_rmd_kernel_time: no timed call yet");
+  double sum = 0;
+  for (int i = 0; i < n; i++) {
+    const int slot = (int)((h->rmdCalls - 1 - i) % cucd_handle::kTimeRing);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->evRmd0[slot], h->evRmd1[slot]));
+    sum += ms;
+  }
+  *avg_ms = (float)(sum / n);
+  return n;
 }
 
 int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr) {
@@ -256,7 +276,11 @@ int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_or
   }
   if (d_rec) {
     const FrameSource fs = make_frame_source(h, d_org, orgPicStride, orgStride, d_rec, recPicStride, recStride, out->rmd_cost);
+    const int slot = (int)(h->rmdCalls % cucd_handle::kTimeRing);
+    CK(cudaEventRecord(h->evRmd0[slot], st));
     CK(launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches));
+    CK(cudaEventRecord(h->evRmd1[slot], st));
+    h->rmdCalls++;
   }
   if (wantFeat) {
     CK(cudaEventSynchronize(h->evHist));      // the RMD kernel keeps the GPU busy while the host fits

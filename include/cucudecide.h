@@ -148,6 +148,10 @@ typedef struct {
 } cucd_dev_out;
 int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
                     const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
+/* Device time of the RMD kernel inside the last `nCalls` cucd_dev_frames calls (CUDA events recorded on the
+ * caller's stream around that launch; ring of 64).  The stream must have been synchronised.  Returns
+ * the number of calls averaged, or a negative status; *avg_ms = mean duration of one launch. */
+int cucd_rmd_kernel_time(cucd_handle* h, int nCalls, float* avg_ms);
 /* the host-side fit that sits between the two passes (TEncSlice.cpp:291-392): hist = 16*4096 counts
  * of ONE picture, nBlocks = (W/4)*(H/4); writes yc[16] and thr[16] */
 int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr);
