@@ -69,99 +69,113 @@ CUCD_HD int warp_half(int warp) { return (warp >> 1) & 1; }
 CUCD_HD int class_num_modes(int cls) { return cls == 0 ? 18 : 17; }
 CUCD_HD int class_mode(int cls, int i) { return cls == 0 ? (i == 0 ? 0 : 17 + i) : (i == 0 ? 1 : 1 + i); }
 
-// which PU / tile a lane owns
+// ---------------------------------------------------------------------------------------------
+// Runtime geometry.  The border phases are templated on the PU size (short, run once per chunk); the
+// mode loop - where the time goes - is ONE piece of code for N = 8..64 that takes the size at run time,
+// so that the five depths of a frame launch share a single hot instruction footprint.
+// ---------------------------------------------------------------------------------------------
+struct RtGeo {
+  int log2n, n, as, xs, puStride, tilesPerPu, tilesPerRow, lanesPerPu, extPerWarp;
+  int arrs16, ext16;                 // int16 index of the ref arrays / the ext scratch in shared memory
+  int dcOff, validOff, accOff;       // byte offsets
+  int edge;                          // luma edge filters apply (N <= 16)
+};
 template <int LOG2N>
+CUCD_HD RtGeo make_rt_geo() {
+  typedef Geo<LOG2N> G; typedef Smem<LOG2N> S;
+  RtGeo g;
+  g.log2n = LOG2N; g.n = G::N; g.as = G::AS; g.xs = G::XS; g.puStride = G::PU_STRIDE;
+  g.tilesPerPu = G::TILES_PER_PU; g.tilesPerRow = G::N >= 8 ? G::N / 8 : 1;
+  g.lanesPerPu = G::TILES_PER_PU < 32 ? G::TILES_PER_PU : 32; g.extPerWarp = G::EXT_PER_WARP;
+  g.arrs16 = S::ARRS_OFF / 2; g.ext16 = S::EXT_OFF / 2; g.dcOff = S::DC_OFF; g.validOff = S::VALID_OFF; g.accOff = S::UNI_OFF;
+  g.edge = G::N <= 16;
+  return g;
+}
+
+CUCD_HD RtGeo make_rt_geo_rt(int log2n) {
+  switch (log2n) {
+    case 2: return make_rt_geo<2>();
+    case 3: return make_rt_geo<3>();
+    case 4: return make_rt_geo<4>();
+    case 5: return make_rt_geo<5>();
+    default: return make_rt_geo<6>();
+  }
+}
+
+// which PU / tile a lane owns
 struct LaneGeo {
-  typedef Geo<LOG2N> G;
   int pu;        // chunk-local PU of the tile (N >= 8) or first of the region's four PUs (N = 4)
   int tx0, ty0;  // tile origin inside its PU, true orientation
   int extSlot;   // index of the lane's first extended-ref array inside the warp's scratch
-  int lanesPerPu, subLane;
-  CUCD_HD void init(int half, int lane) {
+  int subLane;   // position among the lanes that share the PU
+  CUCD_HD void init(const RtGeo& g, int half, int lane) {
     const int t = half * 32 + lane;
-    if constexpr (LOG2N == 2) { pu = 4 * t; tx0 = 0; ty0 = 0; extSlot = 4 * lane; lanesPerPu = 1; subLane = 0; }
+    if (g.log2n == 2) { pu = 4 * t; tx0 = 0; ty0 = 0; extSlot = 4 * lane; subLane = 0; }
     else {
-      constexpr int TPP = G::TILES_PER_PU, TPR = G::N / 8;
-      pu = t / TPP;
-      const int q = t % TPP;
-      tx0 = (q % TPR) * 8; ty0 = (q / TPR) * 8;
-      lanesPerPu = TPP < 32 ? TPP : 32;
-      subLane = lane % lanesPerPu;
-      extSlot = lane / lanesPerPu;
+      pu = t / g.tilesPerPu;
+      const int q = t - pu * g.tilesPerPu;
+      const int row = q / g.tilesPerRow;
+      tx0 = (q - row * g.tilesPerRow) * 8; ty0 = row * 8;
+      subLane = lane % g.lanesPerPu;
+      extSlot = lane / g.lanesPerPu;
     }
   }
 };
 
-// Build the extended main reference(s) of a negative-angle mode for the PU(s) this lane works on.
-template <int LOG2N>
-CUCD_HD void lane_build_ext(const SmemView<LOG2N>& sm, int warp, const LaneGeo<LOG2N>& lg, int cls, int mode) {
-  typedef Geo<LOG2N> G;
-  constexpr int N = G::N;
+// Build the extended main reference(s) of a negative-angle mode for the PU(s) this lane works on
+// (TComPrediction.cpp:300-322).  Lanes that share a PU split its 2N+1 entries.
+CUCD_HD void lane_build_ext(const RtGeo& g, unsigned char* smem, int warp, const LaneGeo& lg, int cls, int mode) {
+  const int N = g.n;
   const int angle = mode_angle(mode), inv = mode_inv_angle(mode);
   const int lastIdx = (N * angle) >> 5;
-  const int fo = mode_uses_filtered<LOG2N>(mode) ? 2 * G::AS : 0;
-  int16_t* ext = sm.ext() + warp * G::EXT_PER_WARP;
-  const int nsub = LOG2N == 2 ? 4 : 1;
+  const int fo = mode_uses_filtered_rt(g.log2n, mode) ? 2 * g.as : 0;
+  int16_t* s16 = reinterpret_cast<int16_t*>(smem);
+  const int nsub = g.log2n == 2 ? 4 : 1, step = g.log2n == 2 ? 1 : g.lanesPerPu;
   for (int s = 0; s < nsub; s++) {
-    const int arr0 = SmemView<LOG2N>::ARRS16 + (lg.pu + s) * G::PU_STRIDE + fo;
-    const int main0 = arr0 + (cls ? G::AS : 0), side0 = arr0 + (cls ? 0 : G::AS);
-    int16_t* e = ext + (lg.extSlot + s) * G::XS + N;       // element k = 0
-    for (int i = lg.subLane; i < G::XS; i += lg.lanesPerPu) {
+    const int arr0 = g.arrs16 + (lg.pu + s) * g.puStride + fo;
+    const int main0 = arr0 + (cls ? g.as : 0), side0 = arr0 + (cls ? 0 : g.as);
+    const int e0 = g.ext16 + warp * g.extPerWarp + (lg.extSlot + s) * g.xs + N;       // element k = 0
+    for (int i = lg.subLane; i < g.xs; i += step) {
       const int k = i - N;
       int16_t v = 0;
-      if (k <= N && k > lastIdx) v = ext_ref_sample<LOG2N>(sm.s16(), main0, side0, inv, k);
-      e[k] = v;
+      if (k <= N && k > lastIdx) v = ext_ref_sample(s16, main0, side0, inv, k);
+      s16[e0 + k] = v;
     }
   }
 }
 
-// Residual + SATD of the lane's tile (N >= 8) for one mode.  `src` is the lane's source tile in the
-// orientation of its warp class.
-template <int LOG2N>
-CUCD_HD uint32_t lane_eval_tile(const SmemView<LOG2N>& sm, int warp, const LaneGeo<LOG2N>& lg, int cls, int mode, int bitDepth, const Tile& src) {
-  typedef Geo<LOG2N> G;
-  constexpr int N = G::N;
-  constexpr bool EDGE = N <= 16;
-  const int fo = mode_uses_filtered<LOG2N>(mode) ? 2 * G::AS : 0;
-  const int arr0 = SmemView<LOG2N>::ARRS16 + lg.pu * G::PU_STRIDE + fo;
-  const int main0 = arr0 + (cls ? G::AS : 0), side0 = arr0 + (cls ? 0 : G::AS);
-  const int x0 = cls ? lg.ty0 : lg.tx0, y0 = cls ? lg.tx0 : lg.ty0;
-  uint32_t d[32];
-  if (mode == 0) resid_planar<LOG2N, 8, 4>(sm.s16(), main0, side0, x0, y0, src.r, 4, d);
-  else if (mode == 1) resid_dc<8, 4>(sm.s16(), main0, side0, x0, y0, sm.dc()[lg.pu], EDGE, src.r, 4, d);
+// Residual of one block (8x8 tile: ROWS 8 / WORDS 4, 4x4 PU: ROWS 4 / WORDS 2) for one mode.
+template <int ROWS, int WORDS>
+CUCD_HD void block_residual(const RtGeo& g, const unsigned char* smem, int warp, int pu, int extSlot, int x0, int y0, int cls, int mode,
+                            int bitDepth, const uint32_t* src, uint32_t* d) {
+  const int16_t* s16 = reinterpret_cast<const int16_t*>(smem);
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(smem);
+  const int fo = mode_uses_filtered_rt(g.log2n, mode) ? 2 * g.as : 0;
+  const int arr0 = g.arrs16 + pu * g.puStride + fo;
+  const int main0 = arr0 + (cls ? g.as : 0), side0 = arr0 + (cls ? 0 : g.as);
+  if (mode == 0) resid_planar<ROWS, WORDS>(g.log2n, s16, main0, side0, x0, y0, src, 4, d);
+  else if (mode == 1) resid_dc<ROWS, WORDS>(s16, main0, side0, x0, y0, reinterpret_cast<const int16_t*>(smem + g.dcOff)[pu], g.edge != 0, src, 4, d);
   else {
     const int angle = mode_angle(mode);
-    if (angle == 0) resid_angular_pure<8, 4>(sm.s32(), sm.s16(), main0, side0, x0, y0, EDGE, (1 << bitDepth) - 1, src.r, 4, d);
-    else {
-      const int m0 = angle < 0 ? SmemView<LOG2N>::EXT16 + warp * G::EXT_PER_WARP + lg.extSlot * G::XS + N : main0;
-      if (angle == 32 || angle == -32) resid_angular_int<8, 4>(sm.s32(), m0, x0, y0, angle, src.r, 4, d);
-      else resid_angular_frac<8, 4>(sm.s32(), m0, x0, y0, angle, src.r, 4, d);
-    }
+    const int m0 = angle < 0 ? g.ext16 + warp * g.extPerWarp + extSlot * g.xs + g.n : main0;
+    resid_angular_frac<ROWS, WORDS>(s32, m0, x0, y0, angle, src, 4, d);
+    if (angle == 0 && g.edge && x0 == 0) patch_pure_edge<ROWS, WORDS>(s16, main0, side0, y0, (1 << bitDepth) - 1, src, 4, d);
   }
+}
+
+// N >= 8: SATD of the lane's tile for one mode.  `src` is the tile in the orientation of the warp class.
+CUCD_HD uint32_t lane_eval_tile(const RtGeo& g, const unsigned char* smem, int warp, const LaneGeo& lg, int cls, int mode, int bitDepth, const Tile& src) {
+  uint32_t d[32];
+  block_residual<8, 4>(g, smem, warp, lg.pu, lg.extSlot, cls ? lg.ty0 : lg.tx0, cls ? lg.tx0 : lg.ty0, cls, mode, bitDepth, src.r, d);
   return satd8x8_packed(d);
 }
 
 // N = 4: the lane's region holds four independent 4x4 PUs; cost[s] for PU lg.pu + s
-CUCD_HD void lane_eval_region4(const SmemView<2>& sm, int warp, const LaneGeo<2>& lg, int cls, int mode, int bitDepth, const Tile& src, uint32_t* cost) {
-  typedef Geo<2> G;
-  constexpr int N = 4;
+CUCD_HD void lane_eval_region4(const RtGeo& g, const unsigned char* smem, int warp, const LaneGeo& lg, int cls, int mode, int bitDepth, const Tile& src, uint32_t* cost) {
 #pragma unroll
   for (int s = 0; s < 4; s++) {
-    const int arr0 = SmemView<2>::ARRS16 + (lg.pu + s) * G::PU_STRIDE;
-    const int main0 = arr0 + (cls ? G::AS : 0), side0 = arr0 + (cls ? 0 : G::AS);
-    const uint32_t* sp = &src.r[((s >> 1) * 4) * 4 + (s & 1) * 2];
     uint32_t d[8];
-    if (mode == 0) resid_planar<2, 4, 2>(sm.s16(), main0, side0, 0, 0, sp, 4, d);
-    else if (mode == 1) resid_dc<4, 2>(sm.s16(), main0, side0, 0, 0, sm.dc()[lg.pu + s], true, sp, 4, d);
-    else {
-      const int angle = mode_angle(mode);
-      if (angle == 0) resid_angular_pure<4, 2>(sm.s32(), sm.s16(), main0, side0, 0, 0, true, (1 << bitDepth) - 1, sp, 4, d);
-      else {
-        const int m0 = angle < 0 ? SmemView<2>::EXT16 + warp * G::EXT_PER_WARP + (lg.extSlot + s) * G::XS + N : main0;
-        if (angle == 32 || angle == -32) resid_angular_int<4, 2>(sm.s32(), m0, 0, 0, angle, sp, 4, d);
-        else resid_angular_frac<4, 2>(sm.s32(), m0, 0, 0, angle, sp, 4, d);
-      }
-    }
+    block_residual<4, 2>(g, smem, warp, lg.pu + s, lg.extSlot + s, 0, 0, cls, mode, bitDepth, &src.r[((s >> 1) * 4) * 4 + (s & 1) * 2], d);
     cost[s] = satd4x4_packed(d);
   }
 }

@@ -92,6 +92,13 @@ CUCD_HD bool mode_uses_filtered(int mode) {
   return (d10 < d26 ? d10 : d26) > thr;
 }
 
+CUCD_HD bool mode_uses_filtered_rt(int log2n, int mode) {
+  if (log2n == 2 || log2n == 6 || mode == 1) return false;
+  const int thr = log2n == 3 ? 7 : (log2n == 4 ? 1 : 0);
+  const int d10 = mode > 10 ? mode - 10 : 10 - mode, d26 = mode > 26 ? mode - 26 : 26 - mode;
+  return (d10 < d26 ? d10 : d26) > thr;
+}
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory geometry of one chunk
 // ---------------------------------------------------------------------------------------------
@@ -403,37 +410,21 @@ CUCD_HD void resid_angular_frac(const uint32_t* smem32, int main0, int x0, int y
     }
   }
 }
-// angular with |angle| == 32: whole-sample copies (modes 2, 18, 34)
+// Every angular mode goes through resid_angular_frac: with f == 0 the interpolation degenerates to an
+// exact copy ((32*a + 16) >> 5 == a), so |angle| == 32 and angle == 0 need no code of their own (one
+// hot loop body keeps the instruction footprint small - the kernel is instruction-fetch sensitive).
+// Pure vertical / horizontal modes then only patch the first column for the luma edge filter of
+// N <= 16 (TComPrediction.cpp:346-363): pred[y][0] = clip(ref[1] + ((side[y+1] - side[0]) >> 1)).
 template <int ROWS, int WORDS>
-CUCD_HD void resid_angular_int(const uint32_t* smem32, int main0, int x0, int y0, int angle, const uint32_t* src, int srcStride, uint32_t* d) {
-#pragma unroll
-  for (int y = 0; y < ROWS; y++) {
-    const int di = ((y0 + y + 1) * angle) >> 5;
-    uint32_t A[WORDS], B[WORDS];
-    load_row_window<ROWS, WORDS>(smem32, main0 + x0 + di + 1, A, B);
-#pragma unroll
-    for (int j = 0; j < WORDS; j++) d[y * WORDS + j] = src[y * srcStride + j] - A[j];
-  }
-}
-// pure vertical / horizontal (angle 0) with the luma edge filter for N <= 16 (TComPrediction.cpp:346-363)
-template <int ROWS, int WORDS>
-CUCD_HD void resid_angular_pure(const uint32_t* smem32, const int16_t* smem16, int main0, int side0, int x0, int y0, bool edge, int maxVal,
-                                const uint32_t* src, int srcStride, uint32_t* d) {
-  uint32_t A[WORDS], B[WORDS];
-  load_row_window<ROWS, WORDS>(smem32, main0 + x0 + 1, A, B);
-  const bool fix = edge && x0 == 0;
+CUCD_HD void patch_pure_edge(const int16_t* smem16, int main0, int side0, int y0, int maxVal, const uint32_t* src, int srcStride, uint32_t* d) {
   const int s0 = smem16[side0], m1 = smem16[main0 + 1];
 #pragma unroll
   for (int y = 0; y < ROWS; y++) {
-    uint32_t p0 = A[0];
-    if (fix) {
-      int v = m1 + ((smem16[side0 + y0 + y + 1] - s0) >> 1);
-      v = imin32(imax32(v, 0), maxVal);
-      p0 = (p0 & 0xffff0000u) | (uint32_t)v;
-    }
-    d[y * WORDS] = src[y * srcStride] - p0;
-#pragma unroll
-    for (int j = 1; j < WORDS; j++) d[y * WORDS + j] = src[y * srcStride + j] - A[j];
+    int v = m1 + ((smem16[side0 + y0 + y + 1] - s0) >> 1);
+    v = imin32(imax32(v, 0), maxVal);
+    // d = src - pred with pred.lo = m1 so far: replace the low half's prediction by v
+    d[y * WORDS] += (uint32_t)(m1 - v);
+    (void)src; (void)srcStride;
   }
 }
 // DC with edge smoothing for N <= 16 (TComPrediction.cpp:266-276, 818-841); orientation-symmetric
@@ -463,9 +454,9 @@ CUCD_HD void resid_dc(const int16_t* smem16, int main0, int side0, int x0, int y
     }
 }
 // planar (TComPrediction.cpp:755-805); T = array along x, L = array along y
-template <int LOG2N, int ROWS, int WORDS>
-CUCD_HD void resid_planar(const int16_t* smem16, int t0, int l0, int x0, int y0, const uint32_t* src, int srcStride, uint32_t* d) {
-  constexpr int N = 1 << LOG2N;
+template <int ROWS, int WORDS>
+CUCD_HD void resid_planar(const int LOG2N, const int16_t* smem16, int t0, int l0, int x0, int y0, const uint32_t* src, int srcStride, uint32_t* d) {
+  const int N = 1 << LOG2N;
   const int tr = smem16[t0 + 1 + N], bl = smem16[l0 + 1 + N];
   int vert[2 * WORDS], vstep[2 * WORDS];
 #pragma unroll
@@ -492,7 +483,6 @@ CUCD_HD void resid_planar(const int16_t* smem16, int t0, int l0, int x0, int y0,
 
 // negative-angle modes: element k of the extended main reference, k in [-N, N]
 // (TComPrediction.cpp:300-322: ref[k<0] = side[(128 + |k|*invAngle) >> 8])
-template <int LOG2N>
 CUCD_HD int16_t ext_ref_sample(const int16_t* smem16, int main0, int side0, int invAngle, int k) {
   if (k >= 0) return smem16[main0 + k];
   return smem16[side0 + ((128 - k * invAngle) >> 8)];

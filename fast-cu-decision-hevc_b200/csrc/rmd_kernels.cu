@@ -14,6 +14,83 @@ namespace cucd {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// The mode loop of a chunk.  Not templated on the PU size: N = 8..64 share this code, N = 4 takes the
+// region branch.  __noinline__ keeps exactly one copy in the frame kernel.
+template <bool FRAME>
+__device__ __noinline__ void phase_modes(const int log2n, const int chunk, const FrameSource& fs, const BatchSource& bs, const int bitDepth,
+                                         const int16_t* orgPic, const int ctuX, const int ctuY) {
+  unsigned char* smem = smem_raw;
+  const RtGeo g = make_rt_geo_rt(log2n);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cls = warp_class(warp), half = warp_half(warp), par = warp & 1;
+  const int N = g.n, pusPerChunk = 4096 >> (2 * g.log2n);
+  const uint8_t* valid = smem + g.validOff;
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem + g.accOff);
+  LaneGeo lg; lg.init(g, half, lane);
+  const bool ok = valid[lg.pu] != 0;     // N = 4: the four PUs of a region share validity (W, H multiples of 8)
+  Tile src;
+  if (ok) {
+    Tile raw;
+    if (FRAME) {
+      int px, py;
+      if (g.log2n == 2) { demorton(lg.pu >> 2, px, py); px *= 8; py *= 8; }
+      else { demorton(lg.pu, px, py); px = px * N + lg.tx0; py = py * N + lg.ty0; }
+      tile_load(raw, orgPic + (size_t)(ctuY + py) * fs.orgStride + ctuX + px, fs.orgStride);
+    } else {
+      if (g.log2n == 2) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const bool okS = chunk * pusPerChunk + lg.pu + s < bs.count;
+          const int16_t* base = bs.org + (okS ? (size_t)bs.pus[chunk * pusPerChunk + lg.pu + s].orgOff : 0);
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+            uint2 v = make_uint2(0u, 0u);
+            if (okS) v = *reinterpret_cast<const uint2*>(base + y * 4);
+            raw.r[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 0] = v.x;
+            raw.r[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 1] = v.y;
+          }
+        }
+      } else {
+        const int16_t* base = bs.org + (size_t)bs.pus[chunk * pusPerChunk + lg.pu].orgOff;
+        tile_load(raw, base + lg.ty0 * N + lg.tx0, N);
+      }
+    }
+    if (cls == 0) src = raw;
+    else if (g.log2n == 2) tile_transpose4x4(raw, src);
+    else tile_transpose8(raw, src);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; k++) src.r[k] = 0;
+  }
+
+  const int nModes = class_num_modes(cls);
+  for (int i = par; i < nModes; i += 2) {
+    const int mode = class_mode(cls, i);
+    const bool neg = mode >= 2 && mode_angle(mode) < 0;
+    if (neg) {
+      if (ok) lane_build_ext(g, smem, warp, lg, cls, mode);
+      __syncwarp();
+    }
+    if (g.log2n == 2) {
+      if (ok) {
+        uint32_t c4[4];
+        lane_eval_region4(g, smem, warp, lg, cls, mode, bitDepth, src, c4);
+#pragma unroll
+        for (int s = 0; s < 4; s++) acc[(lg.pu + s) * kNumModes + mode] = c4[s];
+      }
+    } else {
+      uint32_t v = 0;
+      if (ok) v = lane_eval_tile(g, smem, warp, lg, cls, mode, bitDepth, src);
+      for (int m = 1; m < g.lanesPerPu; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (ok && lg.subLane == 0) {
+        if (g.tilesPerPu > 32) atomicAdd(&acc[lg.pu * kNumModes + mode], v);
+        else acc[lg.pu * kNumModes + mode] = v;
+      }
+    }
+    if (neg) __syncwarp();
+  }
+}
+
 template <int LOG2N, bool FRAME>
 __device__ __forceinline__ void rmd_body(const int chunk, const FrameSource& fs, const BatchSource& bs, const int bitDepth, const int strong) {
   typedef Geo<LOG2N> G;
@@ -61,75 +138,8 @@ __device__ __forceinline__ void rmd_body(const int chunk, const FrameSource& fs,
   for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) sm.acc()[i] = 0;   // aliases lin/flags: derive is done
   __syncthreads();
 
-  // ---- phase E: modes ----------------------------------------------------------------------
-  {
-    const int cls = warp_class(warp), half = warp_half(warp), par = warp & 1;
-    LaneGeo<LOG2N> lg; lg.init(half, lane);
-    const bool ok = sm.valid()[lg.pu] != 0;     // N = 4: the four PUs of a region share validity (W, H multiples of 8)
-    Tile src;
-    if (ok) {
-      Tile raw;
-      if (FRAME) {
-        int px, py;
-        if constexpr (LOG2N == 2) { demorton(lg.pu >> 2, px, py); px *= 8; py *= 8; }
-        else { demorton(lg.pu, px, py); px = px * N + lg.tx0; py = py * N + lg.ty0; }
-        tile_load(raw, orgPic + (size_t)(ctuY + py) * fs.orgStride + ctuX + px, fs.orgStride);
-      } else {
-        if constexpr (LOG2N == 2) {
-#pragma unroll
-          for (int s = 0; s < 4; s++) {
-            const bool okS = chunk * G::PUS + lg.pu + s < bs.count;
-            const int16_t* base = bs.org + (okS ? (size_t)bs.pus[chunk * G::PUS + lg.pu + s].orgOff : 0);
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-              uint2 v = make_uint2(0u, 0u);
-              if (okS) v = *reinterpret_cast<const uint2*>(base + y * 4);
-              raw.r[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 0] = v.x;
-              raw.r[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 1] = v.y;
-            }
-          }
-        } else {
-          const int16_t* base = bs.org + (size_t)bs.pus[chunk * G::PUS + lg.pu].orgOff;
-          tile_load(raw, base + lg.ty0 * N + lg.tx0, N);
-        }
-      }
-      if (cls == 0) src = raw;
-      else if constexpr (LOG2N == 2) tile_transpose4x4(raw, src);
-      else tile_transpose8(raw, src);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 32; k++) src.r[k] = 0;
-    }
-
-    const int nModes = class_num_modes(cls);
-    for (int i = par; i < nModes; i += 2) {
-      const int mode = class_mode(cls, i);
-      const bool neg = mode >= 2 && mode_angle(mode) < 0;
-      if (neg) {
-        if (ok) lane_build_ext<LOG2N>(sm, warp, lg, cls, mode);
-        __syncwarp();
-      }
-      if constexpr (LOG2N == 2) {
-        if (ok) {
-          uint32_t c4[4];
-          lane_eval_region4(sm, warp, lg, cls, mode, bitDepth, src, c4);
-#pragma unroll
-          for (int s = 0; s < 4; s++) sm.acc()[(lg.pu + s) * kNumModes + mode] = c4[s];
-        }
-      } else {
-        uint32_t v = 0;
-        if (ok) v = lane_eval_tile<LOG2N>(sm, warp, lg, cls, mode, bitDepth, src);
-        constexpr int LPP = G::TILES_PER_PU < 32 ? G::TILES_PER_PU : 32;
-#pragma unroll
-        for (int m = 1; m < LPP; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-        if (ok && (lane % LPP) == 0) {
-          if (G::TILES_PER_PU > 32) atomicAdd(&sm.acc()[lg.pu * kNumModes + mode], v);
-          else sm.acc()[lg.pu * kNumModes + mode] = v;
-        }
-      }
-      if (neg) __syncwarp();
-    }
-  }
+  // ---- phase E: modes (one runtime-sized code path for every N, see RtGeo) ----------------------
+  phase_modes<FRAME>(LOG2N, chunk, fs, bs, bitDepth, orgPic, ctuX, ctuY);
   __syncthreads();
 
   // ---- phase F: coalesced cost-table store --------------------------------------------------
@@ -149,12 +159,13 @@ __device__ __forceinline__ void rmd_body(const int chunk, const FrameSource& fs,
   }
 }
 
-// Frame (replay) mode: ONE launch covers every (picture, CTU, depth); the five depths of a CTU are
-// neighbouring CTAs so that its source tile and border rows are hit in L2.
+// Frame (replay) mode: ONE launch covers every (picture, CTU, depth).
 __global__ void __launch_bounds__(kRmdThreads, 2)
 rmd_frame_kernel(const FrameSource fs, const int bitDepth, const int strong) {
   const BatchSource bs = {};
-  const int chunk = blockIdx.x / 5, depth = blockIdx.x - chunk * 5;
+  // depth-major block order: at any moment most SMs run the same size variant (instruction-cache footprint)
+  const int chunks = gridDim.x / 5;
+  const int depth = blockIdx.x / chunks, chunk = blockIdx.x - depth * chunks;
   switch (depth) {
     case 0: rmd_body<6, true>(chunk, fs, bs, bitDepth, strong); break;
     case 1: rmd_body<5, true>(chunk, fs, bs, bitDepth, strong); break;

@@ -55,25 +55,28 @@ void emul_chunk(int chunk, const FrameSource& fs, const BatchSource& bs, int bit
     for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) sm.acc()[i] = 0;
   }
   // phase E: warps one after the other; inside a warp the ext build of all lanes precedes the evaluation
+  const RtGeo g = make_rt_geo_rt(LOG2N);
+  unsigned char* smem = sm.base;
+  const int pusPerChunk = G::PUS;
   for (int warp = 0; warp < kRmdWarps; warp++) {
     const int cls = warp_class(warp), half = warp_half(warp), par = warp & 1;
-    LaneGeo<LOG2N> lg[32]; bool ok[32]; Tile src[32];
+    LaneGeo lg[32]; bool ok[32]; Tile src[32];
     for (int lane = 0; lane < 32; lane++) {
-      lg[lane].init(half, lane);
+      lg[lane].init(g, half, lane);
       ok[lane] = sm.valid()[lg[lane].pu] != 0;
       std::memset(&src[lane], 0, sizeof(Tile));
       if (!ok[lane]) continue;
       Tile raw;
       if (FRAME) {
         int px, py;
-        if constexpr (LOG2N == 2) { demorton(lg[lane].pu >> 2, px, py); px *= 8; py *= 8; }
+        if (g.log2n == 2) { demorton(lg[lane].pu >> 2, px, py); px *= 8; py *= 8; }
         else { demorton(lg[lane].pu, px, py); px = px * N + lg[lane].tx0; py = py * N + lg[lane].ty0; }
         tile_load(raw, orgPic + (size_t)(ctuY + py) * fs.orgStride + ctuX + px, fs.orgStride);
       } else {
-        if constexpr (LOG2N == 2) {
+        if (g.log2n == 2) {
           for (int s = 0; s < 4; s++) {
-            const bool okS = chunk * G::PUS + lg[lane].pu + s < bs.count;
-            const int16_t* base = bs.org + (okS ? (size_t)bs.pus[chunk * G::PUS + lg[lane].pu + s].orgOff : 0);
+            const bool okS = chunk * pusPerChunk + lg[lane].pu + s < bs.count;
+            const int16_t* base = bs.org + (okS ? (size_t)bs.pus[chunk * pusPerChunk + lg[lane].pu + s].orgOff : 0);
             for (int y = 0; y < 4; y++) {
               uint32_t v0 = 0, v1 = 0;
               if (okS) { v0 = (uint16_t)base[y * 4] | ((uint32_t)(uint16_t)base[y * 4 + 1] << 16); v1 = (uint16_t)base[y * 4 + 2] | ((uint32_t)(uint16_t)base[y * 4 + 3] << 16); }
@@ -82,26 +85,26 @@ void emul_chunk(int chunk, const FrameSource& fs, const BatchSource& bs, int bit
             }
           }
         } else {
-          const int16_t* base = bs.org + (size_t)bs.pus[chunk * G::PUS + lg[lane].pu].orgOff;
+          const int16_t* base = bs.org + (size_t)bs.pus[chunk * pusPerChunk + lg[lane].pu].orgOff;
           tile_load(raw, base + lg[lane].ty0 * N + lg[lane].tx0, N);
         }
       }
       if (cls == 0) src[lane] = raw;
-      else if constexpr (LOG2N == 2) tile_transpose4x4(raw, src[lane]);
+      else if (g.log2n == 2) tile_transpose4x4(raw, src[lane]);
       else tile_transpose8(raw, src[lane]);
     }
     for (int i = par; i < class_num_modes(cls); i += 2) {
       const int mode = class_mode(cls, i);
       const bool neg = mode >= 2 && mode_angle(mode) < 0;
-      if (neg) for (int lane = 0; lane < 32; lane++) if (ok[lane]) lane_build_ext<LOG2N>(sm, warp, lg[lane], cls, mode);
+      if (neg) for (int lane = 0; lane < 32; lane++) if (ok[lane]) lane_build_ext(g, smem, warp, lg[lane], cls, mode);
       for (int lane = 0; lane < 32; lane++) {
         if (!ok[lane]) continue;
-        if constexpr (LOG2N == 2) {
+        if (g.log2n == 2) {
           uint32_t c4[4];
-          lane_eval_region4(sm, warp, lg[lane], cls, mode, bitDepth, src[lane], c4);
+          lane_eval_region4(g, smem, warp, lg[lane], cls, mode, bitDepth, src[lane], c4);
           for (int s = 0; s < 4; s++) sm.acc()[(lg[lane].pu + s) * kNumModes + mode] = c4[s];
         } else {
-          sm.acc()[lg[lane].pu * kNumModes + mode] += lane_eval_tile<LOG2N>(sm, warp, lg[lane], cls, mode, bitDepth, src[lane]);
+          sm.acc()[lg[lane].pu * kNumModes + mode] += lane_eval_tile(g, smem, warp, lg[lane], cls, mode, bitDepth, src[lane]);
         }
       }
     }
