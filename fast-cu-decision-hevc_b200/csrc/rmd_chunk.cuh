@@ -110,7 +110,7 @@ struct LaneGeo {
   int subLane;   // position among the lanes that share the PU
   CUCD_HD void init(const RtGeo& g, int half, int lane) {
     const int t = half * 32 + lane;
-    if (g.log2n == 2) { pu = 4 * t; tx0 = 0; ty0 = 0; extSlot = 4 * lane; subLane = 0; }
+    if (g.log2n == 2) { pu = 4 * t; tx0 = 0; ty0 = 0; extSlot = lane; subLane = 0; }   // N = 4: sub-PU s uses ext slot s*32 + lane
     else {
       pu = t / g.tilesPerPu;
       const int q = t - pu * g.tilesPerPu;
@@ -123,24 +123,23 @@ struct LaneGeo {
 };
 
 // Build the extended main reference(s) of a negative-angle mode for the PU(s) this lane works on
-// (TComPrediction.cpp:300-322).  Lanes that share a PU split its 2N+1 entries.
+// (TComPrediction.cpp:300-322): ref[k] = side[(128 + |k|*invAngle) >> 8] for k = -1 .. lastIdx+1 and a
+// copy of main[0..N] behind it so that a row window can straddle k = 0.  Lanes that share a PU split
+// the entries.  Entries outside [lastIdx+1, N] are never consumed (they are only touched as the unused
+// half of an aligned word), so they are left as they are.
 CUCD_HD void lane_build_ext(const RtGeo& g, unsigned char* smem, int warp, const LaneGeo& lg, int cls, int mode) {
   const int N = g.n;
   const int angle = mode_angle(mode), inv = mode_inv_angle(mode);
-  const int lastIdx = (N * angle) >> 5;
+  const int nNeg = -((N * angle) >> 5) - 1;          // projected entries k = -1 .. -nNeg
   const int fo = mode_uses_filtered_rt(g.log2n, mode) ? 2 * g.as : 0;
   int16_t* s16 = reinterpret_cast<int16_t*>(smem);
   const int nsub = g.log2n == 2 ? 4 : 1, step = g.log2n == 2 ? 1 : g.lanesPerPu;
   for (int s = 0; s < nsub; s++) {
-    const int arr0 = g.arrs16 + (lg.pu + s) * g.puStride + fo;
+    const int arr0 = g.arrs16 + pu_slot_rt(g.log2n, lg.pu + s) * g.puStride + fo;
     const int main0 = arr0 + (cls ? g.as : 0), side0 = arr0 + (cls ? 0 : g.as);
-    const int e0 = g.ext16 + warp * g.extPerWarp + (lg.extSlot + s) * g.xs + N;       // element k = 0
-    for (int i = lg.subLane; i < g.xs; i += step) {
-      const int k = i - N;
-      int16_t v = 0;
-      if (k <= N && k > lastIdx) v = ext_ref_sample(s16, main0, side0, inv, k);
-      s16[e0 + k] = v;
-    }
+    const int e0 = g.ext16 + warp * g.extPerWarp + (lg.extSlot + 32 * s) * g.xs + N;  // element k = 0
+    for (int j = 1 + lg.subLane; j <= nNeg; j += step) s16[e0 - j] = s16[side0 + ((128 + j * inv) >> 8)];
+    for (int k = lg.subLane; k <= N; k += step) s16[e0 + k] = s16[main0 + k];
   }
 }
 
@@ -151,7 +150,7 @@ CUCD_HD void block_residual(const RtGeo& g, const unsigned char* smem, int warp,
   const int16_t* s16 = reinterpret_cast<const int16_t*>(smem);
   const uint32_t* s32 = reinterpret_cast<const uint32_t*>(smem);
   const int fo = mode_uses_filtered_rt(g.log2n, mode) ? 2 * g.as : 0;
-  const int arr0 = g.arrs16 + pu * g.puStride + fo;
+  const int arr0 = g.arrs16 + pu_slot_rt(g.log2n, pu) * g.puStride + fo;
   const int main0 = arr0 + (cls ? g.as : 0), side0 = arr0 + (cls ? 0 : g.as);
   if (mode == 0) resid_planar<ROWS, WORDS>(g.log2n, s16, main0, side0, x0, y0, src, 4, d);
   else if (mode == 1) resid_dc<ROWS, WORDS>(s16, main0, side0, x0, y0, reinterpret_cast<const int16_t*>(smem + g.dcOff)[pu], g.edge != 0, src, 4, d);
@@ -175,7 +174,7 @@ CUCD_HD void lane_eval_region4(const RtGeo& g, const unsigned char* smem, int wa
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     uint32_t d[8];
-    block_residual<4, 2>(g, smem, warp, lg.pu + s, lg.extSlot + s, 0, 0, cls, mode, bitDepth, &src.r[((s >> 1) * 4) * 4 + (s & 1) * 2], d);
+    block_residual<4, 2>(g, smem, warp, lg.pu + s, lg.extSlot + 32 * s, 0, 0, cls, mode, bitDepth, &src.r[((s >> 1) * 4) * 4 + (s & 1) * 2], d);
     cost[s] = satd4x4_packed(d);
   }
 }

@@ -73,15 +73,23 @@ CUCD_HD int imin32(int a, int b) { return a < b ? a : b; }
 // mode tables
 // ---------------------------------------------------------------------------------------------
 // signed 1/32-sample displacement per row of an angular mode (TComPrediction.cpp:280-291)
+// The two 9-entry tables {0,2,5,9,13,17,21,26,32} and {0,4096,1638,910,630,482,390,315,256} are packed
+// into 64-bit immediates (8 bits / 16 bits per entry): a table in local memory would cost a store and a
+// load per lookup inside the mode loop.
 CUCD_HD int mode_angle(int mode) {
-  const int ang[9] = {0, 2, 5, 9, 13, 17, 21, 26, 32};
   const int am = mode >= 18 ? mode - 26 : 10 - mode;
-  return am < 0 ? -ang[-am] : ang[am];
+  const int a = am < 0 ? -am : am;
+  const unsigned long long lo = 0x1a15110d09050200ull;        // entries 0..7
+  const int v = a == 8 ? 32 : (int)((lo >> (8 * a)) & 0xffu);
+  return am < 0 ? -v : v;
 }
 CUCD_HD int mode_inv_angle(int mode) {
-  const int inv[9] = {0, 4096, 1638, 910, 630, 482, 390, 315, 256};
   const int am = mode >= 18 ? mode - 26 : 10 - mode;
-  return inv[am < 0 ? -am : am];
+  const int a = am < 0 ? -am : am;
+  const unsigned long long t0 = 0x038e066610000000ull;        // entries 0..3: 0, 4096, 1638, 910
+  const unsigned long long t1 = 0x013b018601e20276ull;        // entries 4..7: 630, 482, 390, 315
+  if (a == 8) return 256;
+  return (int)(((a < 4 ? t0 : t1) >> (16 * (a & 3))) & 0xffffu);
 }
 // TComPattern.cpp:523-548 with the luma row of m_aucIntraFilter (TComPrediction.cpp:50-67)
 template <int LOG2N>
@@ -110,12 +118,20 @@ struct Geo {
   static constexpr int AS = 2 * N + 6;                  // one ascending ref array: corner + 2N samples + over-read pad
   static constexpr bool HAS_FILT = (LOG2N >= 3 && LOG2N <= 5);
   static constexpr int NARR = HAS_FILT ? 4 : 2;         // Tu, Lu [, Tf, Lf]
-  static constexpr int PU_STRIDE = NARR * AS;           // int16 per PU
+  // int16 per PU, padded so that the stride is an ODD number of 32-bit words: lanes that read the same
+  // offset of different PUs then hit 32 different shared-memory banks
+  static constexpr int PU_STRIDE = (NARR * AS) + ((((NARR * AS) / 2) & 1) ? 0 : 2);
   static constexpr int TILES_PER_PU = (N >= 8) ? (N / 8) * (N / 8) : 1;
   static constexpr int PUS_PER_WARP = (N >= 8) ? ((32 / TILES_PER_PU) > 0 ? (32 / TILES_PER_PU) : 1) : 128;
-  static constexpr int XS = 2 * N + 6;                  // extended (negative-angle) ref array: [-N .. N] + pad
+  static constexpr int XS = (2 * N + 6) + ((((2 * N + 6) / 2) & 1) ? 0 : 2);   // extended ref array [-N .. N] + pad, odd word count
   static constexpr int EXT_PER_WARP = PUS_PER_WARP * XS;
 };
+
+// Where PU p of a chunk keeps its arrays.  For N = 4 a lane owns PUs 4t..4t+3; storing them
+// sub-PU-major (slot = (p & 3) * 64 + (p >> 2)) makes the lane stride one PU_STRIDE (odd words) again.
+template <int LOG2N>
+CUCD_HD int pu_slot(int p) { return LOG2N == 2 ? ((p & 3) * 64 + (p >> 2)) : p; }
+CUCD_HD int pu_slot_rt(int log2n, int p) { return log2n == 2 ? ((p & 3) * 64 + (p >> 2)) : p; }
 
 // ---------------------------------------------------------------------------------------------
 // border construction (phases; `tid`/`nthreads` make them replayable on the host)
@@ -221,7 +237,7 @@ CUCD_HD void border_derive(int tid, int nthreads, int bitDepth, int strongEnable
   for (int idx = tid; idx < G::PUS * LEN; idx += nthreads) {
     const int p = idx / LEN, i = idx - p * LEN;
     const int16_t* b = lin + p * G::LIN;
-    int16_t* a = arrs + p * G::PU_STRIDE;
+    int16_t* a = arrs + pu_slot<LOG2N>(p) * G::PU_STRIDE;
     const int v = b[i];
     // position in the ascending arrays
     if (i >= 2 * N) a[0 * G::AS + (i - 2 * N)] = (int16_t)v;           // Tu
@@ -257,7 +273,8 @@ CUCD_HD void border_pad(int tid, int nthreads, int16_t* arrs) {
   constexpr int N = G::N, PAD = G::AS - (2 * N + 1);
   for (int idx = tid; idx < G::PUS * G::NARR * PAD; idx += nthreads) {
     const int arr = idx / PAD, k = idx - arr * PAD;
-    arrs[arr * G::AS + 2 * N + 1 + k] = 0;
+    const int p = arr / G::NARR, which = arr - p * G::NARR;
+    arrs[p * G::PU_STRIDE + which * G::AS + 2 * N + 1 + k] = 0;
   }
 }
 // DC value of every PU (TComPrediction.cpp:183-222 with bAbove = bLeft = true), from the unfiltered arrays
@@ -266,7 +283,7 @@ CUCD_HD void border_dc(int tid, int nthreads, const int16_t* arrs, int16_t* dc /
   typedef Geo<LOG2N> G;
   constexpr int N = G::N;
   for (int p = tid; p < G::PUS; p += nthreads) {
-    const int16_t* a = arrs + p * G::PU_STRIDE;
+    const int16_t* a = arrs + pu_slot<LOG2N>(p) * G::PU_STRIDE;
     int sum = N;
     for (int k = 1; k <= N; k++) sum += a[k] + a[G::AS + k];
     dc[p] = (int16_t)(sum >> (LOG2N + 1));
