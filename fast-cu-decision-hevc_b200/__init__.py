@@ -9,6 +9,7 @@ The directory name contains hyphens, so import it with::
 
     import importlib; cucd = importlib.import_module("fast-cu-decision-hevc_b200")
 """
+from .sharding import FORK_PERIOD, shard_independent, shard_pictures  # noqa: F401
 from .binding import (  # noqa: F401
     CucdError,
     Engine,

@@ -51,7 +51,7 @@ struct cucd_handle {
   cucd_config cfg;
   int ctusPerRow = 0, ctusPerCol = 0, ctusPerPic = 0, pitch = 0;
   size_t planeSamples = 0;
-  cudaStream_t sMain = nullptr, sFeat = nullptr;
+  cudaStream_t sMain = nullptr, sFeat = nullptr, sGrp[2] = {nullptr, nullptr};
   cudaEvent_t evUp = nullptr, evHist = nullptr;
   static constexpr int kTimeRing = 64;
   cudaEvent_t evRmd0[kTimeRing] = {}, evRmd1[kTimeRing] = {};
@@ -156,6 +156,8 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   const size_t P = (size_t)cfg->max_pictures;
   bool ok = cudaStreamCreateWithFlags(&h->sMain, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->sFeat, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->sGrp[0], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->sGrp[1], cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->evUp, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->evHist, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < cucd_handle::kTimeRing; i++) ok = ok && cudaEventCreate(&h->evRmd0[i]) == cudaSuccess && cudaEventCreate(&h->evRmd1[i]) == cudaSuccess;
@@ -189,6 +191,7 @@ int cucd_destroy(cucd_handle* h) {
   for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
   if (h->evUp) cudaEventDestroy(h->evUp);
   if (h->evHist) cudaEventDestroy(h->evHist);
+  for (int i = 0; i < 2; i++) if (h->sGrp[i]) cudaStreamDestroy(h->sGrp[i]);
   if (h->sMain) cudaStreamDestroy(h->sMain);
   if (h->sFeat) cudaStreamDestroy(h->sFeat);
   delete h;
@@ -329,18 +332,27 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
   CK(launch_feature_hist(fp, nPics, h->dHist.p, h->sFeat, &h->launches));
   CK(cudaMemcpyAsync(h->hHist.p, h->dHist.p, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sFeat));
   CK(cudaEventRecord(h->evHist, h->sFeat));
-  // ---- RMD replay on sMain (overlaps the host TCM fit) -----------------------------------------
+  // ---- RMD replay, pipelined in sub-groups of pictures over two streams: the device-to-host copy of a
+  //      group's cost tables (the bulk of the PCIe traffic) overlaps the kernel of the next group, and all
+  //      of it overlaps the host TCM fit ---------------------------------------------------------------
   if (wantRmd) {
-    for (int p = 0; p < nPics; p++) {
-      CK(cudaMemcpy2DAsync(h->dRec.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, recY[p], (size_t)strideRec * 2, (size_t)W * 2, H,
-                           cudaMemcpyHostToDevice, h->sMain));
-    }
-    CK(cudaStreamWaitEvent(h->sMain, h->evUp, 0));
-    const FrameSource fs = make_frame_source(h, h->dOrg.p, (long long)h->planeSamples, h->pitch, h->dRec.p, (long long)h->planeSamples, h->pitch, h->dCost.p);
-    CK(launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
     const size_t perPic = (size_t)h->ctusPerPic * kPusPerCtu * kNumModes;
-    for (int p = 0; p < nPics; p++)
-      if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
+    const int grp = std::max(1, (nPics + 3) / 4);
+    for (int s = 0; s < 2; s++) CK(cudaStreamWaitEvent(h->sGrp[s], h->evUp, 0));
+    int gi = 0;
+    for (int first = 0; first < nPics; first += grp, gi++) {
+      cudaStream_t st = h->sGrp[gi & 1];
+      const int n = std::min(grp, nPics - first);
+      for (int p = first; p < first + n; p++)
+        CK(cudaMemcpy2DAsync(h->dRec.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, recY[p], (size_t)strideRec * 2, (size_t)W * 2, H,
+                             cudaMemcpyHostToDevice, st));
+      const FrameSource fs = make_frame_source(h, h->dOrg.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
+                                               h->dRec.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
+                                               h->dCost.p + (size_t)first * perPic);
+      CK(launch_rmd_frames(fs, n, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches));
+      for (int p = first; p < first + n; p++)
+        if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
   }
   // ---- host: TCM fit per picture and frequency -------------------------------------------------
   CK(cudaEventSynchronize(h->evHist));
@@ -373,7 +385,8 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
     if (o.ctu_src_had) CK(cudaMemcpyAsync(o.ctu_src_had, h->dCtuHad.p + (size_t)p * h->ctusPerPic, (size_t)h->ctusPerPic * 4, cudaMemcpyDeviceToHost, h->sFeat));
   }
   CK(cudaStreamSynchronize(h->sFeat));
-  CK(cudaStreamSynchronize(h->sMain));
+  CK(cudaStreamSynchronize(h->sGrp[0]));
+  CK(cudaStreamSynchronize(h->sGrp[1]));
   flush_launches(h);
   return CUCD_OK;
 }
