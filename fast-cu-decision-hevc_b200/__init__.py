@@ -17,6 +17,7 @@ from .binding import (  # noqa: F401
     NUM_MODES,
     PUS_PER_CTU,
     declared_symbols,
+    exp_satd_tc,
     load_library,
     tcm_fit,
 )

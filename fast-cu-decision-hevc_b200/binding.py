@@ -108,6 +108,21 @@ def tcm_fit(hist, n_blocks):
     return yc, thr
 
 
+def exp_satd_tc(org, pred, iters=1):
+    """cucd_exp_satd_tc: (nTiles, 64) uint8 source and prediction tiles -> (satd uint32[nTiles], mean kernel ms)."""
+    lib = load_library()
+    org = np.ascontiguousarray(org, np.uint8)
+    pred = np.ascontiguousarray(pred, np.uint8)
+    n = org.shape[0]
+    out = np.zeros(n, np.uint32)
+    ms = C.c_float(0)
+    lib.cucd_exp_satd_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    rc = lib.cucd_exp_satd_tc(org.ctypes.data, pred.ctypes.data, n, out.ctypes.data, int(iters), C.byref(ms))
+    if rc != 0:
+        raise CucdError(f"cucd_exp_satd_tc failed ({rc})")
+    return out, float(ms.value)
+
+
 def _plane(a):
     a = np.asarray(a)
     if a.dtype != np.int16 or a.ndim != 2 or a.strides[1] != 2 or a.strides[0] % 2:

@@ -156,6 +156,11 @@ int cucd_rmd_kernel_time(cucd_handle* h, int nCalls, float* avg_ms);
  * of ONE picture, nBlocks = (W/4)*(H/4); writes yc[16] and thr[16] */
 int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr);
 
+/* Experimental building block (csrc/satd_tc.cuh): 8x8 Hadamard SATD of nTiles (multiple of 128) 8-bit
+ * tiles on the tcgen05 tensor cores (kind::i8); host buffers, org/pred = nTiles*64 bytes row-major 8x8,
+ * satd[i] = (sum|H(o-p)| + 2) >> 2 as xCalcHADs8x8 (TComRdCost.cpp:1439-1534).  avg_ms = mean kernel time. */
+int cucd_exp_satd_tc(const uint8_t* org, const uint8_t* pred, int nTiles, uint32_t* satd, int iters, float* avg_ms);
+
 #ifdef __cplusplus
 }
 #endif
