@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -63,6 +64,8 @@ struct cucd_handle {
   // frame path
   DevBuf<int16_t> dOrg, dRec, dObf, dOutlier;
   DevBuf<uint32_t> dCost, dHist;
+  DevBuf<int8_t> dHadamard;       // +-(H8 x H8), +-(blockdiag H4 x H4) operands of the tensor-core SATD
+  int useTensor = 0;              // 8-bit content: tcgen05 Hadamard path (cucd_set_rmd_path)
   DevBuf<int32_t> dThr, dNum[4], dSum[4], dCtuHad;
   PinBuf<uint32_t> hHist;
   PinBuf<int32_t> hThr;
@@ -107,6 +110,11 @@ FeaturePlanes make_feature_planes(const cucd_handle* h, const int16_t* org, long
   fp.org = org; fp.orgPicStride = orgPic; fp.orgStride = orgStride; fp.W = h->cfg.width; fp.H = h->cfg.height;
   fp.ctusPerRow = h->ctusPerRow; fp.ctusPerPic = h->ctusPerPic; fp.bitDepth = h->cfg.bit_depth;
   return fp;
+}
+
+cudaError_t launch_rmd_auto(cucd_handle* h, const FrameSource& fs, int nPics, cudaStream_t st) {
+  if (h->useTensor) return launch_rmd_frames_tc(fs, nPics, h->cfg.strong_intra_smoothing, h->dHadamard.p, st, &h->launches);
+  return launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches);
 }
 
 // parallel-for over [0, n) on up to `threads` host threads
@@ -168,6 +176,10 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   ok = ok && h->dOutlier.reserve(P * (size_t)cfg->width * cfg->height) == cudaSuccess;
   for (int d = 0; d < 4; d++) ok = ok && h->dNum[d].reserve(P * std::max<size_t>(1, h->cuCount[d])) == cudaSuccess && h->dSum[d].reserve(P * std::max<size_t>(1, h->cuCount[d])) == cudaSuccess;
   ok = ok && h->dCtuHad.reserve(P * h->ctusPerPic) == cudaSuccess;
+  ok = ok && h->dHadamard.reserve(16384) == cudaSuccess && launch_hadamard_operands(h->dHadamard.p, h->sMain) == cudaSuccess &&
+       cudaStreamSynchronize(h->sMain) == cudaSuccess;
+  h->useTensor = cfg->bit_depth == 8 ? 1 : 0;
+  { const char* e = getenv("CUCD_RMD_PATH"); if (e && !strcmp(e, "alu")) h->useTensor = 0; }
   ok = ok && h->hHist.reserve(P * kHistFreqs * kHistBins) == cudaSuccess && h->hThr.reserve(P * kHistFreqs) == cudaSuccess;
   if (!ok) {
     const std::string msg = std::string("cucd_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -184,7 +196,7 @@ int cucd_destroy(cucd_handle* h) {
   cudaDeviceSynchronize();
   h->dOrg.release(); h->dRec.release(); h->dObf.release(); h->dOutlier.release(); h->dCost.release(); h->dHist.release(); h->dThr.release();
   for (int d = 0; d < 4; d++) { h->dNum[d].release(); h->dSum[d].release(); }
-  h->dCtuHad.release(); h->hHist.release(); h->hThr.release();
+  h->dCtuHad.release(); h->hHist.release(); h->hThr.release(); h->dHadamard.release();
   h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
   for (auto& r : h->refs) r.buf.release();
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
@@ -195,6 +207,13 @@ int cucd_destroy(cucd_handle* h) {
   if (h->sMain) cudaStreamDestroy(h->sMain);
   if (h->sFeat) cudaStreamDestroy(h->sFeat);
   delete h;
+  return CUCD_OK;
+}
+
+int cucd_set_rmd_path(cucd_handle* h, int use_tensor_cores) {
+  if (!h) return CUCD_ERR_INVALID;
+  if (use_tensor_cores && h->cfg.bit_depth != 8) return fail(h, CUCD_ERR_UNSUPPORTED, "cucd_set_rmd_path: the tcgen05 kind::i8 path needs 8-bit content");
+  h->useTensor = use_tensor_cores ? 1 : 0;
   return CUCD_OK;
 }
 
@@ -228,7 +247,7 @@ int cucd_dev_rmd_frames(cucd_handle* h, void* stream, int nPics, const int16_t* 
   if ((orgStride & 7) || (orgPicStride & 7) || ((uintptr_t)d_org & 15)) return fail(h, CUCD_ERR_INVALID, "cucd_dev_rmd_frames: source plane must be 16-byte aligned with strides multiple of 8");
   CK(cudaSetDevice(h->cfg.device));
   const FrameSource fs = make_frame_source(h, d_org, orgPicStride, orgStride, d_rec, recPicStride, recStride, d_rmd_cost);
-  CK(launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, (cudaStream_t)stream, &h->launches));
+  CK(launch_rmd_auto(h, fs, nPics, (cudaStream_t)stream));
   flush_launches(h);
   return CUCD_OK;
 }
@@ -281,7 +300,7 @@ int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_or
     const FrameSource fs = make_frame_source(h, d_org, orgPicStride, orgStride, d_rec, recPicStride, recStride, out->rmd_cost);
     const int slot = (int)(h->rmdCalls % cucd_handle::kTimeRing);
     CK(cudaEventRecord(h->evRmd0[slot], st));
-    CK(launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches));
+    CK(launch_rmd_auto(h, fs, nPics, st));
     CK(cudaEventRecord(h->evRmd1[slot], st));
     h->rmdCalls++;
   }
@@ -349,7 +368,7 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
       const FrameSource fs = make_frame_source(h, h->dOrg.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
                                                h->dRec.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
                                                h->dCost.p + (size_t)first * perPic);
-      CK(launch_rmd_frames(fs, n, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches));
+      CK(launch_rmd_auto(h, fs, n, st));
       for (int p = first; p < first + n; p++)
         if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }

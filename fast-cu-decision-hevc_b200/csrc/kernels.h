@@ -11,6 +11,9 @@ constexpr int kHistFreqs = 16;      // index 0 (DC) unused
 
 // ---- intra RMD (rmd_kernels.cu) ---------------------------------------------------------------
 cudaError_t launch_rmd_frames(const FrameSource& fs, int nPics, int bitDepth, int strong, cudaStream_t st, int* launches);
+// tensor-core (tcgen05 kind::i8) variant for 8-bit content; `hadamard` = 16 KB prepared by launch_hadamard_operands
+cudaError_t launch_rmd_frames_tc(const FrameSource& fs, int nPics, int strong, const int8_t* hadamard, cudaStream_t st, int* launches);
+cudaError_t launch_hadamard_operands(int8_t* dst, cudaStream_t st);
 cudaError_t launch_rmd_batch(int log2n, const BatchSource& bs, int bitDepth, int strong, cudaStream_t st, int* launches);
 
 // ---- per-picture texture features (feature_kernels.cu) ----------------------------------------

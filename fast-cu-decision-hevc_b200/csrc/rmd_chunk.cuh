@@ -143,29 +143,31 @@ CUCD_HD void lane_build_ext(const RtGeo& g, unsigned char* smem, int warp, const
   }
 }
 
-// Residual of one block (8x8 tile: ROWS 8 / WORDS 4, 4x4 PU: ROWS 4 / WORDS 2) for one mode.
+// Prediction of one block (8x8 tile: ROWS 8 / WORDS 4, 4x4 PU: ROWS 4 / WORDS 2) for one mode, as packed pairs.
 template <int ROWS, int WORDS>
-CUCD_HD void block_residual(const RtGeo& g, const unsigned char* smem, int warp, int pu, int extSlot, int x0, int y0, int cls, int mode,
-                            int bitDepth, const uint32_t* src, uint32_t* d) {
+CUCD_HD void block_predict(const RtGeo& g, const unsigned char* smem, int warp, int pu, int extSlot, int x0, int y0, int cls, int mode,
+                           int bitDepth, uint32_t* p) {
   const int16_t* s16 = reinterpret_cast<const int16_t*>(smem);
   const uint32_t* s32 = reinterpret_cast<const uint32_t*>(smem);
   const int fo = mode_uses_filtered_rt(g.log2n, mode) ? 2 * g.as : 0;
   const int arr0 = g.arrs16 + pu_slot_rt(g.log2n, pu) * g.puStride + fo;
   const int main0 = arr0 + (cls ? g.as : 0), side0 = arr0 + (cls ? 0 : g.as);
-  if (mode == 0) resid_planar<ROWS, WORDS>(g.log2n, s16, main0, side0, x0, y0, src, 4, d);
-  else if (mode == 1) resid_dc<ROWS, WORDS>(s16, main0, side0, x0, y0, reinterpret_cast<const int16_t*>(smem + g.dcOff)[pu], g.edge != 0, src, 4, d);
+  if (mode == 0) pred_planar<ROWS, WORDS>(g.log2n, s16, main0, side0, x0, y0, p);
+  else if (mode == 1) pred_dc<ROWS, WORDS>(s16, main0, side0, x0, y0, reinterpret_cast<const int16_t*>(smem + g.dcOff)[pu], g.edge != 0, p);
   else {
     const int angle = mode_angle(mode);
     const int m0 = angle < 0 ? g.ext16 + warp * g.extPerWarp + extSlot * g.xs + g.n : main0;
-    resid_angular_frac<ROWS, WORDS>(s32, m0, x0, y0, angle, src, 4, d);
-    if (angle == 0 && g.edge && x0 == 0) patch_pure_edge<ROWS, WORDS>(s16, main0, side0, y0, (1 << bitDepth) - 1, src, 4, d);
+    pred_angular<ROWS, WORDS>(s32, m0, x0, y0, angle, p);
+    if (angle == 0 && g.edge && x0 == 0) patch_pure_edge<ROWS, WORDS>(s16, main0, side0, y0, (1 << bitDepth) - 1, p);
   }
 }
 
 // N >= 8: SATD of the lane's tile for one mode.  `src` is the tile in the orientation of the warp class.
 CUCD_HD uint32_t lane_eval_tile(const RtGeo& g, const unsigned char* smem, int warp, const LaneGeo& lg, int cls, int mode, int bitDepth, const Tile& src) {
   uint32_t d[32];
-  block_residual<8, 4>(g, smem, warp, lg.pu, lg.extSlot, cls ? lg.ty0 : lg.tx0, cls ? lg.tx0 : lg.ty0, cls, mode, bitDepth, src.r, d);
+  block_predict<8, 4>(g, smem, warp, lg.pu, lg.extSlot, cls ? lg.ty0 : lg.tx0, cls ? lg.tx0 : lg.ty0, cls, mode, bitDepth, d);
+#pragma unroll
+  for (int k = 0; k < 32; k++) d[k] = src.r[k] - d[k];
   return satd8x8_packed(d);
 }
 
@@ -174,7 +176,10 @@ CUCD_HD void lane_eval_region4(const RtGeo& g, const unsigned char* smem, int wa
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     uint32_t d[8];
-    block_residual<4, 2>(g, smem, warp, lg.pu + s, lg.extSlot + 32 * s, 0, 0, cls, mode, bitDepth, &src.r[((s >> 1) * 4) * 4 + (s & 1) * 2], d);
+    block_predict<4, 2>(g, smem, warp, lg.pu + s, lg.extSlot + 32 * s, 0, 0, cls, mode, bitDepth, d);
+    const uint32_t* sp = &src.r[((s >> 1) * 4) * 4 + (s & 1) * 2];
+#pragma unroll
+    for (int y = 0; y < 4; y++) { d[y * 2] = sp[y * 4] - d[y * 2]; d[y * 2 + 1] = sp[y * 4 + 1] - d[y * 2 + 1]; }
     cost[s] = satd4x4_packed(d);
   }
 }

@@ -123,7 +123,7 @@ struct Geo {
   static constexpr int PU_STRIDE = (NARR * AS) + ((((NARR * AS) / 2) & 1) ? 0 : 2);
   static constexpr int TILES_PER_PU = (N >= 8) ? (N / 8) * (N / 8) : 1;
   static constexpr int PUS_PER_WARP = (N >= 8) ? ((32 / TILES_PER_PU) > 0 ? (32 / TILES_PER_PU) : 1) : 128;
-  static constexpr int XS = (2 * N + 6) + ((((2 * N + 6) / 2) & 1) ? 0 : 2);   // extended ref array [-N .. N] + pad, odd word count
+  static constexpr int XS = 2 * N + 2;                  // extended ref array [-N .. N+1]: N+1 words, an odd count for every N
   static constexpr int EXT_PER_WARP = PUS_PER_WARP * XS;
 };
 
@@ -410,9 +410,15 @@ CUCD_HD void load_row_window(const uint32_t* smem32, int a, uint32_t* A /*WORDS*
   }
 }
 
-// angular, |angle| not in {0, 32}: two-tap 1/32 interpolation (TComPrediction.cpp:368-383)
+// All predictors write the PREDICTION as packed pairs p[y*WORDS + j] = (pred[y][2j], pred[y][2j+1]);
+// the ALU path then forms src - p, the tensor-core path stores p as bytes (rmd_tc.cuh).
+//
+// Angular, any angle: two-tap 1/32 interpolation (TComPrediction.cpp:368-383).  With f == 0 the
+// interpolation degenerates to an exact copy ((32*a + 16) >> 5 == a), so |angle| == 32 and angle == 0
+// need no code of their own (one hot loop body keeps the instruction footprint small - the kernel is
+// instruction-fetch sensitive).
 template <int ROWS, int WORDS>
-CUCD_HD void resid_angular_frac(const uint32_t* smem32, int main0, int x0, int y0, int angle, const uint32_t* src, int srcStride, uint32_t* d) {
+CUCD_HD void pred_angular(const uint32_t* smem32, int main0, int x0, int y0, int angle, uint32_t* p) {
 #pragma unroll
   for (int y = 0; y < ROWS; y++) {
     const int delta = (y0 + y + 1) * angle;
@@ -423,37 +429,31 @@ CUCD_HD void resid_angular_frac(const uint32_t* smem32, int main0, int x0, int y
 #pragma unroll
     for (int j = 0; j < WORDS; j++) {
       const uint32_t t = A[j] * (32u - f) + (B[j] * f + 0x00100010u);
-      d[y * WORDS + j] = src[y * srcStride + j] - ((t >> 5) & 0x07ff07ffu);
+      p[y * WORDS + j] = (t >> 5) & 0x07ff07ffu;
     }
   }
 }
-// Every angular mode goes through resid_angular_frac: with f == 0 the interpolation degenerates to an
-// exact copy ((32*a + 16) >> 5 == a), so |angle| == 32 and angle == 0 need no code of their own (one
-// hot loop body keeps the instruction footprint small - the kernel is instruction-fetch sensitive).
-// Pure vertical / horizontal modes then only patch the first column for the luma edge filter of
-// N <= 16 (TComPrediction.cpp:346-363): pred[y][0] = clip(ref[1] + ((side[y+1] - side[0]) >> 1)).
+// Pure vertical / horizontal modes patch the first column for the luma edge filter of N <= 16
+// (TComPrediction.cpp:346-363): pred[y][0] = clip(ref[1] + ((side[y+1] - side[0]) >> 1)).
 template <int ROWS, int WORDS>
-CUCD_HD void patch_pure_edge(const int16_t* smem16, int main0, int side0, int y0, int maxVal, const uint32_t* src, int srcStride, uint32_t* d) {
+CUCD_HD void patch_pure_edge(const int16_t* smem16, int main0, int side0, int y0, int maxVal, uint32_t* p) {
   const int s0 = smem16[side0], m1 = smem16[main0 + 1];
 #pragma unroll
   for (int y = 0; y < ROWS; y++) {
     int v = m1 + ((smem16[side0 + y0 + y + 1] - s0) >> 1);
     v = imin32(imax32(v, 0), maxVal);
-    // d = src - pred with pred.lo = m1 so far: replace the low half's prediction by v
-    d[y * WORDS] += (uint32_t)(m1 - v);
-    (void)src; (void)srcStride;
+    p[y * WORDS] = (p[y * WORDS] & 0xffff0000u) | (uint32_t)v;
   }
 }
 // DC with edge smoothing for N <= 16 (TComPrediction.cpp:266-276, 818-841); orientation-symmetric
 template <int ROWS, int WORDS>
-CUCD_HD void resid_dc(const int16_t* smem16, int main0, int side0, int x0, int y0, int dc, bool edge,
-                      const uint32_t* src, int srcStride, uint32_t* d) {
+CUCD_HD void pred_dc(const int16_t* smem16, int main0, int side0, int x0, int y0, int dc, bool edge, uint32_t* p) {
   const uint32_t dc2 = (uint32_t)dc * 0x00010001u;
 #pragma unroll
   for (int y = 0; y < ROWS; y++)
 #pragma unroll
     for (int j = 0; j < WORDS; j++) {
-      uint32_t p = dc2;
+      uint32_t v = dc2;
       if (edge) {
         const int yy = y0 + y;
         if (yy == 0) {             // first row of the PU: filtered against the main-side neighbours
@@ -461,18 +461,18 @@ CUCD_HD void resid_dc(const int16_t* smem16, int main0, int side0, int x0, int y
           int lo = (smem16[main0 + 1 + xa] + 3 * dc + 2) >> 2;
           const int hi = (smem16[main0 + 2 + xa] + 3 * dc + 2) >> 2;
           if (xa == 0) lo = (smem16[main0 + 1] + smem16[side0 + 1] + 2 * dc + 2) >> 2;
-          p = (uint32_t)lo | ((uint32_t)hi << 16);
+          v = (uint32_t)lo | ((uint32_t)hi << 16);
         } else if (x0 == 0 && j == 0) {
           const int lo = (smem16[side0 + 1 + yy] + 3 * dc + 2) >> 2;
-          p = (p & 0xffff0000u) | (uint32_t)lo;
+          v = (v & 0xffff0000u) | (uint32_t)lo;
         }
       }
-      d[y * WORDS + j] = src[y * srcStride + j] - p;
+      p[y * WORDS + j] = v;
     }
 }
 // planar (TComPrediction.cpp:755-805); T = array along x, L = array along y
 template <int ROWS, int WORDS>
-CUCD_HD void resid_planar(const int LOG2N, const int16_t* smem16, int t0, int l0, int x0, int y0, const uint32_t* src, int srcStride, uint32_t* d) {
+CUCD_HD void pred_planar(const int LOG2N, const int16_t* smem16, int t0, int l0, int x0, int y0, uint32_t* p) {
   const int N = 1 << LOG2N;
   const int tr = smem16[t0 + 1 + N], bl = smem16[l0 + 1 + N];
   int vert[2 * WORDS], vstep[2 * WORDS];
@@ -491,7 +491,7 @@ CUCD_HD void resid_planar(const int LOG2N, const int16_t* smem16, int t0, int l0
     for (int j = 0; j < WORDS; j++) {
       const int p0 = (hor + vert[2 * j]) >> (LOG2N + 1); hor += hstep;
       const int p1 = (hor + vert[2 * j + 1]) >> (LOG2N + 1); hor += hstep;
-      d[y * WORDS + j] = src[y * srcStride + j] - ((uint32_t)p0 | ((uint32_t)p1 << 16));
+      p[y * WORDS + j] = (uint32_t)p0 | ((uint32_t)p1 << 16);
     }
 #pragma unroll
     for (int x = 0; x < 2 * WORDS; x++) vert[x] += vstep[x];

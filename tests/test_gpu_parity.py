@@ -226,3 +226,32 @@ def test_me_surfaces_vs_oracle(cucd, oracle, bd):
         assert int(eng.me_sad_surface([dict(x=64, y=64, w=32, h=32, ref_idx=0, left=0, right=0, top=0, bottom=0, sub_shift=1)])[0][0, 0]) == 0
         with pytest.raises(cucd.CucdError):
             eng.me_sad_surface([dict(x=0, y=0, w=16, h=16, ref_idx=0, left=-81, right=0, top=0, bottom=0, sub_shift=0)])
+
+
+# ---- the two Hadamard implementations (ALU butterflies vs tcgen05 kind::i8) must agree bit for bit --------
+@pytest.mark.parametrize("W,H", [(416, 240), (200, 136), (64, 64)])
+def test_tensor_core_path_equals_alu_path_and_oracle(cucd, oracle, W, H):
+    org = textured_plane(W, H, 8, seed=W)
+    rec = pseudo_recon(org, 8)
+    rec[:, : W // 2] = (np.arange(H)[:, None] // 3 + np.arange(W // 2)[None, :] // 5 + 40).astype(np.int16)
+    with cucd.Engine(W, H, max_pictures=2) as eng:
+        eng.set_rmd_path(True)
+        tc = eng.frames([org, rec], [rec, org])
+        eng.set_rmd_path(False)
+        alu = eng.frames([org, rec], [rec, org])
+    want = oracle_rmd_frame(oracle, org, rec, 8)
+    assert np.array_equal(tc[0]["rmd_cost"], want)
+    assert np.array_equal(alu[0]["rmd_cost"], want)
+    assert np.array_equal(tc[1]["rmd_cost"], alu[1]["rmd_cost"])
+
+
+def test_tensor_core_path_extreme_values(cucd, oracle):
+    W = H = 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    for org, rec in [(np.where((xx + yy) & 1, 255, 0), np.where((xx + yy) & 1, 0, 255)), (np.full((H, W), 255), np.zeros((H, W))),
+                     (np.where(xx & 1, 255, 0), np.full((H, W), 255))]:
+        org = org.astype(np.int16); rec = rec.astype(np.int16)
+        with cucd.Engine(W, H) as eng:
+            eng.set_rmd_path(True)
+            got = eng.frame(org, rec)["rmd_cost"]
+        assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8))
