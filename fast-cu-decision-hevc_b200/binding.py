@@ -322,3 +322,7 @@ class Engine:
         if n < 0:
             self._check(n, "cucd_rmd_kernel_time")
         return float(ms.value), int(n)
+
+    def set_rmd_path(self, use_tensor_cores):
+        self.lib.cucd_set_rmd_path.argtypes = [C.c_void_p, C.c_int]
+        self._check(self.lib.cucd_set_rmd_path(self.h, 1 if use_tensor_cores else 0), "cucd_set_rmd_path")

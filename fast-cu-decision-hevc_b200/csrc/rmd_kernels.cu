@@ -225,25 +225,29 @@ __device__ __noinline__ void phase_modes_tc(const int log2n, const int chunk, co
 
   for (int j = 0; j < kRounds; j++) {
     const int i = j * 2 + par, buf = j & 1;
-    if (i < nModes && ok) {
+    if (i < nModes) {                                        // warp-uniform
       const int mode = class_mode(cls, i);
       const bool neg = mode >= 2 && mode_angle(mode) < 0;
-      if (neg) { lane_build_ext(g, smem, warp, lg, cls, mode); }
-      __syncwarp();
-      uint32_t p[32];
-      if (g.log2n == 2) {
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          uint32_t q4[8];
-          block_predict<4, 2>(g, smem, warp, lg.pu + s, lg.extSlot + 32 * s, 0, 0, cls, mode, bitDepth, q4);
-#pragma unroll
-          for (int y = 0; y < 4; y++) { p[((s >> 1) * 4 + y) * 4 + (s & 1) * 2] = q4[y * 2]; p[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 1] = q4[y * 2 + 1]; }
-        }
-      } else {
-        block_predict<8, 4>(g, smem, warp, lg.pu, lg.extSlot, cls ? lg.ty0 : lg.tx0, cls ? lg.tx0 : lg.ty0, cls, mode, bitDepth, p);
+      if (neg) {
+        if (ok) lane_build_ext(g, smem, warp, lg, cls, mode);
+        __syncwarp();
       }
-      store_row_u8(sAP + buf * 8192, row, p);
-      __syncwarp();
+      if (ok) {
+        uint32_t p[32];
+        if (g.log2n == 2) {
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            uint32_t q4[8];
+            block_predict<4, 2>(g, smem, warp, lg.pu + s, lg.extSlot + 32 * s, 0, 0, cls, mode, bitDepth, q4);
+#pragma unroll
+            for (int y = 0; y < 4; y++) { p[((s >> 1) * 4 + y) * 4 + (s & 1) * 2] = q4[y * 2]; p[((s >> 1) * 4 + y) * 4 + (s & 1) * 2 + 1] = q4[y * 2 + 1]; }
+          }
+        } else {
+          block_predict<8, 4>(g, smem, warp, lg.pu, lg.extSlot, cls ? lg.ty0 : lg.tx0, cls ? lg.tx0 : lg.ty0, cls, mode, bitDepth, p);
+        }
+        store_row_u8(sAP + buf * 8192, row, p);
+      }
+      __syncwarp();                                          // the ext scratch is rewritten by the next negative-angle mode
     }
     fence_async_smem();
     tc_fence_before();

@@ -148,6 +148,10 @@ typedef struct {
 } cucd_dev_out;
 int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
                     const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
+/* Frame-mode RMD has two bit-identical implementations of the Hadamard stage: integer-ALU butterflies in
+ * registers, and (8-bit content only) tcgen05 kind::i8 tensor-core products.  Default: tensor cores for
+ * 8-bit, ALU otherwise (or CUCD_RMD_PATH=alu in the environment at create time). */
+int cucd_set_rmd_path(cucd_handle* h, int use_tensor_cores);
 /* Device time of the RMD kernel inside the last `nCalls` cucd_dev_frames calls (CUDA events recorded on the
  * caller's stream around that launch; ring of 64).  The stream must have been synchronised.  Returns
  * the number of calls averaged, or a negative status; *avg_ms = mean duration of one launch. */
