@@ -323,6 +323,7 @@ class Engine:
             self._check(n, "cucd_rmd_kernel_time")
         return float(ms.value), int(n)
 
-    def set_rmd_path(self, use_tensor_cores):
+    def set_rmd_path(self, path):
+        """0 / False: integer ALU; 1 / True: predictions + Hadamard on tcgen05 (8-bit); 2: tcgen05 Hadamard only (8-bit)"""
         self.lib.cucd_set_rmd_path.argtypes = [C.c_void_p, C.c_int]
-        self._check(self.lib.cucd_set_rmd_path(self.h, 1 if use_tensor_cores else 0), "cucd_set_rmd_path")
+        self._check(self.lib.cucd_set_rmd_path(self.h, int(path)), "cucd_set_rmd_path")

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include "../../include/cucudecide.h"
 #include "kernels.h"
+#include "rmd_tc2.cuh"
 #include "tcm_host.h"
 
 using namespace cucd;
@@ -65,7 +66,8 @@ struct cucd_handle {
   DevBuf<int16_t> dOrg, dRec, dObf, dOutlier;
   DevBuf<uint32_t> dCost, dHist;
   DevBuf<int8_t> dHadamard;       // +-(H8 x H8), +-(blockdiag H4 x H4) operands of the tensor-core SATD
-  int useTensor = 0;              // 8-bit content: tcgen05 Hadamard path (cucd_set_rmd_path)
+  DevBuf<uint8_t> dTc2Tables;     // interpolation-weight operands of the tensor-core prediction (rmd_tc2.cuh)
+  int useTensor = 0;              // 8-bit content (cucd_set_rmd_path): 1 = predictions + Hadamard on tcgen05, 2 = Hadamard only, 0 = integer ALU
   DevBuf<int32_t> dThr, dNum[4], dSum[4], dCtuHad;
   PinBuf<uint32_t> hHist;
   PinBuf<int32_t> hThr;
@@ -113,7 +115,9 @@ FeaturePlanes make_feature_planes(const cucd_handle* h, const int16_t* org, long
 }
 
 cudaError_t launch_rmd_auto(cucd_handle* h, const FrameSource& fs, int nPics, cudaStream_t st) {
-  if (h->useTensor) return launch_rmd_frames_tc(fs, nPics, h->cfg.strong_intra_smoothing, h->dHadamard.p, st, &h->launches);
+  if (h->useTensor == 1)
+    return launch_rmd_frames_tc2(fs, nPics, h->cfg.strong_intra_smoothing, h->dTc2Tables.p, h->dTc2Tables.p + tc2::kWinTableBytes, h->dHadamard.p, st, &h->launches);
+  if (h->useTensor == 2) return launch_rmd_frames_tc(fs, nPics, h->cfg.strong_intra_smoothing, h->dHadamard.p, st, &h->launches);
   return launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches);
 }
 
@@ -178,8 +182,15 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   ok = ok && h->dCtuHad.reserve(P * h->ctusPerPic) == cudaSuccess;
   ok = ok && h->dHadamard.reserve(16384) == cudaSuccess && launch_hadamard_operands(h->dHadamard.p, h->sMain) == cudaSuccess &&
        cudaStreamSynchronize(h->sMain) == cudaSuccess;
+  if (ok) {
+    std::vector<uint8_t> tab(tc2::kWinTableBytes + tc2::kN4TableBytes);
+    tc2::fill_win_tables(tab.data()); tc2::fill_n4_tables(tab.data() + tc2::kWinTableBytes);
+    ok = h->dTc2Tables.reserve(tab.size()) == cudaSuccess && cudaMemcpy(h->dTc2Tables.p, tab.data(), tab.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
   h->useTensor = cfg->bit_depth == 8 ? 1 : 0;
-  { const char* e = getenv("CUCD_RMD_PATH"); if (e && !strcmp(e, "alu")) h->useTensor = 0; }
+  { const char* e = getenv("CUCD_RMD_PATH");
+    if (e && !strcmp(e, "alu")) h->useTensor = 0;
+    if (e && !strcmp(e, "tc1") && cfg->bit_depth == 8) h->useTensor = 2; }
   ok = ok && h->hHist.reserve(P * kHistFreqs * kHistBins) == cudaSuccess && h->hThr.reserve(P * kHistFreqs) == cudaSuccess;
   if (!ok) {
     const std::string msg = std::string("cucd_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -196,7 +207,7 @@ int cucd_destroy(cucd_handle* h) {
   cudaDeviceSynchronize();
   h->dOrg.release(); h->dRec.release(); h->dObf.release(); h->dOutlier.release(); h->dCost.release(); h->dHist.release(); h->dThr.release();
   for (int d = 0; d < 4; d++) { h->dNum[d].release(); h->dSum[d].release(); }
-  h->dCtuHad.release(); h->hHist.release(); h->hThr.release(); h->dHadamard.release();
+  h->dCtuHad.release(); h->hHist.release(); h->hThr.release(); h->dHadamard.release(); h->dTc2Tables.release();
   h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
   for (auto& r : h->refs) r.buf.release();
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
@@ -213,7 +224,8 @@ int cucd_destroy(cucd_handle* h) {
 int cucd_set_rmd_path(cucd_handle* h, int use_tensor_cores) {
   if (!h) return CUCD_ERR_INVALID;
   if (use_tensor_cores && h->cfg.bit_depth != 8) return fail(h, CUCD_ERR_UNSUPPORTED, "cucd_set_rmd_path: the tcgen05 kind::i8 path needs 8-bit content");
-  h->useTensor = use_tensor_cores ? 1 : 0;
+  if (use_tensor_cores < 0 || use_tensor_cores > 2) return fail(h, CUCD_ERR_INVALID, "cucd_set_rmd_path: path must be 0, 1 or 2");
+  h->useTensor = use_tensor_cores;
   return CUCD_OK;
 }
 

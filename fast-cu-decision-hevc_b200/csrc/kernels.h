@@ -14,6 +14,10 @@ cudaError_t launch_rmd_frames(const FrameSource& fs, int nPics, int bitDepth, in
 // tensor-core (tcgen05 kind::i8) variant for 8-bit content; `hadamard` = 16 KB prepared by launch_hadamard_operands
 cudaError_t launch_rmd_frames_tc(const FrameSource& fs, int nPics, int strong, const int8_t* hadamard, cudaStream_t st, int* launches);
 cudaError_t launch_hadamard_operands(int8_t* dst, cudaStream_t st);
+// predictions AND Hadamard on tcgen05 (rmd_tc2_kernels.cu); tabWin / tabN4 = tc2::fill_win_tables / fill_n4_tables uploaded by the caller
+cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
+                                  cudaStream_t st, int* launches);
+int rmd_tc2_smem_bytes();
 cudaError_t launch_rmd_batch(int log2n, const BatchSource& bs, int bitDepth, int strong, cudaStream_t st, int* launches);
 
 // ---- per-picture texture features (feature_kernels.cu) ----------------------------------------

@@ -1,0 +1,392 @@
+// rmd_tc2.cuh - per-thread logic of the tensor-core RMD frame kernel (8-bit content, sm_100a).
+//
+// Both the 33 angular PREDICTIONS and the Hadamard SATD run on tcgen05 (kind::i8); the integer ALU only
+// moves bytes.  Everything here is `__host__ __device__` like rmd_core.cuh, so tests/emul replays the
+// kernel's phases on the CPU with the two tensor-core products replaced by exact integer matmuls.
+//
+// The arithmetic (reference file:line):
+//   angular prediction  TComPrediction.cpp:278-409   pred = ((32-f)*ref[k] + f*ref[k+1] + 16) >> 5
+//   projection          TComPrediction.cpp:300-322   ref[k<0] = side[(128 + |k|*invAngle) >> 8]
+//   SATD                TComRdCost.cpp:1343-1604
+//
+// MMA 1 (prediction).  A row of the A operand is the tile's WINDOW of its main reference array: 31
+// consecutive u8 samples ref[k0 .. k0+30] and a constant 1.  B holds, for every pixel of the 8x8 tile, the
+// two interpolation weights scaled by 8 (8*(32-f) <= 248, 8*f) at the pixel's window slots and the rounding
+// term 128 at the constant's slot, so   D = 8 * ((32-f)*a + f*b + 16)   and   pred = byte 1 of D.
+// (f == 0: weight 255 and constant 255 give (256*a + (255 - a)) >> 8 = a.)  B depends only on the angle
+// and on (tile row offset * angle) mod 32, which takes at most 4 values ("phase class"); the 128 rows of
+// one MMA share a phase class by construction of the row map.  For N = 4 a row is an 8x8 REGION of four
+// PUs, K = 64 (one 16-byte record per PU: main[0..8], side[1..5], 1) and B is block diagonal with the
+// negative-angle projection folded into the weights.
+// MMA 2 (Hadamard).  A = the 64 predicted bytes of the row, B = +(H8 (x) H8) (or block-diagonal H4 (x) H4);
+// the epilogue sums |D - Ho| against the row's transformed SOURCE tile Ho, which every thread keeps in 64
+// registers for the whole CTA.
+#pragma once
+#include "rmd_chunk.cuh"
+
+namespace cucd {
+namespace tc2 {
+
+constexpr int kThreads = 512;           // 4 row groups of 128 rows (TMEM lanes)
+constexpr int kCtus = 4;                // CTUs of one depth per CTA
+constexpr int kAngles = 17;             // am = -8 .. 8;  vertical mode 26 + am, horizontal mode 10 - am (am > -8)
+constexpr int kWinTableBytes = kAngles * 4 * 2048;
+constexpr int kN4TableBytes = kAngles * 4096;
+
+CUCD_HD int angle_of_am(int am) { return mode_angle(26 + am); }
+CUCD_HD int inv_angle_of_am(int am) { return mode_inv_angle(26 + am); }
+// byte offset of element (row j, k) of a K-major, no-swizzle UMMA operand with 64 rows (see satd_tc.cuh)
+CUCD_HD int umma_off64(int j, int k) { return (k >> 4) * 1024 + (j >> 3) * 128 + (j & 7) * 16 + (k & 15); }
+
+CUCD_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, b, sel);
+#else
+  const uint64_t v = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xffu) << (8 * i);
+  return r;
+#endif
+}
+CUCD_HD uint32_t sad_acc(uint32_t d, uint32_t h, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+  return __sad((int)d, (int)h, acc);
+#else
+  const int v = (int)d - (int)h;
+  return acc + (uint32_t)(v < 0 ? -v : v);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// window geometry shared by the table generator and the gather
+// ---------------------------------------------------------------------------------------------
+// lowest local row shift of an 8-row tile: 0 for angle >= 0, (frac0 + 8*angle) >> 5 otherwise
+CUCD_HD int win_lmin(int angle, int frac0) { return angle >= 0 ? 0 : ((frac0 + 8 * angle) >> 5); }
+// first reference index of the window of the tile at (u0, v0) (orientation coordinates)
+CUCD_HD int win_k0(int angle, int u0, int v0) {
+  const int t = v0 * angle;
+  return u0 + (t >> 5) + 1 + win_lmin(angle, t & 31);
+}
+
+// B operand of MMA 1 for N >= 8: table[(am + 8) * 4 + fc] = 64 pixels x 32 slots, UMMA layout, 2 KB each
+inline void fill_win_tables(uint8_t* dst /*kWinTableBytes*/) {
+  for (int i = 0; i < kWinTableBytes; i++) dst[i] = 0;
+  for (int am = -8; am <= 8; am++)
+    for (int fc = 0; fc < 4; fc++) {
+      uint8_t* t = dst + ((am + 8) * 4 + fc) * 2048;
+      const int a = angle_of_am(am), frac0 = fc * 8, lmin = win_lmin(a, frac0);
+      for (int v = 0; v < 8; v++) {
+        const int d = frac0 + (v + 1) * a, li = d >> 5, f = d & 31;
+        for (int u = 0; u < 8; u++) {
+          const int j = v * 8 + u, s = u + li - lmin;
+          if (f == 0) { t[umma_off64(j, s)] = 255; t[umma_off64(j, 31)] = 255; }
+          else { t[umma_off64(j, s)] = (uint8_t)(8 * (32 - f)); t[umma_off64(j, s + 1)] = (uint8_t)(8 * f); t[umma_off64(j, 31)] = 128; }
+        }
+      }
+    }
+}
+// slot of reference sample k inside a PU record of the N = 4 path: main[0..8] at 0..8, side[1..5] at 9..13, 1 at 15
+CUCD_HD int n4_slot(int k, int inv) { return k >= 0 ? k : 8 + ((128 - k * inv) >> 8); }
+// B operand of MMA 1 for N = 4: table[am + 8] = 64 region pixels x 64 slots (4 records), 4 KB each
+inline void fill_n4_tables(uint8_t* dst /*kN4TableBytes*/) {
+  for (int i = 0; i < kN4TableBytes; i++) dst[i] = 0;
+  for (int am = -8; am <= 8; am++) {
+    uint8_t* t = dst + (am + 8) * 4096;
+    const int a = angle_of_am(am), inv = inv_angle_of_am(am);
+    for (int v = 0; v < 8; v++)
+      for (int u = 0; u < 8; u++) {
+        const int j = v * 8 + u, q = (v >> 2) * 2 + (u >> 2), lv = v & 3, lu = u & 3;
+        const int d = (lv + 1) * a, f = d & 31, k = lu + (d >> 5) + 1;
+        if (f == 0) { t[umma_off64(j, q * 16 + n4_slot(k, inv))] = 255; t[umma_off64(j, q * 16 + 15)] = 255; }
+        else {
+          t[umma_off64(j, q * 16 + n4_slot(k, inv))] = (uint8_t)(8 * (32 - f));
+          t[umma_off64(j, q * 16 + n4_slot(k + 1, inv))] = (uint8_t)(8 * f);
+          t[umma_off64(j, q * 16 + 15)] = 128;
+        }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared memory of the CTA
+// ---------------------------------------------------------------------------------------------
+// u8 reference arrays of the N >= 8 path: element k of an array lives at byte  arr + N + k,  k = -N .. 2N + 20
+// ([-N, -1] holds the projected samples of the negative-angle mode being evaluated, TComPrediction.cpp:300-322).
+// Arrays of one PU: index (filt * 2 + o), o = 0: main = above row ("T"), o = 1: main = left column ("L").
+template <int LOG2N>
+struct Store8 {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int PUS = 4096 / (N * N);
+  static constexpr int NARR = (LOG2N >= 3 && LOG2N <= 5) ? 4 : 2;
+  static constexpr int AS8 = (3 * N + 21 + 3) & ~3;
+  static constexpr int PU_RAW = NARR * AS8;
+  static constexpr int PU_BYTES = PU_RAW + (((PU_RAW >> 2) & 1) ? 0 : 4);      // odd number of words: lanes of different PUs hit different banks
+  static constexpr int CTU_BYTES = PUS * PU_BYTES;
+  static constexpr int TOTAL = LOG2N == 2 ? kCtus * 256 * 2 * 16 : 16 + kCtus * CTU_BYTES;   // N = 4: 16-byte records [ctu][o][pu]
+};
+struct Geo2 {
+  int log2n, n, pus;                // pus = PUs of one CTU at this depth
+  int as8, puBytes, ctuBytes, hasFilt;
+  // byte offsets inside dynamic shared memory
+  int storeOff, validOff, dcOff, accOff, b1Off, hadOff, barOff, scratchOff, total;
+  int b1Bytes;                      // per row group
+  int accStaged;                    // costs staged in shared memory (N >= 8); N = 4 writes global directly
+};
+template <int LOG2N>
+CUCD_HD Geo2 make_geo2() {
+  typedef Store8<LOG2N> S;
+  Geo2 g;
+  g.log2n = LOG2N; g.n = S::N; g.pus = S::PUS; g.as8 = S::AS8; g.puBytes = S::PU_BYTES; g.ctuBytes = S::CTU_BYTES; g.hasFilt = S::NARR == 4;
+  g.b1Bytes = LOG2N == 2 ? 4096 : 2048;
+  g.accStaged = LOG2N != 2;
+  int o = 0;
+  g.hadOff = o; o += 4096;
+  g.b1Off = o; o += 4 * g.b1Bytes;
+  g.barOff = o; o += 64;
+  g.validOff = o; o += kCtus * 256;
+  g.dcOff = o; o += kCtus * 64 * 2;                   // int16 [ctu][64], N >= 8 only (<= 64 PUs per CTU)
+  g.storeOff = o; o += (S::TOTAL + 15) & ~15;
+  g.accOff = o; o += g.accStaged ? kCtus * S::PUS * kNumModes * 4 : 0;
+  g.scratchOff = (o + 15) & ~15; o = g.scratchOff + Smem<LOG2N>::TOTAL;   // border construction of one CTU at a time (rmd_core.cuh phases)
+  g.total = o;
+  return g;
+}
+CUCD_HD Geo2 make_geo2_rt(int log2n) {
+  switch (log2n) {
+    case 2: return make_geo2<2>();
+    case 3: return make_geo2<3>();
+    case 4: return make_geo2<4>();
+    case 5: return make_geo2<5>();
+    default: return make_geo2<6>();
+  }
+}
+// byte offset (from the start of the store) of element k = 0 of array (ctu, pu, o, filt)
+CUCD_HD int arr_k0_off(const Geo2& g, int ctu, int pu, int o, int filt) {
+  return 16 + ctu * g.ctuBytes + pu * g.puBytes + (filt * 2 + o) * g.as8 + g.n;
+}
+CUCD_HD int rec_off(int ctu, int o, int pu) { return ((ctu * 2 + o) * 256 + pu) * 16; }
+
+// ---------------------------------------------------------------------------------------------
+// which tile a thread (= MMA row = TMEM lane) owns
+// ---------------------------------------------------------------------------------------------
+struct Row {
+  int ctu;      // 0..3 inside the CTA
+  int o;        // 0: true orientation (planar + modes 18..34), 1: transposed (DC + modes 2..17)
+  int pu;       // CTU-local PU (z order); N = 4: the REGION index, its PUs are 4*pu .. 4*pu+3
+  int u0, v0;   // tile origin inside the PU in orientation coordinates (u along the main reference)
+  int seg;      // consecutive lanes that share (PU, orientation)
+};
+CUCD_HD Row row_map(int log2n, int tid) {
+  const int g = tid >> 7, wq = (tid >> 5) & 3, lane = tid & 31;
+  Row r;
+  if (log2n <= 3) { r.ctu = g; r.o = wq >> 1; r.pu = (wq & 1) * 32 + lane; r.u0 = 0; r.v0 = 0; r.seg = 1; }
+  else if (log2n == 4) { r.ctu = 2 * (g >> 1) + (wq >> 1); r.o = wq & 1; r.pu = lane >> 1; r.u0 = 8 * (lane & 1); r.v0 = 8 * (g & 1); r.seg = 2; }
+  else if (log2n == 5) { r.ctu = wq; r.o = lane >> 4; r.pu = (lane >> 2) & 3; r.u0 = 8 * (lane & 3); r.v0 = 8 * g; r.seg = 4; }
+  else { r.ctu = wq; r.o = lane >> 4; r.pu = 0; r.u0 = 8 * (lane & 7); r.v0 = 8 * (g + 4 * ((lane >> 3) & 1)); r.seg = 16; }
+  return r;
+}
+// phase class of a row group: (v0 / 8) mod 4 is the same for its 128 rows
+CUCD_HD int group_frac0(int log2n, int group, int angle) {
+  const int t = log2n <= 3 ? 0 : (log2n == 4 ? (group & 1) : group);
+  return (8 * t * angle) & 31;
+}
+
+// ---------------------------------------------------------------------------------------------
+// byte tiles
+// ---------------------------------------------------------------------------------------------
+// w[16]: word 2*y + h = pixels (y, 4h .. 4h+3).  Transpose the whole 8x8 (blocks = true) or each 4x4 quadrant in place.
+CUCD_HD void transpose4x4_bytes(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t* o) {
+  const uint32_t t0 = bperm(a0, a1, 0x5140), t1 = bperm(a2, a3, 0x5140);   // (a0.0 a1.0 a0.1 a1.1), (a2.0 a3.0 a2.1 a3.1)
+  const uint32_t t2 = bperm(a0, a1, 0x7362), t3 = bperm(a2, a3, 0x7362);   // (a0.2 a1.2 a0.3 a1.3), ...
+  o[0] = bperm(t0, t1, 0x5410); o[1] = bperm(t0, t1, 0x7632);
+  o[2] = bperm(t2, t3, 0x5410); o[3] = bperm(t2, t3, 0x7632);
+}
+CUCD_HD void tile_transpose_bytes(const uint32_t* w, uint32_t* d, bool whole) {
+#pragma unroll
+  for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+    for (int qx = 0; qx < 2; qx++) {
+      uint32_t o[4];
+      transpose4x4_bytes(w[(qy * 4 + 0) * 2 + qx], w[(qy * 4 + 1) * 2 + qx], w[(qy * 4 + 2) * 2 + qx], w[(qy * 4 + 3) * 2 + qx], o);
+      const int dy = whole ? qx : qy, dx = whole ? qy : qx;
+#pragma unroll
+      for (int i = 0; i < 4; i++) d[(dy * 4 + i) * 2 + dx] = o[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MMA 1 operand of a row (N >= 8): 32 bytes starting at byte address q of the store, last byte := 1
+// ---------------------------------------------------------------------------------------------
+CUCD_HD void gather_window(const unsigned char* store, int q, uint32_t* w8) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(store + (q & ~3));
+  const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(q & 3);
+  uint32_t x[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) x[j] = s[j];
+#pragma unroll
+  for (int j = 0; j < 8; j++) w8[j] = bperm(x[j], x[j + 1], sel);
+  w8[7] = (w8[7] & 0x00ffffffu) | 0x01000000u;
+}
+// epilogue 1: packed[j] = (D[2j] & 0xffff) | (D[2j+1] << 16)  ->  4 predicted pixels per word
+CUCD_HD void pack_pred(const uint32_t* packed /*2 * NW*/, uint32_t* out /*NW*/, int nw) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) if (i < nw) out[i] = bperm(packed[2 * i], packed[2 * i + 1], 0x7531);
+}
+CUCD_HD int clip8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+// pure vertical / horizontal modes, N <= 16: first column gets the edge filter (TComPrediction.cpp:346-363)
+// main/side: element 0 = corner.  p = 16 words of the tile, v0 = first tile row inside the PU.
+CUCD_HD void patch_edge0_tile(const unsigned char* main0, const unsigned char* side0, int v0, uint32_t* p) {
+  const int m1 = main0[1], s0 = side0[0];
+#pragma unroll
+  for (int v = 0; v < 8; v++) {
+    const int val = clip8(m1 + (((int)side0[v0 + v + 1] - s0) >> 1));
+    p[2 * v] = (p[2 * v] & 0xffffff00u) | (uint32_t)val;
+  }
+}
+CUCD_HD void patch_edge0_region4(const unsigned char* rec /*4 records*/, uint32_t* p) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const unsigned char* r = rec + q * 16;
+    const int m1 = r[1], s0 = r[0];
+#pragma unroll
+    for (int lv = 0; lv < 4; lv++) {
+      const int val = clip8(m1 + (((int)r[9 + lv] - s0) >> 1));
+      const int w = 2 * ((q >> 1) * 4 + lv) + (q & 1);
+      p[w] = (p[w] & 0xffffff00u) | (uint32_t)val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// planar and DC on the integer ALU (2 of the 35 modes), bytes out.  main/side: element 0 = corner.
+// ---------------------------------------------------------------------------------------------
+// TComPrediction.cpp:755-805 for the 8x8 tile at (u0, v0) of an N x N PU
+CUCD_HD void planar_tile(int log2n, const unsigned char* T, const unsigned char* L, int u0, int v0, uint32_t* p) {
+  const int N = 1 << log2n;
+  const int tr = T[N + 1], bl = L[N + 1];
+#pragma unroll
+  for (int v = 0; v < 8; v++) {
+    const int Y = v0 + v, l = L[Y + 1];
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int X = u0 + u;
+      const int val = ((N - 1 - X) * l + (X + 1) * tr + (N - 1 - Y) * (int)T[X + 1] + (Y + 1) * bl + N) >> (log2n + 1);
+      if (u < 4) w0 |= (uint32_t)val << (8 * u); else w1 |= (uint32_t)val << (8 * (u - 4));
+    }
+    p[2 * v] = w0; p[2 * v + 1] = w1;
+  }
+}
+// TComPrediction.cpp:183-222, 818-841
+CUCD_HD void dc_tile(int dc, bool edge, const unsigned char* main0, const unsigned char* side0, int u0, int v0, uint32_t* p) {
+  const uint32_t dc4 = (uint32_t)dc * 0x01010101u;
+#pragma unroll
+  for (int i = 0; i < 16; i++) p[i] = dc4;
+  if (!edge) return;
+  if (v0 == 0) {
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int val = ((int)main0[u0 + u + 1] + 3 * dc + 2) >> 2;
+      if (u0 + u == 0) val = ((int)main0[1] + (int)side0[1] + 2 * dc + 2) >> 2;
+      if (u < 4) w0 |= (uint32_t)val << (8 * u); else w1 |= (uint32_t)val << (8 * (u - 4));
+    }
+    p[0] = w0; p[1] = w1;
+  }
+  if (u0 == 0) {
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+      if (v0 + v == 0) continue;
+      const int val = ((int)side0[v0 + v + 1] + 3 * dc + 2) >> 2;
+      p[2 * v] = (p[2 * v] & 0xffffff00u) | (uint32_t)val;
+    }
+  }
+}
+// N = 4 region: four independent PUs, records [main 0..8 | side 1..5 | 0 | 1]
+CUCD_HD void planar_region4(const unsigned char* rec, uint32_t* p) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const unsigned char* r = rec + q * 16;
+    const int tr = r[5], bl = r[13];
+#pragma unroll
+    for (int lv = 0; lv < 4; lv++) {
+      const int l = r[9 + lv];
+      uint32_t w = 0;
+#pragma unroll
+      for (int lu = 0; lu < 4; lu++) {
+        const int val = ((3 - lu) * l + (lu + 1) * tr + (3 - lv) * (int)r[lu + 1] + (lv + 1) * bl + 4) >> 3;
+        w |= (uint32_t)val << (8 * lu);
+      }
+      p[2 * ((q >> 1) * 4 + lv) + (q & 1)] = w;
+    }
+  }
+}
+CUCD_HD void dc_region4(const unsigned char* rec, uint32_t* p) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const unsigned char* r = rec + q * 16;
+    int sum = 4;
+#pragma unroll
+    for (int i = 1; i <= 4; i++) sum += (int)r[i] + (int)r[8 + i];
+    const int dc = sum >> 3;
+#pragma unroll
+    for (int lv = 0; lv < 4; lv++) {
+      uint32_t w = (uint32_t)dc * 0x01010101u;
+      if (lv == 0) {
+        w = 0;
+#pragma unroll
+        for (int lu = 0; lu < 4; lu++) {
+          int val = ((int)r[lu + 1] + 3 * dc + 2) >> 2;
+          if (lu == 0) val = ((int)r[1] + (int)r[9] + 2 * dc + 2) >> 2;
+          w |= (uint32_t)val << (8 * lu);
+        }
+      } else {
+        w = (w & 0xffffff00u) | (uint32_t)(((int)r[9 + lv] + 3 * dc + 2) >> 2);
+      }
+      p[2 * ((q >> 1) * 4 + lv) + (q & 1)] = w;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prologue helpers: int16 arrays of one CTU (rmd_core.cuh border phases) -> u8 store of the CTA
+// ---------------------------------------------------------------------------------------------
+template <int LOG2N>
+CUCD_HD void convert_arrays(int tid, int nthreads, const Geo2& g, int ctu, const int16_t* arrs, const int16_t* dc, unsigned char* smem) {
+  typedef Geo<LOG2N> G;
+  constexpr int N = G::N, LEN = 2 * N + 1;
+  unsigned char* store = smem + g.storeOff;
+  if (LOG2N == 2) {
+    // record of (pu, o): main[0..8], side[1..5], 0, 1
+    for (int idx = tid; idx < G::PUS * 2 * 16; idx += nthreads) {
+      const int b = idx & 15, o = (idx >> 4) & 1, p = idx >> 5;
+      const int16_t* a = arrs + pu_slot<LOG2N>(p) * G::PU_STRIDE;
+      int v;
+      if (b <= 8) v = a[(o ? 1 : 0) * G::AS + b];
+      else if (b <= 13) v = a[(o ? 0 : 1) * G::AS + (b - 8)];
+      else v = b == 15 ? 1 : 0;
+      store[rec_off(ctu, o, p) + b] = (unsigned char)v;
+    }
+  } else {
+    for (int idx = tid; idx < G::PUS * G::NARR * LEN; idx += nthreads) {
+      const int k = idx % LEN, t = idx / LEN, which = t % G::NARR, p = t / G::NARR;
+      const int16_t* a = arrs + pu_slot<LOG2N>(p) * G::PU_STRIDE;
+      store[arr_k0_off(g, ctu, p, which & 1, which >> 1) + k] = (unsigned char)a[which * G::AS + k];
+    }
+    for (int p = tid; p < G::PUS; p += nthreads) reinterpret_cast<int16_t*>(smem + g.dcOff)[ctu * 64 + p] = dc[p];
+  }
+}
+// projected samples of a negative-angle round: store[main][-j] = store[side][(128 + j*inv) >> 8], j = 1 .. nNeg
+CUCD_HD void build_ext_items(int tid, int nthreads, const Geo2& g, int angle, int inv, int filt, unsigned char* store) {
+  const int nNeg = -((g.n * angle) >> 5) - 1;
+  if (nNeg <= 0) return;
+  const int items = kCtus * g.pus * 2 * nNeg;
+  for (int idx = tid; idx < items; idx += nthreads) {
+    const int j = idx % nNeg + 1, t = idx / nNeg, o = t & 1, p = (t >> 1) % g.pus, ctu = (t >> 1) / g.pus;
+    store[arr_k0_off(g, ctu, p, o, filt) - j] = store[arr_k0_off(g, ctu, p, o ^ 1, filt) + ((128 + j * inv) >> 8)];
+  }
+}
+
+}  // namespace tc2
+}  // namespace cucd

@@ -148,10 +148,11 @@ typedef struct {
 } cucd_dev_out;
 int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
                     const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
-/* Frame-mode RMD has two bit-identical implementations of the Hadamard stage: integer-ALU butterflies in
- * registers, and (8-bit content only) tcgen05 kind::i8 tensor-core products.  Default: tensor cores for
- * 8-bit, ALU otherwise (or CUCD_RMD_PATH=alu in the environment at create time). */
-int cucd_set_rmd_path(cucd_handle* h, int use_tensor_cores);
+/* Frame-mode RMD has bit-identical implementations: 0 = integer ALU (prediction and Hadamard butterflies in
+ * registers, any bit depth); 1 = tcgen05 kind::i8 for BOTH the angular predictions and the Hadamard stage
+ * (8-bit content only, the default for it); 2 = ALU predictions + tcgen05 Hadamard (8-bit only).
+ * CUCD_RMD_PATH=alu|tc1 in the environment at create time selects 0 / 2. */
+int cucd_set_rmd_path(cucd_handle* h, int path);
 /* Device time of the RMD kernel inside the last `nCalls` cucd_dev_frames calls (CUDA events recorded on the
  * caller's stream around that launch; ring of 64).  The stream must have been synchronised.  Returns
  * the number of calls averaged, or a negative status; *avg_ms = mean duration of one launch. */

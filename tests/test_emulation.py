@@ -33,6 +33,34 @@ def test_frame_kernel_code_vs_oracle(emul, oracle, bd, W, H):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("W,H,seed", [(200, 136, 5), (64, 64, 1), (328, 72, 9)])
+def test_tensor_core_frame_kernel_code_vs_oracle(emul, oracle, W, H, seed):
+    """rmd_tc2: prediction and Hadamard as exact integer matmuls through the kernel's own weight tables,
+    window gather, row map and byte packing (tests/emul/rmd_tc2_emul.cpp)"""
+    org = textured_plane(W, H, 8, seed=seed)
+    rec = pseudo_recon(org, 8)
+    rec[:, : W // 2] = (np.arange(H)[:, None] // 3 + np.arange(W // 2)[None, :] // 5 + 40).astype(np.int16)
+    want = oracle_rmd_frame(oracle, org, rec, 8)
+    got = np.zeros_like(want)
+    emul.emul_rmd_frame_tc2(1, P(org, i16p), W, P(rec, i16p), W, W, H, P(got, u32p))
+    assert np.array_equal(got, want)
+
+
+def test_tensor_core_frame_kernel_code_extreme_values(emul, oracle):
+    """the byte-1 extraction must be exact at 0 / 255 and for alternating content"""
+    W = H = 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    rng = np.random.default_rng(3)
+    cases = [(np.where((xx + yy) & 1, 255, 0), np.where((xx + yy) & 1, 0, 255)), (np.full((H, W), 255), np.zeros((H, W))),
+             (np.where(xx & 1, 255, 0), np.full((H, W), 255)), (rng.integers(0, 256, (H, W)), rng.integers(0, 256, (H, W)))]
+    for org, rec in cases:
+        org = np.ascontiguousarray(org.astype(np.int16)); rec = np.ascontiguousarray(rec.astype(np.int16))
+        want = oracle_rmd_frame(oracle, org, rec, 8)
+        got = np.zeros_like(want)
+        emul.emul_rmd_frame_tc2(1, P(org, i16p), W, P(rec, i16p), W, W, H, P(got, u32p))
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("bd", [8, 10])
 def test_extreme_values_do_not_overflow_packed_lanes(emul, oracle, bd):
     """worst case for the 16-bit packed butterflies: full-scale checkerboards against 0 / max borders"""

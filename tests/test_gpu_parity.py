@@ -228,21 +228,26 @@ def test_me_surfaces_vs_oracle(cucd, oracle, bd):
             eng.me_sad_surface([dict(x=0, y=0, w=16, h=16, ref_idx=0, left=-81, right=0, top=0, bottom=0, sub_shift=0)])
 
 
-# ---- the two Hadamard implementations (ALU butterflies vs tcgen05 kind::i8) must agree bit for bit --------
-@pytest.mark.parametrize("W,H", [(416, 240), (200, 136), (64, 64)])
+# ---- the three frame-RMD implementations (ALU, tcgen05 prediction + Hadamard, tcgen05 Hadamard only) must
+# ---- agree bit for bit ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(416, 240), (200, 136), (64, 64), (328, 72)])
 def test_tensor_core_path_equals_alu_path_and_oracle(cucd, oracle, W, H):
     org = textured_plane(W, H, 8, seed=W)
     rec = pseudo_recon(org, 8)
     rec[:, : W // 2] = (np.arange(H)[:, None] // 3 + np.arange(W // 2)[None, :] // 5 + 40).astype(np.int16)
-    with cucd.Engine(W, H, max_pictures=2) as eng:
-        eng.set_rmd_path(True)
-        tc = eng.frames([org, rec], [rec, org])
-        eng.set_rmd_path(False)
-        alu = eng.frames([org, rec], [rec, org])
+    with cucd.Engine(W, H, max_pictures=3) as eng:
+        eng.set_rmd_path(1)
+        tc = eng.frames([org, rec, org], [rec, org, org])      # 3 pictures: CTU groups of 4 straddle pictures
+        eng.set_rmd_path(2)
+        tc1 = eng.frames([org, rec, org], [rec, org, org])
+        eng.set_rmd_path(0)
+        alu = eng.frames([org, rec, org], [rec, org, org])
     want = oracle_rmd_frame(oracle, org, rec, 8)
     assert np.array_equal(tc[0]["rmd_cost"], want)
     assert np.array_equal(alu[0]["rmd_cost"], want)
-    assert np.array_equal(tc[1]["rmd_cost"], alu[1]["rmd_cost"])
+    for k in range(3):
+        assert np.array_equal(tc[k]["rmd_cost"], alu[k]["rmd_cost"])
+        assert np.array_equal(tc1[k]["rmd_cost"], alu[k]["rmd_cost"])
 
 
 def test_tensor_core_path_extreme_values(cucd, oracle):
@@ -251,7 +256,8 @@ def test_tensor_core_path_extreme_values(cucd, oracle):
     for org, rec in [(np.where((xx + yy) & 1, 255, 0), np.where((xx + yy) & 1, 0, 255)), (np.full((H, W), 255), np.zeros((H, W))),
                      (np.where(xx & 1, 255, 0), np.full((H, W), 255))]:
         org = org.astype(np.int16); rec = rec.astype(np.int16)
-        with cucd.Engine(W, H) as eng:
-            eng.set_rmd_path(True)
-            got = eng.frame(org, rec)["rmd_cost"]
-        assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8))
+        for path in (1, 2):
+            with cucd.Engine(W, H) as eng:
+                eng.set_rmd_path(path)
+                got = eng.frame(org, rec)["rmd_cost"]
+            assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8)), path
