@@ -113,6 +113,8 @@ inline void fill_n4_tables(uint8_t* dst /*kN4TableBytes*/) {
 // u8 reference arrays of the N >= 8 path: element k of an array lives at byte  arr + N + k,  k = -N .. 2N + 20
 // ([-N, -1] holds the projected samples of the negative-angle mode being evaluated, TComPrediction.cpp:300-322).
 // Arrays of one PU: index (filt * 2 + o), o = 0: main = above row ("T"), o = 1: main = left column ("L").
+// Every row group owns a PRIVATE copy of the arrays of the PUs its rows touch ("slots"), so that the projected
+// part can be rewritten per mode round with row-group barriers only (the four groups run unsynchronised).
 template <int LOG2N>
 struct Store8 {
   static constexpr int N = 1 << LOG2N;
@@ -121,28 +123,31 @@ struct Store8 {
   static constexpr int AS8 = (3 * N + 21 + 3) & ~3;
   static constexpr int PU_RAW = NARR * AS8;
   static constexpr int PU_BYTES = PU_RAW + (((PU_RAW >> 2) & 1) ? 0 : 4);      // odd number of words: lanes of different PUs hit different banks
-  static constexpr int CTU_BYTES = PUS * PU_BYTES;
-  static constexpr int TOTAL = LOG2N == 2 ? kCtus * 256 * 2 * 16 : 16 + kCtus * CTU_BYTES;   // N = 4: 16-byte records [ctu][o][pu]
+  static constexpr int SLOTS = LOG2N == 3 ? 64 : (LOG2N == 4 ? 32 : kCtus * PUS);   // PUs seen by one row group
+  static constexpr int GROUP_BYTES = LOG2N == 2 ? 0 : ((16 + SLOTS * PU_BYTES + 15) & ~15);
+  static constexpr int TOTAL = LOG2N == 2 ? kCtus * 256 * 2 * 16 : 4 * GROUP_BYTES;   // N = 4: shared 16-byte records [ctu][o][pu]
 };
 struct Geo2 {
   int log2n, n, pus;                // pus = PUs of one CTU at this depth
-  int as8, puBytes, ctuBytes, hasFilt;
+  int as8, puBytes, groupBytes, slots, hasFilt;
   // byte offsets inside dynamic shared memory
-  int storeOff, validOff, dcOff, accOff, b1Off, hadOff, barOff, scratchOff, total;
-  int b1Bytes;                      // per row group
+  int storeOff, validOff, dcOff, accOff, b1Off, a1Off, hadOff, barOff, scratchOff, total;
+  int b1Bytes;                      // one MMA 1 weight operand (two buffers per row group)
   int accStaged;                    // costs staged in shared memory (N >= 8); N = 4 writes global directly
 };
 template <int LOG2N>
 CUCD_HD Geo2 make_geo2() {
   typedef Store8<LOG2N> S;
   Geo2 g;
-  g.log2n = LOG2N; g.n = S::N; g.pus = S::PUS; g.as8 = S::AS8; g.puBytes = S::PU_BYTES; g.ctuBytes = S::CTU_BYTES; g.hasFilt = S::NARR == 4;
+  g.log2n = LOG2N; g.n = S::N; g.pus = S::PUS; g.as8 = S::AS8; g.puBytes = S::PU_BYTES; g.groupBytes = S::GROUP_BYTES; g.slots = S::SLOTS;
+  g.hasFilt = S::NARR == 4;
   g.b1Bytes = LOG2N == 2 ? 4096 : 2048;
   g.accStaged = LOG2N != 2;
   int o = 0;
   g.hadOff = o; o += 4096;
-  g.b1Off = o; o += 4 * g.b1Bytes;
-  g.barOff = o; o += 64;
+  g.b1Off = o; o += 4 * 2 * g.b1Bytes;                // [group][buffer]
+  g.a1Off = o; o += 4 * 8192;                         // [group]: two 4 KB window operands (N >= 8) or one static 8 KB record operand (N = 4)
+  g.barOff = o; o += 128;
   g.validOff = o; o += kCtus * 256;
   g.dcOff = o; o += kCtus * 64 * 2;                   // int16 [ctu][64], N >= 8 only (<= 64 PUs per CTU)
   g.storeOff = o; o += (S::TOTAL + 15) & ~15;
@@ -160,9 +165,11 @@ CUCD_HD Geo2 make_geo2_rt(int log2n) {
     default: return make_geo2<6>();
   }
 }
-// byte offset (from the start of the store) of element k = 0 of array (ctu, pu, o, filt)
-CUCD_HD int arr_k0_off(const Geo2& g, int ctu, int pu, int o, int filt) {
-  return 16 + ctu * g.ctuBytes + pu * g.puBytes + (filt * 2 + o) * g.as8 + g.n;
+// slot of PU (ctu, pu) inside the private store of the row groups that use it
+CUCD_HD int pu_slot2(int log2n, int pus, int ctu, int pu) { return log2n == 3 ? pu : (log2n == 4 ? (ctu & 1) * 16 + pu : ctu * pus + pu); }
+// byte offset (from the start of the store) of element k = 0 of array (slot, o, filt) in row group `grp`'s copy
+CUCD_HD int arr_k0_off(const Geo2& g, int grp, int slot, int o, int filt) {
+  return grp * g.groupBytes + 16 + slot * g.puBytes + (filt * 2 + o) * g.as8 + g.n;
 }
 CUCD_HD int rec_off(int ctu, int o, int pu) { return ((ctu * 2 + o) * 256 + pu) * 16; }
 
@@ -369,23 +376,25 @@ CUCD_HD void convert_arrays(int tid, int nthreads, const Geo2& g, int ctu, const
       store[rec_off(ctu, o, p) + b] = (unsigned char)v;
     }
   } else {
+    // the row groups whose rows touch this CTU: N = 8: group ctu; N = 16: the two groups of the CTU pair; N >= 32: all four
+    const int g0 = LOG2N == 3 ? ctu : (LOG2N == 4 ? 2 * (ctu >> 1) : 0), ng = LOG2N == 3 ? 1 : (LOG2N == 4 ? 2 : 4);
     for (int idx = tid; idx < G::PUS * G::NARR * LEN; idx += nthreads) {
       const int k = idx % LEN, t = idx / LEN, which = t % G::NARR, p = t / G::NARR;
-      const int16_t* a = arrs + pu_slot<LOG2N>(p) * G::PU_STRIDE;
-      store[arr_k0_off(g, ctu, p, which & 1, which >> 1) + k] = (unsigned char)a[which * G::AS + k];
+      const unsigned char v = (unsigned char)arrs[pu_slot<LOG2N>(p) * G::PU_STRIDE + which * G::AS + k];
+      const int slot = pu_slot2(LOG2N, G::PUS, ctu, p);
+      for (int gg = 0; gg < ng; gg++) store[arr_k0_off(g, g0 + gg, slot, which & 1, which >> 1) + k] = v;
     }
     for (int p = tid; p < G::PUS; p += nthreads) reinterpret_cast<int16_t*>(smem + g.dcOff)[ctu * 64 + p] = dc[p];
   }
 }
-// projected samples of a negative-angle round: store[main][-j] = store[side][(128 + j*inv) >> 8], j = 1 .. nNeg
-CUCD_HD void build_ext_items(int tid, int nthreads, const Geo2& g, int angle, int inv, int filt, unsigned char* store) {
+// projected samples of a negative-angle round, by the 128 threads of row group `grp` for its private arrays:
+// store[main][-j] = store[side][(128 + j*inv) >> 8], j = 1 .. nNeg.  N/8 threads share one (slot, orientation) pair.
+CUCD_HD void build_ext_group(int rowTid, const Geo2& g, int grp, int angle, int inv, int filt, unsigned char* store) {
   const int nNeg = -((g.n * angle) >> 5) - 1;
-  if (nNeg <= 0) return;
-  const int items = kCtus * g.pus * 2 * nNeg;
-  for (int idx = tid; idx < items; idx += nthreads) {
-    const int j = idx % nNeg + 1, t = idx / nNeg, o = t & 1, p = (t >> 1) % g.pus, ctu = (t >> 1) / g.pus;
-    store[arr_k0_off(g, ctu, p, o, filt) - j] = store[arr_k0_off(g, ctu, p, o ^ 1, filt) + ((128 + j * inv) >> 8)];
-  }
+  const int sh = g.log2n == 6 ? 4 : g.log2n - 3, tpp = 1 << sh;   // threads per pair; pairs = 2 * slots = 128 >> sh
+  const int pair = rowTid >> sh, slot = pair >> 1, o = pair & 1;
+  const int mainOff = arr_k0_off(g, grp, slot, o, filt), sideOff = arr_k0_off(g, grp, slot, o ^ 1, filt);
+  for (int j = 1 + (rowTid & (tpp - 1)); j <= nNeg; j += tpp) store[mainOff - j] = store[sideOff + ((128 + j * inv) >> 8)];
 }
 
 }  // namespace tc2

@@ -103,23 +103,31 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const Geo2& g, co
 }
 
 // ---- the mode rounds (one copy of the code for every PU size) --------------------------------------------
+// Per row group the rounds are software pipelined so that the integer ALU always has work while an MMA is in
+// flight (a lone tcgen05.mma + commit takes ~350 cycles, profiles/ubench):
+//     wait MMA1(i) | epilogue 1 -> A2, projected refs of round i+1 | issue MMA2(i) | stage B1/A1 of round i+1 |
+//     wait MMA2(i) | issue MMA1(i+1) | epilogue 2 of round i (costs)
+// TMEM per row group: D1 = columns [0, 64) (A2 aliases its first 16 once they have been read), D2 = [64, 128).
 __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const int group) {
   const Geo2 g = make_geo2_rt(log2n);
   unsigned char* smem = smem2;
   const int tid = threadIdx.x, grp = tid >> 7, rowTid = tid & 127, warp = tid >> 5, lane = tid & 31;
   const Row r = row_map(log2n, tid);
   unsigned char* store = smem + g.storeOff;
-  unsigned char* sB1 = smem + g.b1Off + grp * g.b1Bytes;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + g.barOff) + grp;
-  uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + g.barOff + 32);
+  unsigned char* sB1 = smem + g.b1Off + grp * 2 * g.b1Bytes;
+  unsigned char* sA1 = smem + g.a1Off + grp * 8192;
+  uint64_t* mbar1 = reinterpret_cast<uint64_t*>(smem + g.barOff) + grp;
+  uint64_t* mbar2 = mbar1 + 4;
+  uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + g.barOff + 64);
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + g.accOff);
   const FrameSource& fs = a.fs;
   const int cg = group * kCtus + r.ctu;
   const bool ok = smem[g.validOff + r.ctu * 256 + (log2n == 2 ? 4 * r.pu : r.pu)] != 0;   // N = 4: the region's PUs share validity (W, H multiples of 8)
+  const int slot = pu_slot2(log2n, g.pus, r.ctu, r.pu);
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < 4; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + g.barOff) + i, 1);
+    for (int i = 0; i < 8; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + g.barOff) + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmemSlot, 512);
@@ -155,27 +163,69 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
 
   const uint32_t tmemBase = *tmemSlot;
   const uint32_t laneOff = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t tD = tmemBase + grp * 128, tA2 = tD + 64, tA1 = tD + 80;     // per row group: D 64 columns, A2 16, A1 16
+  const uint32_t tD1 = tmemBase + grp * 128, tA2 = tD1, tD2 = tD1 + 64;
   const uint32_t idescPred = make_idesc_i8x(128, 64, 0, 0), idescHad = make_idesc_i8x(128, 64, 0, 1);
-  const uint64_t dHad = make_desc(smem_u32(smem + g.hadOff), 1024, 128), dB1 = make_desc(smem_u32(sB1), 1024, 128);
-  constexpr uint64_t kStep = (2 * 1024) >> 4;       // descriptor advance of one K = 32 step (two 16-byte chunks of 64 rows)
-  uint32_t phase = 0;
+  const uint64_t dHad = make_desc(smem_u32(smem + g.hadOff), 1024, 128);
+  constexpr uint64_t kStepB = (2 * 1024) >> 4;      // descriptor advance of one K = 32 step: two 16-byte chunks of 64 rows
+  constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
+  uint32_t ph1 = 0, ph2 = 0;
   uint32_t ho[64];
 
-  // A2 <- p, D <- A2 x H, wait
-  auto hadamard = [&]() {
-    tmem_st16(tA2 + laneOff, p);
+  // A2 (already stored to TMEM by every thread) x H -> D2
+  auto issue_mma2 = [&]() {
     tmem_st_wait();
     tc_fence_before();
     group_bar(grp);
     if (rowTid == 0) {
       tc_fence_after();
-      mma_i8_ts(tD, tA2, dHad, idescHad, 0u);
-      mma_i8_ts(tD, tA2 + 8, dHad + kStep, idescHad, 1u);
-      mma_commit(mbar);
+      mma_i8_ts(tD2, tA2, dHad, idescHad, 0u);
+      mma_i8_ts(tD2, tA2 + 8, dHad + kStepB, idescHad, 1u);
+      mma_commit(mbar2);
     }
-    mbar_wait(mbar, phase); phase ^= 1u;
-    tc_fence_after();
+  };
+  auto wait_mma2 = [&]() { mbar_wait(mbar2, ph2); ph2 ^= 1u; tc_fence_after(); };
+  // window / record operand (shared memory) x weights -> D1
+  auto issue_mma1 = [&](int buf) {
+    fence_async_smem();
+    tc_fence_before();
+    group_bar(grp);
+    if (rowTid == 0) {
+      tc_fence_after();
+      const uint64_t dB = make_desc(smem_u32(sB1 + buf * g.b1Bytes), 1024, 128);
+      if (log2n == 2) {
+        const uint64_t dA = make_desc(smem_u32(sA1), 2048, 128);
+        mma_i8(tD1, dA, dB, idescPred, 0u);
+        mma_i8(tD1, dA + kStepA, dB + kStepB, idescPred, 1u);
+      } else {
+        mma_i8(tD1, make_desc(smem_u32(sA1 + buf * 4096), 2048, 128), dB, idescPred, 0u);
+      }
+      mma_commit(mbar1);
+    }
+  };
+  auto wait_mma1 = [&]() { mbar_wait(mbar1, ph1); ph1 ^= 1u; tc_fence_after(); };
+  // weights of round `am` from global memory (L2 resident) into registers, one round ahead of their use
+  uint4 nb0 = make_uint4(0, 0, 0, 0), nb1 = nb0;
+  auto prefetch_b1 = [&](int am) {
+    const int ai = am + 8;
+    if (log2n == 2) {
+      const uint4* t = reinterpret_cast<const uint4*>(a.tabN4 + ai * 4096);
+      nb0 = __ldg(t + rowTid); nb1 = __ldg(t + rowTid + 128);
+    } else {
+      const int fc = group_frac0(log2n, grp, angle_of_am(am)) >> 3;
+      nb0 = __ldg(reinterpret_cast<const uint4*>(a.tabWin + (ai * 4 + fc) * 2048) + rowTid);
+    }
+  };
+  // operands of round `am` into buffer `buf`: weights from the prefetch registers, the row's reference window
+  auto stage = [&](int am, int buf) {
+    uint4* b = reinterpret_cast<uint4*>(sB1 + buf * g.b1Bytes);
+    b[rowTid] = nb0;
+    if (log2n == 2) { b[rowTid + 128] = nb1; return; }
+    const int filt = mode_uses_filtered_rt(log2n, 26 + am) ? 1 : 0;
+    uint32_t w8[8];
+    gather_window(store, arr_k0_off(g, grp, slot, r.o, filt) + win_k0(angle_of_am(am), r.u0, r.v0), w8);
+    uint4* d = reinterpret_cast<uint4*>(sA1 + buf * 4096 + (rowTid >> 3) * 128 + (rowTid & 7) * 16);
+    d[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+    d[128] = make_uint4(w8[4], w8[5], w8[6], w8[7]);          // second 16-byte chunk: + 128 rows * 16 B
   };
   // epilogue 2 + cost hand-over for mode `mode` (has = the row has a mode in this round)
   uint32_t* outN4 = fs.out + ((size_t)cg * kPusPerCtu + pu_offset_of_depth(4) + 4 * r.pu) * kNumModes;
@@ -184,7 +234,7 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       uint32_t v[16];
-      tmem_ld16(tD + laneOff + c * 16, v);
+      tmem_ld16(tD2 + laneOff + c * 16, v);
       tmem_ld_wait();
       uint32_t s = 0;
 #pragma unroll
@@ -208,76 +258,50 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
   };
 
   // ---- Ho = H x source tile ------------------------------------------------------------------------------
-  hadamard();
-#pragma unroll
-  for (int c = 0; c < 4; c++) tmem_ld16(tD + laneOff + c * 16, ho + c * 16);
-  tmem_ld_wait();
-  tc_fence_before();
-
-  // N = 4: the record row is the same for every mode
+  tmem_st16(tA2 + laneOff, p);
+  issue_mma2();
+  prefetch_b1(8);
   const unsigned char* rec4 = store + rec_off(r.ctu, r.o, 4 * r.pu);
-  if (log2n == 2) {
-    uint32_t w[16];
+  if (log2n == 2) {                                 // N = 4: the record row is the A operand of every mode (4 chunks)
+    uint4* d = reinterpret_cast<uint4*>(sA1 + (rowTid >> 3) * 128 + (rowTid & 7) * 16);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const uint4 v = reinterpret_cast<const uint4*>(rec4)[i];
-      w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-    }
-    tmem_st16(tA1 + laneOff, w);
+    for (int i = 0; i < 4; i++) d[i * 128] = reinterpret_cast<const uint4*>(rec4)[i];
   }
-
-  // ---- round 0: planar (true orientation rows) / DC (transposed rows) on the ALU ---------------------------
-  const int unfMain = arr_k0_off(g, r.ctu, r.pu, r.o, 0), unfSide = arr_k0_off(g, r.ctu, r.pu, r.o ^ 1, 0);
+  // round 0 prediction while the MMA runs: planar (true orientation rows) / DC (transposed rows) on the ALU
+  const int unfMain = arr_k0_off(g, grp, slot, r.o, 0), unfSide = arr_k0_off(g, grp, slot, r.o ^ 1, 0);
   if (ok) {
     if (log2n == 2) { if (r.o == 0) planar_region4(rec4, p); else dc_region4(rec4, p); }
     else if (r.o == 0) {
       const int f = g.hasFilt;                      // planar reads the smoothed border for N = 8, 16, 32 (TComPattern.cpp:523-548)
-      planar_tile(log2n, store + arr_k0_off(g, r.ctu, r.pu, 0, f), store + arr_k0_off(g, r.ctu, r.pu, 1, f), r.u0, r.v0, p);
+      planar_tile(log2n, store + arr_k0_off(g, grp, slot, 0, f), store + arr_k0_off(g, grp, slot, 1, f), r.u0, r.v0, p);
     } else {
       dc_tile(reinterpret_cast<const int16_t*>(smem + g.dcOff)[r.ctu * 64 + r.pu], g.n <= 16, store + unfMain, store + unfSide, r.u0, r.v0, p);
     }
   }
-  hadamard();
+  wait_mma2();
+#pragma unroll
+  for (int c = 0; c < 4; c++) tmem_ld16(tD2 + laneOff + c * 16, ho + c * 16);
+  tmem_ld_wait();
+  tc_fence_before();
+
+  // ---- round 0 -------------------------------------------------------------------------------------------------
+  tmem_st16(tA2 + laneOff, p);
+  issue_mma2();
+  stage(8, 0);
+  prefetch_b1(7);
+  wait_mma2();
+  issue_mma1(0);
   cost_out(r.o ? 1 : 0, true);
 
   // ---- angular rounds -----------------------------------------------------------------------------------------
   for (int am = 8; am >= -8; --am) {
-    const int angle = angle_of_am(am), ai = am + 8;
-    const int filt = mode_uses_filtered_rt(log2n, 26 + am) ? 1 : 0;
-    if (log2n != 2 && angle < 0) {
-      __syncthreads();                              // every row group has gathered the previous round
-      build_ext_items(tid, kThreads, g, angle, inv_angle_of_am(am), filt, store);
-      __syncthreads();
-    }
-    // weights of this round (the previous round's MMA 1 has completed: its accumulators were read)
-    if (log2n == 2) {
-      const uint4* t = reinterpret_cast<const uint4*>(a.tabN4 + ai * 4096);
-      reinterpret_cast<uint4*>(sB1)[rowTid] = t[rowTid];
-      reinterpret_cast<uint4*>(sB1)[rowTid + 128] = t[rowTid + 128];
-    } else {
-      const int fc = group_frac0(log2n, grp, angle) >> 3;
-      reinterpret_cast<uint4*>(sB1)[rowTid] = reinterpret_cast<const uint4*>(a.tabWin + (ai * 4 + fc) * 2048)[rowTid];
-      uint32_t w8[8];
-      gather_window(store, arr_k0_off(g, r.ctu, r.pu, r.o, filt) + win_k0(angle, r.u0, r.v0), w8);
-      tmem_st8(tA1 + laneOff, w8);
-    }
-    tmem_st_wait();
-    fence_async_smem();
-    tc_fence_before();
-    group_bar(grp);
-    if (rowTid == 0) {
-      tc_fence_after();
-      mma_i8_ts(tD, tA1, dB1, idescPred, 0u);
-      if (log2n == 2) mma_i8_ts(tD, tA1 + 8, dB1 + kStep, idescPred, 1u);
-      mma_commit(mbar);
-    }
-    mbar_wait(mbar, phase); phase ^= 1u;
-    tc_fence_after();
+    const int angle = angle_of_am(am), buf = (8 - am) & 1;
+    wait_mma1();
     // epilogue 1: byte 1 of every accumulator is the predicted pixel
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       uint32_t v[16];
-      tmem_ld16_pack(tD + laneOff + h * 32, v);
+      tmem_ld16_pack(tD1 + laneOff + h * 32, v);
       tmem_ld_wait();
       pack_pred(v, p + 8 * h, 8);
     }
@@ -285,7 +309,16 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
       if (log2n == 2) patch_edge0_region4(rec4, p);
       else if (r.u0 == 0) patch_edge0_tile(store + unfMain, store + unfSide, r.v0, p);
     }
-    hadamard();
+    tmem_st16(tA2 + laneOff, p);
+    if (am > -8 && log2n != 2 && angle_of_am(am - 1) < 0)   // the gathers of round am are done (barrier of its MMA 1)
+      build_ext_group(rowTid, g, grp, angle_of_am(am - 1), inv_angle_of_am(am - 1), mode_uses_filtered_rt(log2n, 25 + am) ? 1 : 0, store);
+    issue_mma2();
+    if (am > -8) {
+      stage(am - 1, buf ^ 1);
+      if (am > -7) prefetch_b1(am - 2);
+    }
+    wait_mma2();
+    if (am > -8) issue_mma1(buf ^ 1);
     cost_out(r.o ? 10 - am : 26 + am, !(r.o && am == -8));
   }
 

@@ -127,17 +127,18 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int group) {
     if (!ok[tid]) continue;
     const Row& r = rows[tid]; uint32_t* p = &P[tid * 16];
     const unsigned char* rec4 = store + rec_off(r.ctu, r.o, 4 * r.pu);
+    const int grp = tid >> 7, slot = pu_slot2(log2n, g.pus, r.ctu, r.pu);
     if (log2n == 2) { if (r.o == 0) planar_region4(rec4, p); else dc_region4(rec4, p); }
-    else if (r.o == 0) planar_tile(log2n, store + arr_k0_off(g, r.ctu, r.pu, 0, g.hasFilt), store + arr_k0_off(g, r.ctu, r.pu, 1, g.hasFilt), r.u0, r.v0, p);
-    else dc_tile(reinterpret_cast<const int16_t*>(smem + g.dcOff)[r.ctu * 64 + r.pu], g.n <= 16, store + arr_k0_off(g, r.ctu, r.pu, 1, 0),
-                 store + arr_k0_off(g, r.ctu, r.pu, 0, 0), r.u0, r.v0, p);
+    else if (r.o == 0) planar_tile(log2n, store + arr_k0_off(g, grp, slot, 0, g.hasFilt), store + arr_k0_off(g, grp, slot, 1, g.hasFilt), r.u0, r.v0, p);
+    else dc_tile(reinterpret_cast<const int16_t*>(smem + g.dcOff)[r.ctu * 64 + r.pu], g.n <= 16, store + arr_k0_off(g, grp, slot, 1, 0),
+                 store + arr_k0_off(g, grp, slot, 0, 0), r.u0, r.v0, p);
   }
   hadamard();
   cost_out(0, false);
   for (int am = 8; am >= -8; --am) {
     const int angle = angle_of_am(am), ai = am + 8;
     const int filt = mode_uses_filtered_rt(log2n, 26 + am) ? 1 : 0;
-    if (log2n != 2 && angle < 0) for (int tid = 0; tid < kThreads; tid++) build_ext_items(tid, kThreads, g, angle, inv_angle_of_am(am), filt, store);
+    if (log2n != 2 && angle < 0) for (int tid = 0; tid < kThreads; tid++) build_ext_group(tid & 127, g, tid >> 7, angle, inv_angle_of_am(am), filt, store);
     for (int grp = 0; grp < 4; grp++) {
       const uint8_t* b1;
       if (log2n == 2) b1 = tb.n4.data() + ai * 4096;
@@ -145,7 +146,7 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int group) {
         b1 = tb.win.data() + (ai * 4 + (group_frac0(log2n, grp, angle) >> 3)) * 2048;
         for (int rt = 0; rt < 128; rt++) {
           const int tid = grp * 128 + rt; const Row& r = rows[tid];
-          gather_window(store, arr_k0_off(g, r.ctu, r.pu, r.o, filt) + win_k0(angle, r.u0, r.v0), &A1[tid * 16]);
+          gather_window(store, arr_k0_off(g, grp, pu_slot2(log2n, g.pus, r.ctu, r.pu), r.o, filt) + win_k0(angle, r.u0, r.v0), &A1[tid * 16]);
         }
       }
       mma(&A1[grp * 128 * 16], 16, log2n == 2 ? 64 : 32, b1, false, &D[grp * 128 * 64]);
@@ -159,7 +160,10 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int group) {
       }
       if (angle == 0 && g.n <= 16 && ok[tid]) {
         if (log2n == 2) patch_edge0_region4(store + rec_off(r.ctu, r.o, 4 * r.pu), p);
-        else if (r.u0 == 0) patch_edge0_tile(store + arr_k0_off(g, r.ctu, r.pu, r.o, 0), store + arr_k0_off(g, r.ctu, r.pu, r.o ^ 1, 0), r.v0, p);
+        else if (r.u0 == 0) {
+          const int slot = pu_slot2(log2n, g.pus, r.ctu, r.pu);
+          patch_edge0_tile(store + arr_k0_off(g, tid >> 7, slot, r.o, 0), store + arr_k0_off(g, tid >> 7, slot, r.o ^ 1, 0), r.v0, p);
+        }
       }
     }
     hadamard();
