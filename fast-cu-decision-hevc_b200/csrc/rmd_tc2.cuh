@@ -27,14 +27,30 @@
 namespace cucd {
 namespace tc2 {
 
-constexpr int kThreads = 512;           // 4 row groups of 128 rows (TMEM lanes)
-constexpr int kCtus = 4;                // CTUs of one depth per CTA
+constexpr int kThreads = 256;           // 2 row groups of 128 rows (TMEM lanes); two CTAs share an SM
+constexpr int kGroups = 2;
 constexpr int kAngles = 17;             // am = -8 .. 8;  vertical mode 26 + am, horizontal mode 10 - am (am > -8)
 constexpr int kWinTableBytes = kAngles * 4 * 2048;
 constexpr int kN4TableBytes = kAngles * 4096;
 
-CUCD_HD int angle_of_am(int am) { return mode_angle(26 + am); }
-CUCD_HD int inv_angle_of_am(int am) { return mode_inv_angle(26 + am); }
+#if defined(__CUDACC__)
+__constant__ int c_angleTab[kAngles] = {-32, -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
+__constant__ int c_invTab[kAngles] = {256, 315, 390, 482, 630, 910, 1638, 4096, 0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+#endif
+CUCD_HD int angle_of_am(int am) {
+#if defined(__CUDA_ARCH__)
+  return c_angleTab[am + 8];
+#else
+  return mode_angle(26 + am);
+#endif
+}
+CUCD_HD int inv_angle_of_am(int am) {
+#if defined(__CUDA_ARCH__)
+  return c_invTab[am + 8];
+#else
+  return mode_inv_angle(26 + am);
+#endif
+}
 // byte offset of element (row j, k) of a K-major, no-swizzle UMMA operand with 64 rows (see satd_tc.cuh)
 CUCD_HD int umma_off64(int j, int k) { return (k >> 4) * 1024 + (j >> 3) * 128 + (j & 7) * 16 + (k & 15); }
 
@@ -113,63 +129,55 @@ inline void fill_n4_tables(uint8_t* dst /*kN4TableBytes*/) {
 // u8 reference arrays of the N >= 8 path: element k of an array lives at byte  arr + N + k,  k = -N .. 2N + 20
 // ([-N, -1] holds the projected samples of the negative-angle mode being evaluated, TComPrediction.cpp:300-322).
 // Arrays of one PU: index (filt * 2 + o), o = 0: main = above row ("T"), o = 1: main = left column ("L").
-// Every row group owns a PRIVATE copy of the arrays of the PUs its rows touch ("slots"), so that the projected
-// part can be rewritten per mode round with row-group barriers only (the four groups run unsynchronised).
+// Each of the two row groups owns a PRIVATE copy of the arrays of the PUs its rows touch ("slots"), so that the
+// projected part can be rewritten per mode round with row-group barriers only (the groups run unsynchronised).
+//
+// Work of one CTA: N = 4, 8: two CTUs, row group = CTU;  N = 16: two CTUs, row group = phase class (tile row
+// parity);  N = 32, 64: four CTUs in two passes, pass p evaluates the phase classes {2p, 2p+1}.
 template <int LOG2N>
-struct Store8 {
+struct Cfg {
+  typedef Geo<LOG2N> G;
+  static constexpr int al16(int v) { return (v + 15) & ~15; }
   static constexpr int N = 1 << LOG2N;
-  static constexpr int PUS = 4096 / (N * N);
-  static constexpr int NARR = (LOG2N >= 3 && LOG2N <= 5) ? 4 : 2;
+  static constexpr int PUS = 4096 / (N * N);                     // PUs of one CTU at this depth
+  static constexpr int CTUS = LOG2N >= 5 ? 4 : 2;                // CTUs per CTA
+  static constexpr int PASSES = LOG2N >= 5 ? 2 : 1;
+  static constexpr bool HAS_FILT = LOG2N >= 3 && LOG2N <= 5;
+  static constexpr int NARR = HAS_FILT ? 4 : 2;
   static constexpr int AS8 = (3 * N + 21 + 3) & ~3;
   static constexpr int PU_RAW = NARR * AS8;
-  static constexpr int PU_BYTES = PU_RAW + (((PU_RAW >> 2) & 1) ? 0 : 4);      // odd number of words: lanes of different PUs hit different banks
-  static constexpr int SLOTS = LOG2N == 3 ? 64 : (LOG2N == 4 ? 32 : kCtus * PUS);   // PUs seen by one row group
-  static constexpr int GROUP_BYTES = LOG2N == 2 ? 0 : ((16 + SLOTS * PU_BYTES + 15) & ~15);
-  static constexpr int TOTAL = LOG2N == 2 ? kCtus * 256 * 2 * 16 : 4 * GROUP_BYTES;   // N = 4: shared 16-byte records [ctu][o][pu]
-};
-struct Geo2 {
-  int log2n, n, pus;                // pus = PUs of one CTU at this depth
-  int as8, puBytes, groupBytes, slots, hasFilt;
+  static constexpr int PU_BYTES = PU_RAW + (((PU_RAW >> 2) & 1) ? 0 : 4);   // odd number of words: lanes of different PUs hit different banks
+  static constexpr int SLOTS = LOG2N == 3 ? 64 : CTUS * PUS;     // PUs seen by one row group
+  static constexpr int GROUP_BYTES = LOG2N == 2 ? 0 : al16(16 + SLOTS * PU_BYTES);
+  static constexpr int STORE_BYTES = LOG2N == 2 ? CTUS * 256 * 2 * 16 : kGroups * GROUP_BYTES;   // N = 4: shared 16-byte records [ctu][o][pu]
+  static constexpr int B1_BYTES = LOG2N == 2 ? 4096 : 2048;      // one MMA 1 weight operand
+  static constexpr bool ACC_STAGED = LOG2N != 2;                 // costs staged in shared memory; N = 4 writes global directly
+  static constexpr bool EDGE = LOG2N <= 4;                       // luma edge filters (DC, pure vertical / horizontal)
   // byte offsets inside dynamic shared memory
-  int storeOff, validOff, dcOff, accOff, b1Off, a1Off, hadOff, barOff, scratchOff, total;
-  int b1Bytes;                      // one MMA 1 weight operand (two buffers per row group)
-  int accStaged;                    // costs staged in shared memory (N >= 8); N = 4 writes global directly
+  static constexpr int HAD_OFF = 0;
+  static constexpr int B1_OFF = HAD_OFF + 4096;                  // [group][buffer]
+  static constexpr int A1_OFF = B1_OFF + kGroups * 2 * B1_BYTES; // [group]: two 4 KB window operands (N >= 8) or one static 8 KB record operand (N = 4)
+  static constexpr int BAR_OFF = A1_OFF + kGroups * 8192;
+  static constexpr int VALID_OFF = BAR_OFF + 128;
+  static constexpr int DC_OFF = VALID_OFF + CTUS * 256;          // int16 [ctu][64], N >= 8
+  static constexpr int STORE_OFF = DC_OFF + CTUS * 64 * 2;
+  static constexpr int ACC_OFF = STORE_OFF + al16(STORE_BYTES);
+  // scratch of the border construction, one CTU at a time (rmd_core.cuh phases)
+  static constexpr int LIN_OFF = ACC_OFF + (ACC_STAGED ? CTUS * PUS * kNumModes * 4 : 0);
+  static constexpr int FLAGS_OFF = LIN_OFF + al16(PUS * G::LIN * 2);
+  static constexpr int ARRS_OFF = FLAGS_OFF + al16(PUS * (N + 1));
+  static constexpr int DC16_OFF = ARRS_OFF + al16(PUS * G::PU_STRIDE * 2);
+  static constexpr int TOTAL = DC16_OFF + al16(PUS * 2);
 };
-template <int LOG2N>
-CUCD_HD Geo2 make_geo2() {
-  typedef Store8<LOG2N> S;
-  Geo2 g;
-  g.log2n = LOG2N; g.n = S::N; g.pus = S::PUS; g.as8 = S::AS8; g.puBytes = S::PU_BYTES; g.groupBytes = S::GROUP_BYTES; g.slots = S::SLOTS;
-  g.hasFilt = S::NARR == 4;
-  g.b1Bytes = LOG2N == 2 ? 4096 : 2048;
-  g.accStaged = LOG2N != 2;
-  int o = 0;
-  g.hadOff = o; o += 4096;
-  g.b1Off = o; o += 4 * 2 * g.b1Bytes;                // [group][buffer]
-  g.a1Off = o; o += 4 * 8192;                         // [group]: two 4 KB window operands (N >= 8) or one static 8 KB record operand (N = 4)
-  g.barOff = o; o += 128;
-  g.validOff = o; o += kCtus * 256;
-  g.dcOff = o; o += kCtus * 64 * 2;                   // int16 [ctu][64], N >= 8 only (<= 64 PUs per CTU)
-  g.storeOff = o; o += (S::TOTAL + 15) & ~15;
-  g.accOff = o; o += g.accStaged ? kCtus * S::PUS * kNumModes * 4 : 0;
-  g.scratchOff = (o + 15) & ~15; o = g.scratchOff + Smem<LOG2N>::TOTAL;   // border construction of one CTU at a time (rmd_core.cuh phases)
-  g.total = o;
-  return g;
-}
-CUCD_HD Geo2 make_geo2_rt(int log2n) {
-  switch (log2n) {
-    case 2: return make_geo2<2>();
-    case 3: return make_geo2<3>();
-    case 4: return make_geo2<4>();
-    case 5: return make_geo2<5>();
-    default: return make_geo2<6>();
-  }
-}
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int kSmemBytes = cmax(cmax(cmax(Cfg<2>::TOTAL, Cfg<3>::TOTAL), cmax(Cfg<4>::TOTAL, Cfg<5>::TOTAL)), Cfg<6>::TOTAL);
+
 // slot of PU (ctu, pu) inside the private store of the row groups that use it
-CUCD_HD int pu_slot2(int log2n, int pus, int ctu, int pu) { return log2n == 3 ? pu : (log2n == 4 ? (ctu & 1) * 16 + pu : ctu * pus + pu); }
+template <int LOG2N> CUCD_HD int pu_slot2(int ctu, int pu) { return LOG2N == 3 ? pu : ctu * Cfg<LOG2N>::PUS + pu; }
 // byte offset (from the start of the store) of element k = 0 of array (slot, o, filt) in row group `grp`'s copy
-CUCD_HD int arr_k0_off(const Geo2& g, int grp, int slot, int o, int filt) {
-  return grp * g.groupBytes + 16 + slot * g.puBytes + (filt * 2 + o) * g.as8 + g.n;
+template <int LOG2N> CUCD_HD int arr_k0_off(int grp, int slot, int o, int filt) {
+  typedef Cfg<LOG2N> C;
+  return grp * C::GROUP_BYTES + 16 + slot * C::PU_BYTES + (filt * 2 + o) * C::AS8 + C::N;
 }
 CUCD_HD int rec_off(int ctu, int o, int pu) { return ((ctu * 2 + o) * 256 + pu) * 16; }
 
@@ -177,24 +185,26 @@ CUCD_HD int rec_off(int ctu, int o, int pu) { return ((ctu * 2 + o) * 256 + pu) 
 // which tile a thread (= MMA row = TMEM lane) owns
 // ---------------------------------------------------------------------------------------------
 struct Row {
-  int ctu;      // 0..3 inside the CTA
+  int ctu;      // inside the CTA
   int o;        // 0: true orientation (planar + modes 18..34), 1: transposed (DC + modes 2..17)
   int pu;       // CTU-local PU (z order); N = 4: the REGION index, its PUs are 4*pu .. 4*pu+3
   int u0, v0;   // tile origin inside the PU in orientation coordinates (u along the main reference)
-  int seg;      // consecutive lanes that share (PU, orientation)
 };
-CUCD_HD Row row_map(int log2n, int tid) {
+template <int LOG2N> struct RowSeg { static constexpr int value = LOG2N <= 3 ? 1 : (LOG2N == 4 ? 2 : (LOG2N == 5 ? 4 : 16)); };   // lanes sharing (PU, orientation)
+template <int LOG2N>
+CUCD_HD Row row_map(int tid, int pass) {
   const int g = tid >> 7, wq = (tid >> 5) & 3, lane = tid & 31;
   Row r;
-  if (log2n <= 3) { r.ctu = g; r.o = wq >> 1; r.pu = (wq & 1) * 32 + lane; r.u0 = 0; r.v0 = 0; r.seg = 1; }
-  else if (log2n == 4) { r.ctu = 2 * (g >> 1) + (wq >> 1); r.o = wq & 1; r.pu = lane >> 1; r.u0 = 8 * (lane & 1); r.v0 = 8 * (g & 1); r.seg = 2; }
-  else if (log2n == 5) { r.ctu = wq; r.o = lane >> 4; r.pu = (lane >> 2) & 3; r.u0 = 8 * (lane & 3); r.v0 = 8 * g; r.seg = 4; }
-  else { r.ctu = wq; r.o = lane >> 4; r.pu = 0; r.u0 = 8 * (lane & 7); r.v0 = 8 * (g + 4 * ((lane >> 3) & 1)); r.seg = 16; }
+  if (LOG2N <= 3) { r.ctu = g; r.o = wq >> 1; r.pu = (wq & 1) * 32 + lane; r.u0 = 0; r.v0 = 0; }
+  else if (LOG2N == 4) { r.ctu = wq >> 1; r.o = wq & 1; r.pu = lane >> 1; r.u0 = 8 * (lane & 1); r.v0 = 8 * g; }
+  else if (LOG2N == 5) { r.ctu = wq; r.o = lane >> 4; r.pu = (lane >> 2) & 3; r.u0 = 8 * (lane & 3); r.v0 = 8 * (2 * pass + g); }
+  else { r.ctu = wq; r.o = lane >> 4; r.pu = 0; r.u0 = 8 * (lane & 7); r.v0 = 8 * (2 * pass + g + 4 * ((lane >> 3) & 1)); }
   return r;
 }
 // phase class of a row group: (v0 / 8) mod 4 is the same for its 128 rows
-CUCD_HD int group_frac0(int log2n, int group, int angle) {
-  const int t = log2n <= 3 ? 0 : (log2n == 4 ? (group & 1) : group);
+template <int LOG2N>
+CUCD_HD int group_frac0(int grp, int pass, int angle) {
+  const int t = LOG2N <= 3 ? 0 : (LOG2N == 4 ? grp : 2 * pass + grp);
   return (8 * t * angle) & 31;
 }
 
@@ -360,10 +370,11 @@ CUCD_HD void dc_region4(const unsigned char* rec, uint32_t* p) {
 // prologue helpers: int16 arrays of one CTU (rmd_core.cuh border phases) -> u8 store of the CTA
 // ---------------------------------------------------------------------------------------------
 template <int LOG2N>
-CUCD_HD void convert_arrays(int tid, int nthreads, const Geo2& g, int ctu, const int16_t* arrs, const int16_t* dc, unsigned char* smem) {
+CUCD_HD void convert_arrays(int tid, int nthreads, int ctu, const int16_t* arrs, const int16_t* dc, unsigned char* smem) {
   typedef Geo<LOG2N> G;
+  typedef Cfg<LOG2N> C;
   constexpr int N = G::N, LEN = 2 * N + 1;
-  unsigned char* store = smem + g.storeOff;
+  unsigned char* store = smem + C::STORE_OFF;
   if (LOG2N == 2) {
     // record of (pu, o): main[0..8], side[1..5], 0, 1
     for (int idx = tid; idx < G::PUS * 2 * 16; idx += nthreads) {
@@ -376,25 +387,27 @@ CUCD_HD void convert_arrays(int tid, int nthreads, const Geo2& g, int ctu, const
       store[rec_off(ctu, o, p) + b] = (unsigned char)v;
     }
   } else {
-    // the row groups whose rows touch this CTU: N = 8: group ctu; N = 16: the two groups of the CTU pair; N >= 32: all four
-    const int g0 = LOG2N == 3 ? ctu : (LOG2N == 4 ? 2 * (ctu >> 1) : 0), ng = LOG2N == 3 ? 1 : (LOG2N == 4 ? 2 : 4);
+    // N = 8: row group = CTU; N >= 16: both groups see every CTU of the CTA
     for (int idx = tid; idx < G::PUS * G::NARR * LEN; idx += nthreads) {
       const int k = idx % LEN, t = idx / LEN, which = t % G::NARR, p = t / G::NARR;
       const unsigned char v = (unsigned char)arrs[pu_slot<LOG2N>(p) * G::PU_STRIDE + which * G::AS + k];
-      const int slot = pu_slot2(LOG2N, G::PUS, ctu, p);
-      for (int gg = 0; gg < ng; gg++) store[arr_k0_off(g, g0 + gg, slot, which & 1, which >> 1) + k] = v;
+      const int slot = pu_slot2<LOG2N>(ctu, p);
+      if (LOG2N == 3) store[arr_k0_off<LOG2N>(ctu, slot, which & 1, which >> 1) + k] = v;
+      else { store[arr_k0_off<LOG2N>(0, slot, which & 1, which >> 1) + k] = v; store[arr_k0_off<LOG2N>(1, slot, which & 1, which >> 1) + k] = v; }
     }
-    for (int p = tid; p < G::PUS; p += nthreads) reinterpret_cast<int16_t*>(smem + g.dcOff)[ctu * 64 + p] = dc[p];
+    for (int p = tid; p < G::PUS; p += nthreads) reinterpret_cast<int16_t*>(smem + C::DC_OFF)[ctu * 64 + p] = dc[p];
   }
 }
 // projected samples of a negative-angle round, by the 128 threads of row group `grp` for its private arrays:
-// store[main][-j] = store[side][(128 + j*inv) >> 8], j = 1 .. nNeg.  N/8 threads share one (slot, orientation) pair.
-CUCD_HD void build_ext_group(int rowTid, const Geo2& g, int grp, int angle, int inv, int filt, unsigned char* store) {
-  const int nNeg = -((g.n * angle) >> 5) - 1;
-  const int sh = g.log2n == 6 ? 4 : g.log2n - 3, tpp = 1 << sh;   // threads per pair; pairs = 2 * slots = 128 >> sh
-  const int pair = rowTid >> sh, slot = pair >> 1, o = pair & 1;
-  const int mainOff = arr_k0_off(g, grp, slot, o, filt), sideOff = arr_k0_off(g, grp, slot, o ^ 1, filt);
-  for (int j = 1 + (rowTid & (tpp - 1)); j <= nNeg; j += tpp) store[mainOff - j] = store[sideOff + ((128 + j * inv) >> 8)];
+// store[main][-j] = store[side][(128 + j*inv) >> 8], j = 1 .. nNeg.  128 / (2 * SLOTS) threads share one (slot, orientation) pair.
+template <int LOG2N>
+CUCD_HD void build_ext_group(int rowTid, int grp, int angle, int inv, int filt, unsigned char* store) {
+  typedef Cfg<LOG2N> C;
+  constexpr int TPP = 128 / (2 * C::SLOTS);
+  const int nNeg = -((C::N * angle) >> 5) - 1;
+  const int pair = rowTid / TPP, slot = pair >> 1, o = pair & 1;
+  const int mainOff = arr_k0_off<LOG2N>(grp, slot, o, filt), sideOff = arr_k0_off<LOG2N>(grp, slot, o ^ 1, filt);
+  for (int j = 1 + (rowTid % TPP); j <= nNeg; j += TPP) store[mainOff - j] = store[sideOff + ((128 + j * inv) >> 8)];
 }
 
 }  // namespace tc2

@@ -1,12 +1,13 @@
 // rmd_tc2_kernels.cu - tensor-core RMD frame kernel for 8-bit content (sm_100a, tcgen05 kind::i8).
 //
-// One CTA (512 threads = 4 row groups x 128 TMEM lanes) evaluates 4 CTUs at one depth.  A thread owns one
-// 8x8 tile in one orientation for the whole CTA ("row"); per mode round and row group:
-//     gather 32-byte reference window -> TMEM (A1)        [N = 4: static 64-byte record row]
-//     MMA 1: D = A1 x weights(angle, phase)               prediction * 256 in byte 1 of every accumulator
+// One CTA (256 threads = 2 row groups x 128 TMEM lanes, two CTAs per SM) evaluates 2 CTUs (N <= 16) or, in two
+// passes, 4 CTUs (N >= 32) at one depth.  A thread owns one 8x8 tile in one orientation ("row") for a pass;
+// per mode round and row group:
+//     gather 32-byte reference window -> shared memory (A1) [N = 4: static 64-byte record row]
+//     MMA 1: D1 = A1 x weights(angle, phase)              prediction * 256 in byte 1 of every accumulator
 //     epilogue 1: tcgen05.ld.pack::16b + 16 PRMT -> 64 predicted bytes -> TMEM (A2)
-//     MMA 2: D = A2 x (H8 (x) H8)
-//     epilogue 2: sum |D - Ho| against the row's transformed source tile (64 registers), HM rounding
+//     MMA 2: D2 = A2 x (H8 (x) H8)
+//     epilogue 2: sum |D2 - Ho| against the row's transformed source tile (64 registers), HM rounding
 // See rmd_tc2.cuh for the arithmetic and the reference citations; planar and DC are predicted on the ALU.
 // Replaces, per PU, the reference loop TEncSearch.cpp:2327-2361.
 #include <cuda_runtime.h>
@@ -65,18 +66,22 @@ __device__ __forceinline__ void tmem_ld16_pack(uint32_t addr, uint32_t* v) {
 }
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;\n" :: "r"(grp + 1) : "memory"); }
 
-// ---- prologue: reference arrays of the CTA's four CTUs -------------------------------------------------
+// ---- prologue: reference arrays of the CTA's CTUs ------------------------------------------------------
 template <int LOG2N>
-__device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const Geo2& g, const int group) {
+__device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
   typedef Geo<LOG2N> G;
+  typedef Cfg<LOG2N> C;
   constexpr int N = G::N;
   unsigned char* smem = smem2;
-  SmemView<LOG2N> sm; sm.base = smem + g.scratchOff;
+  int16_t* lin = reinterpret_cast<int16_t*>(smem + C::LIN_OFF);
+  uint8_t* flags = smem + C::FLAGS_OFF;
+  int16_t* arrs = reinterpret_cast<int16_t*>(smem + C::ARRS_OFF);
+  int16_t* dc16 = reinterpret_cast<int16_t*>(smem + C::DC16_OFF);
   const int tid = threadIdx.x;
   const FrameSource& fs = a.fs;
-  for (int c = 0; c < kCtus; c++) {
-    const int cg = group * kCtus + c;
-    uint8_t* valid = smem + g.validOff + c * 256;
+  for (int c = 0; c < C::CTUS; c++) {
+    const int cg = unit * C::CTUS + c;
+    uint8_t* valid = smem + C::VALID_OFF + c * 256;
     if (cg >= a.totalCtus) {                                   // CTA-uniform
       for (int p = tid; p < G::PUS; p += kThreads) valid[p] = 0;
       continue;
@@ -88,58 +93,49 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const Geo2& g, co
       int px, py; demorton(p, px, py);
       valid[p] = ((ctuX + (px + 1) * N <= fs.W) && (ctuY + (py + 1) * N <= fs.H)) ? 1 : 0;
     }
-    border_gather_frame<LOG2N>(tid, kThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, sm.lin(), sm.flags());
+    border_gather_frame<LOG2N>(tid, kThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, lin, flags);
     __syncthreads();
-    border_substitute<LOG2N>(tid, kThreads, 8, sm.lin(), sm.flags());
+    border_substitute<LOG2N>(tid, kThreads, 8, lin, flags);
     __syncthreads();
-    border_derive<LOG2N>(tid, kThreads, 8, a.strong, sm.lin(), sm.arrs());
-    border_pad<LOG2N>(tid, kThreads, sm.arrs());
+    border_derive<LOG2N>(tid, kThreads, 8, a.strong, lin, arrs);
+    border_pad<LOG2N>(tid, kThreads, arrs);
     __syncthreads();
-    border_dc<LOG2N>(tid, kThreads, sm.arrs(), sm.dc());
-    __syncthreads();
-    convert_arrays<LOG2N>(tid, kThreads, g, c, sm.arrs(), sm.dc(), smem);
+    if (LOG2N != 2) { border_dc<LOG2N>(tid, kThreads, arrs, dc16); __syncthreads(); }
+    convert_arrays<LOG2N>(tid, kThreads, c, arrs, dc16, smem);
     __syncthreads();
   }
 }
 
-// ---- the mode rounds (one copy of the code for every PU size) --------------------------------------------
-// Per row group the rounds are software pipelined so that the integer ALU always has work while an MMA is in
-// flight (a lone tcgen05.mma + commit takes ~350 cycles, profiles/ubench):
+// ---- the mode rounds of one pass ------------------------------------------------------------------------------
+// Per row group the rounds are software pipelined so that the integer ALU has work while an MMA is in flight
+// (a lone tcgen05.mma + commit takes ~350 cycles, profiles/ubench):
 //     wait MMA1(i) | epilogue 1 -> A2, projected refs of round i+1 | issue MMA2(i) | stage B1/A1 of round i+1 |
 //     wait MMA2(i) | issue MMA1(i+1) | epilogue 2 of round i (costs)
 // TMEM per row group: D1 = columns [0, 64) (A2 aliases its first 16 once they have been read), D2 = [64, 128).
-__device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const int group) {
-  const Geo2 g = make_geo2_rt(log2n);
+template <int LOG2N>
+__device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2) {
+  typedef Cfg<LOG2N> C;
+  constexpr int N = C::N, SEG = RowSeg<LOG2N>::value;
   unsigned char* smem = smem2;
   const int tid = threadIdx.x, grp = tid >> 7, rowTid = tid & 127, warp = tid >> 5, lane = tid & 31;
-  const Row r = row_map(log2n, tid);
-  unsigned char* store = smem + g.storeOff;
-  unsigned char* sB1 = smem + g.b1Off + grp * 2 * g.b1Bytes;
-  unsigned char* sA1 = smem + g.a1Off + grp * 8192;
-  uint64_t* mbar1 = reinterpret_cast<uint64_t*>(smem + g.barOff) + grp;
-  uint64_t* mbar2 = mbar1 + 4;
-  uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + g.barOff + 64);
-  uint32_t* acc = reinterpret_cast<uint32_t*>(smem + g.accOff);
+  const Row r = row_map<LOG2N>(tid, pass);
+  unsigned char* store = smem + C::STORE_OFF;
+  unsigned char* sB1 = smem + C::B1_OFF + grp * 2 * C::B1_BYTES;
+  unsigned char* sA1 = smem + C::A1_OFF + grp * 8192;
+  uint64_t* mbar1 = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + grp;
+  uint64_t* mbar2 = mbar1 + kGroups;
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
   const FrameSource& fs = a.fs;
-  const int cg = group * kCtus + r.ctu;
-  const bool ok = smem[g.validOff + r.ctu * 256 + (log2n == 2 ? 4 * r.pu : r.pu)] != 0;   // N = 4: the region's PUs share validity (W, H multiples of 8)
-  const int slot = pu_slot2(log2n, g.pus, r.ctu, r.pu);
-
-  // ---- one-time setup ---------------------------------------------------------------------------------
-  if (tid == 0) {
-    for (int i = 0; i < 8; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + g.barOff) + i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  if (warp == 0) tmem_alloc(tmemSlot, 512);
-  if (tid < 256) reinterpret_cast<uint4*>(smem + g.hadOff)[tid] = reinterpret_cast<const uint4*>(a.had + (log2n == 2 ? 8192 : 0))[tid];
-  if (g.accStaged) for (int i = tid; i < kCtus * g.pus * kNumModes; i += kThreads) acc[i] = 0;
+  const int cg = unit * C::CTUS + r.ctu;
+  const bool ok = smem[C::VALID_OFF + r.ctu * 256 + (LOG2N == 2 ? 4 * r.pu : r.pu)] != 0;   // N = 4: the region's PUs share validity (W, H multiples of 8)
+  const int slot = pu_slot2<LOG2N>(r.ctu, r.pu);
 
   uint32_t p[16];                                   // the row's current byte tile: word 2*v + h = pixels (v, 4h..4h+3)
   if (ok) {
     const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
     int px, py; demorton(r.pu, px, py);
-    if (log2n == 2) { px *= 8; py *= 8; }
-    else { px = px * g.n + (r.o ? r.v0 : r.u0); py = py * g.n + (r.o ? r.u0 : r.v0); }
+    if (LOG2N == 2) { px *= 8; py *= 8; }
+    else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
     const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
     uint32_t raw[16];
 #pragma unroll
@@ -147,7 +143,7 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
       const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)y * fs.orgStride);
       raw[2 * y] = __byte_perm(v.x, v.y, 0x6420); raw[2 * y + 1] = __byte_perm(v.z, v.w, 0x6420);
     }
-    if (r.o) tile_transpose_bytes(raw, p, log2n != 2);
+    if (r.o) tile_transpose_bytes(raw, p, LOG2N != 2);
     else {
 #pragma unroll
       for (int i = 0; i < 16; i++) p[i] = raw[i];
@@ -156,19 +152,14 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
 #pragma unroll
     for (int i = 0; i < 16; i++) p[i] = 0;
   }
-  tc_fence_before();
-  fence_async_smem();
-  __syncthreads();
-  tc_fence_after();
 
-  const uint32_t tmemBase = *tmemSlot;
   const uint32_t laneOff = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t tD1 = tmemBase + grp * 128, tA2 = tD1, tD2 = tD1 + 64;
   const uint32_t idescPred = make_idesc_i8x(128, 64, 0, 0), idescHad = make_idesc_i8x(128, 64, 0, 1);
-  const uint64_t dHad = make_desc(smem_u32(smem + g.hadOff), 1024, 128);
+  const uint64_t dHad = make_desc(smem_u32(smem + C::HAD_OFF), 1024, 128);
+  const uint64_t dB1 = make_desc(smem_u32(sB1), 1024, 128), dA1 = make_desc(smem_u32(sA1), 2048, 128);
   constexpr uint64_t kStepB = (2 * 1024) >> 4;      // descriptor advance of one K = 32 step: two 16-byte chunks of 64 rows
   constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
-  uint32_t ph1 = 0, ph2 = 0;
   uint32_t ho[64];
 
   // A2 (already stored to TMEM by every thread) x H -> D2
@@ -191,13 +182,12 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
     group_bar(grp);
     if (rowTid == 0) {
       tc_fence_after();
-      const uint64_t dB = make_desc(smem_u32(sB1 + buf * g.b1Bytes), 1024, 128);
-      if (log2n == 2) {
-        const uint64_t dA = make_desc(smem_u32(sA1), 2048, 128);
-        mma_i8(tD1, dA, dB, idescPred, 0u);
-        mma_i8(tD1, dA + kStepA, dB + kStepB, idescPred, 1u);
+      const uint64_t dB = dB1 + (uint64_t)((buf * C::B1_BYTES) >> 4);
+      if (LOG2N == 2) {
+        mma_i8(tD1, dA1, dB, idescPred, 0u);
+        mma_i8(tD1, dA1 + kStepA, dB + kStepB, idescPred, 1u);
       } else {
-        mma_i8(tD1, make_desc(smem_u32(sA1 + buf * 4096), 2048, 128), dB, idescPred, 0u);
+        mma_i8(tD1, dA1 + (uint64_t)((buf * 4096) >> 4), dB, idescPred, 0u);
       }
       mma_commit(mbar1);
     }
@@ -205,30 +195,32 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
   auto wait_mma1 = [&]() { mbar_wait(mbar1, ph1); ph1 ^= 1u; tc_fence_after(); };
   // weights of round `am` from global memory (L2 resident) into registers, one round ahead of their use
   uint4 nb0 = make_uint4(0, 0, 0, 0), nb1 = nb0;
-  auto prefetch_b1 = [&](int am) {
+  auto prefetch_b1 = [&](int am, int angle) {
     const int ai = am + 8;
-    if (log2n == 2) {
+    if (LOG2N == 2) {
       const uint4* t = reinterpret_cast<const uint4*>(a.tabN4 + ai * 4096);
       nb0 = __ldg(t + rowTid); nb1 = __ldg(t + rowTid + 128);
     } else {
-      const int fc = group_frac0(log2n, grp, angle_of_am(am)) >> 3;
+      const int fc = group_frac0<LOG2N>(grp, pass, angle) >> 3;
       nb0 = __ldg(reinterpret_cast<const uint4*>(a.tabWin + (ai * 4 + fc) * 2048) + rowTid);
     }
   };
   // operands of round `am` into buffer `buf`: weights from the prefetch registers, the row's reference window
-  auto stage = [&](int am, int buf) {
-    uint4* b = reinterpret_cast<uint4*>(sB1 + buf * g.b1Bytes);
+  const int rowChunk = (rowTid >> 3) * 128 + (rowTid & 7) * 16;
+  auto stage = [&](int am, int angle, int buf) {
+    uint4* b = reinterpret_cast<uint4*>(sB1 + buf * C::B1_BYTES);
     b[rowTid] = nb0;
-    if (log2n == 2) { b[rowTid + 128] = nb1; return; }
-    const int filt = mode_uses_filtered_rt(log2n, 26 + am) ? 1 : 0;
+    if (LOG2N == 2) { b[rowTid + 128] = nb1; return; }
+    const int filt = mode_uses_filtered<LOG2N>(26 + am) ? 1 : 0;
     uint32_t w8[8];
-    gather_window(store, arr_k0_off(g, grp, slot, r.o, filt) + win_k0(angle_of_am(am), r.u0, r.v0), w8);
-    uint4* d = reinterpret_cast<uint4*>(sA1 + buf * 4096 + (rowTid >> 3) * 128 + (rowTid & 7) * 16);
+    gather_window(store, arr_k0_off<LOG2N>(grp, slot, r.o, filt) + win_k0(angle, r.u0, r.v0), w8);
+    uint4* d = reinterpret_cast<uint4*>(sA1 + buf * 4096 + rowChunk);
     d[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);
     d[128] = make_uint4(w8[4], w8[5], w8[6], w8[7]);          // second 16-byte chunk: + 128 rows * 16 B
   };
   // epilogue 2 + cost hand-over for mode `mode` (has = the row has a mode in this round)
   uint32_t* outN4 = fs.out + ((size_t)cg * kPusPerCtu + pu_offset_of_depth(4) + 4 * r.pu) * kNumModes;
+  uint32_t* accRow = acc + (r.ctu * C::PUS + r.pu) * kNumModes;
   auto cost_out = [&](int mode, bool has) {
     uint32_t q[4];
 #pragma unroll
@@ -242,17 +234,17 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
       q[c] = s;
     }
     tc_fence_before();
-    if (log2n == 2) {
+    if (LOG2N == 2) {
       if (ok && has) {
 #pragma unroll
         for (int c = 0; c < 4; c++) outN4[c * kNumModes + mode] = (q[c] + 1u) >> 1;      // xCalcHADs4x4 rounding; 8-bit: no final shift
       }
     } else {
       uint32_t v = ok ? ((q[0] + q[1] + q[2] + q[3] + 2u) >> 2) : 0u;                    // xCalcHADs8x8 rounding
-      for (int m = 1; m < r.seg; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-      if (ok && has && (lane & (r.seg - 1)) == 0) {
-        uint32_t* dst = &acc[(r.ctu * g.pus + r.pu) * kNumModes + mode];
-        if (log2n >= 4) atomicAdd(dst, v); else *dst = v;
+#pragma unroll
+      for (int m = 1; m < SEG; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (ok && has && (lane & (SEG - 1)) == 0) {
+        if (LOG2N >= 4) atomicAdd(accRow + mode, v); else accRow[mode] = v;
       }
     }
   };
@@ -260,22 +252,23 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
   // ---- Ho = H x source tile ------------------------------------------------------------------------------
   tmem_st16(tA2 + laneOff, p);
   issue_mma2();
-  prefetch_b1(8);
+  prefetch_b1(8, 32);
   const unsigned char* rec4 = store + rec_off(r.ctu, r.o, 4 * r.pu);
-  if (log2n == 2) {                                 // N = 4: the record row is the A operand of every mode (4 chunks)
-    uint4* d = reinterpret_cast<uint4*>(sA1 + (rowTid >> 3) * 128 + (rowTid & 7) * 16);
+  if (LOG2N == 2) {                                 // N = 4: the record row is the A operand of every mode (4 chunks)
+    uint4* d = reinterpret_cast<uint4*>(sA1 + rowChunk);
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i * 128] = reinterpret_cast<const uint4*>(rec4)[i];
   }
   // round 0 prediction while the MMA runs: planar (true orientation rows) / DC (transposed rows) on the ALU
-  const int unfMain = arr_k0_off(g, grp, slot, r.o, 0), unfSide = arr_k0_off(g, grp, slot, r.o ^ 1, 0);
+  const unsigned char* unfMain = store + arr_k0_off<LOG2N>(grp, slot, r.o, 0);
+  const unsigned char* unfSide = store + arr_k0_off<LOG2N>(grp, slot, r.o ^ 1, 0);
   if (ok) {
-    if (log2n == 2) { if (r.o == 0) planar_region4(rec4, p); else dc_region4(rec4, p); }
+    if (LOG2N == 2) { if (r.o == 0) planar_region4(rec4, p); else dc_region4(rec4, p); }
     else if (r.o == 0) {
-      const int f = g.hasFilt;                      // planar reads the smoothed border for N = 8, 16, 32 (TComPattern.cpp:523-548)
-      planar_tile(log2n, store + arr_k0_off(g, grp, slot, 0, f), store + arr_k0_off(g, grp, slot, 1, f), r.u0, r.v0, p);
+      constexpr int f = C::HAS_FILT ? 1 : 0;        // planar reads the smoothed border for N = 8, 16, 32 (TComPattern.cpp:523-548)
+      planar_tile(LOG2N, store + arr_k0_off<LOG2N>(grp, slot, 0, f), store + arr_k0_off<LOG2N>(grp, slot, 1, f), r.u0, r.v0, p);
     } else {
-      dc_tile(reinterpret_cast<const int16_t*>(smem + g.dcOff)[r.ctu * 64 + r.pu], g.n <= 16, store + unfMain, store + unfSide, r.u0, r.v0, p);
+      dc_tile(reinterpret_cast<const int16_t*>(smem + C::DC_OFF)[r.ctu * 64 + r.pu], C::EDGE, unfMain, unfSide, r.u0, r.v0, p);
     }
   }
   wait_mma2();
@@ -287,15 +280,18 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
   // ---- round 0 -------------------------------------------------------------------------------------------------
   tmem_st16(tA2 + laneOff, p);
   issue_mma2();
-  stage(8, 0);
-  prefetch_b1(7);
+  stage(8, 32, 0);
+  prefetch_b1(7, 26);
   wait_mma2();
   issue_mma1(0);
   cost_out(r.o ? 1 : 0, true);
 
   // ---- angular rounds -----------------------------------------------------------------------------------------
+  int angle = 32, angleNext = 26;
+#pragma unroll 1
   for (int am = 8; am >= -8; --am) {
-    const int angle = angle_of_am(am), buf = (8 - am) & 1;
+    const int buf = (8 - am) & 1;
+    const int angleNext2 = am > -7 ? angle_of_am(am - 2) : 0;
     wait_mma1();
     // epilogue 1: byte 1 of every accumulator is the predicted pixel
 #pragma unroll
@@ -305,86 +301,101 @@ __device__ __noinline__ void tc2_modes(const Tc2Args& a, const int log2n, const 
       tmem_ld_wait();
       pack_pred(v, p + 8 * h, 8);
     }
-    if (angle == 0 && g.n <= 16 && ok) {
-      if (log2n == 2) patch_edge0_region4(rec4, p);
-      else if (r.u0 == 0) patch_edge0_tile(store + unfMain, store + unfSide, r.v0, p);
+    if (C::EDGE && am == 0 && ok) {
+      if (LOG2N == 2) patch_edge0_region4(rec4, p);
+      else if (r.u0 == 0) patch_edge0_tile(unfMain, unfSide, r.v0, p);
     }
     tmem_st16(tA2 + laneOff, p);
-    if (am > -8 && log2n != 2 && angle_of_am(am - 1) < 0)   // the gathers of round am are done (barrier of its MMA 1)
-      build_ext_group(rowTid, g, grp, angle_of_am(am - 1), inv_angle_of_am(am - 1), mode_uses_filtered_rt(log2n, 25 + am) ? 1 : 0, store);
+    if (LOG2N != 2 && am > -8 && angleNext < 0)     // the gathers of round am are done (barrier of its MMA 1)
+      build_ext_group<LOG2N>(rowTid, grp, angleNext, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
     issue_mma2();
     if (am > -8) {
-      stage(am - 1, buf ^ 1);
-      if (am > -7) prefetch_b1(am - 2);
+      stage(am - 1, angleNext, buf ^ 1);
+      if (am > -7) prefetch_b1(am - 2, angleNext2);
     }
     wait_mma2();
     if (am > -8) issue_mma1(buf ^ 1);
     cost_out(r.o ? 10 - am : 26 + am, !(r.o && am == -8));
+    angle = angleNext; angleNext = angleNext2;
   }
+  (void)angle;
+}
+
+template <int LOG2N>
+__device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
+  typedef Cfg<LOG2N> C;
+  unsigned char* smem = smem2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 64);
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kGroups; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmemSlot, 256);
+  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid];
+  if (C::ACC_STAGED) for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) acc[i] = 0;
+  tc2_prologue<LOG2N>(a, unit);
+  tc_fence_before();
+  fence_async_smem();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = *tmemSlot;
+  uint32_t ph1 = 0, ph2 = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N>(a, unit, pass, tmemBase, ph1, ph2);
 
   // ---- costs leave the SM ------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  for (int c = 0; c < kCtus; c++) {
-    const int cgc = group * kCtus + c;
+  const FrameSource& fs = a.fs;
+  for (int c = 0; c < C::CTUS; c++) {
+    const int cgc = unit * C::CTUS + c;
     if (cgc >= a.totalCtus) break;
-    const uint8_t* valid = smem + g.validOff + c * 256;
-    uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - log2n)) * kNumModes;
-    for (int i = tid; i < g.pus * kNumModes; i += kThreads) {
+    const uint8_t* valid = smem + C::VALID_OFF + c * 256;
+    uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
+    for (int i = tid; i < C::PUS * kNumModes; i += kThreads) {
       const bool v = valid[i / kNumModes] != 0;
-      if (g.accStaged) o[i] = v ? acc[c * g.pus * kNumModes + i] : 0xffffffffu;
+      if (C::ACC_STAGED) o[i] = v ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
       else if (!v) o[i] = 0xffffffffu;
     }
   }
-  if (warp == 0) tmem_dealloc(tmemBase, 512);
+  if (warp == 0) tmem_dealloc(tmemBase, 256);
 }
 
-template <int LOG2N>
-__device__ __forceinline__ void tc2_body(const Tc2Args& a, const int group) {
-  const Geo2 g = make_geo2<LOG2N>();
-  tc2_prologue<LOG2N>(a, g, group);
-  tc2_modes(a, LOG2N, group);
-}
-
-__global__ void __launch_bounds__(kThreads, 1)
+// blocks of one launch: depth-major (as rmd_frame_kernel); a depth has ceil(totalCtus / CTUS) units
+__global__ void __launch_bounds__(kThreads, 2)
 rmd_frame_tc2_kernel(const Tc2Args a) {
-  // depth-major block order, as rmd_frame_kernel
-  const int groups = gridDim.x / 5;
-  const int depth = blockIdx.x / groups, group = blockIdx.x - depth * groups;
-  switch (depth) {
-    case 0: tc2_body<6>(a, group); break;
-    case 1: tc2_body<5>(a, group); break;
-    case 2: tc2_body<4>(a, group); break;
-    case 3: tc2_body<3>(a, group); break;
-    default: tc2_body<2>(a, group); break;
-  }
+  const int u2 = (a.totalCtus + 1) >> 1, u4 = (a.totalCtus + 3) >> 2;
+  int b = blockIdx.x;
+  if (b < u4) { tc2_body<6>(a, b); return; }
+  b -= u4;
+  if (b < u4) { tc2_body<5>(a, b); return; }
+  b -= u4;
+  if (b < u2) { tc2_body<4>(a, b); return; }
+  b -= u2;
+  if (b < u2) { tc2_body<3>(a, b); return; }
+  tc2_body<2>(a, b - u2);
 }
-
-constexpr int cmax2(int a, int b) { return a > b ? a : b; }
 
 }  // namespace
 
-int rmd_tc2_smem_bytes() {
-  int m = 0;
-  for (int l = 2; l <= 6; l++) m = cmax2(m, make_geo2_rt(l).total);
-  return m;
-}
+int rmd_tc2_smem_bytes() { return kSmemBytes; }
 
 cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
                                   cudaStream_t st, int* launches) {
   const int total = nPics * fs.ctusPerPic;
   if (total <= 0) return cudaSuccess;
-  const int smemBytes = rmd_tc2_smem_bytes();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rmd_frame_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+    cudaError_t e = cudaFuncSetAttribute(rmd_frame_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   Tc2Args a;
   a.fs = fs; a.strong = strong; a.totalCtus = total; a.tabWin = tabWin; a.tabN4 = tabN4; a.had = hadamard;
-  const int groups = (total + kCtus - 1) / kCtus;
-  rmd_frame_tc2_kernel<<<groups * 5, kThreads, smemBytes, st>>>(a);
+  const int u2 = (total + 1) >> 1, u4 = (total + 3) >> 2;
+  rmd_frame_tc2_kernel<<<2 * u4 + 3 * u2, kThreads, kSmemBytes, st>>>(a);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -49,134 +49,139 @@ void mma(const uint32_t* aWords, int aStride, int K, const void* b, bool bSigned
 }
 
 template <int LOG2N>
-void emul_cta(const FrameSource& fs, int strong, int totalCtus, int group) {
+void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
   typedef Geo<LOG2N> G;
-  constexpr int N = G::N;
-  const Geo2 g = make_geo2<LOG2N>();
+  typedef Cfg<LOG2N> C;
+  constexpr int N = G::N, log2n = LOG2N;
   const Tables& tb = tables();
-  std::vector<unsigned char> smemStore(g.total + 256, 0xA5);
+  std::vector<unsigned char> smemStore(C::TOTAL + 256, 0xA5);
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemStore.data()) + 127) & ~uintptr_t(127));
-  SmemView<LOG2N> sm; sm.base = smem + g.scratchOff;
+  int16_t* lin = reinterpret_cast<int16_t*>(smem + C::LIN_OFF);
+  uint8_t* flags = smem + C::FLAGS_OFF;
+  int16_t* arrs = reinterpret_cast<int16_t*>(smem + C::ARRS_OFF);
+  int16_t* dc16 = reinterpret_cast<int16_t*>(smem + C::DC16_OFF);
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
+  if (C::ACC_STAGED) for (int i = 0; i < C::CTUS * C::PUS * kNumModes; i++) acc[i] = 0;
   // ---- prologue (tc2_prologue) ----
-  for (int c = 0; c < kCtus; c++) {
-    const int cg = group * kCtus + c;
-    uint8_t* valid = smem + g.validOff + c * 256;
+  for (int c = 0; c < C::CTUS; c++) {
+    const int cg = unit * C::CTUS + c;
+    uint8_t* valid = smem + C::VALID_OFF + c * 256;
     if (cg >= totalCtus) { for (int p = 0; p < G::PUS; p++) valid[p] = 0; continue; }
     const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
     const int ctuX = (ctu % fs.ctusPerRow) * 64, ctuY = (ctu / fs.ctusPerRow) * 64;
     const int16_t* recPic = fs.rec + (size_t)pic * fs.recPicStride;
     for (int p = 0; p < G::PUS; p++) { int px, py; demorton(p, px, py); valid[p] = ((ctuX + (px + 1) * N <= fs.W) && (ctuY + (py + 1) * N <= fs.H)) ? 1 : 0; }
-    for (int tid = 0; tid < kThreads; tid++) border_gather_frame<LOG2N>(tid, kThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, sm.lin(), sm.flags());
-    for (int tid = 0; tid < kThreads; tid++) border_substitute<LOG2N>(tid, kThreads, 8, sm.lin(), sm.flags());
-    for (int tid = 0; tid < kThreads; tid++) { border_derive<LOG2N>(tid, kThreads, 8, strong, sm.lin(), sm.arrs()); border_pad<LOG2N>(tid, kThreads, sm.arrs()); }
-    for (int tid = 0; tid < kThreads; tid++) border_dc<LOG2N>(tid, kThreads, sm.arrs(), sm.dc());
-    for (int tid = 0; tid < kThreads; tid++) convert_arrays<LOG2N>(tid, kThreads, g, c, sm.arrs(), sm.dc(), smem);
+    for (int tid = 0; tid < kThreads; tid++) border_gather_frame<LOG2N>(tid, kThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, lin, flags);
+    for (int tid = 0; tid < kThreads; tid++) border_substitute<LOG2N>(tid, kThreads, 8, lin, flags);
+    for (int tid = 0; tid < kThreads; tid++) { border_derive<LOG2N>(tid, kThreads, 8, strong, lin, arrs); border_pad<LOG2N>(tid, kThreads, arrs); }
+    if (LOG2N != 2) for (int tid = 0; tid < kThreads; tid++) border_dc<LOG2N>(tid, kThreads, arrs, dc16);
+    for (int tid = 0; tid < kThreads; tid++) convert_arrays<LOG2N>(tid, kThreads, c, arrs, dc16, smem);
   }
-  // ---- tc2_modes ----
-  const int log2n = LOG2N;
-  unsigned char* store = smem + g.storeOff;
-  uint32_t* acc = reinterpret_cast<uint32_t*>(smem + g.accOff);
-  if (g.accStaged) for (int i = 0; i < kCtus * g.pus * kNumModes; i++) acc[i] = 0;
+  unsigned char* store = smem + C::STORE_OFF;
   const int8_t* had = tb.had.data() + (log2n == 2 ? 8192 : 0);
-  std::vector<Row> rows(kThreads); std::vector<char> ok(kThreads);
-  std::vector<uint32_t> P(kThreads * 16), A1(kThreads * 16, 0xA5A5A5A5u), D(kThreads * 64), HO(kThreads * 64);
-  for (int tid = 0; tid < kThreads; tid++) {
-    const Row r = rows[tid] = row_map(log2n, tid);
-    const int cg = group * kCtus + r.ctu;
-    ok[tid] = smem[g.validOff + r.ctu * 256 + (log2n == 2 ? 4 * r.pu : r.pu)] != 0;
-    uint32_t* p = &P[tid * 16];
-    if (ok[tid]) {
-      const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-      int px, py; demorton(r.pu, px, py);
-      if (log2n == 2) { px *= 8; py *= 8; }
-      else { px = px * g.n + (r.o ? r.v0 : r.u0); py = py * g.n + (r.o ? r.u0 : r.v0); }
-      const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
-      uint32_t raw[16];
-      for (int y = 0; y < 8; y++)
-        for (int h = 0; h < 2; h++) {
-          uint32_t w = 0;
-          for (int i = 0; i < 4; i++) w |= (uint32_t)(src[(size_t)y * fs.orgStride + 4 * h + i] & 0xff) << (8 * i);
-          raw[2 * y + h] = w;
-        }
-      if (r.o) tile_transpose_bytes(raw, p, log2n != 2); else std::memcpy(p, raw, sizeof(raw));
-    } else std::memset(p, 0, 64);
-  }
-  auto hadamard = [&]() { for (int grp = 0; grp < 4; grp++) mma(&P[grp * 128 * 16], 16, 64, had, true, &D[grp * 128 * 64]); };
-  auto cost_out = [&](int am, bool angular) {
-    // warps in order; the shuffle reduction over r.seg lanes becomes a plain sum
+  for (int pass = 0; pass < C::PASSES; pass++) {
+    // ---- tc2_pass ----
+    std::vector<Row> rows(kThreads); std::vector<char> ok(kThreads);
+    std::vector<uint32_t> P(kThreads * 16), A1(kThreads * 16, 0xA5A5A5A5u), D(kThreads * 64), HO(kThreads * 64);
     for (int tid = 0; tid < kThreads; tid++) {
-      const Row& r = rows[tid];
-      const int mode = angular ? (r.o ? 10 - am : 26 + am) : (r.o ? 1 : 0);
-      const bool has = !(angular && r.o && am == -8);
-      uint32_t q[4];
-      for (int c = 0; c < 4; c++) { uint32_t s = 0; for (int k = 0; k < 16; k++) s = sad_acc(D[tid * 64 + c * 16 + k], HO[tid * 64 + c * 16 + k], s); q[c] = s; }
-      const int cg = group * kCtus + r.ctu;
-      if (log2n == 2) {
-        if (ok[tid] && has) for (int c = 0; c < 4; c++) fs.out[((size_t)cg * kPusPerCtu + pu_offset_of_depth(4) + 4 * r.pu + c) * kNumModes + mode] = (q[c] + 1u) >> 1;
-      } else if (ok[tid] && has) {
-        acc[(r.ctu * g.pus + r.pu) * kNumModes + mode] += (q[0] + q[1] + q[2] + q[3] + 2u) >> 2;
-      }
+      const Row r = rows[tid] = row_map<LOG2N>(tid, pass);
+      const int cg = unit * C::CTUS + r.ctu;
+      ok[tid] = smem[C::VALID_OFF + r.ctu * 256 + (log2n == 2 ? 4 * r.pu : r.pu)] != 0;
+      uint32_t* p = &P[tid * 16];
+      if (ok[tid]) {
+        const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
+        int px, py; demorton(r.pu, px, py);
+        if (log2n == 2) { px *= 8; py *= 8; }
+        else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
+        const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
+        uint32_t raw[16];
+        for (int y = 0; y < 8; y++)
+          for (int h = 0; h < 2; h++) {
+            uint32_t w = 0;
+            for (int i = 0; i < 4; i++) w |= (uint32_t)(src[(size_t)y * fs.orgStride + 4 * h + i] & 0xff) << (8 * i);
+            raw[2 * y + h] = w;
+          }
+        if (r.o) tile_transpose_bytes(raw, p, log2n != 2); else std::memcpy(p, raw, sizeof(raw));
+      } else std::memset(p, 0, 64);
     }
-  };
-  hadamard();
-  HO = D;
-  if (log2n == 2)
-    for (int tid = 0; tid < kThreads; tid++) std::memcpy(&A1[tid * 16], store + rec_off(rows[tid].ctu, rows[tid].o, 4 * rows[tid].pu), 64);
-  // round 0
-  for (int tid = 0; tid < kThreads; tid++) {
-    if (!ok[tid]) continue;
-    const Row& r = rows[tid]; uint32_t* p = &P[tid * 16];
-    const unsigned char* rec4 = store + rec_off(r.ctu, r.o, 4 * r.pu);
-    const int grp = tid >> 7, slot = pu_slot2(log2n, g.pus, r.ctu, r.pu);
-    if (log2n == 2) { if (r.o == 0) planar_region4(rec4, p); else dc_region4(rec4, p); }
-    else if (r.o == 0) planar_tile(log2n, store + arr_k0_off(g, grp, slot, 0, g.hasFilt), store + arr_k0_off(g, grp, slot, 1, g.hasFilt), r.u0, r.v0, p);
-    else dc_tile(reinterpret_cast<const int16_t*>(smem + g.dcOff)[r.ctu * 64 + r.pu], g.n <= 16, store + arr_k0_off(g, grp, slot, 1, 0),
-                 store + arr_k0_off(g, grp, slot, 0, 0), r.u0, r.v0, p);
-  }
-  hadamard();
-  cost_out(0, false);
-  for (int am = 8; am >= -8; --am) {
-    const int angle = angle_of_am(am), ai = am + 8;
-    const int filt = mode_uses_filtered_rt(log2n, 26 + am) ? 1 : 0;
-    if (log2n != 2 && angle < 0) for (int tid = 0; tid < kThreads; tid++) build_ext_group(tid & 127, g, tid >> 7, angle, inv_angle_of_am(am), filt, store);
-    for (int grp = 0; grp < 4; grp++) {
-      const uint8_t* b1;
-      if (log2n == 2) b1 = tb.n4.data() + ai * 4096;
-      else {
-        b1 = tb.win.data() + (ai * 4 + (group_frac0(log2n, grp, angle) >> 3)) * 2048;
-        for (int rt = 0; rt < 128; rt++) {
-          const int tid = grp * 128 + rt; const Row& r = rows[tid];
-          gather_window(store, arr_k0_off(g, grp, pu_slot2(log2n, g.pus, r.ctu, r.pu), r.o, filt) + win_k0(angle, r.u0, r.v0), &A1[tid * 16]);
+    auto hadamard = [&]() { for (int grp = 0; grp < kGroups; grp++) mma(&P[grp * 128 * 16], 16, 64, had, true, &D[grp * 128 * 64]); };
+    auto cost_out = [&](int am, bool angular) {
+      // warps in order; the shuffle reduction over SEG lanes and the shared-memory atomics become a plain sum
+      for (int tid = 0; tid < kThreads; tid++) {
+        const Row& r = rows[tid];
+        const int mode = angular ? (r.o ? 10 - am : 26 + am) : (r.o ? 1 : 0);
+        const bool has = !(angular && r.o && am == -8);
+        uint32_t q[4];
+        for (int c = 0; c < 4; c++) { uint32_t s = 0; for (int k = 0; k < 16; k++) s = sad_acc(D[tid * 64 + c * 16 + k], HO[tid * 64 + c * 16 + k], s); q[c] = s; }
+        const int cg = unit * C::CTUS + r.ctu;
+        if (log2n == 2) {
+          if (ok[tid] && has) for (int c = 0; c < 4; c++) fs.out[((size_t)cg * kPusPerCtu + pu_offset_of_depth(4) + 4 * r.pu + c) * kNumModes + mode] = (q[c] + 1u) >> 1;
+        } else if (ok[tid] && has) {
+          acc[(r.ctu * C::PUS + r.pu) * kNumModes + mode] += (q[0] + q[1] + q[2] + q[3] + 2u) >> 2;
         }
       }
-      mma(&A1[grp * 128 * 16], 16, log2n == 2 ? 64 : 32, b1, false, &D[grp * 128 * 64]);
-    }
+    };
+    hadamard();
+    HO = D;
+    if (log2n == 2)
+      for (int tid = 0; tid < kThreads; tid++) std::memcpy(&A1[tid * 16], store + rec_off(rows[tid].ctu, rows[tid].o, 4 * rows[tid].pu), 64);
+    // round 0
     for (int tid = 0; tid < kThreads; tid++) {
+      if (!ok[tid]) continue;
       const Row& r = rows[tid]; uint32_t* p = &P[tid * 16];
-      for (int h = 0; h < 2; h++) {
-        uint32_t v[16];
-        for (int j = 0; j < 16; j++) v[j] = (D[tid * 64 + h * 32 + 2 * j] & 0xffffu) | (D[tid * 64 + h * 32 + 2 * j + 1] << 16);   // tcgen05.ld.pack::16b
-        pack_pred(v, p + 8 * h, 8);
-      }
-      if (angle == 0 && g.n <= 16 && ok[tid]) {
-        if (log2n == 2) patch_edge0_region4(store + rec_off(r.ctu, r.o, 4 * r.pu), p);
-        else if (r.u0 == 0) {
-          const int slot = pu_slot2(log2n, g.pus, r.ctu, r.pu);
-          patch_edge0_tile(store + arr_k0_off(g, tid >> 7, slot, r.o, 0), store + arr_k0_off(g, tid >> 7, slot, r.o ^ 1, 0), r.v0, p);
-        }
-      }
+      const unsigned char* rec4 = store + rec_off(r.ctu, r.o, 4 * r.pu);
+      const int grp = tid >> 7, slot = pu_slot2<LOG2N>(r.ctu, r.pu);
+      constexpr int f = C::HAS_FILT ? 1 : 0;
+      if (log2n == 2) { if (r.o == 0) planar_region4(rec4, p); else dc_region4(rec4, p); }
+      else if (r.o == 0) planar_tile(log2n, store + arr_k0_off<LOG2N>(grp, slot, 0, f), store + arr_k0_off<LOG2N>(grp, slot, 1, f), r.u0, r.v0, p);
+      else dc_tile(reinterpret_cast<const int16_t*>(smem + C::DC_OFF)[r.ctu * 64 + r.pu], C::EDGE, store + arr_k0_off<LOG2N>(grp, slot, 1, 0),
+                   store + arr_k0_off<LOG2N>(grp, slot, 0, 0), r.u0, r.v0, p);
     }
     hadamard();
-    cost_out(am, true);
+    cost_out(0, false);
+    for (int am = 8; am >= -8; --am) {
+      const int angle = angle_of_am(am), ai = am + 8;
+      const int filt = mode_uses_filtered<LOG2N>(26 + am) ? 1 : 0;
+      if (log2n != 2 && angle < 0) for (int tid = 0; tid < kThreads; tid++) build_ext_group<LOG2N>(tid & 127, tid >> 7, angle, inv_angle_of_am(am), filt, store);
+      for (int grp = 0; grp < kGroups; grp++) {
+        const uint8_t* b1;
+        if (log2n == 2) b1 = tb.n4.data() + ai * 4096;
+        else {
+          b1 = tb.win.data() + (ai * 4 + (group_frac0<LOG2N>(grp, pass, angle) >> 3)) * 2048;
+          for (int rt = 0; rt < 128; rt++) {
+            const int tid = grp * 128 + rt; const Row& r = rows[tid];
+            gather_window(store, arr_k0_off<LOG2N>(grp, pu_slot2<LOG2N>(r.ctu, r.pu), r.o, filt) + win_k0(angle, r.u0, r.v0), &A1[tid * 16]);
+          }
+        }
+        mma(&A1[grp * 128 * 16], 16, log2n == 2 ? 64 : 32, b1, false, &D[grp * 128 * 64]);
+      }
+      for (int tid = 0; tid < kThreads; tid++) {
+        const Row& r = rows[tid]; uint32_t* p = &P[tid * 16];
+        for (int h = 0; h < 2; h++) {
+          uint32_t v[16];
+          for (int j = 0; j < 16; j++) v[j] = (D[tid * 64 + h * 32 + 2 * j] & 0xffffu) | (D[tid * 64 + h * 32 + 2 * j + 1] << 16);   // tcgen05.ld.pack::16b
+          pack_pred(v, p + 8 * h, 8);
+        }
+        if (C::EDGE && am == 0 && ok[tid]) {
+          if (log2n == 2) patch_edge0_region4(store + rec_off(r.ctu, r.o, 4 * r.pu), p);
+          else if (r.u0 == 0) {
+            const int slot = pu_slot2<LOG2N>(r.ctu, r.pu);
+            patch_edge0_tile(store + arr_k0_off<LOG2N>(tid >> 7, slot, r.o, 0), store + arr_k0_off<LOG2N>(tid >> 7, slot, r.o ^ 1, 0), r.v0, p);
+          }
+        }
+      }
+      hadamard();
+      cost_out(am, true);
+    }
   }
-  for (int c = 0; c < kCtus; c++) {
-    const int cgc = group * kCtus + c;
+  for (int c = 0; c < C::CTUS; c++) {
+    const int cgc = unit * C::CTUS + c;
     if (cgc >= totalCtus) break;
-    const uint8_t* valid = smem + g.validOff + c * 256;
+    const uint8_t* valid = smem + C::VALID_OFF + c * 256;
     uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - log2n)) * kNumModes;
-    for (int i = 0; i < g.pus * kNumModes; i++) {
+    for (int i = 0; i < C::PUS * kNumModes; i++) {
       const bool v = valid[i / kNumModes] != 0;
-      if (g.accStaged) o[i] = v ? acc[c * g.pus * kNumModes + i] : 0xffffffffu;
+      if (C::ACC_STAGED) o[i] = v ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
       else if (!v) o[i] = 0xffffffffu;
     }
   }
@@ -191,11 +196,9 @@ int emul_rmd_frame_tc2(int strong, const int16_t* org, int orgStride, const int1
   FrameSource fs;
   fs.org = org; fs.rec = rec; fs.orgPicStride = 0; fs.recPicStride = 0; fs.orgStride = orgStride; fs.recStride = recStride;
   fs.W = W; fs.H = H; fs.ctusPerRow = (W + 63) / 64; fs.ctusPerPic = fs.ctusPerRow * ((H + 63) / 64); fs.out = out;
-  const int total = fs.ctusPerPic, groups = (total + kCtus - 1) / kCtus;
-  for (int grp = 0; grp < groups; grp++) {
-    emul_cta<6>(fs, strong, total, grp); emul_cta<5>(fs, strong, total, grp); emul_cta<4>(fs, strong, total, grp);
-    emul_cta<3>(fs, strong, total, grp); emul_cta<2>(fs, strong, total, grp);
-  }
+  const int total = fs.ctusPerPic, u2 = (total + 1) >> 1, u4 = (total + 3) >> 2;
+  for (int u = 0; u < u4; u++) { emul_cta<6>(fs, strong, total, u); emul_cta<5>(fs, strong, total, u); }
+  for (int u = 0; u < u2; u++) { emul_cta<4>(fs, strong, total, u); emul_cta<3>(fs, strong, total, u); emul_cta<2>(fs, strong, total, u); }
   return 0;
 }
 // the weight tables, for inspection
