@@ -403,11 +403,23 @@ CUCD_HD void convert_arrays(int tid, int nthreads, int ctu, const int16_t* arrs,
 template <int LOG2N>
 CUCD_HD void build_ext_group(int rowTid, int grp, int angle, int inv, int filt, unsigned char* store) {
   typedef Cfg<LOG2N> C;
-  constexpr int TPP = 128 / (2 * C::SLOTS);
+  constexpr int TPP = LOG2N == 2 ? 1 : 128 / (2 * C::SLOTS);   // (N = 4 has no projected arrays; never called)
   const int nNeg = -((C::N * angle) >> 5) - 1;
   const int pair = rowTid / TPP, slot = pair >> 1, o = pair & 1;
   const int mainOff = arr_k0_off<LOG2N>(grp, slot, o, filt), sideOff = arr_k0_off<LOG2N>(grp, slot, o ^ 1, filt);
-  for (int j = 1 + (rowTid % TPP); j <= nNeg; j += TPP) store[mainOff - j] = store[sideOff + ((128 + j * inv) >> 8)];
+  // at most N / TPP <= 8 entries per thread; loads first, then stores (independent chains)
+  constexpr int MAXE = C::N / TPP > 8 ? 8 : C::N / TPP;
+  unsigned char v[MAXE];
+#pragma unroll
+  for (int e = 0; e < MAXE; e++) {
+    const int j = 1 + (rowTid % TPP) + e * TPP;
+    v[e] = j <= nNeg ? store[sideOff + ((128 + j * inv) >> 8)] : 0;
+  }
+#pragma unroll
+  for (int e = 0; e < MAXE; e++) {
+    const int j = 1 + (rowTid % TPP) + e * TPP;
+    if (j <= nNeg) store[mainOff - j] = v[e];
+  }
 }
 
 }  // namespace tc2

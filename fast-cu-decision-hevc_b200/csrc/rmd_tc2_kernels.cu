@@ -64,6 +64,15 @@ __device__ __forceinline__ void tmem_ld16_pack(uint32_t addr, uint32_t* v) {
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(addr) : "memory");
+}
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;\n" :: "r"(grp + 1) : "memory"); }
 
 // ---- prologue: reference arrays of the CTA's CTUs ------------------------------------------------------
@@ -224,14 +233,18 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   auto cost_out = [&](int mode, bool has) {
     uint32_t q[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      uint32_t v[16];
-      tmem_ld16(tD2 + laneOff + c * 16, v);
+    for (int h = 0; h < 2; h++) {
+      uint32_t v[32];
+      tmem_ld32(tD2 + laneOff + h * 32, v);
       tmem_ld_wait();
-      uint32_t s = 0;
+      // two 16-column chunks, each summed by two independent chains (the dependent VABSDIFF chain is the latency here)
+      uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-      for (int k = 0; k < 16; k++) s = sad_acc(v[k], ho[c * 16 + k], s);
-      q[c] = s;
+      for (int k = 0; k < 8; k++) {
+        s0 = sad_acc(v[k], ho[h * 32 + k], s0);           s1 = sad_acc(v[8 + k], ho[h * 32 + 8 + k], s1);
+        s2 = sad_acc(v[16 + k], ho[h * 32 + 16 + k], s2); s3 = sad_acc(v[24 + k], ho[h * 32 + 24 + k], s3);
+      }
+      q[2 * h] = s0 + s1; q[2 * h + 1] = s2 + s3;
     }
     tc_fence_before();
     if (LOG2N == 2) {
@@ -294,12 +307,13 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     const int angleNext2 = am > -7 ? angle_of_am(am - 2) : 0;
     wait_mma1();
     // epilogue 1: byte 1 of every accumulator is the predicted pixel
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      uint32_t v[16];
-      tmem_ld16_pack(tD1 + laneOff + h * 32, v);
+    {
+      uint32_t v[32];
+      tmem_ld16_pack(tD1 + laneOff, v);
+      tmem_ld16_pack(tD1 + laneOff + 32, v + 16);
       tmem_ld_wait();
-      pack_pred(v, p + 8 * h, 8);
+      pack_pred(v, p, 8);
+      pack_pred(v + 16, p + 8, 8);
     }
     if (C::EDGE && am == 0 && ok) {
       if (LOG2N == 2) patch_edge0_region4(rec4, p);
