@@ -159,15 +159,17 @@ struct Cfg {
   static constexpr int A1_OFF = B1_OFF + kGroups * 2 * B1_BYTES; // [group]: two 4 KB window operands (N >= 8) or one static 8 KB record operand (N = 4)
   static constexpr int BAR_OFF = A1_OFF + kGroups * 8192;
   static constexpr int VALID_OFF = BAR_OFF + 128;
-  static constexpr int DC_OFF = VALID_OFF + CTUS * 256;          // int16 [ctu][64], N >= 8
-  static constexpr int STORE_OFF = DC_OFF + CTUS * 64 * 2;
+  static constexpr int DC_OFF = VALID_OFF + CTUS * 256;          // int32 [ctu][64]: sum of the N above + N left samples (N >= 8)
+  static constexpr int STORE_OFF = DC_OFF + CTUS * 64 * 4;
   static constexpr int ACC_OFF = STORE_OFF + al16(STORE_BYTES);
-  // scratch of the border construction, one CTU at a time (rmd_core.cuh phases)
-  static constexpr int LIN_OFF = ACC_OFF + (ACC_STAGED ? CTUS * PUS * kNumModes * 4 : 0);
-  static constexpr int FLAGS_OFF = LIN_OFF + al16(PUS * G::LIN * 2);
-  static constexpr int ARRS_OFF = FLAGS_OFF + al16(PUS * (N + 1));
-  static constexpr int DC16_OFF = ARRS_OFF + al16(PUS * G::PU_STRIDE * 2);
-  static constexpr int TOTAL = DC16_OFF + al16(PUS * 2);
+  static constexpr int TOTAL = ACC_OFF + (ACC_STAGED ? CTUS * PUS * kNumModes * 4 : 0);
+  // u8 copy of the reconstruction around each CTU while the reference arrays are built; aliases the MMA 1 operand
+  // buffers, which are first written after the prologue
+  static constexpr int TILE_OFF = B1_OFF;
+  static constexpr int TILE_PITCH = 68;                          // 17 words: a column walk touches 32 different banks
+  static constexpr int TILE_TOP = 64 * TILE_PITCH;               // row y = -1, x = -1 .. 127
+  static constexpr int TILE_BYTES = al16(TILE_TOP + 136);
+  static_assert(CTUS * TILE_BYTES <= kGroups * 2 * B1_BYTES + kGroups * 8192, "tiles must fit the aliased operand buffers");
 };
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int kSmemBytes = cmax(cmax(cmax(Cfg<2>::TOTAL, Cfg<3>::TOTAL), cmax(Cfg<4>::TOTAL, Cfg<5>::TOTAL)), Cfg<6>::TOTAL);
@@ -367,37 +369,146 @@ CUCD_HD void dc_region4(const unsigned char* rec, uint32_t* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// prologue helpers: int16 arrays of one CTU (rmd_core.cuh border phases) -> u8 store of the CTA
+// prologue: reference arrays of one CTU straight from the reconstruction plane (frame / replay mode)
 // ---------------------------------------------------------------------------------------------
+// Phase 1: the CTU's 64x64 reconstruction block, the row above it (x = -1 .. 127) and the column left of it as
+// bytes in shared memory.  tile[y][x] = t[y * PITCH + 4 + x], y = 0..63, x = -1..63;  top[x] = t[TOP + 4 + x].
+// Samples outside the picture are not touched (never consumed: availability masks them).
 template <int LOG2N>
-CUCD_HD void convert_arrays(int tid, int nthreads, int ctu, const int16_t* arrs, const int16_t* dc, unsigned char* smem) {
-  typedef Geo<LOG2N> G;
+CUCD_HD void stage_tile(int tid, int nthreads, const int16_t* rec, int recStride, int W, int H, int ctuX, int ctuY, unsigned char* t) {
   typedef Cfg<LOG2N> C;
-  constexpr int N = G::N, LEN = 2 * N + 1;
-  unsigned char* store = smem + C::STORE_OFF;
-  if (LOG2N == 2) {
-    // record of (pu, o): main[0..8], side[1..5], 0, 1
-    for (int idx = tid; idx < G::PUS * 2 * 16; idx += nthreads) {
-      const int b = idx & 15, o = (idx >> 4) & 1, p = idx >> 5;
-      const int16_t* a = arrs + pu_slot<LOG2N>(p) * G::PU_STRIDE;
-      int v;
-      if (b <= 8) v = a[(o ? 1 : 0) * G::AS + b];
-      else if (b <= 13) v = a[(o ? 0 : 1) * G::AS + (b - 8)];
-      else v = b == 15 ? 1 : 0;
-      store[rec_off(ctu, o, p) + b] = (unsigned char)v;
-    }
-  } else {
-    // N = 8: row group = CTU; N >= 16: both groups see every CTU of the CTA
-    for (int idx = tid; idx < G::PUS * G::NARR * LEN; idx += nthreads) {
-      const int k = idx % LEN, t = idx / LEN, which = t % G::NARR, p = t / G::NARR;
-      const unsigned char v = (unsigned char)arrs[pu_slot<LOG2N>(p) * G::PU_STRIDE + which * G::AS + k];
-      const int slot = pu_slot2<LOG2N>(ctu, p);
-      if (LOG2N == 3) store[arr_k0_off<LOG2N>(ctu, slot, which & 1, which >> 1) + k] = v;
-      else { store[arr_k0_off<LOG2N>(0, slot, which & 1, which >> 1) + k] = v; store[arr_k0_off<LOG2N>(1, slot, which & 1, which >> 1) + k] = v; }
-    }
-    for (int p = tid; p < G::PUS; p += nthreads) reinterpret_cast<int16_t*>(smem + C::DC_OFF)[ctu * 64 + p] = dc[p];
+  for (int idx = tid; idx < 64 * 8; idx += nthreads) {
+    const int y = idx >> 3, x = (idx & 7) * 8;
+    if (ctuY + y >= H || ctuX + x >= W) continue;                  // W, H are multiples of 8
+    const int16_t* src = rec + (size_t)(ctuY + y) * recStride + ctuX + x;
+    uint32_t w0, w1;
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4*>(src);
+    w0 = __byte_perm(v.x, v.y, 0x6420); w1 = __byte_perm(v.z, v.w, 0x6420);
+#else
+    w0 = 0; w1 = 0;
+    for (int i = 0; i < 4; i++) { w0 |= (uint32_t)(src[i] & 0xff) << (8 * i); w1 |= (uint32_t)(src[4 + i] & 0xff) << (8 * i); }
+#endif
+    uint32_t* d = reinterpret_cast<uint32_t*>(t + y * C::TILE_PITCH + 4 + x);
+    d[0] = w0; d[1] = w1;
+  }
+  if (ctuX > 0) for (int y = tid; y < 64; y += nthreads) if (ctuY + y < H) t[y * C::TILE_PITCH + 3] = (unsigned char)rec[(size_t)(ctuY + y) * recStride + ctuX - 1];
+  if (ctuY > 0) for (int x = tid; x < 129; x += nthreads) {
+    const int gx = ctuX - 1 + x;
+    if (gx >= 0 && gx < W) t[C::TILE_TOP + 3 + x] = (unsigned char)rec[(size_t)(ctuY - 1) * recStride + gx];
   }
 }
+
+// Phase 2: unfiltered reference arrays with HEVC substitution (TComPattern.cpp:314-521) in closed form.  In
+// replay mode availability is positional (z-scan order, TComPattern.cpp:550-727): the left column, the corner
+// and the above row are each available or not as a whole, the below-left / above-right extensions are available
+// for their first cntBL / cntAR 4-sample units (the neighbouring block precedes the PU in z order; the picture
+// edge cuts the run).  Scan order of the substitution: L[2N] .. L[1], corner, T[1] .. T[2N]:
+//   a leading unavailable run takes the first available sample, any other unavailable sample its predecessor.
+struct PuAvail { int lenL, lenT, availC; };
+template <int LOG2N>
+CUCD_HD PuAvail pu_avail(int X0, int Y0, int W, int H) {
+  constexpr int N = 1 << LOG2N;
+  PuAvail a;
+  const bool availL = X0 > 0, availA = Y0 > 0;
+  int cntBL = 0, cntAR = 0;
+  if (availL && unit_available(X0, Y0, X0 - 1, Y0 + N, W, H)) cntBL = imin32(N / 4, (H - (Y0 + N)) >> 2);
+  if (availA && unit_available(X0, Y0, X0 + N, Y0 - 1, W, H)) cntAR = imin32(N / 4, (W - (X0 + N)) >> 2);
+  a.lenL = availL ? N + 4 * cntBL : 0;
+  a.lenT = availA ? N + 4 * cntAR : 0;
+  a.availC = availL && availA;
+  return a;
+}
+// write one unfiltered sample (array o: 0 = T, 1 = L; element k) of PU (ctu, p) into the store
+template <int LOG2N>
+CUCD_HD void put_ref(unsigned char* store, int ctu, int p, int o, int k, int v) {
+  if (LOG2N == 2) {
+    if (k <= 8) store[rec_off(ctu, o, p) + k] = (unsigned char)v;                   // main of orientation o
+    if (k >= 1 && k <= 5) store[rec_off(ctu, o ^ 1, p) + 8 + k] = (unsigned char)v; // side of the other orientation
+  } else {
+    const int slot = pu_slot2<LOG2N>(ctu, p);
+    if (LOG2N == 3) store[arr_k0_off<LOG2N>(ctu, slot, o, 0) + k] = (unsigned char)v;
+    else { store[arr_k0_off<LOG2N>(0, slot, o, 0) + k] = (unsigned char)v; store[arr_k0_off<LOG2N>(1, slot, o, 0) + k] = (unsigned char)v; }
+  }
+}
+// 256 / PUS threads share a PU; each produces 4N / (256 / PUS) consecutive samples of the sequence T[1..2N], L[1..2N]
+// (N = 4: one thread per PU, 16 samples) and the first of them the corner.
+template <int LOG2N>
+CUCD_HD void build_unfiltered(int tid, int ctu, int W, int H, int ctuX, int ctuY, const unsigned char* t, unsigned char* smem) {
+  typedef Cfg<LOG2N> C;
+  constexpr int N = C::N, TPP = 256 / C::PUS, SPT = 4 * N / TPP;
+  unsigned char* store = smem + C::STORE_OFF;
+  const int p = tid / TPP, sub = tid % TPP;
+  if (!smem[C::VALID_OFF + ctu * 256 + p]) return;
+  int px, py; demorton(p, px, py);
+  const int x0 = px * N, y0 = py * N;
+  const PuAvail a = pu_avail<LOG2N>(ctuX + x0, ctuY + y0, W, H);
+  const unsigned char* rowT = y0 == 0 ? t + C::TILE_TOP + 4 + x0 - 1 : t + (y0 - 1) * C::TILE_PITCH + 4 + x0 - 1;   // rowT[k] = T[k]
+  const unsigned char* colL = t + (y0 - 1) * C::TILE_PITCH + 4 + x0 - 1;                                            // colL[k * PITCH] = L[k], k >= 1
+  const int firstAvail = a.lenL > 0 ? colL[a.lenL * C::TILE_PITCH] : (a.availC ? rowT[0] : (a.lenT > 0 ? rowT[1] : 128));
+  const int cval = a.availC ? rowT[0] : (a.lenL > 0 ? colL[C::TILE_PITCH] : firstAvail);
+  const int tailT = a.lenT > 0 ? rowT[a.lenT] : cval;
+  if (sub == 0) {
+    put_ref<LOG2N>(store, ctu, p, 0, 0, cval); put_ref<LOG2N>(store, ctu, p, 1, 0, cval);
+    if (LOG2N == 2) { store[rec_off(ctu, 0, p) + 14] = 0; store[rec_off(ctu, 0, p) + 15] = 1; store[rec_off(ctu, 1, p) + 14] = 0; store[rec_off(ctu, 1, p) + 15] = 1; }
+  }
+  int dcSum = 0;
+#pragma unroll
+  for (int e = 0; e < SPT; e++) {
+    const int j = sub * SPT + e;                     // 0 .. 4N-1
+    const int o = j >= 2 * N, k = j - o * 2 * N + 1; // T[k] or L[k]
+    int v;
+    if (o == 0) v = k <= a.lenT ? rowT[k] : tailT;
+    else v = k <= a.lenL ? colL[k * C::TILE_PITCH] : firstAvail;
+    put_ref<LOG2N>(store, ctu, p, o, k, v);
+    if (k <= N) dcSum += v;
+  }
+  if (LOG2N >= 3) {
+    int* dst = reinterpret_cast<int*>(smem + C::DC_OFF) + ctu * 64 + p;
+#if defined(__CUDA_ARCH__)
+    if (dcSum) atomicAdd(dst, dcSum);
+#else
+    *dst += dcSum;
+#endif
+  }
+}
+// Phase 3: smoothed arrays (TComPattern.cpp:185-283) from the unfiltered ones, same thread -> sample map
+template <int LOG2N>
+CUCD_HD void build_filtered(int tid, int ctu, int strongEnabled, unsigned char* smem) {
+  typedef Cfg<LOG2N> C;
+  if (!C::HAS_FILT) return;
+  constexpr int N = C::N, TPP = 256 / C::PUS, SPT = 4 * N / TPP;
+  unsigned char* store = smem + C::STORE_OFF;
+  const int p = tid / TPP, sub = tid % TPP;
+  if (!smem[C::VALID_OFF + ctu * 256 + p]) return;
+  const int slot = pu_slot2<LOG2N>(ctu, p);
+  const int g0 = LOG2N == 3 ? ctu : 0;
+  const unsigned char* T = store + arr_k0_off<LOG2N>(g0, slot, 0, 0);
+  const unsigned char* L = store + arr_k0_off<LOG2N>(g0, slot, 1, 0);
+  bool strong = false;
+  const int tl = T[0], bl = L[2 * N], tr = T[2 * N];
+  if (LOG2N == 5 && strongEnabled) strong = iabs32(bl + tl - 2 * (int)L[N]) < 8 && iabs32(tl + tr - 2 * (int)T[N]) < 8;   // 1 << (bitDepth - 5)
+  auto put = [&](int o, int k, int v) {
+    if (LOG2N == 3) store[arr_k0_off<LOG2N>(ctu, slot, o, 1) + k] = (unsigned char)v;
+    else { store[arr_k0_off<LOG2N>(0, slot, o, 1) + k] = (unsigned char)v; store[arr_k0_off<LOG2N>(1, slot, o, 1) + k] = (unsigned char)v; }
+  };
+  if (sub == 0) {
+    const int c = strong ? tl : ((int)L[1] + 2 * tl + (int)T[1] + 2) >> 2;
+    put(0, 0, c); put(1, 0, c);
+  }
+#pragma unroll
+  for (int e = 0; e < SPT; e++) {
+    const int j = sub * SPT + e;
+    const int o = j >= 2 * N, k = j - o * 2 * N + 1;
+    const unsigned char* A = o ? L : T;
+    int v;
+    if (k == 2 * N) v = A[k];
+    else if (strong) v = o ? (k * bl + (2 * N - k) * tl + N) >> (LOG2N + 1) : ((2 * N - k) * tl + k * tr + N) >> (LOG2N + 1);
+    else v = ((int)A[k - 1] + 2 * (int)A[k] + (int)A[k + 1] + 2) >> 2;
+    put(o, k, v);
+  }
+}
+
 // projected samples of a negative-angle round, by the 128 threads of row group `grp` for its private arrays:
 // store[main][-j] = store[side][(128 + j*inv) >> 8], j = 1 .. nNeg.  128 / (2 * SLOTS) threads share one (slot, orientation) pair.
 template <int LOG2N>

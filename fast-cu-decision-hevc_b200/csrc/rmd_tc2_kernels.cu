@@ -75,43 +75,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
 }
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;\n" :: "r"(grp + 1) : "memory"); }
 
-// ---- prologue: reference arrays of the CTA's CTUs ------------------------------------------------------
+// ---- prologue: reference arrays of the CTA's CTUs (rmd_tc2.cuh phases 1-3) --------------------------------
 template <int LOG2N>
 __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
-  typedef Geo<LOG2N> G;
   typedef Cfg<LOG2N> C;
-  constexpr int N = G::N;
+  constexpr int N = C::N;
   unsigned char* smem = smem2;
-  int16_t* lin = reinterpret_cast<int16_t*>(smem + C::LIN_OFF);
-  uint8_t* flags = smem + C::FLAGS_OFF;
-  int16_t* arrs = reinterpret_cast<int16_t*>(smem + C::ARRS_OFF);
-  int16_t* dc16 = reinterpret_cast<int16_t*>(smem + C::DC16_OFF);
   const int tid = threadIdx.x;
   const FrameSource& fs = a.fs;
+  int ctuX[C::CTUS], ctuY[C::CTUS];
+#pragma unroll
   for (int c = 0; c < C::CTUS; c++) {
     const int cg = unit * C::CTUS + c;
     uint8_t* valid = smem + C::VALID_OFF + c * 256;
+    ctuX[c] = -1; ctuY[c] = -1;
     if (cg >= a.totalCtus) {                                   // CTA-uniform
-      for (int p = tid; p < G::PUS; p += kThreads) valid[p] = 0;
+      for (int p = tid; p < C::PUS; p += kThreads) valid[p] = 0;
       continue;
     }
     const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-    const int ctuX = (ctu % fs.ctusPerRow) * 64, ctuY = (ctu / fs.ctusPerRow) * 64;
-    const int16_t* recPic = fs.rec + (size_t)pic * fs.recPicStride;
-    for (int p = tid; p < G::PUS; p += kThreads) {
+    ctuX[c] = (ctu % fs.ctusPerRow) * 64; ctuY[c] = (ctu / fs.ctusPerRow) * 64;
+    for (int p = tid; p < C::PUS; p += kThreads) {
       int px, py; demorton(p, px, py);
-      valid[p] = ((ctuX + (px + 1) * N <= fs.W) && (ctuY + (py + 1) * N <= fs.H)) ? 1 : 0;
+      valid[p] = ((ctuX[c] + (px + 1) * N <= fs.W) && (ctuY[c] + (py + 1) * N <= fs.H)) ? 1 : 0;
     }
-    border_gather_frame<LOG2N>(tid, kThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, lin, flags);
+    stage_tile<LOG2N>(tid, kThreads, fs.rec + (size_t)pic * fs.recPicStride, fs.recStride, fs.W, fs.H, ctuX[c], ctuY[c], smem + C::TILE_OFF + c * C::TILE_BYTES);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < C::CTUS; c++)
+    if (ctuX[c] >= 0) build_unfiltered<LOG2N>(tid, c, fs.W, fs.H, ctuX[c], ctuY[c], smem + C::TILE_OFF + c * C::TILE_BYTES, smem);
+  if (C::HAS_FILT) {
     __syncthreads();
-    border_substitute<LOG2N>(tid, kThreads, 8, lin, flags);
-    __syncthreads();
-    border_derive<LOG2N>(tid, kThreads, 8, a.strong, lin, arrs);
-    border_pad<LOG2N>(tid, kThreads, arrs);
-    __syncthreads();
-    if (LOG2N != 2) { border_dc<LOG2N>(tid, kThreads, arrs, dc16); __syncthreads(); }
-    convert_arrays<LOG2N>(tid, kThreads, c, arrs, dc16, smem);
-    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C::CTUS; c++)
+      if (ctuX[c] >= 0) build_filtered<LOG2N>(tid, c, a.strong, smem);
   }
 }
 
@@ -281,7 +279,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
       constexpr int f = C::HAS_FILT ? 1 : 0;        // planar reads the smoothed border for N = 8, 16, 32 (TComPattern.cpp:523-548)
       planar_tile(LOG2N, store + arr_k0_off<LOG2N>(grp, slot, 0, f), store + arr_k0_off<LOG2N>(grp, slot, 1, f), r.u0, r.v0, p);
     } else {
-      dc_tile(reinterpret_cast<const int16_t*>(smem + C::DC_OFF)[r.ctu * 64 + r.pu], C::EDGE, unfMain, unfSide, r.u0, r.v0, p);
+      dc_tile((reinterpret_cast<const int*>(smem + C::DC_OFF)[r.ctu * 64 + r.pu] + N) >> (LOG2N + 1), C::EDGE, unfMain, unfSide, r.u0, r.v0, p);
     }
   }
   wait_mma2();
@@ -349,6 +347,8 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   if (warp == 0) tmem_alloc(tmemSlot, 256);
   reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid];
   if (C::ACC_STAGED) for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) acc[i] = 0;
+  reinterpret_cast<int*>(smem + C::DC_OFF)[tid] = 0;          // CTUS * 64 <= 256 sums
+  __syncthreads();
   tc2_prologue<LOG2N>(a, unit);
   tc_fence_before();
   fence_async_smem();

@@ -56,27 +56,27 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
   const Tables& tb = tables();
   std::vector<unsigned char> smemStore(C::TOTAL + 256, 0xA5);
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemStore.data()) + 127) & ~uintptr_t(127));
-  int16_t* lin = reinterpret_cast<int16_t*>(smem + C::LIN_OFF);
-  uint8_t* flags = smem + C::FLAGS_OFF;
-  int16_t* arrs = reinterpret_cast<int16_t*>(smem + C::ARRS_OFF);
-  int16_t* dc16 = reinterpret_cast<int16_t*>(smem + C::DC16_OFF);
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
   if (C::ACC_STAGED) for (int i = 0; i < C::CTUS * C::PUS * kNumModes; i++) acc[i] = 0;
+  for (int i = 0; i < C::CTUS * 64; i++) reinterpret_cast<int*>(smem + C::DC_OFF)[i] = 0;
   // ---- prologue (tc2_prologue) ----
+  int ctuXs[C::CTUS], ctuYs[C::CTUS];
   for (int c = 0; c < C::CTUS; c++) {
     const int cg = unit * C::CTUS + c;
     uint8_t* valid = smem + C::VALID_OFF + c * 256;
+    ctuXs[c] = ctuYs[c] = -1;
     if (cg >= totalCtus) { for (int p = 0; p < G::PUS; p++) valid[p] = 0; continue; }
     const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-    const int ctuX = (ctu % fs.ctusPerRow) * 64, ctuY = (ctu / fs.ctusPerRow) * 64;
+    const int ctuX = ctuXs[c] = (ctu % fs.ctusPerRow) * 64, ctuY = ctuYs[c] = (ctu / fs.ctusPerRow) * 64;
     const int16_t* recPic = fs.rec + (size_t)pic * fs.recPicStride;
     for (int p = 0; p < G::PUS; p++) { int px, py; demorton(p, px, py); valid[p] = ((ctuX + (px + 1) * N <= fs.W) && (ctuY + (py + 1) * N <= fs.H)) ? 1 : 0; }
-    for (int tid = 0; tid < kThreads; tid++) border_gather_frame<LOG2N>(tid, kThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, lin, flags);
-    for (int tid = 0; tid < kThreads; tid++) border_substitute<LOG2N>(tid, kThreads, 8, lin, flags);
-    for (int tid = 0; tid < kThreads; tid++) { border_derive<LOG2N>(tid, kThreads, 8, strong, lin, arrs); border_pad<LOG2N>(tid, kThreads, arrs); }
-    if (LOG2N != 2) for (int tid = 0; tid < kThreads; tid++) border_dc<LOG2N>(tid, kThreads, arrs, dc16);
-    for (int tid = 0; tid < kThreads; tid++) convert_arrays<LOG2N>(tid, kThreads, c, arrs, dc16, smem);
+    for (int tid = 0; tid < kThreads; tid++) stage_tile<LOG2N>(tid, kThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, smem + C::TILE_OFF + c * C::TILE_BYTES);
   }
+  for (int c = 0; c < C::CTUS; c++)
+    if (ctuXs[c] >= 0) for (int tid = 0; tid < kThreads; tid++) build_unfiltered<LOG2N>(tid, c, fs.W, fs.H, ctuXs[c], ctuYs[c], smem + C::TILE_OFF + c * C::TILE_BYTES, smem);
+  for (int c = 0; c < C::CTUS; c++)
+    if (ctuXs[c] >= 0) for (int tid = 0; tid < kThreads; tid++) build_filtered<LOG2N>(tid, c, strong, smem);
+  std::memset(smem + C::TILE_OFF, 0x5A, C::CTUS * C::TILE_BYTES);   // the tiles alias the operand buffers: gone after the prologue
   unsigned char* store = smem + C::STORE_OFF;
   const int8_t* had = tb.had.data() + (log2n == 2 ? 8192 : 0);
   for (int pass = 0; pass < C::PASSES; pass++) {
@@ -134,7 +134,7 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
       constexpr int f = C::HAS_FILT ? 1 : 0;
       if (log2n == 2) { if (r.o == 0) planar_region4(rec4, p); else dc_region4(rec4, p); }
       else if (r.o == 0) planar_tile(log2n, store + arr_k0_off<LOG2N>(grp, slot, 0, f), store + arr_k0_off<LOG2N>(grp, slot, 1, f), r.u0, r.v0, p);
-      else dc_tile(reinterpret_cast<const int16_t*>(smem + C::DC_OFF)[r.ctu * 64 + r.pu], C::EDGE, store + arr_k0_off<LOG2N>(grp, slot, 1, 0),
+      else dc_tile((reinterpret_cast<const int*>(smem + C::DC_OFF)[r.ctu * 64 + r.pu] + N) >> (LOG2N + 1), C::EDGE, store + arr_k0_off<LOG2N>(grp, slot, 1, 0),
                    store + arr_k0_off<LOG2N>(grp, slot, 0, 0), r.u0, r.v0, p);
     }
     hadamard();
