@@ -151,7 +151,7 @@ struct Cfg {
   static constexpr int GROUP_BYTES = LOG2N == 2 ? 0 : al16(16 + SLOTS * PU_BYTES);
   static constexpr int STORE_BYTES = LOG2N == 2 ? CTUS * 256 * 2 * 16 : kGroups * GROUP_BYTES;   // N = 4: shared 16-byte records [ctu][o][pu]
   static constexpr int B1_BYTES = LOG2N == 2 ? 4096 : 2048;      // one MMA 1 weight operand
-  static constexpr bool ACC_STAGED = LOG2N != 2;                 // costs staged in shared memory; N = 4 writes global directly
+  static constexpr int ACC_ELEM = LOG2N == 2 ? 2 : 4;            // costs are staged in shared memory: uint32, N = 4: uint16 (<= 8160 for 8-bit content)
   static constexpr bool EDGE = LOG2N <= 4;                       // luma edge filters (DC, pure vertical / horizontal)
   // byte offsets inside dynamic shared memory
   static constexpr int HAD_OFF = 0;
@@ -162,7 +162,7 @@ struct Cfg {
   static constexpr int DC_OFF = VALID_OFF + CTUS * 256;          // int32 [ctu][64]: sum of the N above + N left samples (N >= 8)
   static constexpr int STORE_OFF = DC_OFF + CTUS * 64 * 4;
   static constexpr int ACC_OFF = STORE_OFF + al16(STORE_BYTES);
-  static constexpr int TOTAL = ACC_OFF + (ACC_STAGED ? CTUS * PUS * kNumModes * 4 : 0);
+  static constexpr int TOTAL = ACC_OFF + al16(CTUS * PUS * kNumModes * ACC_ELEM);
   // u8 copy of the reconstruction around each CTU while the reference arrays are built; aliases the MMA 1 operand
   // buffers, which are first written after the prologue
   static constexpr int TILE_OFF = B1_OFF;

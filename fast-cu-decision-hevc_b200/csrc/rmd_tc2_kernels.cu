@@ -22,6 +22,14 @@ extern __shared__ __align__(128) unsigned char smem2[];
 using namespace tc;
 using namespace tc2;
 
+// CUCD_TC2_TIMING (profiles/ubench/tc2_timing.cu only): per-CTA clock64 stamps of thread 0 at phase boundaries
+#ifdef CUCD_TC2_TIMING
+__device__ long long* g_tc2Dbg = nullptr;
+#define TC2_STAMP(i) do { if (g_tc2Dbg && threadIdx.x == 0) g_tc2Dbg[(size_t)blockIdx.x * 64 + (i)] = clock64(); } while (0)
+#else
+#define TC2_STAMP(i) do { } while (0)
+#endif
+
 namespace {
 
 struct Tc2Args {
@@ -226,7 +234,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     d[128] = make_uint4(w8[4], w8[5], w8[6], w8[7]);          // second 16-byte chunk: + 128 rows * 16 B
   };
   // epilogue 2 + cost hand-over for mode `mode` (has = the row has a mode in this round)
-  uint32_t* outN4 = fs.out + ((size_t)cg * kPusPerCtu + pu_offset_of_depth(4) + 4 * r.pu) * kNumModes;
+  uint16_t* accN4 = reinterpret_cast<uint16_t*>(acc) + (r.ctu * C::PUS + 4 * r.pu) * kNumModes;
   uint32_t* accRow = acc + (r.ctu * C::PUS + r.pu) * kNumModes;
   auto cost_out = [&](int mode, bool has) {
     uint32_t q[4];
@@ -248,7 +256,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     if (LOG2N == 2) {
       if (ok && has) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) outN4[c * kNumModes + mode] = (q[c] + 1u) >> 1;      // xCalcHADs4x4 rounding; 8-bit: no final shift
+        for (int c = 0; c < 4; c++) accN4[c * kNumModes + mode] = (uint16_t)((q[c] + 1u) >> 1);   // xCalcHADs4x4 rounding; 8-bit: no final shift
       }
     } else {
       uint32_t v = ok ? ((q[0] + q[1] + q[2] + q[3] + 2u) >> 2) : 0u;                    // xCalcHADs8x8 rounding
@@ -296,6 +304,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   wait_mma2();
   issue_mma1(0);
   cost_out(r.o ? 1 : 0, true);
+  if (pass == 0) TC2_STAMP(8);
 
   // ---- angular rounds -----------------------------------------------------------------------------------------
   int angle = 32, angleNext = 26;
@@ -328,6 +337,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     wait_mma2();
     if (am > -8) issue_mma1(buf ^ 1);
     cost_out(r.o ? 10 - am : 26 + am, !(r.o && am == -8));
+    if (pass == 0) TC2_STAMP(9 + 8 - am);
     angle = angleNext; angleNext = angleNext2;
   }
   (void)angle;
@@ -344,9 +354,10 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
     for (int i = 0; i < 2 * kGroups; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  TC2_STAMP(0);
   if (warp == 0) tmem_alloc(tmemSlot, 256);
   reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid];
-  if (C::ACC_STAGED) for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) acc[i] = 0;
+  if (LOG2N >= 4) for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) acc[i] = 0;   // accumulated with atomics
   reinterpret_cast<int*>(smem + C::DC_OFF)[tid] = 0;          // CTUS * 64 <= 256 sums
   __syncthreads();
   tc2_prologue<LOG2N>(a, unit);
@@ -356,8 +367,10 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   tc_fence_after();
   const uint32_t tmemBase = *tmemSlot;
   uint32_t ph1 = 0, ph2 = 0;
+  TC2_STAMP(1);
 #pragma unroll 1
   for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N>(a, unit, pass, tmemBase, ph1, ph2);
+  TC2_STAMP(2);
 
   // ---- costs leave the SM ------------------------------------------------------------------------------------
   tc_fence_before();
@@ -368,13 +381,20 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
     if (cgc >= a.totalCtus) break;
     const uint8_t* valid = smem + C::VALID_OFF + c * 256;
     uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
-    for (int i = tid; i < C::PUS * kNumModes; i += kThreads) {
-      const bool v = valid[i / kNumModes] != 0;
-      if (C::ACC_STAGED) o[i] = v ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
-      else if (!v) o[i] = 0xffffffffu;
+    if (LOG2N == 2) {
+      const uint16_t* a16 = reinterpret_cast<const uint16_t*>(acc) + c * C::PUS * kNumModes;
+#pragma unroll 5
+      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? (uint32_t)a16[i] : 0xffffffffu;
+    } else {
+#pragma unroll 4
+      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
     }
   }
   if (warp == 0) tmem_dealloc(tmemBase, 256);
+  TC2_STAMP(3);
+#ifdef CUCD_TC2_TIMING
+  if (g_tc2Dbg && tid == 0) g_tc2Dbg[(size_t)blockIdx.x * 64 + 4] = LOG2N;
+#endif
 }
 
 // blocks of one launch: depth-major (as rmd_frame_kernel); a depth has ceil(totalCtus / CTUS) units

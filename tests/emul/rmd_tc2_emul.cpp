@@ -57,7 +57,7 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
   std::vector<unsigned char> smemStore(C::TOTAL + 256, 0xA5);
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smemStore.data()) + 127) & ~uintptr_t(127));
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
-  if (C::ACC_STAGED) for (int i = 0; i < C::CTUS * C::PUS * kNumModes; i++) acc[i] = 0;
+  if (LOG2N >= 4) for (int i = 0; i < C::CTUS * C::PUS * kNumModes; i++) acc[i] = 0;
   for (int i = 0; i < C::CTUS * 64; i++) reinterpret_cast<int*>(smem + C::DC_OFF)[i] = 0;
   // ---- prologue (tc2_prologue) ----
   int ctuXs[C::CTUS], ctuYs[C::CTUS];
@@ -115,9 +115,11 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
         for (int c = 0; c < 4; c++) { uint32_t s = 0; for (int k = 0; k < 16; k++) s = sad_acc(D[tid * 64 + c * 16 + k], HO[tid * 64 + c * 16 + k], s); q[c] = s; }
         const int cg = unit * C::CTUS + r.ctu;
         if (log2n == 2) {
-          if (ok[tid] && has) for (int c = 0; c < 4; c++) fs.out[((size_t)cg * kPusPerCtu + pu_offset_of_depth(4) + 4 * r.pu + c) * kNumModes + mode] = (q[c] + 1u) >> 1;
+          if (ok[tid] && has) for (int c = 0; c < 4; c++) reinterpret_cast<uint16_t*>(acc)[(r.ctu * C::PUS + 4 * r.pu + c) * kNumModes + mode] = (uint16_t)((q[c] + 1u) >> 1);
         } else if (ok[tid] && has) {
-          acc[(r.ctu * C::PUS + r.pu) * kNumModes + mode] += (q[0] + q[1] + q[2] + q[3] + 2u) >> 2;
+          uint32_t& dst = acc[(r.ctu * C::PUS + r.pu) * kNumModes + mode];
+          const uint32_t t = (q[0] + q[1] + q[2] + q[3] + 2u) >> 2;
+          if (LOG2N >= 4) dst += t; else dst = t;
         }
       }
     };
@@ -181,8 +183,8 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
     uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - log2n)) * kNumModes;
     for (int i = 0; i < C::PUS * kNumModes; i++) {
       const bool v = valid[i / kNumModes] != 0;
-      if (C::ACC_STAGED) o[i] = v ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
-      else if (!v) o[i] = 0xffffffffu;
+      if (LOG2N == 2) o[i] = v ? (uint32_t)reinterpret_cast<const uint16_t*>(acc)[c * C::PUS * kNumModes + i] : 0xffffffffu;
+      else o[i] = v ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
     }
   }
 }
