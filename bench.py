@@ -234,7 +234,7 @@ def run_ours(args, rank, world, local_rank):
     recs = [pseudo_recon(o, bd, t) for t, o in enumerate(orgs)]
 
     def pinned(shape, dtype):
-        tdt = {np.int16: torch.int16, np.int32: torch.int32, np.uint32: torch.int32, np.float64: torch.float64}[dtype]
+        tdt = {np.int16: torch.int16, np.int32: torch.int32, np.uint32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}[dtype]
         t = torch.empty(shape, dtype=tdt, pin_memory=True)
         pinned.keep.append(t)
         a = t.numpy()
@@ -245,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
     h_rec = [pinned((H, W), np.int16) for _ in range(P)]
     for p in range(P):
         h_org[p][:] = orgs[p]; h_rec[p][:] = recs[p]
-    h_outs = [eng.alloc_frame_out(True, pinned_alloc=pinned) for _ in range(P)]
+    h_outs = [eng.alloc_frame_out(True, pinned_alloc=pinned, packed=True) for _ in range(P)]
 
     # ---- device-resident buffers -------------------------------------------------------------------
     d_org = torch.zeros((P, H, pitch), dtype=torch.int16, device=dev)
@@ -302,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
     d2h = sum(int(a.nbytes) for o in h_outs for a in o.values())
 
     # spot-check that both paths produced the same tables (device-resident vs host-buffer)
-    same = bool(np.array_equal(d_cost[0].cpu().numpy().view(np.uint32), h_outs[0]["rmd_cost"]))
+    same = all(bool(np.array_equal(d_cost[p].cpu().numpy().view(np.uint32), cucd.unpack_costs(h_outs[p]["rmd_cost_packed"]))) for p in (0, P - 1))
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s, rmd_ms], dtype=torch.float64, device=dev)
@@ -319,10 +319,11 @@ def run_ours(args, rank, world, local_rank):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = ALGO_BYTES_PER_CTU * ctus_step_gpu / (rmd_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "rmd_frame_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "rmd_frame_tc2_kernel" if bd == 8 else "rmd_frame_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "launch_ms": rmd_ms, "launches_timed": n_timed, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CTU * ctus_step_gpu,
                 "peak_source": peak_src,
-                "note": "RMD is integer-ALU bound by construction (~140 int-op/B, SURVEY.md 8d): the HBM fraction is small; see profiles/ for pipe utilisation"}
+                "note": "RMD is compute bound by construction (~140 int-op/B, SURVEY.md 8d): predictions and Hadamard run on tcgen05 (kind::i8), "
+                        "the epilogues on the integer ALU; the HBM fraction is small; see profiles/ for pipe utilisation"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -333,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "CTU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host)"},
+                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host; cost tables in the packed CTU format of include/cucudecide.h)"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "paths_agree": same}
         print(json.dumps(line))

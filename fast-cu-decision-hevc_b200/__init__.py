@@ -15,9 +15,11 @@ from .binding import (  # noqa: F401
     Engine,
     LIB_PATH,
     NUM_MODES,
+    PACKED_CTU_BYTES,
     PUS_PER_CTU,
     declared_symbols,
     exp_satd_tc,
     load_library,
     tcm_fit,
+    unpack_costs,
 )

@@ -13,6 +13,21 @@ import numpy as np
 
 NUM_MODES = 35
 PUS_PER_CTU = 341
+PACKED_WIDE_PUS = 21                     # CUCD_PACKED_WIDE_PUS: PUs 0..20 stay uint32
+PACKED_CTU_BYTES = PACKED_WIDE_PUS * 35 * 4 + (PUS_PER_CTU - PACKED_WIDE_PUS) * 35 * 2   # CUCD_PACKED_CTU_BYTES
+
+
+def unpack_costs(packed):
+    """(nCtu, PACKED_CTU_BYTES) uint8 packed CTU tables (cucd_frame_out.rmd_cost_packed) -> (nCtu, 341, 35) uint32,
+    the host-side equivalent of cucd_packed_cost()."""
+    packed = np.ascontiguousarray(packed, np.uint8).reshape(-1, PACKED_CTU_BYTES)
+    n = packed.shape[0]
+    out = np.empty((n, PUS_PER_CTU, NUM_MODES), np.uint32)
+    wide = PACKED_WIDE_PUS * NUM_MODES * 4
+    out[:, :PACKED_WIDE_PUS] = packed[:, :wide].copy().view(np.uint32).reshape(n, PACKED_WIDE_PUS, NUM_MODES)
+    narrow = packed[:, wide:].copy().view(np.uint16).reshape(n, PUS_PER_CTU - PACKED_WIDE_PUS, NUM_MODES)
+    out[:, PACKED_WIDE_PUS:] = np.where(narrow == 0xFFFF, np.uint32(0xFFFFFFFF), narrow.astype(np.uint32))
+    return out
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcucudecide.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "cucudecide.h")
@@ -34,7 +49,7 @@ class _Config(C.Structure):
 
 class _FrameOut(C.Structure):
     _fields_ = [("obf", _i16p), ("outlier", _i16p), ("yc", _f64p), ("num_obf", _i32p * 4), ("n_outlier", _i32p * 4),
-                ("ctu_src_had", _i32p), ("rmd_cost", _u32p)]
+                ("ctu_src_had", _i32p), ("rmd_cost", _u32p), ("rmd_cost_packed", C.POINTER(C.c_uint8))]
 
 
 class _DevOut(C.Structure):
@@ -178,8 +193,9 @@ class Engine:
         return self.height // s, self.width // s
 
     # ---- S1/S4 (+ replay S2) --------------------------------------------------------------------
-    def alloc_frame_out(self, want_rmd=True, pinned_alloc=None):
-        """numpy output buffers for one picture (pinned_alloc(shape, dtype) may supply pinned memory)."""
+    def alloc_frame_out(self, want_rmd=True, pinned_alloc=None, packed=False):
+        """numpy output buffers for one picture (pinned_alloc(shape, dtype) may supply pinned memory).
+        packed=True asks for the cost tables in the packed CTU format (rmd_cost_packed) instead of uint32."""
         mk = pinned_alloc or (lambda shape, dtype: np.zeros(shape, dtype))
         W, H = self.width, self.height
         out = {"obf": mk((H // 4, W // 4), np.int16), "outlier": mk((H, W), np.int16), "yc": mk((16,), np.float64),
@@ -187,7 +203,9 @@ class Engine:
         for d in range(4):
             out[f"num_obf{d}"] = mk(self.cu_grid(d), np.int32)
             out[f"n_outlier{d}"] = mk(self.cu_grid(d), np.int32)
-        if want_rmd:
+        if want_rmd and packed:
+            out["rmd_cost_packed"] = mk((self.ctus_per_pic, PACKED_CTU_BYTES), np.uint8)
+        elif want_rmd:
             out["rmd_cost"] = mk((self.ctus_per_pic, PUS_PER_CTU, NUM_MODES), np.uint32)
         return out
 
@@ -206,6 +224,7 @@ class Engine:
             fo.n_outlier[d] = ptr(f"n_outlier{d}", _i32p)
         fo.ctu_src_had = ptr("ctu_src_had", _i32p)
         fo.rmd_cost = ptr("rmd_cost", _u32p)
+        fo.rmd_cost_packed = ptr("rmd_cost_packed", C.POINTER(C.c_uint8))
         return fo
 
     def frames(self, orgs, recs=None, outs=None, want_rmd=True):

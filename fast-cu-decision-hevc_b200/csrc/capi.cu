@@ -65,6 +65,7 @@ struct cucd_handle {
   // frame path
   DevBuf<int16_t> dOrg, dRec, dObf, dOutlier;
   DevBuf<uint32_t> dCost, dHist;
+  DevBuf<uint8_t> dCostPacked;    // CUCD_PACKED_CTU_BYTES per CTU (cucd_frame_out.rmd_cost_packed)
   DevBuf<int8_t> dHadamard;       // +-(H8 x H8), +-(blockdiag H4 x H4) operands of the tensor-core SATD
   DevBuf<uint8_t> dTc2Tables;     // interpolation-weight operands of the tensor-core prediction (rmd_tc2.cuh)
   int useTensor = 0;              // 8-bit content (cucd_set_rmd_path): 1 = predictions + Hadamard on tcgen05, 2 = Hadamard only, 0 = integer ALU
@@ -139,6 +140,12 @@ extern "C" {
 
 int cucd_abi_version(void) { return CUCD_ABI_VERSION; }
 
+uint32_t cucd_packed_cost(const uint8_t* ctu_table, int pu, int mode) {
+  if (pu < CUCD_PACKED_WIDE_PUS) return reinterpret_cast<const uint32_t*>(ctu_table)[pu * 35 + mode];
+  const uint16_t v = reinterpret_cast<const uint16_t*>(ctu_table + CUCD_PACKED_WIDE_PUS * 35 * 4)[(pu - CUCD_PACKED_WIDE_PUS) * 35 + mode];
+  return v == 0xFFFFu ? 0xFFFFFFFFu : (uint32_t)v;
+}
+
 const char* cucd_last_error(const cucd_handle* h) { return h ? h->err.c_str() : g_createError.c_str(); }
 long long cucd_launch_count(const cucd_handle* h) { return h ? h->launchTotal + h->launches : 0; }
 
@@ -175,6 +182,7 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   for (int i = 0; i < cucd_handle::kTimeRing; i++) ok = ok && cudaEventCreate(&h->evRmd0[i]) == cudaSuccess && cudaEventCreate(&h->evRmd1[i]) == cudaSuccess;
   ok = ok && h->dOrg.reserve(P * h->planeSamples) == cudaSuccess && h->dRec.reserve(P * h->planeSamples) == cudaSuccess;
   ok = ok && h->dCost.reserve(P * h->ctusPerPic * kPusPerCtu * kNumModes) == cudaSuccess;
+  ok = ok && h->dCostPacked.reserve(P * h->ctusPerPic * (size_t)CUCD_PACKED_CTU_BYTES) == cudaSuccess;
   ok = ok && h->dHist.reserve(P * kHistFreqs * kHistBins) == cudaSuccess && h->dThr.reserve(P * kHistFreqs) == cudaSuccess;
   ok = ok && h->dObf.reserve(P * (size_t)(cfg->width / 4) * (cfg->height / 4)) == cudaSuccess;
   ok = ok && h->dOutlier.reserve(P * (size_t)cfg->width * cfg->height) == cudaSuccess;
@@ -205,7 +213,7 @@ int cucd_destroy(cucd_handle* h) {
   if (!h) return CUCD_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  h->dOrg.release(); h->dRec.release(); h->dObf.release(); h->dOutlier.release(); h->dCost.release(); h->dHist.release(); h->dThr.release();
+  h->dOrg.release(); h->dRec.release(); h->dObf.release(); h->dOutlier.release(); h->dCost.release(); h->dCostPacked.release(); h->dHist.release(); h->dThr.release();
   for (int d = 0; d < 4; d++) { h->dNum[d].release(); h->dSum[d].release(); }
   h->dCtuHad.release(); h->hHist.release(); h->hThr.release(); h->dHadamard.release(); h->dTc2Tables.release();
   h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
@@ -351,7 +359,8 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
                         cucd_frame_out* outs) {
   const int W = h->cfg.width, H = h->cfg.height;
   bool wantRmd = false;
-  if (recY) for (int p = 0; p < nPics; p++) wantRmd = wantRmd || outs[p].rmd_cost != nullptr;
+  bool wantPacked = false;
+  if (recY) for (int p = 0; p < nPics; p++) { wantRmd = wantRmd || outs[p].rmd_cost != nullptr || outs[p].rmd_cost_packed != nullptr; wantPacked = wantPacked || outs[p].rmd_cost_packed != nullptr; }
   // ---- upload ----------------------------------------------------------------------------------
   for (int p = 0; p < nPics; p++) {
     CK(cudaMemcpy2DAsync(h->dOrg.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, orgY[p], (size_t)strideY * 2, (size_t)W * 2, H,
@@ -381,8 +390,12 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
                                                h->dRec.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
                                                h->dCost.p + (size_t)first * perPic);
       CK(launch_rmd_auto(h, fs, n, st));
-      for (int p = first; p < first + n; p++)
+      const size_t perPicPacked = (size_t)h->ctusPerPic * CUCD_PACKED_CTU_BYTES;
+      if (wantPacked) CK(launch_pack_costs(h->dCost.p + (size_t)first * perPic, h->dCostPacked.p + (size_t)first * perPicPacked, n * h->ctusPerPic, st, &h->launches));
+      for (int p = first; p < first + n; p++) {
         if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (outs[p].rmd_cost_packed) CK(cudaMemcpyAsync(outs[p].rmd_cost_packed, h->dCostPacked.p + p * perPicPacked, perPicPacked, cudaMemcpyDeviceToHost, st));
+      }
     }
   }
   // ---- host: TCM fit per picture and frequency -------------------------------------------------
@@ -428,7 +441,7 @@ int cuCUDecide_frames(cucd_handle* h, int nPics, const int16_t* const* orgY, int
   if (recY && strideRec < h->cfg.width) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: bad reconstruction stride");
   for (int p = 0; p < nPics; p++) {
     if (!orgY[p] || (recY && !recY[p])) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: null plane");
-    if (outs[p].rmd_cost && !recY) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: rmd_cost wanted but no reconstruction plane given");
+    if ((outs[p].rmd_cost || outs[p].rmd_cost_packed) && !recY) return fail(h, CUCD_ERR_INVALID, "cuCUDecide_frames: rmd_cost wanted but no reconstruction plane given");
   }
   CK(cudaSetDevice(h->cfg.device));
   for (int first = 0; first < nPics; first += h->cfg.max_pictures) {

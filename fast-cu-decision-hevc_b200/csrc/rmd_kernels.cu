@@ -7,6 +7,7 @@
 // Replaces, per PU, the reference loop TEncSearch.cpp:2327-2361 (initAdiPatternChType ->
 // predIntraAng x35 -> xGetHADs).
 #include <cuda_runtime.h>
+#include <algorithm>
 #include "rmd_chunk.cuh"
 #include "satd_tc.cuh"
 #include "kernels.h"
@@ -407,6 +408,27 @@ cudaError_t launch_rmd_frames_tc(const FrameSource& fs, int nPics, int strong, c
     configured = true;
   }
   rmd_frame_tc_kernel<<<chunks * 5, kRmdThreads, kFrameTcSmem, st>>>(fs, strong, reinterpret_cast<const uint4*>(hadamard));
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+// cost tables in the packed host format: PUs 0..20 stay uint32, PUs 21..340 (8x8, 4x4) become uint16
+constexpr int kPackWide = 21, kPackCtuBytes = kPackWide * kNumModes * 4 + (kPusPerCtu - kPackWide) * kNumModes * 2;
+__global__ void pack_costs_kernel(const uint32_t* __restrict__ cost, uint8_t* __restrict__ packed, const int nCtus) {
+  const int perCtu = kPusPerCtu * kNumModes;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)nCtus * perCtu; i += (long long)gridDim.x * blockDim.x) {
+    const int ctu = (int)(i / perCtu), e = (int)(i - (long long)ctu * perCtu);
+    const uint32_t c = cost[i];
+    uint8_t* base = packed + (size_t)ctu * kPackCtuBytes;
+    if (e < kPackWide * kNumModes) reinterpret_cast<uint32_t*>(base)[e] = c;
+    else reinterpret_cast<uint16_t*>(base + kPackWide * kNumModes * 4)[e - kPackWide * kNumModes] = c == 0xffffffffu ? (uint16_t)0xffffu : (uint16_t)c;
+  }
+}
+cudaError_t launch_pack_costs(const uint32_t* cost, uint8_t* packed, int nCtus, cudaStream_t st, int* launches) {
+  if (nCtus <= 0) return cudaSuccess;
+  const long long n = (long long)nCtus * kPusPerCtu * kNumModes;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+  pack_costs_kernel<<<blocks, 256, 0, st>>>(cost, packed, nCtus);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

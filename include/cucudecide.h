@@ -32,7 +32,7 @@ extern "C" {
 
 #define CUCD_NUM_INTRA_MODES 35
 #define CUCD_PUS_PER_CTU 341
-#define CUCD_ABI_VERSION 1
+#define CUCD_ABI_VERSION 2
 
 typedef enum {
   CUCD_OK = 0,
@@ -80,7 +80,18 @@ typedef struct {
   int32_t* n_outlier[4];   /* same shape: N_Outlier                                                       */
   int32_t* ctu_src_had;    /* one per CTU: updateCtuDataISlice's iSumHad                                  */
   uint32_t* rmd_cost;      /* nCtu*341*35: SATD tables; 0xFFFFFFFF for PUs not inside the picture         */
+  uint8_t* rmd_cost_packed;/* nCtu*CUCD_PACKED_CTU_BYTES: the same tables, narrowest exact type (see below)*/
 } cucd_frame_out;
+
+/* Packed cost table of one CTU.  The numbers are those of rmd_cost; PUs of 8x8 and 4x4 are stored as uint16
+ * (exact: an 8x8 SATD is <= 32 736 and a 4x4 SATD <= 8 184 for bit depths <= 10), which nearly halves the
+ * device-to-host traffic of cuCUDecide_frames - the part of the call that is PCIe bound:
+ *   bytes [0, 2940)      uint32[21][35]   PUs 0..20   (64x64, 4 x 32x32, 16 x 16x16)
+ *   bytes [2940, 25340)  uint16[320][35]  PUs 21..340 (64 x 8x8, 256 x 4x4); 0xFFFF = PU not inside the picture */
+#define CUCD_PACKED_WIDE_PUS 21
+#define CUCD_PACKED_CTU_BYTES (CUCD_PACKED_WIDE_PUS * 35 * 4 + (CUCD_PUS_PER_CTU - CUCD_PACKED_WIDE_PUS) * 35 * 2)
+/* cost of (pu, mode) from one packed CTU table (host-side helper; widen 0xFFFF to 0xFFFFFFFF) */
+uint32_t cucd_packed_cost(const uint8_t* ctu_table, int pu, int mode);
 
 int cuCUDecide_frame(cucd_handle* h, const int16_t* orgY, int strideY, const int16_t* recY, int strideRec, int poc,
                      cucd_frame_out* out);

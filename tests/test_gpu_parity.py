@@ -261,3 +261,20 @@ def test_tensor_core_path_extreme_values(cucd, oracle):
                 eng.set_rmd_path(path)
                 got = eng.frame(org, rec)["rmd_cost"]
             assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8)), path
+
+
+# ---- packed cost tables (cucd_frame_out.rmd_cost_packed) carry the same numbers -------------------------------
+@pytest.mark.parametrize("bd,W,H", [(8, 200, 136), (10, 136, 72)])
+def test_packed_cost_tables_equal_wide_tables(cucd, oracle, bd, W, H):
+    org = textured_plane(W, H, bd, seed=11)
+    rec = pseudo_recon(org, bd)
+    with cucd.Engine(W, H, bit_depth=bd, max_pictures=2) as eng:
+        wide = eng.frames([org, rec], [rec, org])
+        outs = [eng.alloc_frame_out(True, packed=True) for _ in range(2)]
+        eng.frames([org, rec], [rec, org], outs)
+    want = oracle_rmd_frame(oracle, org, rec, bd)
+    for k in range(2):
+        got = cucd.unpack_costs(outs[k]["rmd_cost_packed"])
+        assert np.array_equal(got, wide[k]["rmd_cost"])
+    assert np.array_equal(cucd.unpack_costs(outs[0]["rmd_cost_packed"]), want)
+    assert (want == 0xFFFFFFFF).any()          # partial CTUs: the 0xFFFF marker is exercised
