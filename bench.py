@@ -319,8 +319,12 @@ def run_ours(args, rank, world, local_rank):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = ALGO_BYTES_PER_CTU * ctus_step_gpu / (rmd_ms * 1e-3) / 1e9
+    traffic = None            # DRAM bytes per launch, scaled from the committed ncu --set full capture of the same kernel
+    tpath = os.path.join(ROOT, "profiles", "r01_rmd_traffic.json")
+    if bd == 8 and os.path.exists(tpath):
+        traffic = float(json.load(open(tpath))["dram_bytes_per_ctu"]) * ctus_step_gpu
     roofline = {"bound": "hbm", "kernel": "rmd_frame_tc2_kernel" if bd == 8 else "rmd_frame_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "launch_ms": rmd_ms, "launches_timed": n_timed, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CTU * ctus_step_gpu,
+                "traffic": traffic, "launch_ms": rmd_ms, "launches_timed": n_timed, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CTU * ctus_step_gpu,
                 "peak_source": peak_src,
                 "note": "RMD is compute bound by construction (~140 int-op/B, SURVEY.md 8d): predictions and Hadamard run on tcgen05 (kind::i8), "
                         "the epilogues on the integer ALU; the HBM fraction is small; see profiles/ for pipe utilisation"}
