@@ -223,6 +223,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     W, H, bd, P = args.width, args.height, args.bit_depth, args.pics
