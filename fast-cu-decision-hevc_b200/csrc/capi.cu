@@ -4,6 +4,7 @@
 // every entry point either runs the CUDA kernels or fails.
 #include <cuda_runtime.h>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -53,8 +54,10 @@ struct cucd_handle {
   cucd_config cfg;
   int ctusPerRow = 0, ctusPerCol = 0, ctusPerPic = 0, pitch = 0;
   size_t planeSamples = 0;
-  cudaStream_t sMain = nullptr, sFeat = nullptr, sGrp[2] = {nullptr, nullptr};
-  cudaEvent_t evUp = nullptr, evHist = nullptr;
+  cudaStream_t sMain = nullptr, sFeat = nullptr, sGrp[2] = {nullptr, nullptr};   // sGrp: [0] RMD compute, [1] cost-table download
+  cudaStream_t sUp = nullptr;                     // picture upload
+  static constexpr int kGroups = 8;               // sub-groups of pictures one cuCUDecide_frames call is pipelined over
+  cudaEvent_t evUp = nullptr, evHist = nullptr, evUpG[kGroups] = {}, evRmdG[kGroups] = {};
   static constexpr int kTimeRing = 64;
   cudaEvent_t evRmd0[kTimeRing] = {}, evRmd1[kTimeRing] = {};
   long long rmdCalls = 0;
@@ -173,12 +176,17 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   h->hostThreads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   for (int d = 0; d < 4; d++) h->cuCount[d] = (size_t)(cfg->width / (64 >> d)) * (cfg->height / (64 >> d));
   const size_t P = (size_t)cfg->max_pictures;
+  int prioLow = 0, prioHigh = 0;
+  cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh);
   bool ok = cudaStreamCreateWithFlags(&h->sMain, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&h->sFeat, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&h->sFeat, cudaStreamNonBlocking, prioHigh) == cudaSuccess &&   // small feature kernels go ahead of queued RMD blocks
             cudaStreamCreateWithFlags(&h->sGrp[0], cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->sGrp[1], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->sUp, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->evUp, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->evHist, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < cucd_handle::kGroups; i++)
+    ok = ok && cudaEventCreateWithFlags(&h->evUpG[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->evRmdG[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < cucd_handle::kTimeRing; i++) ok = ok && cudaEventCreate(&h->evRmd0[i]) == cudaSuccess && cudaEventCreate(&h->evRmd1[i]) == cudaSuccess;
   ok = ok && h->dOrg.reserve(P * h->planeSamples) == cudaSuccess && h->dRec.reserve(P * h->planeSamples) == cudaSuccess;
   ok = ok && h->dCost.reserve(P * h->ctusPerPic * kPusPerCtu * kNumModes) == cudaSuccess;
@@ -220,6 +228,8 @@ int cucd_destroy(cucd_handle* h) {
   for (auto& r : h->refs) r.buf.release();
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
   for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
+  for (int i = 0; i < cucd_handle::kGroups; i++) { if (h->evUpG[i]) cudaEventDestroy(h->evUpG[i]); if (h->evRmdG[i]) cudaEventDestroy(h->evRmdG[i]); }
+  if (h->sUp) cudaStreamDestroy(h->sUp);
   if (h->evUp) cudaEventDestroy(h->evUp);
   if (h->evHist) cudaEventDestroy(h->evHist);
   for (int i = 0; i < 2; i++) if (h->sGrp[i]) cudaStreamDestroy(h->sGrp[i]);
@@ -358,48 +368,59 @@ int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_or
 static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, int strideY, const int16_t* const* recY, int strideRec,
                         cucd_frame_out* outs) {
   const int W = h->cfg.width, H = h->cfg.height;
+  // CUCD_TRACE=1: host-side timeline of the call on stderr (development aid)
+  static const bool trace = getenv("CUCD_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (trace) fprintf(stderr, "[cucd] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
   bool wantRmd = false;
   bool wantPacked = false;
   if (recY) for (int p = 0; p < nPics; p++) { wantRmd = wantRmd || outs[p].rmd_cost != nullptr || outs[p].rmd_cost_packed != nullptr; wantPacked = wantPacked || outs[p].rmd_cost_packed != nullptr; }
-  // ---- upload ----------------------------------------------------------------------------------
-  for (int p = 0; p < nPics; p++) {
-    CK(cudaMemcpy2DAsync(h->dOrg.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, orgY[p], (size_t)strideY * 2, (size_t)W * 2, H,
-                         cudaMemcpyHostToDevice, h->sFeat));
-  }
-  CK(cudaEventRecord(h->evUp, h->sFeat));
-  // ---- feature pass 1 on sFeat -----------------------------------------------------------------
-  const FeaturePlanes fp = make_feature_planes(h, h->dOrg.p, (long long)h->planeSamples, h->pitch);
-  CK(launch_feature_hist(fp, nPics, h->dHist.p, h->sFeat, &h->launches));
-  CK(cudaMemcpyAsync(h->hHist.p, h->dHist.p, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sFeat));
-  CK(cudaEventRecord(h->evHist, h->sFeat));
-  // ---- RMD replay, pipelined in sub-groups of pictures over two streams: the device-to-host copy of a
-  //      group's cost tables (the bulk of the PCIe traffic) overlaps the kernel of the next group, and all
-  //      of it overlaps the host TCM fit ---------------------------------------------------------------
-  if (wantRmd) {
-    const size_t perPic = (size_t)h->ctusPerPic * kPusPerCtu * kNumModes;
-    const int grp = std::max(1, (nPics + 3) / 4);
-    for (int s = 0; s < 2; s++) CK(cudaStreamWaitEvent(h->sGrp[s], h->evUp, 0));
-    int gi = 0;
-    for (int first = 0; first < nPics; first += grp, gi++) {
-      cudaStream_t st = h->sGrp[gi & 1];
-      const int n = std::min(grp, nPics - first);
-      for (int p = first; p < first + n; p++)
+  // ---- three-stage pipeline over sub-groups of pictures: upload (sUp) -> RMD + pack (sGrp[0]) -> cost-table
+  //      download (sGrp[1]); PCIe is full duplex, so uploads, kernels and the (dominant) downloads overlap.
+  //      The feature path (sFeat) needs every source plane and runs beside it. ---------------------------------
+  const size_t perPic = (size_t)h->ctusPerPic * kPusPerCtu * kNumModes;
+  const size_t perPicPacked = (size_t)h->ctusPerPic * CUCD_PACKED_CTU_BYTES;
+  const int grp = std::max(1, (nPics + 3) / 4);
+  int gi = 0;
+  for (int first = 0; first < nPics; first += grp, gi++) {
+    const int n = std::min(grp, nPics - first);
+    for (int p = first; p < first + n; p++) {
+      CK(cudaMemcpy2DAsync(h->dOrg.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, orgY[p], (size_t)strideY * 2, (size_t)W * 2, H,
+                           cudaMemcpyHostToDevice, h->sUp));
+      if (wantRmd)
         CK(cudaMemcpy2DAsync(h->dRec.p + (size_t)p * h->planeSamples, (size_t)h->pitch * 2, recY[p], (size_t)strideRec * 2, (size_t)W * 2, H,
-                             cudaMemcpyHostToDevice, st));
-      const FrameSource fs = make_frame_source(h, h->dOrg.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
-                                               h->dRec.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
-                                               h->dCost.p + (size_t)first * perPic);
-      CK(launch_rmd_auto(h, fs, n, st));
-      const size_t perPicPacked = (size_t)h->ctusPerPic * CUCD_PACKED_CTU_BYTES;
-      if (wantPacked) CK(launch_pack_costs(h->dCost.p + (size_t)first * perPic, h->dCostPacked.p + (size_t)first * perPicPacked, n * h->ctusPerPic, st, &h->launches));
-      for (int p = first; p < first + n; p++) {
-        if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        if (outs[p].rmd_cost_packed) CK(cudaMemcpyAsync(outs[p].rmd_cost_packed, h->dCostPacked.p + p * perPicPacked, perPicPacked, cudaMemcpyDeviceToHost, st));
-      }
+                             cudaMemcpyHostToDevice, h->sUp));
+    }
+    CK(cudaEventRecord(h->evUpG[gi], h->sUp));
+    if (!wantRmd) continue;
+    CK(cudaStreamWaitEvent(h->sGrp[0], h->evUpG[gi], 0));
+    const FrameSource fs = make_frame_source(h, h->dOrg.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
+                                             h->dRec.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
+                                             h->dCost.p + (size_t)first * perPic);
+    CK(launch_rmd_auto(h, fs, n, h->sGrp[0]));
+    if (wantPacked) CK(launch_pack_costs(h->dCost.p + (size_t)first * perPic, h->dCostPacked.p + (size_t)first * perPicPacked, n * h->ctusPerPic, h->sGrp[0], &h->launches));
+    CK(cudaEventRecord(h->evRmdG[gi], h->sGrp[0]));
+    CK(cudaStreamWaitEvent(h->sGrp[1], h->evRmdG[gi], 0));
+    for (int p = first; p < first + n; p++) {
+      if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sGrp[1]));
+      if (outs[p].rmd_cost_packed) CK(cudaMemcpyAsync(outs[p].rmd_cost_packed, h->dCostPacked.p + p * perPicPacked, perPicPacked, cudaMemcpyDeviceToHost, h->sGrp[1]));
     }
   }
+  CK(cudaEventRecord(h->evUp, h->sUp));
+  // ---- feature pass 1 on sFeat -----------------------------------------------------------------
+  CK(cudaStreamWaitEvent(h->sFeat, h->evUp, 0));
+  const FeaturePlanes fp = make_feature_planes(h, h->dOrg.p, (long long)h->planeSamples, h->pitch);
+  CK(launch_feature_hist(fp, nPics, h->dHist.p, h->sFeat, &h->launches));
+  // histograms to the host by an SM copy (pinned memory is device-visible under UVA): a cudaMemcpyAsync would wait in the
+  // copy-engine queue behind the cost-table downloads and delay the TCM fit, i.e. the whole feature path
+  CK(launch_copy_words(h->dHist.p, h->hHist.p, (size_t)nPics * kHistFreqs * kHistBins, h->sFeat, &h->launches));
+  CK(cudaEventRecord(h->evHist, h->sFeat));
+  stamp("enqueued uploads + RMD");
   // ---- host: TCM fit per picture and frequency -------------------------------------------------
   CK(cudaEventSynchronize(h->evHist));
+  stamp("histograms on host");
   const int nBlocks = (W / 4) * (H / 4);
   std::vector<double> yc((size_t)nPics * 16, 0.0);
   parallel_for(nPics * 15, h->hostThreads, [&](int i) {
@@ -409,6 +430,7 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
     h->hThr.p[p * kHistFreqs + f] = (int32_t)(y * 8.0);
   });
   for (int p = 0; p < nPics; p++) { h->hThr.p[p * kHistFreqs] = 0; if (outs[p].yc) memcpy(outs[p].yc, &yc[(size_t)p * 16], 16 * sizeof(double)); }
+  stamp("TCM fits done");
   // ---- feature pass 2 on sFeat -----------------------------------------------------------------
   CK(cudaMemcpyAsync(h->dThr.p, h->hThr.p, (size_t)nPics * kHistFreqs * sizeof(int32_t), cudaMemcpyHostToDevice, h->sFeat));
   FeatureOut fo;
@@ -428,9 +450,13 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
     }
     if (o.ctu_src_had) CK(cudaMemcpyAsync(o.ctu_src_had, h->dCtuHad.p + (size_t)p * h->ctusPerPic, (size_t)h->ctusPerPic * 4, cudaMemcpyDeviceToHost, h->sFeat));
   }
+  stamp("enqueued pass 2 + copies");
   CK(cudaStreamSynchronize(h->sFeat));
+  stamp("feature stream done");
+  CK(cudaStreamSynchronize(h->sUp));
   CK(cudaStreamSynchronize(h->sGrp[0]));
   CK(cudaStreamSynchronize(h->sGrp[1]));
+  stamp("RMD streams done");
   flush_launches(h);
   return CUCD_OK;
 }

@@ -162,6 +162,16 @@ ctu_src_had_kernel(const FeaturePlanes fp, int32_t* __restrict__ ctuHad) {
   if (lane == 0) ctuHad[(size_t)pic * fp.ctusPerPic + ctu] = sum;
 }
 
+__global__ void copy_words_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+cudaError_t launch_copy_words(const uint32_t* src, uint32_t* dst, size_t nWords, cudaStream_t st, int* launches) {
+  if (nWords == 0) return cudaSuccess;
+  copy_words_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), nWords / 4);   // callers pass multiples of 4 words
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_feature_hist(const FeaturePlanes& fp, int nPics, uint32_t* hist, cudaStream_t st, int* launches) {
   cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;

@@ -29,6 +29,9 @@ struct FeaturePlanes {
 };
 // pass 1: 4x4 DCT of every block, histogram of |coeff/8| per AC frequency: hist[pic][16][4096]
 cudaError_t launch_feature_hist(const FeaturePlanes& fp, int nPics, uint32_t* hist, cudaStream_t st, int* launches);
+// plain device -> (UVA-mapped, pinned) host copy by the SMs: keeps small latency-critical results out of the copy-engine
+// queue, which cuCUDecide_frames fills with cost-table downloads
+cudaError_t launch_copy_words(const uint32_t* src, uint32_t* dst, size_t nWords, cudaStream_t st, int* launches);
 // pass 2: outlier thresholds thr[pic][16] (= Yc*8 as int) -> OBF plane, Outlier plane, per-depth CU sums
 struct FeatureOut {
   int16_t* obf; long long obfPicStride;           // [(H/4)][(W/4)] tight

@@ -281,20 +281,29 @@ CUCD_HD void patch_edge0_region4(const unsigned char* rec /*4 records*/, uint32_
 // planar and DC on the integer ALU (2 of the 35 modes), bytes out.  main/side: element 0 = corner.
 // ---------------------------------------------------------------------------------------------
 // TComPrediction.cpp:755-805 for the 8x8 tile at (u0, v0) of an N x N PU
+// Two pixels per integer: every (hor + vert + N) < 2^15, so pairs live in the 16-bit halves of a word and row /
+// column increments (possibly negative) are single integer adds of (stepHi << 16) + stepLo.
 CUCD_HD void planar_tile(int log2n, const unsigned char* T, const unsigned char* L, int u0, int v0, uint32_t* p) {
   const int N = 1 << log2n;
   const int tr = T[N + 1], bl = L[N + 1];
+  uint32_t V[4], VS[4];                              // vert term of columns (2j, 2j+1) at row v0, and its per-row step
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int t0 = T[u0 + 2 * j + 1], t1 = T[u0 + 2 * j + 2];
+    V[j] = (uint32_t)((N - 1 - v0) * t0 + (v0 + 1) * bl) + ((uint32_t)((N - 1 - v0) * t1 + (v0 + 1) * bl) << 16);
+    VS[j] = (uint32_t)(bl - t0) + ((uint32_t)(bl - t1) << 16);
+  }
+  const uint32_t mask = 0x00ff00ffu;
 #pragma unroll
   for (int v = 0; v < 8; v++) {
-    const int Y = v0 + v, l = L[Y + 1];
-    uint32_t w0 = 0, w1 = 0;
+    const int l = L[v0 + v + 1], hs = tr - l;
+    const int b = (N - 1 - u0) * l + (u0 + 1) * tr + N;      // hor term + rounding at column u0
+    uint32_t H = (uint32_t)b + ((uint32_t)(b + hs) << 16);
+    const uint32_t H2 = (uint32_t)(2 * hs) * 0x00010001u;
+    uint32_t q[4];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int X = u0 + u;
-      const int val = ((N - 1 - X) * l + (X + 1) * tr + (N - 1 - Y) * (int)T[X + 1] + (Y + 1) * bl + N) >> (log2n + 1);
-      if (u < 4) w0 |= (uint32_t)val << (8 * u); else w1 |= (uint32_t)val << (8 * (u - 4));
-    }
-    p[2 * v] = w0; p[2 * v + 1] = w1;
+    for (int j = 0; j < 4; j++) { q[j] = ((H + V[j]) >> (log2n + 1)) & mask; H += H2; V[j] += VS[j]; }
+    p[2 * v] = bperm(q[0], q[1], 0x6420); p[2 * v + 1] = bperm(q[2], q[3], 0x6420);
   }
 }
 // TComPrediction.cpp:183-222, 818-841
@@ -448,6 +457,22 @@ CUCD_HD void build_unfiltered(int tid, int ctu, int W, int H, int ctuX, int ctuY
   const int firstAvail = a.lenL > 0 ? colL[a.lenL * C::TILE_PITCH] : (a.availC ? rowT[0] : (a.lenT > 0 ? rowT[1] : 128));
   const int cval = a.availC ? rowT[0] : (a.lenL > 0 ? colL[C::TILE_PITCH] : firstAvail);
   const int tailT = a.lenT > 0 ? rowT[a.lenT] : cval;
+  if (LOG2N == 2) {
+    // one thread per PU: both 16-byte records are assembled in registers and leave as two 128-bit stores
+    uint32_t tv[9], lv[9];
+    tv[0] = lv[0] = (uint32_t)cval;
+#pragma unroll
+    for (int k = 1; k <= 8; k++) {
+      tv[k] = (uint32_t)(k <= a.lenT ? (int)rowT[k] : tailT);
+      lv[k] = (uint32_t)(k <= a.lenL ? (int)colL[k * C::TILE_PITCH] : firstAvail);
+    }
+    auto w4 = [](uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) { return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24); };
+    uint32_t* r0 = reinterpret_cast<uint32_t*>(store + rec_off(ctu, 0, p));       // main = T, side = L
+    uint32_t* r1 = reinterpret_cast<uint32_t*>(store + rec_off(ctu, 1, p));       // main = L, side = T
+    r0[0] = w4(tv[0], tv[1], tv[2], tv[3]); r0[1] = w4(tv[4], tv[5], tv[6], tv[7]); r0[2] = w4(tv[8], lv[1], lv[2], lv[3]); r0[3] = w4(lv[4], lv[5], 0u, 1u);
+    r1[0] = w4(lv[0], lv[1], lv[2], lv[3]); r1[1] = w4(lv[4], lv[5], lv[6], lv[7]); r1[2] = w4(lv[8], tv[1], tv[2], tv[3]); r1[3] = w4(tv[4], tv[5], 0u, 1u);
+    return;
+  }
   if (sub == 0) {
     put_ref<LOG2N>(store, ctu, p, 0, 0, cval); put_ref<LOG2N>(store, ctu, p, 1, 0, cval);
     if (LOG2N == 2) { store[rec_off(ctu, 0, p) + 14] = 0; store[rec_off(ctu, 0, p) + 15] = 1; store[rec_off(ctu, 1, p) + 14] = 0; store[rec_off(ctu, 1, p) + 15] = 1; }

@@ -26,8 +26,11 @@ using namespace tc2;
 #ifdef CUCD_TC2_TIMING
 __device__ long long* g_tc2Dbg = nullptr;
 #define TC2_STAMP(i) do { if (g_tc2Dbg && threadIdx.x == 0) g_tc2Dbg[(size_t)blockIdx.x * 64 + (i)] = clock64(); } while (0)
+// finer stamps inside the rounds am = 4 (slots 30..) and am = -4 (slots 40..) of the first pass
+#define TC2_FINE(i) do { if (g_tc2Dbg && threadIdx.x == 0 && pass == 0 && (am == 4 || am == -4)) g_tc2Dbg[(size_t)blockIdx.x * 64 + (am == 4 ? 30 : 40) + (i)] = clock64(); } while (0)
 #else
 #define TC2_STAMP(i) do { } while (0)
+#define TC2_FINE(i) do { } while (0)
 #endif
 
 namespace {
@@ -312,7 +315,9 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   for (int am = 8; am >= -8; --am) {
     const int buf = (8 - am) & 1;
     const int angleNext2 = am > -7 ? angle_of_am(am - 2) : 0;
+    TC2_FINE(0);
     wait_mma1();
+    TC2_FINE(1);
     // epilogue 1: byte 1 of every accumulator is the predicted pixel
     {
       uint32_t v[32];
@@ -327,16 +332,23 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
       else if (r.u0 == 0) patch_edge0_tile(unfMain, unfSide, r.v0, p);
     }
     tmem_st16(tA2 + laneOff, p);
+    TC2_FINE(2);
     if (LOG2N != 2 && am > -8 && angleNext < 0)     // the gathers of round am are done (barrier of its MMA 1)
       build_ext_group<LOG2N>(rowTid, grp, angleNext, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
+    TC2_FINE(3);
     issue_mma2();
+    TC2_FINE(4);
     if (am > -8) {
       stage(am - 1, angleNext, buf ^ 1);
       if (am > -7) prefetch_b1(am - 2, angleNext2);
     }
+    TC2_FINE(5);
     wait_mma2();
+    TC2_FINE(6);
     if (am > -8) issue_mma1(buf ^ 1);
+    TC2_FINE(7);
     cost_out(r.o ? 10 - am : 26 + am, !(r.o && am == -8));
+    TC2_FINE(8);
     if (pass == 0) TC2_STAMP(9 + 8 - am);
     angle = angleNext; angleNext = angleNext2;
   }
@@ -382,9 +394,15 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
     const uint8_t* valid = smem + C::VALID_OFF + c * 256;
     uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
     if (LOG2N == 2) {
+      // four uint16 costs per trip (a quad may straddle two PUs: validity per element); the output is only 4-byte aligned
       const uint16_t* a16 = reinterpret_cast<const uint16_t*>(acc) + c * C::PUS * kNumModes;
-#pragma unroll 5
-      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? (uint32_t)a16[i] : 0xffffffffu;
+#pragma unroll 4
+      for (int i4 = tid; i4 < C::PUS * kNumModes / 4; i4 += kThreads) {
+        const uint2 w = reinterpret_cast<const uint2*>(a16)[i4];
+        const int i = 4 * i4;
+        o[i] = valid[i / kNumModes] ? (w.x & 0xffffu) : 0xffffffffu;           o[i + 1] = valid[(i + 1) / kNumModes] ? (w.x >> 16) : 0xffffffffu;
+        o[i + 2] = valid[(i + 2) / kNumModes] ? (w.y & 0xffffu) : 0xffffffffu; o[i + 3] = valid[(i + 3) / kNumModes] ? (w.y >> 16) : 0xffffffffu;
+      }
     } else {
 #pragma unroll 4
       for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;

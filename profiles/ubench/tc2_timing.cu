@@ -59,6 +59,12 @@ int main(int argc, char** argv) {
     printf("N=%2d: %5d CTAs  prologue %7.0f  passes %8.0f (first-pass setup %6.0f)  copy-out %6.0f  clk;  rounds am=8..-8:", 1 << l, n, pro / n, pass / n, setup / n, tail / n);
     for (int r = 0; r < 17; r++) printf(" %4.0f", rounds[r] / n);
     printf("\n");
+    for (int base = 30; base <= 40; base += 10) {
+      double seg[8] = {0};
+      for (int b = 0; b < blocks; b++) { const long long* t = &d[(size_t)b * 64]; if (t[4] != l) continue; for (int k = 0; k < 8; k++) seg[k] += t[base + k + 1] - t[base + k]; }
+      printf("      round am=%2d: wait MMA1 %4.0f | epilogue 1 + st %4.0f | projected refs %4.0f | st wait + barrier + issue MMA2 %4.0f | stage %4.0f | wait MMA2 %4.0f | barrier + issue MMA1 %4.0f | epilogue 2 %4.0f\n",
+             base == 30 ? 4 : -4, seg[0] / n, seg[1] / n, seg[2] / n, seg[3] / n, seg[4] / n, seg[5] / n, seg[6] / n, seg[7] / n);
+    }
   }
   return 0;
 }
