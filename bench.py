@@ -290,15 +290,37 @@ def run_ours(args, rank, world, local_rank):
     clk = clocks.stop()
 
     # ---- end to end through the host-buffer ABI -------------------------------------------------------
-    for _ in range(max(1, min(args.warmup, 2))):
-        eng.frames(h_org, h_rec, h_outs)
-    barrier()
+    # One encoder instance = one handle, calls are synchronous (HM is single-threaded).  The deployment the
+    # reference implies is several encoder instances per GPU, so the headline e2e figure runs
+    # `--e2e-instances` handles from as many host threads (each with its own pinned buffers; ctypes drops the GIL
+    # inside the call): while one instance drains its cost tables over PCIe the other uploads and computes.
+    def e2e_run(engines, outs_list, steps):
+        import threading
+        def work(e, o):
+            for _ in range(steps):
+                e.frames(h_org, h_rec, o)
+        ths = [threading.Thread(target=work, args=(e, o)) for e, o in zip(engines, outs_list)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    n_inst = max(1, args.e2e_instances)
+    engines = [eng] + [cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P) for _ in range(n_inst - 1)]
+    outs_list = [h_outs] + [[e.alloc_frame_out(True, pinned_alloc=pinned, packed=True) for _ in range(P)] for e in engines[1:]]
     e2e_steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.frames(h_org, h_rec, h_outs)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_run(engines[:1], outs_list[:1], max(1, min(args.warmup, 2)))
+    barrier()
+    e2e_single_s = e2e_run(engines[:1], outs_list[:1], e2e_steps)
+    if n_inst > 1:
+        e2e_run(engines, outs_list, 1)
+        barrier()
+        e2e_s = e2e_run(engines, outs_list, e2e_steps)
+    else:
+        e2e_s = e2e_single_s
     h2d = 2 * P * W * H * 2
     d2h = sum(int(a.nbytes) for o in h_outs for a in o.values())
 
@@ -306,13 +328,14 @@ def run_ours(args, rank, world, local_rank):
     same = all(bool(np.array_equal(d_cost[p].cpu().numpy().view(np.uint32), cucd.unpack_costs(h_outs[p]["rmd_cost_packed"]))) for p in (0, P - 1))
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s, rmd_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, rmd_ms, e2e_single_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, rmd_ms = [float(v) for v in t.tolist()]
+    dev_ms, e2e_s, rmd_ms, e2e_single_s = [float(v) for v in t.tolist()]
     ctus_step_gpu = P * nctu
     value = world * ctus_step_gpu * args.steps / (dev_ms * 1e-3)
-    e2e_value = world * ctus_step_gpu * e2e_steps / e2e_s
+    e2e_value = world * n_inst * ctus_step_gpu * e2e_steps / e2e_s
+    e2e_single = world * ctus_step_gpu * e2e_steps / e2e_single_s
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -339,7 +362,8 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "CTU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host; cost tables in the packed CTU format of include/cucudecide.h)"},
+                        "ms_per_step": 1e3 * e2e_s / (e2e_steps * n_inst), "instances_per_gpu": n_inst,
+                        "single_instance_value": e2e_single, "single_instance_ms_per_step": 1e3 * e2e_single_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host; cost tables in the packed CTU format of include/cucudecide.h)"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "paths_agree": same}
         print(json.dumps(line))
@@ -359,6 +383,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--bit-depth", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-instances", type=int, default=2, help="encoder instances (handles + host threads) per GPU in the e2e measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
