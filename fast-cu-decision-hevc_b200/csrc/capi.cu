@@ -515,7 +515,10 @@ int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, cons
     if (pus[l].empty()) continue;
     BatchSource bs;
     bs.org = h->bOrg.p; bs.border = h->bBorder.p; bs.pus = h->bPus.p + first[l]; bs.out = h->bOut.p; bs.count = (int)pus[l].size();
-    CK(launch_rmd_batch(l, bs, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
+    if (h->useTensor == 1)
+      CK(launch_rmd_batch_tc2(l, bs, h->cfg.strong_intra_smoothing, h->dTc2Tables.p, h->dTc2Tables.p + tc2::kWinTableBytes, h->dHadamard.p, h->sMain, &h->launches));
+    else
+      CK(launch_rmd_batch(l, bs, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
   }
   CK(cudaMemcpyAsync(sad, h->bOut.p, (size_t)nPU * kNumModes * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));   // `all` and the caller's buffers must outlive the copies

@@ -18,6 +18,9 @@ cudaError_t launch_hadamard_operands(int8_t* dst, cudaStream_t st);
 cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
                                   cudaStream_t st, int* launches);
 int rmd_tc2_smem_bytes();
+// the same tensor-core rounds for S2 batches of ONE PU size with caller-supplied borders (8-bit content)
+cudaError_t launch_rmd_batch_tc2(int log2n, const BatchSource& bs, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
+                                 cudaStream_t st, int* launches);
 // uint32 [nCtus][341][35] -> packed CTU tables of include/cucudecide.h (CUCD_PACKED_CTU_BYTES each)
 cudaError_t launch_pack_costs(const uint32_t* cost, uint8_t* packed, int nCtus, cudaStream_t st, int* launches);
 cudaError_t launch_rmd_batch(int log2n, const BatchSource& bs, int bitDepth, int strong, cudaStream_t st, int* launches);

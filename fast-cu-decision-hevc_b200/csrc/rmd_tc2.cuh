@@ -497,6 +497,43 @@ CUCD_HD void build_unfiltered(int tid, int ctu, int W, int H, int ctuX, int ctuY
 #endif
   }
 }
+// Batch (S2) mode: the caller supplies the unfiltered border of every PU as the linear 4N+1 array of
+// include/cucudecide.h ([0..2N-1] left column bottom -> top, [2N] corner, [2N+1..4N] above row); substitution has
+// already happened in the encoder (TComPattern.cpp:314-521).  T[k] = b[2N + k], L[k] = b[2N - k].
+template <int LOG2N>
+CUCD_HD void build_unfiltered_batch(int tid, int ctu, const int16_t* b /*border of PU tid / TPP, or null*/, unsigned char* smem) {
+  typedef Cfg<LOG2N> C;
+  constexpr int N = C::N, TPP = 256 / C::PUS, SPT = 4 * N / TPP;
+  unsigned char* store = smem + C::STORE_OFF;
+  const int p = tid / TPP, sub = tid % TPP;
+  if (!smem[C::VALID_OFF + ctu * 256 + p]) return;
+  if (LOG2N == 2) {
+    auto w4 = [](int b0, int b1, int b2, int b3) { return (uint32_t)(b0 & 255) | ((uint32_t)(b1 & 255) << 8) | ((uint32_t)(b2 & 255) << 16) | ((uint32_t)(b3 & 255) << 24); };
+    const int16_t* t = b + 8;                       // t[k] = T[k], t[-k] = L[k]
+    uint32_t* r0 = reinterpret_cast<uint32_t*>(store + rec_off(ctu, 0, p));
+    uint32_t* r1 = reinterpret_cast<uint32_t*>(store + rec_off(ctu, 1, p));
+    r0[0] = w4(t[0], t[1], t[2], t[3]); r0[1] = w4(t[4], t[5], t[6], t[7]); r0[2] = w4(t[8], t[-1], t[-2], t[-3]); r0[3] = w4(t[-4], t[-5], 0, 1);
+    r1[0] = w4(t[0], t[-1], t[-2], t[-3]); r1[1] = w4(t[-4], t[-5], t[-6], t[-7]); r1[2] = w4(t[-8], t[1], t[2], t[3]); r1[3] = w4(t[4], t[5], 0, 1);
+    return;
+  }
+  if (sub == 0) { put_ref<LOG2N>(store, ctu, p, 0, 0, b[2 * N]); put_ref<LOG2N>(store, ctu, p, 1, 0, b[2 * N]); }
+  int dcSum = 0;
+#pragma unroll
+  for (int e = 0; e < SPT; e++) {
+    const int j = sub * SPT + e;
+    const int o = j >= 2 * N, k = j - o * 2 * N + 1;
+    const int v = o ? b[2 * N - k] : b[2 * N + k];
+    put_ref<LOG2N>(store, ctu, p, o, k, v);
+    if (k <= N) dcSum += v;
+  }
+  int* dst = reinterpret_cast<int*>(smem + C::DC_OFF) + ctu * 64 + p;
+#if defined(__CUDA_ARCH__)
+  if (dcSum) atomicAdd(dst, dcSum);
+#else
+  *dst += dcSum;
+#endif
+}
+
 // Phase 3: smoothed arrays (TComPattern.cpp:185-283) from the unfiltered ones, same thread -> sample map
 template <int LOG2N>
 CUCD_HD void build_filtered(int tid, int ctu, int strongEnabled, unsigned char* smem) {

@@ -36,8 +36,9 @@ __device__ long long* g_tc2Dbg = nullptr;
 namespace {
 
 struct Tc2Args {
-  FrameSource fs;
-  int strong, totalCtus;
+  FrameSource fs;             // frame (replay) mode: a unit is a CTU at one depth
+  BatchSource bs;             // batch (S2) mode: a unit is 4096 / N^2 caller-described PUs of one size ("virtual CTU")
+  int strong, totalCtus;      // totalCtus = number of units
   const uint8_t* tabWin; const uint8_t* tabN4; const int8_t* had;
 };
 
@@ -87,13 +88,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;\n" :: "r"(grp + 1) : "memory"); }
 
 // ---- prologue: reference arrays of the CTA's CTUs (rmd_tc2.cuh phases 1-3) --------------------------------
-template <int LOG2N>
+template <int LOG2N, bool FRAME>
 __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N;
   unsigned char* smem = smem2;
   const int tid = threadIdx.x;
   const FrameSource& fs = a.fs;
+  if (!FRAME) {
+    const BatchSource& bs = a.bs;
+    constexpr int TPP = 256 / C::PUS;
+#pragma unroll
+    for (int c = 0; c < C::CTUS; c++) {
+      const int first = (unit * C::CTUS + c) * C::PUS;
+      for (int p = tid; p < C::PUS; p += kThreads) smem[C::VALID_OFF + c * 256 + p] = first + p < bs.count ? 1 : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C::CTUS; c++) {
+      const int idx = (unit * C::CTUS + c) * C::PUS + tid / TPP;
+      build_unfiltered_batch<LOG2N>(tid, c, idx < bs.count ? bs.border + (size_t)bs.pus[idx].borderOff : nullptr, smem);
+    }
+    if (C::HAS_FILT) {
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < C::CTUS; c++)
+        if ((unit * C::CTUS + c) * C::PUS < bs.count) build_filtered<LOG2N>(tid, c, a.strong, smem);
+    }
+    return;
+  }
   int ctuX[C::CTUS], ctuY[C::CTUS];
 #pragma unroll
   for (int c = 0; c < C::CTUS; c++) {
@@ -130,7 +153,7 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
 //     wait MMA1(i) | epilogue 1 -> A2, projected refs of round i+1 | issue MMA2(i) | stage B1/A1 of round i+1 |
 //     wait MMA2(i) | issue MMA1(i+1) | epilogue 2 of round i (costs)
 // TMEM per row group: D1 = columns [0, 64) (A2 aliases its first 16 once they have been read), D2 = [64, 128).
-template <int LOG2N>
+template <int LOG2N, bool FRAME>
 __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N, SEG = RowSeg<LOG2N>::value;
@@ -150,16 +173,43 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
 
   uint32_t p[16];                                   // the row's current byte tile: word 2*v + h = pixels (v, 4h..4h+3)
   if (ok) {
-    const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-    int px, py; demorton(r.pu, px, py);
-    if (LOG2N == 2) { px *= 8; py *= 8; }
-    else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
-    const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
     uint32_t raw[16];
+    if (FRAME) {
+      const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
+      int px, py; demorton(r.pu, px, py);
+      if (LOG2N == 2) { px *= 8; py *= 8; }
+      else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
+      const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
 #pragma unroll
-    for (int y = 0; y < 8; y++) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)y * fs.orgStride);
-      raw[2 * y] = __byte_perm(v.x, v.y, 0x6420); raw[2 * y + 1] = __byte_perm(v.z, v.w, 0x6420);
+      for (int y = 0; y < 8; y++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)y * fs.orgStride);
+        raw[2 * y] = __byte_perm(v.x, v.y, 0x6420); raw[2 * y + 1] = __byte_perm(v.z, v.w, 0x6420);
+      }
+    } else {
+      const BatchSource& bs = a.bs;
+      const int first = cg * C::PUS;                // cg = index of the virtual CTU
+      if (LOG2N == 2) {                             // region = four packed 4x4 blocks (PUs 4*r.pu .. +3, z order: (qy, qx))
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int idx = first + 4 * r.pu + q;
+          uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+          if (idx < bs.count) {
+            const uint4* b = reinterpret_cast<const uint4*>(bs.org + (size_t)bs.pus[idx].orgOff);
+            v0 = b[0]; v1 = b[1];
+          }
+          // rows of the block: (v0.x, v0.y), (v0.z, v0.w), (v1.x, v1.y), (v1.z, v1.w)
+          const int w0 = 2 * ((q >> 1) * 4) + (q & 1);
+          raw[w0] = __byte_perm(v0.x, v0.y, 0x6420); raw[w0 + 2] = __byte_perm(v0.z, v0.w, 0x6420);
+          raw[w0 + 4] = __byte_perm(v1.x, v1.y, 0x6420); raw[w0 + 6] = __byte_perm(v1.z, v1.w, 0x6420);
+        }
+      } else {
+        const int16_t* src = bs.org + (size_t)bs.pus[first + r.pu].orgOff + (r.o ? r.u0 : r.v0) * N + (r.o ? r.v0 : r.u0);
+#pragma unroll
+        for (int y = 0; y < 8; y++) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + y * N);
+          raw[2 * y] = __byte_perm(v.x, v.y, 0x6420); raw[2 * y + 1] = __byte_perm(v.z, v.w, 0x6420);
+        }
+      }
     }
     if (r.o) tile_transpose_bytes(raw, p, LOG2N != 2);
     else {
@@ -355,7 +405,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   (void)angle;
 }
 
-template <int LOG2N>
+template <int LOG2N, bool FRAME>
 __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   typedef Cfg<LOG2N> C;
   unsigned char* smem = smem2;
@@ -372,7 +422,7 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   if (LOG2N >= 4) for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) acc[i] = 0;   // accumulated with atomics
   reinterpret_cast<int*>(smem + C::DC_OFF)[tid] = 0;          // CTUS * 64 <= 256 sums
   __syncthreads();
-  tc2_prologue<LOG2N>(a, unit);
+  tc2_prologue<LOG2N, FRAME>(a, unit);
   tc_fence_before();
   fence_async_smem();
   __syncthreads();
@@ -381,28 +431,34 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   uint32_t ph1 = 0, ph2 = 0;
   TC2_STAMP(1);
 #pragma unroll 1
-  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N>(a, unit, pass, tmemBase, ph1, ph2);
+  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N, FRAME>(a, unit, pass, tmemBase, ph1, ph2);
   TC2_STAMP(2);
 
   // ---- costs leave the SM ------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
   const FrameSource& fs = a.fs;
+  if (!FRAME) {
+    // batch mode: row outIndex of the caller's [nPU][35] table per PU
+    const BatchSource& bs = a.bs;
+    for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) {
+      const int pl = i / kNumModes, m = i - pl * kNumModes, idx = unit * C::CTUS * C::PUS + pl;
+      if (idx >= bs.count) continue;
+      const uint32_t v = LOG2N == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(acc)[i] : acc[i];
+      bs.out[(size_t)bs.pus[idx].outIndex * kNumModes + m] = v;
+    }
+    if (warp == 0) tmem_dealloc(tmemBase, 256);
+    return;
+  }
   for (int c = 0; c < C::CTUS; c++) {
     const int cgc = unit * C::CTUS + c;
     if (cgc >= a.totalCtus) break;
     const uint8_t* valid = smem + C::VALID_OFF + c * 256;
     uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
     if (LOG2N == 2) {
-      // four uint16 costs per trip (a quad may straddle two PUs: validity per element); the output is only 4-byte aligned
       const uint16_t* a16 = reinterpret_cast<const uint16_t*>(acc) + c * C::PUS * kNumModes;
-#pragma unroll 4
-      for (int i4 = tid; i4 < C::PUS * kNumModes / 4; i4 += kThreads) {
-        const uint2 w = reinterpret_cast<const uint2*>(a16)[i4];
-        const int i = 4 * i4;
-        o[i] = valid[i / kNumModes] ? (w.x & 0xffffu) : 0xffffffffu;           o[i + 1] = valid[(i + 1) / kNumModes] ? (w.x >> 16) : 0xffffffffu;
-        o[i + 2] = valid[(i + 2) / kNumModes] ? (w.y & 0xffffu) : 0xffffffffu; o[i + 3] = valid[(i + 3) / kNumModes] ? (w.y >> 16) : 0xffffffffu;
-      }
+#pragma unroll 5
+      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? (uint32_t)a16[i] : 0xffffffffu;
     } else {
 #pragma unroll 4
       for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
@@ -420,19 +476,55 @@ __global__ void __launch_bounds__(kThreads, 2)
 rmd_frame_tc2_kernel(const Tc2Args a) {
   const int u2 = (a.totalCtus + 1) >> 1, u4 = (a.totalCtus + 3) >> 2;
   int b = blockIdx.x;
-  if (b < u4) { tc2_body<6>(a, b); return; }
+  if (b < u4) { tc2_body<6, true>(a, b); return; }
   b -= u4;
-  if (b < u4) { tc2_body<5>(a, b); return; }
+  if (b < u4) { tc2_body<5, true>(a, b); return; }
   b -= u4;
-  if (b < u2) { tc2_body<4>(a, b); return; }
+  if (b < u2) { tc2_body<4, true>(a, b); return; }
   b -= u2;
-  if (b < u2) { tc2_body<3>(a, b); return; }
-  tc2_body<2>(a, b - u2);
+  if (b < u2) { tc2_body<3, true>(a, b); return; }
+  tc2_body<2, true>(a, b - u2);
+}
+
+// batch (S2) mode: one launch per PU size
+template <int LOG2N>
+__global__ void __launch_bounds__(kThreads, 2)
+rmd_batch_tc2_kernel(const Tc2Args a) { tc2_body<LOG2N, false>(a, blockIdx.x); }
+
+template <int LOG2N>
+cudaError_t launch_batch_tc2(const Tc2Args& a, int units, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rmd_batch_tc2_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<LOG2N>::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  rmd_batch_tc2_kernel<LOG2N><<<(units + Cfg<LOG2N>::CTUS - 1) / Cfg<LOG2N>::CTUS, kThreads, Cfg<LOG2N>::TOTAL, st>>>(a);
+  return cudaGetLastError();
 }
 
 }  // namespace
 
 int rmd_tc2_smem_bytes() { return kSmemBytes; }
+
+cudaError_t launch_rmd_batch_tc2(int log2n, const BatchSource& bs, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
+                                 cudaStream_t st, int* launches) {
+  if (bs.count <= 0) return cudaSuccess;
+  const int n = 1 << log2n, pus = 4096 / (n * n);
+  Tc2Args a;
+  a.fs = FrameSource{}; a.bs = bs; a.strong = strong; a.totalCtus = (bs.count + pus - 1) / pus; a.tabWin = tabWin; a.tabN4 = tabN4; a.had = hadamard;
+  cudaError_t e;
+  switch (log2n) {
+    case 2: e = launch_batch_tc2<2>(a, a.totalCtus, st); break;
+    case 3: e = launch_batch_tc2<3>(a, a.totalCtus, st); break;
+    case 4: e = launch_batch_tc2<4>(a, a.totalCtus, st); break;
+    case 5: e = launch_batch_tc2<5>(a, a.totalCtus, st); break;
+    case 6: e = launch_batch_tc2<6>(a, a.totalCtus, st); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e == cudaSuccess && launches) *launches += 1;
+  return e;
+}
 
 cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
                                   cudaStream_t st, int* launches) {
@@ -445,7 +537,7 @@ cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, 
     configured = true;
   }
   Tc2Args a;
-  a.fs = fs; a.strong = strong; a.totalCtus = total; a.tabWin = tabWin; a.tabN4 = tabN4; a.had = hadamard;
+  a.fs = fs; a.bs = BatchSource{}; a.strong = strong; a.totalCtus = total; a.tabWin = tabWin; a.tabN4 = tabN4; a.had = hadamard;
   const int u2 = (total + 1) >> 1, u4 = (total + 3) >> 2;
   rmd_frame_tc2_kernel<<<2 * u4 + 3 * u2, kThreads, kSmemBytes, st>>>(a);
   if (launches) *launches += 1;

@@ -7,6 +7,7 @@
 // and tcgen05.ld.pack::16b by its measured behaviour (profiles/ubench).  Built only by tests/.
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include "rmd_tc2.cuh"
 
@@ -48,8 +49,9 @@ void mma(const uint32_t* aWords, int aStride, int K, const void* b, bool bSigned
     }
 }
 
+// bs == nullptr: frame (replay) mode; otherwise batch (S2) mode over the PUs of one size described by *bs
 template <int LOG2N>
-void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
+void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit, const BatchSource* bs = nullptr) {
   typedef Geo<LOG2N> G;
   typedef Cfg<LOG2N> C;
   constexpr int N = G::N, log2n = LOG2N;
@@ -60,6 +62,20 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
   if (LOG2N >= 4) for (int i = 0; i < C::CTUS * C::PUS * kNumModes; i++) acc[i] = 0;
   for (int i = 0; i < C::CTUS * 64; i++) reinterpret_cast<int*>(smem + C::DC_OFF)[i] = 0;
   // ---- prologue (tc2_prologue) ----
+  if (bs) {
+    constexpr int TPP = 256 / C::PUS;
+    for (int c = 0; c < C::CTUS; c++) {
+      const int first = (unit * C::CTUS + c) * C::PUS;
+      for (int p = 0; p < C::PUS; p++) smem[C::VALID_OFF + c * 256 + p] = first + p < bs->count ? 1 : 0;
+    }
+    for (int c = 0; c < C::CTUS; c++)
+      for (int tid = 0; tid < kThreads; tid++) {
+        const int idx = (unit * C::CTUS + c) * C::PUS + tid / TPP;
+        build_unfiltered_batch<LOG2N>(tid, c, idx < bs->count ? bs->border + (size_t)bs->pus[idx].borderOff : nullptr, smem);
+      }
+    for (int c = 0; c < C::CTUS; c++)
+      if ((unit * C::CTUS + c) * C::PUS < bs->count) for (int tid = 0; tid < kThreads; tid++) build_filtered<LOG2N>(tid, c, strong, smem);
+  } else {
   int ctuXs[C::CTUS], ctuYs[C::CTUS];
   for (int c = 0; c < C::CTUS; c++) {
     const int cg = unit * C::CTUS + c;
@@ -76,6 +92,7 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
     if (ctuXs[c] >= 0) for (int tid = 0; tid < kThreads; tid++) build_unfiltered<LOG2N>(tid, c, fs.W, fs.H, ctuXs[c], ctuYs[c], smem + C::TILE_OFF + c * C::TILE_BYTES, smem);
   for (int c = 0; c < C::CTUS; c++)
     if (ctuXs[c] >= 0) for (int tid = 0; tid < kThreads; tid++) build_filtered<LOG2N>(tid, c, strong, smem);
+  }
   std::memset(smem + C::TILE_OFF, 0x5A, C::CTUS * C::TILE_BYTES);   // the tiles alias the operand buffers: gone after the prologue
   unsigned char* store = smem + C::STORE_OFF;
   const int8_t* had = tb.had.data() + (log2n == 2 ? 8192 : 0);
@@ -89,18 +106,27 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
       ok[tid] = smem[C::VALID_OFF + r.ctu * 256 + (log2n == 2 ? 4 * r.pu : r.pu)] != 0;
       uint32_t* p = &P[tid * 16];
       if (ok[tid]) {
-        const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-        int px, py; demorton(r.pu, px, py);
-        if (log2n == 2) { px *= 8; py *= 8; }
-        else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
-        const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
         uint32_t raw[16];
-        for (int y = 0; y < 8; y++)
-          for (int h = 0; h < 2; h++) {
-            uint32_t w = 0;
-            for (int i = 0; i < 4; i++) w |= (uint32_t)(src[(size_t)y * fs.orgStride + 4 * h + i] & 0xff) << (8 * i);
-            raw[2 * y + h] = w;
+        auto pack4 = [](const int16_t* q) { uint32_t w = 0; for (int i = 0; i < 4; i++) w |= (uint32_t)(q[i] & 0xff) << (8 * i); return w; };
+        if (!bs) {
+          const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
+          int px, py; demorton(r.pu, px, py);
+          if (log2n == 2) { px *= 8; py *= 8; }
+          else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
+          const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
+          for (int y = 0; y < 8; y++) for (int h = 0; h < 2; h++) raw[2 * y + h] = pack4(src + (size_t)y * fs.orgStride + 4 * h);
+        } else {
+          const int first = cg * C::PUS;
+          if (log2n == 2) {
+            for (int q = 0; q < 4; q++) {
+              const int idx = first + 4 * r.pu + q;
+              for (int y = 0; y < 4; y++) raw[2 * ((q >> 1) * 4 + y) + (q & 1)] = idx < bs->count ? pack4(bs->org + (size_t)bs->pus[idx].orgOff + 4 * y) : 0u;
+            }
+          } else {
+            const int16_t* src = bs->org + (size_t)bs->pus[first + r.pu].orgOff + (r.o ? r.u0 : r.v0) * N + (r.o ? r.v0 : r.u0);
+            for (int y = 0; y < 8; y++) for (int h = 0; h < 2; h++) raw[2 * y + h] = pack4(src + y * N + 4 * h);
           }
+        }
         if (r.o) tile_transpose_bytes(raw, p, log2n != 2); else std::memcpy(p, raw, sizeof(raw));
       } else std::memset(p, 0, 64);
     }
@@ -176,6 +202,14 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit) {
       cost_out(am, true);
     }
   }
+  if (bs) {
+    for (int i = 0; i < C::CTUS * C::PUS * kNumModes; i++) {
+      const int pl = i / kNumModes, m = i - pl * kNumModes, idx = unit * C::CTUS * C::PUS + pl;
+      if (idx >= bs->count) continue;
+      bs->out[(size_t)bs->pus[idx].outIndex * kNumModes + m] = LOG2N == 2 ? (uint32_t)reinterpret_cast<const uint16_t*>(acc)[i] : acc[i];
+    }
+    return;
+  }
   for (int c = 0; c < C::CTUS; c++) {
     const int cgc = unit * C::CTUS + c;
     if (cgc >= totalCtus) break;
@@ -201,6 +235,28 @@ int emul_rmd_frame_tc2(int strong, const int16_t* org, int orgStride, const int1
   const int total = fs.ctusPerPic, u2 = (total + 1) >> 1, u4 = (total + 3) >> 2;
   for (int u = 0; u < u4; u++) { emul_cta<6>(fs, strong, total, u); emul_cta<5>(fs, strong, total, u); }
   for (int u = 0; u < u2; u++) { emul_cta<4>(fs, strong, total, u); emul_cta<3>(fs, strong, total, u); emul_cta<2>(fs, strong, total, u); }
+  return 0;
+}
+// batch (S2) mode: `count` PUs of ONE size, tightly packed org blocks and borders, out[count][35]
+int emul_rmd_batch_tc2(int strong, int log2n, int count, const int16_t* org, const int16_t* border, uint32_t* out) {
+  const int n = 1 << log2n, pus = 4096 / (n * n);
+  std::vector<BatchPu> list(count);
+  for (int i = 0; i < count; i++) { list[i].orgOff = i * n * n; list[i].borderOff = i * (4 * n + 1); list[i].outIndex = i; list[i].pad = 0; }
+  BatchSource bs; bs.org = org; bs.border = border; bs.pus = list.data(); bs.out = out; bs.count = count;
+  FrameSource fs = {};
+  const int units = (count + pus - 1) / pus;
+  auto run = [&](auto tag) {
+    constexpr int L = decltype(tag)::value;
+    for (int u = 0; u * Cfg<L>::CTUS < units; u++) emul_cta<L>(fs, strong, units, u, &bs);
+  };
+  switch (log2n) {
+    case 2: run(std::integral_constant<int, 2>()); break;
+    case 3: run(std::integral_constant<int, 3>()); break;
+    case 4: run(std::integral_constant<int, 4>()); break;
+    case 5: run(std::integral_constant<int, 5>()); break;
+    case 6: run(std::integral_constant<int, 6>()); break;
+    default: return -1;
+  }
   return 0;
 }
 // the weight tables, for inspection

@@ -46,6 +46,17 @@ def test_tensor_core_frame_kernel_code_vs_oracle(emul, oracle, W, H, seed):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64])
+def test_tensor_core_batch_kernel_code_vs_golden(emul, n):
+    """S2 batches on the tensor-core code path against the vectors dumped from the reference encoder's own RMD loop"""
+    g = golden("rmd_ai8.npz")
+    org = np.ascontiguousarray(g[f"n{n}_org"])
+    unf = np.ascontiguousarray(g[f"n{n}_unf"])
+    out = np.zeros((len(org), 35), np.uint32)
+    assert emul.emul_rmd_batch_tc2(1, int(np.log2(n)), len(org), P(org, i16p), P(unf, i16p), P(out, u32p)) == 0
+    assert np.array_equal(out, g[f"n{n}_sad"])
+
+
 def test_tensor_core_frame_kernel_code_extreme_values(emul, oracle):
     """the byte-1 extraction must be exact at 0 / 255 and for alternating content"""
     W = H = 64

@@ -278,3 +278,14 @@ def test_packed_cost_tables_equal_wide_tables(cucd, oracle, bd, W, H):
         assert np.array_equal(got, wide[k]["rmd_cost"])
     assert np.array_equal(cucd.unpack_costs(outs[0]["rmd_cost_packed"]), want)
     assert (want == 0xFFFFFFFF).any()          # partial CTUs: the 0xFFFF marker is exercised
+
+
+# ---- S2 batches: the integer-ALU kernels stay bit-exact for 8-bit content too (the default 8-bit path is tcgen05) ----
+def test_rmd_batch_alu_path_8bit_vs_reference_encoder_dump(cucd):
+    g = golden("rmd_ai8.npz")
+    with cucd.Engine(416, 240, bit_depth=8) as eng:
+        for path in (0, 1):
+            eng.set_rmd_path(path)
+            for n in (4, 8, 16, 32, 64):
+                got = eng.intra_rmd_batch([int(np.log2(n))] * len(g[f"n{n}_org"]), g[f"n{n}_org"], g[f"n{n}_unf"])
+                assert np.array_equal(got, g[f"n{n}_sad"]), (path, n)
