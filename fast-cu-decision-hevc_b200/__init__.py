@@ -17,6 +17,7 @@ from .binding import (  # noqa: F401
     NUM_MODES,
     PACKED_CTU_BYTES,
     PUS_PER_CTU,
+    RmdQueue,
     declared_symbols,
     exp_satd_tc,
     load_library,

@@ -104,6 +104,11 @@ def load_library():
                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     lib.cucd_dev_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
                                     C.c_int, C.POINTER(_DevOut), C.c_void_p]
+    lib.cucd_queue_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.cucd_queue_destroy.argtypes = [C.c_void_p]
+    lib.cucd_queue_submit.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.cucd_queue_wait.argtypes = [C.c_void_p, C.c_uint64]
+    lib.cucd_queue_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.cucd_rmd_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
     lib.cucd_tcm_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib
@@ -346,3 +351,51 @@ class Engine:
         """0 / False: integer ALU; 1 / True: predictions + Hadamard on tcgen05 (8-bit); 2: tcgen05 Hadamard only (8-bit)"""
         self.lib.cucd_set_rmd_path.argtypes = [C.c_void_p, C.c_int]
         self._check(self.lib.cucd_set_rmd_path(self.h, int(path)), "cucd_set_rmd_path")
+
+
+class RmdQueue:
+    """cucd_queue: asynchronous, coalescing front end of cucd_intra_rmd_batch shared by several host threads."""
+
+    def __init__(self, engine):
+        self.lib, self.engine = engine.lib, engine
+        self.q = C.c_void_p()
+        rc = self.lib.cucd_queue_create(engine.h, C.byref(self.q))
+        if rc != 0:
+            raise CucdError(f"cucd_queue_create failed ({rc})")
+
+    def submit(self, log2_sizes, org, border):
+        """returns (ticket, sad) - sad (nPU, 35) uint32 is valid after wait(ticket)"""
+        log2_sizes = np.asarray(log2_sizes, np.uint8)
+        n = int(log2_sizes.size)
+        org = np.ascontiguousarray(org, np.int16).ravel()
+        border = np.ascontiguousarray(border, np.int16).ravel()
+        desc = (_PuDesc * max(n, 1))()
+        for i in range(n):
+            desc[i].log2_size = int(log2_sizes[i])
+        sad = np.zeros((n, NUM_MODES), np.uint32)
+        t = C.c_uint64(0)
+        rc = self.lib.cucd_queue_submit(self.q, n, desc, org.ctypes.data, border.ctypes.data, sad.ctypes.data, C.byref(t))
+        if rc != 0:
+            raise CucdError(f"cucd_queue_submit failed ({rc})")
+        return int(t.value), sad
+
+    def wait(self, ticket):
+        rc = self.lib.cucd_queue_wait(self.q, C.c_uint64(ticket))
+        if rc != 0:
+            raise CucdError(f"cucd_queue_wait failed ({rc}): {self.lib.cucd_last_error(self.engine.h).decode()}")
+
+    def stats(self):
+        r, p, b = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        self.lib.cucd_queue_stats(self.q, C.byref(r), C.byref(p), C.byref(b))
+        return {"requests": int(r.value), "pus": int(p.value), "batches": int(b.value)}
+
+    def close(self):
+        if getattr(self, "q", None):
+            self.lib.cucd_queue_destroy(self.q)
+            self.q = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

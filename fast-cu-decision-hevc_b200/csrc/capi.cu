@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -523,6 +526,119 @@ int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, cons
   CK(cudaMemcpyAsync(sad, h->bOut.p, (size_t)nPU * kNumModes * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));   // `all` and the caller's buffers must outlive the copies
   flush_launches(h);
+  return CUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S2, asynchronous and coalescing: a worker thread turns everything that is pending into one batch
+// ------------------------------------------------------------------------------------------------
+struct cucd_queue {
+  struct Request {
+    uint64_t ticket; int nPU;
+    std::vector<cucd_pu_desc> desc; std::vector<int16_t> org, border;
+    uint32_t* sad;
+  };
+  cucd_handle* h = nullptr;
+  std::mutex m;
+  std::condition_variable cvWork, cvDone;
+  std::deque<Request> pending;
+  uint64_t nextTicket = 1, doneUpTo = 0;
+  int lastStatus = CUCD_OK;
+  uint64_t failedFrom = 0;                 // first ticket of a failed batch (0 = none)
+  bool stop = false;
+  long long requests = 0, pus = 0, batches = 0;
+  std::thread worker;
+
+  void run() {
+    std::vector<cucd_pu_desc> desc; std::vector<int16_t> org, border; std::vector<uint32_t> sad;
+    for (;;) {
+      std::deque<Request> batch;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cvWork.wait(lk, [&] { return stop || !pending.empty(); });
+        if (pending.empty()) return;       // stop requested and nothing left
+        batch.swap(pending);
+      }
+      desc.clear(); org.clear(); border.clear();
+      int total = 0;
+      for (const Request& r : batch) {
+        desc.insert(desc.end(), r.desc.begin(), r.desc.end());
+        org.insert(org.end(), r.org.begin(), r.org.end());
+        border.insert(border.end(), r.border.begin(), r.border.end());
+        total += r.nPU;
+      }
+      sad.resize((size_t)total * kNumModes);
+      const int rc = total ? cucd_intra_rmd_batch(h, total, desc.data(), org.data(), border.data(), sad.data()) : CUCD_OK;
+      size_t off = 0;
+      for (const Request& r : batch) {
+        if (rc == CUCD_OK) memcpy(r.sad, sad.data() + off, (size_t)r.nPU * kNumModes * sizeof(uint32_t));
+        off += (size_t)r.nPU * kNumModes;
+      }
+      {
+        std::lock_guard<std::mutex> lk(m);
+        if (rc != CUCD_OK && !failedFrom) { failedFrom = batch.front().ticket; lastStatus = rc; }
+        doneUpTo = batch.back().ticket;
+        batches++;
+      }
+      cvDone.notify_all();
+    }
+  }
+};
+
+int cucd_queue_create(cucd_handle* h, cucd_queue** out) {
+  if (!h || !out) return fail(h, CUCD_ERR_INVALID, "cucd_queue_create: null argument");
+  cucd_queue* q = new cucd_queue;
+  q->h = h;
+  q->worker = std::thread([q] { q->run(); });
+  *out = q;
+  return CUCD_OK;
+}
+
+int cucd_queue_destroy(cucd_queue* q) {
+  if (!q) return CUCD_OK;
+  { std::lock_guard<std::mutex> lk(q->m); q->stop = true; }
+  q->cvWork.notify_all();
+  if (q->worker.joinable()) q->worker.join();
+  delete q;
+  return CUCD_OK;
+}
+
+int cucd_queue_submit(cucd_queue* q, int nPU, const cucd_pu_desc* desc, const int16_t* org, const int16_t* border, uint32_t* sad, uint64_t* ticket) {
+  if (!q || !ticket || nPU < 0 || (nPU > 0 && (!desc || !org || !border || !sad))) return CUCD_ERR_INVALID;
+  cucd_queue::Request r;
+  r.nPU = nPU; r.sad = sad;
+  size_t orgN = 0, brdN = 0;
+  for (int i = 0; i < nPU; i++) {
+    const int l = desc[i].log2_size;
+    if (l < 2 || l > 6) return CUCD_ERR_INVALID;
+    orgN += (size_t)1 << (2 * l); brdN += ((size_t)4 << l) + 1;
+  }
+  r.desc.assign(desc, desc + nPU); r.org.assign(org, org + orgN); r.border.assign(border, border + brdN);
+  {
+    std::lock_guard<std::mutex> lk(q->m);
+    if (q->stop) return CUCD_ERR_INVALID;
+    r.ticket = *ticket = q->nextTicket++;
+    q->requests++; q->pus += nPU;
+    q->pending.push_back(std::move(r));
+  }
+  q->cvWork.notify_one();
+  return CUCD_OK;
+}
+
+int cucd_queue_wait(cucd_queue* q, uint64_t ticket) {
+  if (!q || ticket == 0) return CUCD_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(q->m);
+  if (ticket >= q->nextTicket) return CUCD_ERR_INVALID;
+  q->cvDone.wait(lk, [&] { return q->doneUpTo >= ticket; });
+  return (q->failedFrom && ticket >= q->failedFrom) ? q->lastStatus : CUCD_OK;
+}
+
+int cucd_queue_stats(cucd_queue* q, long long* requests, long long* pus, long long* batches) {
+  if (!q) return CUCD_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(q->m);
+  if (requests) *requests = q->requests;
+  if (pus) *pus = q->pus;
+  if (batches) *batches = q->batches;
   return CUCD_OK;
 }
 

@@ -112,6 +112,24 @@ int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, cons
                          uint32_t* sad);
 
 /* ------------------------------------------------------------------------------------------------
+ * S2, asynchronous and coalescing.  In the live encoder a PU's border is an intermediate state
+ * of the reconstruction, so one encoder instance can only offer the few PUs of its current CU at a time.  Several
+ * instances (host threads, one per picture in flight) therefore share ONE queue on top of a handle: submit copies
+ * the request and returns at once, a worker thread runs everything that is pending as one cucd_intra_rmd_batch
+ * (one launch per PU size, thousands of PUs) and completes the tickets in submission order.
+ * The queue owns the handle's S2 path while it exists: do not call cucd_intra_rmd_batch on `h` directly meanwhile.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cucd_queue cucd_queue;
+int cucd_queue_create(cucd_handle* h, cucd_queue** out);
+int cucd_queue_destroy(cucd_queue* q);      /* completes what is pending first */
+/* thread-safe, non-blocking; `sad` (nPU*35 uint32, caller-owned) is valid once cucd_queue_wait(q, *ticket) returned CUCD_OK */
+int cucd_queue_submit(cucd_queue* q, int nPU, const cucd_pu_desc* desc, const int16_t* org, const int16_t* border, uint32_t* sad,
+                      uint64_t* ticket);
+int cucd_queue_wait(cucd_queue* q, uint64_t ticket);
+/* how well requests coalesce: requests and PUs submitted, batches (cucd_intra_rmd_batch calls) executed so far */
+int cucd_queue_stats(cucd_queue* q, long long* requests, long long* pus, long long* batches);
+
+/* ------------------------------------------------------------------------------------------------
  * S3: integer motion estimation.
  * cucd_set_ref_picture  uploads a reconstructed reference plane with its replicated margins
  *                       (TComPicYuv layout: TComPicYuv.cpp:77-101, extendPicBorder :191).

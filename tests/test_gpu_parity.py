@@ -289,3 +289,42 @@ def test_rmd_batch_alu_path_8bit_vs_reference_encoder_dump(cucd):
             for n in (4, 8, 16, 32, 64):
                 got = eng.intra_rmd_batch([int(np.log2(n))] * len(g[f"n{n}_org"]), g[f"n{n}_org"], g[f"n{n}_unf"])
                 assert np.array_equal(got, g[f"n{n}_sad"]), (path, n)
+
+
+# ---- S2 async coalescing queue: several host threads, one batch stream --------------------------------------------
+def test_rmd_queue_coalesces_concurrent_requests(cucd, oracle):
+    import threading
+    rng = np.random.default_rng(5)
+    reqs = []
+    for t in range(4):
+        mine = []
+        for k in range(12):
+            sizes = rng.integers(2, 7, rng.integers(1, 9))
+            org = np.concatenate([rng.integers(0, 256, (1 << s) ** 2) for s in sizes]).astype(np.int16)
+            brd = np.concatenate([rng.integers(0, 256, 4 * (1 << s) + 1) for s in sizes]).astype(np.int16)
+            mine.append((sizes, org, brd))
+        reqs.append(mine)
+    results = [[None] * 12 for _ in range(4)]
+    with cucd.Engine(64, 64, bit_depth=8) as eng, cucd.RmdQueue(eng) as q:
+        def client(t):
+            tickets = [q.submit(*r) for r in reqs[t]]          # fire everything, then collect: requests pile up behind the worker
+            for k, (ticket, sad) in enumerate(tickets):
+                q.wait(ticket)
+                results[t][k] = sad
+        ths = [threading.Thread(target=client, args=(t,)) for t in range(4)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        st = q.stats()
+    assert st["requests"] == 48 and st["batches"] <= st["requests"]
+    for t in range(4):
+        for (sizes, org, brd), got in zip(reqs[t], results[t]):
+            oo = bo = 0
+            for i, s in enumerate(sizes):
+                n = 1 << int(s)
+                want = np.zeros(35, np.uint32)
+                o = np.ascontiguousarray(org[oo:oo + n * n]); b = np.ascontiguousarray(brd[bo:bo + 4 * n + 1])
+                oracle.oracle_rmd_pu(8, n, 1, P(o, i16p), n, P(b, i16p), P(want, u32p))
+                assert np.array_equal(got[i], want)
+                oo += n * n; bo += 4 * n + 1
