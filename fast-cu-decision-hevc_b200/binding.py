@@ -65,6 +65,13 @@ class _MeDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("x", "y", "w", "h", "ref_idx", "left", "right", "top", "bottom", "sub_shift")]
 
 
+class _CuDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("x", "y", "log2_size")]
+
+
+TMV_FEATURES = 5 * 26
+
+
 def declared_symbols():
     """Every function name include/cucudecide.h declares."""
     text = open(HEADER_PATH).read()
@@ -97,6 +104,8 @@ def load_library():
     lib.cucd_set_ref_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.cucd_set_cur_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.cucd_me_sad_surface.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MeDesc), C.c_void_p]
+    lib.cucd_tmv_features.argtypes = [C.c_void_p, C.c_int, C.POINTER(_CuDesc), C.c_void_p]
+    lib.cucd_aq_activity.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
     lib.cucd_dev_rmd_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
                                         C.c_longlong, C.c_int, C.c_void_p]
     lib.cucd_dev_feature_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
@@ -310,6 +319,28 @@ class Engine:
             res.append(out[off:off + r * c].reshape(r, c))
             off += r * c
         return res
+
+    def tmv_features(self, cus):
+        """cus: iterable of (x, y, log2_size) of the picture given to set_cur_picture. Returns (nCU, 5, 26) float64
+        = TMVFeature::m_adFeature of getTMVFeature (tools_YS.cpp:1682-1839)."""
+        cus = list(cus)
+        arr = (_CuDesc * max(len(cus), 1))()
+        for i, (x, y, l) in enumerate(cus):
+            arr[i].x, arr[i].y, arr[i].log2_size = int(x), int(y), int(l)
+        out = np.zeros((len(cus), 5, 26), np.float64)
+        self._check(self.lib.cucd_tmv_features(self.h, len(cus), arr, out.ctypes.data), "cucd_tmv_features")
+        return out
+
+    def aq_activity(self, max_aq_depth):
+        """TEncPreanalyzer::xPreanalyze of the current picture: ([per-layer (rows, cols) float64 activity], avg[max_aq_depth])."""
+        acts = []
+        for d in range(max_aq_depth):
+            u = 64 >> d
+            acts.append(np.zeros(((self.height + u - 1) // u, (self.width + u - 1) // u), np.float64))
+        ptrs = (C.c_void_p * max_aq_depth)(*[a.ctypes.data for a in acts])
+        avg = np.zeros(max_aq_depth, np.float64)
+        self._check(self.lib.cucd_aq_activity(self.h, int(max_aq_depth), ptrs, avg.ctypes.data), "cucd_aq_activity")
+        return acts, avg
 
     # ---- device-resident entry points (raw pointers) ----------------------------------------------
     def dev_rmd_frames(self, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride, d_cost):

@@ -87,6 +87,7 @@ struct cucd_handle {
   std::vector<RefPlane> refs;
   DevBuf<int16_t> dCur; int curStride = 0; bool curSet = false;
   DevBuf<const int16_t*> dRefPtr; DevBuf<int32_t> dRefStride;
+  DevBuf<TmvCu> dTmvCus; DevBuf<double> dDoubles;   // texture features / AQ activity
   DevBuf<MeJob> dJobs; DevBuf<int32_t> dTileJob, dTileIdx; DevBuf<uint32_t> dSad;
 };
 
@@ -229,6 +230,7 @@ int cucd_destroy(cucd_handle* h) {
   h->dCtuHad.release(); h->hHist.release(); h->hThr.release(); h->dHadamard.release(); h->dTc2Tables.release();
   h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
   for (auto& r : h->refs) r.buf.release();
+  h->dTmvCus.release(); h->dDoubles.release();
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
   for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
   for (int i = 0; i < cucd_handle::kGroups; i++) { if (h->evUpG[i]) cudaEventDestroy(h->evUpG[i]); if (h->evRmdG[i]) cudaEventDestroy(h->evRmdG[i]); }
@@ -718,6 +720,62 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
   CK(launch_me_sad(mp, h->dJobs.p, nPU, h->dTileJob.p, h->dTileIdx.p, (int)tileJob.size(), h->dSad.p, h->sMain, &h->launches));
   CK(cudaMemcpyAsync(sadOut, h->dSad.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CU texture features (getTMVFeature) and AQ activity (TEncPreanalyzer) of the current picture
+// ------------------------------------------------------------------------------------------------
+int cucd_tmv_features(cucd_handle* h, int nCU, const cucd_cu_desc* cus, double* feat) {
+  if (!h || nCU < 0 || (nCU > 0 && (!cus || !feat))) return fail(h, CUCD_ERR_INVALID, "cucd_tmv_features: bad argument");
+  if (nCU == 0) return CUCD_OK;
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_tmv_features: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<TmvCu> v(nCU);
+  for (int i = 0; i < nCU; i++) {
+    const cucd_cu_desc& c = cus[i];
+    if (c.log2_size < 3 || c.log2_size > 6) return fail(h, CUCD_ERR_INVALID, "cucd_tmv_features: log2_size must be 3..6");
+    const int n = 1 << c.log2_size;
+    if (c.x < 0 || c.y < 0 || (c.x & (n - 1)) || (c.y & (n - 1)) || c.x + n > h->cfg.width || c.y + n > h->cfg.height)
+      return fail(h, CUCD_ERR_INVALID, "cucd_tmv_features: CU must be aligned to its size and lie inside the picture");
+    v[i].x = c.x; v[i].y = c.y; v[i].log2n = c.log2_size; v[i].pad = 0;
+  }
+  CK(h->dTmvCus.reserve(nCU)); CK(h->dDoubles.reserve((size_t)nCU * CUCD_TMV_FEATURES));
+  CK(cudaMemcpyAsync(h->dTmvCus.p, v.data(), v.size() * sizeof(TmvCu), cudaMemcpyHostToDevice, h->sMain));
+  CK(launch_tmv_features(h->dCur.p, h->curStride, h->dTmvCus.p, nCU, h->dDoubles.p, h->sMain, &h->launches));
+  CK(cudaMemcpyAsync(feat, h->dDoubles.p, (size_t)nCU * CUCD_TMV_FEATURES * sizeof(double), cudaMemcpyDeviceToHost, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+int cucd_aq_activity(cucd_handle* h, int max_aq_depth, double* const* activity, double* avg_activity) {
+  if (!h || max_aq_depth < 1 || max_aq_depth > 4 || (!activity && !avg_activity)) return fail(h, CUCD_ERR_INVALID, "cucd_aq_activity: bad argument");
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_aq_activity: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  const int W = h->cfg.width, H = h->cfg.height;
+  AqLayers L; L.count = max_aq_depth; L.total = 0;
+  for (int d = 0; d < 4; d++) { L.part[d] = 0; L.off[d] = 0; }
+  for (int d = 0; d < max_aq_depth; d++) {
+    L.part[d] = h->cfg.ctu_size >> d; L.off[d] = L.total;
+    L.total += ((W + L.part[d] - 1) / L.part[d]) * ((H + L.part[d] - 1) / L.part[d]);
+  }
+  for (int d = max_aq_depth; d <= 4; d++) L.off[d] = L.total;
+  CK(h->dDoubles.reserve(L.total));
+  CK(launch_aq_activity(h->dCur.p, h->curStride, W, H, L, h->dDoubles.p, h->sMain, &h->launches));
+  std::vector<double> act(L.total);
+  CK(cudaMemcpyAsync(act.data(), h->dDoubles.p, (size_t)L.total * sizeof(double), cudaMemcpyDeviceToHost, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  for (int d = 0; d < max_aq_depth; d++) {
+    const int n = L.off[d + 1] - L.off[d];
+    if (activity && activity[d]) memcpy(activity[d], act.data() + L.off[d], (size_t)n * sizeof(double));
+    if (avg_activity) {          // dSumAct accumulates in raster order (TEncPreanalyzer.cpp:132): a sequential double sum, kept on the host
+      double sum = 0.0;
+      for (int i = 0; i < n; i++) sum += act[L.off[d] + i];
+      avg_activity[d] = sum / (double)(unsigned)n;
+    }
+  }
   flush_launches(h);
   return CUCD_OK;
 }

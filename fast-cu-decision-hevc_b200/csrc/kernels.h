@@ -46,6 +46,13 @@ cudaError_t launch_feature_obf(const FeaturePlanes& fp, int nPics, const int32_t
 // source-only DC-less 8x8 Hadamard cost per CTU: ctuHad[pic][ctusPerPic]
 cudaError_t launch_ctu_src_had(const FeaturePlanes& fp, int nPics, int32_t* ctuHad, cudaStream_t st, int* launches);
 
+// ---- CU texture features and AQ activity (texture_kernels.cu) -----------------------------------
+struct TmvCu { int32_t x, y, log2n, pad; };
+// feat[cu][5][26] doubles (getTMVFeature, tools_YS.cpp:1682-1839)
+cudaError_t launch_tmv_features(const int16_t* org, int stride, const TmvCu* cus, int nCu, double* feat, cudaStream_t st, int* launches);
+struct AqLayers { int count, total; int part[4]; int off[5]; };   // layer d: units of part[d] samples, results at out[off[d]..off[d+1])
+cudaError_t launch_aq_activity(const int16_t* org, int stride, int W, int H, const AqLayers& layers, double* out, cudaStream_t st, int* launches);
+
 // ---- integer-ME SAD surfaces (me_kernels.cu) ---------------------------------------------------
 struct MeJob {
   int32_t curOff;      // sample offset of the PU's top-left inside the current picture plane

@@ -150,6 +150,25 @@ int cucd_set_cur_picture(cucd_handle* h, const int16_t* orgY, int stride);
 int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut);
 
 /* ------------------------------------------------------------------------------------------------
+ * CU texture features and AQ activity of the picture given to cucd_set_cur_picture.
+ * cucd_tmv_features  replaces getTMVFeature(rpcBestCU) (tools_YS.cpp:1682-1839, call site TEncCu.cpp:1558-1570):
+ *                    feat[i*130 + f*26 + k] = m_adFeature[f][k] of CU i - five 3x3 directional planes (original,
+ *                    horizontal, vertical, diagonal, anti-diagonal difference), mean and mean absolute deviation
+ *                    over whole / halves / triangles / quadrants, as doubles, quirks of the reference included.
+ * cucd_aq_activity   replaces TEncPreanalyzer::xPreanalyze (TEncPreanalyzer.cpp:64-139): for AQ layer d (units of
+ *                    ctu_size >> d samples, TEncPic.cpp:128-137) activity[d][unit] = TEncQPAdaptationUnit::getActivity()
+ *                    in raster order (ceil(W/unit) x ceil(H/unit); activity[d] may be NULL) and
+ *                    avg_activity[d] = TEncPicQPAdaptationLayer::getAvgActivity().  max_aq_depth = 1..4.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int x, y;                  /* CU position in luma samples, multiples of the CU size */
+  int log2_size;             /* 3..6 */
+} cucd_cu_desc;
+#define CUCD_TMV_FEATURES (5 * 26)
+int cucd_tmv_features(cucd_handle* h, int nCU, const cucd_cu_desc* cus, double* feat);
+int cucd_aq_activity(cucd_handle* h, int max_aq_depth, double* const* activity, double* avg_activity);
+
+/* ------------------------------------------------------------------------------------------------
  * Device-resident variants (inputs already in HBM, outputs stay in HBM): what a caller that keeps
  * pictures on the GPU uses, and what bench.py times for the kernel-only figure.  Pointers are
  * device pointers; `stream` is a cudaStream_t (NULL = default stream).  No host synchronisation.

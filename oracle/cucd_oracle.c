@@ -406,3 +406,90 @@ void oracle_ctu_src_had(const int16_t* org, int os, int W, int H, int32_t* perCt
     perCtu[cy * wc + cx] = sum;
   }
 }
+
+/* ---------------------------------------------------------------------------------------------------
+ * a12: TMVFeature / getTMVFeature (tools_YS.cpp:1659-1839, tools_YS.h:99-127).
+ * Five 3x3 masks applied INSIDE the CU (the one-sample ring of every filtered plane stays 0, :1659-1672),
+ * then for each plane 13 regions: mean = integer sum / rows / cols as double (tools_YS.h:106-115), "variance" =
+ * mean of |(Int)(sample - mean)| (:117-126).  The four triangle entries keep the reference's quirks: the divisor
+ * is N*N>>1 (not the triangle's sample count) and the deviation loop ASSIGNS instead of accumulating, so only the
+ * last visited sample - always a ring sample, i.e. 0 - contributes (:1757-1816).
+ * ------------------------------------------------------------------------------------------------- */
+static double tmv_mean(const int16_t* b, int n, int i0, int i1, int j0, int j1) {
+  int sum = 0, i, j;
+  for (i = i0; i < i1; i++) for (j = j0; j < j1; j++) sum += b[i * n + j];
+  return ((double)sum) / (i1 - i0) / (j1 - j0);
+}
+static double tmv_dev(const int16_t* b, double mean, int n, int i0, int i1, int j0, int j1) {
+  int sum = 0, i, j;
+  for (i = i0; i < i1; i++) for (j = j0; j < j1; j++) { const int t = (int)(b[i * n + j] - mean); sum += t > 0 ? t : -t; }
+  return ((double)sum) / (i1 - i0) / (j1 - j0);
+}
+void oracle_tmv_features(const int16_t* cu, int stride, int n, double* feat) {
+  static const int mask[5][9] = {{0, 0, 0, 0, 1, 0, 0, 0, 0}, {0, 0, 0, 1, 0, -1, 0, 0, 0}, {0, 1, 0, 0, 0, 0, 0, -1, 0},
+                                 {0, 0, 1, 0, 0, 0, -1, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0, -1}};
+  int16_t* f = (int16_t*)malloc((size_t)n * n * sizeof(int16_t));
+  const int h = n >> 1;
+  const unsigned tri = ((unsigned)n * (unsigned)n) >> 1;
+  int k, x, y, i, j;
+  for (k = 0; k < 5; k++) {
+    double* d = feat + k * 26;
+    double m, v;
+    memset(f, 0, (size_t)n * n * sizeof(int16_t));
+    for (y = 1; y < n - 1; y++) for (x = 1; x < n - 1; x++)
+      for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) f[y * n + x] = (int16_t)(f[y * n + x] + mask[k][i * 3 + j] * cu[(y - 1 + i) * stride + (x - 1 + j)]);
+    m = tmv_mean(f, n, 0, n, 0, n); d[0] = m; d[1] = tmv_dev(f, m, n, 0, n, 0, n);
+    m = tmv_mean(f, n, 0, h, 0, n); d[2] = m; d[4] = tmv_dev(f, m, n, 0, h, 0, n);
+    m = tmv_mean(f, n, h, n, 0, n); d[3] = m; d[5] = tmv_dev(f, m, n, h, n, 0, n);
+    m = tmv_mean(f, n, 0, n, 0, h); d[6] = m; d[8] = tmv_dev(f, m, n, 0, n, 0, h);
+    m = tmv_mean(f, n, 0, n, h, n); d[7] = m; d[9] = tmv_dev(f, m, n, 0, n, h, n);
+#define TRI(JLO, JHI, MI, VI)                                                                      \
+    m = 0; for (i = 0; i < n; i++) for (j = (JLO); j < (JHI); j++) m += f[i * n + j];              \
+    m /= tri; d[MI] = m; v = 0;                                                                    \
+    for (i = 0; i < n; i++) for (j = (JLO); j < (JHI); j++) { const int t = (int)(f[i * n + j] - m); v = t > 0 ? t : -t; } \
+    v /= tri; d[VI] = v;
+    TRI(0, n - i, 10, 12)
+    TRI(n - i - 1, n, 11, 13)
+    TRI(i, n, 14, 16)
+    TRI(0, i + 1, 15, 17)
+#undef TRI
+    m = tmv_mean(f, n, 0, h, 0, h); d[18] = m; d[22] = tmv_dev(f, m, n, 0, h, 0, h);
+    m = tmv_mean(f, n, 0, h, h, n); d[19] = m; d[23] = tmv_dev(f, m, n, 0, h, h, n);
+    m = tmv_mean(f, n, h, n, 0, n); d[20] = m; d[24] = tmv_dev(f, m, n, h, n, 0, n);       /* sic: columns 0..n (:1830-1832) */
+    m = tmv_mean(f, n, h, n, h, n); d[21] = m; d[25] = tmv_dev(f, m, n, h, n, h, n);
+  }
+  free(f);
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * a13: TEncPreanalyzer::xPreanalyze (TEncPreanalyzer.cpp:64-139) for ONE AQ layer: units of part x part samples
+ * (clipped at the picture edge), four quadrants split at half of the CLIPPED unit size, activity = 1 + min variance
+ * where both moments are divided by the pixel count of the whole unit (:128-131).  Returns the layer average (:137).
+ * activity: ceil(W/part) x ceil(H/part), raster order.
+ * ------------------------------------------------------------------------------------------------- */
+double oracle_aq_activity(const int16_t* org, int stride, int W, int H, int part, double* activity) {
+  const int nw = (W + part - 1) / part, nh = (H + part - 1) / part;
+  double sumAct = 0.0;
+  int ux, uy, q;
+  for (uy = 0; uy < nh; uy++) for (ux = 0; ux < nw; ux++) {
+    const int x0 = ux * part, y0 = uy * part;
+    const int w = W - x0 < part ? W - x0 : part, h = H - y0 < part ? H - y0 : part;
+    uint64_t s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    unsigned npix = 0;
+    double minVar = 1.7976931348623157e308;
+    int bx, by;
+    for (by = 0; by < h; by++) for (bx = 0; bx < w; bx++, npix++) {
+      const int p = org[(y0 + by) * stride + x0 + bx];
+      q = (by < (h >> 1) ? 0 : 2) + (bx < (w >> 1) ? 0 : 1);
+      s[q] += (uint64_t)(int64_t)p; ss[q] += (uint64_t)(int64_t)(p * p);
+    }
+    for (q = 0; q < 4; q++) {
+      const double avg = (double)s[q] / npix;
+      const double var = (double)ss[q] / npix - avg * avg;
+      if (var < minVar) minVar = var;
+    }
+    activity[uy * nw + ux] = 1.0 + minVar;
+    sumAct += 1.0 + minVar;
+  }
+  return sumAct / (double)(unsigned)(nw * nh);
+}

@@ -60,6 +60,10 @@ void oracle_outlier_frame(int bitDepth, const int16_t* org, int orgStride, int W
 void oracle_cu_sums(const int16_t* obf, int W, int H, int depth, int32_t* numObf, int32_t* nOutlier);
 /* TEncCu.cpp:1780-1893: per CTU sum of DC-less 8x8 source Hadamard costs (whole 8x8 blocks inside the picture) */
 void oracle_ctu_src_had(const int16_t* org, int orgStride, int W, int H, int32_t* perCtu);
+/* tools_YS.cpp:1659-1839 (getTMVFeature): feat[5][26] of one n x n CU (n = 8..64) */
+void oracle_tmv_features(const int16_t* cu, int stride, int n, double* feat);
+/* TEncPreanalyzer.cpp:64-139 for one AQ layer of part x part units; activity ceil(W/part) x ceil(H/part); returns the average */
+double oracle_aq_activity(const int16_t* org, int stride, int W, int H, int part, double* activity);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,8 @@
  *   TComRdCost::setDistParam + DistFunc (xGetHADs / xGetSAD*)  TComRdCost.cpp:306-431,465-1604
  *   TEncSlice::getOutlierWithDCT (+ partialButterfly, TCMprocessOneSequence) TEncSlice.cpp:55-392,878-1173
  *   xCalcHADs8x8_ISlice             TEncCu.cpp:1780-1872
+ *   getTMVFeature (+ T3x3Filter, TMVFeature)  tools_YS.cpp:1659-1839   (on a TComDataCU shell carrying position, size, picture)
+ *   TEncPreanalyzer::xPreanalyze    TEncPreanalyzer.cpp:64-139         (on a TEncPic shell carrying the source plane + AQ layers)
  * What the driver has to restate because the reference only has it inline in functions that need a
  * live TComDataCU/TComTU/TComPic (all three restatements are pinned by the encoder KAT dumps in
  * tests/golden/, which come from the reference's real call sites):
@@ -49,6 +51,10 @@
 #include "TLibCommon/TComPrediction.h"
 #include "TLibCommon/TComRdCost.h"
 #include "TLibEncoder/TEncSlice.h"
+#include "TLibEncoder/TEncPic.h"
+#include "TLibEncoder/TEncPreanalyzer.h"
+#include "TLibCommon/TComDataCU.h"
+#include "TLibCommon/tools_YS.h"
 #undef private
 #undef protected
 
@@ -326,6 +332,52 @@ int hmref_rmd_frame(int bitDepth, int strongSmoothing, const int16_t* org, int o
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; t++) th.emplace_back(body);
   for (auto& t : th) t.join();
+  return 0;
+}
+
+/* The reference's getTMVFeature on the CU at (x,y) of size n inside a W x H source plane: feat[5][26]. */
+int hmref_tmv_features(const int16_t* org, int orgStride, int W, int H, int x, int y, int n, double* feat) {
+  set_globals(8);
+  TComPicYuv yOrg;
+  yOrg.create(W, H, CHROMA_420, 64, 64, 4);
+  for (int r = 0; r < H; r++) memcpy(yOrg.getAddr(COMPONENT_Y) + r * yOrg.getStride(COMPONENT_Y), org + r * orgStride, W * sizeof(Pel));
+  TComPic* pic = new TComPic;
+  pic->m_apcPicYuv[TComPic::PIC_YUV_ORG] = &yOrg;
+  TComDataCU* cu = new TComDataCU;     /* shell: only the members getTMVFeature reads */
+  UChar size = (UChar)n;
+  cu->m_pcPic = pic; cu->m_uiCUPelX = x; cu->m_uiCUPelY = y; cu->m_puhWidth = &size; cu->m_puhHeight = &size;
+  TMVFeature* f = getTMVFeature(cu);
+  memcpy(feat, f->m_adFeature, sizeof(double) * 5 * 26);
+  delete f;
+  cu->m_puhWidth = 0; cu->m_puhHeight = 0; cu->m_pcPic = 0;
+  pic->m_apcPicYuv[TComPic::PIC_YUV_ORG] = 0;
+  yOrg.destroy();   /* the TComPic / TComDataCU shells are leaked on purpose (destructors assume create()) */
+  return 0;
+}
+
+/* The reference's TEncPreanalyzer::xPreanalyze with maxAQDepth layers (unit = 64 >> d); activity[d] = ceil(W/unit)*ceil(H/unit)
+ * doubles in raster order (NULL = skip), avg[d] = the layer's average activity. */
+int hmref_aq_activity(const int16_t* org, int orgStride, int W, int H, int maxAQDepth, double* const* activity, double* avg) {
+  set_globals(8);
+  TComPicYuv yOrg;
+  yOrg.create(W, H, CHROMA_420, 64, 64, 4);
+  for (int r = 0; r < H; r++) memcpy(yOrg.getAddr(COMPONENT_Y) + r * yOrg.getStride(COMPONENT_Y), org + r * orgStride, W * sizeof(Pel));
+  TEncPic* pic = new TEncPic;
+  pic->m_apcPicYuv[TComPic::PIC_YUV_ORG] = &yOrg;
+  pic->m_uiMaxAQDepth = maxAQDepth;
+  pic->m_acAQLayer = new TEncPicQPAdaptationLayer[maxAQDepth];          /* what TEncPic::create does, TEncPic.cpp:128-137 */
+  for (int d = 0; d < maxAQDepth; d++) pic->m_acAQLayer[d].create(W, H, 64 >> d, 64 >> d);
+  TEncPreanalyzer pre;
+  pre.xPreanalyze(pic);
+  for (int d = 0; d < maxAQDepth; d++) {
+    TEncPicQPAdaptationLayer* l = pic->getAQLayer(d);
+    const int n = l->getNumAQPartInWidth() * l->getNumAQPartInHeight();
+    if (activity && activity[d]) for (int i = 0; i < n; i++) activity[d][i] = l->getQPAdaptationUnit()[i].getActivity();
+    if (avg) avg[d] = l->getAvgActivity();
+  }
+  delete[] pic->m_acAQLayer; pic->m_acAQLayer = 0; pic->m_uiMaxAQDepth = 0;
+  pic->m_apcPicYuv[TComPic::PIC_YUV_ORG] = 0;
+  yOrg.destroy();
   return 0;
 }
 

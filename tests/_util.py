@@ -42,6 +42,7 @@ def load_oracle():
     lib.oracle_satd.restype = C.c_uint32
     lib.oracle_sad.restype = C.c_uint32
     lib.oracle_tcm_yc.restype = C.c_double
+    lib.oracle_aq_activity.restype = C.c_double
     return lib
 
 
@@ -143,4 +144,35 @@ def oracle_ctu_src_had(lib, org):
     org = np.ascontiguousarray(org)
     out = np.zeros(((W + 63) // 64) * ((H + 63) // 64), np.int32)
     lib.oracle_ctu_src_had(P(org, i16p), W, W, H, P(out, i32p))
+    return out
+
+
+def oracle_tmv_features(lib, org, cus):
+    """cus: (x, y, log2_size) -> (nCU, 5, 26) float64 of oracle_tmv_features."""
+    H, W = org.shape
+    org = np.ascontiguousarray(org)
+    out = np.zeros((len(cus), 5, 26), np.float64)
+    for i, (x, y, l) in enumerate(cus):
+        lib.oracle_tmv_features(C.c_void_p(org.ctypes.data + 2 * (y * W + x)), W, 1 << l, C.c_void_p(out[i].ctypes.data))
+    return out
+
+
+def oracle_aq_activity(lib, org, max_aq_depth):
+    H, W = org.shape
+    org = np.ascontiguousarray(org)
+    acts, avg = [], np.zeros(max_aq_depth, np.float64)
+    for d in range(max_aq_depth):
+        u = 64 >> d
+        a = np.zeros(((H + u - 1) // u, (W + u - 1) // u), np.float64)
+        avg[d] = lib.oracle_aq_activity(P(org, i16p), W, W, H, u, P(a, f64p))
+        acts.append(a)
+    return acts, avg
+
+
+def all_cus(W, H, depths=(0, 1, 2, 3)):
+    """every whole CU of the picture at the given depths as (x, y, log2_size)"""
+    out = []
+    for d in depths:
+        n = 64 >> d
+        out += [(x, y, 6 - d) for y in range(0, H - n + 1, n) for x in range(0, W - n + 1, n)]
     return out

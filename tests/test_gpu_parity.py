@@ -328,3 +328,42 @@ def test_rmd_queue_coalesces_concurrent_requests(cucd, oracle):
                 oracle.oracle_rmd_pu(8, n, 1, P(o, i16p), n, P(b, i16p), P(want, u32p))
                 assert np.array_equal(got[i], want)
                 oo += n * n; bo += 4 * n + 1
+
+
+# ---- a12 / a13: CU texture features and AQ activity (doubles, bit-exact) ---------------------------
+@pytest.mark.parametrize("tag", ["a8", "b10"])
+def test_texture_features_vs_reference_golden(cucd, tag):
+    g = golden("texture.npz")
+    W, H, bd = [int(v) for v in g[f"{tag}_meta"]]
+    with cucd.Engine(W, H, bit_depth=bd) as eng:
+        eng.set_cur_picture(g[f"{tag}_org"])
+        got = eng.tmv_features([tuple(int(v) for v in c) for c in g[f"{tag}_cus"]])
+        assert np.array_equal(got, g[f"{tag}_tmv"])
+        acts, avg = eng.aq_activity(4)
+        for d in range(4):
+            assert np.array_equal(acts[d], g[f"{tag}_act{d}"])
+        assert np.array_equal(avg, g[f"{tag}_avg"])
+        assert eng.tmv_features([]).shape == (0, 5, 26)
+        with pytest.raises(cucd.CucdError):
+            eng.tmv_features([(4, 0, 3)])            # not aligned to the CU size
+        with pytest.raises(cucd.CucdError):
+            eng.aq_activity(5)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_texture_features_vs_oracle_1080p_rows(cucd, oracle, bd):
+    from _util import all_cus, oracle_aq_activity, oracle_tmv_features
+    W, H = 1920, 1080
+    org = textured_plane(W, H, bd, seed=77)
+    with cucd.Engine(W, H, bit_depth=bd) as eng:
+        eng.set_cur_picture(org)
+        cus = all_cus(W, H)
+        got = eng.tmv_features(cus)                   # all 43 k whole CUs of the picture in one launch
+        sel = np.random.default_rng(1).choice(len(cus), 600, replace=False)
+        want = oracle_tmv_features(oracle, org, [cus[i] for i in sel])
+        assert np.array_equal(got[sel], want)
+        acts, avg = eng.aq_activity(4)
+        wacts, wavg = oracle_aq_activity(oracle, org, 4)
+        for a, b in zip(acts, wacts):
+            assert np.array_equal(a, b)               # includes the clipped 56-row units of the last CTU row
+        assert np.array_equal(avg, wavg)

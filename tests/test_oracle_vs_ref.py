@@ -112,3 +112,27 @@ def test_rmd_frame_enumeration(oracle, hmref):
     b = np.zeros_like(a)
     hmref.hmref_rmd_frame(bd, 1, P(org, i16p), W, P(rec, i16p), W, W, H, 0, a.shape[0], 2, P(b, u32p))
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("bd,W,H", [(8, 200, 136), (10, 136, 72), (8, 64, 64)])
+def test_tmv_features_and_aq_activity_match_reference(oracle, hmref, bd, W, H):
+    """a12 / a13: the oracle against the reference's own getTMVFeature and TEncPreanalyzer::xPreanalyze (doubles, bit-exact)."""
+    import ctypes as C
+    from _util import all_cus, oracle_aq_activity, oracle_tmv_features, f64p
+    org = textured_plane(W, H, bd, seed=3)
+    # extreme content too: the quirky triangle entries and the truncation toward zero depend on signs
+    ext = np.random.default_rng(5).choice([0, (1 << bd) - 1], size=(H, W)).astype(np.int16)
+    for plane in (org, ext):
+        cus = all_cus(W, H)[::3]
+        want = np.zeros((len(cus), 5, 26))
+        for i, (x, y, l) in enumerate(cus):
+            hmref.hmref_tmv_features(P(plane, i16p), W, W, H, x, y, 1 << l, C.c_void_p(want[i].ctypes.data))
+        assert np.array_equal(oracle_tmv_features(oracle, plane, cus), want)
+        acts, avg = oracle_aq_activity(oracle, plane, 4)
+        ref = [np.zeros_like(a) for a in acts]
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in ref])
+        ravg = np.zeros(4)
+        hmref.hmref_aq_activity(P(plane, i16p), W, W, H, 4, ptrs, P(ravg, f64p))
+        for a, b in zip(acts, ref):
+            assert np.array_equal(a, b)
+        assert np.array_equal(avg, ravg)
