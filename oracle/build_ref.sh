@@ -79,6 +79,20 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
    "    cucd_hook_me(m_cDistParam.pOrg, m_cDistParam.iStrideOrg, m_cDistParam.pCur, m_cDistParam.iStrideCur, m_cDistParam.iCols, m_cDistParam.iRows,\n"
    "                 m_cDistParam.iSubShift, m_cDistParam.bitDepth, iSearchX, iSearchY, m_cDistParam.DistFunc(&m_cDistParam));\n", "before"),
 ])
+# intra luma TU coding (TEncSearch.cpp:1092-1387)
+patch("Lib/TLibCommon/TComTrQuant.h", [
+  ("  TCoeff* m_plTempCoeff;\n", "public:\n  TCoeff* cucdTempCoeff() { return m_plTempCoeff; }\nprotected:\n", "after"),
+])
+patch("Lib/TLibEncoder/TEncSearch.cpp", [
+  ("  //===== get residual signal =====\n",
+   "  cucd_hook_tu_pred(bIsLuma, g_iPOC, pcCU->getCUPelX() + blkX, pcCU->getCUPelY() + blkY, uiWidth, uiChFinalMode, g_bitDepth[chType], useTransformSkip, default0Save1Load2 == 2,\n"
+   "                    m_piYuvExt[compID][PRED_BUF_UNFILTERED], piPred, piOrg, uiStride);\n", "before"),
+  ("  //--- inverse transform ---\n",
+   "  if (bIsLuma) cucd_hook_tu_coeff(pcCU->getQP(0), pcCU->getSlice()->getSliceType() == I_SLICE, pcCU->getSlice()->getPPS()->getSignHideFlag(),\n"
+   "                                  useTransformSkip ? m_pcEncCfg->getUseRDOQTS() : m_pcEncCfg->getUseRDOQ(), m_pcTrQuant->cucdTempCoeff(), pcCoeff, uiAbsSum);\n", "before"),
+  ("  //===== update distortion =====\n  ruiDist += m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID);\n",
+   "  if (bIsLuma) cucd_hook_tu_end(piReco, uiStride, m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID));\n", "after"),
+])
 # outlier picture pass (TEncSlice.cpp:878-1173)
 patch("Lib/TLibEncoder/TEncSlice.cpp", [
   ("\t\tdelete[] Yc;\n", "\t\tcucd_hook_obf_yc(Yc, FrequencySize);\n", "before"),

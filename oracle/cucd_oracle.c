@@ -493,3 +493,201 @@ double oracle_aq_activity(const int16_t* org, int stride, int W, int H, int part
   }
   return sumAct / (double)(unsigned)(nw * nh);
 }
+
+/* ===================================================================================================
+ * SURVEY.md 8f.2 - intra luma TU coding: xIntraCodingTUBlock TEncSearch.cpp:1092-1387
+ * =================================================================================================== */
+
+/* The HEVC core transform matrices g_aiT4/8/16/32 (TComRom.cpp:356-460, 6-bit precision): row k of the N-point matrix is
+ * round(64*sqrt(2)*cos(k(2n+1)pi/2N)) with the standard's hand-tuned values; all of them are sub-sampled rows of the
+ * 32-point matrix, whose 31 distinct magnitudes are c[m] ~ 64*sqrt(2)*cos(m*pi/64). */
+static const int kDctC[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                              61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0};
+int oracle_dct_coef(int n, int k, int x) {         /* g_aiT<n>[TRANSFORM_FORWARD][k][x] */
+  int a;
+  if (k == 0) return 64;
+  a = (k * (32 / n) * (2 * x + 1)) & 127;           /* angle in units of pi/64 */
+  if (a > 64) a = 128 - a;
+  return a <= 32 ? kDctC[a] : -kDctC[64 - a];
+}
+static const int kDst4[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};   /* TComRom.cpp:343-349 */
+static int tr_coef(int n, int useDST, int k, int x) { return useDST ? kDst4[k][x] : oracle_dct_coef(n, k, x); }
+
+/* TComTrQuant::xT -> xTrMxN (TComTrQuant.cpp:860-919, 1857-1882): the partial butterflies are exact integer matrix products,
+ * dst[k*line + j] = (sum_x T[k][x] * src[j*N + x] + add) >> shift, twice (rows, then columns) */
+void oracle_fwd_transform(int bitDepth, int n, int useDST, const int16_t* resi, int stride, int32_t* coeff) {
+  const int lg = ilog2(n), shift1 = lg + bitDepth + 6 - 15, shift2 = lg + 6;
+  const int add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0, add2 = 1 << (shift2 - 1);
+  int32_t tmp[32 * 32];
+  int j, k, x;
+  for (j = 0; j < n; j++) for (k = 0; k < n; k++) {
+    int32_t s = 0;
+    for (x = 0; x < n; x++) s += tr_coef(n, useDST, k, x) * resi[j * stride + x];
+    tmp[k * n + j] = (s + add1) >> shift1;
+  }
+  for (j = 0; j < n; j++) for (k = 0; k < n; k++) {
+    int32_t s = 0;
+    for (x = 0; x < n; x++) s += tr_coef(n, useDST, k, x) * tmp[j * n + x];
+    coeff[k * n + j] = (s + add2) >> shift2;
+  }
+}
+/* TComTrQuant::xIT -> xITrMxN (:927-985, 1892-1924): columns first (clip to 16 bit), then rows (clip to Pel) */
+void oracle_inv_transform(int bitDepth, int n, int useDST, const int32_t* coeff, int16_t* resi, int stride) {
+  const int shift1 = 7, shift2 = 20 - bitDepth;
+  int32_t tmp[32 * 32];
+  int j, k, x;
+  for (j = 0; j < n; j++) for (x = 0; x < n; x++) {
+    int32_t s = 0;
+    for (k = 0; k < n; k++) s += tr_coef(n, useDST, k, x) * coeff[k * n + j];
+    tmp[j * n + x] = clip3(-32768, 32767, (s + (1 << (shift1 - 1))) >> shift1);
+  }
+  for (j = 0; j < n; j++) for (x = 0; x < n; x++) {
+    int32_t s = 0;
+    for (k = 0; k < n; k++) s += tr_coef(n, useDST, k, x) * tmp[k * n + j];
+    resi[j * stride + x] = (int16_t)clip3(-32768, 32767, (s + (1 << (shift2 - 1))) >> shift2);
+  }
+}
+/* xTransformSkip / xITransformSkip (:1933-2031), no rotation, bit depths <= 10 (shift = 15 - bd - log2 n >= 0) */
+void oracle_transform_skip(int bitDepth, int n, const int16_t* resi, int stride, int32_t* coeff) {
+  const int sh = 15 - bitDepth - ilog2(n); int x, y;
+  for (y = 0; y < n; y++) for (x = 0; x < n; x++) coeff[y * n + x] = (int32_t)resi[y * stride + x] << sh;
+}
+void oracle_inv_transform_skip(int bitDepth, int n, const int32_t* coeff, int16_t* resi, int stride) {
+  const int sh = 15 - bitDepth - ilog2(n), off = sh == 0 ? 0 : 1 << (sh - 1); int x, y;
+  for (y = 0; y < n; y++) for (x = 0; x < n; x++) resi[y * stride + x] = (int16_t)((coeff[y * n + x] + off) >> sh);
+}
+
+/* TComDataCU::getCoefScanIdx (TComDataCU.cpp:3356-3410) for intra luma: 0 diagonal, 1 horizontal, 2 vertical */
+int oracle_scan_idx(int n, int mode) {
+  if (n > 8) return 0;
+  if (iabs(mode - 26) <= 4) return 1;
+  if (iabs(mode - 10) <= 4) return 2;
+  return 0;
+}
+/* g_scanOrder[SCAN_GROUPED_4x4][scanIdx][log2 n][log2 n] (TComRom.cpp:53-228): 4x4 coefficient groups visited in the
+ * scan's order, the same scan inside each group; scan[pos] = raster index */
+static void scan_next(int type, int w, int h, int* line, int* col) {
+  if (type == 0) {
+    if (*col == w - 1 || *line == 0) { *line += *col + 1; *col = 0; if (*line >= h) { *col += *line - (h - 1); *line = h - 1; } }
+    else { (*col)++; (*line)--; }
+  } else if (type == 1) { if (*col == w - 1) { (*line)++; *col = 0; } else (*col)++; }
+  else { if (*line == h - 1) { (*col)++; *line = 0; } else (*line)++; }
+}
+void oracle_scan_order(int scanIdx, int n, uint16_t* scan) {
+  const int g = n >> 2;
+  int gl = 0, gc = 0, gi, p;
+  for (gi = 0; gi < g * g; gi++) {
+    int l = 0, c = 0;
+    for (p = 0; p < 16; p++) { scan[gi * 16 + p] = (uint16_t)((gl * 4 + l) * n + gc * 4 + c); scan_next(scanIdx, 4, 4, &l, &c); }
+    scan_next(scanIdx, g, g, &gl, &gc);
+  }
+}
+
+static const int kQuantScales[6] = {26214, 23302, 20560, 18396, 16384, 14564};   /* TComRom.cpp:328-336 */
+static const int kInvQuantScales[6] = {40, 45, 51, 57, 64, 72};
+
+/* TComTrQuant::xQuant without RDOQ (:1126-1240, flat scaling) + signBitHidingHDQ (:991-1123). qp = CU luma QP. Returns uiAbsSum. */
+int oracle_quant(int bitDepth, int n, int qp, int intraSlice, int signHiding, int scanIdx, const int32_t* coef, int32_t* level) {
+  const int baseQp = qp + 6 * (bitDepth - 8), per = baseQp / 6, rem = baseQp % 6;
+  const int tshift = 15 - bitDepth - ilog2(n), qbits = 14 + per + tshift;
+  const int64_t add = (int64_t)(intraSlice ? 171 : 85) << (qbits - 9);
+  const int scale = kQuantScales[rem], total = n * n;
+  int32_t deltaU[32 * 32];
+  uint16_t scan[32 * 32];
+  int absSum = 0, i;
+  for (i = 0; i < total; i++) {
+    const int64_t t = (int64_t)iabs(coef[i]) * scale;
+    const int32_t q = (int32_t)((t + add) >> qbits);
+    deltaU[i] = (int32_t)((t - ((int64_t)q << qbits)) >> (qbits - 8));
+    absSum += q;
+    level[i] = clip3(-32768, 32767, coef[i] < 0 ? -q : q);
+  }
+  if (signHiding && absSum >= 2) {
+    int lastCG = -1, subSet;
+    oracle_scan_order(scanIdx, n, scan);
+    for (subSet = (total - 1) >> 4; subSet >= 0; subSet--) {
+      const int subPos = subSet << 4;
+      int firstNZ = 16, lastNZ = -1, sum = 0, k;
+      for (k = 15; k >= 0; k--) if (level[scan[k + subPos]]) { lastNZ = k; break; }
+      for (k = 0; k < 16; k++) if (level[scan[k + subPos]]) { firstNZ = k; break; }
+      for (k = firstNZ; k <= lastNZ; k++) sum += level[scan[k + subPos]];
+      if (lastNZ >= 0 && lastCG == -1) lastCG = 1;
+      if (lastNZ - firstNZ >= 4) {
+        const int signbit = level[scan[subPos + firstNZ]] > 0 ? 0 : 1;
+        if (signbit != (sum & 1)) {
+          int32_t curCost = 0x7fffffff, minCostInc = 0x7fffffff;
+          int minPos = -1, finalChange = 0, curChange = 0;
+          for (k = (lastCG == 1 ? lastNZ : 15); k >= 0; k--) {
+            const int blk = scan[k + subPos];
+            if (level[blk] != 0) {
+              if (deltaU[blk] > 0) { curCost = -deltaU[blk]; curChange = 1; }
+              else if (k == firstNZ && iabs(level[blk]) == 1) curCost = 0x7fffffff;
+              else { curCost = deltaU[blk]; curChange = -1; }
+            } else if (k < firstNZ) {
+              const int thisSign = coef[blk] >= 0 ? 0 : 1;
+              if (thisSign != signbit) curCost = 0x7fffffff;
+              else { curCost = -deltaU[blk]; curChange = 1; }
+            } else { curCost = -deltaU[blk]; curChange = 1; }
+            if (curCost < minCostInc) { minCostInc = curCost; finalChange = curChange; minPos = blk; }
+          }
+          if (level[minPos] == 32767 || level[minPos] == -32768) finalChange = -1;
+          if (coef[minPos] >= 0) level[minPos] += finalChange; else level[minPos] -= finalChange;
+        }
+      }
+      if (lastCG == 1) lastCG = 0;
+    }
+  }
+  return absSum;
+}
+/* TComTrQuant::xDeQuant, flat scaling (:1242-1352) */
+void oracle_dequant(int bitDepth, int n, int qp, const int32_t* level, int32_t* coef) {
+  const int baseQp = qp + 6 * (bitDepth - 8), per = baseQp / 6, rem = baseQp % 6;
+  const int tshift = 15 - bitDepth - ilog2(n), rightShift = 6 - (tshift + per), scale = kInvQuantScales[rem];
+  const int bitsIn = 16 < 32 + rightShift - 7 ? 16 : 32 + rightShift - 7;
+  const int inMin = -(1 << (bitsIn - 1)), inMax = (1 << (bitsIn - 1)) - 1;
+  int i;
+  for (i = 0; i < n * n; i++) {
+    const int32_t q = clip3(inMin, inMax, level[i]);
+    const int32_t v = rightShift > 0 ? (q * scale + (1 << (rightShift - 1))) >> rightShift : (int32_t)((uint32_t)(q * scale) << -rightShift);
+    coef[i] = clip3(-32768, 32767, v);
+  }
+}
+/* TComRdCost::xGetSSE* (TComRdCost.cpp:970-1315) */
+uint32_t oracle_sse(int bitDepth, const int16_t* org, int os, const int16_t* cur, int cs, int w, int h) {
+  const int sh = (bitDepth - 8) << 1; uint32_t sum = 0; int x, y;
+  for (y = 0; y < h; y++) for (x = 0; x < w; x++) { const int d = org[y * os + x] - cur[y * cs + x]; sum += (uint32_t)((d * d) >> sh); }
+  return sum;
+}
+
+/* One luma TU through xIntraCodingTUBlock. stage: 0 = forward only (prediction + residual + transform; `coef` and `pred` out),
+ * 1 = whole chain with the plain quantiser (level/reco/dist/absSum out), 2 = reconstruction from GIVEN levels (level in). */
+void oracle_intra_tu(int bitDepth, int n, int mode, int qp, int transformSkip, int strongSmoothing, int intraSlice, int signHiding, int stage,
+                     const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
+                     uint32_t* dist, int32_t* absSum) {
+  int16_t fil[4 * 32 + 1], p[32 * 32], resi[32 * 32];
+  int32_t c[32 * 32], deq[32 * 32];
+  const int useDST = n == 4;                                            /* TComTU::useDST: intra luma 4x4 */
+  int i, x, y, sum = 0;
+  oracle_filter_border(bitDepth, n, strongSmoothing, border, fil);
+  oracle_predict(bitDepth, n, mode, border, fil, p);
+  if (pred) memcpy(pred, p, (size_t)n * n * sizeof(int16_t));
+  if (stage != 2) {
+    for (y = 0; y < n; y++) for (x = 0; x < n; x++) resi[y * n + x] = (int16_t)(org[y * orgStride + x] - p[y * n + x]);   /* :1207-1224 */
+    if (transformSkip) oracle_transform_skip(bitDepth, n, resi, n, c); else oracle_fwd_transform(bitDepth, n, useDST, resi, n, c);
+    if (coef) memcpy(coef, c, (size_t)n * n * sizeof(int32_t));
+    if (stage == 0) return;
+    sum = oracle_quant(bitDepth, n, qp, intraSlice, signHiding, oracle_scan_idx(n, mode), c, level);
+  } else {
+    for (i = 0; i < n * n; i++) sum += iabs(level[i]);                  /* only its being non-zero matters (:1271-1291) */
+  }
+  if (absSum) *absSum = sum;
+  if (sum > 0) {
+    oracle_dequant(bitDepth, n, qp, level, deq);
+    if (transformSkip) oracle_inv_transform_skip(bitDepth, n, deq, resi, n); else oracle_inv_transform(bitDepth, n, useDST, deq, resi, n);
+  } else {
+    if (stage == 1) memset(level, 0, (size_t)n * n * sizeof(int32_t));
+    memset(resi, 0, sizeof(resi));
+  }
+  for (i = 0; i < n * n; i++) reco[i] = (int16_t)clip3(0, (1 << bitDepth) - 1, p[i] + resi[i]);   /* :1360-1381 */
+  *dist = oracle_sse(bitDepth, reco, n, org, orgStride, n, n);                                     /* :1385-1386 */
+}

@@ -65,6 +65,23 @@ void oracle_tmv_features(const int16_t* cu, int stride, int n, double* feat);
 /* TEncPreanalyzer.cpp:64-139 for one AQ layer of part x part units; activity ceil(W/part) x ceil(H/part); returns the average */
 double oracle_aq_activity(const int16_t* org, int stride, int W, int H, int part, double* activity);
 
+
+/* ---- intra luma TU coding, xIntraCodingTUBlock TEncSearch.cpp:1092-1387 (n = 4..32) -------------------- */
+int  oracle_dct_coef(int n, int k, int x);                                              /* g_aiT<n>[k][x], TComRom.cpp:356-460 */
+void oracle_fwd_transform(int bitDepth, int n, int useDST, const int16_t* resi, int stride, int32_t* coeff);   /* TComTrQuant.cpp:860-919 */
+void oracle_inv_transform(int bitDepth, int n, int useDST, const int32_t* coeff, int16_t* resi, int stride);   /* :927-985 */
+void oracle_transform_skip(int bitDepth, int n, const int16_t* resi, int stride, int32_t* coeff);              /* :1933-1978 */
+void oracle_inv_transform_skip(int bitDepth, int n, const int32_t* coeff, int16_t* resi, int stride);          /* :1980-2031 */
+int  oracle_scan_idx(int n, int mode);                                                  /* TComDataCU.cpp:3356-3410; 0 diag 1 hor 2 ver */
+void oracle_scan_order(int scanIdx, int n, uint16_t* scan);                             /* TComRom.cpp:53-228, grouped 4x4 */
+int  oracle_quant(int bitDepth, int n, int qp, int intraSlice, int signHiding, int scanIdx, const int32_t* coef, int32_t* level); /* :991-1240 */
+void oracle_dequant(int bitDepth, int n, int qp, const int32_t* level, int32_t* coef);  /* :1242-1352 */
+uint32_t oracle_sse(int bitDepth, const int16_t* org, int os, const int16_t* cur, int cs, int w, int h);       /* TComRdCost.cpp:970-1315 */
+/* stage 0: prediction + residual + transform (coef, pred out); 1: whole chain with the plain quantiser; 2: reconstruction from given levels */
+void oracle_intra_tu(int bitDepth, int n, int mode, int qp, int transformSkip, int strongSmoothing, int intraSlice, int signHiding, int stage,
+                     const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
+                     uint32_t* dist, int32_t* absSum);
+
 #ifdef __cplusplus
 }
 #endif

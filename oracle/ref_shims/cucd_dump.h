@@ -10,6 +10,7 @@
  *   CUCD_DUMP_ME   : every CUCD_DUMP_ME_EVERY-th integer-ME SAD probe (TEncSearch.cpp:336-437)
  *   CUCD_DUMP_OBF  : one record per picture of the outlier feature pass (TEncSlice.cpp:878-1173)
  *   CUCD_DUMP_CU   : one record per CU visited by xCompressCU (TEncCu.cpp:589-600)
+ *   CUCD_DUMP_TU   : every CUCD_DUMP_TU_EVERY-th luma TU of xIntraCodingTUBlock (TEncSearch.cpp:1092-1387)
  */
 #ifndef CUCD_DUMP_H
 #define CUCD_DUMP_H
@@ -114,6 +115,56 @@ inline void cucd_hook_cu(int poc, int depth, int x, int y, int size, int numObf,
   if (!f) return;
   int32_t rec[7] = {poc, depth, x, y, size, numObf, nOutlier};
   fwrite(rec, 4, 7, f);
+}
+
+/* ---- intra luma TU coding: prediction -> residual -> transform/quant -> inverse -> recon -> SSE ---- */
+struct CucdTuState {
+  CucdDump out; long cnt, every; bool live;
+  int32_t hdr[16];
+  short border[4 * 64 + 1], pred[32 * 32], org[32 * 32];
+  int32_t coef[32 * 32], level[32 * 32];
+  CucdTuState() : cnt(0), every(-1), live(false) {}
+};
+inline CucdTuState& cucd_tu() { static CucdTuState s; return s; }
+/* TEncSearch.cpp:1207 - after the prediction is in piPred, before the residual */
+inline void cucd_hook_tu_pred(int isLuma, int poc, int x, int y, int n, int mode, int bitDepth, int transformSkip, int loadMode,
+                              const short* unfExt, const short* pred, const short* org, int stride) {
+  CucdTuState& s = cucd_tu();
+  s.live = false;
+  if (!isLuma || n > 32) return;
+  FILE* f = s.out.get("CUCD_DUMP_TU");
+  if (!f) return;
+  if (s.every < 0) { const char* e = getenv("CUCD_DUMP_TU_EVERY"); s.every = e ? atol(e) : 53; if (s.every < 1) s.every = 1; }
+  if ((s.cnt++ % s.every) != 0) return;
+  s.live = true;
+  s.hdr[0] = 0x55545243; s.hdr[1] = poc; s.hdr[2] = x; s.hdr[3] = y; s.hdr[4] = n; s.hdr[5] = mode; s.hdr[6] = bitDepth;
+  s.hdr[7] = transformSkip; s.hdr[8] = loadMode;
+  const int sw = 2 * n + 1;
+  for (int i = 0; i < 2 * n; i++) s.border[i] = unfExt[(2 * n - i) * sw];
+  for (int i = 0; i <= 2 * n; i++) s.border[2 * n + i] = unfExt[i];
+  for (int r = 0; r < n; r++) { memcpy(s.pred + r * n, pred + r * stride, 2 * n); memcpy(s.org + r * n, org + r * stride, 2 * n); }
+}
+/* TEncSearch.cpp:1263-1268 - right after transformNxN: m_plTempCoeff still holds the transform output */
+inline void cucd_hook_tu_coeff(int qp, int sliceIsIntra, int signHide, int rdoq, const int* tmpCoeff, const int* level, int absSum) {
+  CucdTuState& s = cucd_tu();
+  if (!s.live) return;
+  const int n = s.hdr[4];
+  s.hdr[9] = qp; s.hdr[10] = sliceIsIntra; s.hdr[11] = signHide; s.hdr[12] = rdoq; s.hdr[13] = absSum;
+  memcpy(s.coef, tmpCoeff, 4 * n * n); memcpy(s.level, level, 4 * n * n);
+}
+/* TEncSearch.cpp:1385-1386 - reconstruction done, distortion of this TU */
+inline void cucd_hook_tu_end(const short* reco, int stride, unsigned dist) {
+  CucdTuState& s = cucd_tu();
+  if (!s.live) return;
+  s.live = false;
+  FILE* f = s.out.get("CUCD_DUMP_TU");
+  const int n = s.hdr[4];
+  s.hdr[14] = (int32_t)dist; s.hdr[15] = 0;
+  fwrite(s.hdr, 4, 16, f);
+  fwrite(s.border, 2, 4 * n + 1, f);
+  fwrite(s.org, 2, n * n, f); fwrite(s.pred, 2, n * n, f);
+  fwrite(s.coef, 4, n * n, f); fwrite(s.level, 4, n * n, f);
+  for (int r = 0; r < n; r++) fwrite(reco + r * stride, 2, n, f);
 }
 #endif /* __cplusplus */
 #endif

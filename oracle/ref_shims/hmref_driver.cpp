@@ -17,6 +17,8 @@
  *   TComRdCost::setDistParam + DistFunc (xGetHADs / xGetSAD*)  TComRdCost.cpp:306-431,465-1604
  *   TEncSlice::getOutlierWithDCT (+ partialButterfly, TCMprocessOneSequence) TEncSlice.cpp:55-392,878-1173
  *   xCalcHADs8x8_ISlice             TEncCu.cpp:1780-1872
+ *   xTrMxN / xITrMxN (partial butterflies, DST)   TComTrQuant.cpp:388-985   (free functions, called as is)
+ *   TComRdCost::getDistPart -> xGetSSE*           TComRdCost.cpp:433-455, 970-1315
  *   getTMVFeature (+ T3x3Filter, TMVFeature)  tools_YS.cpp:1659-1839   (on a TComDataCU shell carrying position, size, picture)
  *   TEncPreanalyzer::xPreanalyze    TEncPreanalyzer.cpp:64-139         (on a TEncPic shell carrying the source plane + AQ layers)
  * What the driver has to restate because the reference only has it inline in functions that need a
@@ -63,6 +65,8 @@ Void fillReferenceSamples(const Int bitDepth, TComDataCU* pcCU, const Pel* piRoi
                           const UInt uiCuWidth, const UInt uiCuHeight, const UInt uiWidth, const UInt uiHeight, const Int iPicStride,
                           const ChannelType chType, const ChromaFormat chFmt);
 Int xCalcHADs8x8_ISlice(Pel* piOrg, Int iStrideOrg);
+Void xTrMxN(Int bitDepth, TCoeff* block, TCoeff* coeff, Int iWidth, Int iHeight, Bool useDST, const Int maxTrDynamicRange);
+Void xITrMxN(Int bitDepth, TCoeff* coeff, TCoeff* block, Int iWidth, Int iHeight, Bool useDST, const Int maxTrDynamicRange);
 
 namespace {
 
@@ -333,6 +337,25 @@ int hmref_rmd_frame(int bitDepth, int strongSmoothing, const int16_t* org, int o
   for (int t = 0; t < nthreads; t++) th.emplace_back(body);
   for (auto& t : th) t.join();
   return 0;
+}
+
+/* The reference's forward / inverse core transform of one n x n block (what TComTrQuant::xT / xIT call). */
+int hmref_fwd_transform(int bitDepth, int n, int useDST, const int32_t* block, int32_t* coeff) {
+  set_globals(bitDepth);
+  std::vector<TCoeff> in(block, block + n * n);
+  xTrMxN(bitDepth, in.data(), coeff, n, n, useDST != 0, 15);
+  return 0;
+}
+int hmref_inv_transform(int bitDepth, int n, int useDST, const int32_t* coeff, int32_t* block) {
+  set_globals(bitDepth);
+  std::vector<TCoeff> in(coeff, coeff + n * n);
+  xITrMxN(bitDepth, in.data(), block, n, n, useDST != 0, 15);
+  return 0;
+}
+uint32_t hmref_sse(int bitDepth, const int16_t* org, int orgStride, const int16_t* cur, int curStride, int w, int h) {
+  set_globals(bitDepth);
+  static TComRdCost rd;          /* the constructor runs init() (TComRdCost.cpp:46-49) */
+  return rd.getDistPart(bitDepth, const_cast<Pel*>(cur), curStride, const_cast<Pel*>(org), orgStride, w, h, COMPONENT_Y, DF_SSE);
 }
 
 /* The reference's getTMVFeature on the CU at (x,y) of size n inside a W x H source plane: feat[5][26]. */

@@ -176,3 +176,33 @@ def all_cus(W, H, depths=(0, 1, 2, 3)):
         n = 64 >> d
         out += [(x, y, 6 - d) for y in range(0, H - n + 1, n) for x in range(0, W - n + 1, n)]
     return out
+
+
+def oracle_intra_tu(lib, bd, n, mode, qp, ts, org, border, stage, strong=1, intra=1, sbh=1, level_in=None):
+    """oracle_intra_tu on one TU: returns dict(coef, level, pred, reco, dist, abs_sum)."""
+    org = np.ascontiguousarray(org, np.int16)
+    border = np.ascontiguousarray(border, np.int16)
+    coef = np.zeros(n * n, np.int32)
+    level = np.zeros(n * n, np.int32) if level_in is None else np.ascontiguousarray(level_in, np.int32).copy()
+    pred = np.zeros(n * n, np.int16)
+    reco = np.zeros(n * n, np.int16)
+    dist = C.c_uint32(0)
+    abs_sum = C.c_int32(0)
+    lib.oracle_intra_tu(bd, n, int(mode), int(qp), int(ts), strong, intra, sbh, stage, P(org, i16p), n, P(border, i16p), P(coef, i32p), P(level, i32p),
+                        P(pred, i16p), P(reco, i16p), C.byref(dist), C.byref(abs_sum))
+    return dict(coef=coef, level=level, pred=pred, reco=reco, dist=dist.value, abs_sum=abs_sum.value)
+
+
+TU_HDR = ("poc", "x", "y", "mode", "bd", "ts", "load", "qp", "intra", "sbh", "rdoq", "abs_sum", "dist")
+
+
+def tu_records(g):
+    """iterate the records of a tests/golden/tu_*.npz file as dicts"""
+    for tag in sorted(k[:-4] for k in g.files if k.endswith("_hdr")):
+        n = int(tag[1:].rstrip("ts"))
+        for i, h in enumerate(g[tag + "_hdr"]):
+            r = dict(zip(TU_HDR, (int(v) for v in h)))
+            r["n"] = n
+            for k in ("border", "org", "pred", "coef", "level", "reco"):
+                r[k] = g[tag + "_" + k][i]
+            yield r

@@ -136,3 +136,47 @@ def test_tmv_features_and_aq_activity_match_reference(oracle, hmref, bd, W, H):
         for a, b in zip(acts, ref):
             assert np.array_equal(a, b)
         assert np.array_equal(avg, ravg)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+@pytest.mark.parametrize("n", [4, 8, 16, 32])
+def test_core_transforms_match_reference(oracle, hmref, n, bd):
+    """xTrMxN / xITrMxN (TComTrQuant.cpp:860-985) on random and extreme inputs, DCT and (4x4) DST; the restated matrices
+    against the reference's partial butterflies, including the 16-bit clipping of the inverse's first stage."""
+    rng = np.random.default_rng(200 + n + bd)
+    hi = (1 << bd) - 1
+    for trial in range(40):
+        kind = trial % 4
+        if kind == 0:
+            resi = rng.integers(-hi, hi + 1, (n, n))
+        elif kind == 1:
+            resi = rng.choice([-hi, hi], size=(n, n))
+        elif kind == 2:
+            resi = np.full((n, n), hi if trial % 8 < 4 else -hi)
+        else:
+            resi = rng.integers(-6, 7, (n, n))
+        resi16 = resi.astype(np.int16)
+        for dst in ([0, 1] if n == 4 else [0]):
+            want = np.zeros(n * n, np.int32)
+            hmref.hmref_fwd_transform(bd, n, dst, P(np.ascontiguousarray(resi.astype(np.int32)), i32p), P(want, i32p))
+            got = np.zeros(n * n, np.int32)
+            oracle.oracle_fwd_transform(bd, n, dst, P(resi16, i16p), n, P(got, i32p))
+            assert np.array_equal(got, want)
+            # inverse on the forward output and on extreme coefficient blocks
+            for coef in (want, rng.choice([-32768, 32767], size=n * n).astype(np.int32), (want * 3).clip(-32768, 32767).astype(np.int32)):
+                wres = np.zeros(n * n, np.int32)
+                hmref.hmref_inv_transform(bd, n, dst, P(np.ascontiguousarray(coef), i32p), P(wres, i32p))
+                gres = np.zeros(n * n, np.int16)
+                oracle.oracle_inv_transform(bd, n, dst, P(np.ascontiguousarray(coef), i32p), P(gres, i16p), n)
+                assert np.array_equal(gres.astype(np.int32), wres)
+
+
+def test_sse_matches_reference(oracle, hmref):
+    hmref.hmref_sse.restype = __import__("ctypes").c_uint32
+    oracle.oracle_sse.restype = __import__("ctypes").c_uint32
+    rng = np.random.default_rng(9)
+    for bd in (8, 10):
+        for n in (4, 8, 16, 32):
+            a = rng.integers(0, 1 << bd, (n, n)).astype(np.int16)
+            b = rng.integers(0, 1 << bd, (n, n)).astype(np.int16)
+            assert oracle.oracle_sse(bd, P(a, i16p), n, P(b, i16p), n, n, n) == hmref.hmref_sse(bd, P(a, i16p), n, P(b, i16p), n, n, n)
