@@ -18,6 +18,8 @@ from .binding import (  # noqa: F401
     PACKED_CTU_BYTES,
     PUS_PER_CTU,
     RmdQueue,
+    TU_INTRA_SLICE,
+    TU_SIGN_HIDING,
     declared_symbols,
     exp_satd_tc,
     load_library,

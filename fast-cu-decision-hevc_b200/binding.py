@@ -65,6 +65,13 @@ class _MeDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("x", "y", "w", "h", "ref_idx", "left", "right", "top", "bottom", "sub_shift")]
 
 
+class _TuDesc(C.Structure):
+    _fields_ = [("log2_size", C.c_uint8), ("mode", C.c_uint8), ("qp", C.c_int8), ("transform_skip", C.c_uint8)]
+
+
+TU_INTRA_SLICE, TU_SIGN_HIDING = 1, 2
+
+
 class _CuDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("x", "y", "log2_size")]
 
@@ -104,6 +111,10 @@ def load_library():
     lib.cucd_set_ref_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.cucd_set_cur_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.cucd_me_sad_surface.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MeDesc), C.c_void_p]
+    lib.cucd_intra_tu_forward.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cucd_intra_tu_recon.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cucd_intra_tu_code.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
     lib.cucd_tmv_features.argtypes = [C.c_void_p, C.c_int, C.POINTER(_CuDesc), C.c_void_p]
     lib.cucd_aq_activity.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
     lib.cucd_dev_rmd_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
@@ -319,6 +330,50 @@ class Engine:
             res.append(out[off:off + r * c].reshape(r, c))
             off += r * c
         return res
+
+    # ---- intra luma TU coding (xIntraCodingTUBlock) ------------------------------------------------
+    @staticmethod
+    def _tu_descs(tus):
+        """tus: iterable of (log2_size, mode, qp, transform_skip)"""
+        tus = list(tus)
+        arr = (_TuDesc * max(len(tus), 1))()
+        total = 0
+        for i, (l, m, q, ts) in enumerate(tus):
+            arr[i].log2_size, arr[i].mode, arr[i].qp, arr[i].transform_skip = int(l), int(m), int(q), int(ts)
+            total += 1 << (2 * int(l))
+        return tus, arr, total
+
+    def intra_tu_forward(self, tus, org, border, want_pred=True):
+        """Returns (coef int32, pred int16), both flat in the packing of org."""
+        tus, arr, total = self._tu_descs(tus)
+        org = np.ascontiguousarray(org, np.int16).ravel(); border = np.ascontiguousarray(border, np.int16).ravel()
+        coef = np.zeros(total, np.int32)
+        pred = np.zeros(total, np.int16) if want_pred else None
+        self._check(self.lib.cucd_intra_tu_forward(self.h, len(tus), arr, org.ctypes.data, border.ctypes.data, coef.ctypes.data,
+                                                   pred.ctypes.data if want_pred else None), "cucd_intra_tu_forward")
+        return coef, pred
+
+    def intra_tu_recon(self, tus, org, border, level):
+        """Returns (reco int16 flat, dist uint32 per TU)."""
+        tus, arr, total = self._tu_descs(tus)
+        org = np.ascontiguousarray(org, np.int16).ravel(); border = np.ascontiguousarray(border, np.int16).ravel()
+        level = np.ascontiguousarray(level, np.int32).ravel()
+        assert level.size == total
+        reco = np.zeros(total, np.int16)
+        dist = np.zeros(len(tus), np.uint32)
+        self._check(self.lib.cucd_intra_tu_recon(self.h, len(tus), arr, org.ctypes.data, border.ctypes.data, level.ctypes.data, reco.ctypes.data,
+                                                 dist.ctypes.data), "cucd_intra_tu_recon")
+        return reco, dist
+
+    def intra_tu_code(self, tus, org, border, flags=TU_INTRA_SLICE | TU_SIGN_HIDING):
+        """Whole chain with the plain quantiser. Returns (level int32 flat, reco int16 flat, dist uint32, abs_sum int32)."""
+        tus, arr, total = self._tu_descs(tus)
+        org = np.ascontiguousarray(org, np.int16).ravel(); border = np.ascontiguousarray(border, np.int16).ravel()
+        level = np.zeros(total, np.int32); reco = np.zeros(total, np.int16)
+        dist = np.zeros(len(tus), np.uint32); abs_sum = np.zeros(len(tus), np.int32)
+        self._check(self.lib.cucd_intra_tu_code(self.h, len(tus), arr, org.ctypes.data, border.ctypes.data, int(flags), level.ctypes.data,
+                                                reco.ctypes.data, dist.ctypes.data, abs_sum.ctypes.data), "cucd_intra_tu_code")
+        return level, reco, dist, abs_sum
 
     def tmv_features(self, cus):
         """cus: iterable of (x, y, log2_size) of the picture given to set_cur_picture. Returns (nCU, 5, 26) float64

@@ -87,6 +87,7 @@ struct cucd_handle {
   std::vector<RefPlane> refs;
   DevBuf<int16_t> dCur; int curStride = 0; bool curSet = false;
   DevBuf<const int16_t*> dRefPtr; DevBuf<int32_t> dRefStride;
+  DevBuf<TuJob> tJobs; DevBuf<int32_t> tCoef, tAbs; DevBuf<int16_t> tPix; DevBuf<uint32_t> tDist;   // TU coding path
   DevBuf<TmvCu> dTmvCus; DevBuf<double> dDoubles;   // texture features / AQ activity
   DevBuf<MeJob> dJobs; DevBuf<int32_t> dTileJob, dTileIdx; DevBuf<uint32_t> dSad;
 };
@@ -231,6 +232,7 @@ int cucd_destroy(cucd_handle* h) {
   h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
   for (auto& r : h->refs) r.buf.release();
   h->dTmvCus.release(); h->dDoubles.release();
+  h->tJobs.release(); h->tCoef.release(); h->tAbs.release(); h->tPix.release(); h->tDist.release();
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
   for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
   for (int i = 0; i < cucd_handle::kGroups; i++) { if (h->evUpG[i]) cudaEventDestroy(h->evUpG[i]); if (h->evRmdG[i]) cudaEventDestroy(h->evRmdG[i]); }
@@ -722,6 +724,69 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
   CK(cudaStreamSynchronize(h->sMain));
   flush_launches(h);
   return CUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Intra luma TU coding (xIntraCodingTUBlock): forward half, reconstruction half, or the whole chain with the plain quantiser
+// ------------------------------------------------------------------------------------------------
+static int tu_batch(cucd_handle* h, const char* who, int stage, int flags, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border,
+                    int32_t* coefOut, const int32_t* levelIn, int16_t* pixOut, uint32_t* dist, int32_t* absSum) {
+  if (!h || nTU < 0 || (nTU > 0 && (!desc || !org || !border))) return fail(h, CUCD_ERR_INVALID, std::string(who) + ": bad argument");
+  if (nTU == 0) return CUCD_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<TuJob> jobs[6];
+  size_t orgOff = 0, borderOff = 0;
+  for (int i = 0; i < nTU; i++) {
+    const cucd_tu_desc& d = desc[i];
+    if (d.log2_size < 2 || d.log2_size > 5) return fail(h, CUCD_ERR_INVALID, std::string(who) + ": log2_size must be 2..5");
+    if (d.mode > 34 || d.qp < 0 || d.qp > 51) return fail(h, CUCD_ERR_INVALID, std::string(who) + ": mode must be 0..34 and qp 0..51");
+    if (d.transform_skip && d.log2_size != 2) return fail(h, CUCD_ERR_UNSUPPORTED, std::string(who) + ": transform skip is a 4x4 tool (log2MaxTransformSkipSize = 2)");
+    const int n = 1 << d.log2_size;
+    TuJob j; j.orgOff = (int32_t)orgOff; j.borderOff = (int32_t)borderOff; j.outIndex = i; j.mode = d.mode; j.ts = d.transform_skip ? 1 : 0; j.qp = d.qp; j.pad = 0;
+    jobs[d.log2_size].push_back(j);
+    orgOff += (size_t)n * n; borderOff += (size_t)4 * n + 1;
+    if (orgOff > 0x7fffffffull) return fail(h, CUCD_ERR_INVALID, std::string(who) + ": batch too large");
+  }
+  std::vector<TuJob> all; all.reserve(nTU);
+  size_t first[6] = {0};
+  for (int l = 2; l <= 5; l++) { first[l] = all.size(); all.insert(all.end(), jobs[l].begin(), jobs[l].end()); }
+  CK(h->bOrg.reserve(orgOff + 64)); CK(h->bBorder.reserve(borderOff + 8)); CK(h->tJobs.reserve(all.size()));
+  CK(h->tCoef.reserve(orgOff)); CK(h->tPix.reserve(orgOff)); CK(h->tDist.reserve(nTU)); CK(h->tAbs.reserve(nTU));
+  CK(cudaMemcpyAsync(h->bOrg.p, org, orgOff * 2, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->bBorder.p, border, borderOff * 2, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->tJobs.p, all.data(), all.size() * sizeof(TuJob), cudaMemcpyHostToDevice, h->sMain));
+  if (stage == 2) CK(cudaMemcpyAsync(h->tCoef.p, levelIn, orgOff * sizeof(int32_t), cudaMemcpyHostToDevice, h->sMain));
+  for (int l = 5; l >= 2; l--) {
+    if (jobs[l].empty()) continue;
+    TuBatch tb;
+    tb.org = h->bOrg.p; tb.border = h->bBorder.p; tb.jobs = h->tJobs.p + first[l]; tb.count = (int)jobs[l].size();
+    tb.stage = stage; tb.bitDepth = h->cfg.bit_depth; tb.strong = h->cfg.strong_intra_smoothing;
+    tb.intraSlice = (flags & CUCD_TU_INTRA_SLICE) ? 1 : 0; tb.signHiding = (flags & CUCD_TU_SIGN_HIDING) ? 1 : 0;
+    tb.coef = h->tCoef.p; tb.pred = (stage == 0 && pixOut) ? h->tPix.p : nullptr; tb.reco = h->tPix.p; tb.dist = h->tDist.p; tb.absSum = h->tAbs.p;
+    CK(launch_intra_tu(l, tb, h->sMain, &h->launches));
+  }
+  if (coefOut) CK(cudaMemcpyAsync(coefOut, h->tCoef.p, orgOff * sizeof(int32_t), cudaMemcpyDeviceToHost, h->sMain));
+  if (pixOut) CK(cudaMemcpyAsync(pixOut, h->tPix.p, orgOff * sizeof(int16_t), cudaMemcpyDeviceToHost, h->sMain));
+  if (dist) CK(cudaMemcpyAsync(dist, h->tDist.p, (size_t)nTU * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
+  if (absSum) CK(cudaMemcpyAsync(absSum, h->tAbs.p, (size_t)nTU * sizeof(int32_t), cudaMemcpyDeviceToHost, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+int cucd_intra_tu_forward(cucd_handle* h, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border, int32_t* coef, int16_t* pred) {
+  if (nTU > 0 && !coef) return fail(h, CUCD_ERR_INVALID, "cucd_intra_tu_forward: coef is NULL");
+  return tu_batch(h, "cucd_intra_tu_forward", 0, 0, nTU, desc, org, border, coef, nullptr, pred, nullptr, nullptr);
+}
+int cucd_intra_tu_recon(cucd_handle* h, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border, const int32_t* level,
+                        int16_t* reco, uint32_t* dist) {
+  if (nTU > 0 && (!level || !reco || !dist)) return fail(h, CUCD_ERR_INVALID, "cucd_intra_tu_recon: NULL level / reco / dist");
+  return tu_batch(h, "cucd_intra_tu_recon", 2, 0, nTU, desc, org, border, nullptr, level, reco, dist, nullptr);
+}
+int cucd_intra_tu_code(cucd_handle* h, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border, int flags,
+                       int32_t* level, int16_t* reco, uint32_t* dist, int32_t* abs_sum) {
+  if (nTU > 0 && (!level || !reco || !dist)) return fail(h, CUCD_ERR_INVALID, "cucd_intra_tu_code: NULL level / reco / dist");
+  return tu_batch(h, "cucd_intra_tu_code", 1, flags, nTU, desc, org, border, level, nullptr, reco, dist, abs_sum);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -150,6 +150,40 @@ int cucd_set_cur_picture(cucd_handle* h, const int16_t* orgY, int stride);
 int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut);
 
 /* ------------------------------------------------------------------------------------------------
+ * Intra luma TU coding: the arithmetic of TEncSearch::xIntraCodingTUBlock (TEncSearch.cpp:1092-1387) for a
+ * batch of luma TUs with caller-supplied borders, packed like S2: org holds the N*N source blocks back to back, border
+ * the 4N+1 unfiltered reference arrays; coef / level / pred / reco use the layout of org (N*N per TU, row-major; coefficient
+ * [v][u] = vertical x horizontal frequency as TCoeff blocks are stored); dist / abs_sum hold one value per TU.
+ * The entropy-coupled parts stay with the caller: RDOQ (xRateDistOptQuant), the CABAC bit count, the RD compare.
+ *   cucd_intra_tu_forward  initAdiPatternChType smoothing + predIntraAng + residual (:1160-1224) + the transform half of
+ *                          TComTrQuant::transformNxN (xT = partial butterflies / 4x4 DST, or xTransformSkip;
+ *                          TComTrQuant.cpp:860-919, 1376-1440, 1857-1978): coef = m_plTempCoeff, what xRateDistOptQuant
+ *                          reads; pred (may be NULL) = piPred.
+ *   cucd_intra_tu_recon    the half after the quantiser for levels chosen by the caller (the host's RDOQ):
+ *                          invTransformNxN (xDeQuant + xIT / xITransformSkip, TComTrQuant.cpp:927-985, 1242-1352, 1462-1586),
+ *                          reconstruction with clipping (TEncSearch.cpp:1360-1381), SSE getDistPart (:1385-1386).
+ *   cucd_intra_tu_code     the whole chain with HM's plain quantiser (encoders run with --RDOQ=0): xQuant with flat scaling
+ *                          lists (TComTrQuant.cpp:1126-1240) and, with CUCD_TU_SIGN_HIDING, signBitHidingHDQ (:991-1123);
+ *                          level = pcCoeff, abs_sum = uiAbsSum (the CBF), reco, dist as above.
+ * Limits: luma, 4:2:0 intra TUs of 4..32, flat scaling lists, no transquant bypass / RDPCM / cross-component prediction /
+ * extended precision (all off in the BASELINE configurations).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint8_t log2_size;         /* 2..5 */
+  uint8_t mode;              /* luma intra mode 0..34 (uiChFinalMode) */
+  int8_t  qp;                /* TComDataCU::getQP(0): luma QP before the bit-depth offset, 0..51 */
+  uint8_t transform_skip;    /* TComDataCU::getTransformSkip, 4x4 TUs only */
+} cucd_tu_desc;
+#define CUCD_TU_INTRA_SLICE 1   /* rounding offset 171/512 instead of 85/512 (TComTrQuant.cpp:1206) */
+#define CUCD_TU_SIGN_HIDING 2   /* PPS sign_data_hiding_enabled_flag */
+int cucd_intra_tu_forward(cucd_handle* h, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border,
+                          int32_t* coef, int16_t* pred);
+int cucd_intra_tu_recon(cucd_handle* h, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border,
+                        const int32_t* level, int16_t* reco, uint32_t* dist);
+int cucd_intra_tu_code(cucd_handle* h, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border, int flags,
+                       int32_t* level, int16_t* reco, uint32_t* dist, int32_t* abs_sum);
+
+/* ------------------------------------------------------------------------------------------------
  * CU texture features and AQ activity of the picture given to cucd_set_cur_picture.
  * cucd_tmv_features  replaces getTMVFeature(rpcBestCU) (tools_YS.cpp:1682-1839, call site TEncCu.cpp:1558-1570):
  *                    feat[i*130 + f*26 + k] = m_adFeature[f][k] of CU i - five 3x3 directional planes (original,
