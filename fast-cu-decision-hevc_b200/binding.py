@@ -129,6 +129,7 @@ def load_library():
     lib.cucd_queue_submit.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     lib.cucd_queue_wait.argtypes = [C.c_void_p, C.c_uint64]
     lib.cucd_queue_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    lib.cucd_last_kernel_time.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.cucd_rmd_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
     lib.cucd_tcm_fit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib
@@ -424,6 +425,11 @@ class Engine:
         yc = yc_host.ctypes.data if yc_host is not None else None
         self._check(self.lib.cucd_dev_frames(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride,
                                              C.byref(o), yc), "cucd_dev_frames")
+
+    def last_kernel_time_ms(self):
+        ms = C.c_float(0)
+        self._check(self.lib.cucd_last_kernel_time(self.h, C.byref(ms)), "cucd_last_kernel_time")
+        return ms.value
 
     def rmd_kernel_time_ms(self, n_calls):
         """mean device duration of the RMD launch over the last n_calls dev_frames calls (stream must be synchronised)"""

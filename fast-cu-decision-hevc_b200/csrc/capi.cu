@@ -63,6 +63,8 @@ struct cucd_handle {
   cudaEvent_t evUp = nullptr, evHist = nullptr, evUpG[kGroups] = {}, evRmdG[kGroups] = {};
   static constexpr int kTimeRing = 64;
   cudaEvent_t evRmd0[kTimeRing] = {}, evRmd1[kTimeRing] = {};
+  cudaEvent_t evK0 = nullptr, evK1 = nullptr;     // around the kernels of the last batch call (cucd_last_kernel_time)
+  bool kTimed = false;
   long long rmdCalls = 0;
   int launches = 0;
   long long launchTotal = 0;
@@ -192,6 +194,7 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
             cudaEventCreateWithFlags(&h->evHist, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < cucd_handle::kGroups; i++)
     ok = ok && cudaEventCreateWithFlags(&h->evUpG[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->evRmdG[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreate(&h->evK0) == cudaSuccess && cudaEventCreate(&h->evK1) == cudaSuccess;
   for (int i = 0; i < cucd_handle::kTimeRing; i++) ok = ok && cudaEventCreate(&h->evRmd0[i]) == cudaSuccess && cudaEventCreate(&h->evRmd1[i]) == cudaSuccess;
   ok = ok && h->dOrg.reserve(P * h->planeSamples) == cudaSuccess && h->dRec.reserve(P * h->planeSamples) == cudaSuccess;
   ok = ok && h->dCost.reserve(P * h->ctusPerPic * kPusPerCtu * kNumModes) == cudaSuccess;
@@ -236,6 +239,8 @@ int cucd_destroy(cucd_handle* h) {
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
   for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
   for (int i = 0; i < cucd_handle::kGroups; i++) { if (h->evUpG[i]) cudaEventDestroy(h->evUpG[i]); if (h->evRmdG[i]) cudaEventDestroy(h->evRmdG[i]); }
+  if (h->evK0) cudaEventDestroy(h->evK0);
+  if (h->evK1) cudaEventDestroy(h->evK1);
   if (h->sUp) cudaStreamDestroy(h->sUp);
   if (h->evUp) cudaEventDestroy(h->evUp);
   if (h->evHist) cudaEventDestroy(h->evHist);
@@ -267,6 +272,13 @@ int cucd_rmd_kernel_time(cucd_handle* h, int nCalls, float* avg_ms) {
   }
   *avg_ms = (float)(sum / n);
   return n;
+}
+
+int cucd_last_kernel_time(cucd_handle* h, float* ms) {
+  if (!h || !ms) return fail(h, CUCD_ERR_INVALID, "cucd_last_kernel_time: bad argument");
+  if (!h->kTimed) return fail(h, CUCD_ERR_INVALID, "cucd_last_kernel_time: no batch call yet");
+  CK(cudaEventElapsedTime(ms, h->evK0, h->evK1));
+  return CUCD_OK;
 }
 
 int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr) {
@@ -518,6 +530,7 @@ int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, cons
   CK(cudaMemcpyAsync(h->bOrg.p, org, orgOff * 2, cudaMemcpyHostToDevice, h->sMain));
   CK(cudaMemcpyAsync(h->bBorder.p, border, borderOff * 2, cudaMemcpyHostToDevice, h->sMain));
   CK(cudaMemcpyAsync(h->bPus.p, all.data(), all.size() * sizeof(BatchPu), cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaEventRecord(h->evK0, h->sMain));
   for (int l = 6; l >= 2; l--) {
     if (pus[l].empty()) continue;
     BatchSource bs;
@@ -527,6 +540,7 @@ int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, cons
     else
       CK(launch_rmd_batch(l, bs, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
   }
+  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   CK(cudaMemcpyAsync(sad, h->bOut.p, (size_t)nPU * kNumModes * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));   // `all` and the caller's buffers must outlive the copies
   flush_launches(h);
@@ -719,7 +733,9 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
   CK(cudaMemcpyAsync(h->dTileIdx.p, tileIdx.data(), tileIdx.size() * 4, cudaMemcpyHostToDevice, h->sMain));
   MePlanes mp;
   mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
+  CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_me_sad(mp, h->dJobs.p, nPU, h->dTileJob.p, h->dTileIdx.p, (int)tileJob.size(), h->dSad.p, h->sMain, &h->launches));
+  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   CK(cudaMemcpyAsync(sadOut, h->dSad.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));
   flush_launches(h);
@@ -756,6 +772,7 @@ static int tu_batch(cucd_handle* h, const char* who, int stage, int flags, int n
   CK(cudaMemcpyAsync(h->bBorder.p, border, borderOff * 2, cudaMemcpyHostToDevice, h->sMain));
   CK(cudaMemcpyAsync(h->tJobs.p, all.data(), all.size() * sizeof(TuJob), cudaMemcpyHostToDevice, h->sMain));
   if (stage == 2) CK(cudaMemcpyAsync(h->tCoef.p, levelIn, orgOff * sizeof(int32_t), cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaEventRecord(h->evK0, h->sMain));
   for (int l = 5; l >= 2; l--) {
     if (jobs[l].empty()) continue;
     TuBatch tb;
@@ -765,6 +782,7 @@ static int tu_batch(cucd_handle* h, const char* who, int stage, int flags, int n
     tb.coef = h->tCoef.p; tb.pred = (stage == 0 && pixOut) ? h->tPix.p : nullptr; tb.reco = h->tPix.p; tb.dist = h->tDist.p; tb.absSum = h->tAbs.p;
     CK(launch_intra_tu(l, tb, h->sMain, &h->launches));
   }
+  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   if (coefOut) CK(cudaMemcpyAsync(coefOut, h->tCoef.p, orgOff * sizeof(int32_t), cudaMemcpyDeviceToHost, h->sMain));
   if (pixOut) CK(cudaMemcpyAsync(pixOut, h->tPix.p, orgOff * sizeof(int16_t), cudaMemcpyDeviceToHost, h->sMain));
   if (dist) CK(cudaMemcpyAsync(dist, h->tDist.p, (size_t)nTU * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
@@ -808,7 +826,9 @@ int cucd_tmv_features(cucd_handle* h, int nCU, const cucd_cu_desc* cus, double* 
   }
   CK(h->dTmvCus.reserve(nCU)); CK(h->dDoubles.reserve((size_t)nCU * CUCD_TMV_FEATURES));
   CK(cudaMemcpyAsync(h->dTmvCus.p, v.data(), v.size() * sizeof(TmvCu), cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_tmv_features(h->dCur.p, h->curStride, h->dTmvCus.p, nCU, h->dDoubles.p, h->sMain, &h->launches));
+  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   CK(cudaMemcpyAsync(feat, h->dDoubles.p, (size_t)nCU * CUCD_TMV_FEATURES * sizeof(double), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));
   flush_launches(h);
@@ -828,7 +848,9 @@ int cucd_aq_activity(cucd_handle* h, int max_aq_depth, double* const* activity, 
   }
   for (int d = max_aq_depth; d <= 4; d++) L.off[d] = L.total;
   CK(h->dDoubles.reserve(L.total));
+  CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_aq_activity(h->dCur.p, h->curStride, W, H, L, h->dDoubles.p, h->sMain, &h->launches));
+  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   std::vector<double> act(L.total);
   CK(cudaMemcpyAsync(act.data(), h->dDoubles.p, (size_t)L.total * sizeof(double), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));

@@ -239,6 +239,10 @@ int cucd_set_rmd_path(cucd_handle* h, int path);
  * caller's stream around that launch; ring of 64).  The stream must have been synchronised.  Returns
  * the number of calls averaged, or a negative status; *avg_ms = mean duration of one launch. */
 int cucd_rmd_kernel_time(cucd_handle* h, int nCalls, float* avg_ms);
+/* Device time between the first and the last kernel of the most recent batch call on this handle (cucd_intra_rmd_batch,
+ * cucd_me_sad_surface, cucd_intra_tu_*, cucd_tmv_features, cucd_aq_activity): CUDA events on the library's stream, host<->device
+ * copies outside.  What bench_rows.py reports as the kernel-only figure of those paths. */
+int cucd_last_kernel_time(cucd_handle* h, float* ms);
 /* the host-side fit that sits between the two passes (TEncSlice.cpp:291-392): hist = 16*4096 counts
  * of ONE picture, nBlocks = (W/4)*(H/4); writes yc[16] and thr[16] */
 int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr);
