@@ -29,8 +29,8 @@ if [ ! -d "$REF/Lib/TLibCommon" ]; then
 fi
 mkdir -p "$WORK" "$OUT"
 STAMP="$WORK/.stamp"
-SIG="$(cat "$HERE/build_ref.sh" "$HERE"/ref_shims/* | md5sum | cut -d' ' -f1)"
-if [ -f "$STAMP" ] && [ "$(cat "$STAMP")" = "$SIG" ] && [ -x "$OUT/TAppEncoder" ] && [ -f "$OUT/libhmref.so" ]; then
+SIG="$(cat "$HERE/build_ref.sh" "$HERE"/ref_shims/* "$HERE/../include/cucudecide.h" | md5sum | cut -d' ' -f1)"
+if [ -f "$STAMP" ] && [ "$(cat "$STAMP")" = "$SIG" ] && [ -x "$OUT/TAppEncoder" ] && [ -f "$OUT/libhmref.so" ] && [ -x "$OUT/TAppEncoderCucd" ]; then
   echo "build_ref.sh: oracle/_ref up to date"
   exit 0
 fi
@@ -71,8 +71,10 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("      for (Int modeIdx = 0; modeIdx < numModesAvailable; modeIdx++)\n      {\n        UInt       uiMode = modeIdx;\n",
    "      cucd_hook_rmd_begin(g_iPOC, pcCU->getCUPelX() + puRect.x0, pcCU->getCUPelY() + puRect.y0, puRect.width, g_bitDepth[CHANNEL_TYPE_LUMA],\n"
    "                          m_piYuvExt[COMPONENT_Y][PRED_BUF_UNFILTERED], m_piYuvExt[COMPONENT_Y][PRED_BUF_FILTERED], piOrg, uiStride);\n", "before"),
+  ("        // do intra prediciton \n        predIntraAng(COMPONENT_Y, uiMode, piOrg, uiStride, piPred, uiStride, tuRecurseWithPU,",
+   "#ifdef CUCD_INTEGRATION\n        uiSad += cucd_shim_rmd_sad(modeIdx);      /* INTEGRATION.md S2 */\n#else\n", "before"),
   ("        uiSad += distParam.DistFunc(&distParam);  // DistFunc is a member of DistParam class \n",
-   "        cucd_hook_rmd_mode(modeIdx, uiSad);\n", "after"),
+   "#endif\n        cucd_hook_rmd_mode(modeIdx, uiSad);\n", "after"),
   ("      //////////////  End of RMD ///",
    "      cucd_hook_rmd_end();\n", "before"),
   ("    uiSad = m_cDistParam.DistFunc(&m_cDistParam);\n\n    // motion cost\n    uiSad += m_pcRdCost->getCost(iSearchX, iSearchY);\n\n    if (uiSad < rcStruct.uiBestSad)",
@@ -92,6 +94,18 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
    "                                  useTransformSkip ? m_pcEncCfg->getUseRDOQTS() : m_pcEncCfg->getUseRDOQ(), m_pcTrQuant->cucdTempCoeff(), pcCoeff, uiAbsSum);\n", "before"),
   ("  //===== update distortion =====\n  ruiDist += m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID);\n",
    "  if (bIsLuma) cucd_hook_tu_end(piReco, uiStride, m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID));\n", "after"),
+])
+# S1 call site (TEncGOP.cpp:1095-1096)
+patch("Lib/TLibEncoder/TEncGOP.cpp", [
+  ("\t\t  m_pcSliceEncoder->getOutlierWithDCT(pcPic);\n",
+   "#ifdef CUCD_INTEGRATION\n"
+   "      cucd_shim_outlier(pcPic->getPicYuvOrg()->getWidth(COMPONENT_Y), pcPic->getPicYuvOrg()->getHeight(COMPONENT_Y), g_bitDepth[CHANNEL_TYPE_LUMA],\n"
+   "                        pcSlice->getSPS()->getUseStrongIntraSmoothing() ? 1 : 0,\n"
+   "                        pcPic->getPicYuvOrg()->getAddr(COMPONENT_Y), pcPic->getPicYuvOrg()->getStride(COMPONENT_Y),\n"
+   "                        pcPic->getOBF()->getAddr(COMPONENT_Y), pcPic->getOBF()->getStride(COMPONENT_Y),\n"
+   "                        pcPic->getPicYuvOutlier()->getAddr(COMPONENT_Y), pcPic->getPicYuvOutlier()->getStride(COMPONENT_Y));   /* INTEGRATION.md S1 */\n"
+   "#else\n", "before"),
+  ("\t\t  m_pcSliceEncoder->getOutlierWithDCT(pcPic);\n", "#endif\n", "after"),
 ])
 # outlier picture pass (TEncSlice.cpp:878-1173)
 patch("Lib/TLibEncoder/TEncSlice.cpp", [
@@ -125,13 +139,18 @@ DEC_O := $(call o,$(DEC_CPP))
 # encmain.cpp defines main() AND the fork's global output streams; the driver library reuses the
 # object with main renamed so that those globals exist without a second definition.
 APP_LIB_O := $(patsubst %.o,%.lib.o,$(APP_O))
-all: $(OUT)/TAppEncoder $(OUT)/TAppDecoder $(OUT)/libhmref.so
+# integration build: the same patched sources with -DCUCD_INTEGRATION, linked against the product library
+INT_O := $(patsubst %.o,%.int.o,$(ENC_O) $(APP_O))
+all: $(OUT)/TAppEncoder $(OUT)/TAppDecoder $(OUT)/libhmref.so $(if $(wildcard $(PKGDIR)/libcucudecide.so),$(OUT)/TAppEncoderCucd)
 $(OBJ)/%.cpp.o: $(SRC)/%.cpp
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 $(OBJ)/%.cpp.lib.o: $(SRC)/%.cpp
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -Dmain=hm_encoder_main -c $< -o $@
+$(OBJ)/%.cpp.int.o: $(SRC)/%.cpp
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -DCUCD_INTEGRATION -I$(INCDIR) -c $< -o $@
 $(OBJ)/%.c.o: $(SRC)/%.c
 	@mkdir -p $(dir $@)
 	gcc $(CFLAGS) -c $< -o $@
@@ -139,9 +158,11 @@ $(OUT)/TAppEncoder: $(BASE_O) $(ENC_O) $(APP_O)
 	$(CXX) -o $@ $^ -lm
 $(OUT)/TAppDecoder: $(BASE_O) $(DEC_O)
 	$(CXX) -o $@ $^ -lm
+$(OUT)/TAppEncoderCucd: $(BASE_O) $(INT_O) $(PKGDIR)/libcucudecide.so
+	$(CXX) -o $@ $(BASE_O) $(INT_O) -L$(PKGDIR) -lcucudecide -Wl,-rpath,'$$ORIGIN/../../fast-cu-decision-hevc_b200' -lm -lpthread
 $(OUT)/libhmref.so: $(BASE_O) $(ENC_O) $(APP_LIB_O) $(OBJ)/hmref_driver.cpp.o
 	$(CXX) -shared -o $@ $^ -lm -lpthread
 EOF
-make -s -f "$WORK/build.mk" -j"$JOBS" SRC="$SRC" OBJ="$WORK/obj" OUT="$OUT" all
+make -s -f "$WORK/build.mk" -j"$JOBS" SRC="$SRC" OBJ="$WORK/obj" OUT="$OUT" INCDIR="$HERE/../include" PKGDIR="$HERE/../fast-cu-decision-hevc_b200" all
 echo "$SIG" > "$STAMP"
 ls -la "$OUT"

@@ -31,6 +31,59 @@ struct CucdDump {
 };
 inline void cucd_w32(FILE* f, int32_t v) { fwrite(&v, 4, 1, f); }
 
+/* ---- integration build (-DCUCD_INTEGRATION): the lines INTEGRATION.md asks a maintainer to add, so that the patched
+ *      reference encoder computes its S1 / S2 numbers on the GPU through libcucudecide.so (oracle/_ref/TAppEncoderCucd).
+ *      Used by tests/test_gpu_encoder_md5.py to show that the bitstream stays byte-identical. ------------------------- */
+#ifdef CUCD_INTEGRATION
+#include <vector>
+#include "cucudecide.h"
+struct CucdShim { cucd_handle* h; int W, H, bd, strong; uint32_t sad[35]; long rmdCalls, frameCalls; };
+inline CucdShim& cucd_shim() { static CucdShim s = {0, 0, 0, 0, 0, {0}, 0, 0}; return s; }
+inline void cucd_shim_die(const char* what) {   /* HM convention: fatal error -> exit(1) (CommonDef.h:141-164) */
+  fprintf(stderr, "cucd shim: %s failed: %s\n", what, cucd_last_error(cucd_shim().h));
+  exit(1);
+}
+/* S0: TEncTop::create would do this once; the shim opens lazily at the first picture */
+inline void cucd_shim_open(int W, int H, int bd, int strong) {
+  CucdShim& s = cucd_shim();
+  if (s.h && (s.W != W || s.H != H || s.bd != bd || s.strong != strong)) { cucd_destroy(s.h); s.h = 0; }
+  if (!s.h) {
+    cucd_config cfg = {W, H, bd, 64, 4, strong, 0, 1, 0};
+    if (cucd_create(&cfg, &s.h) != CUCD_OK) cucd_shim_die("cucd_create");
+    s.W = W; s.H = H; s.bd = bd; s.strong = strong;
+  }
+}
+/* S1: replaces TEncSlice::getOutlierWithDCT(pcPic) at TEncGOP.cpp:1095-1096 */
+inline void cucd_shim_outlier(int W, int H, int bd, int strong, const short* org, int orgStride, short* obf, int obfStride,
+                              short* outl, int outlStride) {
+  cucd_shim_open(W, H, bd, strong);
+  CucdShim& s = cucd_shim();
+  std::vector<int16_t> o((size_t)(W / 4) * (H / 4)), t((size_t)W * H);
+  cucd_frame_out fo; memset(&fo, 0, sizeof fo);
+  fo.obf = o.data(); fo.outlier = t.data();
+  if (cuCUDecide_frame(s.h, org, orgStride, 0, 0, 0, &fo) != CUCD_OK) cucd_shim_die("cuCUDecide_frame");
+  for (int r = 0; r < H / 4; r++) memcpy(obf + (size_t)r * obfStride, &o[(size_t)r * (W / 4)], (W / 4) * sizeof(short));
+  for (int r = 0; r < H; r++) memcpy(outl + (size_t)r * outlStride, &t[(size_t)r * W], W * sizeof(short));
+  s.frameCalls++;
+}
+/* S2: replaces predIntraAng + DistFunc of the 35-mode loop TEncSearch.cpp:2327-2361 by one batch call per PU */
+inline void cucd_shim_rmd(int n, const short* unfExt, const short* org, int orgStride) {
+  CucdShim& s = cucd_shim();
+  int16_t border[4 * 64 + 1], blk[64 * 64];
+  const int sw = 2 * n + 1;
+  for (int i = 0; i < 2 * n; i++) border[i] = unfExt[(2 * n - i) * sw];
+  for (int i = 0; i < sw; i++) border[2 * n + i] = unfExt[i];
+  for (int r = 0; r < n; r++) memcpy(blk + r * n, org + (size_t)r * orgStride, n * sizeof(short));
+  int lg = 0; while ((1 << lg) < n) lg++;
+  cucd_pu_desc d = {(uint8_t)lg, {0, 0, 0}};
+  if (cucd_intra_rmd_batch(s.h, 1, &d, blk, border, s.sad) != CUCD_OK) cucd_shim_die("cucd_intra_rmd_batch");
+  s.rmdCalls++;
+}
+inline unsigned cucd_shim_rmd_sad(int mode) { return cucd_shim().sad[mode]; }
+struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+static CucdShimReport cucd_shim_report_at_exit;
+#endif
+
 /* ---- RMD ------------------------------------------------------------------------------- */
 struct CucdRmdState {
   CucdDump out;
@@ -55,6 +108,9 @@ inline void cucd_hook_rmd_begin(int poc, int x, int y, int n, int bitDepth, cons
   CucdRmdState& s = cucd_rmd();
   s.hdr[0] = 0x444d5243; s.hdr[1] = poc; s.hdr[2] = x; s.hdr[3] = y; s.hdr[4] = n; s.hdr[5] = bitDepth;
   s.unf = unf; s.fil = fil; s.org = org; s.orgStride = orgStride;
+#ifdef CUCD_INTEGRATION
+  cucd_shim_rmd(n, unf, org, orgStride);
+#endif
 }
 inline void cucd_hook_rmd_mode(int mode, unsigned sad) { cucd_rmd().sad[mode] = sad; }
 /* L-shaped (2N+1)-stride array -> linear bottom-left .. top-left .. top-right, 4N+1 samples */
