@@ -79,7 +79,11 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
    "      cucd_hook_rmd_end();\n", "before"),
   ("    uiSad = m_cDistParam.DistFunc(&m_cDistParam);\n\n    // motion cost\n    uiSad += m_pcRdCost->getCost(iSearchX, iSearchY);\n\n    if (uiSad < rcStruct.uiBestSad)",
    "    cucd_hook_me(m_cDistParam.pOrg, m_cDistParam.iStrideOrg, m_cDistParam.pCur, m_cDistParam.iStrideCur, m_cDistParam.iCols, m_cDistParam.iRows,\n"
-   "                 m_cDistParam.iSubShift, m_cDistParam.bitDepth, iSearchX, iSearchY, m_cDistParam.DistFunc(&m_cDistParam));\n", "before"),
+   "                 m_cDistParam.iSubShift, m_cDistParam.bitDepth, iSearchX, iSearchY, m_cDistParam.DistFunc(&m_cDistParam));\n"
+   "#ifdef CUCD_INTEGRATION\n    if (cucd_shim_me_active()) uiSad = cucd_shim_me_sad(iSearchX, iSearchY) + m_pcRdCost->getCost(iSearchX, iSearchY); else\n#endif\n"
+   "    {\n", "before"),
+  ("    uiSad = m_cDistParam.DistFunc(&m_cDistParam);\n\n    // motion cost\n    uiSad += m_pcRdCost->getCost(iSearchX, iSearchY);\n",
+   "    }\n", "after"),
 ])
 # intra luma TU coding (TEncSearch.cpp:1092-1387)
 patch("Lib/TLibCommon/TComTrQuant.h", [
@@ -94,6 +98,26 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
    "                                  useTransformSkip ? m_pcEncCfg->getUseRDOQTS() : m_pcEncCfg->getUseRDOQ(), m_pcTrQuant->cucdTempCoeff(), pcCoeff, uiAbsSum);\n", "before"),
   ("  //===== update distortion =====\n  ruiDist += m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID);\n",
    "  if (bIsLuma) cucd_hook_tu_end(piReco, uiStride, m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID));\n", "after"),
+])
+# S3: integer ME through SAD surfaces (integration build only)
+patch("Lib/TLibEncoder/TEncSearch.cpp", [
+  ("  setWpScalingDistParam(pcCU, iRefIdxPred, eRefPicList);\n  //  Do integer search\n",
+   "#ifdef CUCD_INTEGRATION\n"
+   "  if (!bBi && m_pcEncCfg->getFastSearch() != SELECTIVE) {   /* INTEGRATION.md S3 */\n"
+   "    TComPicYuv* cucdRef = pcCU->getSlice()->getRefPic(eRefPicList, iRefIdxPred)->getPicYuvRec();\n"
+   "    TComPicYuv* cucdOrg = pcCU->getPic()->getPicYuvOrg();\n"
+   "    const long cucdOff = (long)(piRefY - cucdRef->getAddr(COMPONENT_Y));\n"
+   "    const int cucdPuY = (int)(cucdOff / iRefStride), cucdPuX = (int)(cucdOff - (long)cucdPuY * iRefStride);\n"
+   "    cucd_shim_me_begin(cucdOrg->getWidth(COMPONENT_Y), cucdOrg->getHeight(COMPONENT_Y), g_bitDepth[CHANNEL_TYPE_LUMA],\n"
+   "                       pcCU->getSlice()->getSPS()->getUseStrongIntraSmoothing() ? 1 : 0, pcCU->getSlice()->getPOC(),\n"
+   "                       cucdOrg->getAddr(COMPONENT_Y), cucdOrg->getStride(COMPONENT_Y), cucdRef, cucdRef->getAddr(COMPONENT_Y), iRefStride,\n"
+   "                       cucdRef->getMarginX(COMPONENT_Y), cucdRef->getMarginY(COMPONENT_Y), pcCU->getCUPelX(), pcCU->getCUPelY(), cucdPuX, cucdPuY,\n"
+   "                       iRoiWidth, iRoiHeight, (m_pcEncCfg->getUseFastEnc() && iRoiHeight > 8) ? 1 : 0);\n"
+   "  }\n#endif\n", "after"),
+  ("  m_pcRdCost->setCostScale(1);\n\n  const Bool bIsLosslessCoded",
+   "#ifdef CUCD_INTEGRATION\n  cucd_shim_me_end();\n#endif\n", "before"),
+  ("      uiSad = m_cDistParam.DistFunc(&m_cDistParam);\n\n      // motion cost\n      uiSad += m_pcRdCost->getCost(x, y);\n",
+   "#ifdef CUCD_INTEGRATION\n      if (cucd_shim_me_active()) uiSad = cucd_shim_me_sad(x, y) + m_pcRdCost->getCost(x, y);\n#endif\n", "after"),
 ])
 # S1 call site (TEncGOP.cpp:1095-1096)
 patch("Lib/TLibEncoder/TEncGOP.cpp", [

@@ -80,7 +80,61 @@ inline void cucd_shim_rmd(int n, const short* unfExt, const short* org, int orgS
   s.rmdCalls++;
 }
 inline unsigned cucd_shim_rmd_sad(int mode) { return cucd_shim().sad[mode]; }
-struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+/* S3: integer motion estimation (uni-directional search).  xMotionEstimation opens a PU/reference pair; every SAD the
+ * search asks for (xTZSearchHelp TEncSearch.cpp:421, xPatternSearch :3924) is read from SAD surfaces computed by
+ * cucd_me_sad_surface.  The TZ search re-centres its window on the best start point (TEncSearch.cpp:4034-4047), so the shim
+ * asks for 128x128-candidate tiles of the legal MV area (TComDataCU::clipMv) on demand instead of one fixed window. */
+#include <map>
+struct CucdMeShim {
+  bool active; int curPoc, nRefs; const void* refKey[64];
+  cucd_me_desc d; int minX, maxX, minY, maxY;
+  std::map<long, std::vector<uint32_t> > tiles;
+  long pus, tilesComputed, probes;
+  CucdMeShim() : active(false), curPoc(-1000000), nRefs(0), pus(0), tilesComputed(0), probes(0) {}
+};
+inline CucdMeShim& cucd_me_shim() { static CucdMeShim s; return s; }
+inline bool cucd_shim_me_active() { return cucd_me_shim().active; }
+inline void cucd_shim_me_begin(int W, int H, int bd, int strong, int curPoc, const short* orgY, int orgStride, const void* refKey, const short* refY,
+                               int refStride, int marginX, int marginY, int cuX, int cuY, int puX, int puY, int w, int h, int subShift) {
+  cucd_shim_open(W, H, bd, strong);
+  CucdShim& s = cucd_shim(); CucdMeShim& m = cucd_me_shim();
+  if (curPoc != m.curPoc) {
+    if (cucd_set_cur_picture(s.h, orgY, orgStride) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");
+    m.curPoc = curPoc; m.nRefs = 0;
+  }
+  int slot = -1;
+  for (int i = 0; i < m.nRefs; i++) if (m.refKey[i] == refKey) slot = i;
+  if (slot < 0) {
+    slot = m.nRefs++; m.refKey[slot] = refKey;
+    if (cucd_set_ref_picture(s.h, slot, refY, refStride, marginX, marginY) != CUCD_OK) cucd_shim_die("cucd_set_ref_picture");
+  }
+  m.d.x = puX; m.d.y = puY; m.d.w = w; m.d.h = h; m.d.ref_idx = slot; m.d.sub_shift = subShift;
+  m.minX = -(64 + 8 + cuX - 1); m.maxX = W + 8 - cuX - 1;          /* TComDataCU::clipMv, TComDataCU.cpp:2946-2958, in integer pels */
+  m.minY = -(64 + 8 + cuY - 1); m.maxY = H + 8 - cuY - 1;
+  m.tiles.clear(); m.active = true; m.pus++;
+}
+inline void cucd_shim_me_end() { cucd_me_shim().active = false; }
+inline unsigned cucd_shim_me_sad(int x, int y) {
+  CucdShim& s = cucd_shim(); CucdMeShim& m = cucd_me_shim();
+  if (x < m.minX || x > m.maxX || y < m.minY || y > m.maxY) { fprintf(stderr, "cucd shim: ME probe (%d,%d) outside the legal MV area\n", x, y); exit(1); }
+  const int tx = (x + 4096) >> 7, ty = (y + 4096) >> 7;
+  const long key = (long)ty * 4096 + tx;
+  cucd_me_desc d = m.d;
+  d.left = (tx << 7) - 4096; d.right = d.left + 127; d.top = (ty << 7) - 4096; d.bottom = d.top + 127;
+  if (d.left < m.minX) d.left = m.minX; if (d.right > m.maxX) d.right = m.maxX;
+  if (d.top < m.minY) d.top = m.minY; if (d.bottom > m.maxY) d.bottom = m.maxY;
+  std::map<long, std::vector<uint32_t> >::iterator it = m.tiles.find(key);
+  if (it == m.tiles.end()) {
+    std::vector<uint32_t> surf((size_t)(d.right - d.left + 1) * (d.bottom - d.top + 1));
+    if (cucd_me_sad_surface(s.h, 1, &d, surf.data()) != CUCD_OK) cucd_shim_die("cucd_me_sad_surface");
+    it = m.tiles.insert(std::make_pair(key, std::vector<uint32_t>())).first;
+    it->second.swap(surf);
+    m.tilesComputed++;
+  }
+  m.probes++;
+  return it->second[(size_t)(y - d.top) * (d.right - d.left + 1) + (x - d.left)];
+}
+struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;
 #endif
 
@@ -134,6 +188,9 @@ inline void cucd_hook_rmd_end() {
 }
 
 /* ---- integer ME probe ------------------------------------------------------------------ */
+#ifdef CUCD_INTEGRATION
+#define cucd_hook_me(...) ((void)0)       /* its last argument evaluates the CPU SAD */
+#else
 inline void cucd_hook_me(const short* org, int orgStride, const short* ref, int refStride, int cols, int rows,
                          int subShift, int bitDepth, int mvx, int mvy, unsigned sad) {
   static CucdDump out; static long cnt = 0; static long every = -1;
@@ -146,6 +203,7 @@ inline void cucd_hook_me(const short* org, int orgStride, const short* ref, int 
   for (int r = 0; r < rows; r++) fwrite(org + r * orgStride, 2, cols, f);
   for (int r = 0; r < rows; r++) fwrite(ref + r * refStride, 2, cols, f);
 }
+#endif
 
 /* ---- OBF / outlier picture pass -------------------------------------------------------- */
 inline void cucd_hook_obf_yc(const double* yc, int n) {

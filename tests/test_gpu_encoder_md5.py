@@ -19,17 +19,19 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
-def _encode(binary, wd, W, H, frames, bd, qp, extra):
+def _encode(binary, wd, W, H, frames, bd, qp, cfg):
     import gen_golden as gg
     args = [os.path.join(REF, binary), "-i", "clip.yuv", "-wdt", str(W), "-hgt", str(H), "-f", str(frames), "-q", str(qp), "-b", "out.bin",
-            "-o", "rec.yuv", f"--InputBitDepth={bd}", f"--InternalBitDepth={bd}", "--Profile=" + ("main10" if bd > 8 else "main")] + gg.COMMON + gg.AI + extra
+            "-o", "rec.yuv", f"--InputBitDepth={bd}", f"--InternalBitDepth={bd}", "--Profile=" + ("main10" if bd > 8 else "main")] + gg.COMMON + cfg
     r = subprocess.run(args, cwd=wd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r
 
 
-@pytest.mark.parametrize("bd,frames,qp", [(8, 5, 32), (10, 2, 27)])
-def test_bitstream_md5_matches_reference_encoder(bd, frames, qp):
+@pytest.mark.parametrize("cfg,bd,frames,qp", [("AI", 8, 5, 32), ("AI", 10, 2, 27), ("LDP", 8, 3, 32)])
+def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
+    """AI: S1 + S2 on the GPU (5 frames reach the fork's Testing state, so the OBF-driven early decisions are live);
+    LDP (I + 2 P pictures, TZ search range 64, AMP): additionally every integer-ME SAD of the uni-directional searches (S3)."""
     import gen_golden as gg
     for b in ("TAppEncoder", "TAppEncoderCucd", "TAppDecoder"):
         if not os.path.exists(os.path.join(REF, b)):
@@ -40,14 +42,18 @@ def test_bitstream_md5_matches_reference_encoder(bd, frames, qp):
     for binary in ("TAppEncoder", "TAppEncoderCucd"):
         with tempfile.TemporaryDirectory(prefix="cucd_md5_") as wd:
             open(os.path.join(wd, "clip.yuv"), "wb").write(clip)
-            r = _encode(binary, wd, W, H, frames, bd, qp, [])
+            r = _encode(binary, wd, W, H, frames, bd, qp, gg.AI if cfg == "AI" else gg.LDP)
             bits = open(os.path.join(wd, "out.bin"), "rb").read()
             rec = open(os.path.join(wd, "rec.yuv"), "rb").read()
             out[binary] = (hashlib.md5(bits).hexdigest(), hashlib.md5(rec).hexdigest(), len(bits))
             if binary == "TAppEncoderCucd":
                 assert "RMD PUs on the GPU" in r.stderr, r.stderr[-500:]          # the GPU path really ran
                 n_gpu = int(r.stderr.split("pictures,")[1].split("RMD PUs")[0])
-                assert n_gpu > 1000 * frames
+                assert n_gpu > 1000
+                if cfg == "LDP":
+                    n_me = int(r.stderr.split("GPU,")[1].split("ME searches")[0])
+                    assert n_me > 1000
+                print(r.stderr.strip().splitlines()[-1])
                 d = subprocess.run([os.path.join(REF, "TAppDecoder"), "-b", "out.bin", "-o", "dec.yuv", "-d", "0"],
                                    cwd=wd, capture_output=True, text=True, timeout=300)
                 assert d.returncode == 0
