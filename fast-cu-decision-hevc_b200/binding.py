@@ -66,7 +66,7 @@ class _MeDesc(C.Structure):
 
 
 class _TuDesc(C.Structure):
-    _fields_ = [("log2_size", C.c_uint8), ("mode", C.c_uint8), ("qp", C.c_int8), ("transform_skip", C.c_uint8)]
+    _fields_ = [("log2_size", C.c_uint8), ("mode", C.c_uint8), ("qp", C.c_int8), ("flags", C.c_uint8)]
 
 
 TU_INTRA_SLICE, TU_SIGN_HIDING = 1, 2
@@ -335,12 +335,14 @@ class Engine:
     # ---- intra luma TU coding (xIntraCodingTUBlock) ------------------------------------------------
     @staticmethod
     def _tu_descs(tus):
-        """tus: iterable of (log2_size, mode, qp, transform_skip)"""
+        """tus: iterable of (log2_size, mode, qp, transform_skip[, chroma])"""
         tus = list(tus)
         arr = (_TuDesc * max(len(tus), 1))()
         total = 0
-        for i, (l, m, q, ts) in enumerate(tus):
-            arr[i].log2_size, arr[i].mode, arr[i].qp, arr[i].transform_skip = int(l), int(m), int(q), int(ts)
+        for i, tu in enumerate(tus):
+            l, m, q, ts = tu[:4]
+            chroma = tu[4] if len(tu) > 4 else 0
+            arr[i].log2_size, arr[i].mode, arr[i].qp, arr[i].flags = int(l), int(m), int(q), (1 if ts else 0) | (2 if chroma else 0)
             total += 1 << (2 * int(l))
         return tus, arr, total
 

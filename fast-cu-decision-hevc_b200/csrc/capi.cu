@@ -756,9 +756,9 @@ static int tu_batch(cucd_handle* h, const char* who, int stage, int flags, int n
     const cucd_tu_desc& d = desc[i];
     if (d.log2_size < 2 || d.log2_size > 5) return fail(h, CUCD_ERR_INVALID, std::string(who) + ": log2_size must be 2..5");
     if (d.mode > 34 || d.qp < 0 || d.qp > 51) return fail(h, CUCD_ERR_INVALID, std::string(who) + ": mode must be 0..34 and qp 0..51");
-    if (d.transform_skip && d.log2_size != 2) return fail(h, CUCD_ERR_UNSUPPORTED, std::string(who) + ": transform skip is a 4x4 tool (log2MaxTransformSkipSize = 2)");
+    if ((d.flags & CUCD_TU_TRANSFORM_SKIP) && d.log2_size != 2) return fail(h, CUCD_ERR_UNSUPPORTED, std::string(who) + ": transform skip is a 4x4 tool (log2MaxTransformSkipSize = 2)");
     const int n = 1 << d.log2_size;
-    TuJob j; j.orgOff = (int32_t)orgOff; j.borderOff = (int32_t)borderOff; j.outIndex = i; j.mode = d.mode; j.ts = d.transform_skip ? 1 : 0; j.qp = d.qp; j.pad = 0;
+    TuJob j; j.orgOff = (int32_t)orgOff; j.borderOff = (int32_t)borderOff; j.outIndex = i; j.mode = d.mode; j.ts = d.flags & (CUCD_TU_TRANSFORM_SKIP | CUCD_TU_CHROMA); j.qp = d.qp; j.pad = 0;
     jobs[d.log2_size].push_back(j);
     orgOff += (size_t)n * n; borderOff += (size_t)4 * n + 1;
     if (orgOff > 0x7fffffffull) return fail(h, CUCD_ERR_INVALID, std::string(who) + ": batch too large");

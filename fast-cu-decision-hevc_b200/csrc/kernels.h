@@ -58,7 +58,7 @@ struct TuJob {
   int32_t orgOff;      // sample offset of the TU's source block (and of its coef / level / pred / reco blocks)
   int32_t borderOff;   // sample offset of its 4N+1 border
   int32_t outIndex;    // TU index in the caller's order (dist / absSum)
-  uint8_t mode, ts;    // intra mode 0..34, transform skip
+  uint8_t mode, ts;    // intra mode 0..34; bit 0 transform skip, bit 1 chroma block (cucd_tu_desc.flags)
   int8_t qp; uint8_t pad;
 };
 struct TuBatch {

@@ -65,14 +65,14 @@ __device__ __forceinline__ bool tu_use_filtered(int lg, int mode) {
 }
 
 // one predicted sample at (row r, col c); b = the border the mode reads (linear 4N+1: left bottom->top, corner, above left->right)
-__device__ int tu_predict(const int16_t* b, int n, int lg, int mode, int bitDepth, int r, int c, int dc) {
+__device__ int tu_predict(const int16_t* b, int n, int lg, int mode, int bitDepth, int r, int c, int dc, bool luma) {
   const int n2 = 2 * n;
   const int16_t* top = b + n2 + 1;
   if (mode == 0) {                                                                                     // TComPrediction.cpp:755-805
     return ((n - 1 - c) * b[n2 - 1 - r] + (c + 1) * top[n] + (n - 1 - r) * top[c] + (r + 1) * b[n2 - 1 - n] + n) >> (lg + 1);
   }
   if (mode == 1) {                                                                                     // :183-222, 818-841
-    if (n > 16) return dc;
+    if (n > 16 || !luma) return dc;                                                                    // xDCPredFiltering: luma only
     if (r == 0 && c == 0) return (top[0] + b[n2 - 1] + 2 * dc + 2) >> 2;
     if (r == 0) return (top[c] + 3 * dc + 2) >> 2;
     if (c == 0) return (b[n2 - 1 - r] + 3 * dc + 2) >> 2;
@@ -86,7 +86,7 @@ __device__ int tu_predict(const int16_t* b, int n, int lg, int mode, int bitDept
   const int sMain = vertical ? 1 : -1;                             // main(i) = b[n2 + sMain*i], side(i) = b[n2 - sMain*i]
   if (angle == 0) {
     int v = b[n2 + sMain * (x + 1)];
-    if (x == 0 && n <= 16) v = clip3i(0, (1 << bitDepth) - 1, v + ((b[n2 - sMain * (y + 1)] - b[n2]) >> 1));      // :356-362
+    if (x == 0 && n <= 16 && luma) v = clip3i(0, (1 << bitDepth) - 1, v + ((b[n2 - sMain * (y + 1)] - b[n2]) >> 1));      // :356-362
     return v;
   }
   const int delta = (y + 1) * angle, di = delta >> 5, df = delta & 31;
@@ -119,7 +119,8 @@ intra_tu_kernel(const TuBatch tb) {
   const int tuIdx = blockIdx.x * TUS + grp;
   const bool live = tuIdx < tb.count;
   const TuJob job = live ? tb.jobs[tuIdx] : TuJob{0, 0, 0, 0, 0, 0, 0};
-  const int bd = tb.bitDepth, mode = job.mode, ts = job.ts;
+  const int bd = tb.bitDepth, mode = job.mode, ts = job.ts & 1;
+  const bool luma = !(job.ts & 2);
 
   for (int i = tid; i < 32 * 32; i += 256) {
     const int k = i >> 5, x = i & 31;
@@ -156,13 +157,13 @@ intra_tu_kernel(const TuBatch tb) {
   // ---- prediction, residual ---------------------------------------------------------------------------------------------
   const int16_t* org = tb.org + job.orgOff;
   {
-    const int16_t* b = tu_use_filtered(LG, mode) ? sFil[grp] : sUnf[grp];
+    const int16_t* b = (luma && tu_use_filtered(LG, mode)) ? sFil[grp] : sUnf[grp];      // chroma of 4:2:0: never smoothed
     int dc = 0;
     if (mode == 1) { int s = 0; for (int i = 0; i < N; i++) s += b[2 * N + 1 + i] + b[2 * N - 1 - i]; dc = (s + N) / (2 * N); }
 #pragma unroll
     for (int e = 0; e < IPT; e++) {
       const int o = t + e * TPT, r = o >> LG, c = o & (N - 1);
-      const int p = live ? tu_predict(b, N, LG, mode, bd, r, c, dc) : 0;
+      const int p = live ? tu_predict(b, N, LG, mode, bd, r, c, dc, luma) : 0;
       sPred[grp][o] = (int16_t)p;
       sA[grp][r * P + c] = live ? org[o] - p : 0;
       if (live && tb.stage == 0 && tb.pred) tb.pred[job.orgOff + o] = (int16_t)p;
@@ -181,7 +182,7 @@ intra_tu_kernel(const TuBatch tb) {
         const int o = t + e * TPT, k = o >> LG, j = o & (N - 1);
         int s = 0;
         if (ts) s = sA[grp][k * P + j] << tshift;           // xTransformSkip: coefficient = residual << shift, no second stage
-        else if (N == 4) { for (int x = 0; x < 4; x++) s += kDst4[k * 4 + x] * sA[grp][j * P + x]; }     // intra luma 4x4: DST (TComTU::useDST)
+        else if (N == 4 && luma) { for (int x = 0; x < 4; x++) s += kDst4[k * 4 + x] * sA[grp][j * P + x]; }     // intra luma 4x4: DST (TComTU::useDST)
         else { for (int x = 0; x < N; x++) s += sT[k * tstep * 32 + x] * sA[grp][j * P + x]; }
         v[e] = ts ? s : (s + add1) >> shift1;
       }
@@ -194,7 +195,7 @@ intra_tu_kernel(const TuBatch tb) {
         const int o = t + e * TPT, k = o >> LG, j = o & (N - 1);
         int s = 0;
         if (ts) s = sA[grp][k * P + j];
-        else if (N == 4) { for (int x = 0; x < 4; x++) s += kDst4[k * 4 + x] * sA[grp][j * P + x]; }
+        else if (N == 4 && luma) { for (int x = 0; x < 4; x++) s += kDst4[k * 4 + x] * sA[grp][j * P + x]; }
         else { for (int x = 0; x < N; x++) s += sT[k * tstep * 32 + x] * sA[grp][j * P + x]; }
         sB[grp][k * P + j] = ts ? s : (s + (1 << (LG + 5))) >> (LG + 6);
       }
@@ -228,7 +229,7 @@ intra_tu_kernel(const TuBatch tb) {
     __syncthreads();
     // ---- sign-bit hiding (signBitHidingHDQ): one thread per 4x4 coefficient group ---------------------------------------
     if (tb.signHiding) {
-      const int scanIdx = N > 8 ? 0 : (abs(mode - 26) <= 4 ? 1 : (abs(mode - 10) <= 4 ? 2 : 0));       // TComDataCU.cpp:3356-3410
+      const int scanIdx = N > (luma ? 8 : 4) ? 0 : (abs(mode - 26) <= 4 ? 1 : (abs(mode - 10) <= 4 ? 2 : 0));       // TComDataCU.cpp:3356-3410
       constexpr int LGG = LG - 2, G = 1 << LGG;
       int gpos = 0;
       if (t < CGS) {
@@ -311,7 +312,7 @@ intra_tu_kernel(const TuBatch tb) {
       const int o = t + e * TPT, j = o >> LG, x = o & (N - 1);
       int s = 0;
       if (ts) s = (int)(int16_t)((sA[grp][j * P + x] + off) >> tshift);                                // xITransformSkip, stored as Pel
-      else if (N == 4) { for (int k = 0; k < 4; k++) s += kDst4[k * 4 + x] * sA[grp][k * P + j]; }
+      else if (N == 4 && luma) { for (int k = 0; k < 4; k++) s += kDst4[k * 4 + x] * sA[grp][k * P + j]; }
       else { for (int k = 0; k < N; k++) s += sT[k * tstep * 32 + x] * sA[grp][k * P + j]; }
       sB[grp][j * P + x] = ts ? s : clip3i(-32768, 32767, (s + 64) >> 7);
     }
@@ -321,7 +322,7 @@ intra_tu_kernel(const TuBatch tb) {
       const int o = t + e * TPT, j = o >> LG, x = o & (N - 1);
       int s = 0;
       if (ts) s = sB[grp][j * P + x];
-      else if (N == 4) { for (int k = 0; k < 4; k++) s += kDst4[k * 4 + x] * sB[grp][k * P + j]; }
+      else if (N == 4 && luma) { for (int k = 0; k < 4; k++) s += kDst4[k * 4 + x] * sB[grp][k * P + j]; }
       else { for (int k = 0; k < N; k++) s += sT[k * tstep * 32 + x] * sB[grp][k * P + j]; }
       v[e] = ts ? s : clip3i(-32768, 32767, (s + (1 << (shift2 - 1))) >> shift2);
     }

@@ -32,7 +32,7 @@ extern "C" {
 
 #define CUCD_NUM_INTRA_MODES 35
 #define CUCD_PUS_PER_CTU 341
-#define CUCD_ABI_VERSION 2
+#define CUCD_ABI_VERSION 3
 
 typedef enum {
   CUCD_OK = 0,
@@ -165,15 +165,23 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
  *   cucd_intra_tu_code     the whole chain with HM's plain quantiser (encoders run with --RDOQ=0): xQuant with flat scaling
  *                          lists (TComTrQuant.cpp:1126-1240) and, with CUCD_TU_SIGN_HIDING, signBitHidingHDQ (:991-1123);
  *                          level = pcCoeff, abs_sum = uiAbsSum (the CBF), reco, dist as above.
- * Limits: luma, 4:2:0 intra TUs of 4..32, flat scaling lists, no transquant bypass / RDPCM / cross-component prediction /
+ * Limits: 4:2:0 intra blocks of 4..32 (luma, or chroma with CUCD_TU_CHROMA), flat scaling lists, no transquant bypass / RDPCM / cross-component prediction /
  * extended precision (all off in the BASELINE configurations).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   uint8_t log2_size;         /* 2..5 */
   uint8_t mode;              /* luma intra mode 0..34 (uiChFinalMode) */
-  int8_t  qp;                /* TComDataCU::getQP(0): luma QP before the bit-depth offset, 0..51 */
-  uint8_t transform_skip;    /* TComDataCU::getTransformSkip, 4x4 TUs only */
+  int8_t  qp;                /* luma: TComDataCU::getQP(0), the QP before the bit-depth offset, 0..51 */
+  uint8_t flags;             /* CUCD_TU_TRANSFORM_SKIP | CUCD_TU_CHROMA */
 } cucd_tu_desc;
+#define CUCD_TU_TRANSFORM_SKIP 1   /* TComDataCU::getTransformSkip, 4x4 blocks only */
+#define CUCD_TU_CHROMA 2           /* a Cb / Cr block of a 4:2:0 picture (estIntraPredChromaQT TEncSearch.cpp:2660 ->
+                                    * xRecurIntraChromaCodingQT -> xIntraCodingTUBlock): unfiltered references only
+                                    * (TComChromaFormat.h:147-150), no DC / edge filters (TComPrediction.cpp:284, 822), DCT only,
+                                    * mode-dependent scan for 4x4 only; mode = uiChFinalMode (DM already resolved to the luma mode),
+                                    * qp = the component's mapped QP (QpParam, TComTrQuant.cpp:66-118) minus the bit-depth offset;
+                                    * dist is the plain SSE - the caller applies m_distortionWeight (TComRdCost.cpp:447-450) */
+/* `flags` argument of cucd_intra_tu_code */
 #define CUCD_TU_INTRA_SLICE 1   /* rounding offset 171/512 instead of 85/512 (TComTrQuant.cpp:1206) */
 #define CUCD_TU_SIGN_HIDING 2   /* PPS sign_data_hiding_enabled_flag */
 int cucd_intra_tu_forward(cucd_handle* h, int nTU, const cucd_tu_desc* desc, const int16_t* org, const int16_t* border,

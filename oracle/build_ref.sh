@@ -91,13 +91,13 @@ patch("Lib/TLibCommon/TComTrQuant.h", [
 ])
 patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("  //===== get residual signal =====\n",
-   "  cucd_hook_tu_pred(bIsLuma, g_iPOC, pcCU->getCUPelX() + blkX, pcCU->getCUPelY() + blkY, uiWidth, uiChFinalMode, g_bitDepth[chType], useTransformSkip, default0Save1Load2 == 2,\n"
+   "  cucd_hook_tu_pred(compID, g_iPOC, pcCU->getCUPelX() + blkX, pcCU->getCUPelY() + blkY, uiWidth, uiChFinalMode, g_bitDepth[chType], useTransformSkip, default0Save1Load2 == 2,\n"
    "                    m_piYuvExt[compID][PRED_BUF_UNFILTERED], piPred, piOrg, uiStride);\n", "before"),
   ("  //--- inverse transform ---\n",
-   "  if (bIsLuma) cucd_hook_tu_coeff(pcCU->getQP(0), pcCU->getSlice()->getSliceType() == I_SLICE, pcCU->getSlice()->getPPS()->getSignHideFlag(),\n"
+   "  cucd_hook_tu_coeff(cQP.Qp - 6 * (g_bitDepth[chType] - 8), pcCU->getSlice()->getSliceType() == I_SLICE, pcCU->getSlice()->getPPS()->getSignHideFlag(),\n"
    "                                  useTransformSkip ? m_pcEncCfg->getUseRDOQTS() : m_pcEncCfg->getUseRDOQ(), m_pcTrQuant->cucdTempCoeff(), pcCoeff, uiAbsSum);\n", "before"),
   ("  //===== update distortion =====\n  ruiDist += m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID);\n",
-   "  if (bIsLuma) cucd_hook_tu_end(piReco, uiStride, m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID));\n", "after"),
+   "  cucd_hook_tu_end(piReco, uiStride, m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, COMPONENT_Y));   /* unweighted SSE */\n", "after"),
 ])
 # S3: integer ME through SAD surfaces (integration build only)
 patch("Lib/TLibEncoder/TEncSearch.cpp", [

@@ -124,21 +124,21 @@ static void predict_planar(int n, const int16_t* b, int16_t* pred) {   /* :755-8
   }
 }
 
-static void predict_dc(int n, const int16_t* b, int16_t* pred) {        /* :183-222, 266-276, 818-841 */
+static void predict_dc(int n, const int16_t* b, int16_t* pred, int luma) {        /* :183-222, 266-276, 818-841 */
   const int n2 = 2 * n;
   const int16_t* top = b + n2 + 1;
   int sum = 0, i, x, y, dc;
   for (i = 0; i < n; i++) sum += top[i] + b[n2 - 1 - i];
   dc = (sum + n) / (2 * n);
   for (i = 0; i < n * n; i++) pred[i] = (int16_t)dc;
-  if (n <= 16) {
+  if (luma && n <= 16) {                                                /* xDCPredFiltering: luma only (:822) */
     pred[0] = (int16_t)((top[0] + b[n2 - 1] + 2 * dc + 2) >> 2);
     for (x = 1; x < n; x++) pred[x] = (int16_t)((top[x] + 3 * dc + 2) >> 2);
     for (y = 1; y < n; y++) pred[y * n] = (int16_t)((b[n2 - 1 - y] + 3 * dc + 2) >> 2);
   }
 }
 
-static void predict_angular(int bitDepth, int n, int mode, const int16_t* b, int16_t* pred) { /* :278-409 */
+static void predict_angular(int bitDepth, int n, int mode, const int16_t* b, int16_t* pred, int luma) { /* :278-409 */
   static const int angTable[9] = {0, 2, 5, 9, 13, 17, 21, 26, 32};
   static const int invAngTable[9] = {0, 4096, 1638, 910, 630, 482, 390, 315, 256};
   const int n2 = 2 * n, vertical = mode >= 18;
@@ -166,7 +166,7 @@ static void predict_angular(int bitDepth, int n, int mode, const int16_t* b, int
       if (angle == 0) v = ref[x + 1];
       else if (df) v = ((32 - df) * ref[x + di + 1] + df * ref[x + di + 2] + 16) >> 5;
       else v = ref[x + di + 1];
-      if (angle == 0 && x == 0 && n <= 16)                          /* :356-362 */
+      if (angle == 0 && x == 0 && n <= 16 && luma)                  /* :284, 356-362: edge filter is luma only */
         v = clip3(0, (1 << bitDepth) - 1, v + ((side[y + 1] - side[0]) >> 1));
       if (vertical) pred[y * n + x] = (int16_t)v; else pred[x * n + y] = (int16_t)v;  /* :397-408 */
     }
@@ -176,8 +176,14 @@ static void predict_angular(int bitDepth, int n, int mode, const int16_t* b, int
 void oracle_predict(int bitDepth, int n, int mode, const int16_t* unf, const int16_t* fil, int16_t* pred) {
   const int16_t* b = oracle_use_filtered(n, mode) ? fil : unf;
   if (mode == 0) predict_planar(n, b, pred);
-  else if (mode == 1) predict_dc(n, b, pred);
-  else predict_angular(bitDepth, n, mode, b, pred);
+  else if (mode == 1) predict_dc(n, b, pred, 1);
+  else predict_angular(bitDepth, n, mode, b, pred, 1);
+}
+/* chroma of 4:2:0 / 4:2:2: unfiltered references only (TComChromaFormat.h:147-150), no DC / edge filters */
+void oracle_predict_chroma(int bitDepth, int n, int mode, const int16_t* unf, int16_t* pred) {
+  if (mode == 0) predict_planar(n, unf, pred);
+  else if (mode == 1) predict_dc(n, unf, pred, 0);
+  else predict_angular(bitDepth, n, mode, unf, pred, 0);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -557,7 +563,14 @@ void oracle_inv_transform_skip(int bitDepth, int n, const int32_t* coeff, int16_
   for (y = 0; y < n; y++) for (x = 0; x < n; x++) resi[y * stride + x] = (int16_t)((coeff[y * n + x] + off) >> sh);
 }
 
-/* TComDataCU::getCoefScanIdx (TComDataCU.cpp:3356-3410) for intra luma: 0 diagonal, 1 horizontal, 2 vertical */
+/* TComDataCU::getCoefScanIdx (TComDataCU.cpp:3356-3410) for intra blocks: 0 diagonal, 1 horizontal, 2 vertical; mode-dependent
+ * scans up to 8x8 luma / 4x4 chroma (4:2:0), `mode` = the final prediction mode of the component */
+int oracle_scan_idx_c(int n, int mode, int chroma) {
+  if (n > (chroma ? 4 : 8)) return 0;
+  if (iabs(mode - 26) <= 4) return 1;
+  if (iabs(mode - 10) <= 4) return 2;
+  return 0;
+}
 int oracle_scan_idx(int n, int mode) {
   if (n > 8) return 0;
   if (iabs(mode - 26) <= 4) return 1;
@@ -664,19 +677,26 @@ uint32_t oracle_sse(int bitDepth, const int16_t* org, int os, const int16_t* cur
 void oracle_intra_tu(int bitDepth, int n, int mode, int qp, int transformSkip, int strongSmoothing, int intraSlice, int signHiding, int stage,
                      const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
                      uint32_t* dist, int32_t* absSum) {
+  oracle_intra_tu_c(bitDepth, n, mode, qp, transformSkip, 0, strongSmoothing, intraSlice, signHiding, stage, org, orgStride, border, coef, level, pred, reco, dist, absSum);
+}
+/* the same for a chroma block of a 4:2:0 picture when chroma != 0: qp = the component's mapped QP minus the bit-depth offset
+ * (QpParam, TComTrQuant.cpp:66-118), the distortion is returned before the chroma weight (TComRdCost.cpp:447-450) */
+void oracle_intra_tu_c(int bitDepth, int n, int mode, int qp, int transformSkip, int chroma, int strongSmoothing, int intraSlice, int signHiding, int stage,
+                       const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
+                       uint32_t* dist, int32_t* absSum) {
   int16_t fil[4 * 32 + 1], p[32 * 32], resi[32 * 32];
   int32_t c[32 * 32], deq[32 * 32];
-  const int useDST = n == 4;                                            /* TComTU::useDST: intra luma 4x4 */
+  const int useDST = n == 4 && !chroma;                                 /* TComTU::useDST: intra luma 4x4 */
   int i, x, y, sum = 0;
-  oracle_filter_border(bitDepth, n, strongSmoothing, border, fil);
-  oracle_predict(bitDepth, n, mode, border, fil, p);
+  if (chroma) oracle_predict_chroma(bitDepth, n, mode, border, p);
+  else { oracle_filter_border(bitDepth, n, strongSmoothing, border, fil); oracle_predict(bitDepth, n, mode, border, fil, p); }
   if (pred) memcpy(pred, p, (size_t)n * n * sizeof(int16_t));
   if (stage != 2) {
     for (y = 0; y < n; y++) for (x = 0; x < n; x++) resi[y * n + x] = (int16_t)(org[y * orgStride + x] - p[y * n + x]);   /* :1207-1224 */
     if (transformSkip) oracle_transform_skip(bitDepth, n, resi, n, c); else oracle_fwd_transform(bitDepth, n, useDST, resi, n, c);
     if (coef) memcpy(coef, c, (size_t)n * n * sizeof(int32_t));
     if (stage == 0) return;
-    sum = oracle_quant(bitDepth, n, qp, intraSlice, signHiding, oracle_scan_idx(n, mode), c, level);
+    sum = oracle_quant(bitDepth, n, qp, intraSlice, signHiding, oracle_scan_idx_c(n, mode, chroma), c, level);
   } else {
     for (i = 0; i < n * n; i++) sum += iabs(level[i]);                  /* only its being non-zero matters (:1271-1291) */
   }

@@ -82,6 +82,14 @@ void oracle_intra_tu(int bitDepth, int n, int mode, int qp, int transformSkip, i
                      const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
                      uint32_t* dist, int32_t* absSum);
 
+/* chroma blocks of a 4:2:0 picture (estIntraPredChromaQT -> xIntraCodingTUBlock): unfiltered references, no DC / edge
+ * filters, DCT only, mode-dependent scan for 4x4 only */
+void oracle_predict_chroma(int bitDepth, int n, int mode, const int16_t* unfiltered, int16_t* pred);
+int  oracle_scan_idx_c(int n, int mode, int chroma);
+void oracle_intra_tu_c(int bitDepth, int n, int mode, int qp, int transformSkip, int chroma, int strongSmoothing, int intraSlice, int signHiding, int stage,
+                       const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
+                       uint32_t* dist, int32_t* absSum);
+
 #ifdef __cplusplus
 }
 #endif

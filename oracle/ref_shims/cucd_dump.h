@@ -241,18 +241,18 @@ struct CucdTuState {
 };
 inline CucdTuState& cucd_tu() { static CucdTuState s; return s; }
 /* TEncSearch.cpp:1207 - after the prediction is in piPred, before the residual */
-inline void cucd_hook_tu_pred(int isLuma, int poc, int x, int y, int n, int mode, int bitDepth, int transformSkip, int loadMode,
+inline void cucd_hook_tu_pred(int compID, int poc, int x, int y, int n, int mode, int bitDepth, int transformSkip, int loadMode,
                               const short* unfExt, const short* pred, const short* org, int stride) {
   CucdTuState& s = cucd_tu();
   s.live = false;
-  if (!isLuma || n > 32) return;
+  if (n > 32) return;
   FILE* f = s.out.get("CUCD_DUMP_TU");
   if (!f) return;
   if (s.every < 0) { const char* e = getenv("CUCD_DUMP_TU_EVERY"); s.every = e ? atol(e) : 53; if (s.every < 1) s.every = 1; }
   if ((s.cnt++ % s.every) != 0) return;
   s.live = true;
   s.hdr[0] = 0x55545243; s.hdr[1] = poc; s.hdr[2] = x; s.hdr[3] = y; s.hdr[4] = n; s.hdr[5] = mode; s.hdr[6] = bitDepth;
-  s.hdr[7] = transformSkip; s.hdr[8] = loadMode;
+  s.hdr[7] = transformSkip; s.hdr[8] = loadMode; s.hdr[15] = compID;
   const int sw = 2 * n + 1;
   for (int i = 0; i < 2 * n; i++) s.border[i] = unfExt[(2 * n - i) * sw];
   for (int i = 0; i <= 2 * n; i++) s.border[2 * n + i] = unfExt[i];
@@ -273,7 +273,7 @@ inline void cucd_hook_tu_end(const short* reco, int stride, unsigned dist) {
   s.live = false;
   FILE* f = s.out.get("CUCD_DUMP_TU");
   const int n = s.hdr[4];
-  s.hdr[14] = (int32_t)dist; s.hdr[15] = 0;
+  s.hdr[14] = (int32_t)dist;
   fwrite(s.hdr, 4, 16, f);
   fwrite(s.border, 2, 4 * n + 1, f);
   fwrite(s.org, 2, n * n, f); fwrite(s.pred, 2, n * n, f);

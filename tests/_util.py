@@ -178,7 +178,7 @@ def all_cus(W, H, depths=(0, 1, 2, 3)):
     return out
 
 
-def oracle_intra_tu(lib, bd, n, mode, qp, ts, org, border, stage, strong=1, intra=1, sbh=1, level_in=None):
+def oracle_intra_tu(lib, bd, n, mode, qp, ts, org, border, stage, strong=1, intra=1, sbh=1, level_in=None, chroma=0):
     """oracle_intra_tu on one TU: returns dict(coef, level, pred, reco, dist, abs_sum)."""
     org = np.ascontiguousarray(org, np.int16)
     border = np.ascontiguousarray(border, np.int16)
@@ -188,12 +188,12 @@ def oracle_intra_tu(lib, bd, n, mode, qp, ts, org, border, stage, strong=1, intr
     reco = np.zeros(n * n, np.int16)
     dist = C.c_uint32(0)
     abs_sum = C.c_int32(0)
-    lib.oracle_intra_tu(bd, n, int(mode), int(qp), int(ts), strong, intra, sbh, stage, P(org, i16p), n, P(border, i16p), P(coef, i32p), P(level, i32p),
+    lib.oracle_intra_tu_c(bd, n, int(mode), int(qp), int(ts), int(chroma), strong, intra, sbh, stage, P(org, i16p), n, P(border, i16p), P(coef, i32p), P(level, i32p),
                         P(pred, i16p), P(reco, i16p), C.byref(dist), C.byref(abs_sum))
     return dict(coef=coef, level=level, pred=pred, reco=reco, dist=dist.value, abs_sum=abs_sum.value)
 
 
-TU_HDR = ("poc", "x", "y", "mode", "bd", "ts", "load", "qp", "intra", "sbh", "rdoq", "abs_sum", "dist")
+TU_HDR = ("poc", "x", "y", "mode", "bd", "ts", "load", "qp", "intra", "sbh", "rdoq", "abs_sum", "dist", "comp")
 
 
 def tu_records(g):
@@ -203,6 +203,7 @@ def tu_records(g):
         for i, h in enumerate(g[tag + "_hdr"]):
             r = dict(zip(TU_HDR, (int(v) for v in h)))
             r["n"] = n
+            r["chroma"] = int(tag[0] == "c")
             for k in ("border", "org", "pred", "coef", "level", "reco"):
                 r[k] = g[tag + "_" + k][i]
             yield r

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Known-answer vectors for the intra luma TU coding path: xIntraCodingTUBlock
-(TEncSearch.cpp:1092-1387) = predIntraAng -> residual -> TComTrQuant::transformNxN -> invTransformNxN -> reconstruction ->
+(TEncSearch.cpp:1092-1387; luma and, for SURVEY 8f.4, the Cb/Cr blocks of estIntraPredChromaQT) = predIntraAng -> residual -> TComTrQuant::transformNxN -> invTransformNxN -> reconstruction ->
 SSE, dumped from the REAL reference encoder's own call sites (hooks cucd_hook_tu_* of oracle/ref_shims/cucd_dump.h).
 
 Three encoder runs on small seeded clips:
@@ -30,7 +30,7 @@ def read_tu(path):
         assert hdr[0] == 0x55545243
         n = hdr[4]
         r = dict(poc=hdr[1], x=hdr[2], y=hdr[3], n=n, mode=hdr[5], bd=hdr[6], ts=hdr[7], load=hdr[8], qp=hdr[9], intra=hdr[10],
-                 sbh=hdr[11], rdoq=hdr[12], abs_sum=hdr[13], dist=hdr[14] & 0xFFFFFFFF)
+                 sbh=hdr[11], rdoq=hdr[12], abs_sum=hdr[13], dist=hdr[14] & 0xFFFFFFFF, comp=hdr[15])
         r["border"] = np.frombuffer(data, np.int16, 4 * n + 1, off).copy(); off += 2 * (4 * n + 1)
         r["org"] = np.frombuffer(data, np.int16, n * n, off).copy(); off += 2 * n * n
         r["pred"] = np.frombuffer(data, np.int16, n * n, off).copy(); off += 2 * n * n
@@ -44,9 +44,9 @@ def read_tu(path):
 def pack(recs, quota, seed):
     rng = np.random.default_rng(seed)
     out = {}
-    for n, q in quota.items():
+    for (n, chroma), q in [((n, c), q // (2 if c else 1)) for n, q in quota.items() for c in (0, 1)]:
         for ts in (0, 1):
-            cand = [r for r in recs if r["n"] == n and r["ts"] == ts]
+            cand = [r for r in recs if r["n"] == n and r["ts"] == ts and (r["comp"] > 0) == bool(chroma)]
             if not cand:
                 continue
             # prefer records with non-zero levels (absSum > 0) 3:1, keep every mode represented
@@ -59,8 +59,8 @@ def pack(recs, quota, seed):
                 if cand[i]["mode"] not in seen_modes:
                     chosen.append(i); seen_modes.add(cand[i]["mode"])
             sel = [cand[i] for i in chosen]
-            tag = f"n{n}" + ("ts" if ts else "")
-            out[tag + "_hdr"] = np.array([[r[k] for k in ("poc", "x", "y", "mode", "bd", "ts", "load", "qp", "intra", "sbh", "rdoq", "abs_sum", "dist")]
+            tag = ("c" if chroma else "n") + f"{n}" + ("ts" if ts else "")
+            out[tag + "_hdr"] = np.array([[r[k] for k in ("poc", "x", "y", "mode", "bd", "ts", "load", "qp", "intra", "sbh", "rdoq", "abs_sum", "dist", "comp")]
                                           for r in sel], np.int64)
             for k in ("border", "org", "pred", "coef", "level", "reco"):
                 out[tag + "_" + k] = np.stack([r[k] for r in sel])

@@ -1,4 +1,4 @@
-"""Parity of the intra luma TU coding kernels (xIntraCodingTUBlock TEncSearch.cpp:1092-1387) through the C ABI:
+"""Parity of the intra TU coding kernels, luma and 4:2:0 chroma blocks (xIntraCodingTUBlock TEncSearch.cpp:1092-1387) through the C ABI:
 against the TU records dumped from the reference encoder's own call sites (tests/golden/tu_*.npz) and against the oracle on
 seeded random TUs.  Integer work: bit-exact."""
 import numpy as np
@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _pack(recs):
-    tus = [(int(np.log2(r["n"])), r["mode"], r["qp"], r["ts"]) for r in recs]
+    tus = [(int(np.log2(r["n"])), r["mode"], r["qp"], r["ts"], r.get("chroma", 0)) for r in recs]
     org = np.concatenate([np.asarray(r["org"], np.int16).ravel() for r in recs])
     brd = np.concatenate([np.asarray(r["border"], np.int16).ravel() for r in recs])
     offs = np.cumsum([0] + [r["n"] ** 2 for r in recs])
@@ -61,6 +61,7 @@ def test_tu_kernels_vs_oracle_random(cucd, oracle, bd):
                     org = rng.choice([0, hi], n * n)
                     brd = rng.choice([0, hi], 4 * n + 1)
                 recs.append(dict(n=n, mode=mode, qp=int(rng.choice([0, 4, 17, 22, 27, 32, 37, 45, 51])), ts=int(n == 4 and rep == 1),
+                                 chroma=int((mode + n) % 4 == 1),
                                  org=org.astype(np.int16), border=brd.astype(np.int16)))
     tus, org, brd, offs = _pack(recs)
     with cucd.Engine(64, 64, bit_depth=bd) as eng:
@@ -71,10 +72,10 @@ def test_tu_kernels_vs_oracle_random(cucd, oracle, bd):
             assert np.array_equal(reco2, reco) and np.array_equal(dist2, dist)          # stage 2 on stage 1's levels = stage 1
             for i, r in enumerate(recs):
                 sl = slice(offs[i], offs[i + 1])
-                w0 = oracle_intra_tu(oracle, bd, r["n"], r["mode"], r["qp"], r["ts"], r["org"], r["border"], 0)
+                w0 = oracle_intra_tu(oracle, bd, r["n"], r["mode"], r["qp"], r["ts"], r["org"], r["border"], 0, chroma=r["chroma"])
                 assert np.array_equal(pred[sl], w0["pred"]) and np.array_equal(coef[sl], w0["coef"]), (r["n"], r["mode"], r["ts"])
                 w1 = oracle_intra_tu(oracle, bd, r["n"], r["mode"], r["qp"], r["ts"], r["org"], r["border"], 1,
-                                     intra=int(bool(flags & cucd.TU_INTRA_SLICE)), sbh=int(bool(flags & cucd.TU_SIGN_HIDING)))
+                                     intra=int(bool(flags & cucd.TU_INTRA_SLICE)), sbh=int(bool(flags & cucd.TU_SIGN_HIDING)), chroma=r["chroma"])
                 assert abs_sum[i] == w1["abs_sum"] and np.array_equal(level[sl], w1["level"]), (r["n"], r["mode"], r["qp"], r["ts"], flags)
                 assert np.array_equal(reco[sl], w1["reco"]) and dist[i] == w1["dist"]
 
