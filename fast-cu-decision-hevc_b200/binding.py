@@ -65,6 +65,10 @@ class _MeDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("x", "y", "w", "h", "ref_idx", "left", "right", "top", "bottom", "sub_shift")]
 
 
+class _SubpelDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("x", "y", "w", "h", "ref_idx", "mvx", "mvy", "use_hadamard")]
+
+
 class _TuDesc(C.Structure):
     _fields_ = [("log2_size", C.c_uint8), ("mode", C.c_uint8), ("qp", C.c_int8), ("flags", C.c_uint8)]
 
@@ -111,6 +115,7 @@ def load_library():
     lib.cucd_set_ref_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.cucd_set_cur_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.cucd_me_sad_surface.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MeDesc), C.c_void_p]
+    lib.cucd_me_subpel_cost.argtypes = [C.c_void_p, C.c_int, C.POINTER(_SubpelDesc), C.c_void_p]
     lib.cucd_intra_tu_forward.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cucd_intra_tu_recon.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cucd_intra_tu_code.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -331,6 +336,17 @@ class Engine:
             res.append(out[off:off + r * c].reshape(r, c))
             off += r * c
         return res
+
+    def me_subpel_cost(self, descs):
+        """descs: list of dicts(x,y,w,h,ref_idx,mvx,mvy,use_hadamard). Returns (n, 7, 7) uint32: [dy+3][dx+3], quarter-pel offsets."""
+        n = len(descs)
+        arr = (_SubpelDesc * max(n, 1))()
+        for i, d in enumerate(descs):
+            for k in ("x", "y", "w", "h", "ref_idx", "mvx", "mvy", "use_hadamard"):
+                setattr(arr[i], k, int(d[k]))
+        out = np.zeros((n, 7, 7), np.uint32)
+        self._check(self.lib.cucd_me_subpel_cost(self.h, n, arr, out.ctypes.data), "cucd_me_subpel_cost")
+        return out
 
     # ---- intra luma TU coding (xIntraCodingTUBlock) ------------------------------------------------
     @staticmethod

@@ -89,6 +89,7 @@ struct cucd_handle {
   std::vector<RefPlane> refs;
   DevBuf<int16_t> dCur; int curStride = 0; bool curSet = false;
   DevBuf<const int16_t*> dRefPtr; DevBuf<int32_t> dRefStride;
+  DevBuf<SubpelJob> dSubJobs;
   DevBuf<TuJob> tJobs; DevBuf<int32_t> tCoef, tAbs; DevBuf<int16_t> tPix; DevBuf<uint32_t> tDist;   // TU coding path
   DevBuf<TmvCu> dTmvCus; DevBuf<double> dDoubles;   // texture features / AQ activity
   DevBuf<MeJob> dJobs; DevBuf<int32_t> dTileJob, dTileIdx; DevBuf<uint32_t> dSad;
@@ -235,7 +236,7 @@ int cucd_destroy(cucd_handle* h) {
   h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
   for (auto& r : h->refs) r.buf.release();
   h->dTmvCus.release(); h->dDoubles.release();
-  h->tJobs.release(); h->tCoef.release(); h->tAbs.release(); h->tPix.release(); h->tDist.release();
+  h->dSubJobs.release(); h->tJobs.release(); h->tCoef.release(); h->tAbs.release(); h->tPix.release(); h->tDist.release();
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release(); h->dJobs.release(); h->dTileJob.release(); h->dTileIdx.release(); h->dSad.release();
   for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
   for (int i = 0; i < cucd_handle::kGroups; i++) { if (h->evUpG[i]) cudaEventDestroy(h->evUpG[i]); if (h->evRmdG[i]) cudaEventDestroy(h->evRmdG[i]); }
@@ -737,6 +738,48 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
   CK(launch_me_sad(mp, h->dJobs.p, nPU, h->dTileJob.p, h->dTileIdx.p, (int)tileJob.size(), h->dSad.p, h->sMain, &h->launches));
   CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   CK(cudaMemcpyAsync(sadOut, h->dSad.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fractional-pel refinement: distortion of the 49 quarter-pel positions around an integer MV
+// ------------------------------------------------------------------------------------------------
+int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, uint32_t* cost) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !cost))) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  const int W = h->cfg.width, H = h->cfg.height;
+  std::vector<SubpelJob> jobs(nPU);
+  for (int i = 0; i < nPU; i++) {
+    const cucd_subpel_desc& d = desc[i];
+    if (d.w < 4 || d.h < 4 || d.w > 64 || d.h > 64 || (d.w & 3) || (d.h & 3) || d.x < 0 || d.y < 0 || d.x + d.w > W || d.y + d.h > H)
+      return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: bad PU");
+    if (d.ref_idx < 0 || d.ref_idx >= (int)h->refs.size() || !h->refs[d.ref_idx].set) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: reference picture not set");
+    const RefPlane& r = h->refs[d.ref_idx];
+    if (d.x + d.mvx - 4 < -r.marginX || d.y + d.mvy - 4 < -r.marginY || d.x + d.mvx + d.w + 4 > W - 1 + r.marginX || d.y + d.mvy + d.h + 4 > H - 1 + r.marginY)
+      return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: the interpolation support leaves the padded reference picture");
+    SubpelJob& j = jobs[i];
+    j.curOff = d.y * h->curStride + d.x;
+    j.refOff = (d.y + d.mvy + r.marginY) * r.stride + d.x + d.mvx + r.marginX;
+    j.refSlot = d.ref_idx; j.w = (int16_t)d.w; j.h = (int16_t)d.h; j.useHadamard = d.use_hadamard ? 1 : 0;
+  }
+  std::vector<const int16_t*> refPtr(h->refs.size(), nullptr);
+  std::vector<int32_t> refStride(h->refs.size(), 0);
+  for (size_t i = 0; i < h->refs.size(); i++) { refPtr[i] = h->refs[i].buf.p; refStride[i] = h->refs[i].stride; }
+  CK(h->dRefPtr.reserve(refPtr.size())); CK(h->dRefStride.reserve(refStride.size()));
+  CK(h->dSubJobs.reserve(jobs.size())); CK(h->dSad.reserve((size_t)nPU * CUCD_SUBPEL_POINTS));
+  CK(cudaMemcpyAsync(h->dRefPtr.p, refPtr.data(), refPtr.size() * sizeof(void*), cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->dRefStride.p, refStride.data(), refStride.size() * 4, cudaMemcpyHostToDevice, h->sMain));
+  CK(cudaMemcpyAsync(h->dSubJobs.p, jobs.data(), jobs.size() * sizeof(SubpelJob), cudaMemcpyHostToDevice, h->sMain));
+  MePlanes mp;
+  mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
+  CK(cudaEventRecord(h->evK0, h->sMain));
+  CK(launch_me_subpel(mp, h->dSubJobs.p, nPU, h->dSad.p, h->sMain, &h->launches));
+  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
+  CK(cudaMemcpyAsync(cost, h->dSad.p, (size_t)nPU * CUCD_SUBPEL_POINTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
   CK(cudaStreamSynchronize(h->sMain));
   flush_launches(h);
   return CUCD_OK;

@@ -87,6 +87,15 @@ struct MePlanes {
   const int32_t* refStride;   // device array
   int bitDepth;
 };
+struct SubpelJob {
+  int32_t curOff;      // PU origin inside the current picture plane
+  int32_t refOff;      // the PU origin displaced by the INTEGER mv inside the padded reference plane
+  int32_t refSlot;
+  int16_t w, h;
+  int32_t useHadamard;
+};
+// out[job][49]: distortion at quarter-pel offsets (dy+3)*7 + (dx+3), dx, dy = -3..3 around the integer mv
+cudaError_t launch_me_subpel(const MePlanes& mp, const SubpelJob* jobs, int nJobs, uint32_t* out, cudaStream_t st, int* launches);
 cudaError_t launch_me_sad(const MePlanes& mp, const MeJob* jobs, int nJobs, const int32_t* tileJob, const int32_t* tileIdx, int nTiles,
                           uint32_t* out, cudaStream_t st, int* launches);
 

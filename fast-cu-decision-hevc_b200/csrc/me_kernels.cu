@@ -67,6 +67,126 @@ me_sad_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* 
   out[job.outOff + (long long)dy * cols + dx] = ((uint32_t)acc << job.subShift) >> (mp.bitDepth - 8);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fractional-pel refinement: xPatternSearchFracDIF TEncSearch.cpp:4340-4376 = xExtDIFUpSamplingH / Q
+// (:5431-5637) + xPatternRefinement (:808-865).  Every candidate block of the reference's half- and quarter-pel stages is the
+// separable 8-tap luma interpolation (TComInterpolationFilter.cpp:57-290: rows into 14-bit intermediates, then columns with
+// rounding and clipping; filterCopy for zero fractions) of the reference at that quarter-pel position, compared with the source
+// block by xGetHADs (8x8 tiles when both sizes are multiples of 8, else 4x4) or xGetSAD.  The kernel returns the distortion of all
+// 49 positions within +-3 quarter pels of the integer MV; the host walks the two 9-point stages and adds getCost(mv).
+// One CTA = one PU and one horizontal offset dx: the reference window is staged once, filtered horizontally once, and the seven
+// vertical offsets reuse those intermediates.
+// ---------------------------------------------------------------------------------------------------------------------
+__constant__ int8_t kLumaFilter[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+
+template <int T>   // T x T Hadamard of (a - b), returns sum |coefficient|
+__device__ __forceinline__ int hadamard_abs_sum(const int16_t* a, int as, const int16_t* b, int bs) {
+  int m[T * T];
+#pragma unroll
+  for (int y = 0; y < T; y++)
+#pragma unroll
+    for (int x = 0; x < T; x++) m[y * T + x] = a[y * as + x] - b[y * bs + x];
+#pragma unroll
+  for (int y = 0; y < T; y++)
+#pragma unroll
+    for (int len = 1; len < T; len <<= 1)
+#pragma unroll
+      for (int j = 0; j < T; j++)
+        if (!(j & len)) { const int p = m[y * T + j], q = m[y * T + j + len]; m[y * T + j] = p + q; m[y * T + j + len] = p - q; }
+#pragma unroll
+  for (int x = 0; x < T; x++)
+#pragma unroll
+    for (int len = 1; len < T; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < T; i++)
+        if (!(i & len)) { const int p = m[i * T + x], q = m[(i + len) * T + x]; m[i * T + x] = p + q; m[(i + len) * T + x] = p - q; }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < T * T; i++) s += abs(m[i]);
+  return s;
+}
+
+constexpr int kSpWinPitch = 64 + 10;      // int16 per staged window row (w + 9 <= 73)
+
+__global__ void __launch_bounds__(256)
+me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t* __restrict__ out) {
+  __shared__ __align__(16) int16_t sCur[64 * 64];
+  __shared__ __align__(16) int16_t sWin[(64 + 9) * kSpWinPitch];
+  __shared__ __align__(16) int16_t sHor[(64 + 9) * 64];
+  __shared__ __align__(16) int16_t sPred[64 * 64];
+  __shared__ int sSum;
+  const int tid = threadIdx.x;
+  const SubpelJob job = jobs[blockIdx.x];
+  const int w = job.w, h = job.h, bd = mp.bitDepth, head = 14 - bd;
+  const int dx = (int)blockIdx.y - 3, ix = dx >> 2, fx = dx & 3;
+
+  const int16_t* cur = mp.cur + job.curOff;
+  for (int i = tid; i < w * h; i += 256) { const int y = i / w, x = i - y * w; sCur[i] = cur[(size_t)y * mp.curStride + x]; }
+  const int refStride = mp.refStride[job.refSlot];
+  const int16_t* ref = mp.ref[job.refSlot] + job.refOff - 4 * (long long)refStride - 4;       // window origin (-4, -4) from the integer MV position
+  for (int i = tid; i < (h + 9) * (w + 9); i += 256) { const int y = i / (w + 9), x = i - y * (w + 9); sWin[y * kSpWinPitch + x] = ref[(long long)y * refStride + x]; }
+  __syncthreads();
+  // rows of the window -> 14-bit intermediates at horizontal fraction fx (filterHor, isFirst, !isLast)
+  for (int i = tid; i < (h + 9) * w; i += 256) {
+    const int r = i / w, c = i - r * w;
+    const int16_t* s = &sWin[r * kSpWinPitch + c + 4 + ix];
+    int v;
+    if (fx == 0) v = (s[0] << head) - 8192;
+    else {
+      int sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += s[k - 3] * kLumaFilter[fx][k];
+      v = (sum - (8192 << (6 - head))) >> (6 - head);
+    }
+    sHor[r * w + c] = (int16_t)v;
+  }
+  __syncthreads();
+  const bool tile8 = !(w & 7) && !(h & 7);
+  const int T = tile8 ? 8 : 4, tilesX = w / T, nTiles = tilesX * (h / T);
+  for (int dy = -3; dy <= 3; dy++) {
+    const int iy = dy >> 2, fy = dy & 3;
+    if (tid == 0) sSum = 0;
+    for (int i = tid; i < w * h; i += 256) {                 // columns (filterVer, !isFirst, isLast)
+      const int r = i / w, c = i - r * w;
+      const int16_t* s = &sHor[(r + 4 + iy) * w + c];
+      int v;
+      if (fy == 0) v = (s[0] + 8192 + (1 << (head - 1))) >> head;
+      else {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += s[(k - 3) * w] * kLumaFilter[fy][k];
+        v = (sum + (1 << (5 + head)) + (8192 << 6)) >> (6 + head);
+      }
+      sPred[i] = (int16_t)min(max(v, 0), (1 << bd) - 1);
+    }
+    __syncthreads();
+    int part = 0;
+    if (job.useHadamard) {
+      for (int t = tid; t < nTiles; t += 256) {
+        const int ty = t / tilesX, tx = t - ty * tilesX;
+        const int o = ty * T * w + tx * T;
+        if (tile8) part += (hadamard_abs_sum<8>(sCur + o, w, sPred + o, w) + 2) >> 2;      // xCalcHADs8x8
+        else part += (hadamard_abs_sum<4>(sCur + o, w, sPred + o, w) + 1) >> 1;            // xCalcHADs4x4
+      }
+    } else {
+      for (int i = tid; i < w * h; i += 256) part += abs(sCur[i] - sPred[i]);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+    if ((tid & 31) == 0 && part) atomicAdd(&sSum, part);
+    __syncthreads();
+    if (tid == 0) out[(size_t)blockIdx.x * 49 + (dy + 3) * 7 + dx + 3] = (uint32_t)sSum >> (bd - 8);
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_me_subpel(const MePlanes& mp, const SubpelJob* jobs, int nJobs, uint32_t* out, cudaStream_t st, int* launches) {
+  if (nJobs <= 0) return cudaSuccess;
+  me_subpel_kernel<<<dim3(nJobs, 7), 256, 0, st>>>(mp, jobs, out);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_me_sad(const MePlanes& mp, const MeJob* jobs, int nJobs, const int32_t* tileJob, const int32_t* tileIdx, int nTiles,
                           uint32_t* out, cudaStream_t st, int* launches) {
   (void)nJobs;

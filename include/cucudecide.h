@@ -150,6 +150,24 @@ int cucd_set_cur_picture(cucd_handle* h, const int16_t* orgY, int stride);
 int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fractional-pel refinement.  Replaces the arithmetic of xPatternSearchFracDIF (TEncSearch.cpp:4340-4376):
+ * xExtDIFUpSamplingH / Q (:5431-5637, the 8-tap interpolation of TComInterpolationFilter.cpp:57-290) and the distortion of
+ * every candidate of xPatternRefinement (:808-865, m_cDistParam.DistFunc at :851).  For PU i and its integer MV (the result of
+ * the integer search) cost[i*49 + (dy+3)*7 + (dx+3)] = xGetHADs (use_hadamard, HadamardME=1) or xGetSAD between the source block
+ * and the reference interpolated at quarter-pel offset (dx, dy), dx, dy = -3..3.  The host walks the 9-point half-pel stage and
+ * the 9-point quarter-pel stage over the table and adds getCost(mv) (strict '<' keeps HM's tie-break).  Pictures as in S3
+ * (cucd_set_cur_picture / cucd_set_ref_picture; the margins must cover the 8-tap support: 4 samples beyond the moved block).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int x, y, w, h;            /* PU position and size in luma samples; w, h multiples of 4, 4..64 */
+  int ref_idx;               /* slot given to cucd_set_ref_picture */
+  int mvx, mvy;              /* integer-pel MV the refinement is centred on */
+  int use_hadamard;          /* m_pcEncCfg->getUseHADME() && !lossless (TEncSearch.cpp:822) */
+} cucd_subpel_desc;
+#define CUCD_SUBPEL_POINTS 49
+int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, uint32_t* cost);
+
+/* ------------------------------------------------------------------------------------------------
  * Intra luma TU coding: the arithmetic of TEncSearch::xIntraCodingTUBlock (TEncSearch.cpp:1092-1387) for a
  * batch of luma TUs with caller-supplied borders, packed like S2: org holds the N*N source blocks back to back, border
  * the 4N+1 unfiltered reference arrays; coef / level / pred / reco use the layout of org (N*N per TU, row-major; coefficient

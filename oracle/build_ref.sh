@@ -99,6 +99,14 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("  //===== update distortion =====\n  ruiDist += m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID);\n",
    "  cucd_hook_tu_end(piReco, uiStride, m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, COMPONENT_Y));   /* unweighted SSE */\n", "after"),
 ])
+# fractional-pel refinement candidates (TEncSearch.cpp:808-865, 4340-4376)
+patch("Lib/TLibEncoder/TEncSearch.cpp", [
+  ("  //  Half-pel refinement\n  xExtDIFUpSamplingH(&cPatternRoi, biPred);\n",
+   "  cucd_hook_frac_begin(piRefY + iOffset, iRefStride);\n", "before"),
+  ("    uiDist = m_cDistParam.DistFunc(&m_cDistParam);\n    uiDist += m_pcRdCost->getCost(cMvTest.getHor(), cMvTest.getVer());\n",
+   "    cucd_hook_frac_cand(m_cDistParam.pOrg, m_cDistParam.iStrideOrg, m_cDistParam.iCols, m_cDistParam.iRows, m_cDistParam.bitDepth,\n"
+   "                        m_pcEncCfg->getUseHADME() && bAllowUseOfHadamard, horVal, verVal, m_cDistParam.DistFunc(&m_cDistParam));\n", "before"),
+])
 # S3: integer ME through SAD surfaces (integration build only)
 patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("  setWpScalingDistParam(pcCU, iRefIdxPred, eRefPicList);\n  //  Do integer search\n",

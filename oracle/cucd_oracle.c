@@ -711,3 +711,46 @@ void oracle_intra_tu_c(int bitDepth, int n, int mode, int qp, int transformSkip,
   for (i = 0; i < n * n; i++) reco[i] = (int16_t)clip3(0, (1 << bitDepth) - 1, p[i] + resi[i]);   /* :1360-1381 */
   *dist = oracle_sse(bitDepth, reco, n, org, orgStride, n, n);                                     /* :1385-1386 */
 }
+
+/* ===================================================================================================
+ * SURVEY.md 8f.3 - fractional-pel motion-estimation refinement: xPatternSearchFracDIF TEncSearch.cpp:4340-4376,
+ * xExtDIFUpSamplingH / Q :5431-5637, xPatternRefinement :808-865, TComInterpolationFilter.cpp:57-290.
+ * Every candidate block of the half- and quarter-pel refinement is the separable 8-tap luma interpolation of the reference at
+ * that quarter-pel position: rows first into 14-bit intermediates (filterHor, isFirst, !isLast), then columns (filterVer,
+ * !isFirst, isLast) with rounding and clipping - also for zero fractions, where the "filter" is filterCopy.
+ * =================================================================================================== */
+static const int kLumaFilter[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+/* ref points at the block's top-left sample at the INTEGER part of the position; fx, fy = quarter-pel fractions 0..3 */
+void oracle_interp_luma(int bitDepth, const int16_t* ref, int stride, int w, int h, int fx, int fy, int16_t* out) {
+  const int head = 14 - bitDepth;                       /* IF_INTERNAL_PREC - bitDepth (>= 2 for bit depths <= 12) */
+  int16_t tmp[(64 + 7) * 64];
+  int r, c, k;
+  for (r = 0; r < h + 7; r++) for (c = 0; c < w; c++) {               /* rows -3 .. h+3 */
+    const int16_t* s = ref + (r - 3) * stride + c;
+    int v;
+    if (fx == 0) v = (s[0] << head) - 8192;                           /* filterCopy, isFirst */
+    else { int sum = 0; for (k = 0; k < 8; k++) sum += s[k - 3] * kLumaFilter[fx][k]; v = (sum - (8192 << (6 - head))) >> (6 - head); }
+    tmp[r * w + c] = (int16_t)v;
+  }
+  for (r = 0; r < h; r++) for (c = 0; c < w; c++) {
+    int v;
+    if (fy == 0) v = (tmp[(r + 3) * w + c] + 8192 + (1 << (head - 1))) >> head;      /* filterCopy, isLast */
+    else { int sum = 0; for (k = 0; k < 8; k++) sum += tmp[(r + k) * w + c] * kLumaFilter[fy][k]; v = (sum + (1 << (6 + head - 1)) + (8192 << 6)) >> (6 + head); }
+    out[r * w + c] = (int16_t)clip3(0, (1 << bitDepth) - 1, v);
+  }
+}
+/* distortion of one candidate: quarter-pel MV (qx, qy) relative to refAtZeroMv; Hadamard (xGetHADs) or SAD (xGetSAD, no sub-sampling) */
+uint32_t oracle_subpel_cost(int bitDepth, const int16_t* org, int orgStride, int w, int h, const int16_t* refAtZeroMv, int refStride,
+                            int qx, int qy, int useHadamard) {
+  int16_t pred[64 * 64];
+  oracle_interp_luma(bitDepth, refAtZeroMv + (qy >> 2) * refStride + (qx >> 2), refStride, w, h, qx & 3, qy & 3, pred);
+  if (useHadamard) return oracle_satd(bitDepth, org, orgStride, pred, w, w, h);
+  { uint32_t sum = 0; int x, y; for (y = 0; y < h; y++) for (x = 0; x < w; x++) sum += (uint32_t)iabs(org[y * orgStride + x] - pred[y * w + x]); return sum >> (bitDepth - 8); }
+}
+/* all 49 candidates within +-3 quarter-pels of the integer MV (mvx, mvy): out[(dy+3)*7 + (dx+3)] */
+void oracle_subpel_surface(int bitDepth, const int16_t* org, int orgStride, int w, int h, const int16_t* refAtZeroMv, int refStride,
+                           int mvx, int mvy, int useHadamard, uint32_t* out) {
+  int dx, dy;
+  for (dy = -3; dy <= 3; dy++) for (dx = -3; dx <= 3; dx++)
+    out[(dy + 3) * 7 + dx + 3] = oracle_subpel_cost(bitDepth, org, orgStride, w, h, refAtZeroMv, refStride, 4 * mvx + dx, 4 * mvy + dy, useHadamard);
+}

@@ -82,6 +82,12 @@ void oracle_intra_tu(int bitDepth, int n, int mode, int qp, int transformSkip, i
                      const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
                      uint32_t* dist, int32_t* absSum);
 
+/* ---- fractional-pel ME refinement (TEncSearch.cpp:808-865, 4340-4376, 5431-5637; TComInterpolationFilter.cpp) ---- */
+void oracle_interp_luma(int bitDepth, const int16_t* ref, int stride, int w, int h, int fx, int fy, int16_t* out);
+uint32_t oracle_subpel_cost(int bitDepth, const int16_t* org, int orgStride, int w, int h, const int16_t* refAtZeroMv, int refStride,
+                            int qx, int qy, int useHadamard);
+void oracle_subpel_surface(int bitDepth, const int16_t* org, int orgStride, int w, int h, const int16_t* refAtZeroMv, int refStride,
+                           int mvx, int mvy, int useHadamard, uint32_t* out);
 /* chroma blocks of a 4:2:0 picture (estIntraPredChromaQT -> xIntraCodingTUBlock): unfiltered references, no DC / edge
  * filters, DCT only, mode-dependent scan for 4x4 only */
 void oracle_predict_chroma(int bitDepth, int n, int mode, const int16_t* unfiltered, int16_t* pred);

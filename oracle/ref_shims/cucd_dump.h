@@ -280,5 +280,24 @@ inline void cucd_hook_tu_end(const short* reco, int stride, unsigned dist) {
   fwrite(s.coef, 4, n * n, f); fwrite(s.level, 4, n * n, f);
   for (int r = 0; r < n; r++) fwrite(reco + r * stride, 2, n, f);
 }
+
+/* ---- fractional-pel ME refinement: one record per sampled candidate of xPatternRefinement (TEncSearch.cpp:808-865) ---- */
+struct CucdFracState { const short* ref; int stride; CucdFracState() : ref(0), stride(0) {} };
+inline CucdFracState& cucd_frac() { static CucdFracState s; return s; }
+/* TEncSearch.cpp:4353-4358: the reference block at the integer MV */
+inline void cucd_hook_frac_begin(const short* refAtIntMv, int stride) { cucd_frac().ref = refAtIntMv; cucd_frac().stride = stride; }
+/* TEncSearch.cpp:849-851: (horVal, verVal) = the candidate's offset from the integer MV in quarter pels */
+inline void cucd_hook_frac_cand(const short* org, int orgStride, int w, int h, int bitDepth, int hadamard, int horVal, int verVal, unsigned dist) {
+  static CucdDump out; static long cnt = 0; static long every = -1;
+  FILE* f = out.get("CUCD_DUMP_FRAC");
+  if (!f || !cucd_frac().ref) return;
+  if (every < 0) { const char* e = getenv("CUCD_DUMP_FRAC_EVERY"); every = e ? atol(e) : 211; if (every < 1) every = 1; }
+  if ((cnt++ % every) != 0) return;
+  int32_t hdr[8] = {0x52465243, w, h, bitDepth, hadamard, horVal, verVal, (int32_t)dist};
+  fwrite(hdr, 4, 8, f);
+  for (int r = 0; r < h; r++) fwrite(org + r * orgStride, 2, w, f);
+  const short* ref = cucd_frac().ref; const int rs = cucd_frac().stride;
+  for (int r = -4; r < h + 5; r++) fwrite(ref + r * rs - 4, 2, w + 9, f);      /* window rows/cols -4 .. size+4 */
+}
 #endif /* __cplusplus */
 #endif

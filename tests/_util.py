@@ -207,3 +207,13 @@ def tu_records(g):
             for k in ("border", "org", "pred", "coef", "level", "reco"):
                 r[k] = g[tag + "_" + k][i]
             yield r
+
+
+def frac_records(g):
+    """iterate tests/golden/frac_*.npz: dict(w, h, bd, had, qx, qy, dist, org (h,w), win (h+9, w+9) with origin at (-4,-4))"""
+    oo = wo = 0
+    for w, h, bd, had, qx, qy, dist in g["hdr"]:
+        w, h = int(w), int(h)
+        org = g["org"][oo:oo + w * h].reshape(h, w); oo += w * h
+        win = g["win"][wo:wo + (w + 9) * (h + 9)].reshape(h + 9, w + 9); wo += (w + 9) * (h + 9)
+        yield dict(w=w, h=h, bd=int(bd), had=int(had), qx=int(qx), qy=int(qy), dist=int(dist) & 0xFFFFFFFF, org=org, win=win)
