@@ -102,10 +102,15 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
 # fractional-pel refinement candidates (TEncSearch.cpp:808-865, 4340-4376)
 patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("  //  Half-pel refinement\n  xExtDIFUpSamplingH(&cPatternRoi, biPred);\n",
-   "  cucd_hook_frac_begin(piRefY + iOffset, iRefStride);\n", "before"),
+   "  cucd_hook_frac_begin(piRefY + iOffset, iRefStride);\n"
+   "#ifdef CUCD_INTEGRATION\n  cucd_shim_frac_begin(biPred, pcMvInt->getHor(), pcMvInt->getVer(), m_pcEncCfg->getUseHADME() && !bIsLosslessCoded);   /* INTEGRATION.md 8f.3 */\n#endif\n", "before"),
+  ("  ruiCost = xPatternRefinement(pcPatternKey, baseRefMv, 1, rcMvQter, !bIsLosslessCoded);\n",
+   "#ifdef CUCD_INTEGRATION\n  cucd_shim_frac_end();\n#endif\n", "after"),
   ("    uiDist = m_cDistParam.DistFunc(&m_cDistParam);\n    uiDist += m_pcRdCost->getCost(cMvTest.getHor(), cMvTest.getVer());\n",
    "    cucd_hook_frac_cand(m_cDistParam.pOrg, m_cDistParam.iStrideOrg, m_cDistParam.iCols, m_cDistParam.iRows, m_cDistParam.bitDepth,\n"
-   "                        m_pcEncCfg->getUseHADME() && bAllowUseOfHadamard, horVal, verVal, m_cDistParam.DistFunc(&m_cDistParam));\n", "before"),
+   "                        m_pcEncCfg->getUseHADME() && bAllowUseOfHadamard, horVal, verVal, m_cDistParam.DistFunc(&m_cDistParam));\n"
+   "#ifdef CUCD_INTEGRATION\n    if (cucd_shim_frac_active()) { uiDist = cucd_shim_frac_cost(horVal, verVal); uiDist += m_pcRdCost->getCost(cMvTest.getHor(), cMvTest.getVer()); } else\n#endif\n    {\n", "before"),
+  ("    uiDist = m_cDistParam.DistFunc(&m_cDistParam);\n    uiDist += m_pcRdCost->getCost(cMvTest.getHor(), cMvTest.getVer());\n", "    }\n", "after"),
 ])
 # S3: integer ME through SAD surfaces (integration build only)
 patch("Lib/TLibEncoder/TEncSearch.cpp", [

@@ -134,7 +134,22 @@ inline unsigned cucd_shim_me_sad(int x, int y) {
   m.probes++;
   return it->second[(size_t)(y - d.top) * (d.right - d.left + 1) + (x - d.left)];
 }
-struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+/* 8f.3: fractional-pel refinement of the uni-directional searches: xPatternSearchFracDIF asks once for the 49 quarter-pel
+ * positions around the integer MV, xPatternRefinement (TEncSearch.cpp:851) reads its 2 x 9 candidates from that table */
+struct CucdFracShim { bool active; uint32_t cost[49]; long calls; CucdFracShim() : active(false), calls(0) {} };
+inline CucdFracShim& cucd_frac_shim() { static CucdFracShim s; return s; }
+inline bool cucd_shim_frac_active() { return cucd_frac_shim().active; }
+inline void cucd_shim_frac_begin(int biPred, int mvx, int mvy, int useHadamard) {
+  CucdFracShim& f = cucd_frac_shim(); CucdMeShim& m = cucd_me_shim();
+  f.active = false;
+  if (biPred || !cucd_shim().h || m.pus == 0) return;          /* the PU / reference of the integer search that just ended */
+  cucd_subpel_desc d = {m.d.x, m.d.y, m.d.w, m.d.h, m.d.ref_idx, mvx, mvy, useHadamard};
+  if (cucd_me_subpel_cost(cucd_shim().h, 1, &d, f.cost) != CUCD_OK) cucd_shim_die("cucd_me_subpel_cost");
+  f.active = true; f.calls++;
+}
+inline void cucd_shim_frac_end() { cucd_frac_shim().active = false; }
+inline unsigned cucd_shim_frac_cost(int horVal, int verVal) { return cucd_frac_shim().cost[(verVal + 3) * 7 + horVal + 3]; }
+struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;
 #endif
 
@@ -287,6 +302,9 @@ inline CucdFracState& cucd_frac() { static CucdFracState s; return s; }
 /* TEncSearch.cpp:4353-4358: the reference block at the integer MV */
 inline void cucd_hook_frac_begin(const short* refAtIntMv, int stride) { cucd_frac().ref = refAtIntMv; cucd_frac().stride = stride; }
 /* TEncSearch.cpp:849-851: (horVal, verVal) = the candidate's offset from the integer MV in quarter pels */
+#ifdef CUCD_INTEGRATION
+#define cucd_hook_frac_cand(...) ((void)0)     /* its last argument evaluates the CPU distortion */
+#else
 inline void cucd_hook_frac_cand(const short* org, int orgStride, int w, int h, int bitDepth, int hadamard, int horVal, int verVal, unsigned dist) {
   static CucdDump out; static long cnt = 0; static long every = -1;
   FILE* f = out.get("CUCD_DUMP_FRAC");
@@ -299,5 +317,6 @@ inline void cucd_hook_frac_cand(const short* org, int orgStride, int w, int h, i
   const short* ref = cucd_frac().ref; const int rs = cucd_frac().stride;
   for (int r = -4; r < h + 5; r++) fwrite(ref + r * rs - 4, 2, w + 9, f);      /* window rows/cols -4 .. size+4 */
 }
+#endif
 #endif /* __cplusplus */
 #endif

@@ -31,7 +31,8 @@ def _encode(binary, wd, W, H, frames, bd, qp, cfg):
 @pytest.mark.parametrize("cfg,bd,frames,qp", [("AI", 8, 5, 32), ("AI", 10, 2, 27), ("LDP", 8, 3, 32)])
 def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
     """AI: S1 + S2 on the GPU (5 frames reach the fork's Testing state, so the OBF-driven early decisions are live);
-    LDP (I + 2 P pictures, TZ search range 64, AMP): additionally every integer-ME SAD of the uni-directional searches (S3)."""
+    LDP (I + 2 P pictures, TZ search range 64, AMP): additionally every integer-ME SAD of the uni-directional searches (S3) and
+    every candidate of their half-/quarter-pel refinement (8f.3)."""
     import gen_golden as gg
     for b in ("TAppEncoder", "TAppEncoderCucd", "TAppDecoder"):
         if not os.path.exists(os.path.join(REF, b)):
@@ -53,6 +54,7 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
                 if cfg == "LDP":
                     n_me = int(r.stderr.split("GPU,")[1].split("ME searches")[0])
                     assert n_me > 1000
+                    assert int(r.stderr.split("probes) on the GPU,")[1].split("sub-pel")[0]) > 1000
                 print(r.stderr.strip().splitlines()[-1])
                 d = subprocess.run([os.path.join(REF, "TAppDecoder"), "-b", "out.bin", "-o", "dec.yuv", "-d", "0"],
                                    cwd=wd, capture_output=True, text=True, timeout=300)
