@@ -209,6 +209,33 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and allocate its pinned host buffers: first touch) on the CPUs of the NUMA node the GPU hangs off, as a
+    production host would place an encoder instance.  Pinned buffers on the remote socket cost ~20 % of the PCIe D2H rate, and
+    the host-buffer call is D2H bound.  Returns a description for the JSON line; any failure leaves the affinity untouched."""
+    if os.environ.get("BENCH_NO_NUMA_BIND"):
+        return "disabled"
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                           capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = q[-12:] if len(q) >= 12 else q           # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+        if node < 0 or n_nodes < 2:
+            return f"single node (numa_node={node}, nodes={n_nodes})"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node}: no allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} of {n_nodes} ({len(cpus)} CPUs)"
+    except Exception as e:   # noqa: BLE001
+        return f"unavailable ({type(e).__name__})"
+
+
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
@@ -222,6 +249,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -363,7 +391,8 @@ def run_ours(args, rank, world, local_rank):
                 "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "CTU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "ms_per_step": 1e3 * e2e_s / (e2e_steps * n_inst), "instances_per_gpu": n_inst,
-                        "single_instance_value": e2e_single, "single_instance_ms_per_step": 1e3 * e2e_single_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host; cost tables in the packed CTU format of include/cucudecide.h)"},
+                        "single_instance_value": e2e_single, "single_instance_ms_per_step": 1e3 * e2e_single_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host; cost tables in the packed CTU format of include/cucudecide.h)",
+                        "host_numa_binding": numa},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "paths_agree": same}
         print(json.dumps(line))

@@ -402,7 +402,8 @@ static int frames_group(cucd_handle* h, int nPics, const int16_t* const* orgY, i
   //      The feature path (sFeat) needs every source plane and runs beside it. ---------------------------------
   const size_t perPic = (size_t)h->ctusPerPic * kPusPerCtu * kNumModes;
   const size_t perPicPacked = (size_t)h->ctusPerPic * CUCD_PACKED_CTU_BYTES;
-  const int grp = std::max(1, (nPics + 3) / 4);
+  static const int nGroups = [] { const char* e = getenv("CUCD_GROUPS"); const int g = e ? atoi(e) : 8; return std::min(std::max(g, 1), (int)cucd_handle::kGroups); }();
+  const int grp = std::max(1, (nPics + nGroups - 1) / nGroups);
   int gi = 0;
   for (int first = 0; first < nPics; first += grp, gi++) {
     const int n = std::min(grp, nPics - first);
@@ -718,7 +719,8 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
     j.subShift = (int16_t)(special ? d.sub_shift : 0); j.pad = 0;
     j.outOff = total;
     const int cols = d.right - d.left + 1, rows = d.bottom - d.top + 1;
-    const int tiles = ((cols + 31) / 32) * ((rows + 7) / 8);
+    const int tileRows = h->cfg.bit_depth == 8 ? 16 : 8;     // me_sad_u8_kernel covers 32 x 16 candidates per CTA, me_sad_kernel 32 x 8
+    const int tiles = ((cols + 31) / 32) * ((rows + tileRows - 1) / tileRows);
     for (int t = 0; t < tiles; t++) { tileJob.push_back(i); tileIdx.push_back(t); }
     total += (long long)cols * rows;
   }

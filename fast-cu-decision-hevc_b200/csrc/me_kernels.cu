@@ -7,8 +7,9 @@
 // The host walks the TZ pattern over the table and adds getCost(mv) itself, so ties break as in HM.
 //
 // One CTA = one 32x8 tile of candidates of one PU.  The PU and the (w+32)x(h+8) reference window are
-// staged once in shared memory; a lane owns one dx, a warp one dy; samples are handled as packed
-// int16 pairs: |a-b| per half = max-min (VIMNMX.S16x2 x2 + ISUB), accumulated with IDP.2A.
+// staged once in shared memory; a lane owns one dx, a warp one dy.  9/10-bit content: samples as packed
+// int16 pairs, |a-b| per half = max-min (VIMNMX.S16x2 x2 + ISUB), accumulated with IDP.2A.  8-bit content
+// (me_sad_u8_kernel): samples as bytes, VABSDIFF4.U8.ACC.
 #include <cuda_runtime.h>
 #include "rmd_core.cuh"
 #include "kernels.h"
@@ -65,6 +66,63 @@ me_sad_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* 
     }
   }
   out[job.outOff + (long long)dy * cols + dx] = ((uint32_t)acc << job.subShift) >> (mp.bitDepth - 8);
+}
+
+// 8-bit content: the same tile of candidates with samples staged as BYTES - four absolute differences and their accumulation are one
+// VABSDIFF4.U8.ACC, the unaligned reference word of a candidate is two aligned shared-memory words + one PRMT (the second word is
+// the next iteration's first), the source word is a broadcast load: ~1.1 instructions per sample instead of 3.5.
+constexpr int kMe8Pitch = 64 + kMeTileX + 8;         // bytes per staged reference row (multiple of 4, >= w + 31 + 4)
+constexpr int kMe8TileY = 16;                        // candidate rows per CTA: a thread owns dy = warp and warp + 8 (they share the source loads)
+constexpr int kMe8RefRows = 64 + kMe8TileY;
+
+__global__ void __launch_bounds__(256)
+me_sad_u8_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* __restrict__ tileJob, const int32_t* __restrict__ tileIdx,
+                 uint32_t* __restrict__ out) {
+  __shared__ __align__(16) uint8_t sCur[64 * 64];
+  __shared__ __align__(16) uint8_t sRef[kMe8RefRows * kMe8Pitch];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const MeJob job = jobs[tileJob[blockIdx.x]];
+  const int cols = job.right - job.left + 1, rows = job.bottom - job.top + 1;
+  const int tilesX = (cols + kMeTileX - 1) / kMeTileX;
+  const int t = tileIdx[blockIdx.x];
+  const int dx0 = (t % tilesX) * kMeTileX, dy0 = (t / tilesX) * kMe8TileY;
+  const int w = job.w, h = job.h;
+  const int step = 1 << job.subShift;
+
+  // staging: a warp per row, lanes along the row (no divisions); only the rows the sub-sampled SAD reads
+  const int16_t* cur = mp.cur + job.curOff;
+  for (int y = warp * step; y < h; y += 8 * step)
+    for (int x = lane; x < w; x += 32) sCur[y * w + x] = (uint8_t)cur[(size_t)y * mp.curStride + x];
+  const int refStride = mp.refStride[job.refSlot];
+  const int16_t* ref = mp.ref[job.refSlot] + job.refOff + (long long)(job.top + dy0) * refStride + (job.left + dx0);
+  const int winW = min(w + kMeTileX - 1, w + cols - dx0 - 1), winH = min(h + kMe8TileY - 1, h + rows - dy0 - 1);
+  for (int y = warp; y < winH; y += 8)
+    for (int x = lane; x < winW; x += 32) sRef[y * kMe8Pitch + x] = (uint8_t)ref[(long long)y * refStride + x];
+  __syncthreads();
+
+  const int dx = dx0 + lane, dyA = dy0 + warp, dyB = dyA + 8;
+  if (dx >= cols || dyA >= rows) return;
+  const bool hasB = dyB < rows;
+  const uint32_t* cw = reinterpret_cast<const uint32_t*>(sCur);
+  const uint32_t* rw = reinterpret_cast<const uint32_t*>(sRef);
+  const uint32_t sel = 0x3210u + 0x1111u * ((uint32_t)lane & 3u);      // bytes (lane & 3) .. +3 of the 8-byte pair {lo, hi}
+  const int words = w >> 2;                                            // w is a multiple of 4
+  uint32_t accA = 0, accB = 0;
+  for (int y = 0; y < h; y += step) {
+    const int ra = ((y + warp) * kMe8Pitch + lane) >> 2;               // kMe8Pitch is a multiple of 4
+    const int rb = hasB ? ra + 8 * (kMe8Pitch >> 2) : ra;              // rows beyond the window are not staged: keep the reads inside
+    const int cbase = (y * w) >> 2;
+    uint32_t pa = rw[ra], pb = rw[rb];
+    for (int j = 0; j < words; j++) {
+      const uint32_t c = cw[cbase + j];                                // broadcast
+      const uint32_t na = rw[ra + j + 1], nb = rw[rb + j + 1];
+      accA = __vsadu4(c, __byte_perm(pa, na, sel)) + accA;
+      accB = __vsadu4(c, __byte_perm(pb, nb, sel)) + accB;
+      pa = na; pb = nb;
+    }
+  }
+  out[job.outOff + (long long)dyA * cols + dx] = accA << job.subShift;               // bitDepth 8: no final shift
+  if (hasB) out[job.outOff + (long long)dyB * cols + dx] = accB << job.subShift;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -191,7 +249,8 @@ cudaError_t launch_me_sad(const MePlanes& mp, const MeJob* jobs, int nJobs, cons
                           uint32_t* out, cudaStream_t st, int* launches) {
   (void)nJobs;
   if (nTiles <= 0) return cudaSuccess;
-  me_sad_kernel<<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+  if (mp.bitDepth == 8) me_sad_u8_kernel<<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+  else me_sad_kernel<<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
