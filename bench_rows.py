@@ -9,8 +9,8 @@ each on a 1080p-sized workload, and prints ONE JSON line per row:
   e2e      the same call through the C ABI with host buffers, wall clock (pageable numpy buffers, copies inside)
   cpu      the reference's own function (oracle/_ref/libhmref.so, kind "reference") or the oracle port (kind "port") on a
            bounded sample, on `cores` host threads
-Rows: s2 (cucd_intra_rmd_batch), s3 (cucd_me_sad_surface), a12 (cucd_tmv_features), a13 (cucd_aq_activity),
-f2 (cucd_intra_tu_code / _forward / _recon).  Usage: python bench_rows.py [--iters 5] > gpurun_out/rows.jsonl
+Rows: s2 (cucd_intra_rmd_batch), f1 (cucd_queue_*: K concurrent instances), s3 (cucd_me_sad_surface), f3 (cucd_me_subpel_cost),
+a12 (cucd_tmv_features), a13 (cucd_aq_activity), f2 (cucd_intra_tu_code / _forward / _recon).  Usage: python bench_rows.py [--iters 5] > gpurun_out/rows.jsonl
 """
 import argparse
 import ctypes as C
@@ -112,6 +112,20 @@ def main():
     emit("s2_intra_rmd_batch", "PU/s", n_pu, k_s, w_s, algo,
          {"value": len(samp) / sec, "unit": "PU/s", "cores": T, "kind": kind, "sample": f"every 97th PU of the batch ({len(samp)} PUs, same size mix) in {sec:.2f} s"})
 
+    # ---- f1: the coalescing queue: K encoder instances (host threads), each submitting one CU's worth of PUs per request and waiting
+    #      for it (the live encoder's serial dependency), for K = 1, 4, 16: what coalescing buys over one-request-per-launch ----------------
+    #      (a C++ driver: Python threads would measure the GIL) ------------------------------------------------------------------------------
+    import subprocess
+    exe = os.path.join(ROOT, "profiles", "ubench", "queue_bench")
+    pkg = os.path.join(ROOT, "fast-cu-decision-hevc_b200")
+    try:
+        subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "profiles", "ubench", "queue_bench.cpp"),
+                        "-L" + pkg, "-lcucudecide", "-Wl,-rpath," + pkg, "-lpthread", "-o", exe], check=True, capture_output=True)
+        sys.stdout.write(subprocess.run([exe, "2000"], check=True, capture_output=True, text=True).stdout)
+        sys.stdout.flush()
+    except (subprocess.CalledProcessError, OSError) as e:
+        print(json.dumps({"row": "f1_rmd_queue", "unavailable": str(e)[:200]}), flush=True)
+
     # ---- S3: integer-ME SAD surfaces: every whole 32x32 PU of the picture, +-32 window, FEN row sub-sampling ---------------
     pad = 80
     refp = np.pad(rec, pad, mode="edge")
@@ -136,6 +150,23 @@ def main():
          {"value": len(samp) * 65 * 65 / sec, "unit": "candidate SAD/s", "cores": T, "kind": kind,
           "sample": f"{len(samp)} of the {n_pu} PUs (32x32, 65x65 window, iSubShift 1) in {sec:.2f} s"},
          {"pus_per_call": n_pu})
+
+    # ---- f3: fractional-pel refinement of the same PUs around a pseudo-random integer MV, Hadamard -------------------------------------------
+    sdescs = [dict(x=d["x"], y=d["y"], w=32, h=32, ref_idx=0, mvx=int(rng.integers(-16, 17)), mvy=int(rng.integers(-16, 17)), use_hadamard=1) for d in descs]
+    k_s, w_s = timed(lambda: eng.me_subpel_cost(sdescs), eng, a.iters)
+    algo = len(sdescs) * (32 * 32 * 2 + 41 * 41 * 2 + 49 * 4)
+    samp = sdescs[::40]
+
+    def work_f3(i):
+        d = samp[i]
+        blk = np.ascontiguousarray(org[d["y"]:d["y"] + 32, d["x"]:d["x"] + 32])
+        out = np.zeros(49, np.uint32)
+        base = refp.ctypes.data + 2 * ((d["y"] + pad) * Wp + d["x"] + pad)
+        oracle.oracle_subpel_surface(8, P(blk, i16p), 32, 32, 32, C.c_void_p(base), Wp, d["mvx"], d["mvy"], 1, P(out, u32p))
+    sec = cpu_parallel(work_f3, len(samp), T)
+    emit("f3_me_subpel_cost", "PU refinement/s", len(sdescs), k_s, w_s, algo,
+         {"value": len(samp) / sec, "unit": "PU refinement/s", "cores": T, "kind": "port",
+          "sample": f"{len(samp)} of the {len(sdescs)} PUs (32x32, 49 quarter-pel positions, Hadamard) through the oracle in {sec:.2f} s"})
 
     # ---- a12: TMV features of every whole CU of the picture (depths 0..3) -------------------------------------------------------
     cus = _util.all_cus(W, H)

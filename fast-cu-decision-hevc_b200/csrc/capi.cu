@@ -84,6 +84,7 @@ struct cucd_handle {
   // batch RMD path
   DevBuf<int16_t> bOrg, bBorder;
   DevBuf<BatchPu> bPus;
+  PinBuf<uint8_t> hStage; DevBuf<uint8_t> bStage;   // S2: one pinned staging block up, one down
   DevBuf<uint32_t> bOut;
   // ME path
   std::vector<RefPlane> refs;
@@ -233,7 +234,7 @@ int cucd_destroy(cucd_handle* h) {
   h->dOrg.release(); h->dRec.release(); h->dObf.release(); h->dOutlier.release(); h->dCost.release(); h->dCostPacked.release(); h->dHist.release(); h->dThr.release();
   for (int d = 0; d < 4; d++) { h->dNum[d].release(); h->dSum[d].release(); }
   h->dCtuHad.release(); h->hHist.release(); h->hThr.release(); h->dHadamard.release(); h->dTc2Tables.release();
-  h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release();
+  h->bOrg.release(); h->bBorder.release(); h->bPus.release(); h->bOut.release(); h->hStage.release(); h->bStage.release();
   for (auto& r : h->refs) r.buf.release();
   h->dTmvCus.release(); h->dDoubles.release();
   h->dSubJobs.release(); h->tJobs.release(); h->tCoef.release(); h->tAbs.release(); h->tPix.release(); h->tDist.release();
@@ -528,23 +529,33 @@ int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, cons
   std::vector<BatchPu> all; all.reserve(nPU);
   size_t first[7] = {0};
   for (int l = 2; l <= 6; l++) { first[l] = all.size(); all.insert(all.end(), pus[l].begin(), pus[l].end()); }
-  CK(h->bOrg.reserve(orgOff + 64)); CK(h->bBorder.reserve(borderOff + 8)); CK(h->bPus.reserve(all.size())); CK(h->bOut.reserve((size_t)nPU * kNumModes));
-  CK(cudaMemcpyAsync(h->bOrg.p, org, orgOff * 2, cudaMemcpyHostToDevice, h->sMain));
-  CK(cudaMemcpyAsync(h->bBorder.p, border, borderOff * 2, cudaMemcpyHostToDevice, h->sMain));
-  CK(cudaMemcpyAsync(h->bPus.p, all.data(), all.size() * sizeof(BatchPu), cudaMemcpyHostToDevice, h->sMain));
+  // one pinned staging block, one upload: [source blocks | borders | PU records], every part 16-byte aligned; one pinned block back.
+  // (three pageable copies in, one out cost ~30 us per call - most of a small request's latency)
+  auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t orgBytes = up16((orgOff + 64) * 2), brdBytes = up16((borderOff + 8) * 2), puBytes = up16(all.size() * sizeof(BatchPu));
+  const size_t inBytes = orgBytes + brdBytes + puBytes, outWords = (size_t)nPU * kNumModes;
+  CK(h->hStage.reserve(std::max(inBytes, outWords * sizeof(uint32_t)))); CK(h->bStage.reserve(inBytes)); CK(h->bOut.reserve(outWords));
+  memcpy(h->hStage.p, org, orgOff * 2);
+  memcpy(h->hStage.p + orgBytes, border, borderOff * 2);
+  memcpy(h->hStage.p + orgBytes + brdBytes, all.data(), all.size() * sizeof(BatchPu));
+  CK(cudaMemcpyAsync(h->bStage.p, h->hStage.p, inBytes, cudaMemcpyHostToDevice, h->sMain));
+  const int16_t* dOrgB = reinterpret_cast<const int16_t*>(h->bStage.p);
+  const int16_t* dBrdB = reinterpret_cast<const int16_t*>(h->bStage.p + orgBytes);
+  const BatchPu* dPus = reinterpret_cast<const BatchPu*>(h->bStage.p + orgBytes + brdBytes);
   CK(cudaEventRecord(h->evK0, h->sMain));
   for (int l = 6; l >= 2; l--) {
     if (pus[l].empty()) continue;
     BatchSource bs;
-    bs.org = h->bOrg.p; bs.border = h->bBorder.p; bs.pus = h->bPus.p + first[l]; bs.out = h->bOut.p; bs.count = (int)pus[l].size();
+    bs.org = dOrgB; bs.border = dBrdB; bs.pus = dPus + first[l]; bs.out = h->bOut.p; bs.count = (int)pus[l].size();
     if (h->useTensor == 1)
       CK(launch_rmd_batch_tc2(l, bs, h->cfg.strong_intra_smoothing, h->dTc2Tables.p, h->dTc2Tables.p + tc2::kWinTableBytes, h->dHadamard.p, h->sMain, &h->launches));
     else
       CK(launch_rmd_batch(l, bs, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
   }
   CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
-  CK(cudaMemcpyAsync(sad, h->bOut.p, (size_t)nPU * kNumModes * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
-  CK(cudaStreamSynchronize(h->sMain));   // `all` and the caller's buffers must outlive the copies
+  CK(cudaMemcpyAsync(h->hStage.p, h->bOut.p, outWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sMain));
+  CK(cudaStreamSynchronize(h->sMain));
+  memcpy(sad, h->hStage.p, outWords * sizeof(uint32_t));
   flush_launches(h);
   return CUCD_OK;
 }
