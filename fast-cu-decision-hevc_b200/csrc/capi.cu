@@ -60,6 +60,7 @@ struct cucd_handle {
   cudaStream_t sMain = nullptr, sFeat = nullptr, sGrp[2] = {nullptr, nullptr};   // sGrp: [0] RMD compute, [1] cost-table download
   cudaStream_t sUp = nullptr;                     // picture upload
   static constexpr int kGroups = 8;               // sub-groups of pictures one cuCUDecide_frames call is pipelined over
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;   // cucd_dev_frames: feature path beside the RMD kernel
   cudaEvent_t evUp = nullptr, evHist = nullptr, evUpG[kGroups] = {}, evRmdG[kGroups] = {};
   static constexpr int kTimeRing = 64;
   cudaEvent_t evRmd0[kTimeRing] = {}, evRmd1[kTimeRing] = {};
@@ -193,7 +194,9 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
             cudaStreamCreateWithFlags(&h->sGrp[1], cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->sUp, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->evUp, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&h->evHist, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&h->evHist, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < cucd_handle::kGroups; i++)
     ok = ok && cudaEventCreateWithFlags(&h->evUpG[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->evRmdG[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreate(&h->evK0) == cudaSuccess && cudaEventCreate(&h->evK1) == cudaSuccess;
@@ -246,6 +249,8 @@ int cucd_destroy(cucd_handle* h) {
   if (h->sUp) cudaStreamDestroy(h->sUp);
   if (h->evUp) cudaEventDestroy(h->evUp);
   if (h->evHist) cudaEventDestroy(h->evHist);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evJoin) cudaEventDestroy(h->evJoin);
   for (int i = 0; i < 2; i++) if (h->sGrp[i]) cudaStreamDestroy(h->sGrp[i]);
   if (h->sMain) cudaStreamDestroy(h->sMain);
   if (h->sFeat) cudaStreamDestroy(h->sFeat);
@@ -342,10 +347,19 @@ int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_or
   const int W = h->cfg.width, H = h->cfg.height;
   const bool wantFeat = out->obf || out->outlier || out->ctu_src_had || yc_host;
   const FeaturePlanes fp = make_feature_planes(h, d_org, orgPicStride, orgStride);
+  // The feature path (two small streaming kernels around a host fit) runs on the library's high-priority stream beside the RMD
+  // kernel instead of in front of / behind it: fork from the caller's stream here, join before returning.  Its CTAs slip in as
+  // RMD CTAs retire, so a step costs about the RMD launch alone.
+  cudaStream_t sf = st;
+  if (wantFeat && d_rec) {
+    sf = h->sFeat;
+    CK(cudaEventRecord(h->evFork, st));
+    CK(cudaStreamWaitEvent(sf, h->evFork, 0));
+  }
   if (wantFeat) {
-    CK(launch_feature_hist(fp, nPics, h->dHist.p, st, &h->launches));
-    CK(cudaMemcpyAsync(h->hHist.p, h->dHist.p, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(h->evHist, st));
+    CK(launch_feature_hist(fp, nPics, h->dHist.p, sf, &h->launches));
+    CK(cudaMemcpyAsync(h->hHist.p, h->dHist.p, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, sf));
+    CK(cudaEventRecord(h->evHist, sf));
   }
   if (d_rec) {
     const FrameSource fs = make_frame_source(h, d_org, orgPicStride, orgStride, d_rec, recPicStride, recStride, out->rmd_cost);
@@ -367,7 +381,7 @@ int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_or
     });
     for (int p = 0; p < nPics; p++) h->hThr.p[p * kHistFreqs] = 0;
     if (yc_host) memcpy(yc_host, yc.data(), yc.size() * sizeof(double));
-    CK(cudaMemcpyAsync(h->dThr.p, h->hThr.p, (size_t)nPics * kHistFreqs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dThr.p, h->hThr.p, (size_t)nPics * kHistFreqs * sizeof(int32_t), cudaMemcpyHostToDevice, sf));
     FeatureOut fo;
     fo.obf = out->obf ? out->obf : h->dObf.p; fo.obfPicStride = (long long)(W / 4) * (H / 4);
     fo.outlier = out->outlier ? out->outlier : h->dOutlier.p; fo.outlierPicStride = (long long)W * H;
@@ -376,8 +390,12 @@ int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_or
       fo.nOutlier[d] = out->n_outlier[d] ? out->n_outlier[d] : h->dSum[d].p;
       fo.cuPicStride[d] = (long long)h->cuCount[d];
     }
-    CK(launch_feature_obf(fp, nPics, h->dThr.p, fo, st, &h->launches));
-    if (out->ctu_src_had) CK(launch_ctu_src_had(fp, nPics, out->ctu_src_had, st, &h->launches));
+    CK(launch_feature_obf(fp, nPics, h->dThr.p, fo, sf, &h->launches));
+    if (out->ctu_src_had) CK(launch_ctu_src_had(fp, nPics, out->ctu_src_had, sf, &h->launches));
+    if (sf != st) {
+      CK(cudaEventRecord(h->evJoin, sf));
+      CK(cudaStreamWaitEvent(st, h->evJoin, 0));
+    }
   }
   flush_launches(h);
   return CUCD_OK;

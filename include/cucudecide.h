@@ -246,6 +246,9 @@ int cucd_dev_feature_obf(cucd_handle* h, void* stream, int nPics, const int16_t*
                          int32_t* const d_n_outlier[4], int32_t* d_ctu_src_had);
 /* the whole frame path on device-resident pictures, enqueued on `stream`: feature pass 1, RMD replay,
  * host TCM fit (the only host synchronisation: it waits for the pass-1 histograms), feature pass 2.
+ * When both the features and the RMD tables are asked for, the feature kernels run on a high-priority stream of the
+ * library beside the RMD kernel (forked from `stream` at entry, joined back into it before the call returns), so work
+ * the caller enqueues on `stream` afterwards is ordered after every output.
  * All outputs are device pointers, batch-contiguous (picture p at p * per-picture size), any may be
  * NULL except that d_rec and d_rmd_cost go together.  yc_host: nPics*16 doubles on the host or NULL. */
 typedef struct {
