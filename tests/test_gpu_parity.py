@@ -104,9 +104,11 @@ def test_frame_features_vs_reference_encoder_dump(eng8, eng10, oracle, clip):
         assert np.array_equal(o["ctu_src_had"], oracle_ctu_src_had(oracle, orgs[k]))
 
 
-@pytest.mark.parametrize("bd,W,H", [(8, 416, 240), (10, 200, 136), (8, 64, 64), (8, 8, 8), (10, 72, 136)])
+@pytest.mark.parametrize("bd,W,H", [(8, 416, 240), (10, 200, 136), (8, 64, 64), (8, 8, 72), (10, 72, 136)])
 def test_frame_replay_vs_oracle(cucd, oracle, bd, W, H):
-    """full enumeration (341 PUs x 35 modes per CTU), partial CTUs on the right and bottom edges"""
+    """full enumeration (341 PUs x 35 modes per CTU), partial CTUs on the right and bottom edges.
+    (The one-CU-wide case used to be 8x8: on some tiny pictures the reference's lambda iteration of the TCM fit,
+    TEncSlice.cpp:221-226, needs minutes to converge - oracle and product reproduce that faithfully, the suite avoids it.)"""
     org = textured_plane(W, H, bd, seed=W + H)
     rec = pseudo_recon(org, bd)
     if W >= 128:
