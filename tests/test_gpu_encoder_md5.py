@@ -19,6 +19,18 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
+# HM random-access GOP8 (B pictures, two reference lists), closed intra periods (DecodingRefreshType=2: BASELINE configs[4])
+RA = ["--IntraPeriod=16", "--GOPSize=8", "--DecodingRefreshType=2", "--FastSearch=1", "--SearchRange=64", "--BipredSearchRange=4", "--HadamardME=1", "--AMP=1",
+      "--Frame1=B 8 1 0.442 0 0 0 4 4 -8 -10 -12 -16 0",
+      "--Frame2=B 4 2 0.3536 0 0 0 2 3 -4 -6 4 1 4 5 1 1 0 0 1",
+      "--Frame3=B 2 3 0.3536 0 0 0 2 4 -2 -4 2 6 1 2 4 1 1 1 1",
+      "--Frame4=B 1 4 0.68 0 0 0 2 4 -1 1 3 7 1 1 5 1 0 1 1 1",
+      "--Frame5=B 3 4 0.68 0 0 0 2 4 -1 -3 1 5 1 -2 5 1 1 1 1 0",
+      "--Frame6=B 6 3 0.3536 0 0 0 2 4 -2 -4 -6 2 1 -3 5 1 1 1 1 0",
+      "--Frame7=B 5 4 0.68 0 0 0 2 4 -1 -5 1 3 1 1 5 1 0 1 1 1",
+      "--Frame8=B 7 4 0.68 0 0 0 2 4 -1 -3 -7 1 1 -2 5 1 1 1 1 0"]
+
+
 def _encode(binary, wd, W, H, frames, bd, qp, cfg):
     import gen_golden as gg
     args = [os.path.join(REF, binary), "-i", "clip.yuv", "-wdt", str(W), "-hgt", str(H), "-f", str(frames), "-q", str(qp), "-b", "out.bin",
@@ -28,11 +40,12 @@ def _encode(binary, wd, W, H, frames, bd, qp, cfg):
     return r
 
 
-@pytest.mark.parametrize("cfg,bd,frames,qp", [("AI", 8, 5, 32), ("AI", 10, 2, 27), ("LDP", 8, 3, 32)])
+@pytest.mark.parametrize("cfg,bd,frames,qp", [("AI", 8, 5, 32), ("AI", 10, 2, 27), ("LDP", 8, 3, 32), ("RA", 10, 9, 32)])
 def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
     """AI: S1 + S2 on the GPU (5 frames reach the fork's Testing state, so the OBF-driven early decisions are live);
     LDP (I + 2 P pictures, TZ search range 64, AMP): additionally every integer-ME SAD of the uni-directional searches (S3) and
-    every candidate of their half-/quarter-pel refinement (8f.3)."""
+    every candidate of their half-/quarter-pel refinement (8f.3).
+    RA (I + one GOP8 of B pictures, 10 bit): the same with two reference lists; the bi-predictive refinement keeps its CPU SAD."""
     import gen_golden as gg
     for b in ("TAppEncoder", "TAppEncoderCucd", "TAppDecoder"):
         if not os.path.exists(os.path.join(REF, b)):
@@ -43,7 +56,7 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
     for binary in ("TAppEncoder", "TAppEncoderCucd"):
         with tempfile.TemporaryDirectory(prefix="cucd_md5_") as wd:
             open(os.path.join(wd, "clip.yuv"), "wb").write(clip)
-            r = _encode(binary, wd, W, H, frames, bd, qp, gg.AI if cfg == "AI" else gg.LDP)
+            r = _encode(binary, wd, W, H, frames, bd, qp, {"AI": gg.AI, "LDP": gg.LDP, "RA": RA}[cfg])
             bits = open(os.path.join(wd, "out.bin"), "rb").read()
             rec = open(os.path.join(wd, "rec.yuv"), "rb").read()
             out[binary] = (hashlib.md5(bits).hexdigest(), hashlib.md5(rec).hexdigest(), len(bits))
@@ -51,7 +64,7 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
                 assert "RMD PUs on the GPU" in r.stderr, r.stderr[-500:]          # the GPU path really ran
                 n_gpu = int(r.stderr.split("pictures,")[1].split("RMD PUs")[0])
                 assert n_gpu > 1000
-                if cfg == "LDP":
+                if cfg in ("LDP", "RA"):
                     n_me = int(r.stderr.split("GPU,")[1].split("ME searches")[0])
                     assert n_me > 1000
                     assert int(r.stderr.split("probes) on the GPU,")[1].split("sub-pel")[0]) > 1000
