@@ -100,6 +100,25 @@ __device__ int tu_predict(const int16_t* b, int n, int lg, int mode, int bitDept
 
 }  // namespace
 
+// One 1-D transform stage for the outputs of this thread: acc[i] = sum_x M[o0 + i][x] * in[x].  `in` = the thread's input row as packed
+// int16 pairs, `mat` = the stage's matrix as int8 rows of N bytes (MW = N / 4 words): one broadcast LDS.32 + two IDP.2A per 4 terms.
+template <int N, int KPT>
+__device__ __forceinline__ void tu_matvec(const uint32_t (&in)[N / 2], const uint32_t* __restrict__ mat, int o0, int (&acc)[KPT]) {
+  constexpr int MW = N / 4;
+#pragma unroll
+  for (int i = 0; i < KPT; i++) {
+    const uint32_t* m = mat + (o0 + i) * MW;
+    int a = 0;
+#pragma unroll
+    for (int w = 0; w < MW; w++) {
+      const int tw = (int)m[w];
+      a = __dp2a_lo((int)in[2 * w], tw, a);
+      a = __dp2a_hi((int)in[2 * w + 1], tw, a);
+    }
+    acc[i] = a;
+  }
+}
+
 template <int LG>
 __global__ void __launch_bounds__(256)
 intra_tu_kernel(const TuBatch tb) {
@@ -108,10 +127,15 @@ intra_tu_kernel(const TuBatch tb) {
   constexpr int TUS = 256 / TPT;                 // TUs per CTA
   constexpr int IPT = NN / TPT;                  // samples per thread
   constexpr int CGS = NN / 16;                   // coefficient groups per TU
-  __shared__ int8_t sT[32 * 32];                 // 32-point core transform matrix
+  constexpr int KG = TPT / N;                    // transform stages: a thread owns input row (t % N) and KPT = N / KG = IPT outputs
+  constexpr int PW = N / 2 + 1;                  // words per row of the packed int16 stage arrays (odd: conflict-free row loads)
+  constexpr int MW = N / 4;
+  __shared__ __align__(16) int8_t sMF[NN], sMI[NN];         // forward matrix [k][x] = T_N[k][x], inverse matrix [x][k] = T_N[k][x]
+  __shared__ __align__(16) int8_t sDF[16], sDI[16];          // the 4x4 DST pair (luma 4x4 only)
   __shared__ int16_t sUnf[TUS][4 * N + 2], sFil[TUS][4 * N + 2];
   __shared__ int16_t sPred[TUS][NN];
-  __shared__ int32_t sA[TUS][N * P], sB[TUS][N * P];     // row-padded work arrays
+  __shared__ uint32_t sIn[TUS][N * PW], sMid[TUS][N * PW];   // packed int16 pairs, row-major
+  __shared__ int32_t sB[TUS][N * P];                         // transform output / residual, row-padded
   __shared__ int32_t sLevel[TUS][NN], sDelta[TUS][NN];
   __shared__ int sAbs[TUS], sDist[TUS], sCgNz[TUS][CGS];
 
@@ -121,13 +145,17 @@ intra_tu_kernel(const TuBatch tb) {
   const TuJob job = live ? tb.jobs[tuIdx] : TuJob{0, 0, 0, 0, 0, 0, 0};
   const int bd = tb.bitDepth, mode = job.mode, ts = job.ts & 1;
   const bool luma = !(job.ts & 2);
+  const bool dst = N == 4 && luma;                           // TComTU::useDST: intra luma 4x4
+  const int row = t & (N - 1), kg = t >> LG;                 // transform-stage role of this thread
 
-  for (int i = tid; i < 32 * 32; i += 256) {
-    const int k = i >> 5, x = i & 31;
-    int a = (k * (2 * x + 1)) & 127;
+  for (int i = tid; i < NN; i += 256) {                      // rows of the 32-point matrix, sub-sampled (TComRom.cpp:356-460)
+    const int k = i >> LG, x = i & (N - 1);
+    int a = (k * (32 >> LG) * (2 * x + 1)) & 127;
     if (a > 64) a = 128 - a;
-    sT[i] = k == 0 ? (int8_t)64 : (a <= 32 ? kDctC[a] : (int8_t)-kDctC[64 - a]);
+    const int8_t v = k == 0 ? (int8_t)64 : (a <= 32 ? kDctC[a] : (int8_t)-kDctC[64 - a]);
+    sMF[k * N + x] = v; sMI[x * N + k] = v;
   }
+  if (N == 4 && tid < 16) { sDF[tid] = kDst4[tid]; sDI[(tid & 3) * 4 + (tid >> 2)] = kDst4[tid]; }
   if (live) {
     const int16_t* bsrc = tb.border + job.borderOff;
     for (int i = t; i < 4 * N + 1; i += TPT) sUnf[grp][i] = bsrc[i];
@@ -154,8 +182,10 @@ intra_tu_kernel(const TuBatch tb) {
     }
   }
   __syncthreads();
-  // ---- prediction, residual ---------------------------------------------------------------------------------------------
+  // ---- prediction, residual (int16, row-major: the input rows of the first transform stage) ----------------------------------
   const int16_t* org = tb.org + job.orgOff;
+  int16_t* in16 = reinterpret_cast<int16_t*>(sIn[grp]);
+  int16_t* mid16 = reinterpret_cast<int16_t*>(sMid[grp]);
   {
     const int16_t* b = (luma && tu_use_filtered(LG, mode)) ? sFil[grp] : sUnf[grp];      // chroma of 4:2:0: never smoothed
     int dc = 0;
@@ -165,39 +195,38 @@ intra_tu_kernel(const TuBatch tb) {
       const int o = t + e * TPT, r = o >> LG, c = o & (N - 1);
       const int p = live ? tu_predict(b, N, LG, mode, bd, r, c, dc, luma) : 0;
       sPred[grp][o] = (int16_t)p;
-      sA[grp][r * P + c] = live ? org[o] - p : 0;
+      in16[r * 2 * PW + c] = (int16_t)(live ? org[o] - p : 0);
       if (live && tb.stage == 0 && tb.pred) tb.pred[job.orgOff + o] = (int16_t)p;
     }
   }
   __syncthreads();
-  const int tstep = 32 >> LG;                               // row k of the N-point matrix = row k*tstep of the 32-point one
   const int tshift = 15 - bd - LG;
+  const uint32_t* matF = reinterpret_cast<const uint32_t*>(dst ? sDF : sMF);
+  const uint32_t* matI = reinterpret_cast<const uint32_t*>(dst ? sDI : sMI);
   if (tb.stage != 2) {
-    // ---- forward transform (xTrMxN) or transform skip; the barrier sequence is the same for both (TUs of one CTA differ) ---
+    // ---- forward transform (xTrMxN): tmp[k][j] = (sum_x T[k][x] resi[j][x] + add1) >> shift1, coef[k][j] = (sum_x T[k][x] tmp[j][x] + add2) >> shift2.
+    //      Transform skip (xTransformSkip) is elementwise.  TUs of one CTA differ, so every barrier is on a path all threads take. -----
     {
       const int shift1 = LG + bd - 9, add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0;
-      int v[IPT];
+      uint32_t in[N / 2];
+      int acc[IPT];
 #pragma unroll
-      for (int e = 0; e < IPT; e++) {                       // tmp[k][j] = sum_x T[k][x] * resi[j][x]
-        const int o = t + e * TPT, k = o >> LG, j = o & (N - 1);
-        int s = 0;
-        if (ts) s = sA[grp][k * P + j] << tshift;           // xTransformSkip: coefficient = residual << shift, no second stage
-        else if (N == 4 && luma) { for (int x = 0; x < 4; x++) s += kDst4[k * 4 + x] * sA[grp][j * P + x]; }     // intra luma 4x4: DST (TComTU::useDST)
-        else { for (int x = 0; x < N; x++) s += sT[k * tstep * 32 + x] * sA[grp][j * P + x]; }
-        v[e] = ts ? s : (s + add1) >> shift1;
+      for (int w = 0; w < N / 2; w++) in[w] = sIn[grp][row * PW + w];
+      tu_matvec<N, IPT>(in, matF, kg * IPT, acc);
+#pragma unroll
+      for (int i = 0; i < IPT; i++) mid16[(kg * IPT + i) * 2 * PW + row] = (int16_t)((acc[i] + add1) >> shift1);      // tmp[k][j]
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < N / 2; w++) in[w] = sMid[grp][row * PW + w];
+      tu_matvec<N, IPT>(in, matF, kg * IPT, acc);
+#pragma unroll
+      for (int i = 0; i < IPT; i++) {
+        const int k = kg * IPT + i;                                                                        // coef[k][j = row]
+        if (!ts) sB[grp][k * P + row] = (acc[i] + (1 << (LG + 5))) >> (LG + 6);
       }
-      __syncthreads();
+      if (ts) {
 #pragma unroll
-      for (int e = 0; e < IPT; e++) { const int o = t + e * TPT; sA[grp][(o >> LG) * P + (o & (N - 1))] = v[e]; }
-      __syncthreads();
-#pragma unroll
-      for (int e = 0; e < IPT; e++) {                       // coef[k][j] = sum_x T[k][x] * tmp[j][x]
-        const int o = t + e * TPT, k = o >> LG, j = o & (N - 1);
-        int s = 0;
-        if (ts) s = sA[grp][k * P + j];
-        else if (N == 4 && luma) { for (int x = 0; x < 4; x++) s += kDst4[k * 4 + x] * sA[grp][j * P + x]; }
-        else { for (int x = 0; x < N; x++) s += sT[k * tstep * 32 + x] * sA[grp][j * P + x]; }
-        sB[grp][k * P + j] = ts ? s : (s + (1 << (LG + 5))) >> (LG + 6);
+        for (int e = 0; e < IPT; e++) { const int o = t + e * TPT, r = o >> LG, c = o & (N - 1); sB[grp][r * P + c] = (int)in16[r * 2 * PW + c] << tshift; }
       }
     }
     __syncthreads();
@@ -287,50 +316,46 @@ intra_tu_kernel(const TuBatch tb) {
     __syncthreads();
   }
   const bool coded = sAbs[grp] > 0;
-  // ---- de-quantisation (xDeQuant, flat scaling) -> sA ---------------------------------------------------------------------
+  // ---- de-quantisation (xDeQuant, flat scaling).  The coefficient (k, j) goes to row j of the inverse transform's input (int16 after the
+  //      clip); a transform-skipped block gets its residual right here (xITransformSkip is elementwise) -----------------------------------
   {
     const int baseQp = job.qp + 6 * (bd - 8), per = baseQp / 6, rem = baseQp - per * 6;
     const int rightShift = 6 - (tshift + per), scale = kInvQuantScales[rem];
     const int bitsIn = min(16, 32 + rightShift - 7);
     const int inMin = -(1 << (bitsIn - 1)), inMax = (1 << (bitsIn - 1)) - 1;
+    const int off = tshift == 0 ? 0 : 1 << (tshift - 1);
 #pragma unroll
     for (int e = 0; e < IPT; e++) {
-      const int o = t + e * TPT;
+      const int o = t + e * TPT, k = o >> LG, j = o & (N - 1);
       const int q = clip3i(inMin, inMax, sLevel[grp][o]);
-      const int v = rightShift > 0 ? (q * scale + (1 << (rightShift - 1))) >> rightShift : (int)((unsigned)(q * scale) << -rightShift);
-      sA[grp][(o >> LG) * P + (o & (N - 1))] = coded ? clip3i(-32768, 32767, v) : 0;
+      int v = rightShift > 0 ? (q * scale + (1 << (rightShift - 1))) >> rightShift : (int)((unsigned)(q * scale) << -rightShift);
+      v = coded ? clip3i(-32768, 32767, v) : 0;
+      in16[j * 2 * PW + k] = (int16_t)v;
+      if (ts) sB[grp][k * P + j] = (int)(int16_t)((v + off) >> tshift);                              // stored as Pel (TComTrQuant.cpp:2007)
     }
   }
   __syncthreads();
-  // ---- inverse transform (xITrMxN) or inverse transform skip -> residual in sB (uniform barrier sequence again) -----------
+  // ---- inverse transform (xITrMxN): tmp[j][x] = clip16((sum_k T[k][x] coef[k][j] + 64) >> 7), resi[y][x] = clip16((sum_k T[k][x] tmp[k][y] + add) >> shift2) ---
   {
-    const int off = tshift == 0 ? 0 : 1 << (tshift - 1);
     const int shift2 = 20 - bd;
-    int v[IPT];
+    uint32_t in[N / 2];
+    int acc[IPT];
 #pragma unroll
-    for (int e = 0; e < IPT; e++) {                         // tmp[j][x] = clip16(sum_k T[k][x] * coef[k][j] + 64 >> 7)
-      const int o = t + e * TPT, j = o >> LG, x = o & (N - 1);
-      int s = 0;
-      if (ts) s = (int)(int16_t)((sA[grp][j * P + x] + off) >> tshift);                                // xITransformSkip, stored as Pel
-      else if (N == 4 && luma) { for (int k = 0; k < 4; k++) s += kDst4[k * 4 + x] * sA[grp][k * P + j]; }
-      else { for (int k = 0; k < N; k++) s += sT[k * tstep * 32 + x] * sA[grp][k * P + j]; }
-      sB[grp][j * P + x] = ts ? s : clip3i(-32768, 32767, (s + 64) >> 7);
-    }
+    for (int w = 0; w < N / 2; w++) in[w] = sIn[grp][row * PW + w];                                  // row = coefficient column j
+    tu_matvec<N, IPT>(in, matI, kg * IPT, acc);
+#pragma unroll
+    for (int i = 0; i < IPT; i++) mid16[(kg * IPT + i) * 2 * PW + row] = (int16_t)clip3i(-32768, 32767, (acc[i] + 64) >> 7);   // tmp[j][x] stored at [x][j]
     __syncthreads();
 #pragma unroll
-    for (int e = 0; e < IPT; e++) {                         // resi[j][x] = clip16(sum_k T[k][x] * tmp[k][j])
-      const int o = t + e * TPT, j = o >> LG, x = o & (N - 1);
-      int s = 0;
-      if (ts) s = sB[grp][j * P + x];
-      else if (N == 4 && luma) { for (int k = 0; k < 4; k++) s += kDst4[k * 4 + x] * sB[grp][k * P + j]; }
-      else { for (int k = 0; k < N; k++) s += sT[k * tstep * 32 + x] * sB[grp][k * P + j]; }
-      v[e] = ts ? s : clip3i(-32768, 32767, (s + (1 << (shift2 - 1))) >> shift2);
-    }
-    __syncthreads();
+    for (int w = 0; w < N / 2; w++) in[w] = sMid[grp][row * PW + w];                                 // row = spatial row y, entries over k = j of stage 1
+    tu_matvec<N, IPT>(in, matI, kg * IPT, acc);
+    if (!ts) {
 #pragma unroll
-    for (int e = 0; e < IPT; e++) { const int o = t + e * TPT; sB[grp][(o >> LG) * P + (o & (N - 1))] = v[e]; }
+      for (int i = 0; i < IPT; i++) sB[grp][row * P + kg * IPT + i] = clip3i(-32768, 32767, (acc[i] + (1 << (shift2 - 1))) >> shift2);
+    }
   }
-  // ---- reconstruction, SSE, outputs (each thread reads back only what it wrote) -----------------------------------------------------
+  __syncthreads();
+  // ---- reconstruction, SSE, outputs ---------------------------------------------------------------------------------------------------
   {
     const int sh = (bd - 8) << 1;
     int sse = 0;
