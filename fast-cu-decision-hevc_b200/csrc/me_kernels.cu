@@ -137,31 +137,39 @@ me_sad_u8_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_
 // ---------------------------------------------------------------------------------------------------------------------
 __constant__ int8_t kLumaFilter[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
 
-template <int T>   // T x T Hadamard of (a - b), returns sum |coefficient|
-__device__ __forceinline__ int hadamard_abs_sum(const int16_t* a, int as, const int16_t* b, int bs) {
-  int m[T * T];
+// T x T Hadamard cost of (a - b) tiles with T lanes per tile (one tile row each): rows transformed in registers, columns across the
+// lanes with shuffles; every lane of the warp takes part (tasks past the end carry zeros).  Returns the tile's HM-rounded cost in the
+// tile's first lane, 0 elsewhere.  Only sum |coefficient| matters (TComRdCost.cpp:1343-1534), so butterfly order and signs are free.
+template <int T>
+__device__ __forceinline__ int hadamard_tile_rows(const int16_t* a, const int16_t* b, int pitch, int tile, int tilesX, bool valid, int lane) {
+  const int r = lane & (T - 1);
+  int v[T];
+  if (valid) {
+    const int o = ((tile / tilesX) * T + r) * pitch + (tile % tilesX) * T;
 #pragma unroll
-  for (int y = 0; y < T; y++)
+    for (int x = 0; x < T; x++) v[x] = a[o + x] - b[o + x];
+  } else {
 #pragma unroll
-    for (int x = 0; x < T; x++) m[y * T + x] = a[y * as + x] - b[y * bs + x];
+    for (int x = 0; x < T; x++) v[x] = 0;
+  }
 #pragma unroll
-  for (int y = 0; y < T; y++)
+  for (int len = 1; len < T; len <<= 1)
 #pragma unroll
-    for (int len = 1; len < T; len <<= 1)
+    for (int j = 0; j < T; j++)
+      if (!(j & len)) { const int p = v[j], q = v[j + len]; v[j] = p + q; v[j + len] = p - q; }
 #pragma unroll
-      for (int j = 0; j < T; j++)
-        if (!(j & len)) { const int p = m[y * T + j], q = m[y * T + j + len]; m[y * T + j] = p + q; m[y * T + j + len] = p - q; }
+  for (int m = 1; m < T; m <<= 1) {
+    const bool upper = (r & m) != 0;
 #pragma unroll
-  for (int x = 0; x < T; x++)
-#pragma unroll
-    for (int len = 1; len < T; len <<= 1)
-#pragma unroll
-      for (int i = 0; i < T; i++)
-        if (!(i & len)) { const int p = m[i * T + x], q = m[(i + len) * T + x]; m[i * T + x] = p + q; m[(i + len) * T + x] = p - q; }
+    for (int x = 0; x < T; x++) { const int other = __shfl_xor_sync(0xffffffffu, v[x], m); v[x] = upper ? other - v[x] : v[x] + other; }
+  }
   int s = 0;
 #pragma unroll
-  for (int i = 0; i < T * T; i++) s += abs(m[i]);
-  return s;
+  for (int x = 0; x < T; x++) s += abs(v[x]);
+#pragma unroll
+  for (int m = 1; m < T; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (r != 0) return 0;
+  return T == 8 ? (s + 2) >> 2 : (s + 1) >> 1;               // xCalcHADs8x8 / xCalcHADs4x4 rounding
 }
 
 constexpr int kSpWinPitch = 64 + 10;      // int16 per staged window row (w + 9 <= 73)
@@ -220,11 +228,11 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
     __syncthreads();
     int part = 0;
     if (job.useHadamard) {
-      for (int t = tid; t < nTiles; t += 256) {
-        const int ty = t / tilesX, tx = t - ty * tilesX;
-        const int o = ty * T * w + tx * T;
-        if (tile8) part += (hadamard_abs_sum<8>(sCur + o, w, sPred + o, w) + 2) >> 2;      // xCalcHADs8x8
-        else part += (hadamard_abs_sum<4>(sCur + o, w, sPred + o, w) + 1) >> 1;            // xCalcHADs4x4
+      const int nTasks = nTiles * T;                          // T lanes per tile; whole warps iterate so that every lane joins the shuffles
+      for (int base = (tid & ~31); base < nTasks; base += 256) {
+        const int task = base + (tid & 31), tile = task / T;
+        if (tile8) part += hadamard_tile_rows<8>(sCur, sPred, w, tile, tilesX, task < nTasks, tid & 31);
+        else part += hadamard_tile_rows<4>(sCur, sPred, w, tile, tilesX, task < nTasks, tid & 31);
       }
     } else {
       for (int i = tid; i < w * h; i += 256) part += abs(sCur[i] - sPred[i]);
