@@ -183,7 +183,9 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   h->ctusPerRow = (cfg->width + 63) / 64; h->ctusPerCol = (cfg->height + 63) / 64; h->ctusPerPic = h->ctusPerRow * h->ctusPerCol;
   h->pitch = (cfg->width + 63) & ~63;
   h->planeSamples = (size_t)h->pitch * cfg->height;
-  h->hostThreads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  // TCM fits of a 16-picture step are ~4 ms of CPU work; 8 threads hide them behind the RMD kernel.  More would only add thread start-up
+  // cost per call (the pool is spawned per call) and oversubscribe the host when several ranks / instances share it.
+  h->hostThreads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
   for (int d = 0; d < 4; d++) h->cuCount[d] = (size_t)(cfg->width / (64 >> d)) * (cfg->height / (64 >> d));
   const size_t P = (size_t)cfg->max_pictures;
   int prioLow = 0, prioHigh = 0;

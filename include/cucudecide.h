@@ -54,7 +54,7 @@ typedef struct {
   int strong_intra_smoothing;  /* SPS flag (TComPattern.cpp:195)                                  */
   int device;                  /* CUDA device ordinal                                             */
   int max_pictures;            /* pictures one cuCUDecide_frames call may carry (>= 1)            */
-  int host_threads;            /* threads for the host-side TCM fit, 0 = hardware concurrency     */
+  int host_threads;            /* threads for the host-side TCM fit, 0 = min(8, hardware concurrency) */
 } cucd_config;
 
 int cucd_abi_version(void);
