@@ -92,10 +92,20 @@ patch("Lib/TLibCommon/TComTrQuant.h", [
 patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("  //===== get residual signal =====\n",
    "  cucd_hook_tu_pred(compID, g_iPOC, pcCU->getCUPelX() + blkX, pcCU->getCUPelY() + blkY, uiWidth, uiChFinalMode, g_bitDepth[chType], useTransformSkip, default0Save1Load2 == 2,\n"
-   "                    m_piYuvExt[compID][PRED_BUF_UNFILTERED], piPred, piOrg, uiStride);\n", "before"),
+   "                    m_piYuvExt[compID][PRED_BUF_UNFILTERED], piPred, piOrg, uiStride);\n"
+   "#ifdef CUCD_INTEGRATION\n"
+   "  cucd_shim_tu_forward(compID, uiWidth, uiChFinalMode, QpParam(*pcCU, compID).Qp - 6 * (g_bitDepth[chType] - 8), useTransformSkip,\n"
+   "                       m_piYuvExt[compID][PRED_BUF_UNFILTERED], piOrg, piPred, uiStride);   /* INTEGRATION.md, TU coding */\n"
+   "#endif\n", "before"),
   ("  //--- inverse transform ---\n",
    "  cucd_hook_tu_coeff(cQP.Qp - 6 * (g_bitDepth[chType] - 8), pcCU->getSlice()->getSliceType() == I_SLICE, pcCU->getSlice()->getPPS()->getSignHideFlag(),\n"
-   "                                  useTransformSkip ? m_pcEncCfg->getUseRDOQTS() : m_pcEncCfg->getUseRDOQ(), m_pcTrQuant->cucdTempCoeff(), pcCoeff, uiAbsSum);\n", "before"),
+   "                                  useTransformSkip ? m_pcEncCfg->getUseRDOQTS() : m_pcEncCfg->getUseRDOQ(), m_pcTrQuant->cucdTempCoeff(), pcCoeff, uiAbsSum);\n"
+   "#ifdef CUCD_INTEGRATION\n  cucd_shim_tu_after_quant(m_pcTrQuant->cucdTempCoeff(), pcCoeff);\n#endif\n", "before"),
+  ("  //===== update distortion =====\n",
+   "#ifdef CUCD_INTEGRATION\n"
+   "  cucd_shim_tu_reco(piReco, uiStride, piRecQt, uiRecQtStride, piRecIPred, uiRecIPredStride,\n"
+   "                    m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, COMPONENT_Y));\n"
+   "#endif\n", "before"),
   ("  //===== update distortion =====\n  ruiDist += m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, compID);\n",
    "  cucd_hook_tu_end(piReco, uiStride, m_pcRdCost->getDistPart(g_bitDepth[chType], piReco, uiStride, piOrg, uiStride, uiWidth, uiHeight, COMPONENT_Y));   /* unweighted SSE */\n", "after"),
 ])

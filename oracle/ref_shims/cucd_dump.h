@@ -149,7 +149,58 @@ inline void cucd_shim_frac_begin(int biPred, int mvx, int mvy, int useHadamard) 
 }
 inline void cucd_shim_frac_end() { cucd_frac_shim().active = false; }
 inline unsigned cucd_shim_frac_cost(int horVal, int verVal) { return cucd_frac_shim().cost[(verVal + 3) * 7 + horVal + 3]; }
-struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+/* 8f.2 / 8f.4: intra TU coding around the host's quantiser (CUCD_SHIM_TU=1).  Per TU of xIntraCodingTUBlock (TEncSearch.cpp:1092-1387):
+ *   cucd_intra_tu_forward  -> the prediction REPLACES piPred; the transform output is compared with m_plTempCoeff after transformNxN
+ *   (host: RDOQ / xQuant as shipped)
+ *   cucd_intra_tu_recon    -> the reconstruction REPLACES piReco / the picture samples; the SSE is compared with getDistPart
+ * Any difference is fatal, and a difference in the substituted samples would change the bitstream (tests/test_gpu_encoder_md5.py). */
+struct CucdTuShim {
+  int enabled; bool live; cucd_tu_desc d; int n;
+  int16_t org[32 * 32], border[4 * 32 + 1], pix[32 * 32];
+  int32_t coef[32 * 32];
+  uint32_t dist; long tus;
+  CucdTuShim() : enabled(-1), live(false), n(0), dist(0), tus(0) {}
+};
+inline CucdTuShim& cucd_tu_shim() { static CucdTuShim s; return s; }
+inline bool cucd_shim_tu_enabled() {
+  CucdTuShim& t = cucd_tu_shim();
+  if (t.enabled < 0) { const char* e = getenv("CUCD_SHIM_TU"); t.enabled = (e && *e && *e != '0') ? 1 : 0; }
+  return t.enabled == 1 && cucd_shim().h != 0;
+}
+inline void cucd_shim_tu_forward(int compID, int n, int mode, int qp, int transformSkip, const short* unfExt, const short* org, short* pred, int stride) {
+  CucdTuShim& t = cucd_tu_shim();
+  t.live = false;
+  if (!cucd_shim_tu_enabled() || n > 32) return;
+  int lg = 0; while ((1 << lg) < n) lg++;
+  t.d.log2_size = (uint8_t)lg; t.d.mode = (uint8_t)mode; t.d.qp = (int8_t)qp;
+  t.d.flags = (uint8_t)((transformSkip ? CUCD_TU_TRANSFORM_SKIP : 0) | (compID ? CUCD_TU_CHROMA : 0));
+  t.n = n;
+  const int sw = 2 * n + 1;
+  for (int i = 0; i < 2 * n; i++) t.border[i] = unfExt[(2 * n - i) * sw];
+  for (int i = 0; i < sw; i++) t.border[2 * n + i] = unfExt[i];
+  for (int r = 0; r < n; r++) memcpy(t.org + r * n, org + (size_t)r * stride, n * sizeof(short));
+  if (cucd_intra_tu_forward(cucd_shim().h, 1, &t.d, t.org, t.border, t.coef, t.pix) != CUCD_OK) cucd_shim_die("cucd_intra_tu_forward");
+  for (int r = 0; r < n; r++) memcpy(pred + (size_t)r * stride, t.pix + r * n, n * sizeof(short));
+  t.live = true; t.tus++;
+}
+inline void cucd_shim_tu_after_quant(const int* cpuCoef, const int* level) {
+  CucdTuShim& t = cucd_tu_shim();
+  if (!t.live) return;
+  if (memcmp(cpuCoef, t.coef, sizeof(int32_t) * t.n * t.n) != 0) { fprintf(stderr, "cucd shim: transform output of a %dx%d TU differs from the reference\n", t.n, t.n); exit(1); }
+  if (cucd_intra_tu_recon(cucd_shim().h, 1, &t.d, t.org, t.border, level, t.pix, &t.dist) != CUCD_OK) cucd_shim_die("cucd_intra_tu_recon");
+}
+inline void cucd_shim_tu_reco(short* reco, int stride, short* recQt, int recQtStride, short* recPic, int recPicStride, unsigned cpuSse) {
+  CucdTuShim& t = cucd_tu_shim();
+  if (!t.live) return;
+  t.live = false;
+  if (cpuSse != t.dist) { fprintf(stderr, "cucd shim: SSE of a %dx%d TU differs from the reference (%u vs %u)\n", t.n, t.n, t.dist, cpuSse); exit(1); }
+  for (int r = 0; r < t.n; r++) {
+    memcpy(reco + (size_t)r * stride, t.pix + r * t.n, t.n * sizeof(short));
+    memcpy(recQt + (size_t)r * recQtStride, t.pix + r * t.n, t.n * sizeof(short));
+    memcpy(recPic + (size_t)r * recPicStride, t.pix + r * t.n, t.n * sizeof(short));
+  }
+}
+struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_tu_shim().tus, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;
 #endif
 

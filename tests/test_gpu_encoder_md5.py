@@ -31,21 +31,26 @@ RA = ["--IntraPeriod=16", "--GOPSize=8", "--DecodingRefreshType=2", "--FastSearc
       "--Frame8=B 7 4 0.68 0 0 0 2 4 -1 -3 -7 1 1 -2 5 1 1 1 1 0"]
 
 
-def _encode(binary, wd, W, H, frames, bd, qp, cfg):
+def _encode(binary, wd, W, H, frames, bd, qp, cfg, env=None):
     import gen_golden as gg
     args = [os.path.join(REF, binary), "-i", "clip.yuv", "-wdt", str(W), "-hgt", str(H), "-f", str(frames), "-q", str(qp), "-b", "out.bin",
             "-o", "rec.yuv", f"--InputBitDepth={bd}", f"--InternalBitDepth={bd}", "--Profile=" + ("main10" if bd > 8 else "main")] + gg.COMMON + cfg
-    r = subprocess.run(args, cwd=wd, capture_output=True, text=True, timeout=900)
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(args, cwd=wd, capture_output=True, text=True, timeout=900, env=e)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r
 
 
-@pytest.mark.parametrize("cfg,bd,frames,qp", [("AI", 8, 5, 32), ("AI", 10, 2, 27), ("LDP", 8, 3, 32), ("RA", 10, 9, 32)])
+@pytest.mark.parametrize("cfg,bd,frames,qp", [("AI", 8, 5, 32), ("AI", 10, 2, 27), ("LDP", 8, 3, 32), ("RA", 10, 9, 32), ("AITU", 8, 1, 32), ("AITU", 10, 1, 27)])
 def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
     """AI: S1 + S2 on the GPU (5 frames reach the fork's Testing state, so the OBF-driven early decisions are live);
     LDP (I + 2 P pictures, TZ search range 64, AMP): additionally every integer-ME SAD of the uni-directional searches (S3) and
     every candidate of their half-/quarter-pel refinement (8f.3).
-    RA (I + one GOP8 of B pictures, 10 bit): the same with two reference lists; the bi-predictive refinement keeps its CPU SAD."""
+    RA (I + one GOP8 of B pictures, 10 bit): the same with two reference lists; the bi-predictive refinement keeps its CPU SAD.
+    AITU (CUCD_SHIM_TU=1): additionally every luma and chroma TU of xIntraCodingTUBlock goes through cucd_intra_tu_forward (its
+    prediction replaces the encoder's, its transform output must equal m_plTempCoeff), the host's RDOQ, and cucd_intra_tu_recon
+    (its reconstruction replaces the encoder's samples, its SSE must equal getDistPart)."""
     import gen_golden as gg
     for b in ("TAppEncoder", "TAppEncoderCucd", "TAppDecoder"):
         if not os.path.exists(os.path.join(REF, b)):
@@ -56,7 +61,8 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
     for binary in ("TAppEncoder", "TAppEncoderCucd"):
         with tempfile.TemporaryDirectory(prefix="cucd_md5_") as wd:
             open(os.path.join(wd, "clip.yuv"), "wb").write(clip)
-            r = _encode(binary, wd, W, H, frames, bd, qp, {"AI": gg.AI, "LDP": gg.LDP, "RA": RA}[cfg])
+            r = _encode(binary, wd, W, H, frames, bd, qp, {"AI": gg.AI, "AITU": gg.AI, "LDP": gg.LDP, "RA": RA}[cfg],
+                        env={"CUCD_SHIM_TU": "1"} if cfg == "AITU" else None)
             bits = open(os.path.join(wd, "out.bin"), "rb").read()
             rec = open(os.path.join(wd, "rec.yuv"), "rb").read()
             out[binary] = (hashlib.md5(bits).hexdigest(), hashlib.md5(rec).hexdigest(), len(bits))
@@ -68,6 +74,9 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
                     n_me = int(r.stderr.split("GPU,")[1].split("ME searches")[0])
                     assert n_me > 1000
                     assert int(r.stderr.split("probes) on the GPU,")[1].split("sub-pel")[0]) > 1000
+                if cfg == "AITU":
+                    import re
+                    assert int(re.search(r"(\d+) TUs coded on the GPU", r.stderr).group(1)) > 50000
                 print(r.stderr.strip().splitlines()[-1])
                 d = subprocess.run([os.path.join(REF, "TAppDecoder"), "-b", "out.bin", "-o", "dec.yuv", "-d", "0"],
                                    cwd=wd, capture_output=True, text=True, timeout=300)
