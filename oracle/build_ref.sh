@@ -142,6 +142,11 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("      uiSad = m_cDistParam.DistFunc(&m_cDistParam);\n\n      // motion cost\n      uiSad += m_pcRdCost->getCost(x, y);\n",
    "#ifdef CUCD_INTEGRATION\n      if (cucd_shim_me_active()) uiSad = cucd_shim_me_sad(x, y) + m_pcRdCost->getCost(x, y);\n#endif\n", "after"),
 ])
+# a12: TMV features (TEncCu.cpp:1561), integration build only (a13 / AdaptiveQP: the reference itself crashes with --AdaptiveQP=1, no in-situ test)
+patch("Lib/TLibEncoder/TEncCu.cpp", [
+  ("       TMVFeature* feature_x = getTMVFeature(rpcBestCU);\n",
+   "#ifdef CUCD_INTEGRATION\n       cucd_shim_tmv_check(rpcBestCU->getCUPelX(), rpcBestCU->getCUPelY(), rpcBestCU->getWidth(0), &feature_x->m_adFeature[0][0]);\n#endif\n", "after"),
+])
 # S1 call site (TEncGOP.cpp:1095-1096)
 patch("Lib/TLibEncoder/TEncGOP.cpp", [
   ("\t\t  m_pcSliceEncoder->getOutlierWithDCT(pcPic);\n",

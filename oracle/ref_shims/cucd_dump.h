@@ -37,8 +37,8 @@ inline void cucd_w32(FILE* f, int32_t v) { fwrite(&v, 4, 1, f); }
 #ifdef CUCD_INTEGRATION
 #include <vector>
 #include "cucudecide.h"
-struct CucdShim { cucd_handle* h; int W, H, bd, strong; uint32_t sad[35]; long rmdCalls, frameCalls; };
-inline CucdShim& cucd_shim() { static CucdShim s = {0, 0, 0, 0, 0, {0}, 0, 0}; return s; }
+struct CucdShim { cucd_handle* h; int W, H, bd, strong; uint32_t sad[35]; long rmdCalls, frameCalls, tmvCalls; bool curForTmv; };
+inline CucdShim& cucd_shim() { static CucdShim s = {0, 0, 0, 0, 0, {0}, 0, 0, 0, false}; return s; }
 inline void cucd_shim_die(const char* what) {   /* HM convention: fatal error -> exit(1) (CommonDef.h:141-164) */
   fprintf(stderr, "cucd shim: %s failed: %s\n", what, cucd_last_error(cucd_shim().h));
   exit(1);
@@ -62,6 +62,8 @@ inline void cucd_shim_outlier(int W, int H, int bd, int strong, const short* org
   cucd_frame_out fo; memset(&fo, 0, sizeof fo);
   fo.obf = o.data(); fo.outlier = t.data();
   if (cuCUDecide_frame(s.h, org, orgStride, 0, 0, 0, &fo) != CUCD_OK) cucd_shim_die("cuCUDecide_frame");
+  if (cucd_set_cur_picture(s.h, org, orgStride) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");   /* a12 check + S3 of this picture */
+  s.curForTmv = true;
   for (int r = 0; r < H / 4; r++) memcpy(obf + (size_t)r * obfStride, &o[(size_t)r * (W / 4)], (W / 4) * sizeof(short));
   for (int r = 0; r < H; r++) memcpy(outl + (size_t)r * outlStride, &t[(size_t)r * W], W * sizeof(short));
   s.frameCalls++;
@@ -200,7 +202,19 @@ inline void cucd_shim_tu_reco(short* reco, int stride, short* recQt, int recQtSt
     memcpy(recPic + (size_t)r * recPicStride, t.pix + r * t.n, t.n * sizeof(short));
   }
 }
-struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_tu_shim().tus, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+/* a12: getTMVFeature(rpcBestCU) (TEncCu.cpp:1561) -> cucd_tmv_features; compared bit for bit with the reference's doubles, which
+ * then go to the insight file as before.  The S1 shim uploads the picture being encoded. */
+inline void cucd_shim_tmv_check(int x, int y, int size, const double* ref130) {
+  CucdShim& s = cucd_shim();
+  if (!s.h || !s.curForTmv) return;
+  int lg = 0; while ((1 << lg) < size) lg++;
+  cucd_cu_desc cu = {x, y, lg};
+  double got[CUCD_TMV_FEATURES];
+  if (cucd_tmv_features(s.h, 1, &cu, got) != CUCD_OK) cucd_shim_die("cucd_tmv_features");
+  if (memcmp(got, ref130, sizeof got) != 0) { fprintf(stderr, "cucd shim: TMV features of the %dx%d CU at (%d,%d) differ from the reference\n", size, size, x, y); exit(1); }
+  s.tmvCalls++;
+}
+struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;
 #endif
 

@@ -77,6 +77,9 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
                 if cfg == "AITU":
                     import re
                     assert int(re.search(r"(\d+) TUs coded on the GPU", r.stderr).group(1)) > 50000
+                if cfg == "AI" and bd == 8:      # Training pictures dump TMV features: every set was recomputed on the GPU and compared
+                    import re
+                    assert int(re.search(r"(\d+) TMV feature sets verified", r.stderr).group(1)) > 100
                 print(r.stderr.strip().splitlines()[-1])
                 d = subprocess.run([os.path.join(REF, "TAppDecoder"), "-b", "out.bin", "-o", "dec.yuv", "-d", "0"],
                                    cwd=wd, capture_output=True, text=True, timeout=300)
