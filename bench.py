@@ -164,7 +164,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
-    return {"workload": f"{args.width}x{args.height} {args.bit_depth}-bit All-Intra (BASELINE configs[1]): full intra RMD enumeration "
+    which = {(1920, 1080, 8): "BASELINE configs[1]", (3840, 2160, 10): "BASELINE configs[2]"}.get((args.width, args.height, args.bit_depth), "not a BASELINE configuration")
+    return {"workload": f"{args.width}x{args.height} {args.bit_depth}-bit All-Intra ({which}): full intra RMD enumeration "
                         f"341 PUs x 35 modes per CTU + OBF/outlier feature pass, {args.pics} pictures per step per GPU",
             "pictures_per_step_per_gpu": args.pics, "ctus_per_picture": ((args.width + 63) // 64) * ((args.height + 63) // 64),
             "l2_policy": "inputs larger than L2: one step reads 2 planes x pictures and writes the cost tables (> 126 MB) before any reuse",
@@ -255,7 +256,10 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     W, H, bd, P = args.width, args.height, args.bit_depth, args.pics
-    eng = cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P)
+    # host threads of the TCM fits: cores / ranks, so that 8 ranks do not oversubscribe a 32-core host
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    host_threads = max(1, min(8, cores // max(1, world)))
+    eng = cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P, host_threads=host_threads)
     nctu = eng.ctus_per_pic
     pitch = (W + 63) // 64 * 64
     # each rank works on its own pictures (different seeds): weak scaling
@@ -270,11 +274,14 @@ def run_ours(args, rank, world, local_rank):
         return a.view(np.uint32) if dtype is np.uint32 else a
     pinned.keep = []
 
-    h_org = [pinned((H, W), np.int16) for _ in range(P)]
-    h_rec = [pinned((H, W), np.int16) for _ in range(P)]
+    # host side of the e2e call: 8-bit content travels as bytes (cuCUDecide_frames_u8), 10-bit as HM's Pel; outputs in the
+    # narrowest exact formats (packed cost tables, byte OBF / Outlier planes)
+    hdt = np.uint8 if bd == 8 else np.int16
+    h_org = [pinned((H, W), hdt) for _ in range(P)]
+    h_rec = [pinned((H, W), hdt) for _ in range(P)]
     for p in range(P):
         h_org[p][:] = orgs[p]; h_rec[p][:] = recs[p]
-    h_outs = [eng.alloc_frame_out(True, pinned_alloc=pinned, packed=True) for _ in range(P)]
+    h_outs = [eng.alloc_frame_out(True, pinned_alloc=pinned, packed=True, narrow=True) for _ in range(P)]
 
     # ---- device-resident buffers -------------------------------------------------------------------
     d_org = torch.zeros((P, H, pitch), dtype=torch.int16, device=dev)
@@ -292,8 +299,14 @@ def run_ours(args, rank, world, local_rank):
              "n_outlier": [t.data_ptr() for t in d_sum], "ctu_src_had": d_had.data_ptr(), "rmd_cost": d_cost.data_ptr()}
     stream = torch.cuda.current_stream().cuda_stream
 
-    def dev_step():
-        eng.dev_frames(stream, P, d_org.data_ptr(), H * pitch, pitch, d_rec.data_ptr(), H * pitch, pitch, d_out)
+    def dev_steps(n):
+        """n steps through the split call: the host fit of step i runs while the GPU is already on the RMD kernel of step i+1
+        (cucd_dev_frames_begin / _end, at most two steps in flight); every step is complete when the stream drains."""
+        for i in range(n):
+            eng.dev_frames(stream, P, d_org.data_ptr(), H * pitch, pitch, d_rec.data_ptr(), H * pitch, pitch, d_out, begin_only=True)
+            if i > 0:
+                eng.dev_frames_end()
+        eng.dev_frames_end()
 
     def barrier():
         if world > 1:
@@ -304,14 +317,12 @@ def run_ours(args, rank, world, local_rank):
     # nvidia-smi needs a few hundred ms to start: launch the sampler before the warm-up so that it is already reporting when the
     # (tens of ms long) timed region runs, and keep it running through the end-to-end region, which is timed under load too
     clocks = ClockSampler(local_rank)
-    for _ in range(max(args.warmup, 3)):
-        dev_step()
+    dev_steps(max(args.warmup, 3))
     barrier()
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        dev_step()
+    dev_steps(args.steps)
     e1.record()
     barrier()
     launches = eng.launch_count - l0
@@ -323,11 +334,12 @@ def run_ours(args, rank, world, local_rank):
     # reference implies is several encoder instances per GPU, so the headline e2e figure runs
     # `--e2e-instances` handles from as many host threads (each with its own pinned buffers; ctypes drops the GIL
     # inside the call): while one instance drains its cost tables over PCIe the other uploads and computes.
-    def e2e_run(engines, outs_list, steps):
+    def e2e_run(engines, outs_list, steps, planes=None):
         import threading
+        po, pr = planes or (h_org, h_rec)
         def work(e, o):
             for _ in range(steps):
-                e.frames(h_org, h_rec, o)
+                e.frames(po, pr, o)
         ths = [threading.Thread(target=work, args=(e, o)) for e, o in zip(engines, outs_list)]
         t0 = time.perf_counter()
         for t in ths:
@@ -338,8 +350,9 @@ def run_ours(args, rank, world, local_rank):
         return time.perf_counter() - t0
 
     n_inst = max(1, args.e2e_instances)
-    engines = [eng] + [cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P) for _ in range(n_inst - 1)]
-    outs_list = [h_outs] + [[e.alloc_frame_out(True, pinned_alloc=pinned, packed=True) for _ in range(P)] for e in engines[1:]]
+    inst_threads = max(1, host_threads // n_inst)
+    engines = [eng] + [cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P, host_threads=inst_threads) for _ in range(n_inst - 1)]
+    outs_list = [h_outs] + [[e.alloc_frame_out(True, pinned_alloc=pinned, packed=True, narrow=True) for _ in range(P)] for e in engines[1:]]
     e2e_steps = max(1, min(args.steps, 5))
     e2e_run(engines[:1], outs_list[:1], max(1, min(args.warmup, 2)))
     barrier()
@@ -351,8 +364,29 @@ def run_ours(args, rank, world, local_rank):
     else:
         e2e_s = e2e_single_s
     clk = clocks.stop()
-    h2d = 2 * P * W * H * 2
+    h2d = 2 * P * W * H * np.dtype(hdt).itemsize
     d2h = sum(int(a.nbytes) for o in h_outs for a in o.values())
+
+    # ---- the documented integration: HM's own planes - Pel = int16, stride W + 160, xMalloc'ed (pageable,
+    #      TComPicYuv.cpp:97) - and plain caller-owned output buffers, one encoder instance.  (a) as they are, (b) page-locked once
+    #      through cucd_pin_host_buffer / auto_pin_host, as a maintainer would do at TComPicYuv::create.  Rank 0 only. ----------
+    hm_e2e = None
+    if rank == 0 and not args.no_hm_planes:
+        def hm_plane(a):
+            buf = np.zeros((H + 160, W + 160), np.int16)
+            buf[80:80 + H, 80:80 + W] = a
+            return buf[80:80 + H, 80:80 + W]
+        hm_org = [hm_plane(o) for o in orgs]
+        hm_rec = [hm_plane(r) for r in recs]
+        hm_e2e = {"planes": "int16, stride W+160, heap memory (HM TComPicYuv layout); outputs in heap memory, packed / byte formats", "instances": 1}
+        for key, auto in (("pageable", 0), ("page_locked_once", 1)):
+            with cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P, host_threads=host_threads, auto_pin_host=auto) as e:
+                outs = [e.alloc_frame_out(True, packed=True, narrow=True) for _ in range(P)]
+                e2e_run([e], [outs], 2, (hm_org, hm_rec))                 # warm-up (and, with auto_pin_host, the one-time registration)
+                dt = e2e_run([e], [outs], 3, (hm_org, hm_rec))
+                hm_e2e[key] = {"value": P * nctu * 3 / dt, "unit": "CTU/s", "ms_per_step": 1e3 * dt / 3}
+                ok_hm = bool(np.array_equal(outs[0]["rmd_cost_packed"], h_outs[0]["rmd_cost_packed"]) and np.array_equal(outs[P - 1]["obf_u8"], h_outs[P - 1]["obf_u8"]))
+                hm_e2e[key]["agrees_with_pinned_run"] = ok_hm
 
     # spot-check that both paths produced the same tables (device-resident vs host-buffer)
     same = all(bool(np.array_equal(d_cost[p].cpu().numpy().view(np.uint32), cucd.unpack_costs(h_outs[p]["rmd_cost_packed"]))) for p in (0, P - 1))
@@ -393,8 +427,11 @@ def run_ours(args, rank, world, local_rank):
                 "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "CTU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "ms_per_step": 1e3 * e2e_s / (e2e_steps * n_inst), "instances_per_gpu": n_inst,
-                        "single_instance_value": e2e_single, "single_instance_ms_per_step": 1e3 * e2e_single_s / e2e_steps, "api": "cuCUDecide_frames (pinned host planes in, all outputs to host; cost tables in the packed CTU format of include/cucudecide.h)",
-                        "host_numa_binding": numa},
+                        "single_instance_value": e2e_single, "single_instance_ms_per_step": 1e3 * e2e_single_s / e2e_steps,
+                        "api": ("cuCUDecide_frames_u8 (8-bit content as bytes)" if bd == 8 else "cuCUDecide_frames (int16 planes)") +
+                               ": pinned host planes in, every output back on the host in its narrowest exact format",
+                        "outputs_copied": sorted(h_outs[0].keys()), "hm_layout_planes": hm_e2e,
+                        "host_numa_binding": numa, "host_threads_per_handle": host_threads},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "paths_agree": same}
         print(json.dumps(line))
@@ -414,6 +451,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--bit-depth", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hm-planes", action="store_true", help="skip the pageable / page-locked HM-layout e2e measurement")
     ap.add_argument("--e2e-instances", type=int, default=2, help="encoder instances (handles + host threads) per GPU in the e2e measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -21,7 +21,6 @@ from .binding import (  # noqa: F401
     TU_INTRA_SLICE,
     TU_SIGN_HIDING,
     declared_symbols,
-    exp_satd_tc,
     load_library,
     tcm_fit,
     unpack_costs,

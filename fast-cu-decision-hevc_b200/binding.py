@@ -14,20 +14,40 @@ import numpy as np
 NUM_MODES = 35
 PUS_PER_CTU = 341
 PACKED_WIDE_PUS = 21                     # CUCD_PACKED_WIDE_PUS: PUs 0..20 stay uint32
-PACKED_CTU_BYTES = PACKED_WIDE_PUS * 35 * 4 + (PUS_PER_CTU - PACKED_WIDE_PUS) * 35 * 2   # CUCD_PACKED_CTU_BYTES
+PACKED_U16_PUS = 64                      # CUCD_PACKED_U16_PUS: the 8x8 PUs as uint16
+PACKED_U16_OFFSET = PACKED_WIDE_PUS * 35 * 4
+PACKED_B13_OFFSET = PACKED_U16_OFFSET + PACKED_U16_PUS * 35 * 2
+PACKED_CTU_BYTES = PACKED_B13_OFFSET + 256 * 35 * 13 // 8   # CUCD_PACKED_CTU_BYTES = 21980
 
 
 def unpack_costs(packed):
     """(nCtu, PACKED_CTU_BYTES) uint8 packed CTU tables (cucd_frame_out.rmd_cost_packed) -> (nCtu, 341, 35) uint32,
-    the host-side equivalent of cucd_packed_cost()."""
+    a numpy restatement of cucd_unpack_costs() (uint32 | uint16 | 13-bit little-endian bit stream)."""
     packed = np.ascontiguousarray(packed, np.uint8).reshape(-1, PACKED_CTU_BYTES)
     n = packed.shape[0]
     out = np.empty((n, PUS_PER_CTU, NUM_MODES), np.uint32)
-    wide = PACKED_WIDE_PUS * NUM_MODES * 4
-    out[:, :PACKED_WIDE_PUS] = packed[:, :wide].copy().view(np.uint32).reshape(n, PACKED_WIDE_PUS, NUM_MODES)
-    narrow = packed[:, wide:].copy().view(np.uint16).reshape(n, PUS_PER_CTU - PACKED_WIDE_PUS, NUM_MODES)
-    out[:, PACKED_WIDE_PUS:] = np.where(narrow == 0xFFFF, np.uint32(0xFFFFFFFF), narrow.astype(np.uint32))
+    out[:, :PACKED_WIDE_PUS] = packed[:, :PACKED_U16_OFFSET].copy().view(np.uint32).reshape(n, PACKED_WIDE_PUS, NUM_MODES)
+    mid = packed[:, PACKED_U16_OFFSET:PACKED_B13_OFFSET].copy().view(np.uint16).reshape(n, PACKED_U16_PUS, NUM_MODES)
+    out[:, PACKED_WIDE_PUS:PACKED_WIDE_PUS + PACKED_U16_PUS] = np.where(mid == 0xFFFF, np.uint32(0xFFFFFFFF), mid.astype(np.uint32))
+    # 8 values = 13 bytes = 104 bits
+    grp = packed[:, PACKED_B13_OFFSET:].reshape(n, -1, 13).astype(np.uint64)
+    lo = sum(grp[:, :, k] << np.uint64(8 * k) for k in range(8))
+    hi = sum(grp[:, :, 8 + k] << np.uint64(8 * k) for k in range(5))
+    vals = np.empty(grp.shape[:2] + (8,), np.uint32)
+    for k in range(8):
+        bit = 13 * k
+        if bit + 13 <= 64:
+            v = (lo >> np.uint64(bit)) & np.uint64(0x1FFF)
+        elif bit >= 64:
+            v = (hi >> np.uint64(bit - 64)) & np.uint64(0x1FFF)
+        else:
+            v = ((lo >> np.uint64(bit)) | (hi << np.uint64(64 - bit))) & np.uint64(0x1FFF)
+        vals[:, :, k] = v.astype(np.uint32)
+    small = vals.reshape(n, 256, NUM_MODES)
+    out[:, PACKED_WIDE_PUS + PACKED_U16_PUS:] = np.where(small == 0x1FFF, np.uint32(0xFFFFFFFF), small)
     return out
+
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcucudecide.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "cucudecide.h")
@@ -44,12 +64,13 @@ class CucdError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "bit_depth", "ctu_size", "max_depth", "strong_intra_smoothing",
-                                       "device", "max_pictures", "host_threads")]
+                                       "device", "max_pictures", "host_threads", "auto_pin_host")]
 
 
 class _FrameOut(C.Structure):
     _fields_ = [("obf", _i16p), ("outlier", _i16p), ("yc", _f64p), ("num_obf", _i32p * 4), ("n_outlier", _i32p * 4),
-                ("ctu_src_had", _i32p), ("rmd_cost", _u32p), ("rmd_cost_packed", C.POINTER(C.c_uint8))]
+                ("ctu_src_had", _i32p), ("rmd_cost", _u32p), ("rmd_cost_packed", C.POINTER(C.c_uint8)),
+                ("obf_u8", C.POINTER(C.c_uint8)), ("outlier_u8", C.POINTER(C.c_uint8))]
 
 
 class _DevOut(C.Structure):
@@ -110,6 +131,14 @@ def load_library():
     lib.cucd_destroy.argtypes = [C.c_void_p]
     lib.cuCUDecide_frames.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int,
                                       C.POINTER(_FrameOut)]
+    lib.cuCUDecide_frames_u8.argtypes = lib.cuCUDecide_frames.argtypes
+    lib.cucd_pin_host_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.cucd_unpin_host_buffer.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cucd_unpack_costs.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cucd_unpack_costs.restype = None
+    lib.cucd_packed_cost.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.cucd_packed_cost.restype = C.c_uint32
+    lib.cucd_set_rmd_path.argtypes = [C.c_void_p, C.c_int]
     lib.cuCUDecide_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(_FrameOut)]
     lib.cucd_intra_rmd_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PuDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cucd_set_ref_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -129,6 +158,8 @@ def load_library():
                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     lib.cucd_dev_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
                                     C.c_int, C.POINTER(_DevOut), C.c_void_p]
+    lib.cucd_dev_frames_begin.argtypes = lib.cucd_dev_frames.argtypes
+    lib.cucd_dev_frames_end.argtypes = [C.c_void_p]
     lib.cucd_queue_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.cucd_queue_destroy.argtypes = [C.c_void_p]
     lib.cucd_queue_submit.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
@@ -154,38 +185,24 @@ def tcm_fit(hist, n_blocks):
     return yc, thr
 
 
-def exp_satd_tc(org, pred, iters=1):
-    """cucd_exp_satd_tc: (nTiles, 64) uint8 source and prediction tiles -> (satd uint32[nTiles], mean kernel ms)."""
-    lib = load_library()
-    org = np.ascontiguousarray(org, np.uint8)
-    pred = np.ascontiguousarray(pred, np.uint8)
-    n = org.shape[0]
-    out = np.zeros(n, np.uint32)
-    ms = C.c_float(0)
-    lib.cucd_exp_satd_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
-    rc = lib.cucd_exp_satd_tc(org.ctypes.data, pred.ctypes.data, n, out.ctypes.data, int(iters), C.byref(ms))
-    if rc != 0:
-        raise CucdError(f"cucd_exp_satd_tc failed ({rc})")
-    return out, float(ms.value)
-
-
-def _plane(a):
+def _plane(a, dtype=np.int16):
     a = np.asarray(a)
-    if a.dtype != np.int16 or a.ndim != 2 or a.strides[1] != 2 or a.strides[0] % 2:
-        raise ValueError("planes must be 2-D int16 arrays with contiguous rows")
-    return a, a.strides[0] // 2
+    isz = np.dtype(dtype).itemsize
+    if a.dtype != dtype or a.ndim != 2 or a.strides[1] != isz or a.strides[0] % isz:
+        raise ValueError(f"planes must be 2-D {np.dtype(dtype).name} arrays with contiguous rows")
+    return a, a.strides[0] // isz
 
 
 class Engine:
     """One cucd_handle: one encoder instance on one GPU."""
 
-    def __init__(self, width, height, bit_depth=8, strong_intra_smoothing=1, device=0, max_pictures=1, host_threads=0):
+    def __init__(self, width, height, bit_depth=8, strong_intra_smoothing=1, device=0, max_pictures=1, host_threads=0, auto_pin_host=0):
         self.lib = load_library()
         self.width, self.height, self.bit_depth = int(width), int(height), int(bit_depth)
         self.ctus_per_row = (self.width + 63) // 64
         self.ctus_per_pic = self.ctus_per_row * ((self.height + 63) // 64)
         cfg = _Config(self.width, self.height, self.bit_depth, 64, 4, int(strong_intra_smoothing), int(device), int(max_pictures),
-                      int(host_threads))
+                      int(host_threads), int(auto_pin_host))
         self.h = C.c_void_p()
         rc = self.lib.cucd_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -224,13 +241,17 @@ class Engine:
         return self.height // s, self.width // s
 
     # ---- S1/S4 (+ replay S2) --------------------------------------------------------------------
-    def alloc_frame_out(self, want_rmd=True, pinned_alloc=None, packed=False):
+    def alloc_frame_out(self, want_rmd=True, pinned_alloc=None, packed=False, narrow=False):
         """numpy output buffers for one picture (pinned_alloc(shape, dtype) may supply pinned memory).
-        packed=True asks for the cost tables in the packed CTU format (rmd_cost_packed) instead of uint32."""
+        packed=True asks for the cost tables in the packed CTU format (rmd_cost_packed) instead of uint32,
+        narrow=True for the OBF / Outlier planes as bytes (obf_u8 / outlier_u8) instead of int16."""
         mk = pinned_alloc or (lambda shape, dtype: np.zeros(shape, dtype))
         W, H = self.width, self.height
-        out = {"obf": mk((H // 4, W // 4), np.int16), "outlier": mk((H, W), np.int16), "yc": mk((16,), np.float64),
-               "ctu_src_had": mk((self.ctus_per_pic,), np.int32)}
+        out = {"yc": mk((16,), np.float64), "ctu_src_had": mk((self.ctus_per_pic,), np.int32)}
+        if narrow:
+            out["obf_u8"] = mk((H // 4, W // 4), np.uint8); out["outlier_u8"] = mk((H, W), np.uint8)
+        else:
+            out["obf"] = mk((H // 4, W // 4), np.int16); out["outlier"] = mk((H, W), np.int16)
         for d in range(4):
             out[f"num_obf{d}"] = mk(self.cu_grid(d), np.int32)
             out[f"n_outlier{d}"] = mk(self.cu_grid(d), np.int32)
@@ -256,26 +277,48 @@ class Engine:
         fo.ctu_src_had = ptr("ctu_src_had", _i32p)
         fo.rmd_cost = ptr("rmd_cost", _u32p)
         fo.rmd_cost_packed = ptr("rmd_cost_packed", C.POINTER(C.c_uint8))
+        fo.obf_u8 = ptr("obf_u8", C.POINTER(C.c_uint8))
+        fo.outlier_u8 = ptr("outlier_u8", C.POINTER(C.c_uint8))
         return fo
 
     def frames(self, orgs, recs=None, outs=None, want_rmd=True):
-        """cuCUDecide_frames on host planes; returns the list of output dicts."""
+        """cuCUDecide_frames (int16 planes) / cuCUDecide_frames_u8 (uint8 planes) on host planes; returns the list of output dicts."""
         n = len(orgs)
-        planes = [_plane(a) for a in orgs]
+        dt = np.uint8 if np.asarray(orgs[0]).dtype == np.uint8 else np.int16
+        fn = self.lib.cuCUDecide_frames_u8 if dt == np.uint8 else self.lib.cuCUDecide_frames
+        planes = [_plane(a, dt) for a in orgs]
         stride = planes[0][1]
         assert all(s == stride and p.shape == (self.height, self.width) for p, s in planes)
         org_ptrs = (C.c_void_p * n)(*[p.ctypes.data for p, _ in planes])
         rec_ptrs, rstride = None, 0
         if recs is not None:
-            rp = [_plane(a) for a in recs]
+            rp = [_plane(a, dt) for a in recs]
             rstride = rp[0][1]
             assert len(rp) == n and all(s == rstride and p.shape == (self.height, self.width) for p, s in rp)
             rec_ptrs = (C.c_void_p * n)(*[p.ctypes.data for p, _ in rp])
         if outs is None:
             outs = [self.alloc_frame_out(want_rmd and recs is not None) for _ in range(n)]
         fos = (_FrameOut * n)(*[self._frame_out_struct(o) for o in outs])
-        self._check(self.lib.cuCUDecide_frames(self.h, n, org_ptrs, stride, rec_ptrs, rstride, fos), "cuCUDecide_frames")
+        self._check(fn(self.h, n, org_ptrs, stride, rec_ptrs, rstride, fos), "cuCUDecide_frames")
         return outs
+
+    def pin_host_buffer(self, a):
+        """cucd_pin_host_buffer on the memory of a numpy array (page-locks it for the lifetime of the handle)"""
+        a = np.asarray(a)
+        lo = a.ctypes.data
+        nbytes = (a.shape[0] - 1) * a.strides[0] + a.shape[1] * a.strides[1] if a.ndim == 2 else a.nbytes
+        self._check(self.lib.cucd_pin_host_buffer(self.h, lo, nbytes), "cucd_pin_host_buffer")
+
+    def unpin_host_buffer(self, a):
+        self._check(self.lib.cucd_unpin_host_buffer(self.h, np.asarray(a).ctypes.data), "cucd_unpin_host_buffer")
+
+    def unpack_costs_c(self, packed):
+        """cucd_unpack_costs per CTU (the C helper a host encoder would call)"""
+        packed = np.ascontiguousarray(packed, np.uint8).reshape(-1, PACKED_CTU_BYTES)
+        out = np.empty((packed.shape[0], PUS_PER_CTU, NUM_MODES), np.uint32)
+        for i in range(packed.shape[0]):
+            self.lib.cucd_unpack_costs(packed[i].ctypes.data, out[i].ctypes.data)
+        return out
 
     def frame(self, org, rec=None, poc=0, out=None, want_rmd=True):
         """cuCUDecide_frame: one picture."""
@@ -430,8 +473,9 @@ class Engine:
         self._check(self.lib.cucd_dev_feature_obf(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_thr, d_obf, d_outlier,
                                                   num, summ, d_ctu_had), "cucd_dev_feature_obf")
 
-    def dev_frames(self, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride, d_out, yc_host=None):
-        """cucd_dev_frames: d_out = dict of device pointers (obf, outlier, num_obf[4], n_outlier[4], ctu_src_had, rmd_cost)."""
+    def dev_frames(self, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride, d_out, yc_host=None, begin_only=False):
+        """cucd_dev_frames (or, with begin_only, cucd_dev_frames_begin - pair it with dev_frames_end):
+        d_out = dict of device pointers (obf, outlier, num_obf[4], n_outlier[4], ctu_src_had, rmd_cost)."""
         o = _DevOut()
         o.obf = d_out.get("obf")
         o.outlier = d_out.get("outlier")
@@ -441,8 +485,11 @@ class Engine:
         o.ctu_src_had = d_out.get("ctu_src_had")
         o.rmd_cost = d_out.get("rmd_cost")
         yc = yc_host.ctypes.data if yc_host is not None else None
-        self._check(self.lib.cucd_dev_frames(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride,
-                                             C.byref(o), yc), "cucd_dev_frames")
+        fn = self.lib.cucd_dev_frames_begin if begin_only else self.lib.cucd_dev_frames
+        self._check(fn(self.h, stream, n_pics, d_org, org_pic_stride, org_stride, d_rec, rec_pic_stride, rec_stride, C.byref(o), yc), "cucd_dev_frames")
+
+    def dev_frames_end(self):
+        self._check(self.lib.cucd_dev_frames_end(self.h), "cucd_dev_frames_end")
 
     def last_kernel_time_ms(self):
         ms = C.c_float(0)
@@ -458,8 +505,7 @@ class Engine:
         return float(ms.value), int(n)
 
     def set_rmd_path(self, path):
-        """0 / False: integer ALU; 1 / True: predictions + Hadamard on tcgen05 (8-bit); 2: tcgen05 Hadamard only (8-bit)"""
-        self.lib.cucd_set_rmd_path.argtypes = [C.c_void_p, C.c_int]
+        """0 / False: integer ALU; 1 / True: predictions + Hadamard on the tensor cores (tcgen05)"""
         self._check(self.lib.cucd_set_rmd_path(self.h, int(path)), "cucd_set_rmd_path")
 
 

@@ -9,6 +9,7 @@
 // (16 lanes read 128 contiguous bytes of a sample row).  These kernels are HBM/L2 streaming
 // kernels: 8 B of source per thread row, 32 B of Outlier output per thread.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include "feature_core.cuh"
 #include "kernels.h"
 
@@ -70,10 +71,18 @@ feature_obf_kernel(const FeaturePlanes fp, const int32_t* __restrict__ thr, cons
       const uint32_t q = (uint32_t)(uint16_t)(int16_t)(p / 100);
       if (f & 1) o[f >> 1] |= q << 16; else o[f >> 1] = q;
     }
-    int16_t* dst = out.outlier + (size_t)pic * out.outlierPicStride + (size_t)(by * 4) * fp.W + bx * 4;
+    if (out.outlier) {
+      int16_t* dst = out.outlier + (size_t)pic * out.outlierPicStride + (size_t)(by * 4) * fp.W + bx * 4;
 #pragma unroll
-    for (int y = 0; y < 4; y++) *reinterpret_cast<uint2*>(dst + (size_t)y * fp.W) = make_uint2(o[2 * y], o[2 * y + 1]);
-    out.obf[(size_t)pic * out.obfPicStride + (size_t)by * bw + bx] = (int16_t)cnt;
+      for (int y = 0; y < 4; y++) *reinterpret_cast<uint2*>(dst + (size_t)y * fp.W) = make_uint2(o[2 * y], o[2 * y + 1]);
+    }
+    if (out.outlier8) {                   // |AC coefficient| / 100 <= 163: exact as a byte (include/cucudecide.h)
+      uint8_t* dst = out.outlier8 + (size_t)pic * out.outlierPicStride + (size_t)(by * 4) * fp.W + bx * 4;
+#pragma unroll
+      for (int y = 0; y < 4; y++) *reinterpret_cast<uint32_t*>(dst + (size_t)y * fp.W) = __byte_perm(o[2 * y], o[2 * y + 1], 0x6420);
+    }
+    if (out.obf) out.obf[(size_t)pic * out.obfPicStride + (size_t)by * bw + bx] = (int16_t)cnt;
+    if (out.obf8) out.obf8[(size_t)pic * out.obfPicStride + (size_t)by * bw + bx] = (uint8_t)cnt;
   }
   cell[cy][cx] = (int16_t)cnt;
   __syncthreads();
@@ -172,6 +181,21 @@ cudaError_t launch_copy_words(const uint32_t* src, uint32_t* dst, size_t nWords,
   return cudaGetLastError();
 }
 
+// 16 samples per thread: u8 -> int16 (upload of 8-bit content held as bytes)
+__global__ void widen_u8_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = src[i];
+    dst[2 * i] = make_uint4(__byte_perm(v.x, 0, 0x4140), __byte_perm(v.x, 0, 0x4342), __byte_perm(v.y, 0, 0x4140), __byte_perm(v.y, 0, 0x4342));
+    dst[2 * i + 1] = make_uint4(__byte_perm(v.z, 0, 0x4140), __byte_perm(v.z, 0, 0x4342), __byte_perm(v.w, 0, 0x4140), __byte_perm(v.w, 0, 0x4342));
+  }
+}
+static int convert_blocks(size_t n16) { return (int)std::min<size_t>((n16 + 255) / 256, 148 * 8); }
+cudaError_t launch_widen_u8(const uint8_t* src, int16_t* dst, size_t nSamples, cudaStream_t st, int* launches) {
+  if (nSamples == 0) return cudaSuccess;
+  widen_u8_kernel<<<convert_blocks(nSamples / 16), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), nSamples / 16);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
 cudaError_t launch_feature_hist(const FeaturePlanes& fp, int nPics, uint32_t* hist, cudaStream_t st, int* launches) {
   cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;

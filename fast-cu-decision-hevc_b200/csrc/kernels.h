@@ -11,8 +11,10 @@ constexpr int kHistFreqs = 16;      // index 0 (DC) unused
 
 // ---- intra RMD (rmd_kernels.cu) ---------------------------------------------------------------
 cudaError_t launch_rmd_frames(const FrameSource& fs, int nPics, int bitDepth, int strong, cudaStream_t st, int* launches);
-// tensor-core (tcgen05 kind::i8) variant for 8-bit content; `hadamard` = 16 KB prepared by launch_hadamard_operands
-cudaError_t launch_rmd_frames_tc(const FrameSource& fs, int nPics, int strong, const int8_t* hadamard, cudaStream_t st, int* launches);
+// per-device set-up of the kernels that need more than 48 KB of dynamic shared memory (cucd_create, after cudaSetDevice)
+cudaError_t configure_rmd_kernels();
+cudaError_t configure_rmd_tc2_kernels();
+// +-(H8 (x) H8), +-(blockdiag H4 (x) H4) as s8 UMMA operands, 16 KB: B operand of the tensor-core SATD
 cudaError_t launch_hadamard_operands(int8_t* dst, cudaStream_t st);
 // predictions AND Hadamard on tcgen05 (rmd_tc2_kernels.cu); tabWin / tabN4 = tc2::fill_win_tables / fill_n4_tables uploaded by the caller
 cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
@@ -21,8 +23,6 @@ int rmd_tc2_smem_bytes();
 // the same tensor-core rounds for S2 batches of ONE PU size with caller-supplied borders (8-bit content)
 cudaError_t launch_rmd_batch_tc2(int log2n, const BatchSource& bs, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
                                  cudaStream_t st, int* launches);
-// uint32 [nCtus][341][35] -> packed CTU tables of include/cucudecide.h (CUCD_PACKED_CTU_BYTES each)
-cudaError_t launch_pack_costs(const uint32_t* cost, uint8_t* packed, int nCtus, cudaStream_t st, int* launches);
 cudaError_t launch_rmd_batch(int log2n, const BatchSource& bs, int bitDepth, int strong, cudaStream_t st, int* launches);
 
 // ---- per-picture texture features (feature_kernels.cu) ----------------------------------------
@@ -39,12 +39,15 @@ cudaError_t launch_copy_words(const uint32_t* src, uint32_t* dst, size_t nWords,
 struct FeatureOut {
   int16_t* obf; long long obfPicStride;           // [(H/4)][(W/4)] tight
   int16_t* outlier; long long outlierPicStride;   // [H][W] tight
+  uint8_t* obf8; uint8_t* outlier8;               // the same planes as bytes (exact, see include/cucudecide.h); any of the four may be null
   int32_t* numObf[4]; int32_t* nOutlier[4];       // per depth: [(H/size)][(W/size)] tight
   long long cuPicStride[4];
 };
 cudaError_t launch_feature_obf(const FeaturePlanes& fp, int nPics, const int32_t* thr, const FeatureOut& out, cudaStream_t st, int* launches);
 // source-only DC-less 8x8 Hadamard cost per CTU: ctuHad[pic][ctusPerPic]
 cudaError_t launch_ctu_src_had(const FeaturePlanes& fp, int nPics, int32_t* ctuHad, cudaStream_t st, int* launches);
+// u8 -> int16 samples behind the upload of 8-bit content held as bytes (cuCUDecide_frames_u8); nSamples % 16 == 0, 16-byte aligned
+cudaError_t launch_widen_u8(const uint8_t* src, int16_t* dst, size_t nSamples, cudaStream_t st, int* launches);
 
 // ---- CU texture features and AQ activity (texture_kernels.cu) -----------------------------------
 struct TmvCu { int32_t x, y, log2n, pad; };

@@ -194,8 +194,43 @@ struct FrameSource {
   long long orgPicStride, recPicStride;     // samples between pictures
   int orgStride, recStride;                 // samples between rows
   int W, H, ctusPerRow, ctusPerPic;
-  uint32_t* out;                            // [pic][ctu][341][35]
+  uint32_t* out;                            // [pic][ctu][341][35], or null
+  uint8_t* outPacked;                       // [pic][ctu][kPackedCtuBytes]: the packed CTU tables of include/cucudecide.h, or null
 };
+
+// ---------------------------------------------------------------------------------------------
+// packed CTU cost table (include/cucudecide.h): uint32 for PUs 0..20, uint16 for the 8x8 PUs, 13-bit stream for the 4x4 PUs
+// ---------------------------------------------------------------------------------------------
+constexpr int kPackedWidePus = 21;
+constexpr int kPackedU16Off = kPackedWidePus * kNumModes * 4;               // 2940
+constexpr int kPackedB13Off = kPackedU16Off + 64 * kNumModes * 2;           // 7420
+constexpr int kPackedCtuBytes = kPackedB13Off + 256 * kNumModes * 13 / 8;   // 21980
+// Store the cost block of one depth (PUs of size 1 << LOG2N, element i = pu * 35 + mode, PUS * 35 elements) of one CTU.
+// val(i) returns the cost, or 0xffffffff for a PU that is not inside the picture.  Every thread writes whole 32-bit words.
+template <int LOG2N, class Val>
+CUCD_HD void store_packed_depth(uint8_t* ctuBase, int tid, int nthreads, Val val) {
+  constexpr int PUS = 4096 >> (2 * LOG2N), ELEMS = PUS * kNumModes;
+  if (LOG2N >= 4) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(ctuBase) + pu_offset_of_depth(6 - LOG2N) * kNumModes;
+    for (int i = tid; i < ELEMS; i += nthreads) o[i] = val(i);
+  } else if (LOG2N == 3) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(ctuBase + kPackedU16Off);
+    for (int w = tid; w < ELEMS / 2; w += nthreads) o[w] = (val(2 * w) & 0xffffu) | (val(2 * w + 1) << 16);
+  } else {
+    uint32_t* o = reinterpret_cast<uint32_t*>(ctuBase + kPackedB13Off);
+    for (int w = tid; w < ELEMS * 13 / 32; w += nthreads) {
+      const int bit0 = 32 * w, e0 = bit0 / 13, sh = bit0 - 13 * e0;
+      unsigned long long acc = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int e = e0 + k;
+        const unsigned long long v = e < ELEMS ? (unsigned long long)(val(e) & 0x1fffu) : 0ull;
+        acc |= v << (13 * k);
+      }
+      o[w] = (uint32_t)(acc >> sh);
+    }
+  }
+}
 // Batch mode: `count` host-described PUs of one size, tightly packed source blocks and borders.
 struct BatchPu { int32_t orgOff, borderOff, outIndex, pad; };   // sample offsets into org / border, row of the cost table
 struct BatchSource {

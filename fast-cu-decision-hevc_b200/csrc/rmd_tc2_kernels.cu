@@ -454,15 +454,15 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
     const int cgc = unit * C::CTUS + c;
     if (cgc >= a.totalCtus) break;
     const uint8_t* valid = smem + C::VALID_OFF + c * 256;
-    uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
-    if (LOG2N == 2) {
-      const uint16_t* a16 = reinterpret_cast<const uint16_t*>(acc) + c * C::PUS * kNumModes;
-#pragma unroll 5
-      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? (uint32_t)a16[i] : 0xffffffffu;
-    } else {
+    const uint16_t* a16 = reinterpret_cast<const uint16_t*>(acc) + c * C::PUS * kNumModes;
+    const uint32_t* a32 = acc + c * C::PUS * kNumModes;
+    auto val = [&](int i) -> uint32_t { return valid[i / kNumModes] ? (LOG2N == 2 ? (uint32_t)a16[i] : a32[i]) : 0xffffffffu; };
+    if (fs.out) {
+      uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
 #pragma unroll 4
-      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valid[i / kNumModes] ? acc[c * C::PUS * kNumModes + i] : 0xffffffffu;
+      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = val(i);
     }
+    if (fs.outPacked) store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, val);
   }
   if (warp == 0) tmem_dealloc(tmemBase, 256);
   TC2_STAMP(3);
@@ -493,12 +493,6 @@ rmd_batch_tc2_kernel(const Tc2Args a) { tc2_body<LOG2N, false>(a, blockIdx.x); }
 
 template <int LOG2N>
 cudaError_t launch_batch_tc2(const Tc2Args& a, int units, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rmd_batch_tc2_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<LOG2N>::TOTAL);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   rmd_batch_tc2_kernel<LOG2N><<<(units + Cfg<LOG2N>::CTUS - 1) / Cfg<LOG2N>::CTUS, kThreads, Cfg<LOG2N>::TOTAL, st>>>(a);
   return cudaGetLastError();
 }
@@ -506,6 +500,17 @@ cudaError_t launch_batch_tc2(const Tc2Args& a, int units, cudaStream_t st) {
 }  // namespace
 
 int rmd_tc2_smem_bytes() { return kSmemBytes; }
+
+// per-device opt-in to > 48 KB of dynamic shared memory (called by cucd_create after cudaSetDevice)
+cudaError_t configure_rmd_tc2_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(rmd_frame_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rmd_batch_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rmd_batch_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rmd_batch_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<4>::TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rmd_batch_tc2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<5>::TOTAL);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rmd_batch_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<6>::TOTAL);
+  return e;
+}
 
 cudaError_t launch_rmd_batch_tc2(int log2n, const BatchSource& bs, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
                                  cudaStream_t st, int* launches) {
@@ -530,12 +535,6 @@ cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, 
                                   cudaStream_t st, int* launches) {
   const int total = nPics * fs.ctusPerPic;
   if (total <= 0) return cudaSuccess;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rmd_frame_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   Tc2Args a;
   a.fs = fs; a.bs = BatchSource{}; a.strong = strong; a.totalCtus = total; a.tabWin = tabWin; a.tabN4 = tabN4; a.had = hadamard;
   const int u2 = (total + 1) >> 1, u4 = (total + 3) >> 2;

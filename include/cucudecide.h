@@ -12,7 +12,13 @@
  *     (CommonDef.h:141-164): the shim turns a non-zero return into FATAL_ERROR_0.
  *   - samples are HM `Pel` = int16_t (TypeDef.h:769) with a caller-given stride in samples; luma only.
  *   - the caller owns every host buffer; the library owns device memory, pinned staging and streams.
- *   - a handle belongs to one encoder instance and one CUDA device; it is not thread-safe.
+ *   - a handle belongs to one encoder instance and one CUDA device.  Every entry point takes the handle's lock, so calls
+ *     from several host threads (or from a cucd_queue worker beside the encoder thread) serialise instead of racing;
+ *     cucd_last_error / cucd_launch_count / the kernel timers describe the most recent call and are only meaningful to
+ *     the thread that made it.  Concurrency across encoder instances = one handle each.
+ *   - 8-bit content: samples must lie in 0..255 (bit_depth 8 means exactly that).  The 8-bit kernels carry samples as
+ *     bytes; a value outside the range is a caller error and is reduced modulo 256, as storing it into HM's 8-bit
+ *     file formats would.  (9/10-bit content: 0..1023.)
  *   - cost tables are uint32_t[35] per PU, index = HEVC intra mode, value = what
  *     distParam.DistFunc returns at TEncSearch.cpp:2339 (Hadamard SATD >> (bitDepth-8)).
  *   - "border" = the unfiltered reference samples of a PU as a linear array of 4N+1 int16:
@@ -32,7 +38,7 @@ extern "C" {
 
 #define CUCD_NUM_INTRA_MODES 35
 #define CUCD_PUS_PER_CTU 341
-#define CUCD_ABI_VERSION 3
+#define CUCD_ABI_VERSION 4
 
 typedef enum {
   CUCD_OK = 0,
@@ -54,7 +60,12 @@ typedef struct {
   int strong_intra_smoothing;  /* SPS flag (TComPattern.cpp:195)                                  */
   int device;                  /* CUDA device ordinal                                             */
   int max_pictures;            /* pictures one cuCUDecide_frames call may carry (>= 1)            */
-  int host_threads;            /* threads for the host-side TCM fit, 0 = min(8, hardware concurrency) */
+  int host_threads;            /* persistent worker threads for the host-side TCM fit, 0 = min(8, hardware concurrency);
+                                * several handles / ranks on one host: give each cores / handles                    */
+  int auto_pin_host;           /* 1: page-lock (cudaHostRegister) caller planes / output buffers of cuCUDecide_frames on first
+                                * sight and keep them registered until cucd_destroy - for callers whose buffers live as long
+                                * as the handle (HM's TComPicYuv planes, xMalloc, TComPicYuv.cpp:97).  0: only buffers given to
+                                * cucd_pin_host_buffer, or already pinned, take the fast path                        */
 } cucd_config;
 
 int cucd_abi_version(void);
@@ -63,6 +74,12 @@ int cucd_destroy(cucd_handle* h);
 const char* cucd_last_error(const cucd_handle* h);   /* h may be NULL: error of the last failed create */
 /* kernels launched by this handle so far (what bench.py reports as gpu_launches) */
 long long cucd_launch_count(const cucd_handle* h);
+/* Page-lock a caller buffer for the lifetime of the handle (or until cucd_unpin_host_buffer): HM allocates its picture planes
+ * once (TComPicYuv::create, xMalloc, TComPicYuv.cpp:97) and pageable memory costs an extra staging copy inside the driver on
+ * every transfer.  `ptr` may point anywhere inside the allocation; [ptr, ptr + bytes) is registered (rounded out to pages).
+ * Must be unpinned (or the handle destroyed) before the memory is freed. */
+int cucd_pin_host_buffer(cucd_handle* h, const void* ptr, size_t bytes);
+int cucd_unpin_host_buffer(cucd_handle* h, const void* ptr);
 
 /* ------------------------------------------------------------------------------------------------
  * S1 + S4 (+ frame-replay S2): one picture, or a batch of pictures.
@@ -81,22 +98,39 @@ typedef struct {
   int32_t* ctu_src_had;    /* one per CTU: updateCtuDataISlice's iSumHad                                  */
   uint32_t* rmd_cost;      /* nCtu*341*35: SATD tables; 0xFFFFFFFF for PUs not inside the picture         */
   uint8_t* rmd_cost_packed;/* nCtu*CUCD_PACKED_CTU_BYTES: the same tables, narrowest exact type (see below)*/
+  /* narrow, exact variants of obf / outlier (either, both or neither may be given beside the int16 planes): the call is
+   * PCIe bound, and both planes fit a byte - an OBF count is 0..15, and an AC coefficient of the 4x4 transform is at
+   * most 16 368 in magnitude for bit depths <= 10 (a basis row of g_aiT4 other than the DC row sums to at most 128 on
+   * its positive side: 128 * max sample >> shift_1st, then the DC row of the other dimension: * 256 >> 8,
+   * TEncSlice.cpp:922-926; the DC coefficient itself is dropped, :987-988), so |coeff| / 100 <= 163 */
+  uint8_t* obf_u8;         /* (W/4)*(H/4) */
+  uint8_t* outlier_u8;     /* W*H */
 } cucd_frame_out;
 
-/* Packed cost table of one CTU.  The numbers are those of rmd_cost; PUs of 8x8 and 4x4 are stored as uint16
- * (exact: an 8x8 SATD is <= 32 736 and a 4x4 SATD <= 8 184 for bit depths <= 10), which nearly halves the
- * device-to-host traffic of cuCUDecide_frames - the part of the call that is PCIe bound:
- *   bytes [0, 2940)      uint32[21][35]   PUs 0..20   (64x64, 4 x 32x32, 16 x 16x16)
- *   bytes [2940, 25340)  uint16[320][35]  PUs 21..340 (64 x 8x8, 256 x 4x4); 0xFFFF = PU not inside the picture */
+/* Packed cost table of one CTU.  The numbers are those of rmd_cost in the narrowest exact width per PU size, which more
+ * than halves the device-to-host traffic of cuCUDecide_frames - the part of the call that is PCIe bound.  The RMD
+ * kernels write this layout directly.
+ *   bytes [0, 2940)       uint32[21][35]    PUs 0..20    (64x64, 4 x 32x32, 16 x 16x16)
+ *   bytes [2940, 7420)    uint16[64][35]    PUs 21..84   (8x8: SATD <= 32 736); 0xFFFF = PU not inside the picture
+ *   bytes [7420, 21980)   256*35 values of 13 bits, little-endian bit stream (value i occupies bits [13 i, 13 i + 13)
+ *                         of the region): PUs 85..340 (4x4: SATD <= 8 160 for bit depths <= 10); 0x1FFF = not inside */
 #define CUCD_PACKED_WIDE_PUS 21
-#define CUCD_PACKED_CTU_BYTES (CUCD_PACKED_WIDE_PUS * 35 * 4 + (CUCD_PUS_PER_CTU - CUCD_PACKED_WIDE_PUS) * 35 * 2)
-/* cost of (pu, mode) from one packed CTU table (host-side helper; widen 0xFFFF to 0xFFFFFFFF) */
+#define CUCD_PACKED_U16_PUS 64
+#define CUCD_PACKED_U16_OFFSET (CUCD_PACKED_WIDE_PUS * 35 * 4)
+#define CUCD_PACKED_B13_OFFSET (CUCD_PACKED_U16_OFFSET + CUCD_PACKED_U16_PUS * 35 * 2)
+#define CUCD_PACKED_CTU_BYTES (CUCD_PACKED_B13_OFFSET + 256 * 35 * 13 / 8)
+/* cost of (pu, mode) from one packed CTU table (host-side helper; the "not inside" codes widen to 0xFFFFFFFF) */
 uint32_t cucd_packed_cost(const uint8_t* ctu_table, int pu, int mode);
+/* the whole table of one CTU widened to uint32[341][35] */
+void cucd_unpack_costs(const uint8_t* ctu_table, uint32_t* cost);
 
 int cuCUDecide_frame(cucd_handle* h, const int16_t* orgY, int strideY, const int16_t* recY, int strideRec, int poc,
                      cucd_frame_out* out);
 int cuCUDecide_frames(cucd_handle* h, int nPics, const int16_t* const* orgY, int strideY, const int16_t* const* recY,
                       int strideRec, cucd_frame_out* outs);
+/* The same for callers that hold 8-bit content as bytes (the file format of 8-bit YUV; halves the upload).  bit_depth must be 8. */
+int cuCUDecide_frames_u8(cucd_handle* h, int nPics, const uint8_t* const* orgY, int strideY, const uint8_t* const* recY,
+                         int strideRec, cucd_frame_out* outs);
 
 /* ------------------------------------------------------------------------------------------------
  * S2: intra rough mode decision for a batch of PUs with caller-supplied borders.
@@ -259,10 +293,17 @@ typedef struct {
 } cucd_dev_out;
 int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
                     const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
-/* Frame-mode RMD has bit-identical implementations: 0 = integer ALU (prediction and Hadamard butterflies in
- * registers, any bit depth); 1 = tcgen05 kind::i8 for BOTH the angular predictions and the Hadamard stage
- * (8-bit content only, the default for it); 2 = ALU predictions + tcgen05 Hadamard (8-bit only).
- * CUCD_RMD_PATH=alu|tc1 in the environment at create time selects 0 / 2. */
+/* The host fit sits between the two feature passes; the split form lets a caller overlap it with GPU work of its own
+ * choice - typically the next batch:   begin(i); end(i-1); begin(i+1); end(i); ...   (at most 2 batches in flight).
+ * cucd_dev_frames_begin enqueues feature pass 1 and the RMD kernel and returns without waiting;
+ * cucd_dev_frames_end waits for the histograms of the OLDEST batch begun, fits, enqueues pass 2 and joins it into the
+ * stream given to begin.  cucd_dev_frames = begin + end. */
+int cucd_dev_frames_begin(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
+                          const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
+int cucd_dev_frames_end(cucd_handle* h);
+/* Frame-mode RMD has two bit-identical implementations: 0 = integer ALU (prediction and Hadamard butterflies in
+ * registers); 1 = tcgen05 tensor cores for the angular predictions and the Hadamard stage (the default).
+ * CUCD_RMD_PATH=alu in the environment at create time selects 0. */
 int cucd_set_rmd_path(cucd_handle* h, int path);
 /* Device time of the RMD kernel inside the last `nCalls` cucd_dev_frames calls (CUDA events recorded on the
  * caller's stream around that launch; ring of 64).  The stream must have been synchronised.  Returns
@@ -275,11 +316,6 @@ int cucd_last_kernel_time(cucd_handle* h, float* ms);
 /* the host-side fit that sits between the two passes (TEncSlice.cpp:291-392): hist = 16*4096 counts
  * of ONE picture, nBlocks = (W/4)*(H/4); writes yc[16] and thr[16] */
 int cucd_tcm_fit(const uint32_t* hist, int nBlocks, double* yc, int32_t* thr);
-
-/* Experimental building block (csrc/satd_tc.cuh): 8x8 Hadamard SATD of nTiles (multiple of 128) 8-bit
- * tiles on the tcgen05 tensor cores (kind::i8); host buffers, org/pred = nTiles*64 bytes row-major 8x8,
- * satd[i] = (sum|H(o-p)| + 2) >> 2 as xCalcHADs8x8 (TComRdCost.cpp:1439-1534).  avg_ms = mean kernel time. */
-int cucd_exp_satd_tc(const uint8_t* org, const uint8_t* pred, int nTiles, uint32_t* satd, int iters, float* avg_ms);
 
 #ifdef __cplusplus
 }

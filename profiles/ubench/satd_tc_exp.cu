@@ -1,10 +1,14 @@
 // satd_tc_exp.cu - stand-alone check of the tcgen05 (kind::i8) Hadamard SATD building block of
 // satd_tc.cuh: 8x8 tiles of 8-bit source and prediction in, (sum|H(o-p)| + 2) >> 2 per tile out.
-// Exposed as cucd_exp_satd_tc for tests/test_gpu_tensor_satd.py and for throughput measurement;
-// the product kernels adopt the block only where it is shown to beat the ALU butterflies.
+// A round-1 experiment kept for reference (not part of libcucudecide.so): the product's rmd_frame_tc2_kernel uses the same
+// building block.  Stand-alone program: checks the kernel against a CPU Hadamard and prints the kernel time.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../fast-cu-decision-hevc_b200/csrc satd_tc_exp.cu -o satd_tc_exp
 #include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "satd_tc.cuh"
-#include "../../include/cucudecide.h"
+enum { CUCD_OK = 0, CUCD_ERR_INVALID = -1, CUCD_ERR_CUDA = -3, CUCD_ERR_NOMEM = -4 };
 
 namespace cucd {
 using namespace tc;
@@ -74,7 +78,7 @@ satd_tc_exp_kernel(const uint8_t* __restrict__ org, const uint8_t* __restrict__ 
 
 }  // namespace cucd
 
-extern "C" int cucd_exp_satd_tc(const uint8_t* org, const uint8_t* pred, int nTiles, uint32_t* satd, int iters, float* avg_ms) {
+static int exp_satd_tc(const uint8_t* org, const uint8_t* pred, int nTiles, uint32_t* satd, int iters, float* avg_ms) {
   if (!org || !pred || !satd || nTiles <= 0 || (nTiles & 127) || iters < 1) return CUCD_ERR_INVALID;
   uint8_t *dO = nullptr, *dP = nullptr; uint32_t* dS = nullptr;
   const size_t bytes = (size_t)nTiles * 64;
@@ -94,4 +98,27 @@ extern "C" int cucd_exp_satd_tc(const uint8_t* org, const uint8_t* pred, int nTi
   cudaMemcpy(satd, dS, (size_t)nTiles * 4, cudaMemcpyDeviceToHost);
   cudaFree(dO); cudaFree(dP); cudaFree(dS); cudaEventDestroy(e0); cudaEventDestroy(e1);
   return e == cudaSuccess ? CUCD_OK : CUCD_ERR_CUDA;
+}
+
+static uint32_t cpu_satd8x8(const uint8_t* o, const uint8_t* p) {      // xCalcHADs8x8 (TComRdCost.cpp:1439-1534) as a plain matrix product
+  int d[64], t[64];
+  for (int i = 0; i < 64; i++) d[i] = (int)o[i] - (int)p[i];
+  for (int u = 0; u < 8; u++) for (int x = 0; x < 8; x++) { int a = 0; for (int y = 0; y < 8; y++) a += (__builtin_popcount(u & y) & 1) ? -d[y * 8 + x] : d[y * 8 + x]; t[u * 8 + x] = a; }
+  uint32_t sum = 0;
+  for (int u = 0; u < 8; u++) for (int v = 0; v < 8; v++) { int a = 0; for (int x = 0; x < 8; x++) a += (__builtin_popcount(v & x) & 1) ? -t[u * 8 + x] : t[u * 8 + x]; sum += (uint32_t)abs(a); }
+  return (sum + 2) >> 2;
+}
+int main() {
+  const int n = 128 * 40;
+  std::vector<uint8_t> org((size_t)n * 64), pred((size_t)n * 64);
+  srand(5);
+  for (auto& v : org) v = (uint8_t)(rand() & 255);
+  for (auto& v : pred) v = (uint8_t)(rand() & 255);
+  for (int i = 0; i < 128 * 64; i++) { org[i] = 255; pred[i] = 0; }
+  std::vector<uint32_t> got(n);
+  float ms = 0;
+  if (exp_satd_tc(org.data(), pred.data(), n, got.data(), 3, &ms) != CUCD_OK) { printf("kernel failed\n"); return 1; }
+  for (int k = 0; k < n; k++) if (got[k] != cpu_satd8x8(&org[(size_t)k * 64], &pred[(size_t)k * 64])) { printf("MISMATCH at tile %d\n", k); return 1; }
+  printf("tensor-core SATD: %d tiles bit-exact, %.1f us per launch\n", n, ms * 1e3);
+  return 0;
 }

@@ -193,4 +193,18 @@ int emul_feature_obf(int bitDepth, const int16_t* org, int stride, int W, int H,
   return 0;
 }
 
+
+// the kernels' packed-table store (rmd_chunk.cuh store_packed_depth) for one CTU: cost = uint32[341][35] in, packed table out,
+// written depth by depth by `nthreads` emulated threads exactly as the CTAs do
+int emul_store_packed_ctu(const uint32_t* cost, int nthreads, uint8_t* packed) {
+  for (int tid = 0; tid < nthreads; tid++) {
+    store_packed_depth<6>(packed, tid, nthreads, [&](int i) { return cost[(size_t)pu_offset_of_depth(0) * kNumModes + i]; });
+    store_packed_depth<5>(packed, tid, nthreads, [&](int i) { return cost[(size_t)pu_offset_of_depth(1) * kNumModes + i]; });
+    store_packed_depth<4>(packed, tid, nthreads, [&](int i) { return cost[(size_t)pu_offset_of_depth(2) * kNumModes + i]; });
+    store_packed_depth<3>(packed, tid, nthreads, [&](int i) { return cost[(size_t)pu_offset_of_depth(3) * kNumModes + i]; });
+    store_packed_depth<2>(packed, tid, nthreads, [&](int i) { return cost[(size_t)pu_offset_of_depth(4) * kNumModes + i]; });
+  }
+  return kPackedCtuBytes;
+}
+
 }  // extern "C"

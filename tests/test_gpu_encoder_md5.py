@@ -87,3 +87,41 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
                 assert d.stdout.count("(OK)") == frames and "ERROR" not in d.stdout.upper().replace("(OK)", "")
                 assert hashlib.md5(open(os.path.join(wd, "dec.yuv"), "rb").read()).hexdigest() == out[binary][1]
     assert out["TAppEncoder"] == out["TAppEncoderCucd"], out
+
+
+# ---- the BASELINE configurations at their stated sizes (1920x1080 / 3840x2160) --------------------------------------------------------
+# The CPU-only reference encoder was run once in the build container (tests/golden/gen_golden_md5.py -> encoder_md5.json); here only
+# the integrated build runs, on the GPU box, and must reproduce the recorded bitstream and reconstruction byte for byte.
+def _fullsize_cases():
+    import json
+    path = os.path.join(ROOT, "tests", "golden", "encoder_md5.json")
+    return sorted(json.load(open(path)).items()) if os.path.exists(path) else []
+
+
+@pytest.mark.parametrize("name,ref", _fullsize_cases(), ids=[n for n, _ in _fullsize_cases()])
+def test_fullsize_bitstream_md5_matches_recorded_reference(name, ref):
+    """1080p: 17 CTU rows, the last 56 samples high -> forced splits down to 8x8 (TEncCu.cpp:488-489, 648) go through the live
+    encoder; LDP / RA: the full +-64 TZ window at real picture size (TEncSearch.cpp:3865-3881); QP 22 / 27 / 37; Main10 at 2160p."""
+    import time
+    import gen_golden as gg
+    import gen_golden_md5 as gm
+    for b in ("TAppEncoderCucd", "TAppDecoder"):
+        if not os.path.exists(os.path.join(REF, b)):
+            pytest.skip(f"oracle/_ref/{b} not built (needs /root/reference in the build container)")
+    W, H, bd, frames, qp = ref["width"], ref["height"], ref["bit_depth"], ref["frames"], ref["qp"]
+    with tempfile.TemporaryDirectory(prefix="cucd_md5_") as wd:
+        open(os.path.join(wd, "clip.yuv"), "wb").write(gg.synth_clip(W, H, frames, bd, ref["seed"]))
+        t0 = time.perf_counter()
+        r = subprocess.run(gm.encoder_args(os.path.join(REF, "TAppEncoderCucd"), W, H, frames, bd, qp, ref["structure"]), cwd=wd, capture_output=True,
+                           text=True, timeout=2400)
+        dt = time.perf_counter() - t0
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "RMD PUs on the GPU" in r.stderr, r.stderr[-500:]
+        got = (gm.file_md5(os.path.join(wd, "out.bin")), gm.file_md5(os.path.join(wd, "rec.yuv")), os.path.getsize(os.path.join(wd, "out.bin")))
+        print(f"{name}: TAppEncoderCucd {dt:.1f} s (CPU-only reference in the build container: {ref['cpu_encoder_seconds_build_container']} s); " + r.stderr.strip().splitlines()[-1])
+        assert got == (ref["bitstream_md5"], ref["rec_md5"], ref["bitstream_bytes"]), (name, got)
+        if ref["structure"] != "AI":
+            assert int(r.stderr.split("GPU,")[1].split("ME searches")[0]) > 10000
+        d = subprocess.run([os.path.join(REF, "TAppDecoder"), "-b", "out.bin", "-o", "dec.yuv", "-d", "0"], cwd=wd, capture_output=True, text=True, timeout=600)
+        assert d.returncode == 0 and d.stdout.count("(OK)") == frames
+        assert gm.file_md5(os.path.join(wd, "dec.yuv")) == ref["rec_md5"]

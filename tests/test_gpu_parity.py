@@ -230,8 +230,7 @@ def test_me_surfaces_vs_oracle(cucd, oracle, bd):
             eng.me_sad_surface([dict(x=0, y=0, w=16, h=16, ref_idx=0, left=-81, right=0, top=0, bottom=0, sub_shift=0)])
 
 
-# ---- the three frame-RMD implementations (ALU, tcgen05 prediction + Hadamard, tcgen05 Hadamard only) must
-# ---- agree bit for bit ---------------------------------------------------------------------------------------
+# ---- the two frame-RMD implementations (integer ALU, tcgen05 prediction + Hadamard) must agree bit for bit -------
 @pytest.mark.parametrize("W,H", [(416, 240), (200, 136), (64, 64), (328, 72)])
 def test_tensor_core_path_equals_alu_path_and_oracle(cucd, oracle, W, H):
     org = textured_plane(W, H, 8, seed=W)
@@ -240,8 +239,6 @@ def test_tensor_core_path_equals_alu_path_and_oracle(cucd, oracle, W, H):
     with cucd.Engine(W, H, max_pictures=3) as eng:
         eng.set_rmd_path(1)
         tc = eng.frames([org, rec, org], [rec, org, org])      # 3 pictures: CTU groups of 4 straddle pictures
-        eng.set_rmd_path(2)
-        tc1 = eng.frames([org, rec, org], [rec, org, org])
         eng.set_rmd_path(0)
         alu = eng.frames([org, rec, org], [rec, org, org])
     want = oracle_rmd_frame(oracle, org, rec, 8)
@@ -249,7 +246,6 @@ def test_tensor_core_path_equals_alu_path_and_oracle(cucd, oracle, W, H):
     assert np.array_equal(alu[0]["rmd_cost"], want)
     for k in range(3):
         assert np.array_equal(tc[k]["rmd_cost"], alu[k]["rmd_cost"])
-        assert np.array_equal(tc1[k]["rmd_cost"], alu[k]["rmd_cost"])
 
 
 def test_tensor_core_path_extreme_values(cucd, oracle):
@@ -258,11 +254,11 @@ def test_tensor_core_path_extreme_values(cucd, oracle):
     for org, rec in [(np.where((xx + yy) & 1, 255, 0), np.where((xx + yy) & 1, 0, 255)), (np.full((H, W), 255), np.zeros((H, W))),
                      (np.where(xx & 1, 255, 0), np.full((H, W), 255))]:
         org = org.astype(np.int16); rec = rec.astype(np.int16)
-        for path in (1, 2):
-            with cucd.Engine(W, H) as eng:
-                eng.set_rmd_path(path)
-                got = eng.frame(org, rec)["rmd_cost"]
-            assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8)), path
+        with cucd.Engine(W, H) as eng:
+            with pytest.raises(cucd.CucdError):
+                eng.set_rmd_path(2)                       # the round-1 "Hadamard only" experiment is no longer in the ABI
+            got = eng.frame(org, rec)["rmd_cost"]
+        assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8))
 
 
 # ---- packed cost tables (cucd_frame_out.rmd_cost_packed) carry the same numbers -------------------------------
@@ -279,7 +275,130 @@ def test_packed_cost_tables_equal_wide_tables(cucd, oracle, bd, W, H):
         got = cucd.unpack_costs(outs[k]["rmd_cost_packed"])
         assert np.array_equal(got, wide[k]["rmd_cost"])
     assert np.array_equal(cucd.unpack_costs(outs[0]["rmd_cost_packed"]), want)
-    assert (want == 0xFFFFFFFF).any()          # partial CTUs: the 0xFFFF marker is exercised
+    assert (want == 0xFFFFFFFF).any()          # partial CTUs: the 0xFFFF / 0x1FFF markers are exercised
+    with cucd.Engine(W, H, bit_depth=bd) as eng:                     # the C helpers a host encoder would use
+        assert np.array_equal(eng.unpack_costs_c(outs[0]["rmd_cost_packed"]), want)
+        t = np.ascontiguousarray(outs[0]["rmd_cost_packed"][1])
+        for pu, mode in [(0, 0), (4, 34), (20, 7), (21, 0), (84, 34), (85, 0), (86, 1), (200, 17), (340, 34)]:
+            assert eng.lib.cucd_packed_cost(t.ctypes.data, pu, mode) == int(want[1, pu, mode])
+
+
+# ---- ABI v4: byte planes in, byte feature planes out, pinned caller buffers, begin / end ------------------------
+def test_u8_planes_and_narrow_outputs_equal_the_int16_call(cucd):
+    W, H = 200, 136
+    org = textured_plane(W, H, 8, seed=21); rec = pseudo_recon(org, 8)
+    with cucd.Engine(W, H, max_pictures=2) as eng:
+        wide = eng.frames([org, rec], [rec, org])
+        outs = [eng.alloc_frame_out(True, packed=True, narrow=True) for _ in range(2)]
+        # HM-layout byte planes: stride W + 160, the plane starts 80 samples into its row
+        def hm(a):
+            buf = np.zeros((H, W + 160), np.uint8); buf[:, 80:80 + W] = a
+            return buf[:, 80:80 + W]
+        eng.frames([hm(org), hm(rec)], [hm(rec), hm(org)], outs)
+        for k in range(2):
+            assert np.array_equal(cucd.unpack_costs(outs[k]["rmd_cost_packed"]), wide[k]["rmd_cost"])
+            assert np.array_equal(outs[k]["obf_u8"].astype(np.int16), wide[k]["obf"])
+            assert np.array_equal(outs[k]["outlier_u8"].astype(np.int16), wide[k]["outlier"])
+            assert np.array_equal(outs[k]["num_obf3"], wide[k]["num_obf3"]) and np.array_equal(outs[k]["yc"], wide[k]["yc"])
+    with cucd.Engine(W, H, bit_depth=10) as eng10:
+        with pytest.raises(cucd.CucdError):
+            eng10.frames([org.astype(np.uint8)], [rec.astype(np.uint8)])      # byte planes need an 8-bit handle
+
+
+def test_outlier_plane_fits_a_byte_at_the_extremes(cucd, oracle):
+    """|AC coefficient| / 100 <= 163 (include/cucudecide.h): blocks that maximise single AC coefficients"""
+    from test_capi_load import _extreme_outlier_plane
+    for bd in (8, 10):
+        org = _extreme_outlier_plane(bd, 3)
+        obf, outl, _ = oracle_outlier_frame(oracle, org, bd)
+        assert 160 <= outl.max() <= 163
+        with cucd.Engine(org.shape[1], org.shape[0], bit_depth=bd) as eng:
+            out = eng.alloc_frame_out(False, narrow=True)
+            eng.frame(org, None, out=out)
+        assert np.array_equal(out["outlier_u8"].astype(np.int16), outl) and np.array_equal(out["obf_u8"].astype(np.int16), obf)
+
+
+def test_pinned_and_auto_pinned_caller_buffers(cucd):
+    W, H = 416, 240
+    org = textured_plane(W, H, 8, seed=31); rec = pseudo_recon(org, 8)
+    with cucd.Engine(W, H) as eng:
+        want = eng.frame(org, rec)
+    def hm(a):
+        buf = np.zeros((H + 160, W + 160), np.int16); buf[80:80 + H, 80:80 + W] = a
+        return buf, buf[80:80 + H, 80:80 + W]
+    bo, vo = hm(org); br, vr = hm(rec)
+    with cucd.Engine(W, H) as eng:
+        eng.pin_host_buffer(bo); eng.pin_host_buffer(br)
+        eng.pin_host_buffer(bo)                                # pinning twice is fine
+        got = eng.frame(vo, vr)
+        assert np.array_equal(got["rmd_cost"], want["rmd_cost"]) and np.array_equal(got["obf"], want["obf"])
+        eng.unpin_host_buffer(bo)
+        with pytest.raises(cucd.CucdError):
+            eng.unpin_host_buffer(bo)
+        got = eng.frame(vo, vr)                                # pageable again
+        assert np.array_equal(got["rmd_cost"], want["rmd_cost"])
+    with cucd.Engine(W, H, auto_pin_host=1) as eng:
+        for _ in range(2):
+            got = eng.frame(vo, vr)
+            assert np.array_equal(got["rmd_cost"], want["rmd_cost"]) and np.array_equal(got["outlier"], want["outlier"])
+        log2s, o, b = [3] * 4000, np.tile(org[:8, :8].ravel(), 4000), np.tile(rec[0, :33], 4000)      # > 64 KB arrays: registered on first sight
+        a1 = eng.intra_rmd_batch(log2s, o, b)
+        a2 = eng.intra_rmd_batch(log2s, o, b)
+        assert np.array_equal(a1, a2) and (a1 == a1[0]).all()
+
+
+def test_dev_frames_begin_end_pipelined(cucd):
+    import torch
+    W, H, P = 200, 136, 2
+    dev = torch.device("cuda", 0)
+    pitch = (W + 63) // 64 * 64
+    batches = []
+    with cucd.Engine(W, H, max_pictures=P) as eng:
+        for b in range(3):
+            orgs = [textured_plane(W, H, 8, seed=40 + 2 * b + p) for p in range(P)]
+            recs = [pseudo_recon(o, 8) for o in orgs]
+            d_org = torch.zeros((P, H, pitch), dtype=torch.int16, device=dev); d_rec = torch.zeros_like(d_org)
+            for p in range(P):
+                d_org[p, :, :W] = torch.from_numpy(orgs[p]).to(dev); d_rec[p, :, :W] = torch.from_numpy(recs[p]).to(dev)
+            d_cost = torch.zeros((P, eng.ctus_per_pic, 341, 35), dtype=torch.int32, device=dev)
+            d_obf = torch.zeros((P, H // 4, W // 4), dtype=torch.int16, device=dev)
+            d_outl = torch.zeros((P, H, W), dtype=torch.int16, device=dev)
+            yc = np.zeros((P, 16))
+            batches.append((orgs, recs, d_org, d_rec, d_cost, d_obf, d_outl, yc))
+        st = torch.cuda.current_stream().cuda_stream
+        def begin(b):
+            _, _, d_org, d_rec, d_cost, d_obf, d_outl, yc = batches[b]
+            eng.dev_frames(st, P, d_org.data_ptr(), H * pitch, pitch, d_rec.data_ptr(), H * pitch, pitch,
+                           {"obf": d_obf.data_ptr(), "outlier": d_outl.data_ptr(), "rmd_cost": d_cost.data_ptr()}, yc_host=yc, begin_only=True)
+        begin(0); begin(1)
+        with pytest.raises(cucd.CucdError):
+            begin(2)                                          # at most two batches in flight
+        eng.dev_frames_end(); begin(2); eng.dev_frames_end(); eng.dev_frames_end()
+        with pytest.raises(cucd.CucdError):
+            eng.dev_frames_end()
+        torch.cuda.synchronize()
+        for orgs, recs, _, _, d_cost, d_obf, d_outl, yc in batches:
+            want = eng.frames(orgs, recs)
+            for p in range(P):
+                assert np.array_equal(d_cost[p].cpu().numpy().view(np.uint32), want[p]["rmd_cost"])
+                assert np.array_equal(d_obf[p].cpu().numpy(), want[p]["obf"]) and np.array_equal(d_outl[p].cpu().numpy(), want[p]["outlier"])
+                assert np.array_equal(yc[p], want[p]["yc"])
+
+
+def test_misaligned_device_planes_are_rejected_not_faulted(cucd):
+    import torch
+    W, H = 128, 64
+    dev = torch.device("cuda", 0)
+    buf = torch.zeros(4 * H * (W + 64) + 64, dtype=torch.int16, device=dev)
+    cost = torch.zeros((2, 341, 35), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    with cucd.Engine(W, H) as eng:
+        base = buf.data_ptr()
+        for rec_ptr, rec_stride in [(base + 2, W), (base, W + 4), (base, W - 8)]:          # 2-byte offset, stride not multiple of 8, stride < width
+            with pytest.raises(cucd.CucdError):
+                eng.dev_rmd_frames(st, 1, base, H * W, W, rec_ptr, H * rec_stride, rec_stride, cost.data_ptr())
+        eng.dev_rmd_frames(st, 1, base, H * W, W, base, H * W, W, cost.data_ptr())
+        torch.cuda.synchronize()
 
 
 # ---- S2 batches: the integer-ALU kernels stay bit-exact for 8-bit content too (the default 8-bit path is tcgen05) ----
