@@ -20,10 +20,13 @@ static_assert(kPackedCtuBytes == CUCD_PACKED_CTU_BYTES && kPackedU16Off == CUCD_
 namespace cucd {
 std::string g_createError;
 
+// Registers EXACTLY [ptr, ptr + bytes): rounding the range out to pages would make the first / last bytes of neighbouring heap
+// blocks part of a registration, and a later transfer of such a neighbour - a partially registered range - fails with
+// cudaErrorInvalidValue.  A request that overlaps ranges this handle registered earlier (a reference plane with its margins
+// after the bare plane, say) replaces them by the union.
 bool pin_host_range(cucd_handle* h, const void* ptr, size_t bytes) {
   if (!ptr || !bytes) return false;
-  const uintptr_t page = 4096;
-  uintptr_t lo = (uintptr_t)ptr & ~(page - 1), hi = ((uintptr_t)ptr + bytes + page - 1) & ~(page - 1);
+  uintptr_t lo = (uintptr_t)ptr, hi = lo + bytes;
   for (const auto& r : h->pins) if (r.first <= lo && hi <= r.second) return true;
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) {   // pinned by the caller (cudaMallocHost / its own registration)
@@ -31,16 +34,19 @@ bool pin_host_range(cucd_handle* h, const void* ptr, size_t bytes) {
     if (cudaPointerGetAttributes(&at2, (const char*)ptr + bytes - 1) == cudaSuccess && at2.type == cudaMemoryTypeHost) return true;
   }
   cudaGetLastError();
-  // neighbouring heap blocks may share their first / last page with a range this handle registered earlier: those pages are
-  // already locked, so registering the remainder locks the whole range
-  for (int attempt = 0; attempt < 4; attempt++) {
-    const uintptr_t l = lo + ((attempt & 1) ? page : 0), u = hi - ((attempt & 2) ? page : 0);
-    if (u <= l) break;
-    const cudaError_t e = cudaHostRegister((void*)l, u - l, cudaHostRegisterDefault);
-    if (e == cudaSuccess) { h->pins.emplace_back(l, u); return true; }
-    cudaGetLastError();
-    if (e != cudaErrorHostMemoryAlreadyRegistered) break;
+  bool overlapped = false;
+  for (size_t i = 0; i < h->pins.size();) {
+    if (h->pins[i].first < hi && lo < h->pins[i].second) {
+      if (!overlapped) cudaDeviceSynchronize();          // nothing may still be reading through the old registration
+      overlapped = true;
+      lo = std::min(lo, h->pins[i].first); hi = std::max(hi, h->pins[i].second);
+      cudaHostUnregister((void*)h->pins[i].first);
+      h->pins.erase(h->pins.begin() + i);
+    } else i++;
   }
+  const cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterDefault);
+  if (e == cudaSuccess) { h->pins.emplace_back(lo, hi); return true; }
+  cudaGetLastError();
   return false;
 }
 }  // namespace cucd

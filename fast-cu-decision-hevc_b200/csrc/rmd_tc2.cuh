@@ -18,9 +18,9 @@
 // one MMA share a phase class by construction of the row map.  For N = 4 a row is an 8x8 REGION of four
 // PUs, K = 64 (one 16-byte record per PU: main[0..8], side[1..5], 1) and B is block diagonal with the
 // negative-angle projection folded into the weights.
-// MMA 2 (Hadamard).  A = the 64 predicted bytes of the row, B = +(H8 (x) H8) (or block-diagonal H4 (x) H4);
-// the epilogue sums |D - Ho| against the row's transformed SOURCE tile Ho, which every thread keeps in 64
-// registers for the whole CTA.
+// MMA 2 (Hadamard of the residual).  D = source x -(H8 (x) H8) + prediction x +(H8 (x) H8) (block-diagonal H4 (x) H4 for
+// N = 4): the row's source tile sits in shared memory as a static A operand for the whole pass, the 64 predicted bytes
+// come from TMEM, and the second product accumulates onto the first.  The epilogue only sums |D|.
 #pragma once
 #include "rmd_chunk.cuh"
 
@@ -154,10 +154,11 @@ struct Cfg {
   static constexpr int ACC_ELEM = LOG2N == 2 ? 2 : 4;            // costs are staged in shared memory: uint32, N = 4: uint16 (<= 8160 for 8-bit content)
   static constexpr bool EDGE = LOG2N <= 4;                       // luma edge filters (DC, pure vertical / horizontal)
   // byte offsets inside dynamic shared memory
-  static constexpr int HAD_OFF = 0;
-  static constexpr int B1_OFF = HAD_OFF + 4096;                  // [group][buffer]
+  static constexpr int HAD_OFF = 0;                              // +H at 0, -H at 4096 (B operands of MMA 2)
+  static constexpr int B1_OFF = HAD_OFF + 8192;                  // [group][buffer]
   static constexpr int A1_OFF = B1_OFF + kGroups * 2 * B1_BYTES; // [group]: two 4 KB window operands (N >= 8) or one static 8 KB record operand (N = 4)
-  static constexpr int BAR_OFF = A1_OFF + kGroups * 8192;
+  static constexpr int AORG_OFF = A1_OFF + kGroups * 8192;       // [group]: the rows' SOURCE tiles as a 128 x 64-byte operand: MMA 2 accumulates -H x source
+  static constexpr int BAR_OFF = AORG_OFF + kGroups * 8192;
   static constexpr int VALID_OFF = BAR_OFF + 128;
   static constexpr int DC_OFF = VALID_OFF + CTUS * 256;          // int32 [ctu][64]: sum of the N above + N left samples (N >= 8)
   static constexpr int STORE_OFF = DC_OFF + CTUS * 64 * 4;
@@ -572,26 +573,28 @@ CUCD_HD void build_filtered(int tid, int ctu, int strongEnabled, unsigned char* 
 }
 
 // projected samples of a negative-angle round, by the 128 threads of row group `grp` for its private arrays:
-// store[main][-j] = store[side][(128 + j*inv) >> 8], j = 1 .. nNeg.  128 / (2 * SLOTS) threads share one (slot, orientation) pair.
+// store[main][-j] = store[side][(128 + j*inv) >> 8] (TComPrediction.cpp:300-322).  128 / (2 * SLOTS) threads share one
+// (slot, orientation) pair; a thread produces N / TPP consecutive entries, four at a time as one aligned 32-bit store.
+// ALL N entries of the array are written: those beyond the mode's own -((N * angle) >> 5) - 1 are never consumed by a
+// window; their side indices are clamped into the side array.
 template <int LOG2N>
-CUCD_HD void build_ext_group(int rowTid, int grp, int angle, int inv, int filt, unsigned char* store) {
+CUCD_HD void build_ext_group(int rowTid, int grp, int inv, int filt, unsigned char* store) {
   typedef Cfg<LOG2N> C;
   constexpr int TPP = LOG2N == 2 ? 1 : 128 / (2 * C::SLOTS);   // (N = 4 has no projected arrays; never called)
-  const int nNeg = -((C::N * angle) >> 5) - 1;
-  const int pair = rowTid / TPP, slot = pair >> 1, o = pair & 1;
-  const int mainOff = arr_k0_off<LOG2N>(grp, slot, o, filt), sideOff = arr_k0_off<LOG2N>(grp, slot, o ^ 1, filt);
-  // at most N / TPP <= 8 entries per thread; loads first, then stores (independent chains)
-  constexpr int MAXE = C::N / TPP > 8 ? 8 : C::N / TPP;
-  unsigned char v[MAXE];
+  constexpr int EPT = C::N / TPP;                              // 8 entries per thread (N = 64: 4)
+  static_assert(LOG2N == 2 || EPT % 4 == 0, "entries are produced four at a time");
+  const int pair = rowTid / TPP, sub = rowTid % TPP, slot = pair >> 1, o = pair & 1;
+  const int mainOff = arr_k0_off<LOG2N>(grp, slot, o, filt);
+  const unsigned char* side = store + arr_k0_off<LOG2N>(grp, slot, o ^ 1, filt);
+  int t = 128 + (sub * EPT + 1) * inv;                         // 128 + j * inv of the thread's first entry j
+  uint32_t* dst = reinterpret_cast<uint32_t*>(store + mainOff - sub * EPT - 4);   // entries j .. j+3 live at bytes 3 .. 0 of this word
 #pragma unroll
-  for (int e = 0; e < MAXE; e++) {
-    const int j = 1 + (rowTid % TPP) + e * TPP;
-    v[e] = j <= nNeg ? store[sideOff + ((128 + j * inv) >> 8)] : 0;
-  }
-#pragma unroll
-  for (int e = 0; e < MAXE; e++) {
-    const int j = 1 + (rowTid % TPP) + e * TPP;
-    if (j <= nNeg) store[mainOff - j] = v[e];
+  for (int q = 0; q < EPT / 4; q++) {
+    constexpr int kMax = 2 * C::N;
+    const uint32_t b3 = side[imin32(t >> 8, kMax)], b2 = side[imin32((t + inv) >> 8, kMax)], b1 = side[imin32((t + 2 * inv) >> 8, kMax)],
+                   b0 = side[imin32((t + 3 * inv) >> 8, kMax)];
+    dst[-q] = bperm(bperm(b0, b1, 0x3340), bperm(b2, b3, 0x3340), 0x5410);
+    t += 4 * inv;
   }
 }
 

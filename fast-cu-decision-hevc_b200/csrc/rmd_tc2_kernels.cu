@@ -6,8 +6,8 @@
 //     gather 32-byte reference window -> shared memory (A1) [N = 4: static 64-byte record row]
 //     MMA 1: D1 = A1 x weights(angle, phase)              prediction * 256 in byte 1 of every accumulator
 //     epilogue 1: tcgen05.ld.pack::16b + 16 PRMT -> 64 predicted bytes -> TMEM (A2)
-//     MMA 2: D2 = A2 x (H8 (x) H8)
-//     epilogue 2: sum |D2 - Ho| against the row's transformed source tile (64 registers), HM rounding
+//     MMA 2: D2 = source tile (shared memory, static) x -(H8 (x) H8) + A2 x (H8 (x) H8)      Hadamard of the residual
+//     epilogue 2: sum |D2|, HM rounding
 // See rmd_tc2.cuh for the arithmetic and the reference citations; planar and DC are predicted on the ALU.
 // Replaces, per PU, the reference loop TEncSearch.cpp:2327-2361.
 #include <cuda_runtime.h>
@@ -86,6 +86,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
       : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;\n" :: "r"(grp + 1) : "memory"); }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- prologue: reference arrays of the CTA's CTUs (rmd_tc2.cuh phases 1-3) --------------------------------
 template <int LOG2N, bool FRAME>
@@ -163,6 +169,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   unsigned char* store = smem + C::STORE_OFF;
   unsigned char* sB1 = smem + C::B1_OFF + grp * 2 * C::B1_BYTES;
   unsigned char* sA1 = smem + C::A1_OFF + grp * 8192;
+  unsigned char* sAorg = smem + C::AORG_OFF + grp * 8192;
   uint64_t* mbar1 = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + grp;
   uint64_t* mbar2 = mbar1 + kGroups;
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
@@ -222,24 +229,38 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   }
 
   const uint32_t laneOff = (uint32_t)((warp & 3) * 32) << 16;
+  const int rowChunk = (rowTid >> 3) * 128 + (rowTid & 7) * 16;      // the row's 16-byte slot inside a 128-row operand chunk
   const uint32_t tD1 = tmemBase + grp * 128, tA2 = tD1, tD2 = tD1 + 64;
+  // What the MMA-issuing lane needs, derived from warp-uniform values only (a shuffle result is uniform to the compiler), so that
+  // the tcgen05 operands live in uniform registers and the elected lane issues without a per-instruction uniformisation loop.
+  const int warpU = __shfl_sync(0xffffffffu, warp, 0), grpU = warpU >> 2;
+  const bool issuer = (warpU & 3) == 0;
+  const uint32_t tmemU = __shfl_sync(0xffffffffu, tmemBase, 0);
+  const uint32_t uD1 = tmemU + grpU * 128, uA2 = uD1, uD2 = uD1 + 64;
+  uint64_t* ubar1 = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + grpU;
+  uint64_t* ubar2 = ubar1 + kGroups;
   const uint32_t idescPred = make_idesc_i8x(128, 64, 0, 0), idescHad = make_idesc_i8x(128, 64, 0, 1);
-  const uint64_t dHad = make_desc(smem_u32(smem + C::HAD_OFF), 1024, 128);
-  const uint64_t dB1 = make_desc(smem_u32(sB1), 1024, 128), dA1 = make_desc(smem_u32(sA1), 2048, 128);
+  const uint64_t dHad = make_desc(smem_u32(smem + C::HAD_OFF), 1024, 128), dHadNeg = make_desc(smem_u32(smem + C::HAD_OFF + 4096), 1024, 128);
+  const uint64_t dAorg = make_desc(smem_u32(smem + C::AORG_OFF + grpU * 8192), 2048, 128);
+  const uint64_t dB1 = make_desc(smem_u32(smem + C::B1_OFF + grpU * 2 * C::B1_BYTES), 1024, 128), dA1 = make_desc(smem_u32(smem + C::A1_OFF + grpU * 8192), 2048, 128);
   constexpr uint64_t kStepB = (2 * 1024) >> 4;      // descriptor advance of one K = 32 step: two 16-byte chunks of 64 rows
   constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
-  uint32_t ho[64];
 
-  // A2 (already stored to TMEM by every thread) x H -> D2
+  // source x -H + A2 (already stored to TMEM by every thread) x H -> D2
   auto issue_mma2 = [&]() {
     tmem_st_wait();
     tc_fence_before();
     group_bar(grp);
-    if (rowTid == 0) {
-      tc_fence_after();
-      mma_i8_ts(tD2, tA2, dHad, idescHad, 0u);
-      mma_i8_ts(tD2, tA2 + 8, dHad + kStepB, idescHad, 1u);
-      mma_commit(mbar2);
+    if (issuer) {
+      if (elect_one()) {
+        tc_fence_after();
+        mma_i8(uD2, dAorg, dHadNeg, idescHad, 0u);
+        mma_i8(uD2, dAorg + kStepA, dHadNeg + kStepB, idescHad, 1u);
+        mma_i8_ts(uD2, uA2, dHad, idescHad, 1u);
+        mma_i8_ts(uD2, uA2 + 8, dHad + kStepB, idescHad, 1u);
+        mma_commit(ubar2);
+      }
+      __syncwarp();
     }
   };
   auto wait_mma2 = [&]() { mbar_wait(mbar2, ph2); ph2 ^= 1u; tc_fence_after(); };
@@ -248,16 +269,19 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     fence_async_smem();
     tc_fence_before();
     group_bar(grp);
-    if (rowTid == 0) {
-      tc_fence_after();
-      const uint64_t dB = dB1 + (uint64_t)((buf * C::B1_BYTES) >> 4);
-      if (LOG2N == 2) {
-        mma_i8(tD1, dA1, dB, idescPred, 0u);
-        mma_i8(tD1, dA1 + kStepA, dB + kStepB, idescPred, 1u);
-      } else {
-        mma_i8(tD1, dA1 + (uint64_t)((buf * 4096) >> 4), dB, idescPred, 0u);
+    if (issuer) {
+      if (elect_one()) {
+        tc_fence_after();
+        const uint64_t dB = dB1 + (uint64_t)((buf * C::B1_BYTES) >> 4);
+        if (LOG2N == 2) {
+          mma_i8(uD1, dA1, dB, idescPred, 0u);
+          mma_i8(uD1, dA1 + kStepA, dB + kStepB, idescPred, 1u);
+        } else {
+          mma_i8(uD1, dA1 + (uint64_t)((buf * 4096) >> 4), dB, idescPred, 0u);
+        }
+        mma_commit(ubar1);
       }
-      mma_commit(mbar1);
+      __syncwarp();
     }
   };
   auto wait_mma1 = [&]() { mbar_wait(mbar1, ph1); ph1 ^= 1u; tc_fence_after(); };
@@ -274,7 +298,6 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     }
   };
   // operands of round `am` into buffer `buf`: weights from the prefetch registers, the row's reference window
-  const int rowChunk = (rowTid >> 3) * 128 + (rowTid & 7) * 16;
   auto stage = [&](int am, int angle, int buf) {
     uint4* b = reinterpret_cast<uint4*>(sB1 + buf * C::B1_BYTES);
     b[rowTid] = nb0;
@@ -300,8 +323,8 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
       uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        s0 = sad_acc(v[k], ho[h * 32 + k], s0);           s1 = sad_acc(v[8 + k], ho[h * 32 + 8 + k], s1);
-        s2 = sad_acc(v[16 + k], ho[h * 32 + 16 + k], s2); s3 = sad_acc(v[24 + k], ho[h * 32 + 24 + k], s3);
+        s0 = sad_acc(v[k], 0u, s0);      s1 = sad_acc(v[8 + k], 0u, s1);
+        s2 = sad_acc(v[16 + k], 0u, s2); s3 = sad_acc(v[24 + k], 0u, s3);
       }
       q[2 * h] = s0 + s1; q[2 * h + 1] = s2 + s3;
     }
@@ -321,9 +344,12 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     }
   };
 
-  // ---- Ho = H x source tile ------------------------------------------------------------------------------
-  tmem_st16(tA2 + laneOff, p);
-  issue_mma2();
+  // ---- the row's source tile becomes the static A operand of the -H product -------------------------------------
+  {
+    uint4* d = reinterpret_cast<uint4*>(sAorg + rowChunk);
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i * 128] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+  }
   prefetch_b1(8, 32);
   const unsigned char* rec4 = store + rec_off(r.ctu, r.o, 4 * r.pu);
   if (LOG2N == 2) {                                 // N = 4: the record row is the A operand of every mode (4 chunks)
@@ -331,7 +357,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i * 128] = reinterpret_cast<const uint4*>(rec4)[i];
   }
-  // round 0 prediction while the MMA runs: planar (true orientation rows) / DC (transposed rows) on the ALU
+  // round 0 prediction: planar (true orientation rows) / DC (transposed rows) on the ALU
   const unsigned char* unfMain = store + arr_k0_off<LOG2N>(grp, slot, r.o, 0);
   const unsigned char* unfSide = store + arr_k0_off<LOG2N>(grp, slot, r.o ^ 1, 0);
   if (ok) {
@@ -343,11 +369,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
       dc_tile((reinterpret_cast<const int*>(smem + C::DC_OFF)[r.ctu * 64 + r.pu] + N) >> (LOG2N + 1), C::EDGE, unfMain, unfSide, r.u0, r.v0, p);
     }
   }
-  wait_mma2();
-#pragma unroll
-  for (int c = 0; c < 4; c++) tmem_ld16(tD2 + laneOff + c * 16, ho + c * 16);
-  tmem_ld_wait();
-  tc_fence_before();
+  fence_async_smem();                               // the source operand is read by the tensor core (async proxy)
 
   // ---- round 0 -------------------------------------------------------------------------------------------------
   tmem_st16(tA2 + laneOff, p);
@@ -384,7 +406,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     tmem_st16(tA2 + laneOff, p);
     TC2_FINE(2);
     if (LOG2N != 2 && am > -8 && angleNext < 0)     // the gathers of round am are done (barrier of its MMA 1)
-      build_ext_group<LOG2N>(rowTid, grp, angleNext, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
+      build_ext_group<LOG2N>(rowTid, grp, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
     TC2_FINE(3);
     issue_mma2();
     TC2_FINE(4);
@@ -418,7 +440,8 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   }
   TC2_STAMP(0);
   if (warp == 0) tmem_alloc(tmemSlot, 256);
-  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid];
+  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid];              // +H
+  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid + 256] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid + 256];  // -H
   if (LOG2N >= 4) for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) acc[i] = 0;   // accumulated with atomics
   reinterpret_cast<int*>(smem + C::DC_OFF)[tid] = 0;          // CTUS * 64 <= 256 sums
   __syncthreads();

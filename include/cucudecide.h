@@ -76,8 +76,9 @@ const char* cucd_last_error(const cucd_handle* h);   /* h may be NULL: error of 
 long long cucd_launch_count(const cucd_handle* h);
 /* Page-lock a caller buffer for the lifetime of the handle (or until cucd_unpin_host_buffer): HM allocates its picture planes
  * once (TComPicYuv::create, xMalloc, TComPicYuv.cpp:97) and pageable memory costs an extra staging copy inside the driver on
- * every transfer.  `ptr` may point anywhere inside the allocation; [ptr, ptr + bytes) is registered (rounded out to pages).
- * Must be unpinned (or the handle destroyed) before the memory is freed. */
+ * every transfer.  Exactly [ptr, ptr + bytes) is registered - give the whole allocation (a plane with its margins), so that
+ * every later transfer lies inside it: CUDA rejects transfers of partially registered ranges.  A range that overlaps an
+ * earlier one replaces it by the union.  Must be unpinned (or the handle destroyed) before the memory is freed. */
 int cucd_pin_host_buffer(cucd_handle* h, const void* ptr, size_t bytes);
 int cucd_unpin_host_buffer(cucd_handle* h, const void* ptr);
 

@@ -132,7 +132,7 @@ int emul_rmd_frame(int bitDepth, int strong, const int16_t* org, int orgStride, 
                    int ctuBegin, int ctuEnd, uint32_t* outAllCtus) {
   FrameSource fs;
   fs.org = org; fs.rec = rec; fs.orgPicStride = 0; fs.recPicStride = 0; fs.orgStride = orgStride; fs.recStride = recStride;
-  fs.W = W; fs.H = H; fs.ctusPerRow = (W + 63) / 64; fs.ctusPerPic = fs.ctusPerRow * ((H + 63) / 64); fs.out = outAllCtus;
+  fs.W = W; fs.H = H; fs.ctusPerRow = (W + 63) / 64; fs.ctusPerPic = fs.ctusPerRow * ((H + 63) / 64); fs.out = outAllCtus; fs.outPacked = nullptr;
   BatchSource bs = {};
   for (int c = ctuBegin; c < ctuEnd; c++) {
     emul_chunk<6, true>(c, fs, bs, bitDepth, strong);

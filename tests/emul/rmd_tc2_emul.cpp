@@ -99,7 +99,7 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit, const 
   for (int pass = 0; pass < C::PASSES; pass++) {
     // ---- tc2_pass ----
     std::vector<Row> rows(kThreads); std::vector<char> ok(kThreads);
-    std::vector<uint32_t> P(kThreads * 16), A1(kThreads * 16, 0xA5A5A5A5u), D(kThreads * 64), HO(kThreads * 64);
+    std::vector<uint32_t> P(kThreads * 16), A1(kThreads * 16, 0xA5A5A5A5u), D(kThreads * 64);
     for (int tid = 0; tid < kThreads; tid++) {
       const Row r = rows[tid] = row_map<LOG2N>(tid, pass);
       const int cg = unit * C::CTUS + r.ctu;
@@ -130,7 +130,15 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit, const 
         if (r.o) tile_transpose_bytes(raw, p, log2n != 2); else std::memcpy(p, raw, sizeof(raw));
       } else std::memset(p, 0, 64);
     }
-    auto hadamard = [&]() { for (int grp = 0; grp < kGroups; grp++) mma(&P[grp * 128 * 16], 16, 64, had, true, &D[grp * 128 * 64]); };
+    // MMA 2: D = source x -H (the static shared-memory operand) + prediction x +H, accumulated in TMEM
+    std::vector<uint32_t> ORG = P, DN(kThreads * 64);
+    auto hadamard = [&]() {
+      for (int grp = 0; grp < kGroups; grp++) {
+        mma(&ORG[grp * 128 * 16], 16, 64, had + 4096, true, &DN[grp * 128 * 64]);
+        mma(&P[grp * 128 * 16], 16, 64, had, true, &D[grp * 128 * 64]);
+      }
+      for (size_t i = 0; i < D.size(); i++) D[i] += DN[i];
+    };
     auto cost_out = [&](int am, bool angular) {
       // warps in order; the shuffle reduction over SEG lanes and the shared-memory atomics become a plain sum
       for (int tid = 0; tid < kThreads; tid++) {
@@ -138,7 +146,7 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit, const 
         const int mode = angular ? (r.o ? 10 - am : 26 + am) : (r.o ? 1 : 0);
         const bool has = !(angular && r.o && am == -8);
         uint32_t q[4];
-        for (int c = 0; c < 4; c++) { uint32_t s = 0; for (int k = 0; k < 16; k++) s = sad_acc(D[tid * 64 + c * 16 + k], HO[tid * 64 + c * 16 + k], s); q[c] = s; }
+        for (int c = 0; c < 4; c++) { uint32_t s = 0; for (int k = 0; k < 16; k++) s = sad_acc(D[tid * 64 + c * 16 + k], 0u, s); q[c] = s; }
         const int cg = unit * C::CTUS + r.ctu;
         if (log2n == 2) {
           if (ok[tid] && has) for (int c = 0; c < 4; c++) reinterpret_cast<uint16_t*>(acc)[(r.ctu * C::PUS + 4 * r.pu + c) * kNumModes + mode] = (uint16_t)((q[c] + 1u) >> 1);
@@ -149,8 +157,6 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit, const 
         }
       }
     };
-    hadamard();
-    HO = D;
     if (log2n == 2)
       for (int tid = 0; tid < kThreads; tid++) std::memcpy(&A1[tid * 16], store + rec_off(rows[tid].ctu, rows[tid].o, 4 * rows[tid].pu), 64);
     // round 0
@@ -170,7 +176,7 @@ void emul_cta(const FrameSource& fs, int strong, int totalCtus, int unit, const 
     for (int am = 8; am >= -8; --am) {
       const int angle = angle_of_am(am), ai = am + 8;
       const int filt = mode_uses_filtered<LOG2N>(26 + am) ? 1 : 0;
-      if (log2n != 2 && angle < 0) for (int tid = 0; tid < kThreads; tid++) build_ext_group<LOG2N>(tid & 127, tid >> 7, angle, inv_angle_of_am(am), filt, store);
+      if (log2n != 2 && angle < 0) for (int tid = 0; tid < kThreads; tid++) build_ext_group<LOG2N>(tid & 127, tid >> 7, inv_angle_of_am(am), filt, store);
       for (int grp = 0; grp < kGroups; grp++) {
         const uint8_t* b1;
         if (log2n == 2) b1 = tb.n4.data() + ai * 4096;
@@ -231,7 +237,7 @@ extern "C" {
 int emul_rmd_frame_tc2(int strong, const int16_t* org, int orgStride, const int16_t* rec, int recStride, int W, int H, uint32_t* out) {
   FrameSource fs;
   fs.org = org; fs.rec = rec; fs.orgPicStride = 0; fs.recPicStride = 0; fs.orgStride = orgStride; fs.recStride = recStride;
-  fs.W = W; fs.H = H; fs.ctusPerRow = (W + 63) / 64; fs.ctusPerPic = fs.ctusPerRow * ((H + 63) / 64); fs.out = out;
+  fs.W = W; fs.H = H; fs.ctusPerRow = (W + 63) / 64; fs.ctusPerPic = fs.ctusPerRow * ((H + 63) / 64); fs.out = out; fs.outPacked = nullptr;
   const int total = fs.ctusPerPic, u2 = (total + 1) >> 1, u4 = (total + 3) >> 2;
   for (int u = 0; u < u4; u++) { emul_cta<6>(fs, strong, total, u); emul_cta<5>(fs, strong, total, u); }
   for (int u = 0; u < u2; u++) { emul_cta<4>(fs, strong, total, u); emul_cta<3>(fs, strong, total, u); emul_cta<2>(fs, strong, total, u); }
