@@ -83,7 +83,7 @@ def _feature_pass(lib, kind, org, bd):
         lib.oracle_outlier_frame(bd, vp(org), W, W, H, vp(obf), vp(outl), vp(yc))
 
 
-def cpu_path_sample(lib, kind, pics, bit_depth, threads, ctus_per_pic_limit=None):
+def cpu_path_sample(lib, kind, pics, bit_depth, threads, ctus_per_pic_limit=None, feature_rows=None):
     """One CPU step: every picture in `pics` [(org, rec), ...] through the RMD enumeration (CTUs spread over
     `threads` host threads inside the reference driver) and through the per-picture feature pass.  The
     reference's feature pass is single-threaded and not re-entrant, so pictures run concurrently in
@@ -107,7 +107,7 @@ def cpu_path_sample(lib, kind, pics, bit_depth, threads, ctus_per_pic_limit=None
                 devnull = os.open(os.devnull, os.O_WRONLY)
                 os.dup2(devnull, 1)        # the reference prints diagnostics from its TCM fit
                 for i in range(k, len(pics), nproc):
-                    _feature_pass(lib, kind, pics[i][0], bit_depth)
+                    _feature_pass(lib, kind, pics[i][0] if feature_rows is None else np.ascontiguousarray(pics[i][0][:feature_rows]), bit_depth)
             finally:
                 os._exit(0)
         kids.append(pid)
@@ -125,7 +125,63 @@ def cpu_path_sample(lib, kind, pics, bit_depth, threads, ctus_per_pic_limit=None
     return ctus / dt, dt, ctus
 
 
+def cpu_me_sample(lib, kind, cur, refs_padded, pus, bit_depth, threads):
+    """The inter part of one CPU step on `pus` [(x, y, size)]: per reference the whole +-64 SAD surface (the reference's own xGetSAD*
+    through hmref_sad_surface, or the oracle port) and the 49-point sub-pel Hadamard table (oracle port of TComInterpolationFilter +
+    xGetHADs - the reference has no separable entry point for it), PUs spread over `threads` host threads.  Returns seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+    so = os.path.join(ROOT, "oracle", "libcucd_oracle.so")
+    port = C.CDLL(so)
+    R, M = ME_RANGE, ME_MARGIN
+    H, W = cur.shape
+
+    def one(pu):
+        x, y, s = pu
+        blk = np.ascontiguousarray(cur[y:y + s, x:x + s])
+        out = np.empty((2 * R + 1) ** 2, np.uint32)
+        o49 = np.empty(49, np.uint32)
+        for rp in refs_padded:
+            stride = rp.shape[1]
+            base = C.c_void_p(rp.ctypes.data + 2 * ((y + M) * stride + x + M))
+            sub = 1 if s > 8 else 0
+            if kind == "reference":
+                lib.hmref_sad_surface(bit_depth, C.c_void_p(blk.ctypes.data), s, s, s, base, stride, -R, R, -R, R, sub, C.c_void_p(out.ctypes.data))
+            else:
+                port.oracle_sad_surface(bit_depth, C.c_void_p(blk.ctypes.data), s, s, s, base, stride, -R, R, -R, R, sub, C.c_void_p(out.ctypes.data))
+            port.oracle_subpel_surface(bit_depth, C.c_void_p(blk.ctypes.data), s, s, s, base, stride, 1, -1, 1, C.c_void_p(o49.ctypes.data))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        list(ex.map(one, pus))
+    return time.perf_counter() - t0
+
+
+def cpu_reference_run_inter(args, steps, warmup):
+    """Reference arm of the inter configurations on a bounded sample: the first four CTU rows of one picture through the intra path (as
+    the All-Intra arm; the feature pass on those 256 picture rows) and through the ME part; CTU/s = CTUs / (intra seconds + ME seconds)."""
+    lib, kind = load_cpu_checker()
+    threads = os.cpu_count() or 1
+    W, H, bd = args.width, args.height, args.bit_depth
+    n_ctus = 4 * ((W + 63) // 64)
+    cur = textured_plane(W, H, bd, 20261018, 1)
+    recs = [pseudo_recon(textured_plane(W, H, bd, 20261018, t), bd, t) for t in (0, 2)][:args.refs]
+    refs_padded = [np.ascontiguousarray(np.pad(r, ME_MARGIN, mode="edge")) for r in recs]
+    ctus_per_row = (W + 63) // 64
+    # PUs of the first n_ctus CTUs (raster order)
+    pus = [(x, y, s) for (x, y, s) in inter_pus(W, H) if (y // 64) * ctus_per_row + x // 64 < n_ctus]
+    vals, secs = [], 0.0
+    for i in range(warmup + steps):
+        _, dt_intra, _ = cpu_path_sample(lib, kind, [(cur, recs[0])], bd, threads, n_ctus, feature_rows=256)
+        dt_me = cpu_me_sample(lib, kind, cur, refs_padded, pus, bd, threads)
+        if i >= warmup:
+            vals.append(n_ctus / (dt_intra + dt_me)); secs += dt_intra + dt_me
+    desc = (f"{steps} steps x {n_ctus} CTUs (4 CTU rows) of one {W}x{H} picture: intra path + {len(pus)} PUs x {args.refs} reference(s) x {(2 * ME_RANGE + 1) ** 2} SAD candidates "
+            f"(reference xGetSAD*) + 49-point sub-pel Hadamard (oracle port), {secs:.1f} s on {threads} thread(s)")
+    return float(np.mean(vals)), {"value": float(np.mean(vals)), "unit": "CTU/s", "cores": threads, "kind": kind, "sample": desc}
+
+
 def cpu_reference_run(args, steps, warmup, target_step_s=2.0):
+    if args.refs:
+        return cpu_reference_run_inter(args, steps, warmup)
     """The reference's CPU implementation of the path on all host threads: returns (mean CTU/s, dict)."""
     lib, kind = load_cpu_checker()
     threads = (os.cpu_count() or 1) if kind == "reference" else 1
@@ -163,9 +219,47 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# BASELINE.json configs[1..4] as bench workloads (configs[0] is the reference's own 416x240 CPU run: a parity-test case)
+CONFIGS = {
+    "ai1080p8": dict(width=1920, height=1080, bit_depth=8, pics=16, refs=0, label="BASELINE configs[1]: 1920x1080 8-bit All-Intra Main"),
+    "ai2160p10": dict(width=3840, height=2160, bit_depth=10, pics=4, refs=0, label="BASELINE configs[2]: 3840x2160 10-bit All-Intra Main10"),
+    "ldp1080p": dict(width=1920, height=1080, bit_depth=8, pics=1, refs=1, label="BASELINE configs[3]: 1920x1080 low-delay P Main, integer-ME SAD on the GPU, search range 64"),
+    "ra1080p10": dict(width=1920, height=1080, bit_depth=10, pics=1, refs=2, label="BASELINE configs[4]: 1920x1080 Random Access GOP8 Main10 (one reference per list)"),
+}
+ME_RANGE = 64          # --SearchRange=64
+ME_MARGIN = 80         # TComPicYuv margin: CTU + 16 (TComPicYuv.cpp:83-84)
+
+
+def inter_pus(W, H):
+    """the square 2Nx2N PUs of every CU at depths 0..3 that lies inside the picture (85 per whole CTU): (x, y, size)"""
+    pus = []
+    for size in (64, 32, 16, 8):
+        for y in range(0, H - size + 1, size):
+            for x in range(0, W - size + 1, size):
+                pus.append((x, y, size))
+    return pus
+
+
+def me_algo_bytes(pus):
+    """per PU cur w*h*2 + ref (w+2R)(h+2R)*2 + out (2R+1)^2*4"""
+    R = ME_RANGE
+    return sum(s * s * 2 + (s + 2 * R) * (s + 2 * R) * 2 + (2 * R + 1) ** 2 * 4 for _, _, s in pus)
+
+
 def workload_config(args):
-    which = {(1920, 1080, 8): "BASELINE configs[1]", (3840, 2160, 10): "BASELINE configs[2]"}.get((args.width, args.height, args.bit_depth), "not a BASELINE configuration")
-    return {"workload": f"{args.width}x{args.height} {args.bit_depth}-bit All-Intra ({which}): full intra RMD enumeration "
+    which = args.label or "not a BASELINE configuration"
+    if args.refs:
+        npu = len(inter_pus(args.width, args.height))
+        return {"workload": f"{args.width}x{args.height} {args.bit_depth}-bit ({which}): per picture the intra path (feature pass + RMD enumeration 341 PUs x 35 modes per CTU) "
+                            f"plus, per reference picture ({args.refs}), the integer-ME SAD surface of every square PU of depths 0-3 ({npu} PUs, window +-{ME_RANGE} = "
+                            f"{(2 * ME_RANGE + 1) ** 2} candidates each, FEN row sub-sampling) and its 49-point quarter-pel Hadamard refinement; {args.pics} picture(s) per step per GPU",
+                "pictures_per_step_per_gpu": args.pics, "ctus_per_picture": ((args.width + 63) // 64) * ((args.height + 63) // 64), "reference_pictures": args.refs,
+                "me_pus_per_picture": npu,
+                "l2_policy": f"inputs larger than L2: a step writes {npu * (2 * ME_RANGE + 1) ** 2 * 4 * args.refs / 1e9:.2f} GB of SAD surfaces",
+                "parallelism": f"pictures sharded over {args.gpus} GPU(s), no collective"}
+    enum = ("FORK-AWARE (Testing-picture) enumeration - NOT the headline workload: Num_OBF first, then only the PUs TEncCu::xCompressCU still reaches with Skip2Nx2N on at "
+            "every depth and TerminateCU on at depths 0-2; pruned PUs carry CUCD_COST_PRUNED" if getattr(args, "fork_aware", False) else "full intra RMD enumeration")
+    return {"workload": f"{args.width}x{args.height} {args.bit_depth}-bit All-Intra ({which}): {enum} "
                         f"341 PUs x 35 modes per CTU + OBF/outlier feature pass, {args.pics} pictures per step per GPU",
             "pictures_per_step_per_gpu": args.pics, "ctus_per_picture": ((args.width + 63) // 64) * ((args.height + 63) // 64),
             "l2_policy": "inputs larger than L2: one step reads 2 planes x pictures and writes the cost tables (> 126 MB) before any reuse",
@@ -262,6 +356,9 @@ def run_ours(args, rank, world, local_rank):
     eng = cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P, host_threads=host_threads)
     nctu = eng.ctus_per_pic
     pitch = (W + 63) // 64 * 64
+    FORK_SW = ((1, 1, 1, 1), (1, 1, 1, 0))      # tests/golden/fork_ai8.npz: what SetDecisionSwitch left after the verify picture of a real encode
+    if args.fork_aware:
+        eng.set_decision_switches(1, *FORK_SW)
     # each rank works on its own pictures (different seeds): weak scaling
     orgs = [textured_plane(W, H, bd, 20261018 + 97 * rank, t) for t in range(P)]
     recs = [pseudo_recon(o, bd, t) for t, o in enumerate(orgs)]
@@ -352,6 +449,9 @@ def run_ours(args, rank, world, local_rank):
     n_inst = max(1, args.e2e_instances)
     inst_threads = max(1, host_threads // n_inst)
     engines = [eng] + [cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=P, host_threads=inst_threads) for _ in range(n_inst - 1)]
+    if args.fork_aware:
+        for e in engines[1:]:
+            e.set_decision_switches(1, *FORK_SW)
     outs_list = [h_outs] + [[e.alloc_frame_out(True, pinned_alloc=pinned, packed=True, narrow=True) for _ in range(P)] for e in engines[1:]]
     e2e_steps = max(1, min(args.steps, 5))
     e2e_run(engines[:1], outs_list[:1], max(1, min(args.warmup, 2)))
@@ -371,7 +471,7 @@ def run_ours(args, rank, world, local_rank):
     #      TComPicYuv.cpp:97) - and plain caller-owned output buffers, one encoder instance.  (a) as they are, (b) page-locked once
     #      through cucd_pin_host_buffer / auto_pin_host, as a maintainer would do at TComPicYuv::create.  Rank 0 only. ----------
     hm_e2e = None
-    if rank == 0 and not args.no_hm_planes:
+    if rank == 0 and not args.no_hm_planes and not args.fork_aware:
         def hm_plane(a):
             buf = np.zeros((H + 160, W + 160), np.int16)
             buf[80:80 + H, 80:80 + W] = a
@@ -418,7 +518,7 @@ def run_ours(args, rank, world, local_rank):
                         "the epilogues on the integer ALU; the HBM fraction is small; see profiles/ for pipe utilisation"}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.fork_aware:
         _, cpu_baseline = cpu_reference_run(args, steps=3, warmup=1, target_step_s=3.0)
 
     if rank == 0:
@@ -434,6 +534,185 @@ def run_ours(args, rank, world, local_rank):
                         "host_numa_binding": numa, "host_threads_per_handle": host_threads},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "paths_agree": same}
+        if args.fork_aware:
+            t0 = d_cost[0].cpu().numpy().view(np.uint32)[:, :, 0]
+            line["fork_aware"] = {"label": "separate line, not the headline", "skip2Nx2N": FORK_SW[0], "terminateCU": FORK_SW[1],
+                                  "pus_evaluated_fraction_picture0": float(((t0 != 0xFFFFFFFE) & (t0 != 0xFFFFFFFF)).sum() / max(1, (t0 != 0xFFFFFFFF).sum()))}
+            line["cpu_baseline"] = None        # the CPU arm enumerates everything: not comparable with this line
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_inter(args, rank, world, local_rank):
+    """BASELINE configs[3] / [4]: the CU-decision cost path of an inter picture - the intra path of the picture plus, per reference
+    picture, integer-ME SAD surfaces and quarter-pel refinement tables of every square PU.  value: everything resident in HBM
+    (cucd_dev_frames + cucd_dev_me_sad_surface + cucd_dev_me_subpel_cost on torch's stream, CUDA events); e2e: the host-buffer
+    calls (cuCUDecide_frames, cucd_set_cur/ref_picture, cucd_me_sad_surface, cucd_me_subpel_cost), planes up and every table down."""
+    import torch
+    import torch.distributed as dist
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    cucd = importlib.import_module(PKG)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    W, H, bd, P, NR = args.width, args.height, args.bit_depth, args.pics, args.refs
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    host_threads = max(1, min(8, cores // max(1, world)))
+    eng = cucd.Engine(W, H, bit_depth=bd, device=local_rank, max_pictures=1, host_threads=host_threads)
+    nctu, pitch, R, M = eng.ctus_per_pic, (W + 63) // 64 * 64, ME_RANGE, ME_MARGIN
+    # per picture of the step: the current picture (t = 1 + 3p), its reconstruction stand-in, NR reference reconstructions (t - 1, t + 1)
+    seed = 20261018 + 97 * rank
+    curs = [textured_plane(W, H, bd, seed, 1 + 3 * p) for p in range(P)]
+    recs = [pseudo_recon(c, bd, p) for p, c in enumerate(curs)]
+    refs = [[np.ascontiguousarray(np.pad(pseudo_recon(textured_plane(W, H, bd, seed, 3 * p + (0, 2)[k]), bd, 10 + k), M, mode="edge")) for k in range(NR)] for p in range(P)]
+    pus = inter_pus(W, H)
+    n_pu, cand = len(pus), (2 * R + 1) ** 2
+    me_arr, me_n, me_total = [], 0, 0
+    for k in range(NR):
+        arr, me_n, me_total = cucd.Engine.me_descs([dict(x=x, y=y, w=s, h=s, ref_idx=k, left=-R, right=R, top=-R, bottom=R, sub_shift=1 if s > 8 else 0) for x, y, s in pus])
+        me_arr.append(arr)
+    sp_arr = [cucd.Engine.subpel_descs([dict(x=x, y=y, w=s, h=s, ref_idx=k, mvx=1, mvy=-1, use_hadamard=1) for x, y, s in pus])[0] for k in range(NR)]
+
+    # ---- device-resident buffers ---------------------------------------------------------------------
+    d_org = torch.zeros((1, H, pitch), dtype=torch.int16, device=dev); d_rec = torch.zeros_like(d_org)
+    d_cost = torch.empty((1, nctu, 341, 35), dtype=torch.int32, device=dev)
+    d_obf = torch.empty((1, H // 4, W // 4), dtype=torch.int16, device=dev); d_outl = torch.empty((1, H, W), dtype=torch.int16, device=dev)
+    d_had = torch.empty((1, nctu), dtype=torch.int32, device=dev)
+    d_out = {"obf": d_obf.data_ptr(), "outlier": d_outl.data_ptr(), "ctu_src_had": d_had.data_ptr(), "rmd_cost": d_cost.data_ptr()}
+    d_sad = [torch.empty(me_total, dtype=torch.int32, device=dev) for _ in range(NR)]
+    d_sub = [torch.empty((n_pu, 49), dtype=torch.int32, device=dev) for _ in range(NR)]
+    stream = torch.cuda.current_stream().cuda_stream
+    me_ev = []
+
+    def resident_picture(p):
+        """a picture and its references become resident (untimed for `value`: inputs are in HBM when the timed region starts)"""
+        d_org[0, :, :W] = torch.from_numpy(curs[p]).to(dev); d_rec[0, :, :W] = torch.from_numpy(recs[p]).to(dev)
+        eng.set_cur_picture(curs[p])
+        for k in range(NR):
+            eng.set_ref_picture(k, refs[p][k], M, M)
+
+    def dev_step(timed):
+        eng.dev_frames(stream, 1, d_org.data_ptr(), H * pitch, pitch, d_rec.data_ptr(), H * pitch, pitch, d_out)
+        for k in range(NR):
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            eng.dev_me_sad_surface(stream, me_arr[k], me_n, d_sad[k].data_ptr())
+            if timed:
+                b.record(); me_ev.append((a, b))
+            eng.dev_me_subpel_cost(stream, sp_arr[k], me_n, d_sub[k].data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # `pics` pictures per step: the same resident picture is processed P times per step (P = 1 by default) - uploading between
+    # the timed calls would turn `value` into an e2e figure
+    resident_picture(0)
+    clocks = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        for _ in range(P):
+            dev_step(False)
+    barrier()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        for _ in range(P):
+            dev_step(True)
+    e1.record()
+    barrier()
+    launches = eng.launch_count - l0
+    dev_ms = e0.elapsed_time(e1)
+    me_ms = float(np.mean([a.elapsed_time(b) for a, b in me_ev]))
+
+    # ---- end to end: host planes up, every table down ---------------------------------------------------
+    def pinned(shape, dtype):
+        tdt = {np.int16: torch.int16, np.int32: torch.int32, np.uint32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}[dtype]
+        t = torch.empty(shape, dtype=tdt, pin_memory=True)
+        pinned.keep.append(t)
+        a = t.numpy()
+        return a.view(np.uint32) if dtype is np.uint32 else a
+    pinned.keep = []
+    hdt = np.uint8 if bd == 8 else np.int16
+    h_cur = [pinned((H, W), hdt) for _ in range(P)]; h_rec = [pinned((H, W), hdt) for _ in range(P)]
+    h_cur16 = [pinned((H, W), np.int16) for _ in range(P)]
+    h_refs = [[pinned(refs[p][k].shape, np.int16) for k in range(NR)] for p in range(P)]
+    for p in range(P):
+        h_cur[p][:] = curs[p]; h_rec[p][:] = recs[p]; h_cur16[p][:] = curs[p]
+        for k in range(NR):
+            h_refs[p][k][:] = refs[p][k]
+    h_out = eng.alloc_frame_out(True, pinned_alloc=pinned, packed=True, narrow=True)
+    h_sad = pinned((me_total,), np.uint32)              # one surface block, reused per reference (an encoder consumes it before the next)
+    h_sub = pinned((n_pu, 49), np.uint32)
+
+    def e2e_step():
+        for p in range(P):
+            eng.frames([h_cur[p]], [h_rec[p]], [h_out])
+            eng.set_cur_picture(h_cur16[p])
+            for k in range(NR):
+                eng.set_ref_picture(k, h_refs[p][k], M, M)
+                eng.me_sad_surface_raw(me_arr[k], me_n, h_sad)
+                eng.me_subpel_cost_raw(sp_arr[k], me_n, h_sub)
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    h2d = P * (2 * W * H * np.dtype(hdt).itemsize + W * H * 2 + NR * int(refs[0][0].nbytes))
+    d2h = P * (sum(int(a.nbytes) for a in h_out.values()) + NR * (int(h_sad.nbytes) + int(h_sub.nbytes)))
+    # the two paths agree (last reference of the last picture)
+    resident_picture(P - 1)
+    dev_step(False)
+    torch.cuda.synchronize()
+    same = bool(np.array_equal(d_sad[NR - 1].cpu().numpy().view(np.uint32), h_sad) and np.array_equal(d_sub[NR - 1].cpu().numpy().view(np.uint32), h_sub) and
+                np.array_equal(d_cost[0].cpu().numpy().view(np.uint32), cucd.unpack_costs(h_out["rmd_cost_packed"])))
+
+    t = torch.tensor([dev_ms, e2e_s, me_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s, me_ms = [float(v) for v in t.tolist()]
+    ctus_step_gpu = P * nctu
+    value = world * ctus_step_gpu * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * ctus_step_gpu * e2e_steps / e2e_s
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    algo = me_algo_bytes(pus)
+    achieved = algo / (me_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "me_sad_u8_kernel" if bd == 8 else "me_sad_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "launch_ms": me_ms, "launches_timed": len(me_ev), "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
+                "note": "the dominant launch of an inter step: one SAD surface launch per reference (CUDA events on the launching stream around the "
+                        "call; includes the upload of its job records).  Algorithmic bytes per PU = source + reference window + surface (SURVEY.md 8d); "
+                        f"the work is {(2 * ME_RANGE + 1) ** 2} candidates x w x h absolute differences per PU: integer-ALU bound (VABSDIFF4), see profiles/"}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cpu_baseline = cpu_reference_run(args, steps=2, warmup=1)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "CTU/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "ms_per_step": 1e3 * e2e_s / e2e_steps, "instances_per_gpu": 1,
+                        "api": "cuCUDecide_frames(_u8) + cucd_set_cur_picture / cucd_set_ref_picture + cucd_me_sad_surface + cucd_me_subpel_cost: pinned host planes in, "
+                               "cost tables, feature planes, every SAD surface and refinement table back on the host",
+                        "host_numa_binding": numa},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "paths_agree": same}
         print(json.dumps(line))
     eng.close()
     if world > 1:
@@ -446,14 +725,24 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pics", type=int, default=16, help="pictures per step per GPU")
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--bit-depth", type=int, default=8)
+    ap.add_argument("--config", default="ai1080p8", choices=sorted(CONFIGS), help="BASELINE.json workload (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--pics", type=int, default=None, help="pictures per step per GPU (default: the configuration's)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--bit-depth", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hm-planes", action="store_true", help="skip the pageable / page-locked HM-layout e2e measurement")
+    ap.add_argument("--fork-aware", action="store_true",
+                    help="SEPARATE, labelled line (never the headline): Testing-picture mode of the fork - the frame calls prune the PUs the encoder's "
+                         "early decisions would skip (cucd_set_decision_switches; switches as a real 416x240 encode held them: Skip2Nx2N on at every depth, "
+                         "TerminateCU on at depths 0-2)")
     ap.add_argument("--e2e-instances", type=int, default=2, help="encoder instances (handles + host threads) per GPU in the e2e measurement")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    custom = any(v is not None for v in (args.width, args.height, args.bit_depth))
+    args.width, args.height = args.width or cfg["width"], args.height or cfg["height"]
+    args.bit_depth, args.pics, args.refs = args.bit_depth or cfg["bit_depth"], args.pics or cfg["pics"], cfg["refs"]
+    args.label = None if custom else cfg["label"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -461,7 +750,10 @@ def main():
         run_reference(args, rank, world)
         return
     args.gpus = world if world > 1 else args.gpus
-    run_ours(args, rank, world, local_rank)
+    if args.refs:
+        run_inter(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -11,6 +11,8 @@ The directory name contains hyphens, so import it with::
 """
 from .sharding import FORK_PERIOD, shard_independent, shard_pictures  # noqa: F401
 from .binding import (  # noqa: F401
+    COST_NOT_INSIDE,
+    COST_PRUNED,
     CucdError,
     Engine,
     LIB_PATH,

@@ -13,6 +13,7 @@ import numpy as np
 
 NUM_MODES = 35
 PUS_PER_CTU = 341
+COST_NOT_INSIDE, COST_PRUNED = 0xFFFFFFFF, 0xFFFFFFFE     # table codes (CUCD_COST_NOT_INSIDE / CUCD_COST_PRUNED)
 PACKED_WIDE_PUS = 21                     # CUCD_PACKED_WIDE_PUS: PUs 0..20 stay uint32
 PACKED_U16_PUS = 64                      # CUCD_PACKED_U16_PUS: the 8x8 PUs as uint16
 PACKED_U16_OFFSET = PACKED_WIDE_PUS * 35 * 4
@@ -28,7 +29,7 @@ def unpack_costs(packed):
     out = np.empty((n, PUS_PER_CTU, NUM_MODES), np.uint32)
     out[:, :PACKED_WIDE_PUS] = packed[:, :PACKED_U16_OFFSET].copy().view(np.uint32).reshape(n, PACKED_WIDE_PUS, NUM_MODES)
     mid = packed[:, PACKED_U16_OFFSET:PACKED_B13_OFFSET].copy().view(np.uint16).reshape(n, PACKED_U16_PUS, NUM_MODES)
-    out[:, PACKED_WIDE_PUS:PACKED_WIDE_PUS + PACKED_U16_PUS] = np.where(mid == 0xFFFF, np.uint32(0xFFFFFFFF), mid.astype(np.uint32))
+    out[:, PACKED_WIDE_PUS:PACKED_WIDE_PUS + PACKED_U16_PUS] = np.where(mid >= 0xFFFE, mid.astype(np.uint32) | np.uint32(0xFFFF0000), mid.astype(np.uint32))
     # 8 values = 13 bytes = 104 bits
     grp = packed[:, PACKED_B13_OFFSET:].reshape(n, -1, 13).astype(np.uint64)
     lo = sum(grp[:, :, k] << np.uint64(8 * k) for k in range(8))
@@ -44,7 +45,7 @@ def unpack_costs(packed):
             v = ((lo >> np.uint64(bit)) | (hi << np.uint64(64 - bit))) & np.uint64(0x1FFF)
         vals[:, :, k] = v.astype(np.uint32)
     small = vals.reshape(n, 256, NUM_MODES)
-    out[:, PACKED_WIDE_PUS + PACKED_U16_PUS:] = np.where(small == 0x1FFF, np.uint32(0xFFFFFFFF), small)
+    out[:, PACKED_WIDE_PUS + PACKED_U16_PUS:] = np.where(small >= 0x1FFE, small | np.uint32(0xFFFFE000), small)
     return out
 
 
@@ -139,6 +140,7 @@ def load_library():
     lib.cucd_packed_cost.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.cucd_packed_cost.restype = C.c_uint32
     lib.cucd_set_rmd_path.argtypes = [C.c_void_p, C.c_int]
+    lib.cucd_set_decision_switches.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.cuCUDecide_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(_FrameOut)]
     lib.cucd_intra_rmd_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PuDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cucd_set_ref_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -158,6 +160,8 @@ def load_library():
                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     lib.cucd_dev_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
                                     C.c_int, C.POINTER(_DevOut), C.c_void_p]
+    lib.cucd_dev_me_sad_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_MeDesc), C.c_void_p]
+    lib.cucd_dev_me_subpel_cost.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(_SubpelDesc), C.c_void_p]
     lib.cucd_dev_frames_begin.argtypes = lib.cucd_dev_frames.argtypes
     lib.cucd_dev_frames_end.argtypes = [C.c_void_p]
     lib.cucd_queue_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -361,6 +365,39 @@ class Engine:
         p, stride = _plane(org)
         self._check(self.lib.cucd_set_cur_picture(self.h, p.ctypes.data, stride), "cucd_set_cur_picture")
 
+    @staticmethod
+    def me_descs(descs):
+        """list of dicts(x,y,w,h,ref_idx,left,right,top,bottom,sub_shift) -> (ctypes array, n, total candidates): build once, reuse"""
+        arr = (_MeDesc * max(len(descs), 1))()
+        total = 0
+        for i, d in enumerate(descs):
+            for k in ("x", "y", "w", "h", "ref_idx", "left", "right", "top", "bottom", "sub_shift"):
+                setattr(arr[i], k, int(d[k]))
+            total += (d["bottom"] - d["top"] + 1) * (d["right"] - d["left"] + 1)
+        return arr, len(descs), total
+
+    @staticmethod
+    def subpel_descs(descs):
+        arr = (_SubpelDesc * max(len(descs), 1))()
+        for i, d in enumerate(descs):
+            for k in ("x", "y", "w", "h", "ref_idx", "mvx", "mvy", "use_hadamard"):
+                setattr(arr[i], k, int(d[k]))
+        return arr, len(descs)
+
+    def me_sad_surface_raw(self, arr, n, out):
+        """cucd_me_sad_surface with a prebuilt descriptor array; out: uint32 host array of `total` candidates"""
+        self._check(self.lib.cucd_me_sad_surface(self.h, n, arr, out.ctypes.data), "cucd_me_sad_surface")
+
+    def me_subpel_cost_raw(self, arr, n, out):
+        self._check(self.lib.cucd_me_subpel_cost(self.h, n, arr, out.ctypes.data), "cucd_me_subpel_cost")
+
+    def dev_me_sad_surface(self, stream, arr, n, d_out):
+        """cucd_dev_me_sad_surface: surfaces stay in HBM at device pointer d_out"""
+        self._check(self.lib.cucd_dev_me_sad_surface(self.h, stream, n, arr, d_out), "cucd_dev_me_sad_surface")
+
+    def dev_me_subpel_cost(self, stream, arr, n, d_out):
+        self._check(self.lib.cucd_dev_me_subpel_cost(self.h, stream, n, arr, d_out), "cucd_dev_me_subpel_cost")
+
     def me_sad_surface(self, descs):
         """descs: list of dicts(x,y,w,h,ref_idx,left,right,top,bottom,sub_shift). Returns list of (rows, cols) uint32 surfaces."""
         n = len(descs)
@@ -503,6 +540,11 @@ class Engine:
         if n < 0:
             self._check(n, "cucd_rmd_kernel_time")
         return float(ms.value), int(n)
+
+    def set_decision_switches(self, enable, skip2nx2n=(0, 0, 0, 0), terminate_cu=(0, 0, 0, 0)):
+        """cucd_set_decision_switches: fork-aware enumeration of the frame calls (Testing pictures); per-depth switch lists of 4"""
+        a = (C.c_uint8 * 4)(*[int(bool(v)) for v in skip2nx2n]); b = (C.c_uint8 * 4)(*[int(bool(v)) for v in terminate_cu])
+        self._check(self.lib.cucd_set_decision_switches(self.h, int(bool(enable)), a, b), "cucd_set_decision_switches")
 
     def set_rmd_path(self, path):
         """0 / False: integer ALU; 1 / True: predictions + Hadamard on the tensor cores (tcgen05)"""

@@ -54,10 +54,10 @@ bool pin_host_range(cucd_handle* h, const void* ptr, size_t bytes) {
 namespace {
 
 FrameSource make_frame_source(const cucd_handle* h, const int16_t* org, long long orgPic, int orgStride, const int16_t* rec, long long recPic,
-                              int recStride, uint32_t* out, uint8_t* outPacked) {
+                              int recStride, uint32_t* out, uint8_t* outPacked, const uint8_t* needed = nullptr) {
   FrameSource fs;
   fs.org = org; fs.rec = rec; fs.orgPicStride = orgPic; fs.recPicStride = recPic; fs.orgStride = orgStride; fs.recStride = recStride;
-  fs.W = h->cfg.width; fs.H = h->cfg.height; fs.ctusPerRow = h->ctusPerRow; fs.ctusPerPic = h->ctusPerPic; fs.out = out; fs.outPacked = outPacked;
+  fs.W = h->cfg.width; fs.H = h->cfg.height; fs.ctusPerRow = h->ctusPerRow; fs.ctusPerPic = h->ctusPerPic; fs.out = out; fs.outPacked = outPacked; fs.needed = needed;
   return fs;
 }
 FeaturePlanes make_feature_planes(const cucd_handle* h, const int16_t* org, long long orgPic, int orgStride) {
@@ -100,19 +100,19 @@ uint32_t cucd_packed_cost(const uint8_t* t, int pu, int mode) {
   if (pu < CUCD_PACKED_WIDE_PUS) return reinterpret_cast<const uint32_t*>(t)[pu * 35 + mode];
   if (pu < CUCD_PACKED_WIDE_PUS + CUCD_PACKED_U16_PUS) {
     const uint16_t v = reinterpret_cast<const uint16_t*>(t + CUCD_PACKED_U16_OFFSET)[(pu - CUCD_PACKED_WIDE_PUS) * 35 + mode];
-    return v == 0xFFFFu ? 0xFFFFFFFFu : (uint32_t)v;
+    return v >= 0xFFFEu ? 0xFFFF0000u | v : (uint32_t)v;      /* 0xFFFF / 0xFFFE -> CUCD_COST_NOT_INSIDE / CUCD_COST_PRUNED */
   }
   const size_t bit = (size_t)((pu - CUCD_PACKED_WIDE_PUS - CUCD_PACKED_U16_PUS) * 35 + mode) * 13;
   const uint8_t* b = t + CUCD_PACKED_B13_OFFSET + (bit >> 3);
   const uint32_t w = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((bit & 7) > 3 ? (uint32_t)b[2] << 16 : 0u);   // 13 bits span 2 or 3 bytes
   const uint32_t v = (w >> (bit & 7)) & 0x1FFFu;
-  return v == 0x1FFFu ? 0xFFFFFFFFu : v;
+  return v >= 0x1FFEu ? 0xFFFFE000u | v : v;
 }
 void cucd_unpack_costs(const uint8_t* t, uint32_t* cost) {
   memcpy(cost, t, CUCD_PACKED_U16_OFFSET);
   const uint16_t* u = reinterpret_cast<const uint16_t*>(t + CUCD_PACKED_U16_OFFSET);
   uint32_t* o = cost + CUCD_PACKED_WIDE_PUS * 35;
-  for (int i = 0; i < CUCD_PACKED_U16_PUS * 35; i++) o[i] = u[i] == 0xFFFFu ? 0xFFFFFFFFu : (uint32_t)u[i];
+  for (int i = 0; i < CUCD_PACKED_U16_PUS * 35; i++) o[i] = u[i] >= 0xFFFEu ? 0xFFFF0000u | u[i] : (uint32_t)u[i];
   o += CUCD_PACKED_U16_PUS * 35;
   const uint8_t* b = t + CUCD_PACKED_B13_OFFSET;
   // 8 values = 13 bytes: walk the stream with a 64-bit window
@@ -121,7 +121,7 @@ void cucd_unpack_costs(const uint8_t* t, uint32_t* cost) {
     while (have < 13) { acc |= (uint64_t)b[pos++] << have; have += 8; }
     const uint32_t v = (uint32_t)(acc & 0x1FFFu);
     acc >>= 13; have -= 13;
-    o[i] = v == 0x1FFFu ? 0xFFFFFFFFu : v;
+    o[i] = v >= 0x1FFEu ? 0xFFFFE000u | v : v;
   }
 }
 
@@ -167,6 +167,8 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   for (int i = 0; i < cucd_handle::kGroups; i++)
     ok = ok && cudaEventCreateWithFlags(&h->evUpG[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->evRmdG[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreate(&h->evK0) == cudaSuccess && cudaEventCreate(&h->evK1) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->evMask, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->evDevUp, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&h->evDevDone, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < cucd_handle::kTimeRing; i++) ok = ok && cudaEventCreate(&h->evRmd0[i]) == cudaSuccess && cudaEventCreate(&h->evRmd1[i]) == cudaSuccess;
   for (FrameSlot& s : h->slots) {
     ok = ok && cudaEventCreateWithFlags(&s.evHist, cudaEventDisableTiming) == cudaSuccess &&
@@ -219,6 +221,11 @@ int cucd_destroy(cucd_handle* h) {
   h->dCur.release(); h->dRefPtr.release(); h->dRefStride.release();
   for (int i = 0; i < cucd_handle::kTimeRing; i++) { if (h->evRmd0[i]) cudaEventDestroy(h->evRmd0[i]); if (h->evRmd1[i]) cudaEventDestroy(h->evRmd1[i]); }
   for (int i = 0; i < cucd_handle::kGroups; i++) { if (h->evUpG[i]) cudaEventDestroy(h->evUpG[i]); if (h->evRmdG[i]) cudaEventDestroy(h->evRmdG[i]); }
+  h->hDevScratch.release(); h->dDevStage.release();
+  if (h->evDevUp) cudaEventDestroy(h->evDevUp);
+  if (h->evDevDone) cudaEventDestroy(h->evDevDone);
+  h->dNeeded.release();
+  if (h->evMask) cudaEventDestroy(h->evMask);
   if (h->evK0) cudaEventDestroy(h->evK0);
   if (h->evK1) cudaEventDestroy(h->evK1);
   if (h->sUp) cudaStreamDestroy(h->sUp);
@@ -249,6 +256,15 @@ int cucd_unpin_host_buffer(cucd_handle* h, const void* ptr) {
       return CUCD_OK;
     }
   return fail(h, CUCD_ERR_INVALID, "cucd_unpin_host_buffer: not a range this handle pinned");
+}
+
+int cucd_set_decision_switches(cucd_handle* h, int enable, const uint8_t skip2Nx2N[4], const uint8_t terminateCU[4]) {
+  if (!h || (enable && (!skip2Nx2N || !terminateCU))) return fail(h, CUCD_ERR_INVALID, "cucd_set_decision_switches: bad argument");
+  LOCK(h);
+  if (h->begun != h->ended) return fail(h, CUCD_ERR_INVALID, "cucd_set_decision_switches: a cucd_dev_frames_begin batch is still in flight");
+  h->prune = enable != 0;
+  for (int d = 0; d < 4; d++) { h->sw.skip2Nx2N[d] = enable && skip2Nx2N[d] ? 1 : 0; h->sw.terminateCU[d] = enable && terminateCU[d] ? 1 : 0; }
+  return CUCD_OK;
 }
 
 int cucd_set_rmd_path(cucd_handle* h, int path) {
@@ -350,6 +366,9 @@ int cucd_dev_frames_begin(cucd_handle* h, void* stream, int nPics, const int16_t
   cudaStream_t st = (cudaStream_t)stream;
   s.st = st; s.nPics = nPics; s.out = *out; s.ycHost = yc_host;
   s.wantFeat = out->obf || out->outlier || out->ctu_src_had || yc_host || out->num_obf[0] || out->num_obf[1] || out->num_obf[2] || out->num_obf[3];
+  // fork-aware mode: the RMD enumeration depends on Num_OBF, so the feature path runs first and the RMD launch moves to _end
+  s.pruned = h->prune && d_rec;
+  if (s.pruned) { s.wantFeat = true; s.rec = d_rec; s.recPicStride = recPicStride; s.recStride = recStride; }
   s.fp = make_feature_planes(h, d_org, orgPicStride, orgStride);
   // The feature path (two small streaming kernels around a host fit) runs on the library's high-priority stream beside the RMD
   // kernel instead of in front of / behind it: fork from the caller's stream here, join in cucd_dev_frames_end.  Its CTAs slip in
@@ -365,7 +384,7 @@ int cucd_dev_frames_begin(cucd_handle* h, void* stream, int nPics, const int16_t
     CK(cudaMemcpyAsync(s.hHist.p, s.dHist.p, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.sf));
     CK(cudaEventRecord(s.evHist, s.sf));
   }
-  if (d_rec) {
+  if (d_rec && !s.pruned) {
     const FrameSource fs = make_frame_source(h, d_org, orgPicStride, orgStride, d_rec, recPicStride, recStride, out->rmd_cost, nullptr);
     const int slot = (int)(h->rmdCalls % cucd_handle::kTimeRing);
     CK(cudaEventRecord(h->evRmd0[slot], st));
@@ -404,10 +423,22 @@ int cucd_dev_frames_end(cucd_handle* h) {
     fo.cuPicStride[d] = (long long)h->cuCount[d];
   }
   CK(launch_feature_obf(s.fp, nPics, s.dThr.p, fo, s.sf, &h->launches));
+  if (s.pruned) {
+    CK(h->dNeeded.reserve((size_t)h->cfg.max_pictures * h->ctusPerPic * kPusPerCtu));
+    CK(launch_prune_mask(s.fp, nPics, fo, h->sw, h->dNeeded.p, s.sf, &h->launches));
+  }
   if (s.out.ctu_src_had) CK(launch_ctu_src_had(s.fp, nPics, s.out.ctu_src_had, s.sf, &h->launches));
   if (s.sf != s.st) {
     CK(cudaEventRecord(s.evJoin, s.sf));
     CK(cudaStreamWaitEvent(s.st, s.evJoin, 0));
+  }
+  if (s.pruned) {
+    const FrameSource fs = make_frame_source(h, s.fp.org, s.fp.orgPicStride, s.fp.orgStride, s.rec, s.recPicStride, s.recStride, s.out.rmd_cost, nullptr, h->dNeeded.p);
+    const int slot = (int)(h->rmdCalls % cucd_handle::kTimeRing);
+    CK(cudaEventRecord(h->evRmd0[slot], s.st));
+    CK(launch_rmd_auto(h, fs, nPics, s.st));
+    CK(cudaEventRecord(h->evRmd1[slot], s.st));
+    h->rmdCalls++;
   }
   flush_launches(h);
   return CUCD_OK;
@@ -470,6 +501,26 @@ static int frames_group(cucd_handle* h, int nPics, const Pel* const* orgY, int s
   // ---- three-stage pipeline over sub-groups of pictures: upload (sUp) -> RMD (sGrp[0]) -> cost-table download (sGrp[1]); PCIe
   //      is full duplex, so uploads, kernels and the (dominant) downloads overlap.  The RMD kernels write the packed tables
   //      themselves.  The feature path (sFeat) needs every source plane and runs beside it. -----------------------------
+  const bool pruned = h->prune && wantRmd;     // fork-aware mode: the RMD launches wait for the prune mask, i.e. for feature pass 2
+  if (pruned) CK(h->dNeeded.reserve(P * h->ctusPerPic * kPusPerCtu));
+  // RMD of one sub-group on sGrp[0] behind its upload (and, in fork-aware mode, behind the mask), its downloads on sGrp[1]
+  auto rmd_group = [&](int gi, int first, int n) -> int {
+    CK(cudaStreamWaitEvent(h->sGrp[0], h->evUpG[gi], 0));
+    if (pruned) CK(cudaStreamWaitEvent(h->sGrp[0], h->evMask, 0));
+    const FrameSource fs = make_frame_source(h, h->dOrg.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
+                                             h->dRec.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
+                                             wantWide ? h->dCost.p + (size_t)first * perPic : nullptr,
+                                             wantPacked ? h->dCostPacked.p + (size_t)first * perPicPacked : nullptr,
+                                             pruned ? h->dNeeded.p + (size_t)first * h->ctusPerPic * kPusPerCtu : nullptr);
+    CK(launch_rmd_auto(h, fs, n, h->sGrp[0]));
+    CK(cudaEventRecord(h->evRmdG[gi], h->sGrp[0]));
+    CK(cudaStreamWaitEvent(h->sGrp[1], h->evRmdG[gi], 0));
+    for (int p = first; p < first + n; p++) {
+      if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sGrp[1]));
+      if (outs[p].rmd_cost_packed) CK(cudaMemcpyAsync(outs[p].rmd_cost_packed, h->dCostPacked.p + p * perPicPacked, perPicPacked, cudaMemcpyDeviceToHost, h->sGrp[1]));
+    }
+    return CUCD_OK;
+  };
   static const int nGroups = [] { const char* e = getenv("CUCD_GROUPS"); const int g = e ? atoi(e) : 8; return std::min(std::max(g, 1), (int)cucd_handle::kGroups); }();
   const int grp = std::max(1, (nPics + nGroups - 1) / nGroups);
   int gi = 0;
@@ -488,19 +539,7 @@ static int frames_group(cucd_handle* h, int nPics, const Pel* const* orgY, int s
       if (wantRmd) CK(launch_widen_u8(h->dRec8.p + (size_t)first * h->planeSamples, h->dRec.p + (size_t)first * h->planeSamples, (size_t)n * h->planeSamples, h->sUp, &h->launches));
     }
     CK(cudaEventRecord(h->evUpG[gi], h->sUp));
-    if (!wantRmd) continue;
-    CK(cudaStreamWaitEvent(h->sGrp[0], h->evUpG[gi], 0));
-    const FrameSource fs = make_frame_source(h, h->dOrg.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
-                                             h->dRec.p + (size_t)first * h->planeSamples, (long long)h->planeSamples, h->pitch,
-                                             wantWide ? h->dCost.p + (size_t)first * perPic : nullptr,
-                                             wantPacked ? h->dCostPacked.p + (size_t)first * perPicPacked : nullptr);
-    CK(launch_rmd_auto(h, fs, n, h->sGrp[0]));
-    CK(cudaEventRecord(h->evRmdG[gi], h->sGrp[0]));
-    CK(cudaStreamWaitEvent(h->sGrp[1], h->evRmdG[gi], 0));
-    for (int p = first; p < first + n; p++) {
-      if (outs[p].rmd_cost) CK(cudaMemcpyAsync(outs[p].rmd_cost, h->dCost.p + p * perPic, perPic * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->sGrp[1]));
-      if (outs[p].rmd_cost_packed) CK(cudaMemcpyAsync(outs[p].rmd_cost_packed, h->dCostPacked.p + p * perPicPacked, perPicPacked, cudaMemcpyDeviceToHost, h->sGrp[1]));
-    }
+    if (wantRmd && !pruned) { const int rc = rmd_group(gi, first, n); if (rc != CUCD_OK) return rc; }
   }
   CK(cudaEventRecord(h->evUp, h->sUp));
   // ---- feature pass 1 on sFeat -----------------------------------------------------------------
@@ -528,6 +567,12 @@ static int frames_group(cucd_handle* h, int nPics, const Pel* const* orgY, int s
   fo.obf8 = wantObf8 ? h->dObf8.p : nullptr; fo.outlier8 = wantOutl8 ? h->dOutlier8.p : nullptr;
   for (int d = 0; d < 4; d++) { fo.numObf[d] = h->dNum[d].p; fo.nOutlier[d] = h->dSum[d].p; fo.cuPicStride[d] = (long long)h->cuCount[d]; }
   CK(launch_feature_obf(fp, nPics, s.dThr.p, fo, h->sFeat, &h->launches));
+  if (pruned) {
+    CK(launch_prune_mask(fp, nPics, fo, h->sw, h->dNeeded.p, h->sFeat, &h->launches));
+    CK(cudaEventRecord(h->evMask, h->sFeat));
+    int g2 = 0;
+    for (int first = 0; first < nPics; first += grp, g2++) { const int rc = rmd_group(g2, first, std::min(grp, nPics - first)); if (rc != CUCD_OK) return rc; }
+  }
   bool wantHad = false;
   for (int p = 0; p < nPics; p++) wantHad = wantHad || outs[p].ctu_src_had;
   if (wantHad) CK(launch_ctu_src_had(fp, nPics, h->dCtuHad.p, h->sFeat, &h->launches));

@@ -355,16 +355,11 @@ static int sync_ref_table(cucd_handle* h) {
   return CUCD_OK;
 }
 
-int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut) {
-  if (!h || nPU < 0 || (nPU > 0 && (!desc || !sadOut))) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: bad argument");
-  if (nPU == 0) return CUCD_OK;
-  LOCK(h);
-  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: cucd_set_cur_picture not called");
-  CK(cudaSetDevice(h->cfg.device));
+// validate the PUs, build job + tile records into `scratch` (pinned); returns the sizes through the references
+static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinBuf<uint8_t>& scratch, size_t& jobBytes, size_t& tileBytes, long long& total, long long& nTiles) {
   const int W = h->cfg.width, H = h->cfg.height;
   const int tileRows = h->cfg.bit_depth == 8 ? 16 : 8;     // me_sad_u8_kernel covers 32 x 16 candidates per CTA, me_sad_kernel 32 x 8
-  // pass 1: validate, count the tiles
-  long long total = 0, nTiles = 0;
+  total = 0; nTiles = 0;
   for (int i = 0; i < nPU; i++) {
     const cucd_me_desc& d = desc[i];
     // HM's PU widths are multiples of 4 (4..64, AMP 12 / 24 / 48 included); the 8-bit kernel reads the source as 32-bit words
@@ -380,13 +375,11 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
     total += (long long)cols * rows;
   }
   if (nTiles > 0x7fffffffll) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: batch too large");
-  if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
-  // pass 2: job and tile records straight into pinned scratch
-  const size_t jobBytes = up16((size_t)nPU * sizeof(MeJob)), tileBytes = up16((size_t)nTiles * 4);
-  CK(h->hScratch.reserve(jobBytes + 2 * tileBytes));
-  MeJob* jobs = reinterpret_cast<MeJob*>(h->hScratch.p);
-  int32_t* tileJob = reinterpret_cast<int32_t*>(h->hScratch.p + jobBytes);
-  int32_t* tileIdx = reinterpret_cast<int32_t*>(h->hScratch.p + jobBytes + tileBytes);
+  jobBytes = up16((size_t)nPU * sizeof(MeJob)); tileBytes = up16((size_t)nTiles * 4);
+  CK(scratch.reserve(jobBytes + 2 * tileBytes));
+  MeJob* jobs = reinterpret_cast<MeJob*>(scratch.p);
+  int32_t* tileJob = reinterpret_cast<int32_t*>(scratch.p + jobBytes);
+  int32_t* tileIdx = reinterpret_cast<int32_t*>(scratch.p + jobBytes + tileBytes);
   long long off = 0; size_t nt = 0;
   for (int i = 0; i < nPU; i++) {
     const cucd_me_desc& d = desc[i];
@@ -405,6 +398,19 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
     for (int t = 0; t < tiles; t++) { tileJob[nt] = i; tileIdx[nt] = t; nt++; }
     off += (long long)cols * rows;
   }
+  return CUCD_OK;
+}
+
+int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !sadOut))) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  size_t jobBytes, tileBytes; long long total, nTiles;
+  const int rc = me_build_jobs(h, nPU, desc, h->hScratch, jobBytes, tileBytes, total, nTiles);
+  if (rc != CUCD_OK) return rc;
+  if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
   BatchIo io(h);
   const int iAll = io.add_in(h->hScratch.p, jobBytes + 2 * tileBytes, true);
   const int oSad = io.add_out(sadOut, (size_t)total * sizeof(uint32_t));
@@ -421,18 +427,45 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
   return CUCD_OK;
 }
 
+// Device-resident variants: the surfaces / cost tables stay in HBM (d_out), everything is enqueued on `stream` and the call does
+// not wait for the GPU.  The job records travel through buffers of their own, guarded by an event, so that back-to-back calls on
+// one stream pipeline and a host-buffer call in between cannot overwrite records a queued kernel still has to read.
+static int dev_records_begin(cucd_handle* h, cudaStream_t st) {
+  if (h->devBusy) { CK(cudaEventSynchronize(h->evDevUp)); CK(cudaStreamWaitEvent(st, h->evDevDone, 0)); h->devBusy = false; }
+  return CUCD_OK;
+}
+int cucd_dev_me_sad_surface(cucd_handle* h, void* stream, int nPU, const cucd_me_desc* desc, uint32_t* d_sad) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !d_sad))) return fail(h, CUCD_ERR_INVALID, "cucd_dev_me_sad_surface: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_dev_me_sad_surface: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dev_records_begin(h, st) != CUCD_OK) return CUCD_ERR_CUDA;
+  size_t jobBytes, tileBytes; long long total, nTiles;
+  const int rc = me_build_jobs(h, nPU, desc, h->hDevScratch, jobBytes, tileBytes, total, nTiles);
+  if (rc != CUCD_OK) return rc;
+  if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
+  CK(h->dDevStage.reserve(jobBytes + 2 * tileBytes));
+  CK(cudaMemcpyAsync(h->dDevStage.p, h->hDevScratch.p, jobBytes + 2 * tileBytes, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(h->evDevUp, st));
+  MePlanes mp;
+  mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
+  const uint8_t* dAll = h->dDevStage.p;
+  CK(launch_me_sad(mp, reinterpret_cast<const MeJob*>(dAll), nPU, reinterpret_cast<const int32_t*>(dAll + jobBytes), reinterpret_cast<const int32_t*>(dAll + jobBytes + tileBytes),
+                   (int)nTiles, d_sad, st, &h->launches));
+  CK(cudaEventRecord(h->evDevDone, st)); h->devBusy = true;
+  flush_launches(h);
+  return CUCD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fractional-pel refinement: distortion of the 49 quarter-pel positions around an integer MV
 // ------------------------------------------------------------------------------------------------
-int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, uint32_t* cost) {
-  if (!h || nPU < 0 || (nPU > 0 && (!desc || !cost))) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: bad argument");
-  if (nPU == 0) return CUCD_OK;
-  LOCK(h);
-  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: cucd_set_cur_picture not called");
-  CK(cudaSetDevice(h->cfg.device));
+static int subpel_build_jobs(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, PinBuf<uint8_t>& scratch) {
   const int W = h->cfg.width, H = h->cfg.height;
-  CK(h->hScratch.reserve((size_t)nPU * sizeof(SubpelJob) + 64));
-  SubpelJob* jobs = reinterpret_cast<SubpelJob*>(h->hScratch.p);
+  CK(scratch.reserve((size_t)nPU * sizeof(SubpelJob) + 64));
+  SubpelJob* jobs = reinterpret_cast<SubpelJob*>(scratch.p);
   for (int i = 0; i < nPU; i++) {
     const cucd_subpel_desc& d = desc[i];
     if (d.w < 4 || d.h < 4 || d.w > 64 || d.h > 64 || (d.w & 3) || (d.h & 3) || d.x < 0 || d.y < 0 || d.x + d.w > W || d.y + d.h > H)
@@ -446,9 +479,20 @@ int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, u
     j.refOff = (d.y + d.mvy + r.marginY) * r.stride + d.x + d.mvx + r.marginX;
     j.refSlot = d.ref_idx; j.w = (int16_t)d.w; j.h = (int16_t)d.h; j.useHadamard = d.use_hadamard ? 1 : 0;
   }
+  return CUCD_OK;
+}
+
+int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, uint32_t* cost) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !cost))) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  const int rc = subpel_build_jobs(h, nPU, desc, h->hScratch);
+  if (rc != CUCD_OK) return rc;
   if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
   BatchIo io(h);
-  const int iJobs = io.add_in(jobs, (size_t)nPU * sizeof(SubpelJob), true);
+  const int iJobs = io.add_in(h->hScratch.p, (size_t)nPU * sizeof(SubpelJob), true);
   const int oCost = io.add_out(cost, (size_t)nPU * CUCD_SUBPEL_POINTS * sizeof(uint32_t));
   if (io.reserve() != CUCD_OK || io.upload(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   MePlanes mp;
@@ -457,6 +501,29 @@ int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, u
   CK(launch_me_subpel(mp, io.din<SubpelJob>(iJobs), nPU, io.dout<uint32_t>(oCost), h->sMain, &h->launches));
   CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   if (io.download(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
+  flush_launches(h);
+  return CUCD_OK;
+}
+
+int cucd_dev_me_subpel_cost(cucd_handle* h, void* stream, int nPU, const cucd_subpel_desc* desc, uint32_t* d_cost) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !d_cost))) return fail(h, CUCD_ERR_INVALID, "cucd_dev_me_subpel_cost: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_dev_me_subpel_cost: cucd_set_cur_picture not called");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dev_records_begin(h, st) != CUCD_OK) return CUCD_ERR_CUDA;
+  const int rc = subpel_build_jobs(h, nPU, desc, h->hDevScratch);
+  if (rc != CUCD_OK) return rc;
+  if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
+  const size_t bytes = (size_t)nPU * sizeof(SubpelJob);
+  CK(h->dDevStage.reserve(bytes));
+  CK(cudaMemcpyAsync(h->dDevStage.p, h->hDevScratch.p, bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(h->evDevUp, st));
+  MePlanes mp;
+  mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
+  CK(launch_me_subpel(mp, reinterpret_cast<const SubpelJob*>(h->dDevStage.p), nPU, d_cost, st, &h->launches));
+  CK(cudaEventRecord(h->evDevDone, st)); h->devBusy = true;
   flush_launches(h);
   return CUCD_OK;
 }

@@ -41,4 +41,44 @@ CUCD_HD int coeff_bin(int c) { return iabs32(c) >> 3; }
 // outlier test TEncSlice.cpp:1010 with thr = Yc*8 (Yc is integer valued): kept iff not strictly inside
 CUCD_HD bool coeff_is_outlier(int c, int thr) { return c != 0 && !(c < thr && c > -thr); }
 
+// ---------------------------------------------------------------------------------------------
+// Fork-aware PU enumeration of one CTU (Testing pictures).  Restates the control flow of TEncCu::xCompressCU around the
+// early decisions for an intra picture with the default Naive model (tools_YS.cpp:686-695: Num_OBF == 0 -> TerminateCU,
+// else Skip2Nx2N):
+//   - a CU that is not completely inside the picture is never predicted and never evaluated, its sub-CUs are visited
+//     (bBoundary, TEncCu.cpp:488-489, 645);
+//   - bSkip2Nx2N = switch[depth][Skip2Nx2N] && Num_OBF > 0   -> the 2Nx2N PU is not evaluated (:951-996, 1040);
+//   - bEarlyTerminate = switch[depth][TerminateCU] && Num_OBF == 0 -> no NxN at depth 3 (:1140-1143), no sub-CUs (:1257-1260).
+// numObf(d, cuX, cuY) returns Num_OBF of the whole CU at depth d with CU coordinates (cuX, cuY).
+// needed[341]: PU order of the cost tables (depth-major, z-order inside a depth).
+// ---------------------------------------------------------------------------------------------
+template <class NumObf>
+CUCD_HD void prune_mask_ctu(int ctuX, int ctuY, int W, int H, const uint8_t* swSkip, const uint8_t* swTerm, NumObf numObf, uint8_t* needed) {
+  for (int i = 0; i < 341; i++) needed[i] = 0;
+  unsigned long long visited = 1;       // bit i: CU i (z-order) of the current depth is reached by the recursion
+  int off = 0;                          // first PU index of the depth
+  for (int d = 0; d < 4; d++) {
+    const int n = 1 << (2 * d), size = 64 >> d;
+    unsigned long long next = 0;        // the (at most 64) CUs of the next depth
+    for (int i = 0; i < n; i++) {
+      if (!((visited >> i) & 1)) continue;
+      int px, py; demorton(i, px, py);
+      const int x = ctuX + px * size, y = ctuY + py * size;
+      if (x >= W || y >= H) continue;                                   // outside the picture: not coded at all
+      bool recurse = true;                                              // boundary CU: forced split
+      if (x + size <= W && y + size <= H) {
+        const int num = numObf(d, x / size, y / size);
+        const bool term = swTerm[d] && num == 0, skip = swSkip[d] && num > 0;
+        if (!skip) needed[off + i] = 1;
+        recurse = !term;
+      }
+      if (!recurse) continue;
+      if (d == 3) { for (int q = 0; q < 4; q++) needed[85 + 4 * i + q] = 1; }   // NxN of the 8x8 CU (W, H multiples of 8: never a boundary CU)
+      else next |= 0xfull << (4 * i);
+    }
+    off += n;
+    visited = next;
+  }
+}
+
 }  // namespace cucd

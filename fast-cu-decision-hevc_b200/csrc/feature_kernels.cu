@@ -196,6 +196,24 @@ cudaError_t launch_widen_u8(const uint8_t* src, int16_t* dst, size_t nSamples, c
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
+// one thread per CTU walks its 85 CUs (prune_mask_ctu)
+__global__ void prune_mask_kernel(const FeaturePlanes fp, const FeatureOut sums, const PruneSwitches sw, uint8_t* __restrict__ needed, int nPics) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nPics * fp.ctusPerPic) return;
+  const int pic = i / fp.ctusPerPic, ctu = i - pic * fp.ctusPerPic;
+  auto numObf = [&](int d, int cx, int cy) { return sums.numObf[d][(size_t)pic * sums.cuPicStride[d] + (size_t)cy * (fp.W / (64 >> d)) + cx]; };
+  uint8_t m[341];
+  prune_mask_ctu((ctu % fp.ctusPerRow) * 64, (ctu / fp.ctusPerRow) * 64, fp.W, fp.H, sw.skip2Nx2N, sw.terminateCU, numObf, m);
+  uint8_t* dst = needed + (size_t)i * 341;
+  for (int k = 0; k < 341; k++) dst[k] = m[k];
+}
+cudaError_t launch_prune_mask(const FeaturePlanes& fp, int nPics, const FeatureOut& sums, PruneSwitches sw, uint8_t* needed, cudaStream_t st, int* launches) {
+  const int n = nPics * fp.ctusPerPic;
+  prune_mask_kernel<<<(n + 63) / 64, 64, 0, st>>>(fp, sums, sw, needed, nPics);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_feature_hist(const FeaturePlanes& fp, int nPics, uint32_t* hist, cudaStream_t st, int* launches) {
   cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)nPics * kHistFreqs * kHistBins * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;

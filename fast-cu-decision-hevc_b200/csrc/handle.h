@@ -100,7 +100,8 @@ struct FrameSlot {
   DevBuf<uint32_t> dHist; PinBuf<uint32_t> hHist;
   DevBuf<int32_t> dThr; PinBuf<int32_t> hThr;
   cudaEvent_t evHist = nullptr, evFork = nullptr, evJoin = nullptr;
-  bool pending = false, wantFeat = false;
+  bool pending = false, wantFeat = false, pruned = false;
+  const int16_t* rec = nullptr; long long recPicStride = 0; int recStride = 0;   // pruned mode: the RMD launch happens in _end
   cudaStream_t st = nullptr, sf = nullptr;
   int nPics = 0;
   FeaturePlanes fp;
@@ -141,6 +142,9 @@ struct cucd_handle {
   int useTensor = 0;                              // cucd_set_rmd_path: 1 = predictions + Hadamard on tcgen05, 0 = integer ALU
   cucd::DevBuf<int32_t> dNum[4], dSum[4], dCtuHad;
   size_t cuCount[4] = {0, 0, 0, 0};
+  bool prune = false; cucd::PruneSwitches sw = {};   // fork-aware enumeration (cucd_set_decision_switches)
+  cucd::DevBuf<uint8_t> dNeeded;                     // [pic][ctu][341]
+  cudaEvent_t evMask = nullptr;
   std::vector<std::pair<uintptr_t, uintptr_t>> pins;   // host ranges page-locked by this handle (cucd_pin_host_buffer / auto_pin_host)
   // batch entry points (capi_batch.cu): one device block for the inputs of a call, one for its outputs; pinned staging each way for
   // small calls; pinned scratch for the job records the library builds
@@ -152,6 +156,9 @@ struct cucd_handle {
   bool refTableDirty = true;
   cucd::DevBuf<int16_t> dCur; int curStride = 0; bool curSet = false;
   cucd::DevBuf<const int16_t*> dRefPtr; cucd::DevBuf<int32_t> dRefStride;
+  // job records of the device-resident ME calls (cucd_dev_me_*): their own pinned / device blocks, guarded by events
+  cucd::PinBuf<uint8_t> hDevScratch; cucd::DevBuf<uint8_t> dDevStage;
+  cudaEvent_t evDevUp = nullptr, evDevDone = nullptr; bool devBusy = false;
 };
 
 namespace cucd {

@@ -46,6 +46,11 @@ struct FeatureOut {
 cudaError_t launch_feature_obf(const FeaturePlanes& fp, int nPics, const int32_t* thr, const FeatureOut& out, cudaStream_t st, int* launches);
 // source-only DC-less 8x8 Hadamard cost per CTU: ctuHad[pic][ctusPerPic]
 cudaError_t launch_ctu_src_had(const FeaturePlanes& fp, int nPics, int32_t* ctuHad, cudaStream_t st, int* launches);
+// Fork-aware enumeration (Testing pictures of the fork's train / verify / test schedule): which of a CTU's 341 PUs the encoder
+// would still evaluate once the per-depth Skip2Nx2N / TerminateCU switches act on the Naive model's prediction from Num_OBF
+// (TEncCu.cpp:645-675, 951-996, 1040-1079, 1140-1143, 1257-1260; tools_YS.cpp:686-695).  needed[pic][ctu][341]: 1 = evaluate.
+struct PruneSwitches { uint8_t skip2Nx2N[4], terminateCU[4]; };
+cudaError_t launch_prune_mask(const FeaturePlanes& fp, int nPics, const FeatureOut& sums, PruneSwitches sw, uint8_t* needed, cudaStream_t st, int* launches);
 // u8 -> int16 samples behind the upload of 8-bit content held as bytes (cuCUDecide_frames_u8); nSamples % 16 == 0, 16-byte aligned
 cudaError_t launch_widen_u8(const uint8_t* src, int16_t* dst, size_t nSamples, cudaStream_t st, int* launches);
 

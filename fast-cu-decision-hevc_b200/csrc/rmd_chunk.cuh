@@ -196,7 +196,11 @@ struct FrameSource {
   int W, H, ctusPerRow, ctusPerPic;
   uint32_t* out;                            // [pic][ctu][341][35], or null
   uint8_t* outPacked;                       // [pic][ctu][kPackedCtuBytes]: the packed CTU tables of include/cucudecide.h, or null
+  const uint8_t* needed;                    // [pic][ctu][341] or null: fork-aware mode, 0 = this PU is pruned by the early decisions
 };
+// per-PU state inside a chunk / CTA
+constexpr uint8_t kPuOutside = 0, kPuEvaluate = 1, kPuPruned = 2;
+constexpr uint32_t kCostOutside = 0xffffffffu, kCostPruned = 0xfffffffeu;   // table codes (include/cucudecide.h)
 
 // ---------------------------------------------------------------------------------------------
 // packed CTU cost table (include/cucudecide.h): uint32 for PUs 0..20, uint16 for the 8x8 PUs, 13-bit stream for the 4x4 PUs

@@ -29,7 +29,7 @@ __device__ __noinline__ void phase_modes(const int log2n, const int chunk, const
   const uint8_t* valid = smem + g.validOff;
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + g.accOff);
   LaneGeo lg; lg.init(g, half, lane);
-  const bool ok = valid[lg.pu] != 0;     // N = 4: the four PUs of a region share validity (W, H multiples of 8)
+  const bool ok = valid[lg.pu] == kPuEvaluate;     // N = 4: the four PUs of a region share their state (W, H multiples of 8; NxN is pruned as a whole)
   Tile src;
   if (ok) {
     Tile raw;
@@ -111,11 +111,25 @@ __device__ __forceinline__ void rmd_body(const int chunk, const FrameSource& fs,
   }
 
   // ---- phase A: validity + unfiltered linear borders --------------------------------------
+  int anyEval = 0;
   for (int p = tid; p < G::PUS; p += kRmdThreads) {
     bool ok;
     if (FRAME) { int px, py; demorton(p, px, py); ok = (ctuX + (px + 1) * N <= fs.W) && (ctuY + (py + 1) * N <= fs.H); }
     else ok = chunk * G::PUS + p < bs.count;
-    sm.valid()[p] = ok ? 1 : 0;
+    uint8_t st = ok ? kPuEvaluate : kPuOutside;
+    if (FRAME && ok && fs.needed && !fs.needed[(size_t)chunk * kPusPerCtu + pu_offset_of_depth(6 - LOG2N) + p]) st = kPuPruned;
+    sm.valid()[p] = st;
+    anyEval |= st == kPuEvaluate;
+  }
+  if (FRAME && fs.needed && !__syncthreads_or(anyEval)) {
+    // fork-aware mode: nothing to evaluate in this chunk - only the table codes are written
+    auto val = [&](int i) -> uint32_t { return sm.valid()[i / kNumModes] == kPuPruned ? kCostPruned : kCostOutside; };
+    if (fs.out) {
+      uint32_t* o = fs.out + ((size_t)chunk * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
+      for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) o[i] = val(i);
+    }
+    if (fs.outPacked) store_packed_depth<LOG2N>(fs.outPacked + (size_t)chunk * kPackedCtuBytes, tid, kRmdThreads, val);
+    return;
   }
   if (FRAME) {
     border_gather_frame<LOG2N>(tid, kRmdThreads, recPic, fs.recStride, fs.W, fs.H, ctuX, ctuY, sm.lin(), sm.flags());
@@ -147,7 +161,10 @@ __device__ __forceinline__ void rmd_body(const int chunk, const FrameSource& fs,
   // ---- phase F: coalesced cost-table store --------------------------------------------------
   const int shift = bitDepth - 8;     // xGetHADs' final DISTORTION_PRECISION_ADJUSTMENT, TComRdCost.cpp:1603
   if (FRAME) {
-    auto val = [&](int i) -> uint32_t { return sm.valid()[i / kNumModes] ? (sm.acc()[i] >> shift) : 0xffffffffu; };
+    auto val = [&](int i) -> uint32_t {
+      const uint8_t v = sm.valid()[i / kNumModes];
+      return v == kPuEvaluate ? (sm.acc()[i] >> shift) : (v == kPuPruned ? kCostPruned : kCostOutside);
+    };
     if (fs.out) {
       uint32_t* o = fs.out + ((size_t)chunk * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
       for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) o[i] = val(i);
@@ -157,7 +174,7 @@ __device__ __forceinline__ void rmd_body(const int chunk, const FrameSource& fs,
     const int first = chunk * G::PUS;
     for (int i = tid; i < G::PUS * kNumModes; i += kRmdThreads) {
       const int p = i / kNumModes, m = i - p * kNumModes;
-      if (sm.valid()[p]) bs.out[(size_t)bs.pus[first + p].outIndex * kNumModes + m] = sm.acc()[i] >> shift;
+      if (sm.valid()[p] == kPuEvaluate) bs.out[(size_t)bs.pus[first + p].outIndex * kNumModes + m] = sm.acc()[i] >> shift;
     }
   }
 }

@@ -86,6 +86,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
       : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;\n" :: "r"(grp + 1) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(mbar)) : "memory"); }
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -135,9 +136,11 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
     }
     const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
     ctuX[c] = (ctu % fs.ctusPerRow) * 64; ctuY[c] = (ctu / fs.ctusPerRow) * 64;
+    const uint8_t* need = fs.needed ? fs.needed + ((size_t)cg * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) : nullptr;
     for (int p = tid; p < C::PUS; p += kThreads) {
       int px, py; demorton(p, px, py);
-      valid[p] = ((ctuX[c] + (px + 1) * N <= fs.W) && (ctuY[c] + (py + 1) * N <= fs.H)) ? 1 : 0;
+      const bool inside = (ctuX[c] + (px + 1) * N <= fs.W) && (ctuY[c] + (py + 1) * N <= fs.H);
+      valid[p] = !inside ? kPuOutside : ((need && !need[p]) ? kPuPruned : kPuEvaluate);
     }
     stage_tile<LOG2N>(tid, kThreads, fs.rec + (size_t)pic * fs.recPicStride, fs.recStride, fs.W, fs.H, ctuX[c], ctuY[c], smem + C::TILE_OFF + c * C::TILE_BYTES);
   }
@@ -160,7 +163,7 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
 //     wait MMA2(i) | issue MMA1(i+1) | epilogue 2 of round i (costs)
 // TMEM per row group: D1 = columns [0, 64) (A2 aliases its first 16 once they have been read), D2 = [64, 128).
 template <int LOG2N, bool FRAME>
-__device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2) {
+__device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2, uint32_t& phA, uint32_t& phB) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N, SEG = RowSeg<LOG2N>::value;
   unsigned char* smem = smem2;
@@ -172,10 +175,15 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   unsigned char* sAorg = smem + C::AORG_OFF + grp * 8192;
   uint64_t* mbar1 = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + grp;
   uint64_t* mbar2 = mbar1 + kGroups;
+  // "my operands are in place" barriers (128 arrivals each).  Only the issuing warp waits on them: the other three warps of
+  // the group arrive and go straight on to their next piece of work instead of idling at a bar.sync.
+  uint64_t* arrA = mbar1 + 2 * kGroups;
+  uint64_t* arrB = mbar1 + 3 * kGroups;
+  const uint8_t* const tabWin = a.tabWin; const uint8_t* const tabN4 = a.tabN4;
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
   const FrameSource& fs = a.fs;
   const int cg = unit * C::CTUS + r.ctu;
-  const bool ok = smem[C::VALID_OFF + r.ctu * 256 + (LOG2N == 2 ? 4 * r.pu : r.pu)] != 0;   // N = 4: the region's PUs share validity (W, H multiples of 8)
+  const bool ok = smem[C::VALID_OFF + r.ctu * 256 + (LOG2N == 2 ? 4 * r.pu : r.pu)] == kPuEvaluate;   // N = 4: the region's PUs share their state (W, H multiples of 8; NxN is pruned as a whole)
   const int slot = pu_slot2<LOG2N>(r.ctu, r.pu);
 
   uint32_t p[16];                                   // the row's current byte tile: word 2*v + h = pixels (v, 4h..4h+3)
@@ -239,6 +247,8 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   const uint32_t uD1 = tmemU + grpU * 128, uA2 = uD1, uD2 = uD1 + 64;
   uint64_t* ubar1 = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + grpU;
   uint64_t* ubar2 = ubar1 + kGroups;
+  uint64_t* uarrA = ubar1 + 2 * kGroups;
+  uint64_t* uarrB = ubar1 + 3 * kGroups;
   const uint32_t idescPred = make_idesc_i8x(128, 64, 0, 0), idescHad = make_idesc_i8x(128, 64, 0, 1);
   const uint64_t dHad = make_desc(smem_u32(smem + C::HAD_OFF), 1024, 128), dHadNeg = make_desc(smem_u32(smem + C::HAD_OFF + 4096), 1024, 128);
   const uint64_t dAorg = make_desc(smem_u32(smem + C::AORG_OFF + grpU * 8192), 2048, 128);
@@ -250,10 +260,11 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   auto issue_mma2 = [&]() {
     tmem_st_wait();
     tc_fence_before();
-    group_bar(grp);
+    mbar_arrive(arrA);
     if (issuer) {
+      mbar_wait(uarrA, phA);
+      tc_fence_after();
       if (elect_one()) {
-        tc_fence_after();
         mma_i8(uD2, dAorg, dHadNeg, idescHad, 0u);
         mma_i8(uD2, dAorg + kStepA, dHadNeg + kStepB, idescHad, 1u);
         mma_i8_ts(uD2, uA2, dHad, idescHad, 1u);
@@ -262,16 +273,18 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
       }
       __syncwarp();
     }
+    phA ^= 1u;
   };
   auto wait_mma2 = [&]() { mbar_wait(mbar2, ph2); ph2 ^= 1u; tc_fence_after(); };
   // window / record operand (shared memory) x weights -> D1
   auto issue_mma1 = [&](int buf) {
     fence_async_smem();
     tc_fence_before();
-    group_bar(grp);
+    mbar_arrive(arrB);
     if (issuer) {
+      mbar_wait(uarrB, phB);
+      tc_fence_after();
       if (elect_one()) {
-        tc_fence_after();
         const uint64_t dB = dB1 + (uint64_t)((buf * C::B1_BYTES) >> 4);
         if (LOG2N == 2) {
           mma_i8(uD1, dA1, dB, idescPred, 0u);
@@ -283,6 +296,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
       }
       __syncwarp();
     }
+    phB ^= 1u;
   };
   auto wait_mma1 = [&]() { mbar_wait(mbar1, ph1); ph1 ^= 1u; tc_fence_after(); };
   // weights of round `am` from global memory (L2 resident) into registers, one round ahead of their use
@@ -290,11 +304,11 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   auto prefetch_b1 = [&](int am, int angle) {
     const int ai = am + 8;
     if (LOG2N == 2) {
-      const uint4* t = reinterpret_cast<const uint4*>(a.tabN4 + ai * 4096);
+      const uint4* t = reinterpret_cast<const uint4*>(tabN4 + ai * 4096);
       nb0 = __ldg(t + rowTid); nb1 = __ldg(t + rowTid + 128);
     } else {
       const int fc = group_frac0<LOG2N>(grp, pass, angle) >> 3;
-      nb0 = __ldg(reinterpret_cast<const uint4*>(a.tabWin + (ai * 4 + fc) * 2048) + rowTid);
+      nb0 = __ldg(reinterpret_cast<const uint4*>(tabWin + (ai * 4 + fc) * 2048) + rowTid);
     }
   };
   // operands of round `am` into buffer `buf`: weights from the prefetch registers, the row's reference window
@@ -432,10 +446,40 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   typedef Cfg<LOG2N> C;
   unsigned char* smem = smem2;
   const int tid = threadIdx.x, warp = tid >> 5;
+  if (FRAME && a.fs.needed) {
+    // fork-aware mode: a CTA none of whose PUs has to be evaluated writes the table codes and leaves
+    const FrameSource& fs = a.fs;
+    int any = 0;
+    for (int i = tid; i < C::CTUS * C::PUS; i += kThreads) {
+      const int c = i / C::PUS, p = i - c * C::PUS, cg = unit * C::CTUS + c;
+      if (cg >= a.totalCtus) continue;
+      const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
+      int px, py; demorton(p, px, py);
+      const bool inside = ((ctu % fs.ctusPerRow) * 64 + (px + 1) * C::N <= fs.W) && ((ctu / fs.ctusPerRow) * 64 + (py + 1) * C::N <= fs.H);
+      const uint8_t st = !inside ? kPuOutside : (fs.needed[(size_t)cg * kPusPerCtu + pu_offset_of_depth(6 - LOG2N) + p] ? kPuEvaluate : kPuPruned);
+      smem[C::VALID_OFF + c * 256 + p] = st;
+      any |= st == kPuEvaluate;
+    }
+    if (!__syncthreads_or(any)) {
+      for (int c = 0; c < C::CTUS; c++) {
+        const int cgc = unit * C::CTUS + c;
+        if (cgc >= a.totalCtus) break;
+        const uint8_t* valid = smem + C::VALID_OFF + c * 256;
+        auto val = [&](int i) -> uint32_t { return valid[i / kNumModes] == kPuPruned ? kCostPruned : kCostOutside; };
+        if (fs.out) {
+          uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
+          for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = val(i);
+        }
+        if (fs.outPacked) store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, val);
+      }
+      return;
+    }
+    __syncthreads();
+  }
   uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 64);
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
   if (tid == 0) {
-    for (int i = 0; i < 2 * kGroups; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + i, 1);
+    for (int i = 0; i < 4 * kGroups; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + i, i < 2 * kGroups ? 1 : 128);   // MMA done x2, operands ready x2
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   TC2_STAMP(0);
@@ -451,10 +495,10 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *tmemSlot;
-  uint32_t ph1 = 0, ph2 = 0;
+  uint32_t ph1 = 0, ph2 = 0, phA = 0, phB = 0;
   TC2_STAMP(1);
 #pragma unroll 1
-  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N, FRAME>(a, unit, pass, tmemBase, ph1, ph2);
+  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N, FRAME>(a, unit, pass, tmemBase, ph1, ph2, phA, phB);
   TC2_STAMP(2);
 
   // ---- costs leave the SM ------------------------------------------------------------------------------------
@@ -479,7 +523,10 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
     const uint8_t* valid = smem + C::VALID_OFF + c * 256;
     const uint16_t* a16 = reinterpret_cast<const uint16_t*>(acc) + c * C::PUS * kNumModes;
     const uint32_t* a32 = acc + c * C::PUS * kNumModes;
-    auto val = [&](int i) -> uint32_t { return valid[i / kNumModes] ? (LOG2N == 2 ? (uint32_t)a16[i] : a32[i]) : 0xffffffffu; };
+    auto val = [&](int i) -> uint32_t {
+      const uint8_t v = valid[i / kNumModes];
+      return v == kPuEvaluate ? (LOG2N == 2 ? (uint32_t)a16[i] : a32[i]) : (v == kPuPruned ? kCostPruned : kCostOutside);
+    };
     if (fs.out) {
       uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
 #pragma unroll 4
@@ -496,7 +543,7 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
 
 // blocks of one launch: depth-major (as rmd_frame_kernel); a depth has ceil(totalCtus / CTUS) units
 __global__ void __launch_bounds__(kThreads, 2)
-rmd_frame_tc2_kernel(const Tc2Args a) {
+rmd_frame_tc2_kernel(const __grid_constant__ Tc2Args a) {
   const int u2 = (a.totalCtus + 1) >> 1, u4 = (a.totalCtus + 3) >> 2;
   int b = blockIdx.x;
   if (b < u4) { tc2_body<6, true>(a, b); return; }
@@ -512,7 +559,7 @@ rmd_frame_tc2_kernel(const Tc2Args a) {
 // batch (S2) mode: one launch per PU size
 template <int LOG2N>
 __global__ void __launch_bounds__(kThreads, 2)
-rmd_batch_tc2_kernel(const Tc2Args a) { tc2_body<LOG2N, false>(a, blockIdx.x); }
+rmd_batch_tc2_kernel(const __grid_constant__ Tc2Args a) { tc2_body<LOG2N, false>(a, blockIdx.x); }
 
 template <int LOG2N>
 cudaError_t launch_batch_tc2(const Tc2Args& a, int units, cudaStream_t st) {

@@ -115,6 +115,9 @@ typedef struct {
  *   bytes [2940, 7420)    uint16[64][35]    PUs 21..84   (8x8: SATD <= 32 736); 0xFFFF = PU not inside the picture
  *   bytes [7420, 21980)   256*35 values of 13 bits, little-endian bit stream (value i occupies bits [13 i, 13 i + 13)
  *                         of the region): PUs 85..340 (4x4: SATD <= 8 160 for bit depths <= 10); 0x1FFF = not inside */
+#define CUCD_COST_NOT_INSIDE 0xFFFFFFFFu   /* table code: the PU does not lie inside the picture */
+#define CUCD_COST_PRUNED     0xFFFFFFFEu   /* table code: fork-aware mode (cucd_set_decision_switches) - the encoder would not evaluate this PU;
+                                            * 0xFFFE / 0x1FFE in the narrow regions of the packed table */
 #define CUCD_PACKED_WIDE_PUS 21
 #define CUCD_PACKED_U16_PUS 64
 #define CUCD_PACKED_U16_OFFSET (CUCD_PACKED_WIDE_PUS * 35 * 4)
@@ -132,6 +135,17 @@ int cuCUDecide_frames(cucd_handle* h, int nPics, const int16_t* const* orgY, int
 /* The same for callers that hold 8-bit content as bytes (the file format of 8-bit YUV; halves the upload).  bit_depth must be 8. */
 int cuCUDecide_frames_u8(cucd_handle* h, int nPics, const uint8_t* const* orgY, int strideY, const uint8_t* const* recY,
                          int strideRec, cucd_frame_out* outs);
+
+/* Fork-aware enumeration for the frame calls (cuCUDecide_frame(s)(_u8), cucd_dev_frames*).  The fork's whole point is that on
+ * Testing pictures (POC % 60 >= 3, tools_YS.cpp:1237-1242) the per-depth switches set after the verify picture
+ * (SetDecisionSwitch, tools_YS.cpp:1123-1154: g_bDecisionSwitch[depth][model][Skip2Nx2N / TerminateCU]) let the Naive model's
+ * prediction from Num_OBF (tools_YS.cpp:686-695) skip work in TEncCu::xCompressCU: Skip2Nx2N drops the 2Nx2N intra candidate of
+ * a CU with Num_OBF > 0 (TEncCu.cpp:951-996, 1040), TerminateCU stops the recursion (and NxN at depth 3) below a CU with
+ * Num_OBF == 0 (:1140-1143, 1257-1260); boundary CUs are never predicted (:488-489, 645).
+ * With enable != 0 the frame calls compute Num_OBF first and evaluate only the PUs that recursion still reaches; every other
+ * PU inside the picture holds CUCD_COST_PRUNED in all 35 modes.  The caller (the encoder's train / verify / test schedule)
+ * switches this on for Testing pictures only and passes the switches it holds; enable = 0 restores the full enumeration. */
+int cucd_set_decision_switches(cucd_handle* h, int enable, const uint8_t skip2Nx2N[4], const uint8_t terminateCU[4]);
 
 /* ------------------------------------------------------------------------------------------------
  * S2: intra rough mode decision for a batch of PUs with caller-supplied borders.
@@ -294,6 +308,11 @@ typedef struct {
 } cucd_dev_out;
 int cucd_dev_frames(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
                     const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
+/* S3 and the fractional-pel refinement with the results left in HBM: d_sad / d_cost are device pointers laid out like sadOut /
+ * cost of cucd_me_sad_surface / cucd_me_subpel_cost (pictures through cucd_set_cur_picture / cucd_set_ref_picture as there); the
+ * descriptors are host memory and are consumed before the call returns.  Enqueued on `stream`, no wait for the GPU. */
+int cucd_dev_me_sad_surface(cucd_handle* h, void* stream, int nPU, const cucd_me_desc* desc, uint32_t* d_sad);
+int cucd_dev_me_subpel_cost(cucd_handle* h, void* stream, int nPU, const cucd_subpel_desc* desc, uint32_t* d_cost);
 /* The host fit sits between the two feature passes; the split form lets a caller overlap it with GPU work of its own
  * choice - typically the next batch:   begin(i); end(i-1); begin(i+1); end(i); ...   (at most 2 batches in flight).
  * cucd_dev_frames_begin enqueues feature pass 1 and the RMD kernel and returns without waiting;

@@ -168,7 +168,8 @@ patch("Lib/TLibEncoder/TEncSlice.cpp", [
 # per-CU OBF block sums (TEncCu.cpp:589-600)
 patch("Lib/TLibEncoder/TEncCu.cpp", [
   ("\t\tuiHasOutlier = Num_OBF>0 ? 1 : 0;\n\t\tN_NonZeroFeature = Num_OBF;\n",
-   "\t\tif (!bBoundary) cucd_hook_cu(g_iPOC, uiDepth, uiLPelX, uiTPelY, BlockSize, Num_OBF, N_Outlier);\n", "after"),
+   "\t\tif (!bBoundary) cucd_hook_cu(g_iPOC, uiDepth, uiLPelX, uiTPelY, BlockSize, Num_OBF, N_Outlier);\n"
+   "\t\tcucd_hook_switches(g_iPOC, (int)g_mainModelType, g_bDecisionSwitch);\n", "after"),
 ])
 PY
 

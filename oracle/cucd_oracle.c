@@ -754,3 +754,43 @@ void oracle_subpel_surface(int bitDepth, const int16_t* org, int orgStride, int 
   for (dy = -3; dy <= 3; dy++) for (dx = -3; dx <= 3; dx++)
     out[(dy + 3) * 7 + dx + 3] = oracle_subpel_cost(bitDepth, org, orgStride, w, h, refAtZeroMv, refStride, 4 * mvx + dx, 4 * mvy + dy, useHadamard);
 }
+
+
+/* ---- fork-aware enumeration (TEST INFRASTRUCTURE like everything in this file) ---------------------------------------------------
+ * A recursive walk that mirrors TEncCu::xCompressCU for an intra slice in the Testing state:
+ *   xCompressCU(CU, depth):                                                        TEncCu.cpp
+ *     bBoundary = CU not completely inside the picture                             :488-489
+ *     if !bBoundary: Num_OBF over the CU's OBF cells                               :589-600
+ *                    Naive model: Num_OBF == 0 -> TerminateCU else Skip2Nx2N       tools_YS.cpp:686-695, TEncCu.cpp:645-675
+ *                    bEarlyTerminate / bSkip2Nx2N gated by the per-depth switches  :973-980
+ *                    intra 2Nx2N unless bSkip2Nx2N                                 :1040
+ *                    depth 3: intra NxN unless bEarlyTerminate                     :1140-1143
+ *     sub-CUs unless bEarlyTerminate (boundary CUs always recurse)                 :1257-1260, 1290-1330 */
+static int pu_index_in_ctu(int depth, int xInCtu, int yInCtu) {
+  static const int first[5] = {0, 1, 5, 21, 85};
+  const int size = 64 >> depth, px = xInCtu / size, py = yInCtu / size;
+  int z = 0, b;
+  for (b = 0; b < 4; b++) z |= ((px >> b) & 1) << (2 * b) | ((py >> b) & 1) << (2 * b + 1);
+  return first[depth] + z;
+}
+static void prune_walk(const int16_t* obf, int W, int H, const uint8_t* swSkip, const uint8_t* swTerm, int depth, int x, int y, uint8_t* ctuMask) {
+  const int size = 64 >> depth, bw = W / 4;
+  int term = 0, q;
+  if (x >= W || y >= H) return;                                  /* the recursion only enters sub-CUs whose origin is inside the picture */
+  if (x + size <= W && y + size <= H) {
+    int num = 0, cx, cy, skip;
+    for (cy = 0; cy < size / 4; cy++) for (cx = 0; cx < size / 4; cx++) if (obf[(y / 4 + cy) * bw + x / 4 + cx] > 0) num++;
+    term = swTerm[depth] && num == 0;
+    skip = swSkip[depth] && num > 0;
+    if (!skip) ctuMask[pu_index_in_ctu(depth, x & 63, y & 63)] = 1;
+    if (depth == 3 && !term) for (q = 0; q < 4; q++) ctuMask[pu_index_in_ctu(4, (x & 63) + 4 * (q & 1), (y & 63) + 4 * (q >> 1))] = 1;
+  }
+  if (depth == 3 || term) return;
+  for (q = 0; q < 4; q++) prune_walk(obf, W, H, swSkip, swTerm, depth + 1, x + (q & 1) * (size / 2), y + (q >> 1) * (size / 2), ctuMask);
+}
+void oracle_prune_mask(const int16_t* obf, int W, int H, const uint8_t* swSkip2Nx2N, const uint8_t* swTerminateCU, uint8_t* needed) {
+  const int wc = (W + 63) >> 6, hc = (H + 63) >> 6;
+  int cx, cy;
+  memset(needed, 0, (size_t)wc * hc * 341);
+  for (cy = 0; cy < hc; cy++) for (cx = 0; cx < wc; cx++) prune_walk(obf, W, H, swSkip2Nx2N, swTerminateCU, 0, cx * 64, cy * 64, needed + (size_t)(cy * wc + cx) * 341);
+}

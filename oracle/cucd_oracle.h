@@ -96,6 +96,11 @@ void oracle_intra_tu_c(int bitDepth, int n, int mode, int qp, int transformSkip,
                        const int16_t* org, int orgStride, const int16_t* border, int32_t* coef, int32_t* level, int16_t* pred, int16_t* reco,
                        uint32_t* dist, int32_t* absSum);
 
+/* ---- fork-aware enumeration: which luma RMD PUs TEncCu::xCompressCU still evaluates on a Testing picture (intra slice, default Naive
+ * model on N_OBF, tools_YS.cpp:686-695) given the per-depth switches g_bDecisionSwitch[d][model][Skip2Nx2N / TerminateCU]
+ * (TEncCu.cpp:488-489, 645-675, 951-996, 1040, 1140-1143, 1257-1260).  obf = the picture's OBF plane; needed[nCtu][341], table PU order. */
+void oracle_prune_mask(const int16_t* obf, int W, int H, const uint8_t* swSkip2Nx2N, const uint8_t* swTerminateCU, uint8_t* needed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -311,6 +311,18 @@ inline void cucd_hook_cu(int poc, int depth, int x, int y, int size, int numObf,
   fwrite(rec, 4, 7, f);
 }
 
+/* ---- the fork's per-depth decision switches as they stand while a picture is coded (g_bDecisionSwitch, set by SetDecisionSwitch
+ *      tools_YS.cpp:1123-1154 after the verify picture): one record per POC: poc, skip2Nx2N[4], terminateCU[4] ---- */
+inline void cucd_hook_switches(int poc, int mainModel, bool*** sw) {
+  static CucdDump out; static int lastPoc = -1000000;
+  FILE* f = out.get("CUCD_DUMP_SWITCHES");
+  if (!f || poc == lastPoc || !sw) return;
+  lastPoc = poc;
+  int32_t rec[9]; rec[0] = poc;
+  for (int d = 0; d < 4; d++) { rec[1 + d] = sw[d][mainModel][1] ? 1 : 0; rec[5 + d] = sw[d][mainModel][2] ? 1 : 0; }   /* DecisionType: Skip2Nx2N = 1, TerminateCU = 2 */
+  fwrite(rec, 4, 9, f); fflush(f);
+}
+
 /* ---- intra luma TU coding: prediction -> residual -> transform/quant -> inverse -> recon -> SSE ---- */
 struct CucdTuState {
   CucdDump out; long cnt, every; bool live;

@@ -217,3 +217,19 @@ def frac_records(g):
         org = g["org"][oo:oo + w * h].reshape(h, w); oo += w * h
         win = g["win"][wo:wo + (w + 9) * (h + 9)].reshape(h + 9, w + 9); wo += (w + 9) * (h + 9)
         yield dict(w=w, h=h, bd=int(bd), had=int(had), qx=int(qx), qy=int(qy), dist=int(dist) & 0xFFFFFFFF, org=org, win=win)
+
+
+def pu_table_index(x, y, n):
+    """index of the PU at picture position (x, y) of size n inside its CTU's 341-entry cost table (depth-major, z-order)"""
+    d = {64: 0, 32: 1, 16: 2, 8: 3, 4: 4}[n]
+    px, py, z = (x % 64) // n, (y % 64) // n, 0
+    for b in range(4):
+        z |= ((px >> b) & 1) << (2 * b) | ((py >> b) & 1) << (2 * b + 1)
+    return (0, 1, 5, 21, 85)[d] + z
+
+
+def oracle_prune_mask(lib, obf, W, H, skip, term):
+    obf = np.ascontiguousarray(obf, np.int16); skip = np.ascontiguousarray(skip, np.uint8); term = np.ascontiguousarray(term, np.uint8)
+    need = np.zeros((((W + 63) // 64) * ((H + 63) // 64), 341), np.uint8)
+    lib.oracle_prune_mask(C.c_void_p(obf.ctypes.data), W, H, C.c_void_p(skip.ctypes.data), C.c_void_p(term.ctypes.data), C.c_void_p(need.ctypes.data))
+    return need

@@ -207,4 +207,16 @@ int emul_store_packed_ctu(const uint32_t* cost, int nthreads, uint8_t* packed) {
   return kPackedCtuBytes;
 }
 
+
+// the kernel-side fork-aware enumeration (feature_core.cuh prune_mask_ctu) for every CTU of a picture; numObf[d] = per-depth grids of whole CUs
+int emul_prune_mask(int W, int H, const int32_t* n0, const int32_t* n1, const int32_t* n2, const int32_t* n3, const uint8_t* swSkip, const uint8_t* swTerm, uint8_t* needed) {
+  const int32_t* grids[4] = {n0, n1, n2, n3};
+  const int wc = (W + 63) / 64, hc = (H + 63) / 64;
+  for (int ctu = 0; ctu < wc * hc; ctu++) {
+    auto numObf = [&](int d, int cx, int cy) { return grids[d][(size_t)cy * (W / (64 >> d)) + cx]; };
+    prune_mask_ctu((ctu % wc) * 64, (ctu / wc) * 64, W, H, swSkip, swTerm, numObf, needed + (size_t)ctu * 341);
+  }
+  return 0;
+}
+
 }  // extern "C"

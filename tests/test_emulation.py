@@ -108,3 +108,29 @@ def test_feature_kernel_code_vs_golden(emul, cucd, clip):
     emul.emul_feature_obf(bd, P(org, i16p), W, W, H, P(thr, i32p), P(obf, i16p), P(outl, i16p))
     assert np.array_equal(obf, g["f0_obf"])
     assert np.array_equal(outl, g["f0_outlier"])
+
+
+def test_fork_aware_enumeration_kernel_code_vs_oracle_walk(emul, oracle):
+    """prune_mask_ctu (the kernel's iterative walk over per-depth Num_OBF grids) == the oracle's recursive restatement of
+    TEncCu::xCompressCU on the OBF plane, for every switch combination, on pictures with partial CTUs (1080p-like 56-row edge)"""
+    import ctypes as C
+    import itertools
+    from _util import oracle_cu_sums
+    rng = np.random.default_rng(12)
+    for W, H in ((200, 136), (256, 120), (64, 64)):
+        obf = (rng.integers(0, 16, (H // 4, W // 4)) * (rng.random((H // 4, W // 4)) < 0.08)).astype(np.int16)
+        obf[: H // 8] = 0                                             # a flat band: Num_OBF == 0 up to depth 0
+        grids = [oracle_cu_sums(oracle, obf, W, H, d)[0] for d in range(4)]
+        nctu = ((W + 63) // 64) * ((H + 63) // 64)
+        for bits in itertools.product((0, 1), repeat=4):
+            for skip, term in ((bits, (0, 0, 0, 0)), ((0, 0, 0, 0), bits), (bits, bits[::-1]), ((1, 1, 1, 1), bits)):
+                a = (C.c_uint8 * 4)(*skip); b = (C.c_uint8 * 4)(*term)
+                want = np.zeros((nctu, 341), np.uint8); got = np.full((nctu, 341), 7, np.uint8)
+                oracle.oracle_prune_mask(obf.ctypes.data_as(C.c_void_p), W, H, a, b, want.ctypes.data_as(C.c_void_p))
+                emul.emul_prune_mask(W, H, *[g.ctypes.data_as(C.c_void_p) for g in grids], a, b, got.ctypes.data_as(C.c_void_p))
+                assert np.array_equal(got, want), (W, H, skip, term)
+        # no switch on: the full enumeration of everything inside the picture
+        a = (C.c_uint8 * 4)(0, 0, 0, 0)
+        full = np.zeros((nctu, 341), np.uint8)
+        oracle.oracle_prune_mask(obf.ctypes.data_as(C.c_void_p), W, H, a, a, full.ctypes.data_as(C.c_void_p))
+        assert full.sum() > 0 and (W % 64 or H % 64 or full.all())

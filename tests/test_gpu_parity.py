@@ -488,3 +488,74 @@ def test_texture_features_vs_oracle_1080p_rows(cucd, oracle, bd):
         for a, b in zip(acts, wacts):
             assert np.array_equal(a, b)               # includes the clipped 56-row units of the last CTU row
         assert np.array_equal(avg, wavg)
+
+
+# ---- fork-aware frame mode (cucd_set_decision_switches) ------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["a8", "b8"])
+def test_fork_aware_frame_mode_vs_real_encoder_visits(cucd, oracle, name):
+    """On the Testing pictures of a real encode (fork_ai8.npz: source planes, the switches the encoder held) the pruned frame
+    call evaluates exactly the PUs the encoder's RMD loop visited, with the costs of the full enumeration; every other PU inside
+    the picture carries CUCD_COST_PRUNED.  Host-buffer call (wide and packed tables) and the device-resident begin / end call."""
+    import torch
+    from _util import oracle_prune_mask, pu_table_index
+    g = golden("fork_ai8.npz")
+    W, H, bd = [int(v) for v in g[f"{name}_meta"]]
+    pocs = [int(p) for p in g[f"{name}_pocs"]]
+    orgs = [g[f"{name}_p{p}_org"] for p in pocs]
+    recs = [pseudo_recon(o, bd) for o in orgs]
+    nctu = ((W + 63) // 64) * ((H + 63) // 64)
+    with cucd.Engine(W, H, bit_depth=bd, max_pictures=len(pocs)) as eng:
+        full = eng.frames(orgs, recs)
+        for k, poc in enumerate(pocs):
+            sk, te = g[f"{name}_p{poc}_skip"], g[f"{name}_p{poc}_term"]
+            eng.set_decision_switches(1, sk, te)
+            got = eng.frames([orgs[k]], [recs[k]])[0]
+            outp = eng.alloc_frame_out(True, packed=True, narrow=True)
+            eng.frames([orgs[k]], [recs[k]], [outp])
+            assert np.array_equal(got["obf"], g[f"{name}_p{poc}_obf"]) and np.array_equal(got["obf"], full[k]["obf"])
+            vis = np.zeros((nctu, 341), bool)
+            for x, y, n in g[f"{name}_p{poc}_visited"]:
+                vis[(int(y) // 64) * ((W + 63) // 64) + int(x) // 64, pu_table_index(int(x), int(y), int(n))] = True
+            assert np.array_equal(vis, oracle_prune_mask(oracle, got["obf"], W, H, sk, te).astype(bool))
+            inside = full[k]["rmd_cost"][:, :, 0] != cucd.COST_NOT_INSIDE
+            want = np.where(vis[:, :, None], full[k]["rmd_cost"], np.where(inside[:, :, None], np.uint32(cucd.COST_PRUNED), np.uint32(cucd.COST_NOT_INSIDE)))
+            assert np.array_equal(got["rmd_cost"], want), (name, poc)
+            assert np.array_equal(cucd.unpack_costs(outp["rmd_cost_packed"]), want)
+            assert np.array_equal(eng.unpack_costs_c(outp["rmd_cost_packed"]), want)
+            # device-resident, split call
+            dev = torch.device("cuda", 0); pitch = (W + 63) // 64 * 64
+            d_org = torch.zeros((1, H, pitch), dtype=torch.int16, device=dev); d_rec = torch.zeros_like(d_org)
+            d_org[0, :, :W] = torch.from_numpy(orgs[k]).to(dev); d_rec[0, :, :W] = torch.from_numpy(recs[k]).to(dev)
+            d_cost = torch.zeros((1, nctu, 341, 35), dtype=torch.int32, device=dev)
+            st = torch.cuda.current_stream().cuda_stream
+            eng.dev_frames(st, 1, d_org.data_ptr(), H * pitch, pitch, d_rec.data_ptr(), H * pitch, pitch, {"rmd_cost": d_cost.data_ptr()}, begin_only=True)
+            eng.dev_frames_end()
+            torch.cuda.synchronize()
+            assert np.array_equal(d_cost[0].cpu().numpy().view(np.uint32), want)
+            eng.set_decision_switches(0)
+        again = eng.frames(orgs, recs)
+        assert all(np.array_equal(a["rmd_cost"], b["rmd_cost"]) for a, b in zip(again, full))
+
+
+@pytest.mark.parametrize("bd,path", [(8, 1), (8, 0), (10, 0)])
+def test_fork_aware_frame_mode_all_switch_patterns(cucd, oracle, bd, path):
+    """every Skip2Nx2N / TerminateCU pattern on a picture with flat and textured regions and partial CTUs, tensor-core and ALU kernels"""
+    import itertools
+    from _util import oracle_prune_mask
+    W, H = 328, 200
+    org = textured_plane(W, H, bd, seed=51)
+    org[:72, :] = 100 << (bd - 8)                        # flat: Num_OBF == 0 there
+    org[:, 200:264] = 60 << (bd - 8)
+    rec = pseudo_recon(org, bd)
+    with cucd.Engine(W, H, bit_depth=bd) as eng:
+        eng.set_rmd_path(path)
+        full = eng.frame(org, rec)
+        inside = full["rmd_cost"][:, :, 0] != cucd.COST_NOT_INSIDE
+        for i, bits in enumerate(itertools.product((0, 1), repeat=4)):
+            sk, te = bits, bits[::-1] if i % 2 else (1, 1, 1, 1)
+            eng.set_decision_switches(1, sk, te)
+            got = eng.frame(org, rec)
+            need = oracle_prune_mask(oracle, full["obf"], W, H, sk, te).astype(bool)
+            want = np.where(need[:, :, None], full["rmd_cost"], np.where(inside[:, :, None], np.uint32(cucd.COST_PRUNED), np.uint32(cucd.COST_NOT_INSIDE)))
+            assert np.array_equal(got["rmd_cost"], want), (sk, te)
+            assert np.array_equal(got["obf"], full["obf"]) and np.array_equal(got["num_obf2"], full["num_obf2"])
