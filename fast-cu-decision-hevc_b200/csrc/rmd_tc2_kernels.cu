@@ -312,10 +312,13 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     }
   };
   // operands of round `am` into buffer `buf`: weights from the prefetch registers, the row's reference window
-  auto stage = [&](int am, int angle, int buf) {
+  auto stage_weights = [&](int buf) {
     uint4* b = reinterpret_cast<uint4*>(sB1 + buf * C::B1_BYTES);
     b[rowTid] = nb0;
-    if (LOG2N == 2) { b[rowTid + 128] = nb1; return; }
+    if (LOG2N == 2) b[rowTid + 128] = nb1;
+  };
+  auto stage_window = [&](int am, int angle, int buf) {
+    if (LOG2N == 2) return;
     const int filt = mode_uses_filtered<LOG2N>(26 + am) ? 1 : 0;
     uint32_t w8[8];
     gather_window(store, arr_k0_off<LOG2N>(grp, slot, r.o, filt) + win_k0(angle, r.u0, r.v0), w8);
@@ -388,7 +391,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   // ---- round 0 -------------------------------------------------------------------------------------------------
   tmem_st16(tA2 + laneOff, p);
   issue_mma2();
-  stage(8, 32, 0);
+  stage_weights(0); stage_window(8, 32, 0);
   prefetch_b1(7, 26);
   wait_mma2();
   issue_mma1(0);
@@ -419,18 +422,24 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     }
     tmem_st16(tA2 + laneOff, p);
     TC2_FINE(2);
-    if (LOG2N != 2 && am > -8 && angleNext < 0)     // the gathers of round am are done (barrier of its MMA 1)
-      build_ext_group<LOG2N>(rowTid, grp, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
+    // Projected samples of the next (negative) angle.  The gathers of round am have all finished: MMA 1 of this round was only
+    // issued after every row of the group had announced its window (arrB).  The OTHER rows' projected samples are complete once
+    // MMA 2 below has been issued (every row announces arrA after this point), i.e. after wait_mma2: a window that may read
+    // them is gathered there, one that cannot (angle >= 0) right away, under the MMA.
+    const bool lateWindow = LOG2N != 2 && am > -8 && angleNext < 0;
+    if (lateWindow) build_ext_group<LOG2N>(rowTid, grp, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
     TC2_FINE(3);
     issue_mma2();
     TC2_FINE(4);
     if (am > -8) {
-      stage(am - 1, angleNext, buf ^ 1);
+      stage_weights(buf ^ 1);
+      if (!lateWindow) stage_window(am - 1, angleNext, buf ^ 1);
       if (am > -7) prefetch_b1(am - 2, angleNext2);
     }
     TC2_FINE(5);
     wait_mma2();
     TC2_FINE(6);
+    if (lateWindow) stage_window(am - 1, angleNext, buf ^ 1);
     if (am > -8) issue_mma1(buf ^ 1);
     TC2_FINE(7);
     cost_out(r.o ? 10 - am : 26 + am, !(r.o && am == -8));

@@ -212,7 +212,7 @@ $(OUT)/TAppEncoder: $(BASE_O) $(ENC_O) $(APP_O)
 $(OUT)/TAppDecoder: $(BASE_O) $(DEC_O)
 	$(CXX) -o $@ $^ -lm
 $(OUT)/TAppEncoderCucd: $(BASE_O) $(INT_O) $(PKGDIR)/libcucudecide.so
-	$(CXX) -o $@ $(BASE_O) $(INT_O) -L$(PKGDIR) -lcucudecide -Wl,-rpath,'$$ORIGIN/../../fast-cu-decision-hevc_b200' -lm -lpthread
+	$(CXX) -o $@ $(BASE_O) $(INT_O) -L$(PKGDIR) -lcucudecide -Wl,-rpath,'$$ORIGIN/../../fast-cu-decision-hevc_b200' -lm -lpthread -lrt
 $(OUT)/libhmref.so: $(BASE_O) $(ENC_O) $(APP_LIB_O) $(OBJ)/hmref_driver.cpp.o
 	$(CXX) -shared -o $@ $^ -lm -lpthread
 EOF

@@ -37,15 +37,36 @@ inline void cucd_w32(FILE* f, int32_t v) { fwrite(&v, 4, 1, f); }
 #ifdef CUCD_INTEGRATION
 #include <vector>
 #include "cucudecide.h"
-struct CucdShim { cucd_handle* h; int W, H, bd, strong; uint32_t sad[35]; long rmdCalls, frameCalls, tmvCalls; bool curForTmv; };
-inline CucdShim& cucd_shim() { static CucdShim s = {0, 0, 0, 0, 0, {0}, 0, 0, 0, false}; return s; }
+#include "cucd_ipc.h"
+struct CucdShim { cucd_handle* h; int W, H, bd, strong; uint32_t sad[35]; long rmdCalls, frameCalls, tmvCalls; bool curForTmv; bool ipcOpen; };
+inline CucdShim& cucd_shim() { static CucdShim s = {0, 0, 0, 0, 0, {0}, 0, 0, 0, false, false}; return s; }
+/* Server mode (CUCD_SERVER=<shared-memory name>): this encoder instance is one of several processes whose requests cucd_server
+ * coalesces (include/cucd_ipc.h); the instance itself never touches CUDA.  Otherwise the library is called in-process. */
+inline cucd_ipc_client& cucd_ipc() { static cucd_ipc_client c; return c; }
+inline bool cucd_ipc_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("CUCD_SERVER");
+    mode = (e && *e) ? 1 : 0;
+    if (mode && cucd_ipc().connect(e) != CUCD_OK) { fprintf(stderr, "cucd shim: cannot reach cucd_server: %s\n", cucd_ipc().err); exit(1); }
+  }
+  return mode == 1;
+}
+inline bool cucd_shim_ready() { return cucd_shim().h != 0 || cucd_shim().ipcOpen; }
 inline void cucd_shim_die(const char* what) {   /* HM convention: fatal error -> exit(1) (CommonDef.h:141-164) */
-  fprintf(stderr, "cucd shim: %s failed: %s\n", what, cucd_last_error(cucd_shim().h));
+  fprintf(stderr, "cucd shim: %s failed: %s\n", what, cucd_ipc_mode() ? cucd_ipc().err : cucd_last_error(cucd_shim().h));
   exit(1);
 }
 /* S0: TEncTop::create would do this once; the shim opens lazily at the first picture */
 inline void cucd_shim_open(int W, int H, int bd, int strong) {
   CucdShim& s = cucd_shim();
+  if (cucd_ipc_mode()) {
+    if (!s.ipcOpen || s.W != W || s.H != H || s.bd != bd || s.strong != strong) {
+      if (cucd_ipc().open(W, H, bd, strong) != CUCD_OK) cucd_shim_die("cucd_server OPEN");
+      s.W = W; s.H = H; s.bd = bd; s.strong = strong; s.ipcOpen = true;
+    }
+    return;
+  }
   if (s.h && (s.W != W || s.H != H || s.bd != bd || s.strong != strong)) { cucd_destroy(s.h); s.h = 0; }
   if (!s.h) {
     cucd_config cfg = {W, H, bd, 64, 4, strong, 0, 1, 0};
@@ -59,11 +80,15 @@ inline void cucd_shim_outlier(int W, int H, int bd, int strong, const short* org
   cucd_shim_open(W, H, bd, strong);
   CucdShim& s = cucd_shim();
   std::vector<int16_t> o((size_t)(W / 4) * (H / 4)), t((size_t)W * H);
-  cucd_frame_out fo; memset(&fo, 0, sizeof fo);
-  fo.obf = o.data(); fo.outlier = t.data();
-  if (cuCUDecide_frame(s.h, org, orgStride, 0, 0, 0, &fo) != CUCD_OK) cucd_shim_die("cuCUDecide_frame");
-  if (cucd_set_cur_picture(s.h, org, orgStride) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");   /* a12 check + S3 of this picture */
-  s.curForTmv = true;
+  if (cucd_ipc_mode()) {
+    if (cucd_ipc().frame(W, H, org, orgStride, o.data(), t.data()) != CUCD_OK) cucd_shim_die("cucd_server FRAME");
+  } else {
+    cucd_frame_out fo; memset(&fo, 0, sizeof fo);
+    fo.obf = o.data(); fo.outlier = t.data();
+    if (cuCUDecide_frame(s.h, org, orgStride, 0, 0, 0, &fo) != CUCD_OK) cucd_shim_die("cuCUDecide_frame");
+    if (cucd_set_cur_picture(s.h, org, orgStride) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");   /* a12 check + S3 of this picture */
+    s.curForTmv = true;
+  }
   for (int r = 0; r < H / 4; r++) memcpy(obf + (size_t)r * obfStride, &o[(size_t)r * (W / 4)], (W / 4) * sizeof(short));
   for (int r = 0; r < H; r++) memcpy(outl + (size_t)r * outlStride, &t[(size_t)r * W], W * sizeof(short));
   s.frameCalls++;
@@ -78,7 +103,8 @@ inline void cucd_shim_rmd(int n, const short* unfExt, const short* org, int orgS
   for (int r = 0; r < n; r++) memcpy(blk + r * n, org + (size_t)r * orgStride, n * sizeof(short));
   int lg = 0; while ((1 << lg) < n) lg++;
   cucd_pu_desc d = {(uint8_t)lg, {0, 0, 0}};
-  if (cucd_intra_rmd_batch(s.h, 1, &d, blk, border, s.sad) != CUCD_OK) cucd_shim_die("cucd_intra_rmd_batch");
+  if ((cucd_ipc_mode() ? cucd_ipc().intra_rmd_batch(1, &d, blk, border, s.sad) : cucd_intra_rmd_batch(s.h, 1, &d, blk, border, s.sad)) != CUCD_OK)
+    cucd_shim_die("cucd_intra_rmd_batch");
   s.rmdCalls++;
 }
 inline unsigned cucd_shim_rmd_sad(int mode) { return cucd_shim().sad[mode]; }
@@ -101,14 +127,15 @@ inline void cucd_shim_me_begin(int W, int H, int bd, int strong, int curPoc, con
   cucd_shim_open(W, H, bd, strong);
   CucdShim& s = cucd_shim(); CucdMeShim& m = cucd_me_shim();
   if (curPoc != m.curPoc) {
-    if (cucd_set_cur_picture(s.h, orgY, orgStride) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");
+    if ((cucd_ipc_mode() ? cucd_ipc().set_cur_picture(W, H, orgY, orgStride) : cucd_set_cur_picture(s.h, orgY, orgStride)) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");
     m.curPoc = curPoc; m.nRefs = 0;
   }
   int slot = -1;
   for (int i = 0; i < m.nRefs; i++) if (m.refKey[i] == refKey) slot = i;
   if (slot < 0) {
     slot = m.nRefs++; m.refKey[slot] = refKey;
-    if (cucd_set_ref_picture(s.h, slot, refY, refStride, marginX, marginY) != CUCD_OK) cucd_shim_die("cucd_set_ref_picture");
+    if ((cucd_ipc_mode() ? cucd_ipc().set_ref_picture(W, H, slot, refY, refStride, marginX, marginY) : cucd_set_ref_picture(s.h, slot, refY, refStride, marginX, marginY)) != CUCD_OK)
+      cucd_shim_die("cucd_set_ref_picture");
   }
   m.d.x = puX; m.d.y = puY; m.d.w = w; m.d.h = h; m.d.ref_idx = slot; m.d.sub_shift = subShift;
   m.minX = -(64 + 8 + cuX - 1); m.maxX = W + 8 - cuX - 1;          /* TComDataCU::clipMv, TComDataCU.cpp:2946-2958, in integer pels */
@@ -128,7 +155,7 @@ inline unsigned cucd_shim_me_sad(int x, int y) {
   std::map<long, std::vector<uint32_t> >::iterator it = m.tiles.find(key);
   if (it == m.tiles.end()) {
     std::vector<uint32_t> surf((size_t)(d.right - d.left + 1) * (d.bottom - d.top + 1));
-    if (cucd_me_sad_surface(s.h, 1, &d, surf.data()) != CUCD_OK) cucd_shim_die("cucd_me_sad_surface");
+    if ((cucd_ipc_mode() ? cucd_ipc().me_sad_surface(1, &d, surf.data()) : cucd_me_sad_surface(s.h, 1, &d, surf.data())) != CUCD_OK) cucd_shim_die("cucd_me_sad_surface");
     it = m.tiles.insert(std::make_pair(key, std::vector<uint32_t>())).first;
     it->second.swap(surf);
     m.tilesComputed++;
@@ -144,9 +171,9 @@ inline bool cucd_shim_frac_active() { return cucd_frac_shim().active; }
 inline void cucd_shim_frac_begin(int biPred, int mvx, int mvy, int useHadamard) {
   CucdFracShim& f = cucd_frac_shim(); CucdMeShim& m = cucd_me_shim();
   f.active = false;
-  if (biPred || !cucd_shim().h || m.pus == 0) return;          /* the PU / reference of the integer search that just ended */
+  if (biPred || !cucd_shim_ready() || m.pus == 0) return;          /* the PU / reference of the integer search that just ended */
   cucd_subpel_desc d = {m.d.x, m.d.y, m.d.w, m.d.h, m.d.ref_idx, mvx, mvy, useHadamard};
-  if (cucd_me_subpel_cost(cucd_shim().h, 1, &d, f.cost) != CUCD_OK) cucd_shim_die("cucd_me_subpel_cost");
+  if ((cucd_ipc_mode() ? cucd_ipc().me_subpel_cost(1, &d, f.cost) : cucd_me_subpel_cost(cucd_shim().h, 1, &d, f.cost)) != CUCD_OK) cucd_shim_die("cucd_me_subpel_cost");
   f.active = true; f.calls++;
 }
 inline void cucd_shim_frac_end() { cucd_frac_shim().active = false; }
@@ -214,7 +241,9 @@ inline void cucd_shim_tmv_check(int x, int y, int size, const double* ref130) {
   if (memcmp(got, ref130, sizeof got) != 0) { fprintf(stderr, "cucd shim: TMV features of the %dx%d CU at (%d,%d) differ from the reference\n", size, size, x, y); exit(1); }
   s.tmvCalls++;
 }
-struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim(); if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim();
+  if (s.ipcOpen) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, through cucd_server\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls); cucd_ipc().close_client(); }
+  if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;
 #endif
 
