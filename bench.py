@@ -340,8 +340,16 @@ def run_ours(args, rank, world, local_rank):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     cucd = importlib.import_module(PKG)
+    no_gpu = "bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)"
+    if not os.path.exists("/dev/nvidiactl") and not torch.cuda.is_available():      # a GPU-less box fails at once; on a GPU box CUDA is first touched below
+        raise SystemExit(no_gpu)
+    # The CPU baseline forks worker processes (the reference's feature pass is not re-entrant): it runs BEFORE this process creates
+    # its CUDA context, page-locked buffers and worker threads - a fork after that is not safe.
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.fork_aware:
+        _, cpu_baseline = cpu_reference_run(args, steps=3, warmup=1, target_step_s=3.0)
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+        raise SystemExit(no_gpu)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank)
@@ -517,10 +525,6 @@ def run_ours(args, rank, world, local_rank):
                 "note": "launch_ms is the CUDA-event window around the RMD launch on the caller's stream; the small feature kernels run beside it on a high-priority stream and take part of that window. RMD is compute bound by construction (~140 int-op/B, SURVEY.md 8d): predictions and Hadamard run on tcgen05 (kind::i8), "
                         "the epilogues on the integer ALU; the HBM fraction is small; see profiles/ for pipe utilisation"}
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.fork_aware:
-        _, cpu_baseline = cpu_reference_run(args, steps=3, warmup=1, target_step_s=3.0)
-
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -555,8 +559,14 @@ def run_inter(args, rank, world, local_rank):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     cucd = importlib.import_module(PKG)
+    no_gpu = "bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)"
+    if not os.path.exists("/dev/nvidiactl") and not torch.cuda.is_available():      # a GPU-less box fails at once; on a GPU box CUDA is first touched below
+        raise SystemExit(no_gpu)
+    cpu_baseline = None                     # before the CUDA context exists (the CPU arm forks)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, cpu_baseline = cpu_reference_run(args, steps=2, warmup=1)
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+        raise SystemExit(no_gpu)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank)
@@ -700,9 +710,6 @@ def run_inter(args, rank, world, local_rank):
                 "note": "the dominant launch of an inter step: one SAD surface launch per reference (CUDA events on the launching stream around the "
                         "call; includes the upload of its job records).  Algorithmic bytes per PU = source + reference window + surface (SURVEY.md 8d); "
                         f"the work is {(2 * ME_RANGE + 1) ** 2} candidates x w x h absolute differences per PU: integer-ALU bound (VABSDIFF4), see profiles/"}
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, cpu_baseline = cpu_reference_run(args, steps=2, warmup=1)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "CTU/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -6,7 +6,9 @@ each on a 1080p-sized workload, and prints ONE JSON line per row:
   kernel   throughput from the device time between the first and last kernel of the call (cucd_last_kernel_time: CUDA events
            on the library's stream, copies outside) and the HBM roofline fraction of that time for the row's ALGORITHMIC bytes
            (every input read once, every output written once; DESIGN.md section 4 states the per-unit figures)
-  e2e      the same call through the C ABI with host buffers, wall clock (pageable numpy buffers, copies inside)
+  e2e      the same C-ABI call with host buffers, wall clock around the bare call (descriptor arrays prebuilt, copies inside): the caller's
+           buffers page-locked once through cucd_pin_host_buffer (what an encoder does with its long-lived buffers); e2e_pageable: the same
+           buffers before they were pinned.  h2d_bytes / d2h_bytes let the reader subtract the PCIe time
   cpu      the reference's own function (oracle/_ref/libhmref.so, kind "reference") or the oracle port (kind "port") on a
            bounded sample, on `cores` host threads
 Rows: s2 (cucd_intra_rmd_batch), f1 (cucd_queue_*: K concurrent instances), s3 (cucd_me_sad_surface), f3 (cucd_me_subpel_cost),
@@ -39,9 +41,17 @@ def hbm_peak():
         return 7700.0, "fallback (B200_PROFILING.md nominal)"
 
 
-def timed(fn, eng, iters):
+def timed(fn, eng, iters, pin=()):
+    """returns (kernel s, call s with the buffers in `pin` page-locked, call s with pageable buffers)"""
     fn()                                     # warm-up (allocations inside the handle)
     fn()
+    ps = []
+    for _ in range(max(2, iters // 2)):
+        t0 = time.perf_counter()
+        fn()
+        ps.append(time.perf_counter() - t0)
+    for a in pin:
+        eng.pin_host_buffer(a)
     fn()
     ks, ws = [], []
     for _ in range(iters):
@@ -49,7 +59,9 @@ def timed(fn, eng, iters):
         fn()
         ws.append(time.perf_counter() - t0)
         ks.append(eng.last_kernel_time_ms() * 1e-3)
-    return float(np.median(ks)), float(np.median(ws))
+    for a in pin:
+        eng.unpin_host_buffer(a)
+    return float(np.median(ks)), float(np.median(ws)), float(np.median(ps))
 
 
 def cpu_parallel(work, n_items, threads):
@@ -60,13 +72,14 @@ def cpu_parallel(work, n_items, threads):
     return time.perf_counter() - t0
 
 
-def emit(row, unit, units, k_s, w_s, algo_bytes, cpu, extra=None):
+def emit(row, unit, units, k_s, w_s, algo_bytes, cpu, extra=None, p_s=None, h2d=None, d2h=None):
     peak, src = hbm_peak()
     gbs = algo_bytes / k_s / 1e9
     d = {"row": row, "unit": unit, "units_per_call": units,
          "kernel": {"value": units / k_s, "ms": k_s * 1e3, "algorithmic_bytes": algo_bytes, "achieved_gbs": gbs, "hbm_peak_gbs": peak,
                     "frac": gbs / peak, "peak_source": src},
-         "e2e": {"value": units / w_s, "ms": w_s * 1e3},
+         "e2e": {"value": units / w_s, "ms": w_s * 1e3, "call_over_kernel": w_s / k_s, "h2d_bytes": h2d, "d2h_bytes": d2h},
+         "e2e_pageable": None if p_s is None else {"value": units / p_s, "ms": p_s * 1e3},
          "cpu": cpu}
     if extra:
         d.update(extra)
@@ -95,8 +108,10 @@ def main():
         orgs.append(rng.integers(0, 256, cnt * n * n).astype(np.int16))
         brds.append(rng.integers(0, 256, cnt * (4 * n + 1)).astype(np.int16))
     o, b = np.concatenate(orgs), np.concatenate(brds)
-    k_s, w_s = timed(lambda: eng.intra_rmd_batch(sizes, o, b), eng, a.iters)
     n_pu = len(sizes)
+    pu_arr, _ = cucd.Engine.pu_descs(sizes)
+    sad_out = np.zeros((n_pu, 35), np.uint32)
+    k_s, w_s, p_s = timed(lambda: eng.intra_rmd_batch_raw(pu_arr, n_pu, o, b, sad_out), eng, a.iters, pin=(o, b, sad_out))
     algo = o.nbytes + b.nbytes + n_pu * 35 * 4
     # CPU: the reference's own prediction + Hadamard functions per PU
     samp = list(range(0, n_pu, 97))
@@ -110,7 +125,8 @@ def main():
         fn(8, n, 1, C.c_void_p(o.ctypes.data + 2 * int(off_o[j])), n, C.c_void_p(b.ctypes.data + 2 * int(off_b[j])), P(out, u32p))
     sec = cpu_parallel(work_s2, len(samp), T)
     emit("s2_intra_rmd_batch", "PU/s", n_pu, k_s, w_s, algo,
-         {"value": len(samp) / sec, "unit": "PU/s", "cores": T, "kind": kind, "sample": f"every 97th PU of the batch ({len(samp)} PUs, same size mix) in {sec:.2f} s"})
+         {"value": len(samp) / sec, "unit": "PU/s", "cores": T, "kind": kind, "sample": f"every 97th PU of the batch ({len(samp)} PUs, same size mix) in {sec:.2f} s"},
+         p_s=p_s, h2d=int(o.nbytes + b.nbytes + n_pu * 16), d2h=int(sad_out.nbytes))
 
     # ---- f1: the coalescing queue: K encoder instances (host threads), each submitting one CU's worth of PUs per request and waiting
     #      for it (the live encoder's serial dependency), for K = 1, 4, 16: what coalescing buys over one-request-per-launch ----------------
@@ -132,8 +148,10 @@ def main():
     eng.set_cur_picture(org); eng.set_ref_picture(0, refp, pad, pad)
     descs = [dict(x=x, y=y, w=32, h=32, ref_idx=0, left=-32, right=32, top=-32, bottom=32, sub_shift=1)
              for y in range(0, H - 31, 32) for x in range(0, W - 31, 32)]
-    k_s, w_s = timed(lambda: eng.me_sad_surface(descs), eng, a.iters)
     n_pu = len(descs)
+    me_arr, _, me_total = cucd.Engine.me_descs(descs)
+    surf = np.zeros(me_total, np.uint32)
+    k_s, w_s, p_s = timed(lambda: eng.me_sad_surface_raw(me_arr, n_pu, surf), eng, a.iters, pin=(surf,))
     algo = n_pu * (32 * 32 * 2 + 96 * 96 * 2 + 65 * 65 * 4)
     samp = descs[::40]
     Wp = W + 2 * pad
@@ -149,11 +167,13 @@ def main():
     emit("s3_me_sad_surface", "candidate SAD/s", n_pu * 65 * 65, k_s, w_s, algo,
          {"value": len(samp) * 65 * 65 / sec, "unit": "candidate SAD/s", "cores": T, "kind": kind,
           "sample": f"{len(samp)} of the {n_pu} PUs (32x32, 65x65 window, iSubShift 1) in {sec:.2f} s"},
-         {"pus_per_call": n_pu})
+         {"pus_per_call": n_pu}, p_s=p_s, h2d=int(n_pu * 40), d2h=int(surf.nbytes))
 
     # ---- f3: fractional-pel refinement of the same PUs around a pseudo-random integer MV, Hadamard -------------------------------------------
     sdescs = [dict(x=d["x"], y=d["y"], w=32, h=32, ref_idx=0, mvx=int(rng.integers(-16, 17)), mvy=int(rng.integers(-16, 17)), use_hadamard=1) for d in descs]
-    k_s, w_s = timed(lambda: eng.me_subpel_cost(sdescs), eng, a.iters)
+    sp_arr, _ = cucd.Engine.subpel_descs(sdescs)
+    sp_out = np.zeros((len(sdescs), 49), np.uint32)
+    k_s, w_s, p_s = timed(lambda: eng.me_subpel_cost_raw(sp_arr, len(sdescs), sp_out), eng, a.iters, pin=(sp_out,))
     algo = len(sdescs) * (32 * 32 * 2 + 41 * 41 * 2 + 49 * 4)
     samp = sdescs[::40]
 
@@ -166,11 +186,12 @@ def main():
     sec = cpu_parallel(work_f3, len(samp), T)
     emit("f3_me_subpel_cost", "PU refinement/s", len(sdescs), k_s, w_s, algo,
          {"value": len(samp) / sec, "unit": "PU refinement/s", "cores": T, "kind": "port",
-          "sample": f"{len(samp)} of the {len(sdescs)} PUs (32x32, 49 quarter-pel positions, Hadamard) through the oracle in {sec:.2f} s"})
+          "sample": f"{len(samp)} of the {len(sdescs)} PUs (32x32, 49 quarter-pel positions, Hadamard) through the oracle in {sec:.2f} s"},
+         p_s=p_s, h2d=int(len(sdescs) * 32), d2h=int(sp_out.nbytes))
 
     # ---- a12: TMV features of every whole CU of the picture (depths 0..3) -------------------------------------------------------
     cus = _util.all_cus(W, H)
-    k_s, w_s = timed(lambda: eng.tmv_features(cus), eng, a.iters)
+    k_s, w_s, _ = timed(lambda: eng.tmv_features(cus), eng, a.iters)
     algo = sum((1 << (2 * l)) * 2 + 130 * 8 for _, _, l in cus)
     samp = cus[::61]
 
@@ -186,7 +207,7 @@ def main():
          {"value": len(samp) / sec, "unit": "CU/s", "cores": 1, "kind": kind, "sample": f"every 61st CU ({len(samp)}) in {sec:.2f} s (driver copies the plane per call)"})
 
     # ---- a13: AQ activity, 4 layers ------------------------------------------------------------------------------------------------
-    k_s, w_s = timed(lambda: eng.aq_activity(4), eng, a.iters)
+    k_s, w_s, _ = timed(lambda: eng.aq_activity(4), eng, a.iters)
     units = sum(((W + (64 >> d) - 1) // (64 >> d)) * ((H + (64 >> d) - 1) // (64 >> d)) for d in range(4))
     algo = 4 * W * H * 2 + units * 8
     t0 = time.perf_counter()
@@ -208,11 +229,12 @@ def main():
     b = np.resize(o, nb).astype(np.int16)            # borders drawn from the picture's own samples
     n_tu = len(tus)
     samples = o.size
-    for name, call, out_bytes in (("f2_intra_tu_code", lambda: eng.intra_tu_code(tus, o, b), samples * 6 + n_tu * 8),
-                                  ("f2_intra_tu_forward", lambda: eng.intra_tu_forward(tus, o, b), samples * 6),
-                                  ):
-        k_s, w_s = timed(call, eng, a.iters)
-        algo = o.nbytes + b.nbytes + out_bytes
+    _, tu_arr, _ = cucd.Engine._tu_descs(tus)
+    coef = np.zeros(samples, np.int32); pix = np.zeros(samples, np.int16); dist = np.zeros(n_tu, np.uint32); asum = np.zeros(n_tu, np.int32)
+    pins = (o, b, coef, pix, dist, asum)
+    for name, stage, out_bytes in (("f2_intra_tu_forward", 0, samples * 6), ("f2_intra_tu_code", 1, samples * 6 + n_tu * 8), ("f2_intra_tu_recon", 2, samples * 2 + n_tu * 4)):
+        k_s, w_s, p_s = timed(lambda: eng.intra_tu_raw(stage, tu_arr, n_tu, o, b, coef, pix, dist, asum), eng, a.iters, pin=pins)
+        algo = o.nbytes + b.nbytes + out_bytes + (samples * 4 if stage == 2 else 0)
         cpu = None
         if name == "f2_intra_tu_code":
             samp = list(range(0, n_tu, 53))
@@ -224,10 +246,8 @@ def main():
             sec = cpu_parallel(work_tu, len(samp), T)
             cpu = {"value": len(samp) / sec, "unit": "TU/s", "cores": T, "kind": "port",
                    "sample": f"every 53rd TU ({len(samp)}, same size mix) through the oracle's matrix-form chain in {sec:.2f} s"}
-        emit(name, "TU/s", n_tu, k_s, w_s, algo, cpu, {"luma_samples_per_call": int(samples)})
-    level, reco, dist, _ = eng.intra_tu_code(tus, o, b)
-    k_s, w_s = timed(lambda: eng.intra_tu_recon(tus, o, b, level), eng, a.iters)
-    emit("f2_intra_tu_recon", "TU/s", n_tu, k_s, w_s, o.nbytes + b.nbytes + samples * 6 + n_tu * 4, None, {"luma_samples_per_call": int(samples)})
+        emit(name, "TU/s", n_tu, k_s, w_s, algo, cpu, {"luma_samples_per_call": int(samples)}, p_s=p_s,
+             h2d=int(o.nbytes + b.nbytes + n_tu * 16 + (samples * 4 if stage == 2 else 0)), d2h=int(out_bytes))
     eng.close()
 
 

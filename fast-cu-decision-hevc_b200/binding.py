@@ -353,6 +353,29 @@ class Engine:
         self._check(self.lib.cucd_intra_rmd_batch(self.h, n, desc, org.ctypes.data, border.ctypes.data, sad.ctypes.data), "cucd_intra_rmd_batch")
         return sad
 
+    @staticmethod
+    def pu_descs(log2_sizes):
+        """ctypes descriptor array for cucd_intra_rmd_batch (build once, reuse): (array, n)"""
+        log2_sizes = np.asarray(log2_sizes, np.uint8)
+        desc = (_PuDesc * max(int(log2_sizes.size), 1))()
+        np.frombuffer(desc, np.uint8)[: 4 * log2_sizes.size: 4] = log2_sizes
+        return desc, int(log2_sizes.size)
+
+    def intra_rmd_batch_raw(self, desc, n, org, border, sad):
+        """the bare C call on prebuilt descriptors and caller-owned numpy buffers (what an encoder's own call costs)"""
+        self._check(self.lib.cucd_intra_rmd_batch(self.h, n, desc, org.ctypes.data, border.ctypes.data, sad.ctypes.data), "cucd_intra_rmd_batch")
+
+    def intra_tu_raw(self, stage, arr, n, org, border, coef_or_level, pix, dist, abs_sum, flags=TU_INTRA_SLICE | TU_SIGN_HIDING):
+        """stage 0: cucd_intra_tu_forward (coef out, pix = pred), 1: cucd_intra_tu_code, 2: cucd_intra_tu_recon (level in) on prebuilt descriptors"""
+        if stage == 0:
+            rc = self.lib.cucd_intra_tu_forward(self.h, n, arr, org.ctypes.data, border.ctypes.data, coef_or_level.ctypes.data, pix.ctypes.data)
+        elif stage == 1:
+            rc = self.lib.cucd_intra_tu_code(self.h, n, arr, org.ctypes.data, border.ctypes.data, int(flags), coef_or_level.ctypes.data, pix.ctypes.data,
+                                             dist.ctypes.data, abs_sum.ctypes.data)
+        else:
+            rc = self.lib.cucd_intra_tu_recon(self.h, n, arr, org.ctypes.data, border.ctypes.data, coef_or_level.ctypes.data, pix.ctypes.data, dist.ctypes.data)
+        self._check(rc, "cucd_intra_tu_*")
+
     # ---- S3 ---------------------------------------------------------------------------------------
     def set_ref_picture(self, ref_idx, padded, margin_x, margin_y):
         """padded: (H+2my, W+2mx) int16 plane including the replicated margins."""

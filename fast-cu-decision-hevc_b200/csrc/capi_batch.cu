@@ -118,7 +118,11 @@ int rmd_batch_core(cucd_handle* h, int nPU, const cucd_pu_desc* desc, const int3
     if (!count[l]) continue;
     BatchSource bs;
     bs.org = io.din<int16_t>(iOrg); bs.border = io.din<int16_t>(iBrd); bs.pus = io.din<BatchPu>(iPus) + first[l]; bs.out = io.dout<uint32_t>(oSad); bs.count = count[l];
-    if (h->useTensor == 1 && h->cfg.bit_depth == 8)
+    // A handful of PUs (what a live encoder sends per request) is latency bound: the integer-ALU kernel spreads the 35 modes over its
+    // warps and finishes a lone PU in a few microseconds, the tensor-core kernel walks its 19 MMA rounds whatever the row count.
+    // The tensor-core kernel wins on throughput as soon as there is more than one chunk (4096 samples) of a size.
+    const bool small = count[l] <= (4096 >> (2 * l));
+    if (h->useTensor == 1 && h->cfg.bit_depth == 8 && !small)
       CK(launch_rmd_batch_tc2(l, bs, h->cfg.strong_intra_smoothing, h->dTc2Tables.p, h->dTc2Tables.p + tc2::kWinTableBytes, h->dHadamard.p, h->sMain, &h->launches));
     else
       CK(launch_rmd_batch(l, bs, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));

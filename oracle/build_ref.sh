@@ -72,9 +72,9 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
    "      cucd_hook_rmd_begin(g_iPOC, pcCU->getCUPelX() + puRect.x0, pcCU->getCUPelY() + puRect.y0, puRect.width, g_bitDepth[CHANNEL_TYPE_LUMA],\n"
    "                          m_piYuvExt[COMPONENT_Y][PRED_BUF_UNFILTERED], m_piYuvExt[COMPONENT_Y][PRED_BUF_FILTERED], piOrg, uiStride);\n", "before"),
   ("        // do intra prediciton \n        predIntraAng(COMPONENT_Y, uiMode, piOrg, uiStride, piPred, uiStride, tuRecurseWithPU,",
-   "#ifdef CUCD_INTEGRATION\n        uiSad += cucd_shim_rmd_sad(modeIdx);      /* INTEGRATION.md S2 */\n#else\n", "before"),
+   "#ifdef CUCD_INTEGRATION\n        if (cucd_shim_rmd_active()) uiSad += cucd_shim_rmd_sad(modeIdx);      /* INTEGRATION.md S2 */\n        else {\n#endif\n", "before"),
   ("        uiSad += distParam.DistFunc(&distParam);  // DistFunc is a member of DistParam class \n",
-   "#endif\n        cucd_hook_rmd_mode(modeIdx, uiSad);\n", "after"),
+   "#ifdef CUCD_INTEGRATION\n        }\n#endif\n        cucd_hook_rmd_mode(modeIdx, uiSad);\n", "after"),
   ("      //////////////  End of RMD ///",
    "      cucd_hook_rmd_end();\n", "before"),
   ("    uiSad = m_cDistParam.DistFunc(&m_cDistParam);\n\n    // motion cost\n    uiSad += m_pcRdCost->getCost(iSearchX, iSearchY);\n\n    if (uiSad < rcStruct.uiBestSad)",

@@ -38,8 +38,8 @@ inline void cucd_w32(FILE* f, int32_t v) { fwrite(&v, 4, 1, f); }
 #include <vector>
 #include "cucudecide.h"
 #include "cucd_ipc.h"
-struct CucdShim { cucd_handle* h; int W, H, bd, strong; uint32_t sad[35]; long rmdCalls, frameCalls, tmvCalls; bool curForTmv; bool ipcOpen; };
-inline CucdShim& cucd_shim() { static CucdShim s = {0, 0, 0, 0, 0, {0}, 0, 0, 0, false, false}; return s; }
+struct CucdShim { cucd_handle* h; int W, H, bd, strong; uint32_t sad[35]; long rmdCalls, frameCalls, tmvCalls; bool curForTmv; bool ipcOpen; bool rmdActive; int minN; long rmdCpu; };
+inline CucdShim& cucd_shim() { static CucdShim s = {0, 0, 0, 0, 0, {0}, 0, 0, 0, false, false, false, -1, 0}; return s; }
 /* Server mode (CUCD_SERVER=<shared-memory name>): this encoder instance is one of several processes whose requests cucd_server
  * coalesces (include/cucd_ipc.h); the instance itself never touches CUDA.  Otherwise the library is called in-process. */
 inline cucd_ipc_client& cucd_ipc() { static cucd_ipc_client c; return c; }
@@ -94,8 +94,16 @@ inline void cucd_shim_outlier(int W, int H, int bd, int strong, const short* org
   s.frameCalls++;
 }
 /* S2: replaces predIntraAng + DistFunc of the 35-mode loop TEncSearch.cpp:2327-2361 by one batch call per PU */
+/* Offload policy: CUCD_SHIM_MIN_N=<size> keeps PUs smaller than <size> on the encoder's own CPU loop.  One PU at a time is all the live
+ * encoder can offer (its border is the reconstruction of the PU before it), so a request costs a host<->device round trip of tens of
+ * microseconds - more than the CPU needs for the 35 modes of a 4x4 or 8x8 PU, much less than it needs for a 32x32 or 64x64 one
+ * (profiles/r02_encoder_wallclock.md).  Default 0: everything goes to the GPU (what the byte-identity tests exercise). */
+inline bool cucd_shim_rmd_active() { return cucd_shim().rmdActive; }
 inline void cucd_shim_rmd(int n, const short* unfExt, const short* org, int orgStride) {
   CucdShim& s = cucd_shim();
+  if (s.minN < 0) { const char* e = getenv("CUCD_SHIM_MIN_N"); s.minN = e ? atoi(e) : 0; }
+  s.rmdActive = n >= s.minN;
+  if (!s.rmdActive) { s.rmdCpu++; return; }
   int16_t border[4 * 64 + 1], blk[64 * 64];
   const int sw = 2 * n + 1;
   for (int i = 0; i < 2 * n; i++) border[i] = unfExt[(2 * n - i) * sw];
@@ -242,6 +250,7 @@ inline void cucd_shim_tmv_check(int x, int y, int size, const double* ref130) {
   s.tmvCalls++;
 }
 struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim();
+  if (s.rmdCpu) fprintf(stderr, "cucd shim: %ld RMD PUs smaller than %d kept on the CPU (CUCD_SHIM_MIN_N)\n", s.rmdCpu, s.minN);
   if (s.ipcOpen) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, through cucd_server\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls); cucd_ipc().close_client(); }
   if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;

@@ -125,3 +125,50 @@ def test_fullsize_bitstream_md5_matches_recorded_reference(name, ref):
         d = subprocess.run([os.path.join(REF, "TAppDecoder"), "-b", "out.bin", "-o", "dec.yuv", "-d", "0"], cwd=wd, capture_output=True, text=True, timeout=600)
         assert d.returncode == 0 and d.stdout.count("(OK)") == frames
         assert gm.file_md5(os.path.join(wd, "dec.yuv")) == ref["rec_md5"]
+
+
+def test_three_encoder_instances_through_cucd_server_stay_byte_identical():
+    """three encoder PROCESSES (All-Intra, low-delay P and 10-bit All-Intra clips) share the GPU through cucd_server
+    (include/cucd_ipc.h): their S2 requests are coalesced into common batches, S1 / S3 / sub-pel requests are served per instance.
+    Every bitstream must equal the CPU-only reference encoder's."""
+    import json
+    import time
+    import gen_golden as gg
+    server = os.path.join(ROOT, "fast-cu-decision-hevc_b200", "cucd_server")
+    for b in ("TAppEncoder", "TAppEncoderCucd"):
+        if not os.path.exists(os.path.join(REF, b)):
+            pytest.skip(f"oracle/_ref/{b} not built (needs /root/reference in the build container)")
+    assert os.path.exists(server), "cucd_server not built"
+    W, H = 416, 240
+    jobs = [("AI", 8, 3, 32, gg.AI), ("LDP", 8, 3, 32, gg.LDP), ("AI", 10, 2, 27, gg.AI)]
+    name = f"/cucd_test_{os.getpid()}"
+    srv = subprocess.Popen([server, "--name", name, "--clients", str(len(jobs))], stdout=subprocess.PIPE, text=True)
+    time.sleep(1.0)
+    dirs, procs = [], []
+    try:
+        for i, (cfg, bd, frames, qp, struct) in enumerate(jobs):
+            wd = tempfile.mkdtemp(prefix="cucd_srv_")
+            dirs.append(wd)
+            open(os.path.join(wd, "clip.yuv"), "wb").write(gg.synth_clip(W, H, frames, bd, 20261300 + i))
+            args = [os.path.join(REF, "TAppEncoderCucd"), "-i", "clip.yuv", "-wdt", str(W), "-hgt", str(H), "-f", str(frames), "-q", str(qp), "-b", "out.bin", "-o", "rec.yuv",
+                    f"--InputBitDepth={bd}", f"--InternalBitDepth={bd}", "--Profile=" + ("main10" if bd > 8 else "main")] + gg.COMMON + struct
+            procs.append(subprocess.Popen(args, cwd=wd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=dict(os.environ, CUCD_SERVER=name)))
+        errs = [p.communicate(timeout=900)[1] for p in procs]
+        for p, e in zip(procs, errs):
+            assert p.returncode == 0, e[-1500:]
+            assert "through cucd_server" in e
+        stats = json.loads(srv.communicate(timeout=60)[0].strip().splitlines()[-1])
+        assert stats["closed"] == len(jobs) and stats["rmd_requests"] > 3000 and stats["me_surfaces"] > 100 and stats["subpel"] > 100 and stats["frames"] == 8
+        assert stats["rmd_batches"] < stats["rmd_requests"]            # requests of different instances really shared batches
+        print(stats)
+        for i, (cfg, bd, frames, qp, struct) in enumerate(jobs):
+            with tempfile.TemporaryDirectory(prefix="cucd_md5_") as wd:
+                open(os.path.join(wd, "clip.yuv"), "wb").write(gg.synth_clip(W, H, frames, bd, 20261300 + i))
+                _encode("TAppEncoder", wd, W, H, frames, bd, qp, struct)
+                assert open(os.path.join(wd, "out.bin"), "rb").read() == open(os.path.join(dirs[i], "out.bin"), "rb").read(), (cfg, bd)
+                assert hashlib.md5(open(os.path.join(wd, "rec.yuv"), "rb").read()).hexdigest() == hashlib.md5(open(os.path.join(dirs[i], "rec.yuv"), "rb").read()).hexdigest()
+    finally:
+        if srv.poll() is None:
+            srv.terminate()
+        for d in dirs:
+            subprocess.run(["rm", "-rf", d])
