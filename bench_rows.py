@@ -191,7 +191,9 @@ def main():
 
     # ---- a12: TMV features of every whole CU of the picture (depths 0..3) -------------------------------------------------------
     cus = _util.all_cus(W, H)
-    k_s, w_s, _ = timed(lambda: eng.tmv_features(cus), eng, a.iters)
+    cu_arr, n_cu = cucd.Engine.cu_descs(cus)
+    feat = np.zeros((n_cu, 5, 26))
+    k_s, w_s, p_s = timed(lambda: eng.tmv_features_raw(cu_arr, n_cu, feat), eng, a.iters, pin=(feat,))
     algo = sum((1 << (2 * l)) * 2 + 130 * 8 for _, _, l in cus)
     samp = cus[::61]
 
@@ -204,7 +206,8 @@ def main():
             oracle.oracle_tmv_features(C.c_void_p(org.ctypes.data + 2 * (y * W + x)), W, 1 << l, P(out, f64p))
     sec = cpu_parallel(work_a12, len(samp), 1)          # the reference shim copies the whole plane per call: 1 thread, plane copy included
     emit("a12_tmv_features", "CU/s", len(cus), k_s, w_s, algo,
-         {"value": len(samp) / sec, "unit": "CU/s", "cores": 1, "kind": kind, "sample": f"every 61st CU ({len(samp)}) in {sec:.2f} s (driver copies the plane per call)"})
+         {"value": len(samp) / sec, "unit": "CU/s", "cores": 1, "kind": kind, "sample": f"every 61st CU ({len(samp)}) in {sec:.2f} s (driver copies the plane per call)"},
+         p_s=p_s, h2d=int(n_cu * 12), d2h=int(feat.nbytes))
 
     # ---- a13: AQ activity, 4 layers ------------------------------------------------------------------------------------------------
     k_s, w_s, _ = timed(lambda: eng.aq_activity(4), eng, a.iters)

@@ -508,6 +508,16 @@ class Engine:
         self._check(self.lib.cucd_tmv_features(self.h, len(cus), arr, out.ctypes.data), "cucd_tmv_features")
         return out
 
+    @staticmethod
+    def cu_descs(cus):
+        arr = (_CuDesc * max(len(cus), 1))()
+        for i, (x, y, l) in enumerate(cus):
+            arr[i].x, arr[i].y, arr[i].log2_size = int(x), int(y), int(l)
+        return arr, len(cus)
+
+    def tmv_features_raw(self, arr, n, out):
+        self._check(self.lib.cucd_tmv_features(self.h, n, arr, out.ctypes.data), "cucd_tmv_features")
+
     def aq_activity(self, max_aq_depth):
         """TEncPreanalyzer::xPreanalyze of the current picture: ([per-layer (rows, cols) float64 activity], avg[max_aq_depth])."""
         acts = []

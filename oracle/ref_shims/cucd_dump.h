@@ -242,6 +242,9 @@ inline void cucd_shim_tu_reco(short* reco, int stride, short* recQt, int recQtSt
 inline void cucd_shim_tmv_check(int x, int y, int size, const double* ref130) {
   CucdShim& s = cucd_shim();
   if (!s.h || !s.curForTmv) return;
+  static int enabled = -1;          /* CUCD_SHIM_TMV=0: no verification calls (wall-clock measurements) */
+  if (enabled < 0) { const char* e = getenv("CUCD_SHIM_TMV"); enabled = (e && *e == '0') ? 0 : 1; }
+  if (!enabled) return;
   int lg = 0; while ((1 << lg) < size) lg++;
   cucd_cu_desc cu = {x, y, lg};
   double got[CUCD_TMV_FEATURES];

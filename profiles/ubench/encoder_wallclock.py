@@ -28,7 +28,7 @@ def md5(path):
 
 
 def launch(binary, wd, W, H, frames, bd, qp, structure, env=None):
-    e = dict(os.environ); e.update(env or {})
+    e = dict(os.environ); e["CUCD_SHIM_TMV"] = "0"; e.update(env or {})      # no TMV verification calls: they are test instrumentation, not integration
     return subprocess.Popen(gm.encoder_args(os.path.join(REF, binary), W, H, frames, bd, qp, structure), cwd=wd, stdout=subprocess.DEVNULL,
                             stderr=subprocess.PIPE, text=True, env=e)
 
