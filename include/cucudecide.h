@@ -161,12 +161,14 @@ int cucd_intra_rmd_batch(cucd_handle* h, int nPU, const cucd_pu_desc* desc, cons
                          uint32_t* sad);
 
 /* ------------------------------------------------------------------------------------------------
- * S2, asynchronous and coalescing.  In the live encoder a PU's border is an intermediate state
- * of the reconstruction, so one encoder instance can only offer the few PUs of its current CU at a time.  Several
- * instances (host threads, one per picture in flight) therefore share ONE queue on top of a handle: submit copies
- * the request and returns at once, a worker thread runs everything that is pending as one cucd_intra_rmd_batch
- * (one launch per PU size, thousands of PUs) and completes the tickets in submission order.
- * The queue owns the handle's S2 path while it exists: do not call cucd_intra_rmd_batch on `h` directly meanwhile.
+ * S2, asynchronous and coalescing, for host THREADS of one process (encoder PROCESSES use cucd_server,
+ * include/cucd_ipc.h).  In the live encoder a PU's border is an intermediate state of the reconstruction, so one encoder
+ * instance can only offer the few PUs of its current CU at a time.  Several instances therefore share ONE queue on top of a
+ * handle: submit copies the request once, into the pinned arena that is being filled, and returns; a worker thread swaps
+ * arenas and runs everything that is pending as one batch (one launch per PU size), after a short batching window
+ * (CUCD_QUEUE_WINDOW_US, default 30: the instances released by the previous batch come back within tens of microseconds), and
+ * completes the tickets in submission order.  A failed batch fails its own tickets only.  Other calls on `h` from other threads
+ * are safe (every entry point takes the handle's lock); they serialise with the worker's batches.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct cucd_queue cucd_queue;
 int cucd_queue_create(cucd_handle* h, cucd_queue** out);
