@@ -330,21 +330,27 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   uint16_t* accN4 = reinterpret_cast<uint16_t*>(acc) + (r.ctu * C::PUS + 4 * r.pu) * kNumModes;
   uint32_t* accRow = acc + (r.ctu * C::PUS + r.pu) * kNumModes;
   auto cost_out = [&](int mode, bool has) {
-    uint32_t q[4];
+    // sum |D2| over the row's 64 columns, 16 at a time; the load of chunk c+1 is in flight while chunk c is summed (two independent
+    // VABSDIFF chains per chunk), so one TMEM load latency is exposed per epilogue instead of one per load
+    uint32_t q[4], va[16], vb[16];
+    auto sum16 = [](const uint32_t* v) {
+      uint32_t s0 = 0, s1 = 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      uint32_t v[32];
-      tmem_ld32(tD2 + laneOff + h * 32, v);
-      tmem_ld_wait();
-      // two 16-column chunks, each summed by two independent chains (the dependent VABSDIFF chain is the latency here)
-      uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        s0 = sad_acc(v[k], 0u, s0);      s1 = sad_acc(v[8 + k], 0u, s1);
-        s2 = sad_acc(v[16 + k], 0u, s2); s3 = sad_acc(v[24 + k], 0u, s3);
-      }
-      q[2 * h] = s0 + s1; q[2 * h + 1] = s2 + s3;
-    }
+      for (int k = 0; k < 8; k++) { s0 = sad_acc(v[k], 0u, s0); s1 = sad_acc(v[8 + k], 0u, s1); }
+      return s0 + s1;
+    };
+    tmem_ld16(tD2 + laneOff, va);
+    tmem_ld_wait();
+    tmem_ld16(tD2 + laneOff + 16, vb);
+    q[0] = sum16(va);
+    tmem_ld_wait();
+    tmem_ld16(tD2 + laneOff + 32, va);
+    q[1] = sum16(vb);
+    tmem_ld_wait();
+    tmem_ld16(tD2 + laneOff + 48, vb);
+    q[2] = sum16(va);
+    tmem_ld_wait();
+    q[3] = sum16(vb);
     tc_fence_before();
     if (LOG2N == 2) {
       if (ok && has) {
