@@ -519,10 +519,10 @@ def run_ours(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "r01_rmd_traffic.json")
     if bd == 8 and os.path.exists(tpath):
         traffic = float(json.load(open(tpath))["dram_bytes_per_ctu"]) * ctus_step_gpu
-    roofline = {"bound": "hbm", "kernel": "rmd_frame_tc2_kernel" if bd == 8 else "rmd_frame_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": ("rmd_frame_kernel" if os.environ.get("CUCD_RMD_PATH") == "alu" else ("rmd_frame_tc2_kernel" if bd == 8 else "rmd_frame_tc3_kernel")), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "launch_ms": rmd_ms, "launches_timed": n_timed, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CTU * ctus_step_gpu,
                 "peak_source": peak_src,
-                "note": "launch_ms is the CUDA-event window around the RMD launch on the caller's stream; the small feature kernels run beside it on a high-priority stream and take part of that window. RMD is compute bound by construction (~140 int-op/B, SURVEY.md 8d): predictions and Hadamard run on tcgen05 (kind::i8), "
+                "note": "launch_ms is the CUDA-event window around the RMD launch on the caller's stream; the small feature kernels run beside it on a high-priority stream and take part of that window. RMD is compute bound by construction (~140 int-op/B, SURVEY.md 8d): predictions and Hadamard run on tcgen05 (kind::i8 for 8-bit content, kind::f16 with exact integer operands for 9/10-bit content), "
                         "the epilogues on the integer ALU; the HBM fraction is small; see profiles/ for pipe utilisation"}
 
     if rank == 0:

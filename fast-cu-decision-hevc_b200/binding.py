@@ -580,7 +580,8 @@ class Engine:
         self._check(self.lib.cucd_set_decision_switches(self.h, int(bool(enable)), a, b), "cucd_set_decision_switches")
 
     def set_rmd_path(self, path):
-        """0 / False: integer ALU; 1 / True: predictions + Hadamard on the tensor cores (tcgen05)"""
+        """0 / False: integer ALU; 1 / True: predictions + Hadamard on the tensor cores (kind::i8 at 8 bit, kind::f16 above);
+        2: the half-precision tensor-core kernel whatever the bit depth"""
         self._check(self.lib.cucd_set_rmd_path(self.h, int(path)), "cucd_set_rmd_path")
 
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include "handle.h"
 #include "rmd_tc2.cuh"
+#include "rmd_tc3.cuh"
 #include "tcm_host.h"
 
 using namespace cucd;
@@ -68,8 +69,11 @@ FeaturePlanes make_feature_planes(const cucd_handle* h, const int16_t* org, long
 }
 
 cudaError_t launch_rmd_auto(cucd_handle* h, const FrameSource& fs, int nPics, cudaStream_t st) {
-  if (h->useTensor == 1 && h->cfg.bit_depth == 8)
+  if (h->useTensor == 1 && h->cfg.bit_depth == 8)     // kind::i8: samples are bytes
     return launch_rmd_frames_tc2(fs, nPics, h->cfg.strong_intra_smoothing, h->dTc2Tables.p, h->dTc2Tables.p + tc2::kWinTableBytes, h->dHadamard.p, st, &h->launches);
+  if (h->useTensor >= 1)      // 9/10-bit content (or path 2: any bit depth): half-precision operands, fp32 accumulators (exact integers)
+    return launch_rmd_frames_tc3(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->dTc3Tables.p, h->dTc3Tables.p + tc3::kWinTableBytes16,
+                                 h->dTc3Tables.p + tc3::kWinTableBytes16 + tc3::kN4TableBytes16, st, &h->launches);
   return launch_rmd_frames(fs, nPics, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, st, &h->launches);
 }
 
@@ -144,7 +148,7 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
   if (prop.major != 10) return fail(nullptr, CUCD_ERR_NO_DEVICE, "cucd_create: kernels are built for sm_100a only, device is sm_" + std::to_string(prop.major * 10 + prop.minor));
   if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
   // per-device function attributes (> 48 KB of dynamic shared memory): once per handle, so every device a process uses is configured
-  if ((e = configure_rmd_kernels()) != cudaSuccess || (e = configure_rmd_tc2_kernels()) != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute");
+  if ((e = configure_rmd_kernels()) != cudaSuccess || (e = configure_rmd_tc2_kernels()) != cudaSuccess || (e = configure_rmd_tc3_kernels()) != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute");
 
   cucd_handle* h = new cucd_handle;
   h->cfg = *cfg;
@@ -188,6 +192,12 @@ int cucd_create(const cucd_config* cfg, cucd_handle** out) {
     std::vector<uint8_t> tab(tc2::kWinTableBytes + tc2::kN4TableBytes);
     tc2::fill_win_tables(tab.data()); tc2::fill_n4_tables(tab.data() + tc2::kWinTableBytes);
     ok = h->dTc2Tables.reserve(tab.size()) == cudaSuccess && cudaMemcpy(h->dTc2Tables.p, tab.data(), tab.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  if (ok) {
+    std::vector<uint8_t> tab(tc3::kWinTableBytes16 + tc3::kN4TableBytes16 + tc3::kHadBytes16);
+    tc3::fill_win_tables16(tab.data()); tc3::fill_n4_tables16(tab.data() + tc3::kWinTableBytes16);
+    tc3::fill_had_tables16(tab.data() + tc3::kWinTableBytes16 + tc3::kN4TableBytes16);
+    ok = h->dTc3Tables.reserve(tab.size()) == cudaSuccess && cudaMemcpy(h->dTc3Tables.p, tab.data(), tab.size(), cudaMemcpyHostToDevice) == cudaSuccess;
   }
   h->useTensor = 1;
   { const char* ev = getenv("CUCD_RMD_PATH"); if (ev && !strcmp(ev, "alu")) h->useTensor = 0; }
@@ -270,7 +280,7 @@ int cucd_set_decision_switches(cucd_handle* h, int enable, const uint8_t skip2Nx
 int cucd_set_rmd_path(cucd_handle* h, int path) {
   if (!h) return CUCD_ERR_INVALID;
   LOCK(h);
-  if (path < 0 || path > 1) return fail(h, CUCD_ERR_INVALID, "cucd_set_rmd_path: path must be 0 (integer ALU) or 1 (tensor cores)");
+  if (path < 0 || path > 2) return fail(h, CUCD_ERR_INVALID, "cucd_set_rmd_path: path must be 0 (integer ALU), 1 (tensor cores) or 2 (half-precision tensor-core kernel at any bit depth)");
   h->useTensor = path;
   return CUCD_OK;
 }

@@ -138,6 +138,7 @@ struct cucd_handle {
   cucd::DevBuf<uint32_t> dCost;
   cucd::DevBuf<uint8_t> dCostPacked;              // CUCD_PACKED_CTU_BYTES per CTU (cucd_frame_out.rmd_cost_packed)
   cucd::DevBuf<int8_t> dHadamard;                 // +-(H8 x H8), +-(blockdiag H4 x H4) operands of the tensor-core SATD
+  cucd::DevBuf<uint8_t> dTc3Tables;               // half-precision weight / Hadamard operands of the 9/10-bit tensor-core path (rmd_tc3.cuh)
   cucd::DevBuf<uint8_t> dTc2Tables;               // interpolation-weight operands of the tensor-core prediction (rmd_tc2.cuh)
   int useTensor = 0;                              // cucd_set_rmd_path: 1 = predictions + Hadamard on tcgen05, 0 = integer ALU
   cucd::DevBuf<int32_t> dNum[4], dSum[4], dCtuHad;

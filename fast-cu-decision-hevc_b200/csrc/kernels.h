@@ -20,6 +20,11 @@ cudaError_t launch_hadamard_operands(int8_t* dst, cudaStream_t st);
 cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
                                   cudaStream_t st, int* launches);
 int rmd_tc2_smem_bytes();
+// the same on tcgen05 kind::f16 for 9/10-bit content (rmd_tc3_kernels.cu); tables = tc3::fill_win_tables16 / fill_n4_tables16 / fill_had_tables16
+cudaError_t configure_rmd_tc3_kernels();
+cudaError_t launch_rmd_frames_tc3(const FrameSource& fs, int nPics, int bitDepth, int strong, const uint8_t* tabWin16, const uint8_t* tabN416,
+                                  const uint8_t* hadamard16, cudaStream_t st, int* launches);
+int rmd_tc3_smem_bytes();
 // the same tensor-core rounds for S2 batches of ONE PU size with caller-supplied borders (8-bit content)
 cudaError_t launch_rmd_batch_tc2(int log2n, const BatchSource& bs, int strong, const uint8_t* tabWin, const uint8_t* tabN4, const int8_t* hadamard,
                                  cudaStream_t st, int* launches);

@@ -323,8 +323,10 @@ int cucd_dev_me_subpel_cost(cucd_handle* h, void* stream, int nPU, const cucd_su
 int cucd_dev_frames_begin(cucd_handle* h, void* stream, int nPics, const int16_t* d_org, long long orgPicStride, int orgStride,
                           const int16_t* d_rec, long long recPicStride, int recStride, const cucd_dev_out* out, double* yc_host);
 int cucd_dev_frames_end(cucd_handle* h);
-/* Frame-mode RMD has two bit-identical implementations: 0 = integer ALU (prediction and Hadamard butterflies in
- * registers); 1 = tcgen05 tensor cores for the angular predictions and the Hadamard stage (the default).
+/* Frame-mode RMD has bit-identical implementations: 0 = integer ALU (prediction and Hadamard butterflies in
+ * registers); 1 = tcgen05 tensor cores for the angular predictions and the Hadamard stage (the default): kind::i8 for
+ * 8-bit content, kind::f16 with fp32 accumulation (every operand and sum an exactly representable integer) for 9/10-bit
+ * content; 2 = the half-precision kernel whatever the bit depth (verification).
  * CUCD_RMD_PATH=alu in the environment at create time selects 0. */
 int cucd_set_rmd_path(cucd_handle* h, int path);
 /* Device time of the RMD kernel inside the last `nCalls` cucd_dev_frames calls (CUDA events recorded on the

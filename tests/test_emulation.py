@@ -46,6 +46,37 @@ def test_tensor_core_frame_kernel_code_vs_oracle(emul, oracle, W, H, seed):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("bd,W,H,seed", [(10, 200, 136, 5), (10, 64, 64, 1), (9, 328, 72, 9), (8, 136, 72, 2)])
+def test_half_precision_tensor_core_frame_kernel_code_vs_oracle(emul, oracle, bd, W, H, seed):
+    """rmd_tc3 (9/10-bit content on tcgen05 kind::f16): the kernel's fp16 weight tables, record / window operands, magic-number
+    accumulator read-out and FADD |x| epilogue, replayed with exact products (tests/emul/rmd_tc3_emul.cpp)"""
+    org = textured_plane(W, H, bd, seed=seed)
+    rec = pseudo_recon(org, bd)
+    rec[:, : W // 2] = ((np.arange(H)[:, None] // 3 + np.arange(W // 2)[None, :] // 5 + 40) << (bd - 8)).astype(np.int16)   # flat: strong smoothing
+    want = oracle_rmd_frame(oracle, org, rec, bd)
+    S = (W + 7) // 8 * 8
+    orgp = np.zeros((H, S), np.int16); orgp[:, :W] = org
+    recp = np.zeros((H, S), np.int16); recp[:, :W] = rec
+    got = np.zeros_like(want)
+    emul.emul_rmd_frame_tc3(bd, 1, P(orgp, i16p), S, P(recp, i16p), S, W, H, P(got, u32p))
+    assert np.array_equal(got, want)
+
+
+def test_half_precision_tensor_core_frame_kernel_code_extreme_values(emul, oracle):
+    """0 / 1023 checkerboards and stripes: the largest accumulators (2^23 + 65535) and Hadamard sums the fp32 path sees"""
+    W = H = 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    rng = np.random.default_rng(3)
+    cases = [(np.where((xx + yy) & 1, 1023, 0), np.where((xx + yy) & 1, 0, 1023)), (np.full((H, W), 1023), np.zeros((H, W))),
+             (np.where(xx & 1, 1023, 0), np.full((H, W), 1023)), (rng.integers(0, 1024, (H, W)), rng.integers(0, 1024, (H, W)))]
+    for org, rec in cases:
+        org = np.ascontiguousarray(org.astype(np.int16)); rec = np.ascontiguousarray(rec.astype(np.int16))
+        want = oracle_rmd_frame(oracle, org, rec, 10)
+        got = np.zeros_like(want)
+        emul.emul_rmd_frame_tc3(10, 1, P(org, i16p), W, P(rec, i16p), W, W, H, P(got, u32p))
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("n", [4, 8, 16, 32, 64])
 def test_tensor_core_batch_kernel_code_vs_golden(emul, n):
     """S2 batches on the tensor-core code path against the vectors dumped from the reference encoder's own RMD loop"""

@@ -256,9 +256,42 @@ def test_tensor_core_path_extreme_values(cucd, oracle):
         org = org.astype(np.int16); rec = rec.astype(np.int16)
         with cucd.Engine(W, H) as eng:
             with pytest.raises(cucd.CucdError):
-                eng.set_rmd_path(2)                       # the round-1 "Hadamard only" experiment is no longer in the ABI
+                eng.set_rmd_path(3)                       # 0 / 1 / 2 are the paths of the ABI
             got = eng.frame(org, rec)["rmd_cost"]
         assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 8))
+
+
+# ---- 9/10-bit content: tcgen05 kind::f16 kernel (exact integers in fp16 operands / fp32 accumulators) == integer ALU == oracle ----
+@pytest.mark.parametrize("bd,W,H", [(10, 416, 240), (10, 200, 136), (9, 328, 72), (10, 64, 64), (8, 200, 136)])
+def test_half_precision_tensor_core_path_equals_alu_path_and_oracle(cucd, oracle, bd, W, H):
+    org = textured_plane(W, H, bd, seed=W + bd)
+    rec = pseudo_recon(org, bd)
+    rec[:, : W // 2] = ((np.arange(H)[:, None] // 3 + np.arange(W // 2)[None, :] // 5 + 40) << (bd - 8)).astype(np.int16)
+    with cucd.Engine(W, H, bit_depth=bd, max_pictures=3) as eng:
+        eng.set_rmd_path(2)                                    # the half-precision kernel whatever the bit depth
+        tc = eng.frames([org, rec, org], [rec, org, org])      # 3 pictures: CTU groups of 4 straddle pictures
+        eng.set_rmd_path(0)
+        alu = eng.frames([org, rec, org], [rec, org, org])
+        eng.set_rmd_path(1)                                    # the default: kind::f16 above 8 bit, kind::i8 at 8 bit
+        dflt = eng.frame(org, rec)
+    want = oracle_rmd_frame(oracle, org, rec, bd)
+    assert np.array_equal(tc[0]["rmd_cost"], want)
+    assert np.array_equal(dflt["rmd_cost"], want)
+    for k in range(3):
+        assert np.array_equal(tc[k]["rmd_cost"], alu[k]["rmd_cost"])
+
+
+def test_half_precision_tensor_core_path_extreme_values(cucd, oracle):
+    """0 / 1023 checkerboards and stripes: the largest accumulators (2^23 + 65535) and Hadamard sums; random full-range content"""
+    W = H = 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    rng = np.random.default_rng(3)
+    for org, rec in [(np.where((xx + yy) & 1, 1023, 0), np.where((xx + yy) & 1, 0, 1023)), (np.full((H, W), 1023), np.zeros((H, W))),
+                     (np.where(xx & 1, 1023, 0), np.full((H, W), 1023)), (rng.integers(0, 1024, (H, W)), rng.integers(0, 1024, (H, W)))]:
+        org = np.ascontiguousarray(org.astype(np.int16)); rec = np.ascontiguousarray(rec.astype(np.int16))
+        with cucd.Engine(W, H, bit_depth=10) as eng:
+            got = eng.frame(org, rec)["rmd_cost"]
+        assert np.array_equal(got, oracle_rmd_frame(oracle, org, rec, 10))
 
 
 # ---- packed cost tables (cucd_frame_out.rmd_cost_packed) carry the same numbers -------------------------------
@@ -537,7 +570,7 @@ def test_fork_aware_frame_mode_vs_real_encoder_visits(cucd, oracle, name):
         assert all(np.array_equal(a["rmd_cost"], b["rmd_cost"]) for a, b in zip(again, full))
 
 
-@pytest.mark.parametrize("bd,path", [(8, 1), (8, 0), (10, 0)])
+@pytest.mark.parametrize("bd,path", [(8, 1), (8, 0), (10, 0), (10, 1)])
 def test_fork_aware_frame_mode_all_switch_patterns(cucd, oracle, bd, path):
     """every Skip2Nx2N / TerminateCU pattern on a picture with flat and textured regions and partial CTUs, tensor-core and ALU kernels"""
     import itertools
