@@ -478,16 +478,22 @@ CUCD_HD void build_unfiltered(int tid, int ctu, int W, int H, int ctuX, int ctuY
     put_ref<LOG2N>(store, ctu, p, 0, 0, cval); put_ref<LOG2N>(store, ctu, p, 1, 0, cval);
     if (LOG2N == 2) { store[rec_off(ctu, 0, p) + 14] = 0; store[rec_off(ctu, 0, p) + 15] = 1; store[rec_off(ctu, 1, p) + 14] = 0; store[rec_off(ctu, 1, p) + 15] = 1; }
   }
-  int dcSum = 0;
+  // all the samples are read before the first one is stored: the stores may alias the tile as far as the compiler can tell, and
+  // interleaved they would serialise every shared-memory round trip
+  int dcSum = 0, vals[SPT];
 #pragma unroll
   for (int e = 0; e < SPT; e++) {
     const int j = sub * SPT + e;                     // 0 .. 4N-1
     const int o = j >= 2 * N, k = j - o * 2 * N + 1; // T[k] or L[k]
-    int v;
-    if (o == 0) v = k <= a.lenT ? rowT[k] : tailT;
-    else v = k <= a.lenL ? colL[k * C::TILE_PITCH] : firstAvail;
-    put_ref<LOG2N>(store, ctu, p, o, k, v);
-    if (k <= N) dcSum += v;
+    if (o == 0) vals[e] = k <= a.lenT ? rowT[k] : tailT;
+    else vals[e] = k <= a.lenL ? colL[k * C::TILE_PITCH] : firstAvail;
+    if (k <= N) dcSum += vals[e];
+  }
+#pragma unroll
+  for (int e = 0; e < SPT; e++) {
+    const int j = sub * SPT + e;
+    const int o = j >= 2 * N, k = j - o * 2 * N + 1;
+    put_ref<LOG2N>(store, ctu, p, o, k, vals[e]);
   }
   if (LOG2N >= 3) {
     int* dst = reinterpret_cast<int*>(smem + C::DC_OFF) + ctu * 64 + p;
@@ -559,16 +565,21 @@ CUCD_HD void build_filtered(int tid, int ctu, int strongEnabled, unsigned char* 
     const int c = strong ? tl : ((int)L[1] + 2 * tl + (int)T[1] + 2) >> 2;
     put(0, 0, c); put(1, 0, c);
   }
+  int vals[SPT];
 #pragma unroll
   for (int e = 0; e < SPT; e++) {
     const int j = sub * SPT + e;
     const int o = j >= 2 * N, k = j - o * 2 * N + 1;
     const unsigned char* A = o ? L : T;
-    int v;
-    if (k == 2 * N) v = A[k];
-    else if (strong) v = o ? (k * bl + (2 * N - k) * tl + N) >> (LOG2N + 1) : ((2 * N - k) * tl + k * tr + N) >> (LOG2N + 1);
-    else v = ((int)A[k - 1] + 2 * (int)A[k] + (int)A[k + 1] + 2) >> 2;
-    put(o, k, v);
+    if (k == 2 * N) vals[e] = A[k];
+    else if (strong) vals[e] = o ? (k * bl + (2 * N - k) * tl + N) >> (LOG2N + 1) : ((2 * N - k) * tl + k * tr + N) >> (LOG2N + 1);
+    else vals[e] = ((int)A[k - 1] + 2 * (int)A[k] + (int)A[k + 1] + 2) >> 2;
+  }
+#pragma unroll
+  for (int e = 0; e < SPT; e++) {
+    const int j = sub * SPT + e;
+    const int o = j >= 2 * N, k = j - o * 2 * N + 1;
+    put(o, k, vals[e]);
   }
 }
 

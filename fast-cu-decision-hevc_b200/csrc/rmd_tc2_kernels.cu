@@ -94,9 +94,41 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Phase 1 of the prologue (rmd_tc2.cuh stage_tile) split into its global loads and its shared-memory stores, so that the
+// loads of ALL the CTA's CTUs (and the rows' source tiles, tc2_body) are in flight together: the prologue used to pay four
+// dependent global-memory round trips per CTU, ~4.5 k cycles each CTU, with the CTA's TMEM idle.
+struct TileLoad { uint4 v[2]; int left, top; };
+template <int LOG2N>
+__device__ __forceinline__ void tile_load(int tid, const int16_t* rec, int recStride, int W, int H, int ctuX, int ctuY, TileLoad& t) {
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const int idx = tid + it * kThreads, y = idx >> 3, x = (idx & 7) * 8;
+    t.v[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (ctuY + y < H && ctuX + x < W) t.v[it] = *reinterpret_cast<const uint4*>(rec + (size_t)(ctuY + y) * recStride + ctuX + x);
+  }
+  t.left = 0; t.top = 0;
+  if (ctuX > 0 && tid < 64 && ctuY + tid < H) t.left = rec[(size_t)(ctuY + tid) * recStride + ctuX - 1];
+  const int gx = ctuX - 1 + tid;
+  if (ctuY > 0 && tid < 129 && gx >= 0 && gx < W) t.top = rec[(size_t)(ctuY - 1) * recStride + gx];
+}
+template <int LOG2N>
+__device__ __forceinline__ void tile_store(int tid, int W, int H, int ctuX, int ctuY, const TileLoad& t, unsigned char* dst) {
+  typedef Cfg<LOG2N> C;
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const int idx = tid + it * kThreads, y = idx >> 3, x = (idx & 7) * 8;
+    if (ctuY + y >= H || ctuX + x >= W) continue;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + y * C::TILE_PITCH + 4 + x);
+    d[0] = __byte_perm(t.v[it].x, t.v[it].y, 0x6420); d[1] = __byte_perm(t.v[it].z, t.v[it].w, 0x6420);
+  }
+  if (ctuX > 0 && tid < 64 && ctuY + tid < H) dst[tid * C::TILE_PITCH + 3] = (unsigned char)t.left;
+  const int gx = ctuX - 1 + tid;
+  if (ctuY > 0 && tid < 129 && gx >= 0 && gx < W) dst[C::TILE_TOP + 3 + tid] = (unsigned char)t.top;
+}
+
 // ---- prologue: reference arrays of the CTA's CTUs (rmd_tc2.cuh phases 1-3) --------------------------------
 template <int LOG2N, bool FRAME>
-__device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
+__device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit, const TileLoad* tl, const int* ctuX, const int* ctuY) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N;
   unsigned char* smem = smem2;
@@ -124,32 +156,33 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
     }
     return;
   }
-  int ctuX[C::CTUS], ctuY[C::CTUS];
 #pragma unroll
   for (int c = 0; c < C::CTUS; c++) {
     const int cg = unit * C::CTUS + c;
     uint8_t* valid = smem + C::VALID_OFF + c * 256;
-    ctuX[c] = -1; ctuY[c] = -1;
-    if (cg >= a.totalCtus) {                                   // CTA-uniform
+    if (ctuX[c] < 0) {
       for (int p = tid; p < C::PUS; p += kThreads) valid[p] = 0;
       continue;
     }
-    const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-    ctuX[c] = (ctu % fs.ctusPerRow) * 64; ctuY[c] = (ctu / fs.ctusPerRow) * 64;
     const uint8_t* need = fs.needed ? fs.needed + ((size_t)cg * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) : nullptr;
     for (int p = tid; p < C::PUS; p += kThreads) {
       int px, py; demorton(p, px, py);
       const bool inside = (ctuX[c] + (px + 1) * N <= fs.W) && (ctuY[c] + (py + 1) * N <= fs.H);
       valid[p] = !inside ? kPuOutside : ((need && !need[p]) ? kPuPruned : kPuEvaluate);
     }
-    stage_tile<LOG2N>(tid, kThreads, fs.rec + (size_t)pic * fs.recPicStride, fs.recStride, fs.W, fs.H, ctuX[c], ctuY[c], smem + C::TILE_OFF + c * C::TILE_BYTES);
   }
+#pragma unroll
+  for (int c = 0; c < C::CTUS; c++)
+    if (ctuX[c] >= 0) tile_store<LOG2N>(tid, fs.W, fs.H, ctuX[c], ctuY[c], tl[c], smem + C::TILE_OFF + c * C::TILE_BYTES);
   __syncthreads();
+  TC2_STAMP(51);
 #pragma unroll
   for (int c = 0; c < C::CTUS; c++)
     if (ctuX[c] >= 0) build_unfiltered<LOG2N>(tid, c, fs.W, fs.H, ctuX[c], ctuY[c], smem + C::TILE_OFF + c * C::TILE_BYTES, smem);
+  TC2_STAMP(52);
   if (C::HAS_FILT) {
     __syncthreads();
+    TC2_STAMP(53);
 #pragma unroll
     for (int c = 0; c < C::CTUS; c++)
       if (ctuX[c] >= 0) build_filtered<LOG2N>(tid, c, a.strong, smem);
@@ -162,8 +195,22 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit) {
 //     wait MMA1(i) | epilogue 1 -> A2, projected refs of round i+1 | issue MMA2(i) | stage B1/A1 of round i+1 |
 //     wait MMA2(i) | issue MMA1(i+1) | epilogue 2 of round i (costs)
 // TMEM per row group: D1 = columns [0, 64) (A2 aliases its first 16 once they have been read), D2 = [64, 128).
+// first sample of the row's source tile in frame mode (tile origin inside the CTU from the row map)
+template <int LOG2N>
+__device__ __forceinline__ const int16_t* frame_src_ptr(const FrameSource& fs, const Row& r, int cg, int& tileX, int& tileY) {
+  constexpr int N = Cfg<LOG2N>::N;
+  const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
+  int px, py; demorton(r.pu, px, py);
+  if (LOG2N == 2) { px *= 8; py *= 8; }
+  else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
+  tileX = (ctu % fs.ctusPerRow) * 64 + px; tileY = (ctu / fs.ctusPerRow) * 64 + py;
+  return fs.org + (size_t)pic * fs.orgPicStride + (size_t)tileY * fs.orgStride + tileX;
+}
+
+// `pre`: the eight rows of the source tile of pass 0, loaded by tc2_body before the prologue (frame mode), or nullptr
 template <int LOG2N, bool FRAME>
-__device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2, uint32_t& phA, uint32_t& phB) {
+__device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2, uint32_t& phA, uint32_t& phB,
+                                         const uint4* pre) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N, SEG = RowSeg<LOG2N>::value;
   unsigned char* smem = smem2;
@@ -190,15 +237,17 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   if (ok) {
     uint32_t raw[16];
     if (FRAME) {
-      const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-      int px, py; demorton(r.pu, px, py);
-      if (LOG2N == 2) { px *= 8; py *= 8; }
-      else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
-      const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
+      if (pre && pass == 0) {
 #pragma unroll
-      for (int y = 0; y < 8; y++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)y * fs.orgStride);
-        raw[2 * y] = __byte_perm(v.x, v.y, 0x6420); raw[2 * y + 1] = __byte_perm(v.z, v.w, 0x6420);
+        for (int y = 0; y < 8; y++) { raw[2 * y] = __byte_perm(pre[y].x, pre[y].y, 0x6420); raw[2 * y + 1] = __byte_perm(pre[y].z, pre[y].w, 0x6420); }
+      } else {
+        int tx, ty;
+        const int16_t* src = frame_src_ptr<LOG2N>(fs, r, cg, tx, ty);
+#pragma unroll
+        for (int y = 0; y < 8; y++) {
+          const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)y * fs.orgStride);
+          raw[2 * y] = __byte_perm(v.x, v.y, 0x6420); raw[2 * y + 1] = __byte_perm(v.z, v.w, 0x6420);
+        }
       }
     } else {
       const BatchSource& bs = a.bs;
@@ -236,6 +285,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     for (int i = 0; i < 16; i++) p[i] = 0;
   }
 
+  if (pass == 0) TC2_STAMP(56);
   const uint32_t laneOff = (uint32_t)((warp & 3) * 32) << 16;
   const int rowChunk = (rowTid >> 3) * 128 + (rowTid & 7) * 16;      // the row's 16-byte slot inside a 128-row operand chunk
   const uint32_t tD1 = tmemBase + grp * 128, tA2 = tD1, tD2 = tD1 + 64;
@@ -257,10 +307,12 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
 
   // source x -H + A2 (already stored to TMEM by every thread) x H -> D2
-  auto issue_mma2 = [&]() {
+  auto arrive_mma2 = [&]() {
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(arrA);
+  };
+  auto fire_mma2 = [&]() {
     if (issuer) {
       mbar_wait(uarrA, phA);
       tc_fence_after();
@@ -275,6 +327,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     }
     phA ^= 1u;
   };
+  auto issue_mma2 = [&]() { arrive_mma2(); fire_mma2(); };
   auto wait_mma2 = [&]() { mbar_wait(mbar2, ph2); ph2 ^= 1u; tc_fence_after(); };
   // window / record operand (shared memory) x weights -> D1
   auto issue_mma1 = [&](int buf) {
@@ -332,7 +385,8 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   auto cost_out = [&](int mode, bool has) {
     // sum |D2| over the row's 64 columns, 16 at a time; the load of chunk c+1 is in flight while chunk c is summed (two independent
     // VABSDIFF chains per chunk), so one TMEM load latency is exposed per epilogue instead of one per load
-    uint32_t q[4], va[16], vb[16];
+    uint32_t q[4];
+    uint32_t va[16], vb[16];
     auto sum16 = [](const uint32_t* v) {
       uint32_t s0 = 0, s1 = 0;
 #pragma unroll
@@ -393,6 +447,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     }
   }
   fence_async_smem();                               // the source operand is read by the tensor core (async proxy)
+  if (pass == 0) TC2_STAMP(57);
 
   // ---- round 0 -------------------------------------------------------------------------------------------------
   tmem_st16(tA2 + laneOff, p);
@@ -435,7 +490,8 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     const bool lateWindow = LOG2N != 2 && am > -8 && angleNext < 0;
     if (lateWindow) build_ext_group<LOG2N>(rowTid, grp, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
     TC2_FINE(3);
-    issue_mma2();
+    arrive_mma2();
+    fire_mma2();
     TC2_FINE(4);
     if (am > -8) {
       stage_weights(buf ^ 1);
@@ -499,12 +555,49 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   }
   TC2_STAMP(0);
   if (warp == 0) tmem_alloc(tmemSlot, 256);
-  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid];              // +H
-  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid + 256] = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid + 256];  // -H
+  TC2_STAMP(58);
+  // Every global load of the set-up is issued here, before anything waits: the Hadamard operands, the reconstruction
+  // neighbourhoods of the CTA's CTUs (tile_load) and the rows' source tiles of pass 0 share ONE memory round trip.
+  const uint4 hadP = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid];        // +H
+  const uint4 hadN = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0))[tid + 256];  // -H
+  int ctuX[C::CTUS], ctuY[C::CTUS];
+  TileLoad tl[C::CTUS];
+  if (FRAME) {
+#pragma unroll
+    for (int c = 0; c < C::CTUS; c++) {
+      const int cg = unit * C::CTUS + c;
+      ctuX[c] = -1; ctuY[c] = -1;
+      if (cg >= a.totalCtus) continue;                           // CTA-uniform
+      const int pic = cg / a.fs.ctusPerPic, ctu = cg - pic * a.fs.ctusPerPic;
+      ctuX[c] = (ctu % a.fs.ctusPerRow) * 64; ctuY[c] = (ctu / a.fs.ctusPerRow) * 64;
+      tile_load<LOG2N>(tid, a.fs.rec + (size_t)pic * a.fs.recPicStride, a.fs.recStride, a.fs.W, a.fs.H, ctuX[c], ctuY[c], tl[c]);
+    }
+  }
+  uint4 pre[8];
+  if (FRAME) {
+    const Row r0 = row_map<LOG2N>(tid, 0);
+    const int cg0 = unit * C::CTUS + r0.ctu;
+#pragma unroll
+    for (int y = 0; y < 8; y++) pre[y] = make_uint4(0u, 0u, 0u, 0u);
+    if (cg0 < a.totalCtus) {
+      int tx, ty;
+      const int16_t* src = frame_src_ptr<LOG2N>(a.fs, r0, cg0, tx, ty);
+      if (tx + 8 <= a.fs.W && ty + 8 <= a.fs.H) {
+#pragma unroll
+        for (int y = 0; y < 8; y++) pre[y] = *reinterpret_cast<const uint4*>(src + (size_t)y * a.fs.orgStride);
+      }
+    }
+  }
+  TC2_STAMP(59);
   if (LOG2N >= 4) for (int i = tid; i < C::CTUS * C::PUS * kNumModes; i += kThreads) acc[i] = 0;   // accumulated with atomics
   reinterpret_cast<int*>(smem + C::DC_OFF)[tid] = 0;          // CTUS * 64 <= 256 sums
+  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = hadP;
+  TC2_STAMP(60);
+  reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid + 256] = hadN;
   __syncthreads();
-  tc2_prologue<LOG2N, FRAME>(a, unit);
+  TC2_STAMP(50);
+  tc2_prologue<LOG2N, FRAME>(a, unit, tl, ctuX, ctuY);
+  TC2_STAMP(54);
   tc_fence_before();
   fence_async_smem();
   __syncthreads();
@@ -513,12 +606,15 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   uint32_t ph1 = 0, ph2 = 0, phA = 0, phB = 0;
   TC2_STAMP(1);
 #pragma unroll 1
-  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N, FRAME>(a, unit, pass, tmemBase, ph1, ph2, phA, phB);
+  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N, FRAME>(a, unit, pass, tmemBase, ph1, ph2, phA, phB, FRAME ? pre : nullptr);
   TC2_STAMP(2);
 
   // ---- costs leave the SM ------------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  // the common case - every PU of the CTA evaluated - copies the accumulators without a per-element state look-up
+  bool mine = true;
+  if (FRAME) for (int i = tid; i < C::CTUS * 256; i += kThreads) mine = mine && ((i & 255) >= C::PUS || smem[C::VALID_OFF + i] == kPuEvaluate);
+  const bool allEval = __syncthreads_and(mine) && unit * C::CTUS + C::CTUS <= a.totalCtus;
   const FrameSource& fs = a.fs;
   if (!FRAME) {
     // batch mode: row outIndex of the caller's [nPU][35] table per PU
@@ -542,12 +638,21 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
       const uint8_t v = valid[i / kNumModes];
       return v == kPuEvaluate ? (LOG2N == 2 ? (uint32_t)a16[i] : a32[i]) : (v == kPuPruned ? kCostPruned : kCostOutside);
     };
+    auto valAll = [&](int i) -> uint32_t { return LOG2N == 2 ? (uint32_t)a16[i] : a32[i]; };
     if (fs.out) {
       uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
+      if (allEval) {
 #pragma unroll 4
-      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = val(i);
+        for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valAll(i);
+      } else {
+#pragma unroll 4
+        for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = val(i);
+      }
     }
-    if (fs.outPacked) store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, val);
+    if (fs.outPacked) {
+      if (allEval) store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, valAll);
+      else store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, val);
+    }
   }
   if (warp == 0) tmem_dealloc(tmemBase, 256);
   TC2_STAMP(3);

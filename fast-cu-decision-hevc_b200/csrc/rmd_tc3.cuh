@@ -394,16 +394,20 @@ CUCD_HD void build_unfiltered16(int tid, int ctu, int W, int H, int ctuX, int ct
     return;
   }
   if (sub == 0) { put_ref16<LOG2N>(store, ctu, p, 0, 0, cval); put_ref16<LOG2N>(store, ctu, p, 1, 0, cval); }
-  int dcSum = 0;
+  int dcSum = 0, vals[SPT];                          // loads first, stores afterwards (see tc2::build_unfiltered)
 #pragma unroll
   for (int e = 0; e < SPT; e++) {
     const int j = sub * SPT + e;                     // 0 .. 4N-1
     const int o = j >= 2 * N, k = j - o * 2 * N + 1; // T[k] or L[k]
-    int v;
-    if (o == 0) v = k <= a.lenT ? rowT[k] : tailT;
-    else v = k <= a.lenL ? colL[k * P] : firstAvail;
-    put_ref16<LOG2N>(store, ctu, p, o, k, v);
-    if (k <= N) dcSum += v;
+    if (o == 0) vals[e] = k <= a.lenT ? rowT[k] : tailT;
+    else vals[e] = k <= a.lenL ? colL[k * P] : firstAvail;
+    if (k <= N) dcSum += vals[e];
+  }
+#pragma unroll
+  for (int e = 0; e < SPT; e++) {
+    const int j = sub * SPT + e;
+    const int o = j >= 2 * N, k = j - o * 2 * N + 1;
+    put_ref16<LOG2N>(store, ctu, p, o, k, vals[e]);
   }
   int* dst = reinterpret_cast<int*>(smem + C::DC_OFF) + ctu * 64 + p;
 #if defined(__CUDA_ARCH__)
@@ -443,16 +447,21 @@ CUCD_HD void build_filtered16(int tid, int ctu, int strongEnabled, int bitDepth,
     const int c = strong ? tl : (ld_s16(L + 2) + 2 * tl + ld_s16(T + 2) + 2) >> 2;
     put(0, 0, c); put(1, 0, c);
   }
+  int vals[SPT];
 #pragma unroll
   for (int e = 0; e < SPT; e++) {
     const int j = sub * SPT + e;
     const int o = j >= 2 * N, k = j - o * 2 * N + 1;
     const unsigned char* A = o ? L : T;
-    int v;
-    if (k == 2 * N) v = ld_s16(A + 2 * k);
-    else if (strong) v = o ? (k * bl + (2 * N - k) * tl + N) >> (LOG2N + 1) : ((2 * N - k) * tl + k * tr + N) >> (LOG2N + 1);
-    else v = (ld_s16(A + 2 * (k - 1)) + 2 * ld_s16(A + 2 * k) + ld_s16(A + 2 * (k + 1)) + 2) >> 2;
-    put(o, k, v);
+    if (k == 2 * N) vals[e] = ld_s16(A + 2 * k);
+    else if (strong) vals[e] = o ? (k * bl + (2 * N - k) * tl + N) >> (LOG2N + 1) : ((2 * N - k) * tl + k * tr + N) >> (LOG2N + 1);
+    else vals[e] = (ld_s16(A + 2 * (k - 1)) + 2 * ld_s16(A + 2 * k) + ld_s16(A + 2 * (k + 1)) + 2) >> 2;
+  }
+#pragma unroll
+  for (int e = 0; e < SPT; e++) {
+    const int j = sub * SPT + e;
+    const int o = j >= 2 * N, k = j - o * 2 * N + 1;
+    put(o, k, vals[e]);
   }
 }
 // projected samples of a negative-angle round (tc2::build_ext_group): store[main][-j] = store[side][(128 + j*inv) >> 8],

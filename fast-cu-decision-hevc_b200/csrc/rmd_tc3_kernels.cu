@@ -86,34 +86,59 @@ __device__ __forceinline__ bool elect_one3() {
   return pred != 0;
 }
 
+// Phase 1 of the prologue (rmd_tc3.cuh stage_tile16) split into its global loads and its shared-memory stores, so that the
+// loads of all the CTA's CTUs, the Hadamard operand and the rows' source tiles share one memory round trip (tc3_body).
+struct TileLoad { uint4 v[2]; int left, top; };
+__device__ __forceinline__ void tile_load(int tid, const int16_t* rec, int recStride, int W, int H, int ctuX, int ctuY, TileLoad& t) {
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const int idx = tid + it * kThreads, y = idx >> 3, x = (idx & 7) * 8;
+    t.v[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (ctuY + y < H && ctuX + x < W) t.v[it] = *reinterpret_cast<const uint4*>(rec + (size_t)(ctuY + y) * recStride + ctuX + x);
+  }
+  t.left = 0; t.top = 0;
+  if (ctuX > 0 && tid < 64 && ctuY + tid < H) t.left = rec[(size_t)(ctuY + tid) * recStride + ctuX - 1];
+  const int gx = ctuX - 1 + tid;
+  if (ctuY > 0 && tid < 129 && gx >= 0 && gx < W) t.top = rec[(size_t)(ctuY - 1) * recStride + gx];
+}
+template <int LOG2N>
+__device__ __forceinline__ void tile_store(int tid, int W, int H, int ctuX, int ctuY, const TileLoad& t, uint16_t* dst) {
+  typedef Cfg<LOG2N> C;
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const int idx = tid + it * kThreads, y = idx >> 3, x = (idx & 7) * 8;
+    if (ctuY + y >= H || ctuX + x >= W) continue;
+    uint2* d = reinterpret_cast<uint2*>(dst + y * C::TILE_PITCH + 8 + x);      // rows are 8-byte aligned (pitch 136 B)
+    d[0] = make_uint2(t.v[it].x, t.v[it].y); d[1] = make_uint2(t.v[it].z, t.v[it].w);
+  }
+  if (ctuX > 0 && tid < 64 && ctuY + tid < H) dst[tid * C::TILE_PITCH + 7] = (uint16_t)t.left;
+  const int gx = ctuX - 1 + tid;
+  if (ctuY > 0 && tid < 129 && gx >= 0 && gx < W) dst[C::TILE_TOP + 7 + tid] = (uint16_t)t.top;
+}
+
 // ---- prologue: reference arrays of the CTA's CTUs (rmd_tc3.cuh phases 1-3) --------------------------------
 template <int LOG2N>
-__device__ __forceinline__ void tc3_prologue(const Tc3Args& a, const int unit) {
+__device__ __forceinline__ void tc3_prologue(const Tc3Args& a, const int unit, const TileLoad* tl, const int* ctuX, const int* ctuY) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N;
   unsigned char* smem = smem3;
   const int tid = threadIdx.x;
   const FrameSource& fs = a.fs;
-  int ctuX[C::CTUS], ctuY[C::CTUS];
 #pragma unroll
   for (int c = 0; c < C::CTUS; c++) {
     const int cg = unit * C::CTUS + c;
     uint8_t* valid = smem + C::VALID_OFF + c * 256;
-    ctuX[c] = -1; ctuY[c] = -1;
-    if (cg >= a.totalCtus) {                                   // CTA-uniform
+    if (ctuX[c] < 0) {                                         // CTA-uniform
       for (int p = tid; p < C::PUS; p += kThreads) valid[p] = 0;
       continue;
     }
-    const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-    ctuX[c] = (ctu % fs.ctusPerRow) * 64; ctuY[c] = (ctu / fs.ctusPerRow) * 64;
     const uint8_t* need = fs.needed ? fs.needed + ((size_t)cg * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) : nullptr;
     for (int p = tid; p < C::PUS; p += kThreads) {
       int px, py; demorton(p, px, py);
       const bool inside = (ctuX[c] + (px + 1) * N <= fs.W) && (ctuY[c] + (py + 1) * N <= fs.H);
       valid[p] = !inside ? kPuOutside : ((need && !need[p]) ? kPuPruned : kPuEvaluate);
     }
-    stage_tile16<LOG2N>(tid, kThreads, fs.rec + (size_t)pic * fs.recPicStride, fs.recStride, fs.W, fs.H, ctuX[c], ctuY[c],
-                        reinterpret_cast<uint16_t*>(smem + C::TILE_OFF + c * C::TILE_BYTES));
+    tile_store<LOG2N>(tid, fs.W, fs.H, ctuX[c], ctuY[c], tl[c], reinterpret_cast<uint16_t*>(smem + C::TILE_OFF + c * C::TILE_BYTES));
   }
   __syncthreads();
 #pragma unroll
@@ -130,9 +155,22 @@ __device__ __forceinline__ void tc3_prologue(const Tc3Args& a, const int unit) {
 
 // ---- the mode rounds of one pass (pipeline of rmd_tc2_kernels.cu tc2_pass) ------------------------------------------
 // TMEM per row group: D1 = columns [0, 64) (A2 aliases its first 32 once they have been read), D2 = [64, 128).
+// first sample of the row's source tile (tile origin inside the CTU from the row map)
+template <int LOG2N>
+__device__ __forceinline__ const int16_t* frame_src_ptr(const FrameSource& fs, const Row& r, int cg, int& tileX, int& tileY) {
+  constexpr int N = Cfg<LOG2N>::N;
+  const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
+  int px, py; demorton(r.pu, px, py);
+  if (LOG2N == 2) { px *= 8; py *= 8; }
+  else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
+  tileX = (ctu % fs.ctusPerRow) * 64 + px; tileY = (ctu / fs.ctusPerRow) * 64 + py;
+  return fs.org + (size_t)pic * fs.orgPicStride + (size_t)tileY * fs.orgStride + tileX;
+}
+
+// `pre`: the eight rows of the source tile of pass 0, loaded by tc3_body before the prologue
 template <int LOG2N>
 __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2,
-                                         uint32_t& phA, uint32_t& phB, uint32_t& phT) {
+                                         uint32_t& phA, uint32_t& phB, uint32_t& phT, const uint4* pre) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N, SEG = RowSeg<LOG2N>::value;
   unsigned char* smem = smem3;
@@ -157,15 +195,17 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
   uint32_t p[32];                                   // the row's current tile as fp16 pairs: word = pixels (2w, 2w + 1)
   if (ok) {
     uint32_t raw[32];
-    const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
-    int px, py; demorton(r.pu, px, py);
-    if (LOG2N == 2) { px *= 8; py *= 8; }
-    else { px = px * N + (r.o ? r.v0 : r.u0); py = py * N + (r.o ? r.u0 : r.v0); }
-    const int16_t* src = fs.org + (size_t)pic * fs.orgPicStride + (size_t)((ctu / fs.ctusPerRow) * 64 + py) * fs.orgStride + (ctu % fs.ctusPerRow) * 64 + px;
+    if (pass == 0) {
 #pragma unroll
-    for (int y = 0; y < 8; y++) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)y * fs.orgStride);
-      raw[4 * y] = v.x; raw[4 * y + 1] = v.y; raw[4 * y + 2] = v.z; raw[4 * y + 3] = v.w;
+      for (int y = 0; y < 8; y++) { raw[4 * y] = pre[y].x; raw[4 * y + 1] = pre[y].y; raw[4 * y + 2] = pre[y].z; raw[4 * y + 3] = pre[y].w; }
+    } else {
+      int tx, ty;
+      const int16_t* src = frame_src_ptr<LOG2N>(fs, r, cg, tx, ty);
+#pragma unroll
+      for (int y = 0; y < 8; y++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)y * fs.orgStride);
+        raw[4 * y] = v.x; raw[4 * y + 1] = v.y; raw[4 * y + 2] = v.z; raw[4 * y + 3] = v.w;
+      }
     }
     if (LOG2N == 2) region_to_quadrants16(raw, p, r.o != 0);
     else if (r.o) tile_transpose16(raw, p);
@@ -203,10 +243,12 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
   constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
 
   // -(source) x H + A2 (already stored to TMEM by every thread) x H -> D2
-  auto issue_mma2 = [&]() {
+  auto arrive_mma2 = [&]() {
     tmem_st_wait3();
     tc_fence_before();
     mbar_arrive3(arrA);
+  };
+  auto fire_mma2 = [&]() {
     if (issuer) {
       mbar_wait(uarrA, phA);
       tc_fence_after();
@@ -229,6 +271,7 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
     }
     phA ^= 1u;
   };
+  auto issue_mma2 = [&]() { arrive_mma2(); fire_mma2(); };
   auto wait_mma2 = [&]() { mbar_wait(mbar2, ph2); ph2 ^= 1u; tc_fence_after(); };
   // window / record operand (shared memory) x weights -> D1
   auto issue_mma1 = [&]() {
@@ -374,7 +417,8 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
     // does after writing its projected samples)
     const bool lateWindow = LOG2N != 2 && am > -8 && angleNext < 0;
     if (lateWindow) build_ext_group16<LOG2N>(rowTid, grp, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
-    issue_mma2();
+    arrive_mma2();
+    fire_mma2();
     if (am > -8 && !lateWindow) stage_window(am - 1, angleNext);
     wait_mma2();
     if (lateWindow) stage_window(am - 1, angleNext);
@@ -428,9 +472,40 @@ __device__ __noinline__ void tc3_body(const Tc3Args& a, const int unit) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmemSlot, 256);
+  // Every global load of the set-up is issued here, before anything waits: the Hadamard operand, the reconstruction
+  // neighbourhoods of the CTA's CTUs and the rows' source tiles of pass 0 share ONE memory round trip.
+  constexpr int HAD_V = C::HAD_BYTES / 16;         // 512 (two per thread) or 32
+  uint4 hadV[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
   {
     const uint4* h = reinterpret_cast<const uint4*>(a.had + (LOG2N == 2 ? 8192 : 0));
-    for (int i = tid; i < C::HAD_BYTES / 16; i += kThreads) reinterpret_cast<uint4*>(smem + C::HAD_OFF)[i] = h[i];
+    if (tid < HAD_V) hadV[0] = h[tid];
+    if (tid + kThreads < HAD_V) hadV[1] = h[tid + kThreads];
+  }
+  int ctuX[C::CTUS], ctuY[C::CTUS];
+  TileLoad tl[C::CTUS];
+#pragma unroll
+  for (int c = 0; c < C::CTUS; c++) {
+    const int cg = unit * C::CTUS + c;
+    ctuX[c] = -1; ctuY[c] = -1;
+    if (cg >= a.totalCtus) continue;                           // CTA-uniform
+    const int pic = cg / a.fs.ctusPerPic, ctu = cg - pic * a.fs.ctusPerPic;
+    ctuX[c] = (ctu % a.fs.ctusPerRow) * 64; ctuY[c] = (ctu / a.fs.ctusPerRow) * 64;
+    tile_load(tid, a.fs.rec + (size_t)pic * a.fs.recPicStride, a.fs.recStride, a.fs.W, a.fs.H, ctuX[c], ctuY[c], tl[c]);
+  }
+  uint4 pre[8];
+  {
+    const Row r0 = row_map<LOG2N>(tid, 0);
+    const int cg0 = unit * C::CTUS + r0.ctu;
+#pragma unroll
+    for (int y = 0; y < 8; y++) pre[y] = make_uint4(0u, 0u, 0u, 0u);
+    if (cg0 < a.totalCtus) {
+      int tx, ty;
+      const int16_t* src = frame_src_ptr<LOG2N>(a.fs, r0, cg0, tx, ty);
+      if (tx + 8 <= a.fs.W && ty + 8 <= a.fs.H) {
+#pragma unroll
+        for (int y = 0; y < 8; y++) pre[y] = *reinterpret_cast<const uint4*>(src + (size_t)y * a.fs.orgStride);
+      }
+    }
   }
   // every byte a window, a record or an accumulator update may touch starts as zero (finite operands; sums for N >= 16)
   {
@@ -443,8 +518,10 @@ __device__ __noinline__ void tc3_body(const Tc3Args& a, const int unit) {
     }
     reinterpret_cast<int*>(smem + C::DC_OFF)[tid] = 0;          // CTUS * 64 <= 256 sums
   }
+  if (tid < HAD_V) reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = hadV[0];
+  if (tid + kThreads < HAD_V) reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid + kThreads] = hadV[1];
   __syncthreads();
-  tc3_prologue<LOG2N>(a, unit);
+  tc3_prologue<LOG2N>(a, unit, tl, ctuX, ctuY);
   __syncthreads();
   // (N >= 8: the tiles aliased the window and source operands; every row rewrites all of its operand chunks before the first MMA)
   tc_fence_before();
@@ -454,11 +531,14 @@ __device__ __noinline__ void tc3_body(const Tc3Args& a, const int unit) {
   const uint32_t tmemBase = *tmemSlot;
   uint32_t ph1 = 0, ph2 = 0, phA = 0, phB = 0, phT = 0;
 #pragma unroll 1
-  for (int pass = 0; pass < C::PASSES; pass++) tc3_pass<LOG2N>(a, unit, pass, tmemBase, ph1, ph2, phA, phB, phT);
+  for (int pass = 0; pass < C::PASSES; pass++) tc3_pass<LOG2N>(a, unit, pass, tmemBase, ph1, ph2, phA, phB, phT, pre);
 
   // ---- costs leave the SM ------------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  // the common case - every PU of the CTA evaluated - copies the accumulators without a per-element state look-up
+  bool mine = true;
+  for (int i = tid; i < C::CTUS * 256; i += kThreads) mine = mine && ((i & 255) >= C::PUS || smem[C::VALID_OFF + i] == kPuEvaluate);
+  const bool allEval = __syncthreads_and(mine) && unit * C::CTUS + C::CTUS <= a.totalCtus;
   const FrameSource& fs = a.fs;
   for (int c = 0; c < C::CTUS; c++) {
     const int cgc = unit * C::CTUS + c;
@@ -470,12 +550,21 @@ __device__ __noinline__ void tc3_body(const Tc3Args& a, const int unit) {
       const uint8_t v = valid[i / kNumModes];
       return v == kPuEvaluate ? (LOG2N <= 3 ? (uint32_t)a16[i] : (a32[i] >> shift)) : (v == kPuPruned ? kCostPruned : kCostOutside);
     };
+    auto valAll = [&](int i) -> uint32_t { return LOG2N <= 3 ? (uint32_t)a16[i] : (a32[i] >> shift); };
     if (fs.out) {
       uint32_t* o = fs.out + ((size_t)cgc * kPusPerCtu + pu_offset_of_depth(6 - LOG2N)) * kNumModes;
+      if (allEval) {
 #pragma unroll 4
-      for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = val(i);
+        for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = valAll(i);
+      } else {
+#pragma unroll 4
+        for (int i = tid; i < C::PUS * kNumModes; i += kThreads) o[i] = val(i);
+      }
     }
-    if (fs.outPacked) store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, val);
+    if (fs.outPacked) {
+      if (allEval) store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, valAll);
+      else store_packed_depth<LOG2N>(fs.outPacked + (size_t)cgc * kPackedCtuBytes, tid, kThreads, val);
+    }
   }
   if (warp == 0) tmem_dealloc(tmemBase, 256);
 }

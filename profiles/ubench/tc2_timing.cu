@@ -38,7 +38,8 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dDbg, (size_t)blocks * 64 * 8)); CK(cudaMemset(dDbg, 0, (size_t)blocks * 64 * 8));
   CK(cudaMemcpyToSymbol(g_tc2Dbg, &dDbg, sizeof(dDbg)));
   FrameSource fs; fs.org = dOrg; fs.rec = dRec; fs.orgPicStride = (long long)pitch * H; fs.recPicStride = fs.orgPicStride; fs.orgStride = pitch; fs.recStride = pitch;
-  fs.W = W; fs.H = H; fs.ctusPerRow = ctusPerRow; fs.ctusPerPic = ctusPerPic; fs.out = dOut;
+  fs.W = W; fs.H = H; fs.ctusPerRow = ctusPerRow; fs.ctusPerPic = ctusPerPic; fs.out = dOut; fs.outPacked = nullptr; fs.needed = nullptr;
+  CK(configure_rmd_tc2_kernels());
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; it++) {
     cudaEventRecord(e0);
@@ -59,6 +60,19 @@ int main(int argc, char** argv) {
     printf("N=%2d: %5d CTAs  prologue %7.0f  passes %8.0f (first-pass setup %6.0f)  copy-out %6.0f  clk;  rounds am=8..-8:", 1 << l, n, pro / n, pass / n, setup / n, tail / n);
     for (int r = 0; r < 17; r++) printf(" %4.0f", rounds[r] / n);
     printf("\n");
+    {
+      double g[8] = {0};
+      for (int b = 0; b < blocks; b++) {
+        const long long* t = &d[(size_t)b * 64];
+        if (t[4] != l) continue;
+        g[0] += t[50] - t[0]; g[1] += t[51] - t[50]; g[2] += t[52] - t[51]; g[3] += (t[53] ? t[53] - t[52] : 0); g[4] += t[54] - (t[53] ? t[53] : t[52]); g[5] += t[1] - t[54];
+        g[6] += t[56] - t[1]; g[7] += t[57] - t[56];
+      }
+      { double h[4] = {0}; for (int b = 0; b < blocks; b++) { const long long* t = &d[(size_t)b * 64]; if (t[4] != l) continue; h[0] += t[58] - t[0]; h[1] += t[59] - t[58]; h[2] += t[60] - t[59]; h[3] += t[50] - t[60]; }
+        printf("      first phase: tmem alloc %5.0f | issue loads %5.0f | zero + first load lands %5.0f | second table store + sync %5.0f\n", h[0] / n, h[1] / n, h[2] / n, h[3] / n); }
+      printf("      prologue: alloc+tables+zero+sync %5.0f | tile staging+sync %5.0f | unfiltered %5.0f | sync %5.0f | filtered %5.0f | fences+sync %5.0f || pass set-up: source tile %5.0f | operands+planar/DC %5.0f\n",
+             g[0] / n, g[1] / n, g[2] / n, g[3] / n, g[4] / n, g[5] / n, g[6] / n, g[7] / n);
+    }
     for (int base = 30; base <= 40; base += 10) {
       double seg[8] = {0};
       for (int b = 0; b < blocks; b++) { const long long* t = &d[(size_t)b * 64]; if (t[4] != l) continue; for (int k = 0; k < 8; k++) seg[k] += t[base + k + 1] - t[base + k]; }
