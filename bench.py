@@ -515,12 +515,19 @@ def run_ours(args, rank, world, local_rank):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = ALGO_BYTES_PER_CTU * ctus_step_gpu / (rmd_ms * 1e-3) / 1e9
-    traffic = None            # DRAM bytes per launch, scaled from the committed ncu --set full capture of the same kernel
-    tpath = os.path.join(ROOT, "profiles", "r01_rmd_traffic.json")
-    if bd == 8 and os.path.exists(tpath):
-        traffic = float(json.load(open(tpath))["dram_bytes_per_ctu"]) * ctus_step_gpu
-    roofline = {"bound": "hbm", "kernel": ("rmd_frame_kernel" if os.environ.get("CUCD_RMD_PATH") == "alu" else ("rmd_frame_tc2_kernel" if bd == 8 else "rmd_frame_tc3_kernel")), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "launch_ms": rmd_ms, "launches_timed": n_timed, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CTU * ctus_step_gpu,
+    kernel_name = "rmd_frame_kernel" if os.environ.get("CUCD_RMD_PATH") == "alu" else ("rmd_frame_tc2_kernel" if bd == 8 else "rmd_frame_tc3_kernel")
+    # DRAM bytes per launch: dram__bytes_read + dram__bytes_write per CTU of the committed ncu --set full capture of the SAME kernel
+    # (profiles/r02/rmd_traffic.json, cold-cache 2040-CTU launches) x the CTUs of this launch; null when that kernel has no capture
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02", "rmd_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if kernel_name in tj:
+            traffic = float(tj[kernel_name]["dram_bytes_per_ctu"]) * ctus_step_gpu
+            traffic_src = "profiles/r02/rmd_traffic.json: %.0f B/CTU measured by ncu on a %d-CTU launch, scaled to this launch; cost-table lines still dirty in L2 at kernel end are not counted" % (
+                tj[kernel_name]["dram_bytes_per_ctu"], tj[kernel_name]["ctus_per_launch"])
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "launch_ms": rmd_ms, "launches_timed": n_timed, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CTU * ctus_step_gpu,
                 "peak_source": peak_src,
                 "note": "launch_ms is the CUDA-event window around the RMD launch on the caller's stream; the small feature kernels run beside it on a high-priority stream and take part of that window. RMD is compute bound by construction (~140 int-op/B, SURVEY.md 8d): predictions and Hadamard run on tcgen05 (kind::i8 for 8-bit content, kind::f16 with exact integer operands for 9/10-bit content), "
                         "the epilogues on the integer ALU; the HBM fraction is small; see profiles/ for pipe utilisation"}
