@@ -25,9 +25,12 @@ using namespace tc2;
 // CUCD_TC2_TIMING (profiles/ubench/tc2_timing.cu only): per-CTA clock64 stamps of thread 0 at phase boundaries
 #ifdef CUCD_TC2_TIMING
 __device__ long long* g_tc2Dbg = nullptr;
-#define TC2_STAMP(i) do { if (g_tc2Dbg && threadIdx.x == 0) g_tc2Dbg[(size_t)blockIdx.x * 64 + (i)] = clock64(); } while (0)
+#ifndef CUCD_TC2_STAMP_TID
+#define CUCD_TC2_STAMP_TID 0    // which thread stamps: 0 = the MMA-issuing warp of row group 0, 32 / 96 = other warps of that group
+#endif
+#define TC2_STAMP(i) do { if (g_tc2Dbg && threadIdx.x == CUCD_TC2_STAMP_TID) g_tc2Dbg[(size_t)blockIdx.x * 64 + (i)] = clock64(); } while (0)
 // finer stamps inside the rounds am = 4 (slots 30..) and am = -4 (slots 40..) of the first pass
-#define TC2_FINE(i) do { if (g_tc2Dbg && threadIdx.x == 0 && pass == 0 && (am == 4 || am == -4)) g_tc2Dbg[(size_t)blockIdx.x * 64 + (am == 4 ? 30 : 40) + (i)] = clock64(); } while (0)
+#define TC2_FINE(i) do { if (g_tc2Dbg && threadIdx.x == CUCD_TC2_STAMP_TID && pass == 0 && (am == 4 || am == -4)) g_tc2Dbg[(size_t)blockIdx.x * 64 + (am == 4 ? 30 : 40) + (i)] = clock64(); } while (0)
 #else
 #define TC2_STAMP(i) do { } while (0)
 #define TC2_FINE(i) do { } while (0)
