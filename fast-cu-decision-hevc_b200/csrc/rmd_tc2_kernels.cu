@@ -35,6 +35,13 @@ __device__ long long* g_tc2Dbg = nullptr;
 #define TC2_STAMP(i) do { } while (0)
 #define TC2_FINE(i) do { } while (0)
 #endif
+// CUCD_TC2_WARPSKEW (profiles/ubench/tc2_skew.cu only): lane 0 of the four warps of row group 0 stamps the events of round am = 4
+#ifdef CUCD_TC2_WARPSKEW
+__device__ long long* g_tc2Skew = nullptr;
+#define TC2_SKEW(e) do { if (g_tc2Skew && pass == 0 && am == 4 && (threadIdx.x & 31) == 0 && threadIdx.x < 128) g_tc2Skew[(size_t)blockIdx.x * 64 + (threadIdx.x >> 5) * 16 + (e)] = clock64(); } while (0)
+#else
+#define TC2_SKEW(e) do { } while (0)
+#endif
 
 namespace {
 
@@ -469,8 +476,10 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     const int buf = (8 - am) & 1;
     const int angleNext2 = am > -7 ? angle_of_am(am - 2) : 0;
     TC2_FINE(0);
+    TC2_SKEW(0);
     wait_mma1();
     TC2_FINE(1);
+    TC2_SKEW(1);
     // epilogue 1: byte 1 of every accumulator is the predicted pixel
     {
       uint32_t v[32];
@@ -486,6 +495,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     }
     tmem_st16(tA2 + laneOff, p);
     TC2_FINE(2);
+    TC2_SKEW(2);
     // Projected samples of the next (negative) angle.  The gathers of round am have all finished: MMA 1 of this round was only
     // issued after every row of the group had announced its window (arrB).  The OTHER rows' projected samples are complete once
     // MMA 2 below has been issued (every row announces arrA after this point), i.e. after wait_mma2: a window that may read
@@ -493,22 +503,28 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     const bool lateWindow = LOG2N != 2 && am > -8 && angleNext < 0;
     if (lateWindow) build_ext_group<LOG2N>(rowTid, grp, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
     TC2_FINE(3);
+    TC2_SKEW(3);
     arrive_mma2();
     fire_mma2();
     TC2_FINE(4);
+    TC2_SKEW(4);
     if (am > -8) {
       stage_weights(buf ^ 1);
       if (!lateWindow) stage_window(am - 1, angleNext, buf ^ 1);
       if (am > -7) prefetch_b1(am - 2, angleNext2);
     }
     TC2_FINE(5);
+    TC2_SKEW(5);
     wait_mma2();
     TC2_FINE(6);
+    TC2_SKEW(6);
     if (lateWindow) stage_window(am - 1, angleNext, buf ^ 1);
     if (am > -8) issue_mma1(buf ^ 1);
     TC2_FINE(7);
+    TC2_SKEW(7);
     cost_out(r.o ? 10 - am : 26 + am, !(r.o && am == -8));
     TC2_FINE(8);
+    TC2_SKEW(8);
     if (pass == 0) TC2_STAMP(9 + 8 - am);
     angle = angleNext; angleNext = angleNext2;
   }
