@@ -147,6 +147,8 @@ def load_library():
     lib.cucd_set_cur_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.cucd_me_sad_surface.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MeDesc), C.c_void_p]
     lib.cucd_me_subpel_cost.argtypes = [C.c_void_p, C.c_int, C.POINTER(_SubpelDesc), C.c_void_p]
+    lib.cucd_me_sad_surface_src.argtypes = [C.c_void_p, C.c_int, C.POINTER(_MeDesc), C.c_void_p, C.c_void_p]
+    lib.cucd_me_subpel_cost_src.argtypes = [C.c_void_p, C.c_int, C.POINTER(_SubpelDesc), C.c_void_p, C.c_void_p]
     lib.cucd_intra_tu_forward.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cucd_intra_tu_recon.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cucd_intra_tu_code.argtypes = [C.c_void_p, C.c_int, C.POINTER(_TuDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -421,8 +423,9 @@ class Engine:
     def dev_me_subpel_cost(self, stream, arr, n, d_out):
         self._check(self.lib.cucd_dev_me_subpel_cost(self.h, stream, n, arr, d_out), "cucd_dev_me_subpel_cost")
 
-    def me_sad_surface(self, descs):
-        """descs: list of dicts(x,y,w,h,ref_idx,left,right,top,bottom,sub_shift). Returns list of (rows, cols) uint32 surfaces."""
+    def me_sad_surface(self, descs, src=None):
+        """descs: list of dicts(x,y,w,h,ref_idx,left,right,top,bottom,sub_shift). Returns list of (rows, cols) uint32 surfaces.
+        src: optional int16 array with the PUs' own w x h source blocks back to back (cucd_me_sad_surface_src: bi-predictive search)."""
         n = len(descs)
         arr = (_MeDesc * max(n, 1))()
         total = 0
@@ -433,22 +436,33 @@ class Engine:
             shapes.append((d["bottom"] - d["top"] + 1, d["right"] - d["left"] + 1))
             total += shapes[-1][0] * shapes[-1][1]
         out = np.zeros(max(total, 1), np.uint32)
-        self._check(self.lib.cucd_me_sad_surface(self.h, n, arr, out.ctypes.data), "cucd_me_sad_surface")
+        if src is None:
+            self._check(self.lib.cucd_me_sad_surface(self.h, n, arr, out.ctypes.data), "cucd_me_sad_surface")
+        else:
+            src = np.ascontiguousarray(src, np.int16)
+            assert src.size == sum(int(d["w"]) * int(d["h"]) for d in descs)
+            self._check(self.lib.cucd_me_sad_surface_src(self.h, n, arr, src.ctypes.data, out.ctypes.data), "cucd_me_sad_surface_src")
         res, off = [], 0
         for r, c in shapes:
             res.append(out[off:off + r * c].reshape(r, c))
             off += r * c
         return res
 
-    def me_subpel_cost(self, descs):
-        """descs: list of dicts(x,y,w,h,ref_idx,mvx,mvy,use_hadamard). Returns (n, 7, 7) uint32: [dy+3][dx+3], quarter-pel offsets."""
+    def me_subpel_cost(self, descs, src=None):
+        """descs: list of dicts(x,y,w,h,ref_idx,mvx,mvy,use_hadamard). Returns (n, 7, 7) uint32: [dy+3][dx+3], quarter-pel offsets.
+        src: optional int16 array with the PUs' own source blocks back to back (cucd_me_subpel_cost_src)."""
         n = len(descs)
         arr = (_SubpelDesc * max(n, 1))()
         for i, d in enumerate(descs):
             for k in ("x", "y", "w", "h", "ref_idx", "mvx", "mvy", "use_hadamard"):
                 setattr(arr[i], k, int(d[k]))
         out = np.zeros((n, 7, 7), np.uint32)
-        self._check(self.lib.cucd_me_subpel_cost(self.h, n, arr, out.ctypes.data), "cucd_me_subpel_cost")
+        if src is None:
+            self._check(self.lib.cucd_me_subpel_cost(self.h, n, arr, out.ctypes.data), "cucd_me_subpel_cost")
+        else:
+            src = np.ascontiguousarray(src, np.int16)
+            assert src.size == sum(int(d["w"]) * int(d["h"]) for d in descs)
+            self._check(self.lib.cucd_me_subpel_cost_src(self.h, n, arr, src.ctypes.data, out.ctypes.data), "cucd_me_subpel_cost_src")
         return out
 
     # ---- intra luma TU coding (xIntraCodingTUBlock) ------------------------------------------------

@@ -360,9 +360,11 @@ static int sync_ref_table(cucd_handle* h) {
 }
 
 // validate the PUs, build job + tile records into `scratch` (pinned); returns the sizes through the references
-static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinBuf<uint8_t>& scratch, size_t& jobBytes, size_t& tileBytes, long long& total, long long& nTiles) {
+// ownBlocks: the source blocks are the caller's (cucd_me_sad_surface_src): offsets run through the packed block array
+static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinBuf<uint8_t>& scratch, size_t& jobBytes, size_t& tileBytes, long long& total, long long& nTiles,
+                         bool ownBlocks = false, size_t* srcSamples = nullptr) {
   const int W = h->cfg.width, H = h->cfg.height;
-  const int tileRows = h->cfg.bit_depth == 8 ? 16 : 8;     // me_sad_u8_kernel covers 32 x 16 candidates per CTA, me_sad_kernel 32 x 8
+  const int tileRows = (h->cfg.bit_depth == 8 && !ownBlocks) ? 16 : 8;     // me_sad_u8_kernel covers 32 x 16 candidates per CTA, me_sad_kernel 32 x 8
   total = 0; nTiles = 0;
   for (int i = 0; i < nPU; i++) {
     const cucd_me_desc& d = desc[i];
@@ -384,12 +386,13 @@ static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinB
   MeJob* jobs = reinterpret_cast<MeJob*>(scratch.p);
   int32_t* tileJob = reinterpret_cast<int32_t*>(scratch.p + jobBytes);
   int32_t* tileIdx = reinterpret_cast<int32_t*>(scratch.p + jobBytes + tileBytes);
-  long long off = 0; size_t nt = 0;
+  long long off = 0; size_t nt = 0, blockOff = 0;
   for (int i = 0; i < nPU; i++) {
     const cucd_me_desc& d = desc[i];
     const RefPlane& r = h->refs[d.ref_idx];
     MeJob& j = jobs[i];
-    j.curOff = d.y * h->curStride + d.x;
+    j.curOff = ownBlocks ? (int32_t)blockOff : d.y * h->curStride + d.x;
+    blockOff += (size_t)d.w * d.h;
     j.refOff = (d.y + r.marginY) * r.stride + d.x + r.marginX;
     j.refSlot = d.ref_idx; j.w = (int16_t)d.w; j.h = (int16_t)d.h;
     j.left = (int16_t)d.left; j.right = (int16_t)d.right; j.top = (int16_t)d.top; j.bottom = (int16_t)d.bottom;
@@ -402,25 +405,27 @@ static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinB
     for (int t = 0; t < tiles; t++) { tileJob[nt] = i; tileIdx[nt] = t; nt++; }
     off += (long long)cols * rows;
   }
+  if (blockOff > 0x7fffffffull) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface_src: batch too large");
+  if (srcSamples) *srcSamples = blockOff;
   return CUCD_OK;
 }
 
-int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut) {
-  if (!h || nPU < 0 || (nPU > 0 && (!desc || !sadOut))) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: bad argument");
-  if (nPU == 0) return CUCD_OK;
-  LOCK(h);
-  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: cucd_set_cur_picture not called");
+static int me_sad_surface_impl(cucd_handle* h, int nPU, const cucd_me_desc* desc, const int16_t* src, uint32_t* sadOut) {
+  const bool own = src != nullptr;
+  if (!own && !h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: cucd_set_cur_picture not called");
   CK(cudaSetDevice(h->cfg.device));
-  size_t jobBytes, tileBytes; long long total, nTiles;
-  const int rc = me_build_jobs(h, nPU, desc, h->hScratch, jobBytes, tileBytes, total, nTiles);
+  size_t jobBytes, tileBytes, srcSamples = 0; long long total, nTiles;
+  const int rc = me_build_jobs(h, nPU, desc, h->hScratch, jobBytes, tileBytes, total, nTiles, own, &srcSamples);
   if (rc != CUCD_OK) return rc;
   if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
   BatchIo io(h);
   const int iAll = io.add_in(h->hScratch.p, jobBytes + 2 * tileBytes, true);
+  const int iSrc = own ? io.add_in(src, srcSamples * sizeof(int16_t)) : -1;
   const int oSad = io.add_out(sadOut, (size_t)total * sizeof(uint32_t));
   if (io.reserve() != CUCD_OK || io.upload(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   MePlanes mp;
-  mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
+  mp.cur = own ? io.din<int16_t>(iSrc) : h->dCur.p; mp.curStride = own ? 0 : h->curStride;
+  mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
   const uint8_t* dAll = io.din<uint8_t>(iAll);
   CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_me_sad(mp, reinterpret_cast<const MeJob*>(dAll), nPU, reinterpret_cast<const int32_t*>(dAll + jobBytes), reinterpret_cast<const int32_t*>(dAll + jobBytes + tileBytes),
@@ -429,6 +434,18 @@ int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint3
   if (io.download(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   flush_launches(h);
   return CUCD_OK;
+}
+int cucd_me_sad_surface(cucd_handle* h, int nPU, const cucd_me_desc* desc, uint32_t* sadOut) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !sadOut))) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  return me_sad_surface_impl(h, nPU, desc, nullptr, sadOut);
+}
+int cucd_me_sad_surface_src(cucd_handle* h, int nPU, const cucd_me_desc* desc, const int16_t* src, uint32_t* sadOut) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !src || !sadOut))) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface_src: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  return me_sad_surface_impl(h, nPU, desc, src, sadOut);
 }
 
 // Device-resident variants: the surfaces / cost tables stay in HBM (d_out), everything is enqueued on `stream` and the call does
@@ -466,7 +483,8 @@ int cucd_dev_me_sad_surface(cucd_handle* h, void* stream, int nPU, const cucd_me
 // ------------------------------------------------------------------------------------------------
 // Fractional-pel refinement: distortion of the 49 quarter-pel positions around an integer MV
 // ------------------------------------------------------------------------------------------------
-static int subpel_build_jobs(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, PinBuf<uint8_t>& scratch) {
+static int subpel_build_jobs(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, PinBuf<uint8_t>& scratch, bool ownBlocks = false, size_t* srcSamples = nullptr) {
+  size_t blockOff = 0;
   const int W = h->cfg.width, H = h->cfg.height;
   CK(scratch.reserve((size_t)nPU * sizeof(SubpelJob) + 64));
   SubpelJob* jobs = reinterpret_cast<SubpelJob*>(scratch.p);
@@ -479,34 +497,50 @@ static int subpel_build_jobs(cucd_handle* h, int nPU, const cucd_subpel_desc* de
     if (d.x + d.mvx - 4 < -r.marginX || d.y + d.mvy - 4 < -r.marginY || d.x + d.mvx + d.w + 4 > W - 1 + r.marginX || d.y + d.mvy + d.h + 4 > H - 1 + r.marginY)
       return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: the interpolation support leaves the padded reference picture");
     SubpelJob& j = jobs[i];
-    j.curOff = d.y * h->curStride + d.x;
+    j.curOff = ownBlocks ? (int32_t)blockOff : d.y * h->curStride + d.x;
+    blockOff += (size_t)d.w * d.h;
     j.refOff = (d.y + d.mvy + r.marginY) * r.stride + d.x + d.mvx + r.marginX;
     j.refSlot = d.ref_idx; j.w = (int16_t)d.w; j.h = (int16_t)d.h; j.useHadamard = d.use_hadamard ? 1 : 0;
   }
+  if (blockOff > 0x7fffffffull) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost_src: batch too large");
+  if (srcSamples) *srcSamples = blockOff;
   return CUCD_OK;
 }
 
-int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, uint32_t* cost) {
-  if (!h || nPU < 0 || (nPU > 0 && (!desc || !cost))) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: bad argument");
-  if (nPU == 0) return CUCD_OK;
-  LOCK(h);
-  if (!h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: cucd_set_cur_picture not called");
+static int me_subpel_cost_impl(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, const int16_t* src, uint32_t* cost) {
+  const bool own = src != nullptr;
+  if (!own && !h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: cucd_set_cur_picture not called");
   CK(cudaSetDevice(h->cfg.device));
-  const int rc = subpel_build_jobs(h, nPU, desc, h->hScratch);
+  size_t srcSamples = 0;
+  const int rc = subpel_build_jobs(h, nPU, desc, h->hScratch, own, &srcSamples);
   if (rc != CUCD_OK) return rc;
   if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
   BatchIo io(h);
   const int iJobs = io.add_in(h->hScratch.p, (size_t)nPU * sizeof(SubpelJob), true);
+  const int iSrc = own ? io.add_in(src, srcSamples * sizeof(int16_t)) : -1;
   const int oCost = io.add_out(cost, (size_t)nPU * CUCD_SUBPEL_POINTS * sizeof(uint32_t));
   if (io.reserve() != CUCD_OK || io.upload(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   MePlanes mp;
-  mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
+  mp.cur = own ? io.din<int16_t>(iSrc) : h->dCur.p; mp.curStride = own ? 0 : h->curStride;
+  mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
   CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_me_subpel(mp, io.din<SubpelJob>(iJobs), nPU, io.dout<uint32_t>(oCost), h->sMain, &h->launches));
   CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
   if (io.download(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   flush_launches(h);
   return CUCD_OK;
+}
+int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, uint32_t* cost) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !cost))) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  return me_subpel_cost_impl(h, nPU, desc, nullptr, cost);
+}
+int cucd_me_subpel_cost_src(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, const int16_t* src, uint32_t* cost) {
+  if (!h || nPU < 0 || (nPU > 0 && (!desc || !src || !cost))) return fail(h, CUCD_ERR_INVALID, "cucd_me_subpel_cost_src: bad argument");
+  if (nPU == 0) return CUCD_OK;
+  LOCK(h);
+  return me_subpel_cost_impl(h, nPU, desc, src, cost);
 }
 
 int cucd_dev_me_subpel_cost(cucd_handle* h, void* stream, int nPU, const cucd_subpel_desc* desc, uint32_t* d_cost) {

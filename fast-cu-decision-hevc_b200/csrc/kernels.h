@@ -95,7 +95,7 @@ struct MeJob {
   int64_t outOff;      // offset (in uint32) of this PU's surface inside the output buffer
 };
 struct MePlanes {
-  const int16_t* cur; int curStride;
+  const int16_t* cur; int curStride;   // curStride == 0: `cur` holds caller-supplied source blocks (w x h each, any int16), MeJob / SubpelJob::curOff their offsets
   const int16_t* const* ref;  // device array of plane origins (sample (0,0) of each padded plane)
   const int32_t* refStride;   // device array
   int bitDepth;

@@ -20,6 +20,10 @@ constexpr int kMeTileX = 32, kMeTileY = 8;
 constexpr int kMeRefPitch = 64 + kMeTileX + 4;       // int16 per staged reference row (even)
 constexpr int kMeRefRows = 64 + kMeTileY;
 
+// SIGNED: the source blocks are caller-supplied and may hold any int16 (the bi-predictive search compares 2 * org - other prediction,
+// TEncSearch.cpp:3787-3797): |a - b| per half through the signed SIMD intrinsic instead of max - min of packed words, whose 32-bit
+// subtraction would borrow across the halves for negative samples.
+template <bool SIGNED>
 __global__ void __launch_bounds__(256)
 me_sad_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* __restrict__ tileJob, const int32_t* __restrict__ tileIdx,
               uint32_t* __restrict__ out) {
@@ -34,7 +38,8 @@ me_sad_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* 
   const int w = job.w, h = job.h;
 
   const int16_t* cur = mp.cur + job.curOff;
-  for (int i = tid; i < w * h; i += 256) { const int y = i / w, x = i - y * w; sCur[y * w + x] = cur[(size_t)y * mp.curStride + x]; }
+  const int curStride = mp.curStride ? mp.curStride : w;               // 0: caller-supplied blocks, w x h each, back to back
+  for (int i = tid; i < w * h; i += 256) { const int y = i / w, x = i - y * w; sCur[y * w + x] = cur[(size_t)y * curStride + x]; }
   const int refStride = mp.refStride[job.refSlot];
   const int16_t* ref = mp.ref[job.refSlot] + job.refOff + (long long)(job.top + dy0) * refStride + (job.left + dx0);
   const int winW = min(w + kMeTileX - 1, w + cols - dx0 - 1), winH = min(h + kMeTileY - 1, h + rows - dy0 - 1);
@@ -60,7 +65,7 @@ me_sad_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* 
       const uint32_t next = rw[rbase + j + 1];
       const uint32_t r = funnel_r(prev, next, e16);
       const uint32_t c = cw[cbase + j];
-      const uint32_t d = __vmaxs2(c, r) - __vmins2(c, r);
+      const uint32_t d = SIGNED ? __vabsdiffs2(c, r) : __vmaxs2(c, r) - __vmins2(c, r);
       acc = __dp2a_lo((int)d, 0x0101, acc);
       prev = next;
     }
@@ -187,7 +192,8 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
   const int dx = (int)blockIdx.y - 3, ix = dx >> 2, fx = dx & 3;
 
   const int16_t* cur = mp.cur + job.curOff;
-  for (int i = tid; i < w * h; i += 256) { const int y = i / w, x = i - y * w; sCur[i] = cur[(size_t)y * mp.curStride + x]; }
+  const int curStride = mp.curStride ? mp.curStride : w;               // 0: caller-supplied blocks (bi-predictive refinement)
+  for (int i = tid; i < w * h; i += 256) { const int y = i / w, x = i - y * w; sCur[i] = cur[(size_t)y * curStride + x]; }
   const int refStride = mp.refStride[job.refSlot];
   const int16_t* ref = mp.ref[job.refSlot] + job.refOff - 4 * (long long)refStride - 4;       // window origin (-4, -4) from the integer MV position
   for (int i = tid; i < (h + 9) * (w + 9); i += 256) { const int y = i / (w + 9), x = i - y * (w + 9); sWin[y * kSpWinPitch + x] = ref[(long long)y * refStride + x]; }
@@ -257,8 +263,9 @@ cudaError_t launch_me_sad(const MePlanes& mp, const MeJob* jobs, int nJobs, cons
                           uint32_t* out, cudaStream_t st, int* launches) {
   (void)nJobs;
   if (nTiles <= 0) return cudaSuccess;
-  if (mp.bitDepth == 8) me_sad_u8_kernel<<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
-  else me_sad_kernel<<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+  if (mp.curStride == 0) me_sad_kernel<true><<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);     // caller-supplied (possibly signed) source blocks
+  else if (mp.bitDepth == 8) me_sad_u8_kernel<<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+  else me_sad_kernel<false><<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -38,7 +38,7 @@ extern "C" {
 
 #define CUCD_NUM_INTRA_MODES 35
 #define CUCD_PUS_PER_CTU 341
-#define CUCD_ABI_VERSION 4
+#define CUCD_ABI_VERSION 5
 
 typedef enum {
   CUCD_OK = 0,
@@ -217,6 +217,17 @@ typedef struct {
 } cucd_subpel_desc;
 #define CUCD_SUBPEL_POINTS 49
 int cucd_me_subpel_cost(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, uint32_t* cost);
+
+/* ------------------------------------------------------------------------------------------------
+ * The same two searches for a caller-supplied source block ("pattern key") instead of the block of the current picture:
+ * what the bi-predictive refinement of xMotionEstimation needs (if (bBi), TEncSearch.cpp:3787-3797, 3826-3849: the key is
+ * m_cYuvPredTemp = 2 * org - prediction of the other list, TComYuv::removeHighFreq, so its samples may be negative or exceed
+ * the bit depth's range), xPatternSearch (:3886-3943) over the +-bipredSearchRange window and xPatternSearchFracDIF around its
+ * result.  src holds the w x h blocks of the PUs back to back (row-major, any int16); x / y of the descriptors still place
+ * the PU inside the reference picture.  No cucd_set_cur_picture needed.
+ * ---------------------------------------------------------------------------------------------- */
+int cucd_me_sad_surface_src(cucd_handle* h, int nPU, const cucd_me_desc* desc, const int16_t* src, uint32_t* sadOut);
+int cucd_me_subpel_cost_src(cucd_handle* h, int nPU, const cucd_subpel_desc* desc, const int16_t* src, uint32_t* cost);
 
 /* ------------------------------------------------------------------------------------------------
  * Intra luma TU coding: the arithmetic of TEncSearch::xIntraCodingTUBlock (TEncSearch.cpp:1092-1387) for a

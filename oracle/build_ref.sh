@@ -126,7 +126,7 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
 patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("  setWpScalingDistParam(pcCU, iRefIdxPred, eRefPicList);\n  //  Do integer search\n",
    "#ifdef CUCD_INTEGRATION\n"
-   "  if (!bBi && m_pcEncCfg->getFastSearch() != SELECTIVE) {   /* INTEGRATION.md S3 */\n"
+   "  if ((!bBi || !cucd_ipc_mode()) && m_pcEncCfg->getFastSearch() != SELECTIVE) {   /* INTEGRATION.md S3; bBi: the key is m_cYuvPredTemp */\n"
    "    TComPicYuv* cucdRef = pcCU->getSlice()->getRefPic(eRefPicList, iRefIdxPred)->getPicYuvRec();\n"
    "    TComPicYuv* cucdOrg = pcCU->getPic()->getPicYuvOrg();\n"
    "    const long cucdOff = (long)(piRefY - cucdRef->getAddr(COMPONENT_Y));\n"
@@ -135,7 +135,8 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
    "                       pcCU->getSlice()->getSPS()->getUseStrongIntraSmoothing() ? 1 : 0, pcCU->getSlice()->getPOC(),\n"
    "                       cucdOrg->getAddr(COMPONENT_Y), cucdOrg->getStride(COMPONENT_Y), cucdRef, cucdRef->getAddr(COMPONENT_Y), iRefStride,\n"
    "                       cucdRef->getMarginX(COMPONENT_Y), cucdRef->getMarginY(COMPONENT_Y), pcCU->getCUPelX(), pcCU->getCUPelY(), cucdPuX, cucdPuY,\n"
-   "                       iRoiWidth, iRoiHeight, (m_pcEncCfg->getUseFastEnc() && iRoiHeight > 8) ? 1 : 0);\n"
+   "                       iRoiWidth, iRoiHeight, (m_pcEncCfg->getUseFastEnc() && iRoiHeight > 8) ? 1 : 0,\n"
+   "                       bBi ? pcYuv->getAddr(COMPONENT_Y, uiPartAddr) : (const Pel*)0, bBi ? (int)pcYuv->getStride(COMPONENT_Y) : 0);\n"
    "  }\n#endif\n", "after"),
   ("  m_pcRdCost->setCostScale(1);\n\n  const Bool bIsLosslessCoded",
    "#ifdef CUCD_INTEGRATION\n  cucd_shim_me_end();\n#endif\n", "before"),

@@ -125,15 +125,24 @@ struct CucdMeShim {
   bool active; int curPoc, nRefs; const void* refKey[64];
   cucd_me_desc d; int minX, maxX, minY, maxY;
   std::map<long, std::vector<uint32_t> > tiles;
-  long pus, tilesComputed, probes;
-  CucdMeShim() : active(false), curPoc(-1000000), nRefs(0), pus(0), tilesComputed(0), probes(0) {}
+  long pus, tilesComputed, probes, biPus;
+  bool ownKey; std::vector<short> key;       /* bi-predictive search: the pattern key 2 * org - other prediction (w x h, packed) */
+  CucdMeShim() : active(false), curPoc(-1000000), nRefs(0), pus(0), tilesComputed(0), probes(0), biPus(0), ownKey(false) {}
 };
 inline CucdMeShim& cucd_me_shim() { static CucdMeShim s; return s; }
 inline bool cucd_shim_me_active() { return cucd_me_shim().active; }
+/* keyBlock != 0: bi-predictive refinement (if (bBi), TEncSearch.cpp:3787-3797): the search key is the caller's block, not the picture's */
 inline void cucd_shim_me_begin(int W, int H, int bd, int strong, int curPoc, const short* orgY, int orgStride, const void* refKey, const short* refY,
-                               int refStride, int marginX, int marginY, int cuX, int cuY, int puX, int puY, int w, int h, int subShift) {
+                               int refStride, int marginX, int marginY, int cuX, int cuY, int puX, int puY, int w, int h, int subShift,
+                               const short* keyBlock = 0, int keyStride = 0) {
   cucd_shim_open(W, H, bd, strong);
   CucdShim& s = cucd_shim(); CucdMeShim& m = cucd_me_shim();
+  m.ownKey = keyBlock != 0;
+  if (m.ownKey) {
+    m.key.resize((size_t)w * h);
+    for (int y = 0; y < h; y++) memcpy(&m.key[(size_t)y * w], keyBlock + (size_t)y * keyStride, (size_t)w * sizeof(short));
+    m.biPus++;
+  }
   if (curPoc != m.curPoc) {
     if ((cucd_ipc_mode() ? cucd_ipc().set_cur_picture(W, H, orgY, orgStride) : cucd_set_cur_picture(s.h, orgY, orgStride)) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");
     m.curPoc = curPoc; m.nRefs = 0;
@@ -154,16 +163,19 @@ inline void cucd_shim_me_end() { cucd_me_shim().active = false; }
 inline unsigned cucd_shim_me_sad(int x, int y) {
   CucdShim& s = cucd_shim(); CucdMeShim& m = cucd_me_shim();
   if (x < m.minX || x > m.maxX || y < m.minY || y > m.maxY) { fprintf(stderr, "cucd shim: ME probe (%d,%d) outside the legal MV area\n", x, y); exit(1); }
-  const int tx = (x + 4096) >> 7, ty = (y + 4096) >> 7;
+  /* tiles of 128 x 128 candidates for the TZ search, 32 x 32 for the bi-predictive refinement (+-4 around its start, xPatternSearch) */
+  const int sh = m.ownKey ? 5 : 7, span = (1 << sh) - 1;
+  const int tx = (x + 4096) >> sh, ty = (y + 4096) >> sh;
   const long key = (long)ty * 4096 + tx;
   cucd_me_desc d = m.d;
-  d.left = (tx << 7) - 4096; d.right = d.left + 127; d.top = (ty << 7) - 4096; d.bottom = d.top + 127;
+  d.left = (tx << sh) - 4096; d.right = d.left + span; d.top = (ty << sh) - 4096; d.bottom = d.top + span;
   if (d.left < m.minX) d.left = m.minX; if (d.right > m.maxX) d.right = m.maxX;
   if (d.top < m.minY) d.top = m.minY; if (d.bottom > m.maxY) d.bottom = m.maxY;
   std::map<long, std::vector<uint32_t> >::iterator it = m.tiles.find(key);
   if (it == m.tiles.end()) {
     std::vector<uint32_t> surf((size_t)(d.right - d.left + 1) * (d.bottom - d.top + 1));
-    if ((cucd_ipc_mode() ? cucd_ipc().me_sad_surface(1, &d, surf.data()) : cucd_me_sad_surface(s.h, 1, &d, surf.data())) != CUCD_OK) cucd_shim_die("cucd_me_sad_surface");
+    if (m.ownKey) { if (cucd_me_sad_surface_src(s.h, 1, &d, &m.key[0], surf.data()) != CUCD_OK) cucd_shim_die("cucd_me_sad_surface_src"); }
+    else if ((cucd_ipc_mode() ? cucd_ipc().me_sad_surface(1, &d, surf.data()) : cucd_me_sad_surface(s.h, 1, &d, surf.data())) != CUCD_OK) cucd_shim_die("cucd_me_sad_surface");
     it = m.tiles.insert(std::make_pair(key, std::vector<uint32_t>())).first;
     it->second.swap(surf);
     m.tilesComputed++;
@@ -179,9 +191,11 @@ inline bool cucd_shim_frac_active() { return cucd_frac_shim().active; }
 inline void cucd_shim_frac_begin(int biPred, int mvx, int mvy, int useHadamard) {
   CucdFracShim& f = cucd_frac_shim(); CucdMeShim& m = cucd_me_shim();
   f.active = false;
-  if (biPred || !cucd_shim_ready() || m.pus == 0) return;          /* the PU / reference of the integer search that just ended */
+  if (!cucd_shim_ready() || m.pus == 0) return;                    /* the PU / reference of the integer search that just ended */
+  if (biPred && !m.ownKey) return;                                 /* (server mode keeps the bi-predictive refinement on the CPU) */
   cucd_subpel_desc d = {m.d.x, m.d.y, m.d.w, m.d.h, m.d.ref_idx, mvx, mvy, useHadamard};
-  if ((cucd_ipc_mode() ? cucd_ipc().me_subpel_cost(1, &d, f.cost) : cucd_me_subpel_cost(cucd_shim().h, 1, &d, f.cost)) != CUCD_OK) cucd_shim_die("cucd_me_subpel_cost");
+  if (m.ownKey) { if (cucd_me_subpel_cost_src(cucd_shim().h, 1, &d, &m.key[0], f.cost) != CUCD_OK) cucd_shim_die("cucd_me_subpel_cost_src"); }
+  else if ((cucd_ipc_mode() ? cucd_ipc().me_subpel_cost(1, &d, f.cost) : cucd_me_subpel_cost(cucd_shim().h, 1, &d, f.cost)) != CUCD_OK) cucd_shim_die("cucd_me_subpel_cost");
   f.active = true; f.calls++;
 }
 inline void cucd_shim_frac_end() { cucd_frac_shim().active = false; }
@@ -255,7 +269,7 @@ inline void cucd_shim_tmv_check(int x, int y, int size, const double* ref130) {
 struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim();
   if (s.rmdCpu) fprintf(stderr, "cucd shim: %ld RMD PUs smaller than %d kept on the CPU (CUCD_SHIM_MIN_N)\n", s.rmdCpu, s.minN);
   if (s.ipcOpen) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, through cucd_server\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls); cucd_ipc().close_client(); }
-  if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+  if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld of them bi-predictive, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_me_shim().biPus, cucd_frac_shim().calls, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;
 #endif
 

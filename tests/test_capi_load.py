@@ -13,7 +13,7 @@ def test_library_exports_every_declared_symbol(cucd):
     assert len(names) >= 32
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.cucd_abi_version() == 4
+    assert lib.cucd_abi_version() == 5
 
 
 def test_header_cites_reference_for_every_entry_point(cucd):

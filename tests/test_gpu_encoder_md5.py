@@ -47,7 +47,8 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
     """AI: S1 + S2 on the GPU (5 frames reach the fork's Testing state, so the OBF-driven early decisions are live);
     LDP (I + 2 P pictures, TZ search range 64, AMP): additionally every integer-ME SAD of the uni-directional searches (S3) and
     every candidate of their half-/quarter-pel refinement (8f.3).
-    RA (I + one GOP8 of B pictures, 10 bit): the same with two reference lists; the bi-predictive refinement keeps its CPU SAD.
+    RA (I + one GOP8 of B pictures, 10 bit): the same with two reference lists, including the bi-predictive refinement
+    (search key 2 * org - other prediction through cucd_me_sad_surface_src / cucd_me_subpel_cost_src).
     AITU (CUCD_SHIM_TU=1): additionally every luma and chroma TU of xIntraCodingTUBlock goes through cucd_intra_tu_forward (its
     prediction replaces the encoder's, its transform output must equal m_plTempCoeff), the host's RDOQ, and cucd_intra_tu_recon
     (its reconstruction replaces the encoder's samples, its SSE must equal getDistPart)."""
@@ -73,7 +74,10 @@ def test_bitstream_md5_matches_reference_encoder(cfg, bd, frames, qp):
                 if cfg in ("LDP", "RA"):
                     n_me = int(r.stderr.split("GPU,")[1].split("ME searches")[0])
                     assert n_me > 1000
-                    assert int(r.stderr.split("probes) on the GPU,")[1].split("sub-pel")[0]) > 1000
+                    import re
+                    assert int(re.search(r"(\d+) sub-pel refinements on the GPU", r.stderr).group(1)) > 1000
+                    n_bi = int(re.search(r"(\d+) of them bi-predictive", r.stderr).group(1))
+                    assert (n_bi > 100) if cfg == "RA" else (n_bi == 0)       # B pictures: the bi-predictive refinement runs on the GPU too
                 if cfg == "AITU":
                     import re
                     assert int(re.search(r"(\d+) TUs coded on the GPU", r.stderr).group(1)) > 50000

@@ -68,3 +68,44 @@ def test_subpel_vs_oracle(cucd, oracle, bd):
         zero = C.c_void_p(refp.ctypes.data + 2 * ((d["y"] + M) * Wp + d["x"] + M))
         oracle.oracle_subpel_surface(bd, P(blk, i16p), d["w"], d["w"], d["h"], zero, Wp, d["mvx"], d["mvy"], d["use_hadamard"], P(want, u32p))
         assert np.array_equal(got[i].ravel(), want), d
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_bipred_key_blocks_vs_oracle(cucd, oracle, bd):
+    """cucd_me_sad_surface_src / cucd_me_subpel_cost_src: the bi-predictive refinement of xMotionEstimation (TEncSearch.cpp:3787-3849)
+    searches with the key 2 * org - prediction of the other list (TComYuv::removeHighFreq): samples below 0 and above the bit depth's
+    range, caller-supplied blocks instead of the current picture.  Integer search (+-4, xPatternSearch) and the 49 sub-pel positions."""
+    W, H, M = 256, 128, 80
+    hi = (1 << bd) - 1
+    org = textured_plane(W, H, bd, seed=33).astype(np.int32)
+    other = pseudo_recon(textured_plane(W, H, bd, seed=34, t=2), bd).astype(np.int32)
+    other[:, ::3] = hi; other[::5, :] = 0                      # push 2 * org - other to both ends of [-hi, 2 * hi]
+    key = (2 * org - other).astype(np.int16)
+    assert key.min() < 0 and key.max() > hi
+    rec = pseudo_recon(textured_plane(W, H, bd, seed=33, t=1), bd)
+    refp = np.pad(rec, M, mode="edge")
+    rng = np.random.default_rng(8)
+    shapes = [(64, 64), (32, 32), (16, 16), (8, 8), (64, 32), (16, 64), (32, 24), (12, 16), (8, 4), (4, 8)]
+    me, sp, blocks = [], [], []
+    for w, h in shapes:
+        x = int(rng.integers(0, (W - w) // 4 + 1)) * 4; y = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+        cx, cy = int(rng.integers(-20, 21)), int(rng.integers(-20, 21))
+        me.append(dict(x=x, y=y, w=w, h=h, ref_idx=0, left=cx - 4, right=cx + 4, top=cy - 4, bottom=cy + 4, sub_shift=1 if h > 8 else 0))
+        sp.append(dict(x=x, y=y, w=w, h=h, ref_idx=0, mvx=cx, mvy=cy, use_hadamard=int(rng.integers(0, 2))))
+        blocks.append(np.ascontiguousarray(key[y:y + h, x:x + w]))
+    src = np.concatenate([b.ravel() for b in blocks])
+    with cucd.Engine(W, H, bit_depth=bd) as eng:
+        eng.set_ref_picture(0, refp, M, M)                     # no cucd_set_cur_picture: the source blocks are the caller's
+        surf = eng.me_sad_surface(me, src=src)
+        frac = eng.me_subpel_cost(sp, src=src)
+        with pytest.raises(cucd.CucdError):
+            eng.me_sad_surface(me)                             # the plain call still needs the current picture
+    Wp = W + 2 * M
+    for i, (d, f, blk) in enumerate(zip(me, sp, blocks)):
+        zero = C.c_void_p(refp.ctypes.data + 2 * ((d["y"] + M) * Wp + d["x"] + M))
+        want = np.zeros_like(surf[i])
+        oracle.oracle_sad_surface(bd, P(blk, i16p), d["w"], d["w"], d["h"], zero, Wp, d["left"], d["right"], d["top"], d["bottom"], d["sub_shift"], P(want, u32p))
+        assert np.array_equal(surf[i], want), d
+        want49 = np.zeros(49, np.uint32)
+        oracle.oracle_subpel_surface(bd, P(blk, i16p), f["w"], f["w"], f["h"], zero, Wp, f["mvx"], f["mvy"], f["use_hadamard"], P(want49, u32p))
+        assert np.array_equal(frac[i].ravel(), want49), f
