@@ -236,6 +236,7 @@ int cucd_destroy(cucd_handle* h) {
   if (h->evDevDone) cudaEventDestroy(h->evDevDone);
   h->dNeeded.release();
   if (h->evMask) cudaEventDestroy(h->evMask);
+  if (h->evDirect) cudaEventDestroy(h->evDirect);
   if (h->evK0) cudaEventDestroy(h->evK0);
   if (h->evK1) cudaEventDestroy(h->evK1);
   if (h->sUp) cudaStreamDestroy(h->sUp);

@@ -33,25 +33,45 @@ bool host_pinned(cucd_handle* h, const void* p, size_t bytes) {
   return pinned;
 }
 
+// Requests of a live encoder are tiny (one PU: ~1 KB in, 140 B out; one 128 x 128 SAD tile: 64 KB out) and latency bound: two DMA
+// copies, two timing events and a blocking stream wait cost several times the kernel.  Below `directLimit` bytes the kernels read
+// their inputs from and write their results to page-locked HOST memory directly (zero copy over PCIe, unified addressing) and the
+// call polls one event: a host memcpy each way, the launches, one cudaEventRecord.  CUCD_DIRECT_LIMIT=<bytes> (0 = off).
+inline size_t direct_limit() {
+  static const size_t v = [] { const char* e = getenv("CUCD_DIRECT_LIMIT"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)96 << 10; }();
+  return v;
+}
+
 struct BatchIo {
   struct Part { const void* src; void* dst; size_t bytes, off; bool pinned; };
   cucd_handle* h;
   Part in[8], out[8];
   int nIn = 0, nOut = 0;
   size_t inBytes = 0, outBytes = 0;
+  bool direct = false;
   explicit BatchIo(cucd_handle* hh) : h(hh) {}
   int add_in(const void* src, size_t bytes, bool pinned = false) { in[nIn] = Part{src, nullptr, bytes, inBytes, pinned}; inBytes += up16(bytes); return nIn++; }
   int add_out(void* dst, size_t bytes) { out[nOut] = Part{nullptr, dst, dst ? bytes : 0, outBytes, false}; outBytes += up16(dst ? bytes : 0); return nOut++; }
   // device-side room for an array the kernels produce but the caller did not ask for
   int add_scratch_out(size_t bytes) { out[nOut] = Part{nullptr, nullptr, 0, outBytes, false}; outBytes += up16(bytes); return nOut++; }
   int reserve() {
+    direct = inBytes + outBytes <= direct_limit() && inBytes + 256 <= kStageLimit && outBytes + 256 <= kStageLimit;
+    if (direct) {
+      CK(h->hStage.reserve(kStageLimit)); CK(h->hStageOut.reserve(kStageLimit));
+      if (!h->evDirect) CK(cudaEventCreateWithFlags(&h->evDirect, cudaEventDisableTiming));
+      return CUCD_OK;
+    }
     CK(h->bStage.reserve(inBytes + 256));
     CK(h->bOut.reserve(outBytes / 4 + 64));
     return CUCD_OK;
   }
-  template <class T> T* din(int i) const { return reinterpret_cast<T*>(h->bStage.p + in[i].off); }
-  template <class T> T* dout(int i) const { return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(h->bOut.p) + out[i].off); }
+  template <class T> T* din(int i) const { return reinterpret_cast<T*>((direct ? h->hStage.p : h->bStage.p) + in[i].off); }
+  template <class T> T* dout(int i) const { return reinterpret_cast<T*>((direct ? h->hStageOut.p : reinterpret_cast<uint8_t*>(h->bOut.p)) + out[i].off); }
   int upload(cudaStream_t st) {
+    if (direct) {
+      for (int i = 0; i < nIn; i++) if (in[i].bytes) memcpy(h->hStage.p + in[i].off, in[i].src, in[i].bytes);
+      return CUCD_OK;
+    }
     bool allPinned = true;
     for (int i = 0; i < nIn; i++) allPinned = allPinned && in[i].pinned;
     if (inBytes <= kStageLimit && !allPinned) {
@@ -69,6 +89,14 @@ struct BatchIo {
   }
   // enqueue the copies back, wait for the stream, hand the results to the caller
   int download(cudaStream_t st) {
+    if (direct) {
+      CK(cudaEventRecord(h->evDirect, st));
+      cudaError_t e;
+      while ((e = cudaEventQuery(h->evDirect)) == cudaErrorNotReady) { }
+      CK(e);
+      for (int i = 0; i < nOut; i++) if (out[i].bytes) memcpy(out[i].dst, h->hStageOut.p + out[i].off, out[i].bytes);
+      return CUCD_OK;
+    }
     size_t wanted = 0;
     for (int i = 0; i < nOut; i++) wanted += out[i].bytes;
     if (outBytes <= kStageLimit) {
@@ -113,7 +141,7 @@ int rmd_batch_core(cucd_handle* h, int nPU, const cucd_pu_desc* desc, const int3
   const int oSad = io.add_out(sad, (size_t)nPU * kNumModes * sizeof(uint32_t));
   if (io.reserve() != CUCD_OK) return CUCD_ERR_CUDA;
   if (io.upload(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
-  CK(cudaEventRecord(h->evK0, h->sMain));
+  if (!io.direct) CK(cudaEventRecord(h->evK0, h->sMain));
   for (int l = 6; l >= 2; l--) {
     if (!count[l]) continue;
     BatchSource bs;
@@ -127,7 +155,7 @@ int rmd_batch_core(cucd_handle* h, int nPU, const cucd_pu_desc* desc, const int3
     else
       CK(launch_rmd_batch(l, bs, h->cfg.bit_depth, h->cfg.strong_intra_smoothing, h->sMain, &h->launches));
   }
-  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
+  if (!io.direct) { CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true; } else h->kTimed = false;
   if (io.download(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   flush_launches(h);
   return CUCD_OK;
@@ -427,10 +455,10 @@ static int me_sad_surface_impl(cucd_handle* h, int nPU, const cucd_me_desc* desc
   mp.cur = own ? io.din<int16_t>(iSrc) : h->dCur.p; mp.curStride = own ? 0 : h->curStride;
   mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
   const uint8_t* dAll = io.din<uint8_t>(iAll);
-  CK(cudaEventRecord(h->evK0, h->sMain));
+  if (!io.direct) CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_me_sad(mp, reinterpret_cast<const MeJob*>(dAll), nPU, reinterpret_cast<const int32_t*>(dAll + jobBytes), reinterpret_cast<const int32_t*>(dAll + jobBytes + tileBytes),
                    (int)nTiles, io.dout<uint32_t>(oSad), h->sMain, &h->launches));
-  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
+  if (!io.direct) { CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true; } else h->kTimed = false;
   if (io.download(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   flush_launches(h);
   return CUCD_OK;
@@ -523,9 +551,9 @@ static int me_subpel_cost_impl(cucd_handle* h, int nPU, const cucd_subpel_desc* 
   MePlanes mp;
   mp.cur = own ? io.din<int16_t>(iSrc) : h->dCur.p; mp.curStride = own ? 0 : h->curStride;
   mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
-  CK(cudaEventRecord(h->evK0, h->sMain));
+  if (!io.direct) CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_me_subpel(mp, io.din<SubpelJob>(iJobs), nPU, io.dout<uint32_t>(oCost), h->sMain, &h->launches));
-  CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true;
+  if (!io.direct) { CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true; } else h->kTimed = false;
   if (io.download(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   flush_launches(h);
   return CUCD_OK;

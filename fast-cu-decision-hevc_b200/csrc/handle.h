@@ -151,6 +151,7 @@ struct cucd_handle {
   // small calls; pinned scratch for the job records the library builds
   cucd::DevBuf<uint8_t> bStage; cucd::DevBuf<uint32_t> bOut;
   cucd::PinBuf<uint8_t> hStage, hStageOut, hScratch;
+  cudaEvent_t evDirect = nullptr;                 // completion of a zero-copy ("direct") small request (capi_batch.cu BatchIo)
   std::vector<int32_t> tmpOffA, tmpOffB;
   // ME path
   std::vector<cucd::RefPlane> refs;
