@@ -38,7 +38,7 @@ __device__ long long* g_tc2Dbg = nullptr;
 // CUCD_TC2_WARPSKEW (profiles/ubench/tc2_skew.cu only): lane 0 of the four warps of row group 0 stamps the events of round am = 4
 #ifdef CUCD_TC2_WARPSKEW
 __device__ long long* g_tc2Skew = nullptr;
-#define TC2_SKEW(e) do { if (g_tc2Skew && pass == 0 && am == 4 && (threadIdx.x & 31) == 0 && threadIdx.x < 128) g_tc2Skew[(size_t)blockIdx.x * 64 + (threadIdx.x >> 5) * 16 + (e)] = clock64(); } while (0)
+#define TC2_SKEW(e) do { if (g_tc2Skew && pass == 0 && (am == 4 || (am == 3 && (e) < 2)) && (threadIdx.x & 31) == 0 && threadIdx.x < 128) g_tc2Skew[(size_t)blockIdx.x * 64 + (threadIdx.x >> 5) * 16 + (am == 4 ? (e) : 9 + (e))] = clock64(); } while (0)
 #else
 #define TC2_SKEW(e) do { } while (0)
 #endif
@@ -95,7 +95,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
         "=r"(v[30]), "=r"(v[31])
       : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;\n" :: "r"(grp + 1) : "memory"); }
+// A CTA = 256 worker threads (the rows) + one MMA-issuing warp per row group.  The workers only ARRIVE on mbarriers when their
+// operands are in place; the issuing warp waits for the 128 arrivals, issues the tcgen05.mma and the bulk copy of the next weights
+// and commits.  (With the issue inside worker warp 0 that warp ran ~490 cycles behind the other three in every round - the
+// tcgen05.wait::st / fence / four UTCIMMA / commit sequence sat on the round's critical path, profiles/ubench/tc2_skew.cu.)
+constexpr int kIssuerThreads = 32 * kGroups;
+constexpr int kCtaThreads = kThreads + kIssuerThreads;
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }     // the 256 workers only
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine, 1-D); completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(mbar)) : "memory"); }
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
@@ -152,14 +166,14 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit, c
       const int first = (unit * C::CTUS + c) * C::PUS;
       for (int p = tid; p < C::PUS; p += kThreads) smem[C::VALID_OFF + c * 256 + p] = first + p < bs.count ? 1 : 0;
     }
-    __syncthreads();
+    worker_bar();
 #pragma unroll
     for (int c = 0; c < C::CTUS; c++) {
       const int idx = (unit * C::CTUS + c) * C::PUS + tid / TPP;
       build_unfiltered_batch<LOG2N>(tid, c, idx < bs.count ? bs.border + (size_t)bs.pus[idx].borderOff : nullptr, smem);
     }
     if (C::HAS_FILT) {
-      __syncthreads();
+      worker_bar();
 #pragma unroll
       for (int c = 0; c < C::CTUS; c++)
         if ((unit * C::CTUS + c) * C::PUS < bs.count) build_filtered<LOG2N>(tid, c, a.strong, smem);
@@ -184,14 +198,14 @@ __device__ __forceinline__ void tc2_prologue(const Tc2Args& a, const int unit, c
 #pragma unroll
   for (int c = 0; c < C::CTUS; c++)
     if (ctuX[c] >= 0) tile_store<LOG2N>(tid, fs.W, fs.H, ctuX[c], ctuY[c], tl[c], smem + C::TILE_OFF + c * C::TILE_BYTES);
-  __syncthreads();
+  worker_bar();
   TC2_STAMP(51);
 #pragma unroll
   for (int c = 0; c < C::CTUS; c++)
     if (ctuX[c] >= 0) build_unfiltered<LOG2N>(tid, c, fs.W, fs.H, ctuX[c], ctuY[c], smem + C::TILE_OFF + c * C::TILE_BYTES, smem);
   TC2_STAMP(52);
   if (C::HAS_FILT) {
-    __syncthreads();
+    worker_bar();
     TC2_STAMP(53);
 #pragma unroll
     for (int c = 0; c < C::CTUS; c++)
@@ -219,15 +233,13 @@ __device__ __forceinline__ const int16_t* frame_src_ptr(const FrameSource& fs, c
 
 // `pre`: the eight rows of the source tile of pass 0, loaded by tc2_body before the prologue (frame mode), or nullptr
 template <int LOG2N, bool FRAME>
-__device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2, uint32_t& phA, uint32_t& phB,
-                                         const uint4* pre) {
+__device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const int pass, const uint32_t tmemBase, uint32_t& ph1, uint32_t& ph2, const uint4* pre) {
   typedef Cfg<LOG2N> C;
   constexpr int N = C::N, SEG = RowSeg<LOG2N>::value;
   unsigned char* smem = smem2;
   const int tid = threadIdx.x, grp = tid >> 7, rowTid = tid & 127, warp = tid >> 5, lane = tid & 31;
   const Row r = row_map<LOG2N>(tid, pass);
   unsigned char* store = smem + C::STORE_OFF;
-  unsigned char* sB1 = smem + C::B1_OFF + grp * 2 * C::B1_BYTES;
   unsigned char* sA1 = smem + C::A1_OFF + grp * 8192;
   unsigned char* sAorg = smem + C::AORG_OFF + grp * 8192;
   uint64_t* mbar1 = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + grp;
@@ -236,7 +248,6 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   // the group arrive and go straight on to their next piece of work instead of idling at a bar.sync.
   uint64_t* arrA = mbar1 + 2 * kGroups;
   uint64_t* arrB = mbar1 + 3 * kGroups;
-  const uint8_t* const tabWin = a.tabWin; const uint8_t* const tabN4 = a.tabN4;
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
   const FrameSource& fs = a.fs;
   const int cg = unit * C::CTUS + r.ctu;
@@ -299,87 +310,20 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   const uint32_t laneOff = (uint32_t)((warp & 3) * 32) << 16;
   const int rowChunk = (rowTid >> 3) * 128 + (rowTid & 7) * 16;      // the row's 16-byte slot inside a 128-row operand chunk
   const uint32_t tD1 = tmemBase + grp * 128, tA2 = tD1, tD2 = tD1 + 64;
-  // What the MMA-issuing lane needs, derived from warp-uniform values only (a shuffle result is uniform to the compiler), so that
-  // the tcgen05 operands live in uniform registers and the elected lane issues without a per-instruction uniformisation loop.
-  const int warpU = __shfl_sync(0xffffffffu, warp, 0), grpU = warpU >> 2;
-  const bool issuer = (warpU & 3) == 0;
-  const uint32_t tmemU = __shfl_sync(0xffffffffu, tmemBase, 0);
-  const uint32_t uD1 = tmemU + grpU * 128, uA2 = uD1, uD2 = uD1 + 64;
-  uint64_t* ubar1 = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + grpU;
-  uint64_t* ubar2 = ubar1 + kGroups;
-  uint64_t* uarrA = ubar1 + 2 * kGroups;
-  uint64_t* uarrB = ubar1 + 3 * kGroups;
-  const uint32_t idescPred = make_idesc_i8x(128, 64, 0, 0), idescHad = make_idesc_i8x(128, 64, 0, 1);
-  const uint64_t dHad = make_desc(smem_u32(smem + C::HAD_OFF), 1024, 128), dHadNeg = make_desc(smem_u32(smem + C::HAD_OFF + 4096), 1024, 128);
-  const uint64_t dAorg = make_desc(smem_u32(smem + C::AORG_OFF + grpU * 8192), 2048, 128);
-  const uint64_t dB1 = make_desc(smem_u32(smem + C::B1_OFF + grpU * 2 * C::B1_BYTES), 1024, 128), dA1 = make_desc(smem_u32(smem + C::A1_OFF + grpU * 8192), 2048, 128);
-  constexpr uint64_t kStepB = (2 * 1024) >> 4;      // descriptor advance of one K = 32 step: two 16-byte chunks of 64 rows
-  constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
-
-  // source x -H + A2 (already stored to TMEM by every thread) x H -> D2
-  auto arrive_mma2 = [&]() {
+  // the row announces "my A2 is in TMEM" / "my window is in shared memory"; the row group's issuing warp (tc2_issue_pass) does the rest
+  auto issue_mma2 = [&]() {
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(arrA);
   };
-  auto fire_mma2 = [&]() {
-    if (issuer) {
-      mbar_wait(uarrA, phA);
-      tc_fence_after();
-      if (elect_one()) {
-        mma_i8(uD2, dAorg, dHadNeg, idescHad, 0u);
-        mma_i8(uD2, dAorg + kStepA, dHadNeg + kStepB, idescHad, 1u);
-        mma_i8_ts(uD2, uA2, dHad, idescHad, 1u);
-        mma_i8_ts(uD2, uA2 + 8, dHad + kStepB, idescHad, 1u);
-        mma_commit(ubar2);
-      }
-      __syncwarp();
-    }
-    phA ^= 1u;
-  };
-  auto issue_mma2 = [&]() { arrive_mma2(); fire_mma2(); };
   auto wait_mma2 = [&]() { mbar_wait(mbar2, ph2); ph2 ^= 1u; tc_fence_after(); };
-  // window / record operand (shared memory) x weights -> D1
-  auto issue_mma1 = [&](int buf) {
+  auto issue_mma1 = [&]() {
     fence_async_smem();
     tc_fence_before();
     mbar_arrive(arrB);
-    if (issuer) {
-      mbar_wait(uarrB, phB);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t dB = dB1 + (uint64_t)((buf * C::B1_BYTES) >> 4);
-        if (LOG2N == 2) {
-          mma_i8(uD1, dA1, dB, idescPred, 0u);
-          mma_i8(uD1, dA1 + kStepA, dB + kStepB, idescPred, 1u);
-        } else {
-          mma_i8(uD1, dA1 + (uint64_t)((buf * 4096) >> 4), dB, idescPred, 0u);
-        }
-        mma_commit(ubar1);
-      }
-      __syncwarp();
-    }
-    phB ^= 1u;
   };
   auto wait_mma1 = [&]() { mbar_wait(mbar1, ph1); ph1 ^= 1u; tc_fence_after(); };
-  // weights of round `am` from global memory (L2 resident) into registers, one round ahead of their use
-  uint4 nb0 = make_uint4(0, 0, 0, 0), nb1 = nb0;
-  auto prefetch_b1 = [&](int am, int angle) {
-    const int ai = am + 8;
-    if (LOG2N == 2) {
-      const uint4* t = reinterpret_cast<const uint4*>(tabN4 + ai * 4096);
-      nb0 = __ldg(t + rowTid); nb1 = __ldg(t + rowTid + 128);
-    } else {
-      const int fc = group_frac0<LOG2N>(grp, pass, angle) >> 3;
-      nb0 = __ldg(reinterpret_cast<const uint4*>(tabWin + (ai * 4 + fc) * 2048) + rowTid);
-    }
-  };
-  // operands of round `am` into buffer `buf`: weights from the prefetch registers, the row's reference window
-  auto stage_weights = [&](int buf) {
-    uint4* b = reinterpret_cast<uint4*>(sB1 + buf * C::B1_BYTES);
-    b[rowTid] = nb0;
-    if (LOG2N == 2) b[rowTid + 128] = nb1;
-  };
+  // the row's reference window of round `am` into window buffer `buf`
   auto stage_window = [&](int am, int angle, int buf) {
     if (LOG2N == 2) return;
     const int filt = mode_uses_filtered<LOG2N>(26 + am) ? 1 : 0;
@@ -437,7 +381,6 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i * 128] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
   }
-  prefetch_b1(8, 32);
   const unsigned char* rec4 = store + rec_off(r.ctu, r.o, 4 * r.pu);
   if (LOG2N == 2) {                                 // N = 4: the record row is the A operand of every mode (4 chunks)
     uint4* d = reinterpret_cast<uint4*>(sA1 + rowChunk);
@@ -462,10 +405,9 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   // ---- round 0 -------------------------------------------------------------------------------------------------
   tmem_st16(tA2 + laneOff, p);
   issue_mma2();
-  stage_weights(0); stage_window(8, 32, 0);
-  prefetch_b1(7, 26);
+  stage_window(8, 32, 0);
   wait_mma2();
-  issue_mma1(0);
+  issue_mma1();
   cost_out(r.o ? 1 : 0, true);
   if (pass == 0) TC2_STAMP(8);
 
@@ -504,14 +446,11 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     if (lateWindow) build_ext_group<LOG2N>(rowTid, grp, inv_angle_of_am(am - 1), mode_uses_filtered<LOG2N>(25 + am) ? 1 : 0, store);
     TC2_FINE(3);
     TC2_SKEW(3);
-    arrive_mma2();
-    fire_mma2();
+    issue_mma2();
     TC2_FINE(4);
     TC2_SKEW(4);
     if (am > -8) {
-      stage_weights(buf ^ 1);
       if (!lateWindow) stage_window(am - 1, angleNext, buf ^ 1);
-      if (am > -7) prefetch_b1(am - 2, angleNext2);
     }
     TC2_FINE(5);
     TC2_SKEW(5);
@@ -519,7 +458,7 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
     TC2_FINE(6);
     TC2_SKEW(6);
     if (lateWindow) stage_window(am - 1, angleNext, buf ^ 1);
-    if (am > -8) issue_mma1(buf ^ 1);
+    if (am > -8) issue_mma1();
     TC2_FINE(7);
     TC2_SKEW(7);
     cost_out(r.o ? 10 - am : 26 + am, !(r.o && am == -8));
@@ -531,16 +470,94 @@ __device__ __forceinline__ void tc2_pass(const Tc2Args& a, const int unit, const
   (void)angle;
 }
 
+// ---- the MMA-issuing warp of row group `g` (threads 256 + 32 g ...): one pass ---------------------------------------------
+// Mirrors the workers' sequence of tc2_pass: round 0 (MMA 2 only), then per angular round MMA 2 of the round and MMA 1 of the next.
+// The weights of round am - 2 are fetched (cp.async.bulk, completion on barT) right after MMA 1 of round am - 1 has been issued,
+// into the buffer MMA 1 of round am has finished with (the workers passed wait_mma1 of that round before they arrived here).
+template <int LOG2N>
+__device__ __forceinline__ void tc2_issue_pass(const Tc2Args& a, const int pass, const uint32_t tmemBase, const int g, uint32_t& phA, uint32_t& phB, uint32_t& phT) {
+  typedef Cfg<LOG2N> C;
+  unsigned char* smem = smem2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* bar1 = bars + g;
+  uint64_t* bar2 = bars + kGroups + g;
+  uint64_t* arrA = bars + 2 * kGroups + g;
+  uint64_t* arrB = bars + 3 * kGroups + g;
+  uint64_t* barT = bars + 4 * kGroups + g;
+  const uint32_t uD1 = tmemBase + g * 128, uA2 = uD1, uD2 = uD1 + 64;
+  unsigned char* sB1 = smem + C::B1_OFF + g * 2 * C::B1_BYTES;
+  const uint32_t idescPred = make_idesc_i8x(128, 64, 0, 0), idescHad = make_idesc_i8x(128, 64, 0, 1);
+  const uint64_t dHad = make_desc(smem_u32(smem + C::HAD_OFF), 1024, 128), dHadNeg = make_desc(smem_u32(smem + C::HAD_OFF + 4096), 1024, 128);
+  const uint64_t dAorg = make_desc(smem_u32(smem + C::AORG_OFF + g * 8192), 2048, 128);
+  const uint64_t dB1 = make_desc(smem_u32(sB1), 1024, 128), dA1 = make_desc(smem_u32(smem + C::A1_OFF + g * 8192), 2048, 128);
+  constexpr uint64_t kStepB = (2 * 1024) >> 4;      // descriptor advance of one K = 32 step: two 16-byte chunks of 64 rows
+  constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
+  const bool lead = elect_one();
+
+  auto fetch = [&](int am, int buf) {               // weights of round `am` -> buffer `buf`
+    if (lead) {
+      const int ai = am + 8;
+      const uint8_t* src = LOG2N == 2 ? a.tabN4 + ai * 4096 : a.tabWin + (ai * 4 + (group_frac0<LOG2N>(g, pass, angle_of_am(am)) >> 3)) * 2048;
+      mbar_expect_tx(barT, C::B1_BYTES);
+      bulk_g2s(sB1 + buf * C::B1_BYTES, src, C::B1_BYTES, barT);
+    }
+  };
+  // source x -H + A2 (stored to TMEM by every row) x H -> D2
+  auto mma2 = [&]() {
+    mbar_wait(arrA, phA); phA ^= 1u;
+    tc_fence_after();
+    if (lead) {
+      mma_i8(uD2, dAorg, dHadNeg, idescHad, 0u);
+      mma_i8(uD2, dAorg + kStepA, dHadNeg + kStepB, idescHad, 1u);
+      mma_i8_ts(uD2, uA2, dHad, idescHad, 1u);
+      mma_i8_ts(uD2, uA2 + 8, dHad + kStepB, idescHad, 1u);
+      mma_commit(bar2);
+    }
+    __syncwarp();
+  };
+  // window / record operand (shared memory) x weights -> D1
+  auto mma1 = [&](int buf) {
+    mbar_wait(arrB, phB); phB ^= 1u;
+    mbar_wait(barT, phT); phT ^= 1u;
+    tc_fence_after();
+    if (lead) {
+      const uint64_t dB = dB1 + (uint64_t)((buf * C::B1_BYTES) >> 4);
+      if (LOG2N == 2) {
+        mma_i8(uD1, dA1, dB, idescPred, 0u);
+        mma_i8(uD1, dA1 + kStepA, dB + kStepB, idescPred, 1u);
+      } else {
+        mma_i8(uD1, dA1 + (uint64_t)((buf * 4096) >> 4), dB, idescPred, 0u);
+      }
+      mma_commit(bar1);
+    }
+    __syncwarp();
+  };
+  fetch(8, 0);
+  mma2();                                           // round 0: planar / DC
+  mma1(0);
+  fetch(7, 1);
+#pragma unroll 1
+  for (int am = 8; am >= -8; --am) {
+    const int buf = (8 - am) & 1;
+    mma2();
+    if (am > -8) {
+      mma1(buf ^ 1);
+      if (am > -7) fetch(am - 2, buf);
+    }
+  }
+}
+
 template <int LOG2N, bool FRAME>
 __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   typedef Cfg<LOG2N> C;
   unsigned char* smem = smem2;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool worker = tid < kThreads;               // threads 256.. are the MMA-issuing warps (tc2_issue_pass)
   if (FRAME && a.fs.needed) {
     // fork-aware mode: a CTA none of whose PUs has to be evaluated writes the table codes and leaves
     const FrameSource& fs = a.fs;
     int any = 0;
-    for (int i = tid; i < C::CTUS * C::PUS; i += kThreads) {
+    if (worker) for (int i = tid; i < C::CTUS * C::PUS; i += kThreads) {
       const int c = i / C::PUS, p = i - c * C::PUS, cg = unit * C::CTUS + c;
       if (cg >= a.totalCtus) continue;
       const int pic = cg / fs.ctusPerPic, ctu = cg - pic * fs.ctusPerPic;
@@ -551,6 +568,7 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
       any |= st == kPuEvaluate;
     }
     if (!__syncthreads_or(any)) {
+      if (!worker) return;
       for (int c = 0; c < C::CTUS; c++) {
         const int cgc = unit * C::CTUS + c;
         if (cgc >= a.totalCtus) break;
@@ -564,14 +582,18 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
       }
       return;
     }
-    __syncthreads();
+    if (worker) worker_bar();
   }
-  uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 64);
+  uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 96);
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + C::ACC_OFF);
   if (tid == 0) {
-    for (int i = 0; i < 4 * kGroups; i++) mbar_init(reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + i, i < 2 * kGroups ? 1 : 128);   // MMA done x2, operands ready x2
+    for (int i = 0; i < 5 * kGroups; i++)           // MMA done x2 (1 arrival: the commit), operands ready x2 (128 rows), weights landed (1 + bytes)
+      mbar_init(reinterpret_cast<uint64_t*>(smem + C::BAR_OFF) + i, (i >= 2 * kGroups && i < 4 * kGroups) ? 128 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  uint32_t ph1 = 0, ph2 = 0;
+  uint4 pre[8];
+  if (worker) {
   TC2_STAMP(0);
   if (warp == 0) tmem_alloc(tmemSlot, 256);
   TC2_STAMP(58);
@@ -592,7 +614,6 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
       tile_load<LOG2N>(tid, a.fs.rec + (size_t)pic * a.fs.recPicStride, a.fs.recStride, a.fs.W, a.fs.H, ctuX[c], ctuY[c], tl[c]);
     }
   }
-  uint4 pre[8];
   if (FRAME) {
     const Row r0 = row_map<LOG2N>(tid, 0);
     const int cg0 = unit * C::CTUS + r0.ctu;
@@ -613,27 +634,34 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
   reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid] = hadP;
   TC2_STAMP(60);
   reinterpret_cast<uint4*>(smem + C::HAD_OFF)[tid + 256] = hadN;
-  __syncthreads();
+  worker_bar();
   TC2_STAMP(50);
   tc2_prologue<LOG2N, FRAME>(a, unit, tl, ctuX, ctuY);
   TC2_STAMP(54);
   tc_fence_before();
   fence_async_smem();
-  __syncthreads();
+  }                                                 // if (worker)
+  __syncthreads();                                  // barriers initialised, TMEM allocated, operands of the set-up visible: workers and issuers
   tc_fence_after();
   const uint32_t tmemBase = *tmemSlot;
-  uint32_t ph1 = 0, ph2 = 0, phA = 0, phB = 0;
   TC2_STAMP(1);
+  if (worker) {
 #pragma unroll 1
-  for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N, FRAME>(a, unit, pass, tmemBase, ph1, ph2, phA, phB, FRAME ? pre : nullptr);
+    for (int pass = 0; pass < C::PASSES; pass++) tc2_pass<LOG2N, FRAME>(a, unit, pass, tmemBase, ph1, ph2, FRAME ? pre : nullptr);
+  } else {
+    uint32_t phA = 0, phB = 0, phT = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < C::PASSES; pass++) tc2_issue_pass<LOG2N>(a, pass, tmemBase, warp - kThreads / 32, phA, phB, phT);
+  }
   TC2_STAMP(2);
 
   // ---- costs leave the SM ------------------------------------------------------------------------------------
   tc_fence_before();
   // the common case - every PU of the CTA evaluated - copies the accumulators without a per-element state look-up
   bool mine = true;
-  if (FRAME) for (int i = tid; i < C::CTUS * 256; i += kThreads) mine = mine && ((i & 255) >= C::PUS || smem[C::VALID_OFF + i] == kPuEvaluate);
+  if (FRAME && worker) for (int i = tid; i < C::CTUS * 256; i += kThreads) mine = mine && ((i & 255) >= C::PUS || smem[C::VALID_OFF + i] == kPuEvaluate);
   const bool allEval = __syncthreads_and(mine) && unit * C::CTUS + C::CTUS <= a.totalCtus;
+  if (!worker) return;
   const FrameSource& fs = a.fs;
   if (!FRAME) {
     // batch mode: row outIndex of the caller's [nPU][35] table per PU
@@ -681,7 +709,7 @@ __device__ __noinline__ void tc2_body(const Tc2Args& a, const int unit) {
 }
 
 // blocks of one launch: depth-major (as rmd_frame_kernel); a depth has ceil(totalCtus / CTUS) units
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kCtaThreads, 2)
 rmd_frame_tc2_kernel(const __grid_constant__ Tc2Args a) {
   const int u2 = (a.totalCtus + 1) >> 1, u4 = (a.totalCtus + 3) >> 2;
   int b = blockIdx.x;
@@ -697,12 +725,12 @@ rmd_frame_tc2_kernel(const __grid_constant__ Tc2Args a) {
 
 // batch (S2) mode: one launch per PU size
 template <int LOG2N>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kCtaThreads, 2)
 rmd_batch_tc2_kernel(const __grid_constant__ Tc2Args a) { tc2_body<LOG2N, false>(a, blockIdx.x); }
 
 template <int LOG2N>
 cudaError_t launch_batch_tc2(const Tc2Args& a, int units, cudaStream_t st) {
-  rmd_batch_tc2_kernel<LOG2N><<<(units + Cfg<LOG2N>::CTUS - 1) / Cfg<LOG2N>::CTUS, kThreads, Cfg<LOG2N>::TOTAL, st>>>(a);
+  rmd_batch_tc2_kernel<LOG2N><<<(units + Cfg<LOG2N>::CTUS - 1) / Cfg<LOG2N>::CTUS, kCtaThreads, Cfg<LOG2N>::TOTAL, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -747,7 +775,7 @@ cudaError_t launch_rmd_frames_tc2(const FrameSource& fs, int nPics, int strong, 
   Tc2Args a;
   a.fs = fs; a.bs = BatchSource{}; a.strong = strong; a.totalCtus = total; a.tabWin = tabWin; a.tabN4 = tabN4; a.had = hadamard;
   const int u2 = (total + 1) >> 1, u4 = (total + 3) >> 2;
-  rmd_frame_tc2_kernel<<<2 * u4 + 3 * u2, kThreads, kSmemBytes, st>>>(a);
+  rmd_frame_tc2_kernel<<<2 * u4 + 3 * u2, kCtaThreads, kSmemBytes, st>>>(a);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

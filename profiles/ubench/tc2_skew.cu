@@ -3,6 +3,7 @@
 // Events of round am = 4 of the first pass, lane 0 of warps 0..3 of row group 0, clock64 of the SM:
 //   0 before wait MMA1 | 1 after it | 2 after epilogue 1 + tcgen05.st | 3 before arrive(A) | 4 after arrive(A) (+ MMA 2 issue in warp 0)
 //   5 after window / weight staging | 6 after wait MMA2 | 7 after arrive(B) (+ MMA 1 issue in warp 0) | 8 after epilogue 2
+//   9 / 10: events 0 / 1 of the NEXT round (am = 3)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -45,16 +46,16 @@ int main() {
   CK(cudaDeviceSynchronize());
   std::vector<long long> d((size_t)blocks * 64); CK(cudaMemcpy(d.data(), dDbg, d.size() * 8, cudaMemcpyDeviceToHost));
   // N = 8 blocks: indices [2*u4 + u2, 2*u4 + 2*u2)
-  const char* names[9] = {"pre-wait1", "wait1 done", "E1+st", "pre-arrA", "arrA(+iss2)", "staged", "wait2 done", "arrB(+iss1)", "E2 done"};
+  const char* names[11] = {"pre-wait1", "wait1 done", "E1+st", "pre-arrA", "arrA(+iss2)", "staged", "wait2 done", "arrB(+iss1)", "E2 done", "next pre-wait1", "next wait1 done"};
   for (int kind = 0; kind < 2; kind++) {
     const int b0 = kind == 0 ? 2 * u4 + u2 : 2 * u4, b1 = b0 + u2;
-    double avg[4][9] = {{0}}; double spreadA = 0, spreadB = 0, mma2lat = 0, mma1lat = 0; int n = 0;
+    double avg[4][11] = {{0}}; double spreadA = 0, spreadB = 0, mma2lat = 0, mma1lat = 0; int n = 0;
     for (int b = b0 + 300; b < b1 - 300; b++) {
       const long long* t = &d[(size_t)b * 64];
       if (!t[0]) continue;
       n++;
       long long t0 = t[0];
-      for (int w = 0; w < 4; w++) for (int e = 0; e < 9; e++) avg[w][e] += (double)(t[w * 16 + e] - t0);
+      for (int w = 0; w < 4; w++) for (int e = 0; e < 11; e++) avg[w][e] += (double)(t[w * 16 + e] - t0);
       long long lastA = 0, firstA = 1LL << 62, lastB = 0, firstB = 1LL << 62, done2 = 1LL << 62, done1n = 0;
       for (int w = 0; w < 4; w++) {
         lastA = std::max(lastA, t[w * 16 + 3]); firstA = std::min(firstA, t[w * 16 + 3]);
@@ -65,7 +66,7 @@ int main() {
       mma2lat += (double)(done2 - lastA);
     }
     printf("%s CTAs (%d sampled), round am = 4, cycles relative to warp 0's first stamp:\n", kind == 0 ? "N = 8" : "N = 16", n);
-    for (int w = 0; w < 4; w++) { printf("  warp %d:", w); for (int e = 0; e < 9; e++) printf(" %s %6.0f |", names[e], avg[w][e] / n); printf("\n"); }
+    for (int w = 0; w < 4; w++) { printf("  warp %d:", w); for (int e = 0; e < 11; e++) printf(" %s %6.0f |", names[e], avg[w][e] / n); printf("\n"); }
     printf("  spread of the four warps at arrive(A): %.0f cycles; earliest 'wait MMA2 done' minus LAST arrive(A): %.0f cycles (= tcgen05.wait::st + fence + issue + MMA 2 + commit)\n",
            spreadA / n, mma2lat / n);
   }
