@@ -143,6 +143,44 @@ patch("Lib/TLibEncoder/TEncSearch.cpp", [
   ("      uiSad = m_cDistParam.DistFunc(&m_cDistParam);\n\n      // motion cost\n      uiSad += m_pcRdCost->getCost(x, y);\n",
    "#ifdef CUCD_INTEGRATION\n      if (cucd_shim_me_active()) uiSad = cucd_shim_me_sad(x, y) + m_pcRdCost->getCost(x, y);\n#endif\n", "after"),
 ])
+# AMVP candidate check and merge candidates: source vs uni-directional motion-compensated prediction (integration build only)
+patch("Lib/TLibEncoder/TEncSearch.cpp", [
+  ("  uiCost = m_pcRdCost->getDistPart(g_bitDepth[CHANNEL_TYPE_LUMA], pcTemplateCand->getAddr(COMPONENT_Y, uiPartAddr), pcTemplateCand->getStride(COMPONENT_Y), pcOrgYuv->getAddr(COMPONENT_Y, uiPartAddr), pcOrgYuv->getStride(COMPONENT_Y), iSizeX, iSizeY, COMPONENT_Y, DF_SAD);\n",
+   "#ifdef CUCD_INTEGRATION\n"
+   "  if (cucd_shim_mc_enabled() && !(pcCU->getSlice()->testWeightPred() && pcCU->getSlice()->getSliceType() == P_SLICE)) {   /* xGetTemplateCost */\n"
+   "    TComPicYuv* cucdOrg = pcCU->getPic()->getPicYuvOrg();\n"
+   "    const long cucdOff = (long)(pcPicYuvRef->getAddr(COMPONENT_Y, pcCU->getCtuRsAddr(), pcCU->getZorderIdxInCtu() + uiPartAddr) - pcPicYuvRef->getAddr(COMPONENT_Y));\n"
+   "    const int cucdRs = pcPicYuvRef->getStride(COMPONENT_Y), cucdPuY = (int)(cucdOff / cucdRs), cucdPuX = (int)(cucdOff - (long)cucdPuY * cucdRs);\n"
+   "    uiCost = cucd_shim_mc_dist(cucdOrg->getWidth(COMPONENT_Y), cucdOrg->getHeight(COMPONENT_Y), g_bitDepth[CHANNEL_TYPE_LUMA],\n"
+   "                               pcCU->getSlice()->getSPS()->getUseStrongIntraSmoothing() ? 1 : 0, pcCU->getSlice()->getPOC(),\n"
+   "                               cucdOrg->getAddr(COMPONENT_Y), cucdOrg->getStride(COMPONENT_Y), pcPicYuvRef, pcPicYuvRef->getAddr(COMPONENT_Y), cucdRs,\n"
+   "                               pcPicYuvRef->getMarginX(COMPONENT_Y), pcPicYuvRef->getMarginY(COMPONENT_Y), cucdPuX, cucdPuY, iSizeX, iSizeY,\n"
+   "                               cMvCand.getHor(), cMvCand.getVer(), 0, 0);\n"
+   "  } else\n#endif\n", "before"),
+  ("  motionCompensation(pcCU, &m_tmpYuvPred, REF_PIC_LIST_X, iPartIdx);\n\n  UInt uiAbsPartIdx = 0;\n",
+   "#ifdef CUCD_INTEGRATION\n"
+   "  if (cucd_shim_mc_enabled()) {   /* xGetInterPredictionError: uni-directional candidates (bi-predictive ones average two 14-bit predictions: host) */\n"
+   "    UInt cucdPart = 0; Int cucdW = 0, cucdH = 0;\n"
+   "    pcCU->getPartIndexAndSize(iPartIdx, cucdPart, cucdW, cucdH);\n"
+   "    const Int cucdR0 = pcCU->getCUMvField(REF_PIC_LIST_0)->getRefIdx(cucdPart), cucdR1 = pcCU->getCUMvField(REF_PIC_LIST_1)->getRefIdx(cucdPart);\n"
+   "    const Bool cucdWp = (pcCU->getSlice()->getPPS()->getUseWP() && pcCU->getSlice()->getSliceType() == P_SLICE) || (pcCU->getSlice()->getPPS()->getWPBiPred() && pcCU->getSlice()->getSliceType() == B_SLICE);\n"
+   "    if (((cucdR0 >= 0) != (cucdR1 >= 0)) && !cucdWp) {\n"
+   "      const RefPicList cucdList = cucdR0 >= 0 ? REF_PIC_LIST_0 : REF_PIC_LIST_1;\n"
+   "      TComMv cucdMv = pcCU->getCUMvField(cucdList)->getMv(cucdPart);\n"
+   "      pcCU->clipMv(cucdMv);\n"
+   "      TComPicYuv* cucdRef = pcCU->getSlice()->getRefPic(cucdList, cucdR0 >= 0 ? cucdR0 : cucdR1)->getPicYuvRec();\n"
+   "      TComPicYuv* cucdOrg = pcCU->getPic()->getPicYuvOrg();\n"
+   "      const long cucdOff = (long)(cucdRef->getAddr(COMPONENT_Y, pcCU->getCtuRsAddr(), pcCU->getZorderIdxInCtu() + cucdPart) - cucdRef->getAddr(COMPONENT_Y));\n"
+   "      const int cucdRs = cucdRef->getStride(COMPONENT_Y), cucdPuY = (int)(cucdOff / cucdRs), cucdPuX = (int)(cucdOff - (long)cucdPuY * cucdRs);\n"
+   "      ruiErr = cucd_shim_mc_dist(cucdOrg->getWidth(COMPONENT_Y), cucdOrg->getHeight(COMPONENT_Y), g_bitDepth[CHANNEL_TYPE_LUMA],\n"
+   "                                 pcCU->getSlice()->getSPS()->getUseStrongIntraSmoothing() ? 1 : 0, pcCU->getSlice()->getPOC(),\n"
+   "                                 cucdOrg->getAddr(COMPONENT_Y), cucdOrg->getStride(COMPONENT_Y), cucdRef, cucdRef->getAddr(COMPONENT_Y), cucdRs,\n"
+   "                                 cucdRef->getMarginX(COMPONENT_Y), cucdRef->getMarginY(COMPONENT_Y), cucdPuX, cucdPuY, cucdW, cucdH,\n"
+   "                                 cucdMv.getHor(), cucdMv.getVer(), (m_pcEncCfg->getUseHADME() && (pcCU->getCUTransquantBypass(iPartIdx) == 0)) ? 1 : 0, 1);\n"
+   "      return;\n"
+   "    }\n"
+   "  }\n#endif\n", "before"),
+])
 # a12: TMV features (TEncCu.cpp:1561), integration build only (a13 / AdaptiveQP: the reference itself crashes with --AdaptiveQP=1, no in-situ test)
 patch("Lib/TLibEncoder/TEncCu.cpp", [
   ("       TMVFeature* feature_x = getTMVFeature(rpcBestCU);\n",

@@ -131,18 +131,11 @@ struct CucdMeShim {
 };
 inline CucdMeShim& cucd_me_shim() { static CucdMeShim s; return s; }
 inline bool cucd_shim_me_active() { return cucd_me_shim().active; }
-/* keyBlock != 0: bi-predictive refinement (if (bBi), TEncSearch.cpp:3787-3797): the search key is the caller's block, not the picture's */
-inline void cucd_shim_me_begin(int W, int H, int bd, int strong, int curPoc, const short* orgY, int orgStride, const void* refKey, const short* refY,
-                               int refStride, int marginX, int marginY, int cuX, int cuY, int puX, int puY, int w, int h, int subShift,
-                               const short* keyBlock = 0, int keyStride = 0) {
+/* the current picture (once per POC) and the reference plane (once per picture object) become resident; returns the reference's slot */
+inline int cucd_shim_me_pictures(int W, int H, int bd, int strong, int curPoc, const short* orgY, int orgStride, const void* refKey, const short* refY,
+                                 int refStride, int marginX, int marginY) {
   cucd_shim_open(W, H, bd, strong);
   CucdShim& s = cucd_shim(); CucdMeShim& m = cucd_me_shim();
-  m.ownKey = keyBlock != 0;
-  if (m.ownKey) {
-    m.key.resize((size_t)w * h);
-    for (int y = 0; y < h; y++) memcpy(&m.key[(size_t)y * w], keyBlock + (size_t)y * keyStride, (size_t)w * sizeof(short));
-    m.biPus++;
-  }
   if (curPoc != m.curPoc) {
     if ((cucd_ipc_mode() ? cucd_ipc().set_cur_picture(W, H, orgY, orgStride) : cucd_set_cur_picture(s.h, orgY, orgStride)) != CUCD_OK) cucd_shim_die("cucd_set_cur_picture");
     m.curPoc = curPoc; m.nRefs = 0;
@@ -154,6 +147,40 @@ inline void cucd_shim_me_begin(int W, int H, int bd, int strong, int curPoc, con
     if ((cucd_ipc_mode() ? cucd_ipc().set_ref_picture(W, H, slot, refY, refStride, marginX, marginY) : cucd_set_ref_picture(s.h, slot, refY, refStride, marginX, marginY)) != CUCD_OK)
       cucd_shim_die("cucd_set_ref_picture");
   }
+  return slot;
+}
+/* Distortion between the source PU and its uni-directional motion-compensated prediction at quarter-pel MV (mvxQ, mvyQ): what
+ * xGetTemplateCost (AMVP candidate check, TEncSearch.cpp:3719-3760: xPredInterBlk + getDistPart DF_SAD) and xGetInterPredictionError
+ * (merge candidates, :2905-2926: motionCompensation + SAD / Hadamard) compute.  HM's motion compensation of a PU is the separable
+ * 8-tap interpolation at (mv & 3) around the integer part (mv >> 2): one entry of cucd_me_subpel_cost's 49-point table. */
+struct CucdMcShim { long amvp, merge; CucdMcShim() : amvp(0), merge(0) {} };
+inline CucdMcShim& cucd_mc_shim() { static CucdMcShim s; return s; }
+inline bool cucd_shim_mc_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("CUCD_SHIM_MC"); on = (e && *e == '0') ? 0 : 1; }
+  return on != 0;
+}
+inline unsigned cucd_shim_mc_dist(int W, int H, int bd, int strong, int curPoc, const short* orgY, int orgStride, const void* refKey, const short* refY,
+                                  int refStride, int marginX, int marginY, int puX, int puY, int w, int h, int mvxQ, int mvyQ, int useHadamard, int isMerge) {
+  const int slot = cucd_shim_me_pictures(W, H, bd, strong, curPoc, orgY, orgStride, refKey, refY, refStride, marginX, marginY);
+  cucd_subpel_desc d = {puX, puY, w, h, slot, mvxQ >> 2, mvyQ >> 2, useHadamard};
+  uint32_t cost[49];
+  if ((cucd_ipc_mode() ? cucd_ipc().me_subpel_cost(1, &d, cost) : cucd_me_subpel_cost(cucd_shim().h, 1, &d, cost)) != CUCD_OK) cucd_shim_die("cucd_me_subpel_cost (MC distortion)");
+  if (isMerge) cucd_mc_shim().merge++; else cucd_mc_shim().amvp++;
+  return cost[((mvyQ & 3) + 3) * 7 + (mvxQ & 3) + 3];
+}
+/* keyBlock != 0: bi-predictive refinement (if (bBi), TEncSearch.cpp:3787-3797): the search key is the caller's block, not the picture's */
+inline void cucd_shim_me_begin(int W, int H, int bd, int strong, int curPoc, const short* orgY, int orgStride, const void* refKey, const short* refY,
+                               int refStride, int marginX, int marginY, int cuX, int cuY, int puX, int puY, int w, int h, int subShift,
+                               const short* keyBlock = 0, int keyStride = 0) {
+  CucdMeShim& m = cucd_me_shim();
+  m.ownKey = keyBlock != 0;
+  if (m.ownKey) {
+    m.key.resize((size_t)w * h);
+    for (int y = 0; y < h; y++) memcpy(&m.key[(size_t)y * w], keyBlock + (size_t)y * keyStride, (size_t)w * sizeof(short));
+    m.biPus++;
+  }
+  const int slot = cucd_shim_me_pictures(W, H, bd, strong, curPoc, orgY, orgStride, refKey, refY, refStride, marginX, marginY);
   m.d.x = puX; m.d.y = puY; m.d.w = w; m.d.h = h; m.d.ref_idx = slot; m.d.sub_shift = subShift;
   m.minX = -(64 + 8 + cuX - 1); m.maxX = W + 8 - cuX - 1;          /* TComDataCU::clipMv, TComDataCU.cpp:2946-2958, in integer pels */
   m.minY = -(64 + 8 + cuY - 1); m.maxY = H + 8 - cuY - 1;
@@ -269,7 +296,7 @@ inline void cucd_shim_tmv_check(int x, int y, int size, const double* ref130) {
 struct CucdShimReport { ~CucdShimReport() { CucdShim& s = cucd_shim();
   if (s.rmdCpu) fprintf(stderr, "cucd shim: %ld RMD PUs smaller than %d kept on the CPU (CUCD_SHIM_MIN_N)\n", s.rmdCpu, s.minN);
   if (s.ipcOpen) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld sub-pel refinements on the GPU, through cucd_server\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_frac_shim().calls); cucd_ipc().close_client(); }
-  if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld of them bi-predictive, %ld sub-pel refinements on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_me_shim().biPus, cucd_frac_shim().calls, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
+  if (s.h) { fprintf(stderr, "cucd shim: %ld pictures, %ld RMD PUs on the GPU, %ld ME searches (%ld SAD tiles, %ld probes) on the GPU, %ld of them bi-predictive, %ld sub-pel refinements on the GPU, %ld AMVP + %ld merge candidate distortions on the GPU, %ld TUs coded on the GPU, %ld TMV feature sets verified, %lld kernel launches\n", s.frameCalls, s.rmdCalls, cucd_me_shim().pus, cucd_me_shim().tilesComputed, cucd_me_shim().probes, cucd_me_shim().biPus, cucd_frac_shim().calls, cucd_mc_shim().amvp, cucd_mc_shim().merge, cucd_tu_shim().tus, s.tmvCalls, cucd_launch_count(s.h)); cucd_destroy(s.h); s.h = 0; } } };
 static CucdShimReport cucd_shim_report_at_exit;
 #endif
 

@@ -109,6 +109,10 @@ def test_fullsize_bitstream_md5_matches_recorded_reference(name, ref):
     import time
     import gen_golden as gg
     import gen_golden_md5 as gm
+    if "gop8" in name and not os.environ.get("CUCD_LONG_TESTS"):
+        # nine 1080p Main10 pictures with B-picture GOP8: ~20 M single-PU requests, 18 minutes on the GPU box.  Last run (round 2, every
+        # hook on, profiles/r02_summary.md): byte-identical.  CUCD_LONG_TESTS=1 runs it.
+        pytest.skip("long case: set CUCD_LONG_TESTS=1")
     for b in ("TAppEncoderCucd", "TAppDecoder"):
         if not os.path.exists(os.path.join(REF, b)):
             pytest.skip(f"oracle/_ref/{b} not built (needs /root/reference in the build container)")
@@ -116,8 +120,11 @@ def test_fullsize_bitstream_md5_matches_recorded_reference(name, ref):
     with tempfile.TemporaryDirectory(prefix="cucd_md5_") as wd:
         open(os.path.join(wd, "clip.yuv"), "wb").write(gg.synth_clip(W, H, frames, bd, ref["seed"]))
         t0 = time.perf_counter()
+        # full-size random access: the AMVP / merge candidate distortions (one 35 us request each, ~1 M per picture) stay on the CPU to
+        # bound the suite's run time; the 416x240 RA case above and the long gop8 case run them on the GPU
+        env = dict(os.environ, CUCD_SHIM_MC="0") if (ref["structure"] == "RA" and "gop8" not in name) else None
         r = subprocess.run(gm.encoder_args(os.path.join(REF, "TAppEncoderCucd"), W, H, frames, bd, qp, ref["structure"]), cwd=wd, capture_output=True,
-                           text=True, timeout=2400)
+                           text=True, timeout=2400, env=env)
         dt = time.perf_counter() - t0
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "RMD PUs on the GPU" in r.stderr, r.stderr[-500:]
