@@ -1,8 +1,9 @@
 // rmd_tc2_kernels.cu - tensor-core RMD frame kernel for 8-bit content (sm_100a, tcgen05 kind::i8).
 //
-// One CTA (256 threads = 2 row groups x 128 TMEM lanes, two CTAs per SM) evaluates 2 CTUs (N <= 16) or, in two
-// passes, 4 CTUs (N >= 32) at one depth.  A thread owns one 8x8 tile in one orientation ("row") for a pass;
-// per mode round and row group:
+// One CTA (256 worker threads = 2 row groups x 128 TMEM lanes, plus one MMA-issuing warp per row group; two CTAs per SM)
+// evaluates 2 CTUs (N <= 16) or, in two passes, 4 CTUs (N >= 32) at one depth.  A worker thread owns one 8x8 tile in one
+// orientation ("row") for a pass; the issuing warps wait for the rows' arrivals, issue the tcgen05.mma and fetch the
+// weights (cp.async.bulk).  Per mode round and row group:
 //     gather 32-byte reference window -> shared memory (A1) [N = 4: static 64-byte record row]
 //     MMA 1: D1 = A1 x weights(angle, phase)              prediction * 256 in byte 1 of every accumulator
 //     epilogue 1: tcgen05.ld.pack::16b + 16 PRMT -> 64 predicted bytes -> TMEM (A2)
