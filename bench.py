@@ -367,8 +367,10 @@ def run_ours(args, rank, world, local_rank):
     FORK_SW = ((1, 1, 1, 1), (1, 1, 1, 0))      # tests/golden/fork_ai8.npz: what SetDecisionSwitch left after the verify picture of a real encode
     if args.fork_aware:
         eng.set_decision_switches(1, *FORK_SW)
-    # each rank works on its own pictures (different seeds): weak scaling
-    orgs = [textured_plane(W, H, bd, 20261018 + 97 * rank, t) for t in range(P)]
+    # the job is a clip of world x P pictures per step; ranks deal its pictures out round-robin (no schedule coupling between the
+    # synthetic pictures: fast-cu-decision-hevc_b200/sharding.py shard_independent) - weak scaling, P pictures per rank and step
+    my_pictures = list(cucd.shard_independent(world * P, rank, world))
+    orgs = [textured_plane(W, H, bd, 20261018, t) for t in my_pictures]
     recs = [pseudo_recon(o, bd, t) for t, o in enumerate(orgs)]
 
     def pinned(shape, dtype):
