@@ -8,7 +8,8 @@
 //               = 2^23 + 32768 + [(32-f)*a + f*b + 16]                       (TComPrediction.cpp:368-383)
 //     an fp32 in [2^23, 2^24) has ulp 1, so the low 16 bits of its bit pattern are 32768 + 32*pred + remainder:
 //     tcgen05.ld.pack::16b returns two of them per register and pred = (x >> 5) & 0x3ff;
-//   * MMA 2:  D = -(1024 + src) x H + (1024 + pred) x H = H (pred - src) exactly (|.| <= 64 * 2047 < 2^24);
+//   * the residual (1024 + pred) - (1024 + src) = pred - src is one HSUB2 per pixel pair and exact in fp16 (|.| <= 1023 < 2048);
+//     MMA 2:  D = (pred - src) x H exactly (|.| <= 64 * 1023 < 2^24): no source operand on the tensor-core side;
 //     the epilogue sums |D| with FADD |x| (exact: the sum stays below 2^24) and converts once.
 // N = 4: a row is an 8x8 region of four PUs; the four quadrants are four N = 16, K = 16 products against ONE 16 x 16
 // weight table / H4 (x) H4, so region pixels are ordered quadrant-major: j = q*16 + lv*4 + lu.

@@ -5,8 +5,9 @@
 // holding exact integers (rmd_tc3.cuh).  Per mode round and row group:
 //     gather 24 reference samples (fp16 1024 + s) -> shared memory (A1)      [N = 4: static records, written by the prologue]
 //     MMA 1: D1 = A1 x weights(angle, phase) = 2^23 + 32768 + 32 * pred + remainder      (weights arrive by cp.async.bulk)
-//     epilogue 1: tcgen05.ld.pack::16b, (x >> 5) & 0x3ff | 0x6400 -> 64 predicted fp16 -> TMEM (A2)
-//     MMA 2: D2 = -(source tile, shared memory, static) x H + A2 x H                       Hadamard of the residual
+//     epilogue 1: tcgen05.ld.pack::16b, (x >> 5) & 0x3ff | 0x6400 -> 64 predicted fp16 (1024 + pred)
+//     (epilogue 1 also subtracts the row's source tile: A2 = pred - src, exact in fp16)
+//     MMA 2: D2 = A2 x H                                                                   Hadamard of the residual
 //     epilogue 2: sum |D2| with FADD |x| (exact), HM rounding, >> (bitDepth - 8)
 // Differences that matter: single-buffered operands (MMA 1 of a round has completed before the next round is staged), the
 // MMA 1 weights are fetched by one elected lane with a bulk copy that completes on an mbarrier (no registers, no LDG/STS per
@@ -14,6 +15,7 @@
 // core can see is a finite number (the stores are zeroed first: 0 x NaN would poison an accumulator).
 // Replaces, per PU, the reference loop TEncSearch.cpp:2327-2361 for internal bit depths 9 and 10 (8 also works and is tested).
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include "rmd_tc3.cuh"
 #include "satd_tc.cuh"
 #include "kernels.h"
@@ -235,9 +237,8 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
   unsigned char* uB1 = smem + C::B1_OFF + grpU * C::B1_BYTES;
   constexpr int NB = LOG2N == 2 ? 16 : 64;          // N of one MMA (N = 4: one quadrant)
   constexpr uint32_t kLboB = NB * 16;               // bytes between 16-byte K chunks of a B operand
-  const uint32_t idescPred = make_idesc_f16(128, NB, 0), idescHad = make_idesc_f16(128, NB, 0), idescHadNeg = make_idesc_f16(128, NB, 1);
+  const uint32_t idescPred = make_idesc_f16(128, NB, 0), idescHad = make_idesc_f16(128, NB, 0);
   const uint64_t dHad = make_desc(smem_u32(smem + C::HAD_OFF), kLboB, 128);
-  const uint64_t dAorg = make_desc(smem_u32(smem + C::AORG_OFF + grpU * C::AORG_BYTES), 2048, 128);
   const uint64_t dB1 = make_desc(smem_u32(uB1), kLboB, 128), dA1 = make_desc(smem_u32(smem + C::A1_OFF + grpU * C::A1_BYTES), 2048, 128);
   constexpr uint64_t kStepB = (2 * kLboB) >> 4;     // descriptor advance of one K = 16 step: two 16-byte chunks
   constexpr uint64_t kStepA = (2 * 2048) >> 4;      // ... of 128 rows
@@ -253,17 +254,13 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
       mbar_wait(uarrA, phA);
       tc_fence_after();
       if (elect_one3()) {
+        // A2 holds the residual pred - src itself (exact in fp16: |.| <= 1023): one product, no source operand
         if (LOG2N == 2) {
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            mma_f16_ss(uD2 + 16 * q, dAorg + q * kStepA, dHad, idescHadNeg, 0u);
-            mma_f16_ts(uD2 + 16 * q, uA2 + 8 * q, dHad, idescHad, 1u);
-          }
+          for (int q = 0; q < 4; q++) mma_f16_ts(uD2 + 16 * q, uA2 + 8 * q, dHad, idescHad, 0u);
         } else {
 #pragma unroll
-          for (int s = 0; s < 4; s++) mma_f16_ss(uD2, dAorg + s * kStepA, dHad + s * kStepB, idescHadNeg, s ? 1u : 0u);
-#pragma unroll
-          for (int s = 0; s < 4; s++) mma_f16_ts(uD2, uA2 + 8 * s, dHad + s * kStepB, idescHad, 1u);
+          for (int s = 0; s < 4; s++) mma_f16_ts(uD2, uA2 + 8 * s, dHad + s * kStepB, idescHad, s ? 1u : 0u);
         }
         mma_commit(ubar2);
       }
@@ -318,6 +315,21 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
     d[0] = make_uint4(w[0], w[1], w[2], w[3]);
     d[128] = make_uint4(w[4], w[5], w[6], w[7]);            // next 16-byte chunk: + 128 rows * 16 B
     d[256] = make_uint4(w[8], w[9], w[10], w[11]);
+  };
+  // A2 = (1024 + pred) - (1024 + src) per half = the residual itself, exact in fp16 (|pred - src| <= 1023): MMA 2 needs no source
+  // operand.  The row reads its source tile back from its own slot of the source buffer (written once per pass, below).
+  auto store_a2 = [&](uint32_t* q) {
+    const uint4* sv = reinterpret_cast<const uint4*>(sAorg + rowChunk);
+    auto sub2 = [](uint32_t x, uint32_t y) {
+      const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&x), *reinterpret_cast<const __half2*>(&y));
+      return *reinterpret_cast<const uint32_t*>(&d);
+    };
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint4 o = sv[i * 128];
+      q[4 * i] = sub2(q[4 * i], o.x); q[4 * i + 1] = sub2(q[4 * i + 1], o.y); q[4 * i + 2] = sub2(q[4 * i + 2], o.z); q[4 * i + 3] = sub2(q[4 * i + 3], o.w);
+    }
+    tmem_st32(tA2 + laneOff, q);
   };
   auto rec = [&](int q, int s) { return ld_s16(smem + rec_slot_off(r.ctu, r.o, 4 * r.pu + q, s)); };
   // epilogue 2 + cost hand-over for mode `mode` (has = the row has a mode in this round)
@@ -384,7 +396,7 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
   fence_async_smem();                               // the source operand is read by the tensor core (async proxy)
 
   // ---- round 0 -------------------------------------------------------------------------------------------------
-  tmem_st32(tA2 + laneOff, p);
+  store_a2(p);
   issue_mma2();
   stage_window(8, 32);
   wait_mma2();
@@ -411,7 +423,7 @@ __device__ __forceinline__ void tc3_pass(const Tc3Args& a, const int unit, const
       if (LOG2N == 2) patch_edge0_region16(rec, maxVal, p);
       else if (r.u0 == 0) patch_edge0_tile16(unfMain, unfSide, r.v0, maxVal, p);
     }
-    tmem_st32(tA2 + laneOff, p);
+    store_a2(p);
     // projected samples of the next (negative) angle; ordering argument as in tc2_pass: a window that may read another row's
     // projected samples is gathered after wait_mma2 (MMA 2 is only issued once every row has announced arrA, which a row
     // does after writing its projected samples)

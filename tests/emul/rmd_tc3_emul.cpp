@@ -108,19 +108,30 @@ void emul_cta3(const FrameSource& fs, int strong, int bitDepth, int totalCtus, i
         std::memcpy(smem + C::A1_OFF + grp * C::A1_BYTES + row_chunk(rowTid) + 3 * 2048, c3, 16);
       }
     }
-    // MMA 2: D2 = -(source) x H + A2 x H
+    // store_a2: A2 = (1024 + pred) - (1024 + src) per half as HSUB2 computes it - exact, because the difference of two fp16
+    // integers in [1024, 2048) (or 0 for rows that are not evaluated) is an integer of magnitude <= 2047; then MMA 2: D2 = A2 x H
+    auto hsub = [](uint16_t x, uint16_t y) -> uint16_t {
+      const double d = h2d(x) - h2d(y);
+      const int v = (int)d;
+      if ((double)v != d || v < -2048 || v > 2048) return 0x7e00;                 // not exactly representable: poison (NaN)
+      return (uint16_t)((v < 0 ? 0x8000 : 0) | h16_of_int(v < 0 ? -v : v));
+    };
     auto hadamard = [&]() {
       for (int tid = 0; tid < kThreads; tid++) {
         const int grp = tid >> 7, row = tid & 127;
+        uint32_t A2[32];
+        for (int w = 0; w < 32; w++) {
+          const unsigned char* sp = smem + C::AORG_OFF + grp * C::AORG_BYTES + (w >> 2) * 2048 + row_chunk(row) + (w & 3) * 4;
+          const uint32_t pw = P[tid * 32 + w];
+          A2[w] = (uint32_t)hsub((uint16_t)(pw & 0xffffu), rd16(sp)) | ((uint32_t)hsub((uint16_t)(pw >> 16), rd16(sp + 2)) << 16);
+        }
         for (int j = 0; j < 64; j++) {
           const int q = log2n == 2 ? j >> 4 : 0, jl = log2n == 2 ? j & 15 : j, K = log2n == 2 ? 16 : 64;
           double s = 0;
           for (int k = 0; k < K; k++) {
             const int kk = q * 16 + k;
-            const uint32_t w = P[tid * 32 + (kk >> 1)];
-            const double a2 = h2d((uint16_t)((kk & 1) ? w >> 16 : w & 0xffffu));
-            const double hm = h2d(rd16(smem + C::HAD_OFF + umma16_off(NB, jl, k)));
-            s += (a2 - a_elem(C::AORG_OFF, C::AORG_BYTES, grp, row, kk)) * hm;
+            const uint32_t w = A2[kk >> 1];
+            s += h2d((uint16_t)((kk & 1) ? w >> 16 : w & 0xffffu)) * h2d(rd16(smem + C::HAD_OFF + umma16_off(NB, jl, k)));
           }
           D[tid * 64 + j] = f32_bits(s);
         }
