@@ -714,9 +714,10 @@ def run_inter(args, rank, world, local_rank):
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     algo = me_algo_bytes(pus)
     achieved = algo / (me_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "me_sad_u8_kernel" if bd == 8 else "me_sad_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "me_sad_dy_kernel<u8>" if bd == 8 else "me_sad_dy_kernel<s16>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "launch_ms": me_ms, "launches_timed": len(me_ev), "algorithmic_bytes_per_launch": algo, "peak_source": peak_src,
-                "note": "the dominant launch of an inter step: one SAD surface launch per reference (CUDA events on the launching stream around the "
+                "note": "the dominant launch of an inter step: one SAD surface call per reference = the dy-lane kernel (tiles M / E of csrc/me_core.cuh) "
+                        "plus the dx-lane kernel for the last row of the window (CUDA events on the launching stream around the "
                         "call; includes the upload of its job records).  Algorithmic bytes per PU = source + reference window + surface (SURVEY.md 8d); "
                         f"the work is {(2 * ME_RANGE + 1) ** 2} candidates x w x h absolute differences per PU: integer-ALU bound (VABSDIFF4), see profiles/"}
     if rank == 0:

@@ -15,6 +15,7 @@
 #include <deque>
 #include "handle.h"
 #include "rmd_tc2.cuh"
+#include "me_core.cuh"
 
 using namespace cucd;
 
@@ -389,11 +390,13 @@ static int sync_ref_table(cucd_handle* h) {
 
 // validate the PUs, build job + tile records into `scratch` (pinned); returns the sizes through the references
 // ownBlocks: the source blocks are the caller's (cucd_me_sad_surface_src): offsets run through the packed block array
-static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinBuf<uint8_t>& scratch, size_t& jobBytes, size_t& tileBytes, long long& total, long long& nTiles,
-                         bool ownBlocks = false, size_t* srcSamples = nullptr) {
+// Tile records (me_core.cuh): the dy-lane tiles of every PU first, then the dx-lane tiles; nTilesDy / nTilesO count them.
+static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinBuf<uint8_t>& scratch, size_t& jobBytes, size_t& tileBytes, long long& total, long long& nTilesDy,
+                         long long& nTilesO, bool ownBlocks = false, size_t* srcSamples = nullptr) {
   const int W = h->cfg.width, H = h->cfg.height;
   const int tileRows = (h->cfg.bit_depth == 8 && !ownBlocks) ? 16 : 8;     // me_sad_u8_kernel covers 32 x 16 candidates per CTA, me_sad_kernel 32 x 8
-  total = 0; nTiles = 0;
+  const bool fast = !ownBlocks;                                            // caller-supplied blocks may hold signed samples: dx-lane kernel only
+  total = 0; nTilesDy = 0; nTilesO = 0;
   for (int i = 0; i < nPU; i++) {
     const cucd_me_desc& d = desc[i];
     // HM's PU widths are multiples of 4 (4..64, AMP 12 / 24 / 48 included); the 8-bit kernel reads the source as 32-bit words
@@ -405,16 +408,18 @@ static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinB
     if (d.x + d.left < -r.marginX || d.y + d.top < -r.marginY || d.x + d.w - 1 + d.right > W - 1 + r.marginX || d.y + d.h - 1 + d.bottom > H - 1 + r.marginY)
       return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: window leaves the padded reference picture");
     const int cols = d.right - d.left + 1, rows = d.bottom - d.top + 1;
-    nTiles += (long long)((cols + 31) / 32) * ((rows + tileRows - 1) / tileRows);
+    if (cols > kMeMaxWindow || rows > kMeMaxWindow) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: window too large");
+    me_enum_tiles(cols, rows, fast, tileRows, [&](int kind, int, int) { if (kind == kMeKindO) nTilesO++; else nTilesDy++; });
     total += (long long)cols * rows;
   }
+  const long long nTiles = nTilesDy + nTilesO;
   if (nTiles > 0x7fffffffll) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: batch too large");
   jobBytes = up16((size_t)nPU * sizeof(MeJob)); tileBytes = up16((size_t)nTiles * 4);
   CK(scratch.reserve(jobBytes + 2 * tileBytes));
   MeJob* jobs = reinterpret_cast<MeJob*>(scratch.p);
   int32_t* tileJob = reinterpret_cast<int32_t*>(scratch.p + jobBytes);
   int32_t* tileIdx = reinterpret_cast<int32_t*>(scratch.p + jobBytes + tileBytes);
-  long long off = 0; size_t nt = 0, blockOff = 0;
+  long long off = 0; size_t ntDy = 0, ntO = (size_t)nTilesDy, blockOff = 0;
   for (int i = 0; i < nPU; i++) {
     const cucd_me_desc& d = desc[i];
     const RefPlane& r = h->refs[d.ref_idx];
@@ -429,8 +434,10 @@ static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinB
     j.subShift = (int16_t)(special ? d.sub_shift : 0); j.pad = 0;
     j.outOff = off;
     const int cols = d.right - d.left + 1, rows = d.bottom - d.top + 1;
-    const int tiles = ((cols + 31) / 32) * ((rows + tileRows - 1) / tileRows);
-    for (int t = 0; t < tiles; t++) { tileJob[nt] = i; tileIdx[nt] = t; nt++; }
+    me_enum_tiles(cols, rows, fast, tileRows, [&](int kind, int x0, int y0) {
+      size_t& nt = kind == kMeKindO ? ntO : ntDy;
+      tileJob[nt] = i; tileIdx[nt] = me_tile_pack(kind, x0, y0); nt++;
+    });
     off += (long long)cols * rows;
   }
   if (blockOff > 0x7fffffffull) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface_src: batch too large");
@@ -442,8 +449,8 @@ static int me_sad_surface_impl(cucd_handle* h, int nPU, const cucd_me_desc* desc
   const bool own = src != nullptr;
   if (!own && !h->curSet) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: cucd_set_cur_picture not called");
   CK(cudaSetDevice(h->cfg.device));
-  size_t jobBytes, tileBytes, srcSamples = 0; long long total, nTiles;
-  const int rc = me_build_jobs(h, nPU, desc, h->hScratch, jobBytes, tileBytes, total, nTiles, own, &srcSamples);
+  size_t jobBytes, tileBytes, srcSamples = 0; long long total, nTilesDy, nTilesO;
+  const int rc = me_build_jobs(h, nPU, desc, h->hScratch, jobBytes, tileBytes, total, nTilesDy, nTilesO, own, &srcSamples);
   if (rc != CUCD_OK) return rc;
   if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
   BatchIo io(h);
@@ -457,7 +464,7 @@ static int me_sad_surface_impl(cucd_handle* h, int nPU, const cucd_me_desc* desc
   const uint8_t* dAll = io.din<uint8_t>(iAll);
   if (!io.direct) CK(cudaEventRecord(h->evK0, h->sMain));
   CK(launch_me_sad(mp, reinterpret_cast<const MeJob*>(dAll), nPU, reinterpret_cast<const int32_t*>(dAll + jobBytes), reinterpret_cast<const int32_t*>(dAll + jobBytes + tileBytes),
-                   (int)nTiles, io.dout<uint32_t>(oSad), h->sMain, &h->launches));
+                   (int)nTilesDy, (int)nTilesO, io.dout<uint32_t>(oSad), h->sMain, &h->launches));
   if (!io.direct) { CK(cudaEventRecord(h->evK1, h->sMain)); h->kTimed = true; } else h->kTimed = false;
   if (io.download(h->sMain) != CUCD_OK) return CUCD_ERR_CUDA;
   flush_launches(h);
@@ -491,8 +498,8 @@ int cucd_dev_me_sad_surface(cucd_handle* h, void* stream, int nPU, const cucd_me
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if (dev_records_begin(h, st) != CUCD_OK) return CUCD_ERR_CUDA;
-  size_t jobBytes, tileBytes; long long total, nTiles;
-  const int rc = me_build_jobs(h, nPU, desc, h->hDevScratch, jobBytes, tileBytes, total, nTiles);
+  size_t jobBytes, tileBytes; long long total, nTilesDy, nTilesO;
+  const int rc = me_build_jobs(h, nPU, desc, h->hDevScratch, jobBytes, tileBytes, total, nTilesDy, nTilesO);
   if (rc != CUCD_OK) return rc;
   if (sync_ref_table(h) != CUCD_OK) return CUCD_ERR_CUDA;
   CK(h->dDevStage.reserve(jobBytes + 2 * tileBytes));
@@ -502,7 +509,7 @@ int cucd_dev_me_sad_surface(cucd_handle* h, void* stream, int nPU, const cucd_me
   mp.cur = h->dCur.p; mp.curStride = h->curStride; mp.ref = h->dRefPtr.p; mp.refStride = h->dRefStride.p; mp.bitDepth = h->cfg.bit_depth;
   const uint8_t* dAll = h->dDevStage.p;
   CK(launch_me_sad(mp, reinterpret_cast<const MeJob*>(dAll), nPU, reinterpret_cast<const int32_t*>(dAll + jobBytes), reinterpret_cast<const int32_t*>(dAll + jobBytes + tileBytes),
-                   (int)nTiles, d_sad, st, &h->launches));
+                   (int)nTilesDy, (int)nTilesO, d_sad, st, &h->launches));
   CK(cudaEventRecord(h->evDevDone, st)); h->devBusy = true;
   flush_launches(h);
   return CUCD_OK;

@@ -1,0 +1,216 @@
+// me_core.cuh - tile decomposition and per-lane arithmetic of the integer-ME SAD surface kernels (me_kernels.cu).
+// Host/device so that tests/emul can replay it.  Reference: TComRdCost::xGetSAD* (TComRdCost.cpp:465-962): rows stepped by
+// 1 << subShift, sum << subShift, then >> (bitDepth - 8); the candidates are those of TEncSearch::xTZSearchHelp
+// (TEncSearch.cpp:336-437) / xPatternSearch (:3886-3943).
+//
+// A surface (cols x rows candidates of one PU) is cut into three kinds of tiles:
+//   M  32 dx x 64 dy, "dy lanes": a lane owns one dy, a warp one byte / half-word alignment of dx, a thread EIGHT candidates
+//      dx = x0 + s + stride * k that slide over the same staged reference words: one shared-memory load (+ one PRMT / SHF when the
+//      alignment is not 0) feeds eight absolute-difference instructions, the source word is a broadcast load.
+//   E  the last 1..4 columns of a window whose width is 32 * n + 1..4 (HM's +-R windows are 2R + 1 wide): dy lanes, one candidate
+//      per thread, up to 128 dy per CTA.
+//   O  everything else (windows below 32 x 32, the last rows % 32 rows, a right strip wider than 4): the dx-lane tiles of
+//      me_sad_kernel / me_sad_u8_kernel.
+#pragma once
+#include "rmd_core.cuh"
+
+namespace cucd {
+
+constexpr int kMeKindO = 0, kMeKindM = 1, kMeKindE = 2;
+constexpr int kMeMaxWindow = 8191;                  // cols, rows of a window (13 bits each in a tile record)
+constexpr int kMeDyPitch8 = 25;                     // staged reference row in 32-bit words, 8-bit samples: >= (64 + 31) / 4 + 2, odd (lanes = rows)
+constexpr int kMeDyPitch16 = 49;                    // 16-bit samples: >= (64 + 31) / 2 + 2, odd
+constexpr int kMeDyRows = 64 + 127;                 // an E tile covers up to 128 dy
+constexpr int kMeDyK = 8;                           // candidates per thread in an M tile
+
+CUCD_HD int32_t me_tile_pack(int kind, int x0, int y0) { return (int32_t)((kind << 26) | (y0 << 13) | x0); }
+CUCD_HD void me_tile_unpack(int32_t t, int& kind, int& x0, int& y0) { kind = (t >> 26) & 3; y0 = (t >> 13) & 0x1fff; x0 = t & 0x1fff; }
+CUCD_HD int me_edge_blocks(int cr) { return 8 / cr < 4 ? 8 / cr : 4; }     // 32-dy blocks of an E tile with cr columns (8 warps)
+
+// emit(kind, x0, y0) for every tile of a cols x rows window; `fast`: the dy-lane kernel may be used (picture-resident source, unsigned samples)
+template <class F>
+inline void me_enum_tiles(int cols, int rows, bool fast, int tileRowsO, F&& emit) {
+  if (!fast || cols < 32 || rows < 32) {
+    for (int y0 = 0; y0 < rows; y0 += tileRowsO) for (int x0 = 0; x0 < cols; x0 += 32) emit(kMeKindO, x0, y0);
+    return;
+  }
+  const int colsMain = cols & ~31, rowsA = rows & ~31, cr = cols - colsMain;
+  for (int y0 = 0; y0 < rowsA; y0 += 64) for (int x0 = 0; x0 < colsMain; x0 += 32) emit(kMeKindM, x0, y0);
+  if (cr > 0) {
+    if (cr <= 4) { const int span = 32 * me_edge_blocks(cr); for (int y0 = 0; y0 < rows; y0 += span) emit(kMeKindE, colsMain, y0); }
+    else for (int y0 = 0; y0 < rows; y0 += tileRowsO) emit(kMeKindO, colsMain, y0);
+  }
+  for (int y0 = rowsA; y0 < rows; y0 += tileRowsO) for (int x0 = 0; x0 < colsMain; x0 += 32) emit(kMeKindO, x0, y0);
+}
+
+// geometry of a dy-lane tile (kinds M and E), identical for both sample widths
+struct MeDyTile {
+  int nLam;        // candidate rows (dy) of the tile
+  int winW, winH;  // staged reference window in samples / rows
+  int cr;          // E: columns of the strip
+};
+CUCD_HD MeDyTile me_dy_tile(int kind, int x0, int y0, int w, int h, int cols, int rows) {
+  MeDyTile t;
+  if (kind == kMeKindM) { const int rowsA = rows & ~31; t.cr = 32; t.nLam = rowsA - y0 < 64 ? rowsA - y0 : 64; t.winW = w + 31; }
+  else { t.cr = cols - x0; const int span = 32 * me_edge_blocks(t.cr); t.nLam = rows - y0 < span ? rows - y0 : span; t.winW = w + t.cr - 1; }
+  t.winH = h + t.nLam - 1;
+  return t;
+}
+// what a warp of a dy-lane tile does: candidates dx = x0 + delta0 + stride * k (k < K), dy = y0 + 32 * blk + lane
+struct MeDyWarp { bool active; int blk, s, wbase, delta0; };
+template <bool U8>
+CUCD_HD MeDyWarp me_dy_warp(int kind, int warp, int cr) {
+  MeDyWarp q;
+  if (kind == kMeKindM) {
+    q.active = true; q.blk = warp >> 2;
+    if (U8) { q.s = warp & 3; q.wbase = 0; q.delta0 = q.s; }                                        // delta = s + 4 k
+    else { q.s = warp & 1; q.wbase = 8 * ((warp >> 1) & 1); q.delta0 = q.s + 2 * q.wbase; }         // delta = s + 2 (8 kg + k)
+  } else {
+    const int col = warp % cr; q.blk = warp / cr; q.active = q.blk < me_edge_blocks(cr); q.delta0 = col;
+    if (U8) { q.s = col; q.wbase = 0; } else { q.s = col & 1; q.wbase = col >> 1; }
+  }
+  return q;
+}
+
+// ---- intrinsics with host restatements ---------------------------------------------------------------------------------------
+CUCD_HD uint32_t me_prmt_shift(uint32_t lo, uint32_t hi, uint32_t s) {   // bytes s .. s + 3 of the pair {lo, hi}
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(lo, hi, 0x3210u + 0x1111u * s);
+#else
+  return s ? (uint32_t)((((uint64_t)hi << 32) | lo) >> (8 * s)) : lo;
+#endif
+}
+CUCD_HD uint32_t me_sad4(uint32_t a, uint32_t b, uint32_t acc) {          // VABSDIFF4.U8.ACC
+#if defined(__CUDA_ARCH__)
+  uint32_t d;                                                             // __vsadu4(a, b) + acc keeps a separate IADD: the header's asm has a literal 0 addend
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+  return d;
+#else
+  for (int i = 0; i < 4; i++) { const int x = (a >> (8 * i)) & 255, y = (b >> (8 * i)) & 255; acc += (uint32_t)(x > y ? x - y : y - x); }
+  return acc;
+#endif
+}
+CUCD_HD uint32_t me_min2(uint32_t a, uint32_t b) {                        // VIMNMX.S16x2
+#if defined(__CUDA_ARCH__)
+  return __vmins2(a, b);
+#else
+  const int16_t al = (int16_t)(a & 0xffffu), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xffffu), bh = (int16_t)(b >> 16);
+  return (uint32_t)(uint16_t)(al < bl ? al : bl) | ((uint32_t)(uint16_t)(ah < bh ? ah : bh) << 16);
+#endif
+}
+CUCD_HD uint32_t me_fold2(uint32_t packed, uint32_t acc) {                // acc + low half + high half (unsigned IDP.2A)
+#if defined(__CUDA_ARCH__)
+  return __dp2a_lo(packed, 0x0101u, acc);
+#else
+  return acc + (packed & 0xffffu) + (packed >> 16);
+#endif
+}
+
+// ---- per-lane work of a dy-lane tile -------------------------------------------------------------------------------------------
+// cw: the PU as words, row y at cw[y * words]; rw: the staged window, row r at rw[r * P]; lam: the lane's candidate row inside the tile.
+// Aligned word m of a window row = staged bytes 4 (wbase + m) + s ...; candidate k compares source word j with aligned word j + k.
+template <int K>
+CUCD_HD void me_dy_sad_u8(const uint32_t* cw, const uint32_t* rw, int words, int h, int step, int lam, int wbase, int s, uint32_t* acc /*K*/) {
+#pragma unroll
+  for (int k = 0; k < K; k++) acc[k] = 0;
+  for (int y = 0; y < h; y += step) {
+    const uint32_t* rr = rw + (lam + y) * kMeDyPitch8 + wbase;
+    const uint32_t* cc = cw + y * words;
+    for (int jc = 0; jc < words; jc += K) {
+      const int n = words - jc < K ? words - jc : K;
+      uint32_t A[2 * K - 1];
+      uint32_t prev = rr[jc];
+#pragma unroll
+      for (int m = 0; m < 2 * K - 1; m++)
+        if (m < n + K - 1) { const uint32_t nx = rr[jc + m + 1]; A[m] = me_prmt_shift(prev, nx, (uint32_t)s); prev = nx; }
+#pragma unroll
+      for (int t = 0; t < K; t++) {
+        if (t < n) {
+          const uint32_t c = cc[jc + t];
+#pragma unroll
+          for (int k = 0; k < K; k++) acc[k] = me_sad4(c, A[t + k], acc[k]);
+        }
+      }
+    }
+  }
+}
+
+// 9/10-bit samples as packed int16 pairs, all in [0, 2^bitDepth): sum |c - r| = sum c + sum r - 2 sum min(c, r).  The three sums are
+// accumulated per 16-bit half in packed words (one IADD per word, two fused into an IADD3) and folded into 32-bit totals every
+// foldRows rows, before a half can exceed 65535: foldRows * pairs * (2^bitDepth - 1) < 65536.
+CUCD_HD int me_fold_rows(int bitDepth, int pairs) { const int f = (1 << (16 - bitDepth)) / pairs; return f < 1 ? 1 : f; }
+template <int K>
+CUCD_HD void me_dy_sad_s16(const uint32_t* cw, const uint32_t* rw, int pairs, int h, int step, int lam, int wbase, int s, int foldRows, uint32_t* sad /*K*/) {
+  uint32_t totM[K], totR[K], pM[K], pR[K], totA = 0, pA = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) { totM[k] = 0; totR[k] = 0; pM[k] = 0; pR[k] = 0; }
+  int pend = 0;
+  for (int y = 0; y < h; y += step) {
+    const uint32_t* rr = rw + (lam + y) * kMeDyPitch16 + wbase;
+    const uint32_t* cc = cw + y * pairs;
+    for (int jc = 0; jc < pairs; jc += K) {
+      const int n = pairs - jc < K ? pairs - jc : K;
+      uint32_t A[2 * K - 1];
+      uint32_t prev = rr[jc];
+#pragma unroll
+      for (int m = 0; m < 2 * K - 1; m++)
+        if (m < n + K - 1) { const uint32_t nx = rr[jc + m + 1]; A[m] = funnel_r(prev, nx, 16u * (uint32_t)s); prev = nx; }
+#pragma unroll
+      for (int t = 0; t < K; t += 2) {                                    // two source words per step: the additions pair up into IADD3
+        if (t + 1 < n) {
+          const uint32_t c0 = cc[jc + t], c1 = cc[jc + t + 1];
+          pA = pA + c0 + c1;
+#pragma unroll
+          for (int k = 0; k < K; k++) { pM[k] = pM[k] + me_min2(c0, A[t + k]) + me_min2(c1, A[t + 1 + k]); pR[k] = pR[k] + A[t + k] + A[t + 1 + k]; }
+        } else if (K == 1 && t < n) {                                     // pairs = w / 2 is even: only the one-candidate tiles step by single words
+          const uint32_t c = cc[jc + t];
+          pA += c;
+#pragma unroll
+          for (int k = 0; k < K; k++) { pM[k] += me_min2(c, A[t + k]); pR[k] += A[t + k]; }
+        }
+      }
+    }
+    if (++pend == foldRows) {
+      pend = 0;
+      totA = me_fold2(pA, totA); pA = 0;
+#pragma unroll
+      for (int k = 0; k < K; k++) { totM[k] = me_fold2(pM[k], totM[k]); totR[k] = me_fold2(pR[k], totR[k]); pM[k] = 0; pR[k] = 0; }
+    }
+  }
+  totA = me_fold2(pA, totA);
+#pragma unroll
+  for (int k = 0; k < K; k++) sad[k] = totA + me_fold2(pR[k], totR[k]) - 2u * me_fold2(pM[k], totM[k]);
+}
+
+// ---- staging of a dy-lane tile (every thread of the CTA; tid = 32 * warp + lane) ---------------------------------------------------
+// source: rows y = 0, step, 2 step, ... of the PU at cur (stride curStride) -> cw[y * (w / spw) + ...], spw samples per word
+template <bool U8>
+CUCD_HD void me_dy_stage_cur(int warp, int lane, const int16_t* cur, int curStride, int w, int h, int step, uint32_t* cw) {
+  constexpr int SPW = U8 ? 4 : 2;
+  const int words = w / SPW;
+  for (int y = warp * step; y < h; y += 8 * step)
+    for (int q = lane; q < words; q += 32) {
+      const int16_t* p = cur + (size_t)y * curStride + q * SPW;
+      cw[y * words + q] = U8 ? ((uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) | ((uint32_t)(uint8_t)p[3] << 24))
+                             : ((uint32_t)(uint16_t)p[0] | ((uint32_t)(uint16_t)p[1] << 16));
+    }
+}
+// reference window: winH rows of winW samples starting at ref (stride refStride); the words a candidate's PRMT / SHF touches beyond
+// winW are zero filled, nothing outside the window is read
+template <bool U8>
+CUCD_HD void me_dy_stage_ref(int warp, int lane, const int16_t* ref, long long refStride, int winW, int winH, uint32_t* rw) {
+  constexpr int SPW = U8 ? 4 : 2, P = U8 ? kMeDyPitch8 : kMeDyPitch16;
+  int wp = (winW + SPW - 1) / SPW + 1;
+  if (wp > P) wp = P;
+  for (int r = warp; r < winH; r += 8)
+    for (int q = lane; q < wp; q += 32) {
+      const int16_t* p = ref + (long long)r * refStride + q * SPW;
+      uint32_t v = 0;
+#pragma unroll
+      for (int i = 0; i < SPW; i++)
+        if (q * SPW + i < winW) v |= (U8 ? (uint32_t)(uint8_t)p[i] : (uint32_t)(uint16_t)p[i]) << ((U8 ? 8 : 16) * i);
+      rw[r * P + q] = v;
+    }
+}
+
+}  // namespace cucd

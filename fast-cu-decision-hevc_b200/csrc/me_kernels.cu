@@ -6,12 +6,14 @@
 // (TComRdCost.cpp:465-962): rows stepped by 1<<subShift, sum << subShift, then >> (bitDepth-8).
 // The host walks the TZ pattern over the table and adds getCost(mv) itself, so ties break as in HM.
 //
-// One CTA = one 32x8 tile of candidates of one PU.  The PU and the (w+32)x(h+8) reference window are
-// staged once in shared memory; a lane owns one dx, a warp one dy.  9/10-bit content: samples as packed
-// int16 pairs, |a-b| per half = max-min (VIMNMX.S16x2 x2 + ISUB), accumulated with IDP.2A.  8-bit content
-// (me_sad_u8_kernel): samples as bytes, VABSDIFF4.U8.ACC.
+// A surface is cut into tiles (me_core.cuh, me_enum_tiles).  The bulk of a window of 32 x 32 candidates or more goes to
+// me_sad_dy_kernel (tiles M / E, "dy lanes": a thread owns eight candidates that slide over the same staged reference words);
+// small windows, the last rows % 32 rows and caller-supplied (signed) source blocks go to the dx-lane kernels below (tiles O):
+// one CTA = one 32x8 (32x16 for bytes) tile of candidates of one PU, the PU and the reference window staged once in shared memory,
+// a lane owns one dx, a warp one dy.  9/10-bit content: samples as packed int16 pairs, |a-b| per half = max-min (VIMNMX.S16x2 x2 +
+// ISUB), accumulated with IDP.2A.  8-bit content (me_sad_u8_kernel): samples as bytes, VABSDIFF4.U8.ACC.
 #include <cuda_runtime.h>
-#include "rmd_core.cuh"
+#include "me_core.cuh"
 #include "kernels.h"
 
 namespace cucd {
@@ -32,9 +34,9 @@ me_sad_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const MeJob job = jobs[tileJob[blockIdx.x]];
   const int cols = job.right - job.left + 1, rows = job.bottom - job.top + 1;
-  const int tilesX = (cols + kMeTileX - 1) / kMeTileX;
-  const int t = tileIdx[blockIdx.x];
-  const int dx0 = (t % tilesX) * kMeTileX, dy0 = (t / tilesX) * kMeTileY;     // relative to (left, top)
+  int kind, dx0, dy0;                                                          // tile origin relative to (left, top)
+  me_tile_unpack(tileIdx[blockIdx.x], kind, dx0, dy0);
+  (void)kind;
   const int w = job.w, h = job.h;
 
   const int16_t* cur = mp.cur + job.curOff;
@@ -88,9 +90,9 @@ me_sad_u8_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const MeJob job = jobs[tileJob[blockIdx.x]];
   const int cols = job.right - job.left + 1, rows = job.bottom - job.top + 1;
-  const int tilesX = (cols + kMeTileX - 1) / kMeTileX;
-  const int t = tileIdx[blockIdx.x];
-  const int dx0 = (t % tilesX) * kMeTileX, dy0 = (t / tilesX) * kMe8TileY;
+  int kind, dx0, dy0;
+  me_tile_unpack(tileIdx[blockIdx.x], kind, dx0, dy0);
+  (void)kind;
   const int w = job.w, h = job.h;
   const int step = 1 << job.subShift;
 
@@ -121,13 +123,69 @@ me_sad_u8_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_
     for (int j = 0; j < words; j++) {
       const uint32_t c = cw[cbase + j];                                // broadcast
       const uint32_t na = rw[ra + j + 1], nb = rw[rb + j + 1];
-      accA = __vsadu4(c, __byte_perm(pa, na, sel)) + accA;
-      accB = __vsadu4(c, __byte_perm(pb, nb, sel)) + accB;
+      accA = me_sad4(c, __byte_perm(pa, na, sel), accA);
+      accB = me_sad4(c, __byte_perm(pb, nb, sel), accB);
       pa = na; pb = nb;
     }
   }
   out[job.outOff + (long long)dyA * cols + dx] = accA << job.subShift;               // bitDepth 8: no final shift
   if (hasB) out[job.outOff + (long long)dyB * cols + dx] = accB << job.subShift;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiles M and E (me_core.cuh): lanes along dy.  All lanes of a warp share dx, hence the byte / half-word alignment of their
+// reference words: an aligned word is one conflict-free shared-memory load (row pitch odd) + one PRMT / SHF, and it serves the eight
+// candidates dx, dx + 4, ... (dx + 2, ... for 16-bit samples) of the thread as they slide along the row.  Per four 8-bit samples and
+// candidate: 1 VABSDIFF4.U8.ACC + 3/8 of a load / permute instead of 3.5 instructions; per two 16-bit samples: VIMNMX.S16x2 + two
+// packed additions (sum c + sum r - 2 sum min) instead of 7.  Results leave through shared memory as 128-byte rows of the surface.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool U8>
+__global__ void __launch_bounds__(256)
+me_sad_dy_kernel(const MePlanes mp, const MeJob* __restrict__ jobs, const int32_t* __restrict__ tileJob, const int32_t* __restrict__ tileIdx,
+                 uint32_t* __restrict__ out) {
+  constexpr int P = U8 ? kMeDyPitch8 : kMeDyPitch16, SPW = U8 ? 4 : 2;
+  __shared__ __align__(16) uint32_t sCur[64 * 64 / SPW];
+  __shared__ __align__(16) uint32_t sRef[kMeDyRows * P];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const MeJob job = jobs[tileJob[blockIdx.x]];
+  const int cols = job.right - job.left + 1, rows = job.bottom - job.top + 1;
+  int kind, x0, y0;
+  me_tile_unpack(tileIdx[blockIdx.x], kind, x0, y0);
+  const int w = job.w, h = job.h, step = 1 << job.subShift;
+  const MeDyTile tl = me_dy_tile(kind, x0, y0, w, h, cols, rows);
+
+  me_dy_stage_cur<U8>(warp, lane, mp.cur + job.curOff, mp.curStride, w, h, step, sCur);
+  const int refStride = mp.refStride[job.refSlot];
+  me_dy_stage_ref<U8>(warp, lane, mp.ref[job.refSlot] + job.refOff + (long long)(job.top + y0) * refStride + (job.left + x0), refStride, tl.winW, tl.winH, sRef);
+  __syncthreads();
+
+  const MeDyWarp q = me_dy_warp<U8>(kind, warp, tl.cr);
+  const int lam = 32 * q.blk + lane;
+  const bool work = q.active && 32 * q.blk < tl.nLam;                  // warp uniform
+  const int shiftOut = U8 ? 0 : mp.bitDepth - 8;
+  if (kind == kMeKindM) {
+    uint32_t sad[kMeDyK];
+    if (work) {
+      if (U8) me_dy_sad_u8<kMeDyK>(sCur, sRef, w >> 2, h, step, lam, q.wbase, q.s, sad);
+      else me_dy_sad_s16<kMeDyK>(sCur, sRef, w >> 1, h, step, lam, q.wbase, q.s, me_fold_rows(mp.bitDepth, w >> 1), sad);
+    }
+    __syncthreads();                                                   // the staged window is dead: its space carries the tile out
+    if (work) {
+#pragma unroll
+      for (int k = 0; k < kMeDyK; k++) sRef[lam * 33 + q.delta0 + SPW * k] = (sad[k] << job.subShift) >> shiftOut;
+    }
+    __syncthreads();
+    for (int i = tid; i < tl.nLam * 32; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      out[job.outOff + (long long)(y0 + r) * cols + x0 + c] = sRef[r * 33 + c];
+    }
+  } else {
+    if (!work) return;
+    uint32_t sad[1];
+    if (U8) me_dy_sad_u8<1>(sCur, sRef, w >> 2, h, step, lam, q.wbase, q.s, sad);
+    else me_dy_sad_s16<1>(sCur, sRef, w >> 1, h, step, lam, q.wbase, q.s, me_fold_rows(mp.bitDepth, w >> 1), sad);
+    if (lam < tl.nLam) out[job.outOff + (long long)(y0 + lam) * cols + x0 + q.delta0] = (sad[0] << job.subShift) >> shiftOut;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -259,13 +317,23 @@ cudaError_t launch_me_subpel(const MePlanes& mp, const SubpelJob* jobs, int nJob
   return cudaGetLastError();
 }
 
-cudaError_t launch_me_sad(const MePlanes& mp, const MeJob* jobs, int nJobs, const int32_t* tileJob, const int32_t* tileIdx, int nTiles,
+// tile records: [0, nTilesDy) the dy-lane tiles (M, E), [nTilesDy, nTilesDy + nTilesO) the dx-lane tiles (O); the two launches write disjoint candidates
+cudaError_t launch_me_sad(const MePlanes& mp, const MeJob* jobs, int nJobs, const int32_t* tileJob, const int32_t* tileIdx, int nTilesDy, int nTilesO,
                           uint32_t* out, cudaStream_t st, int* launches) {
   (void)nJobs;
-  if (nTiles <= 0) return cudaSuccess;
-  if (mp.curStride == 0) me_sad_kernel<true><<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);     // caller-supplied (possibly signed) source blocks
-  else if (mp.bitDepth == 8) me_sad_u8_kernel<<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
-  else me_sad_kernel<false><<<nTiles, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+  if (nTilesDy > 0) {
+    if (mp.curStride == 0) return cudaErrorInvalidValue;                // dy-lane tiles need the picture-resident (unsigned) source
+    if (mp.bitDepth == 8) me_sad_dy_kernel<true><<<nTilesDy, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+    else me_sad_dy_kernel<false><<<nTilesDy, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+    if (launches) *launches += 1;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (nTilesO <= 0) return cudaSuccess;
+  tileJob += nTilesDy; tileIdx += nTilesDy;
+  if (mp.curStride == 0) me_sad_kernel<true><<<nTilesO, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);     // caller-supplied (possibly signed) source blocks
+  else if (mp.bitDepth == 8) me_sad_u8_kernel<<<nTilesO, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
+  else me_sad_kernel<false><<<nTilesO, 256, 0, st>>>(mp, jobs, tileJob, tileIdx, out);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -165,3 +165,62 @@ def test_fork_aware_enumeration_kernel_code_vs_oracle_walk(emul, oracle):
         full = np.zeros((nctu, 341), np.uint8)
         oracle.oracle_prune_mask(obf.ctypes.data_as(C.c_void_p), W, H, a, a, full.ctypes.data_as(C.c_void_p))
         assert full.sum() > 0 and (W % 64 or H % 64 or full.all())
+
+
+# ---- integer-ME SAD: the dy-lane kernel's tiling, staging and sliding SAD (csrc/me_core.cuh) ---------------------------------
+def _emul_me_surface(emul, oracle, bd, cur, refp, M, x, y, w, h, left, right, top, bottom, sub):
+    import ctypes as C
+    S = refp.shape[1]
+    cols, rows = right - left + 1, bottom - top + 1
+    o = np.ascontiguousarray(cur[y:y + h, x:x + w])
+    base = refp.ctypes.data + 2 * ((y + M) * S + x + M)
+    want = np.zeros((rows, cols), np.uint32)
+    oracle.oracle_sad_surface(bd, P(o, i16p), w, w, h, C.c_void_p(base), S, left, right, top, bottom, sub, P(want, u32p))
+    got = np.full((rows, cols), 0xdeadbeef, np.uint32); hits = np.zeros((rows, cols), np.uint8); counts = (C.c_int * 3)()
+    win = refp.ctypes.data + 2 * ((y + M + top) * S + x + M + left)
+    emul.emul_me_sad_surface(bd, P(o, i16p), w, w, h, C.c_void_p(win), S, cols, rows, sub, P(got, u32p), hits.ctypes.data_as(C.c_void_p), counts)
+    assert (hits == 1).all(), "every candidate is written by exactly one tile"
+    dy_lane = got != 0xffffffff                                     # candidates of the O tiles carry the sentinel
+    assert np.array_equal(got[dy_lane], want[dy_lane]), (bd, w, h, cols, rows, sub)
+    return list(counts), int(dy_lane.sum())
+
+
+@pytest.mark.parametrize("bd", [8, 9, 10])
+def test_me_dy_lane_kernel_code_vs_oracle(emul, oracle, bd):
+    """TComRdCost::xGetSAD* (TComRdCost.cpp:465-962) over whole windows: every PU width HM has (AMP 12 / 24 / 48 included), the +-64
+    window of TEncSearch::xSetSearchRange, windows whose width / height leave every kind of strip, row sub-sampling 0 / 1 / 2"""
+    W, H, M = 192, 128, 80
+    cur = textured_plane(W, H, bd, seed=31, t=1)
+    refp = np.pad(pseudo_recon(textured_plane(W, H, bd, seed=31, t=0), bd), M, mode="edge")
+    cases = [(64, 64, 64, 64, -64, 64, -64, 64, 1),       # the production window: 8 M + 2 E + 4 O tiles
+             (0, 0, 16, 16, -72, 8, -72, 8, 1), (176, 112, 16, 16, -5, 72, -3, 72, 0), (32, 16, 12, 16, -40, 9, -30, 40, 1),
+             (40, 24, 24, 32, -33, 0, 0, 31, 1), (8, 8, 8, 4, -20, 20, -20, 20, 0), (8, 8, 4, 8, -16, 17, -16, 50, 0),
+             (64, 32, 48, 64, -16, 19, -40, 30, 1), (64, 32, 64, 16, -40, -5, -2, 61, 1), (96, 64, 32, 32, -64, 64, -64, 63, 2),
+             (16, 16, 8, 8, -16, 15, -16, 15, 0), (100, 60, 4, 4, -32, 34, -32, 31, 0), (64, 64, 64, 64, 0, 71, 0, 32, 0),
+             (16, 8, 32, 8, -3, 3, -3, 3, 0), (48, 48, 16, 32, -8, 8, -64, 64, 1)]
+    total_dy = 0
+    for x, y, w, h, l, r, t, b, sub in cases:
+        counts, n = _emul_me_surface(emul, oracle, bd, cur, refp, M, x, y, w, h, l, r, t, b, sub)
+        total_dy += n
+        if (r - l + 1, b - t + 1) == (129, 129):
+            assert counts == [4, 8, 2]
+        if r - l + 1 < 32 or b - t + 1 < 32:
+            assert counts[1] == 0 and counts[2] == 0
+    assert total_dy > 50000
+
+
+@pytest.mark.parametrize("bd", [8, 9, 10])
+def test_me_dy_lane_kernel_code_extreme_values(emul, oracle, bd):
+    """source at one end of the sample range, reference at the other (and mixed): the packed 16-bit partial sums of the 9/10-bit path
+    must be folded before they overflow, for the widest PU and the smallest"""
+    W, H, M = 128, 128, 72
+    top = (1 << bd) - 1
+    rng = np.random.default_rng(5)
+    for pattern in range(3):
+        cur = np.full((H, W), top if pattern != 1 else 0, np.int16)
+        ref = np.full((H, W), 0 if pattern != 1 else top, np.int16)
+        if pattern == 2:
+            ref = (rng.integers(0, 2, (H, W)) * top).astype(np.int16)
+        refp = np.pad(ref, M, mode="edge")
+        for x, y, w, h, sub in ((32, 32, 64, 64, 0), (32, 32, 64, 64, 1), (40, 40, 4, 4, 0), (32, 48, 48, 16, 0), (64, 64, 8, 64, 0)):
+            _emul_me_surface(emul, oracle, bd, cur, refp, M, x, y, w, h, -32, 32, -40, 31, sub)
