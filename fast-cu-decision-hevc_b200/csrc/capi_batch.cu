@@ -409,7 +409,7 @@ static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinB
       return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: window leaves the padded reference picture");
     const int cols = d.right - d.left + 1, rows = d.bottom - d.top + 1;
     if (cols > kMeMaxWindow || rows > kMeMaxWindow) return fail(h, CUCD_ERR_INVALID, "cucd_me_sad_surface: window too large");
-    me_enum_tiles(cols, rows, fast, tileRows, [&](int kind, int, int) { if (kind == kMeKindO) nTilesO++; else nTilesDy++; });
+    me_enum_tiles(cols, rows, fast && me_width_is_hm(d.w), tileRows, [&](int kind, int, int) { if (kind == kMeKindO) nTilesO++; else nTilesDy++; });
     total += (long long)cols * rows;
   }
   const long long nTiles = nTilesDy + nTilesO;
@@ -430,11 +430,11 @@ static int me_build_jobs(cucd_handle* h, int nPU, const cucd_me_desc* desc, PinB
     j.refSlot = d.ref_idx; j.w = (int16_t)d.w; j.h = (int16_t)d.h;
     j.left = (int16_t)d.left; j.right = (int16_t)d.right; j.top = (int16_t)d.top; j.bottom = (int16_t)d.bottom;
     // the width-specialised xGetSAD* honour iSubShift, the generic xGetSAD (TComRdCost.cpp:465-491) does not
-    const bool special = d.w == 4 || d.w == 8 || d.w == 12 || d.w == 16 || d.w == 24 || d.w == 32 || d.w == 48 || d.w == 64;
+    const bool special = me_width_is_hm(d.w);
     j.subShift = (int16_t)(special ? d.sub_shift : 0); j.pad = 0;
     j.outOff = off;
     const int cols = d.right - d.left + 1, rows = d.bottom - d.top + 1;
-    me_enum_tiles(cols, rows, fast, tileRows, [&](int kind, int x0, int y0) {
+    me_enum_tiles(cols, rows, fast && special, tileRows, [&](int kind, int x0, int y0) {
       size_t& nt = kind == kMeKindO ? ntO : ntDy;
       tileJob[nt] = i; tileIdx[nt] = me_tile_pack(kind, x0, y0); nt++;
     });

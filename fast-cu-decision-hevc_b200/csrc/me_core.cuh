@@ -27,7 +27,10 @@ CUCD_HD int32_t me_tile_pack(int kind, int x0, int y0) { return (int32_t)((kind 
 CUCD_HD void me_tile_unpack(int32_t t, int& kind, int& x0, int& y0) { kind = (t >> 26) & 3; y0 = (t >> 13) & 0x1fff; x0 = t & 0x1fff; }
 CUCD_HD int me_edge_blocks(int cr) { return 8 / cr < 4 ? 8 / cr : 4; }     // 32-dy blocks of an E tile with cr columns (8 warps)
 
-// emit(kind, x0, y0) for every tile of a cols x rows window; `fast`: the dy-lane kernel may be used (picture-resident source, unsigned samples)
+// the dy-lane kernel unrolls a row by its width: HM's PU widths (TComRdCost.cpp:322-372 has a SAD function for each of them)
+CUCD_HD bool me_width_is_hm(int w) { return w == 4 || w == 8 || w == 12 || w == 16 || w == 24 || w == 32 || w == 48 || w == 64; }
+// emit(kind, x0, y0) for every tile of a cols x rows window; `fast`: the dy-lane kernel may be used (picture-resident source, unsigned
+// samples, one of HM's PU widths)
 template <class F>
 inline void me_enum_tiles(int cols, int rows, bool fast, int tileRowsO, F&& emit) {
   if (!fast || cols < 32 || rows < 32) {
@@ -109,29 +112,39 @@ CUCD_HD uint32_t me_fold2(uint32_t packed, uint32_t acc) {                // acc
 // ---- per-lane work of a dy-lane tile -------------------------------------------------------------------------------------------
 // cw: the PU as words, row y at cw[y * words]; rw: the staged window, row r at rw[r * P]; lam: the lane's candidate row inside the tile.
 // Aligned word m of a window row = staged bytes 4 (wbase + m) + s ...; candidate k compares source word j with aligned word j + k.
+// The row width is a template parameter (HM's PU widths are 4, 8, 12, 16, 24, 32, 48, 64): a run of N source words is fully
+// unrolled - N + K - 1 aligned words in registers, no loop or bounds predicates between the absolute-difference instructions.
+template <int K, int N>
+CUCD_HD void me_dy_run_u8(const uint32_t* cc, const uint32_t* rr, uint32_t s, uint32_t* acc /*K*/) {
+  uint32_t A[N + K - 1];
+  uint32_t prev = rr[0];
+#pragma unroll
+  for (int m = 0; m < N + K - 1; m++) { const uint32_t nx = rr[m + 1]; A[m] = me_prmt_shift(prev, nx, s); prev = nx; }
+#pragma unroll
+  for (int t = 0; t < N; t++) {
+    const uint32_t c = cc[t];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = me_sad4(c, A[t + k], acc[k]);
+  }
+}
+template <int K, int WORDS>
+CUCD_HD void me_dy_rows_u8(const uint32_t* cw, const uint32_t* rw, int h, int step, int lam, int wbase, int s, uint32_t* acc /*K*/) {
+#pragma unroll 1
+  for (int y = 0; y < h; y += step) me_dy_run_u8<K, WORDS>(cw + y * WORDS, rw + (lam + y) * kMeDyPitch8 + wbase, (uint32_t)s, acc);
+}
 template <int K>
 CUCD_HD void me_dy_sad_u8(const uint32_t* cw, const uint32_t* rw, int words, int h, int step, int lam, int wbase, int s, uint32_t* acc /*K*/) {
 #pragma unroll
   for (int k = 0; k < K; k++) acc[k] = 0;
-  for (int y = 0; y < h; y += step) {
-    const uint32_t* rr = rw + (lam + y) * kMeDyPitch8 + wbase;
-    const uint32_t* cc = cw + y * words;
-    for (int jc = 0; jc < words; jc += K) {
-      const int n = words - jc < K ? words - jc : K;
-      uint32_t A[2 * K - 1];
-      uint32_t prev = rr[jc];
-#pragma unroll
-      for (int m = 0; m < 2 * K - 1; m++)
-        if (m < n + K - 1) { const uint32_t nx = rr[jc + m + 1]; A[m] = me_prmt_shift(prev, nx, (uint32_t)s); prev = nx; }
-#pragma unroll
-      for (int t = 0; t < K; t++) {
-        if (t < n) {
-          const uint32_t c = cc[jc + t];
-#pragma unroll
-          for (int k = 0; k < K; k++) acc[k] = me_sad4(c, A[t + k], acc[k]);
-        }
-      }
-    }
+  switch (words) {
+    case 1: me_dy_rows_u8<K, 1>(cw, rw, h, step, lam, wbase, s, acc); break;
+    case 2: me_dy_rows_u8<K, 2>(cw, rw, h, step, lam, wbase, s, acc); break;
+    case 3: me_dy_rows_u8<K, 3>(cw, rw, h, step, lam, wbase, s, acc); break;
+    case 4: me_dy_rows_u8<K, 4>(cw, rw, h, step, lam, wbase, s, acc); break;
+    case 6: me_dy_rows_u8<K, 6>(cw, rw, h, step, lam, wbase, s, acc); break;
+    case 8: me_dy_rows_u8<K, 8>(cw, rw, h, step, lam, wbase, s, acc); break;
+    case 12: me_dy_rows_u8<K, 12>(cw, rw, h, step, lam, wbase, s, acc); break;
+    default: me_dy_rows_u8<K, 16>(cw, rw, h, step, lam, wbase, s, acc); break;
   }
 }
 
@@ -139,37 +152,34 @@ CUCD_HD void me_dy_sad_u8(const uint32_t* cw, const uint32_t* rw, int words, int
 // accumulated per 16-bit half in packed words (one IADD per word, two fused into an IADD3) and folded into 32-bit totals every
 // foldRows rows, before a half can exceed 65535: foldRows * pairs * (2^bitDepth - 1) < 65536.
 CUCD_HD int me_fold_rows(int bitDepth, int pairs) { const int f = (1 << (16 - bitDepth)) / pairs; return f < 1 ? 1 : f; }
-template <int K>
-CUCD_HD void me_dy_sad_s16(const uint32_t* cw, const uint32_t* rw, int pairs, int h, int step, int lam, int wbase, int s, int foldRows, uint32_t* sad /*K*/) {
+template <int K, int N>                              // a run of N source words (N even: two words per step, the additions pair up into IADD3)
+CUCD_HD void me_dy_run_s16(const uint32_t* cc, const uint32_t* rr, uint32_t sh, uint32_t& pA, uint32_t* pM /*K*/, uint32_t* pR /*K*/) {
+  uint32_t A[N + K - 1];
+  uint32_t prev = rr[0];
+#pragma unroll
+  for (int m = 0; m < N + K - 1; m++) { const uint32_t nx = rr[m + 1]; A[m] = funnel_r(prev, nx, sh); prev = nx; }
+#pragma unroll
+  for (int t = 0; t < N; t += 2) {
+    const uint32_t c0 = cc[t], c1 = cc[t + 1];
+    pA = pA + c0 + c1;
+#pragma unroll
+    for (int k = 0; k < K; k++) { pM[k] = pM[k] + me_min2(c0, A[t + k]) + me_min2(c1, A[t + 1 + k]); pR[k] = pR[k] + A[t + k] + A[t + 1 + k]; }
+  }
+}
+template <int K, int PAIRS>
+CUCD_HD void me_dy_rows_s16(const uint32_t* cw, const uint32_t* rw, int h, int step, int lam, int wbase, int s, int foldRows, uint32_t* sad /*K*/) {
   uint32_t totM[K], totR[K], pM[K], pR[K], totA = 0, pA = 0;
 #pragma unroll
   for (int k = 0; k < K; k++) { totM[k] = 0; totR[k] = 0; pM[k] = 0; pR[k] = 0; }
   int pend = 0;
+  const uint32_t sh = 16u * (uint32_t)s;
+#pragma unroll 1
   for (int y = 0; y < h; y += step) {
     const uint32_t* rr = rw + (lam + y) * kMeDyPitch16 + wbase;
-    const uint32_t* cc = cw + y * pairs;
-    for (int jc = 0; jc < pairs; jc += K) {
-      const int n = pairs - jc < K ? pairs - jc : K;
-      uint32_t A[2 * K - 1];
-      uint32_t prev = rr[jc];
-#pragma unroll
-      for (int m = 0; m < 2 * K - 1; m++)
-        if (m < n + K - 1) { const uint32_t nx = rr[jc + m + 1]; A[m] = funnel_r(prev, nx, 16u * (uint32_t)s); prev = nx; }
-#pragma unroll
-      for (int t = 0; t < K; t += 2) {                                    // two source words per step: the additions pair up into IADD3
-        if (t + 1 < n) {
-          const uint32_t c0 = cc[jc + t], c1 = cc[jc + t + 1];
-          pA = pA + c0 + c1;
-#pragma unroll
-          for (int k = 0; k < K; k++) { pM[k] = pM[k] + me_min2(c0, A[t + k]) + me_min2(c1, A[t + 1 + k]); pR[k] = pR[k] + A[t + k] + A[t + 1 + k]; }
-        } else if (K == 1 && t < n) {                                     // pairs = w / 2 is even: only the one-candidate tiles step by single words
-          const uint32_t c = cc[jc + t];
-          pA += c;
-#pragma unroll
-          for (int k = 0; k < K; k++) { pM[k] += me_min2(c, A[t + k]); pR[k] += A[t + k]; }
-        }
-      }
-    }
+    const uint32_t* cc = cw + y * PAIRS;
+    constexpr int R0 = PAIRS > 16 ? 16 : PAIRS;      // runs of at most 16 words keep the aligned words in registers
+    me_dy_run_s16<K, R0>(cc, rr, sh, pA, pM, pR);
+    if constexpr (PAIRS > 16) me_dy_run_s16<K, PAIRS - R0>(cc + R0, rr + R0, sh, pA, pM, pR);
     if (++pend == foldRows) {
       pend = 0;
       totA = me_fold2(pA, totA); pA = 0;
@@ -180,6 +190,19 @@ CUCD_HD void me_dy_sad_s16(const uint32_t* cw, const uint32_t* rw, int pairs, in
   totA = me_fold2(pA, totA);
 #pragma unroll
   for (int k = 0; k < K; k++) sad[k] = totA + me_fold2(pR[k], totR[k]) - 2u * me_fold2(pM[k], totM[k]);
+}
+template <int K>
+CUCD_HD void me_dy_sad_s16(const uint32_t* cw, const uint32_t* rw, int pairs, int h, int step, int lam, int wbase, int s, int foldRows, uint32_t* sad /*K*/) {
+  switch (pairs) {
+    case 2: me_dy_rows_s16<K, 2>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+    case 4: me_dy_rows_s16<K, 4>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+    case 6: me_dy_rows_s16<K, 6>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+    case 8: me_dy_rows_s16<K, 8>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+    case 12: me_dy_rows_s16<K, 12>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+    case 16: me_dy_rows_s16<K, 16>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+    case 24: me_dy_rows_s16<K, 24>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+    default: me_dy_rows_s16<K, 32>(cw, rw, h, step, lam, wbase, s, foldRows, sad); break;
+  }
 }
 
 // ---- staging of a dy-lane tile (every thread of the CTA; tid = 32 * warp + lane) ---------------------------------------------------
@@ -202,8 +225,12 @@ CUCD_HD void me_dy_stage_ref(int warp, int lane, const int16_t* ref, long long r
   constexpr int SPW = U8 ? 4 : 2, P = U8 ? kMeDyPitch8 : kMeDyPitch16;
   int wp = (winW + SPW - 1) / SPW + 1;
   if (wp > P) wp = P;
-  for (int r = warp; r < winH; r += 8)
-    for (int q = lane; q < wp; q += 32) {
+  int lg = 0;
+  while ((1 << lg) < wp) lg++;                       // a warp takes 32 >> lg rows at a time (narrow PUs: 2 or 4 rows per pass)
+  const int rpw = lg < 5 ? 32 >> lg : 1, lanesPerRow = lg < 5 ? 1 << lg : 32;
+  const int rs = lane >> (lg < 5 ? lg : 5), q0 = lane & (lanesPerRow - 1);
+  for (int r = warp * rpw + rs; r < winH; r += 8 * rpw)
+    for (int q = q0; q < wp; q += lanesPerRow) {
       const int16_t* p = ref + (long long)r * refStride + q * SPW;
       uint32_t v = 0;
 #pragma unroll
