@@ -243,7 +243,7 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
   __shared__ __align__(16) int16_t sWin[(64 + 9) * kSpWinPitch];
   __shared__ __align__(16) int16_t sHor[(64 + 9) * 64];
   __shared__ __align__(16) int16_t sPred[64 * 64];
-  __shared__ int sSum;
+  __shared__ int sSum[8];
   const int tid = threadIdx.x;
   const SubpelJob job = jobs[blockIdx.x];
   const int w = job.w, h = job.h, bd = mp.bitDepth, head = 14 - bd;
@@ -251,14 +251,16 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
 
   const int16_t* cur = mp.cur + job.curOff;
   const int curStride = mp.curStride ? mp.curStride : w;               // 0: caller-supplied blocks (bi-predictive refinement)
-  for (int i = tid; i < w * h; i += 256) { const int y = i / w, x = i - y * w; sCur[i] = cur[(size_t)y * curStride + x]; }
+  // i / w and i / (w + 9) as one IMAD.HI: exact for i * d < 2^32 (i < 6000, d <= 73)
+  const uint32_t invW = 0xffffffffu / (uint32_t)w + 1u, invW9 = 0xffffffffu / (uint32_t)(w + 9) + 1u;
+  for (int i = tid; i < w * h; i += 256) { const int y = (int)__umulhi((uint32_t)i, invW), x = i - y * w; sCur[i] = cur[(size_t)y * curStride + x]; }
   const int refStride = mp.refStride[job.refSlot];
   const int16_t* ref = mp.ref[job.refSlot] + job.refOff - 4 * (long long)refStride - 4;       // window origin (-4, -4) from the integer MV position
-  for (int i = tid; i < (h + 9) * (w + 9); i += 256) { const int y = i / (w + 9), x = i - y * (w + 9); sWin[y * kSpWinPitch + x] = ref[(long long)y * refStride + x]; }
+  for (int i = tid; i < (h + 9) * (w + 9); i += 256) { const int y = (int)__umulhi((uint32_t)i, invW9), x = i - y * (w + 9); sWin[y * kSpWinPitch + x] = ref[(long long)y * refStride + x]; }
   __syncthreads();
   // rows of the window -> 14-bit intermediates at horizontal fraction fx (filterHor, isFirst, !isLast)
   for (int i = tid; i < (h + 9) * w; i += 256) {
-    const int r = i / w, c = i - r * w;
+    const int r = (int)__umulhi((uint32_t)i, invW), c = i - r * w;
     const int16_t* s = &sWin[r * kSpWinPitch + c + 4 + ix];
     int v;
     if (fx == 0) v = (s[0] << head) - 8192;
@@ -273,11 +275,17 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
   __syncthreads();
   const bool tile8 = !(w & 7) && !(h & 7);
   const int T = tile8 ? 8 : 4, tilesX = w / T, nTiles = tilesX * (h / T);
-  for (int dy = -3; dy <= 3; dy++) {
-    const int iy = dy >> 2, fy = dy & 3;
-    if (tid == 0) sSum = 0;
-    for (int i = tid; i < w * h; i += 256) {                 // columns (filterVer, !isFirst, isLast)
-      const int r = i / w, c = i - r * w;
+  // Small PUs leave most of the CTA idle (an 8x8 PU is 64 samples, 8 Hadamard lanes): G vertical offsets share one pass of the
+  // column filter / distortion / reduction, so that such a PU takes 2 passes (3 barriers each) instead of 7.
+  const int wh = w * h;
+  const int G = wh >= 256 ? 1 : (256 / wh < 7 ? 256 / wh : 7);
+  for (int dyBase = -3; dyBase <= 3; dyBase += G) {
+    const int nG = 4 - dyBase < G ? 4 - dyBase : G;
+    if (tid < nG) sSum[tid] = 0;
+    for (int i = tid; i < nG * wh; i += 256) {               // columns (filterVer, !isFirst, isLast)
+      const int g = G == 1 ? 0 : i / wh, rem = i - g * wh;
+      const int r = (int)__umulhi((uint32_t)rem, invW), c = rem - r * w;
+      const int dy = dyBase + g, iy = dy >> 2, fy = dy & 3;
       const int16_t* s = &sHor[(r + 4 + iy) * w + c];
       int v;
       if (fy == 0) v = (s[0] + 8192 + (1 << (head - 1))) >> head;
@@ -290,22 +298,35 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
       sPred[i] = (int16_t)min(max(v, 0), (1 << bd) - 1);
     }
     __syncthreads();
-    int part = 0;
-    if (job.useHadamard) {
-      const int nTasks = nTiles * T;                          // T lanes per tile; whole warps iterate so that every lane joins the shuffles
-      for (int base = (tid & ~31); base < nTasks; base += 256) {
-        const int task = base + (tid & 31), tile = task / T;
-        if (tile8) part += hadamard_tile_rows<8>(sCur, sPred, w, tile, tilesX, task < nTasks, tid & 31);
-        else part += hadamard_tile_rows<4>(sCur, sPred, w, tile, tilesX, task < nTasks, tid & 31);
+    if (G == 1) {
+      int part = 0;
+      if (job.useHadamard) {
+        const int nTasks = nTiles * T;                        // T lanes per tile; whole warps iterate so that every lane joins the shuffles
+        for (int base = (tid & ~31); base < nTasks; base += 256) {
+          const int task = base + (tid & 31), tile = task / T;
+          if (tile8) part += hadamard_tile_rows<8>(sCur, sPred, w, tile, tilesX, task < nTasks, tid & 31);
+          else part += hadamard_tile_rows<4>(sCur, sPred, w, tile, tilesX, task < nTasks, tid & 31);
+        }
+      } else {
+        for (int i = tid; i < wh; i += 256) part += abs(sCur[i] - sPred[i]);
+      }
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+      if ((tid & 31) == 0 && part) atomicAdd(&sSum[0], part);
+    } else if (job.useHadamard) {                             // nG * nTiles * T <= 256 tasks: one pass, the tile's first lane adds to its offset's sum
+      const int perG = nTiles * T, nTasks = nG * perG;
+      if ((tid & ~31) < nTasks) {
+        const int g = tid / perG, local = tid - g * perG, tile = local / T;
+        const bool ok = tid < nTasks;
+        const int16_t* pg = sPred + (ok ? g : 0) * wh;
+        const int part = tile8 ? hadamard_tile_rows<8>(sCur, pg, w, tile, tilesX, ok, tid & 31) : hadamard_tile_rows<4>(sCur, pg, w, tile, tilesX, ok, tid & 31);
+        if (ok && part) atomicAdd(&sSum[g], part);
       }
     } else {
-      for (int i = tid; i < w * h; i += 256) part += abs(sCur[i] - sPred[i]);
+      for (int i = tid; i < nG * wh; i += 256) { const int g = i / wh; const int d = abs(sCur[i - g * wh] - sPred[i]); if (d) atomicAdd(&sSum[g], d); }
     }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-    if ((tid & 31) == 0 && part) atomicAdd(&sSum, part);
     __syncthreads();
-    if (tid == 0) out[(size_t)blockIdx.x * 49 + (dy + 3) * 7 + dx + 3] = (uint32_t)sSum >> (bd - 8);
+    if (tid < nG) out[(size_t)blockIdx.x * 49 + (dyBase + tid + 3) * 7 + dx + 3] = (uint32_t)sSum[tid] >> (bd - 8);
     __syncthreads();
   }
 }
