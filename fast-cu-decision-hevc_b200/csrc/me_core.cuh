@@ -240,4 +240,127 @@ CUCD_HD void me_dy_stage_ref(int warp, int lane, const int16_t* ref, long long r
     }
 }
 
+// =============================================================================================================================
+// Fractional-pel refinement of small PUs (w * h <= 256): ONE CTA per PU evaluates all 49 quarter-pel positions.
+// me_subpel_kernel gives a CTA one PU and one horizontal offset; for an 8x8 PU that is 64 samples and 8 Hadamard lanes per pass of a
+// 256-thread CTA, and every pass still costs all eight warps their loop and barrier overhead.  Here the seven horizontally filtered
+// planes of the PU are built together (7 (h + 9) w intermediates), and the column filter, the distortion and the sums run over
+// GROUPS of positions (as many as fit 4096 predicted samples: all 49 for an 8x8 PU, 16 for a 16x16 PU), one thread per sample /
+// per Hadamard tile.  Same arithmetic as me_subpel_kernel (TComInterpolationFilter.cpp:57-290, TComRdCost.cpp:1343-1534); the
+// Hadamard is satd8x8_packed / satd4x4_packed of rmd_core.cuh on the packed residual (picture-resident sources only: samples in
+// [0, 2^bitDepth), so that the packed halves stay inside int16 - caller-supplied key blocks keep me_subpel_kernel).
+// =============================================================================================================================
+constexpr int kSpSmallWinCap = 1024;      // (h + 9) x (w + 10) int16, max 73 x 14 (4 x 64 PU)
+constexpr int kSpHorCap = 73 * 64;        // seven planes of (h + 9) x w intermediates must fit this
+constexpr int kSpPredCap = 4096;
+CUCD_HD bool subpel_is_small(int w, int h) { return w * h <= 256 && 7 * (h + 9) * w <= kSpHorCap; }
+CUCD_HD uint32_t me_inv(uint32_t d) { return 0xffffffffu / d + 1u; }                     // n / d == mulhi(n, me_inv(d)) while n * d < 2^32
+CUCD_HD uint32_t me_mulhi(uint32_t n, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(n, m);
+#else
+  return (uint32_t)(((uint64_t)n * m) >> 32);
+#endif
+}
+CUCD_HD uint32_t me_ld_pair(const int16_t* p) {                                        // two int16 at an even index as one word
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const uint32_t*>(p);
+#else
+  return (uint32_t)(uint16_t)p[0] | ((uint32_t)(uint16_t)p[1] << 16);
+#endif
+}
+// sum s[(k - 3) * stride] * lumaFilter[frac][k], frac = 1..3 (TComInterpolationFilter.cpp:57-63)
+CUCD_HD int luma_filter8(const int16_t* s, int stride, int frac) {
+  const int a = s[-3 * stride], b = s[-2 * stride], c = s[-stride], d = s[0], e = s[stride], f = s[2 * stride], g = s[3 * stride], h = s[4 * stride];
+  if (frac == 1) return -a + 4 * b - 10 * c + 58 * d + 17 * e - 5 * f + g;
+  if (frac == 2) return -a + 4 * b - 11 * c + 40 * d + 40 * e - 11 * f + 4 * g - h;
+  return b - 5 * c + 17 * d + 58 * e - 10 * f + 4 * g - h;
+}
+struct SubpelGeo {
+  int w, h, bd, head, wh, plane /* (h + 9) * w */, pitch /* w + 10 */;
+  uint32_t invW, invWh, invPlane, invPitch;
+};
+CUCD_HD SubpelGeo subpel_geo(int w, int h, int bd) {
+  SubpelGeo g;
+  g.w = w; g.h = h; g.bd = bd; g.head = 14 - bd; g.wh = w * h; g.plane = (h + 9) * w; g.pitch = w + 10;
+  g.invW = me_inv((uint32_t)w); g.invWh = me_inv((uint32_t)g.wh); g.invPlane = me_inv((uint32_t)g.plane); g.invPitch = me_inv((uint32_t)(w + 9));
+  return g;
+}
+// source block and the (w + 9) x (h + 9) window whose origin is (-4, -4) from the integer MV position
+CUCD_HD void subpel_small_stage(int tid, const SubpelGeo& g, const int16_t* cur, int curStride, const int16_t* refWin, long long refStride, int16_t* sCur, int16_t* sWin) {
+  for (int i = tid; i < g.wh; i += 256) { const int y = (int)me_mulhi((uint32_t)i, g.invW), x = i - y * g.w; sCur[i] = cur[(size_t)y * curStride + x]; }
+  for (int i = tid; i < (g.h + 9) * (g.w + 9); i += 256) {
+    const int y = (int)me_mulhi((uint32_t)i, g.invPitch), x = i - y * (g.w + 9);
+    sWin[y * g.pitch + x] = refWin[(long long)y * refStride + x];
+  }
+}
+// rows -> 14-bit intermediates for the seven horizontal offsets dx = -3..3 (filterHor, isFirst, !isLast): sHor[dxi][r][c]
+CUCD_HD void subpel_small_hor(int tid, const SubpelGeo& g, const int16_t* sWin, int16_t* sHor) {
+  for (int i = tid; i < 7 * g.plane; i += 256) {
+    const int dxi = (int)me_mulhi((uint32_t)i, g.invPlane), rem = i - dxi * g.plane;
+    const int r = (int)me_mulhi((uint32_t)rem, g.invW), c = rem - r * g.w;
+    const int dx = dxi - 3, ix = dx >> 2, fx = dx & 3;
+    const int16_t* s = &sWin[r * g.pitch + c + 4 + ix];
+    const int v = fx == 0 ? (s[0] << g.head) - 8192 : (luma_filter8(s, 1, fx) - (8192 << (6 - g.head))) >> (6 - g.head);
+    sHor[i] = (int16_t)v;
+  }
+}
+// columns (filterVer, !isFirst, isLast) for the positions pBase .. pBase + nP - 1 (position p = (dy + 3) * 7 + dx + 3): sPred[pl][r][c]
+CUCD_HD void subpel_small_ver(int tid, const SubpelGeo& g, int pBase, int nP, const int16_t* sHor, int16_t* sPred) {
+  const uint32_t inv7 = me_inv(7u);
+  for (int i = tid; i < nP * g.wh; i += 256) {
+    const int pl = (int)me_mulhi((uint32_t)i, g.invWh), rem = i - pl * g.wh;
+    const int r = (int)me_mulhi((uint32_t)rem, g.invW), c = rem - r * g.w;
+    const int p = pBase + pl, dyi = (int)me_mulhi((uint32_t)p, inv7), dxi = p - 7 * dyi;
+    const int dy = dyi - 3, iy = dy >> 2, fy = dy & 3;
+    const int16_t* s = &sHor[dxi * g.plane + (r + 4 + iy) * g.w + c];
+    int v = fy == 0 ? (s[0] + 8192 + (1 << (g.head - 1))) >> g.head : (luma_filter8(s, g.w, fy) + (1 << (5 + g.head)) + (8192 << 6)) >> (6 + g.head);
+    v = v < 0 ? 0 : (v > (1 << g.bd) - 1 ? (1 << g.bd) - 1 : v);
+    sPred[i] = (int16_t)v;
+  }
+}
+CUCD_HD void me_smem_add(int* where, int what) {       // shared-memory atomic in the kernel, a plain addition in the CPU replay
+#if defined(__CUDA_ARCH__)
+  atomicAdd(where, what);
+#else
+  *where += what;
+#endif
+}
+// distortion of the nP predicted blocks: xGetHADs (8x8 tiles when both sizes are multiples of 8, else 4x4) or xGetSAD, one thread per
+// tile / per sample
+CUCD_HD void subpel_small_dist(int tid, const SubpelGeo& g, int nP, int useHadamard, const int16_t* sCur, const int16_t* sPred, int* sSum) {
+  if (useHadamard) {
+    const bool tile8 = !(g.w & 7) && !(g.h & 7);
+    const int T = tile8 ? 8 : 4, tilesX = g.w / T, nTiles = tilesX * (g.h / T);
+    for (int task = tid; task < nP * nTiles; task += 256) {
+      const int pl = task / nTiles, tile = task - pl * nTiles, ty = tile / tilesX, tx = tile - ty * tilesX;
+      const int16_t* a = sCur + ty * T * g.w + tx * T;
+      const int16_t* b = sPred + pl * g.wh + ty * T * g.w + tx * T;
+      uint32_t cost;
+      if (tile8) {
+        uint32_t d[32];
+#pragma unroll
+        for (int y = 0; y < 8; y++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) d[y * 4 + j] = me_ld_pair(a + y * g.w + 2 * j) - me_ld_pair(b + y * g.w + 2 * j);
+        cost = satd8x8_packed(d);
+      } else {
+        uint32_t d[8];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) d[y * 2 + j] = me_ld_pair(a + y * g.w + 2 * j) - me_ld_pair(b + y * g.w + 2 * j);
+        cost = satd4x4_packed(d);
+      }
+      me_smem_add(&sSum[pl], (int)cost);
+    }
+  } else {
+    for (int i = tid; i < nP * g.wh; i += 256) {
+      const int pl = (int)me_mulhi((uint32_t)i, g.invWh);
+      const int d = iabs32((int)sCur[i - pl * g.wh] - (int)sPred[i]);
+      if (d) me_smem_add(&sSum[pl], d);
+    }
+  }
+}
+
 }  // namespace cucd

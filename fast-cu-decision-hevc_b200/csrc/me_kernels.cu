@@ -247,6 +247,7 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
   const int tid = threadIdx.x;
   const SubpelJob job = jobs[blockIdx.x];
   const int w = job.w, h = job.h, bd = mp.bitDepth, head = 14 - bd;
+  if (mp.curStride != 0 && subpel_is_small(w, h)) return;            // me_subpel_small_kernel's PU (block uniform)
   const int dx = (int)blockIdx.y - 3, ix = dx >> 2, fx = dx & 3;
 
   const int16_t* cur = mp.cur + job.curOff;
@@ -331,9 +332,42 @@ me_subpel_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t
   }
 }
 
+// Small PUs (me_core.cuh, subpel_is_small): one CTA per PU, all 49 positions; the phases are the host/device functions the CPU replay runs.
+__global__ void __launch_bounds__(256)
+me_subpel_small_kernel(const MePlanes mp, const SubpelJob* __restrict__ jobs, uint32_t* __restrict__ out) {
+  __shared__ __align__(16) int16_t sCur[256];
+  __shared__ __align__(16) int16_t sWin[kSpSmallWinCap];
+  __shared__ __align__(16) int16_t sHor[kSpHorCap];
+  __shared__ __align__(16) int16_t sPred[kSpPredCap];
+  __shared__ int sSum[64];
+  const int tid = threadIdx.x;
+  const SubpelJob job = jobs[blockIdx.x];
+  if (!subpel_is_small(job.w, job.h)) return;                         // me_subpel_kernel's PU (block uniform)
+  const SubpelGeo g = subpel_geo(job.w, job.h, mp.bitDepth);
+  const int refStride = mp.refStride[job.refSlot];
+  subpel_small_stage(tid, g, mp.cur + job.curOff, mp.curStride, mp.ref[job.refSlot] + job.refOff - 4 * (long long)refStride - 4, refStride, sCur, sWin);
+  __syncthreads();
+  subpel_small_hor(tid, g, sWin, sHor);
+  __syncthreads();
+  const int perGroup = kSpPredCap / g.wh < 49 ? kSpPredCap / g.wh : 49;
+  for (int pBase = 0; pBase < 49; pBase += perGroup) {
+    const int nP = 49 - pBase < perGroup ? 49 - pBase : perGroup;
+    if (tid < nP) sSum[tid] = 0;
+    subpel_small_ver(tid, g, pBase, nP, sHor, sPred);
+    __syncthreads();
+    subpel_small_dist(tid, g, nP, job.useHadamard, sCur, sPred, sSum);
+    __syncthreads();
+    if (tid < nP) out[(size_t)blockIdx.x * 49 + pBase + tid] = (uint32_t)sSum[tid] >> (mp.bitDepth - 8);
+  }
+}
+
 cudaError_t launch_me_subpel(const MePlanes& mp, const SubpelJob* jobs, int nJobs, uint32_t* out, cudaStream_t st, int* launches) {
   if (nJobs <= 0) return cudaSuccess;
   me_subpel_kernel<<<dim3(nJobs, 7), 256, 0, st>>>(mp, jobs, out);
+  if (launches) *launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || mp.curStride == 0) return e;                // caller-supplied key blocks: every PU stays with me_subpel_kernel
+  me_subpel_small_kernel<<<nJobs, 256, 0, st>>>(mp, jobs, out);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

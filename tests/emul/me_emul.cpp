@@ -76,3 +76,22 @@ void emul_me_sad_surface(int bitDepth, const int16_t* cur, int curStride, int w,
 }
 
 }  // extern "C"
+
+// ---- fractional-pel refinement of a small PU: the phases of me_subpel_small_kernel, every phase for all 256 thread ids ----------
+extern "C" int emul_subpel_small(int bitDepth, const int16_t* cur, int curStride, int w, int h, const int16_t* refAtIntMv, int refStride,
+                                 int useHadamard, uint32_t* out /*49*/) {
+  if (!subpel_is_small(w, h)) return 0;
+  std::vector<int16_t> sCur(256, 0x5a5a), sWin(kSpSmallWinCap, 0x5a5a), sHor(kSpHorCap, 0x5a5a), sPred(kSpPredCap, 0x5a5a);
+  int sSum[64];
+  const SubpelGeo g = subpel_geo(w, h, bitDepth);
+  for (int tid = 0; tid < 256; tid++) subpel_small_stage(tid, g, cur, curStride, refAtIntMv - 4 * (long long)refStride - 4, refStride, sCur.data(), sWin.data());
+  for (int tid = 0; tid < 256; tid++) subpel_small_hor(tid, g, sWin.data(), sHor.data());
+  const int perGroup = kSpPredCap / g.wh < 49 ? kSpPredCap / g.wh : 49;
+  for (int pBase = 0; pBase < 49; pBase += perGroup) {
+    const int nP = 49 - pBase < perGroup ? 49 - pBase : perGroup;
+    for (int tid = 0; tid < 256; tid++) { if (tid < nP) sSum[tid] = 0; subpel_small_ver(tid, g, pBase, nP, sHor.data(), sPred.data()); }
+    for (int tid = 0; tid < 256; tid++) subpel_small_dist(tid, g, nP, useHadamard, sCur.data(), sPred.data(), sSum);
+    for (int tid = 0; tid < nP; tid++) out[pBase + tid] = (uint32_t)sSum[tid] >> (bitDepth - 8);
+  }
+  return 1;
+}

@@ -224,3 +224,37 @@ def test_me_dy_lane_kernel_code_extreme_values(emul, oracle, bd):
         refp = np.pad(ref, M, mode="edge")
         for x, y, w, h, sub in ((32, 32, 64, 64, 0), (32, 32, 64, 64, 1), (40, 40, 4, 4, 0), (32, 48, 48, 16, 0), (64, 64, 8, 64, 0)):
             _emul_me_surface(emul, oracle, bd, cur, refp, M, x, y, w, h, -32, 32, -40, 31, sub)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_subpel_small_pu_kernel_code_vs_oracle(emul, oracle, bd):
+    """me_subpel_small_kernel (one CTA per PU, all 49 quarter-pel positions; csrc/me_core.cuh) against the oracle's restatement of
+    xPatternSearchFracDIF (TEncSearch.cpp:4340-4376): every PU shape with w * h <= 256 HM has, Hadamard and SAD, textured and
+    extreme content"""
+    import ctypes as C
+    W, H, M = 96, 96, 16
+    top = (1 << bd) - 1
+    rng = np.random.default_rng(8)
+    shapes = [(8, 8), (4, 8), (8, 4), (16, 16), (16, 8), (8, 16), (16, 4), (4, 16), (12, 16), (16, 12), (32, 8), (8, 32), (4, 4)]
+    n_small = 0
+    for content in range(3):
+        if content == 0:
+            cur = textured_plane(W, H, bd, seed=41, t=1); ref = pseudo_recon(textured_plane(W, H, bd, seed=41, t=0), bd)
+        elif content == 1:
+            cur = np.full((H, W), top, np.int16); ref = ((np.indices((H, W)).sum(0) & 1) * top).astype(np.int16)
+        else:
+            cur = (rng.integers(0, 2, (H, W)) * top).astype(np.int16); ref = (rng.integers(0, 2, (H, W)) * top).astype(np.int16)
+        refp = np.pad(ref, M, mode="edge")
+        S = W + 2 * M
+        for k, (w, h) in enumerate(shapes):
+            x, y = 8 + 4 * (k % 5), 12 + 4 * (k % 3)
+            mvx, mvy = (-3 + k) % 7 - 3, (2 * k) % 5 - 2
+            for had in (1, 0):
+                blk = np.ascontiguousarray(cur[y:y + h, x:x + w])
+                zero = C.c_void_p(refp.ctypes.data + 2 * ((y + M) * S + x + M))
+                want = np.zeros(49, np.uint32); got = np.full(49, 0xdeadbeef, np.uint32)
+                oracle.oracle_subpel_surface(bd, P(blk, i16p), w, w, h, zero, S, mvx, mvy, had, P(want, u32p))
+                at_mv = C.c_void_p(refp.ctypes.data + 2 * ((y + M + mvy) * S + x + M + mvx))
+                n_small += emul.emul_subpel_small(bd, P(blk, i16p), w, w, h, at_mv, S, had, P(got, u32p))
+                assert np.array_equal(got, want), (bd, content, w, h, had)
+    assert n_small == 3 * len(shapes) * 2
