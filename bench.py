@@ -99,8 +99,7 @@ def cpu_path_sample(lib, kind, pics, bit_depth, threads, ctus_per_pic_limit=None
     nproc = max(1, min(threads, len(pics)))
     sys.stdout.flush()
     t0 = time.perf_counter()
-    kids = []
-    for k in range(nproc):
+    def spawn(k):
         pid = os.fork()
         if pid == 0:
             try:
@@ -110,16 +109,22 @@ def cpu_path_sample(lib, kind, pics, bit_depth, threads, ctus_per_pic_limit=None
                     _feature_pass(lib, kind, pics[i][0] if feature_rows is None else np.ascontiguousarray(pics[i][0][:feature_rows]), bit_depth)
             finally:
                 os._exit(0)
-        kids.append(pid)
+        return pid
+    kids = [(k, spawn(k)) for k in range(nproc)]
     for org, rec in pics:
         if kind == "reference":
             lib.hmref_rmd_frame(bit_depth, 1, vp(org), W, vp(rec), W, W, H, 0, n_ctus, threads, vp(out))
         else:
             lib.oracle_rmd_frame(bit_depth, 1, vp(org), W, vp(rec), W, W, H, 0, n_ctus, vp(out))
-    for pid in kids:
+    for k, pid in kids:
         _, status = os.waitpid(pid, 0)
+        for _ in range(2):                 # the reference's feature pass has been seen to die once in a run on the GPU box: run that worker's pictures again
+            if status == 0:
+                break
+            print(f"[bench] CPU feature-pass worker {k} ended with wait status {status}; retrying", file=sys.stderr)
+            _, status = os.waitpid(spawn(k), 0)
         if status != 0:
-            raise RuntimeError("a CPU feature-pass worker failed")
+            raise RuntimeError(f"a CPU feature-pass worker failed (wait status {status})")
     dt = time.perf_counter() - t0
     ctus = n_ctus * len(pics)
     return ctus / dt, dt, ctus
