@@ -189,6 +189,9 @@ int cucd_queue_stats(cucd_queue* q, long long* requests, long long* pus, long lo
  *                       integer mv of a window: out[off_i + (mvy-top)*(right-left+1) + (mvx-left)]
  *                       = xGetSAD*(cur PU, ref + mv) with iSubShift = sub_shift; off_i = sum of the
  *                       previous PUs' window sizes.  The host adds getCost(mv).
+ * Precondition (as HM's own planes satisfy): every sample of the planes given to cucd_set_cur_picture / cucd_set_ref_picture lies
+ * in [0, 2^bit_depth); the kernels keep 8-bit samples as bytes and sum 9/10-bit samples in packed 16-bit halves.  Source blocks
+ * with other values (the bi-predictive search key) go through cucd_me_sad_surface_src / cucd_me_subpel_cost_src below.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   int x, y, w, h;            /* PU position and size in luma samples */
