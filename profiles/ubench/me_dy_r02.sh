@@ -1,7 +1,7 @@
 #!/bin/bash
 # first GPU run of the dy-lane ME SAD kernel: parity of every ME entry point, then the two inter configurations
 O=gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_subpel.py -x -q -m gpu -k "me_ or subpel or bi" > $O/r3a_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r3a_pytest.log
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_subpel.py -x -q -m gpu -k "me_ or subpel or bipred" > $O/r3a_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r3a_pytest.log
 python bench.py --config ldp1080p --no-cpu-baseline --steps 5 --warmup 3 > $O/r3a_ldp.json 2> $O/r3a_ldp.err; echo "ldp rc=$?"
 python bench.py --config ra1080p10 --no-cpu-baseline --steps 3 --warmup 3 > $O/r3a_ra.json 2> $O/r3a_ra.err; echo "ra rc=$?"
 python - <<'P'
